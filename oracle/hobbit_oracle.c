@@ -1,0 +1,542 @@
+/* TEST INFRASTRUCTURE ONLY — see hobbit_oracle.h.  Plain-C restatement of the
+ * reference hot path; pinned against oracle/_ref (the unmodified reference). */
+#include "hobbit_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef orc_F F;
+typedef unsigned __int128 u128;
+#define P61 2305843009213693951ULL
+
+/* ------------------------------------------------------------------ F1 ---
+ * fieldElement.cpp:34-104 (+ - * unary-), :336-360 (myMod, mymult).
+ * Outputs are canonical (limbs in [0,p)) for canonical inputs, so any exact
+ * formula reproduces the reference bits. */
+static inline uint64_t red(u128 x) {           /* x < 2^125 -> [0,p) */
+    uint64_t lo = (uint64_t)x & P61, hi = (uint64_t)(x >> 61);
+    uint64_t s = lo + (hi & P61) + (hi >> 61);
+    s = (s & P61) + (s >> 61);
+    return s >= P61 ? s - P61 : s;
+}
+static inline uint64_t addm(uint64_t a, uint64_t b) { uint64_t s = a + b; return s >= P61 ? s - P61 : s; }
+static inline uint64_t subm(uint64_t a, uint64_t b) { return a >= b ? a - b : a + P61 - b; }
+static inline uint64_t mulm(uint64_t a, uint64_t b) { return red((u128)a * b); }
+
+static inline F f_add(F a, F b) { F r = { addm(a.re, b.re), addm(a.im, b.im) }; return r; }
+static inline F f_sub(F a, F b) { F r = { subm(a.re, b.re), subm(a.im, b.im) }; return r; }
+static inline F f_neg(F a) { F z = {0, 0}; return f_sub(z, a); }
+static inline F f_mul(F a, F b) {              /* (a.re + i a.im)(b.re + i b.im), i^2 = -1 */
+    uint64_t ac = mulm(a.re, b.re), bd = mulm(a.im, b.im);
+    uint64_t ad = mulm(a.re, b.im), bc = mulm(a.im, b.re);
+    F r = { subm(ac, bd), addm(ad, bc) };
+    return r;
+}
+static inline int f_eq(F a, F b) { return a.re == b.re && a.im == b.im; }
+static inline F f_int(long long x) { F r = { x >= 0 ? (uint64_t)x : P61 + x, 0 }; return r; } /* fieldElement.cpp:25-28 */
+static const F F0 = {0, 0}, F1 = {1, 0};
+
+/* fieldElement.cpp:206-209, 322-334: inv = x^(p^2-2) by square-and-multiply */
+static F f_inv(F x) {
+    u128 e = (u128)P61 * P61 - 2;
+    F ret = F1, tmp = x;
+    while (e) { if (e & 1) ret = f_mul(ret, tmp); tmp = f_mul(tmp, tmp); e >>= 1; }
+    return ret;
+}
+
+void orc_field_binop(int op, const F *a, const F *b, F *c, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        switch (op) {
+            case 0: c[i] = f_add(a[i], b[i]); break;
+            case 1: c[i] = f_sub(a[i], b[i]); break;
+            case 2: c[i] = f_mul(a[i], b[i]); break;
+            case 3: c[i] = f_neg(a[i]); break;
+            case 4: c[i] = f_inv(a[i]); break;
+        }
+    }
+}
+
+/* utils.cpp:452-463 */
+static F root_of_unity(int n) {
+    F rou = { 2147483648ULL, 1033321771269002680ULL };
+    for (int i = 0; i < 62 - n; i++) rou = f_mul(rou, rou);
+    return rou;
+}
+void orc_root_of_unity(int n, F *out) { *out = root_of_unity(n); }
+
+/* ------------------------------------------------------------------ M1 ---
+ * mimc.cpp:11-19 (constants c_i = F(i), key unused here), :95-107. */
+static F mimc(F input, F k) {
+    F t, h = F0;
+    for (int i = 0; i < 161; i++) {
+        if (i == 0) t = f_add(input, k);
+        else t = f_add(f_add(h, k), f_int(i - 1));
+        h = f_mul(f_mul(t, t), t);
+    }
+    return f_add(h, k);
+}
+void orc_mimc_hash(const F *in, const F *k, F *out) { *out = mimc(*in, *k); }
+
+/* ------------------------------------------------------------------ N1 ---
+ * utils.cpp:605-673 (_fft, flag=false): bit-reverse, twiddles w[k]=rou^k by
+ * repeated multiplication, radix-2 DIT. */
+void orc_fft(F *arr, int logn) {
+    uint32_t len = 1u << logn;
+    F rou = root_of_unity(logn);
+    uint32_t *rev = (uint32_t *)malloc(len * sizeof(uint32_t));
+    rev[0] = 0;
+    for (uint32_t i = 1; i < len; i++) rev[i] = rev[i >> 1] >> 1 | (i & 1) << (logn - 1);
+    for (uint32_t i = 0; i < len; i++) if (rev[i] < i) { F t = arr[i]; arr[i] = arr[rev[i]]; arr[rev[i]] = t; }
+    F *w = (F *)malloc(len * sizeof(F));
+    w[0] = F1; if (len > 1) w[1] = rou;
+    for (uint32_t i = 2; i < len; i++) w[i] = f_mul(w[i - 1], w[1]);
+    for (uint32_t i = 2; i <= len; i <<= 1)
+        for (uint32_t j = 0; j < len; j += i)
+            for (uint32_t k = 0; k < (i >> 1); k++) {
+                F u = arr[j + k], v = f_mul(arr[j + k + (i >> 1)], w[len / i * k]);
+                arr[j + k] = f_add(u, v);
+                arr[j + k + (i >> 1)] = f_sub(u, v);
+            }
+    free(rev); free(w);
+}
+
+/* utils.cpp:873-883: c = random() every 100 elements; x_i = c + F(rand()) */
+void orc_generate_randomness(int n, F *out) {
+    F c = F0;
+    for (int i = 0; i < n; i++) {
+        if (i % 100 == 0) c = f_int(random());
+        out[i] = f_add(c, f_int(rand()));
+    }
+}
+
+/* --------------------------------------------------------------- E1/E2 ---
+ * parameter.h:4-8, expanders.h:20-47,78-92, linear_code_encode.h:62-119. */
+static const double kAlpha = 0.211, kR = 1.72;
+enum { kCn = 9, kDn = 12, kMaxDep = 64 };
+static const int kDistThreshold = (int)(1.0 / 0.07) - 1;      /* 13 */
+typedef struct { long long L, R; int deg; uint32_t *nbr; uint64_t *w; } orc_graph;
+static orc_graph gC[kMaxDep], gD[kMaxDep];
+
+static void gen_graph(orc_graph *g, long long L, long long R, int d) {
+    free(g->nbr); free(g->w);
+    g->L = L; g->R = R; g->deg = d;
+    g->nbr = (uint32_t *)malloc((size_t)L * d * sizeof(uint32_t));
+    g->w = (uint64_t *)malloc((size_t)L * d * sizeof(uint64_t));
+    for (long long i = 0; i < L; i++)
+        for (int j = 0; j < d; j++) {
+            g->nbr[i * d + j] = (uint32_t)(rand() % R);   /* target first ... */
+            g->w[i * d + j] = (uint64_t)random();          /* ... then weight = F(random()) */
+        }
+}
+static long long expander_init(long long n, int dep) {
+    if (n <= kDistThreshold) return n;
+    gen_graph(&gC[dep], n, (long long)(kAlpha * n), kCn);
+    long long L = expander_init((long long)(kAlpha * n), dep + 1);
+    gen_graph(&gD[dep], L, (long long)(n * (kR - 1) - L), kDn);
+    return n + L + (long long)(n * (kR - 1) - L);
+}
+long long orc_expander_init_store(long long n) { return expander_init(n, 0); }
+int orc_expander_levels(long long n) { int d = 0; while (n > kDistThreshold) { n = (long long)(kAlpha * n); d++; } return d; }
+long long orc_expander_dims(int which, int dep, long long *R, int *deg) {
+    orc_graph *g = which ? &gD[dep] : &gC[dep]; *R = g->R; *deg = g->deg; return g->L;
+}
+void orc_expander_dump(int which, int dep, uint32_t *nbr, uint64_t *w) {
+    orc_graph *g = which ? &gD[dep] : &gC[dep];
+    memcpy(nbr, g->nbr, (size_t)g->L * g->deg * sizeof(uint32_t));
+    memcpy(w, g->w, (size_t)g->L * g->deg * sizeof(uint64_t));
+}
+static long long encode_rec(const F *src, F *dst, long long n, int dep) {
+    if (n <= kDistThreshold) { for (long long i = 0; i < n; i++) dst[i] = src[i]; return n; }
+    for (long long i = 0; i < n; i++) dst[i] = src[i];
+    long long R = (long long)(kAlpha * n);
+    F *y = (F *)calloc((size_t)R, sizeof(F));
+    const orc_graph *c = &gC[dep];
+    for (long long i = 0; i < n; i++)
+        for (int d = 0; d < c->deg; d++) {
+            uint32_t t = c->nbr[i * c->deg + d];
+            F wv = { c->w[i * c->deg + d], 0 };
+            y[t] = f_add(y[t], f_mul(wv, src[i]));
+        }
+    long long L = encode_rec(y, dst + n, R, dep + 1);
+    free(y);
+    const orc_graph *g = &gD[dep];
+    R = g->R;
+    for (long long i = 0; i < R; i++) dst[n + L + i] = F0;
+    for (long long i = 0; i < L; i++)
+        for (int d = 0; d < g->deg; d++) {
+            uint32_t t = g->nbr[i * g->deg + d];
+            F wv = { g->w[i * g->deg + d], 0 };
+            dst[n + L + t] = f_add(dst[n + L + t], f_mul(dst[n + i], wv));
+        }
+    return n + L + R;
+}
+int orc_encode_monolithic(const F *src, F *dst, long long n) { return (int)encode_rec(src, dst, n, 0); }
+
+/* ------------------------------------------------------------------ H1 ---
+ * Blake3_hash.cpp:5-10 = BLAKE3 of exactly 64 bytes -> one compression with
+ * cv = IV, counter 0, block_len 64, flags CHUNK_START|CHUNK_END|ROOT
+ * (Blake/blake3_impl.h:18-21; compression per Blake/blake3_portable.c). */
+static const uint32_t B3_IV[8] = { 0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u };
+static const uint8_t B3_PERM[16] = { 2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8 };
+static inline uint32_t rotr32(uint32_t x, int c) { return (x >> c) | (x << (32 - c)); }
+#define B3G(a, b, c, d, x, y) do { \
+    v[a] = v[a] + v[b] + (x); v[d] = rotr32(v[d] ^ v[a], 16); v[c] = v[c] + v[d]; v[b] = rotr32(v[b] ^ v[c], 12); \
+    v[a] = v[a] + v[b] + (y); v[d] = rotr32(v[d] ^ v[a], 8);  v[c] = v[c] + v[d]; v[b] = rotr32(v[b] ^ v[c], 7); } while (0)
+void orc_blake3_hash(const uint8_t *src, uint8_t *dst) {
+    uint32_t m[16], v[16], t[16];
+    memcpy(m, src, 64);                                   /* little-endian host */
+    for (int i = 0; i < 8; i++) v[i] = B3_IV[i];
+    v[8] = B3_IV[0]; v[9] = B3_IV[1]; v[10] = B3_IV[2]; v[11] = B3_IV[3];
+    v[12] = 0; v[13] = 0; v[14] = 64; v[15] = 1 | 2 | 8;
+    for (int r = 0; r < 7; r++) {
+        B3G(0, 4, 8, 12, m[0], m[1]);  B3G(1, 5, 9, 13, m[2], m[3]);
+        B3G(2, 6, 10, 14, m[4], m[5]); B3G(3, 7, 11, 15, m[6], m[7]);
+        B3G(0, 5, 10, 15, m[8], m[9]); B3G(1, 6, 11, 12, m[10], m[11]);
+        B3G(2, 7, 8, 13, m[12], m[13]); B3G(3, 4, 9, 14, m[14], m[15]);
+        for (int i = 0; i < 16; i++) t[i] = m[B3_PERM[i]];
+        memcpy(m, t, sizeof m);
+    }
+    for (int i = 0; i < 8; i++) v[i] ^= v[i + 8];
+    memcpy(dst, v, 32);
+}
+
+/* H2: merkle_tree.cpp:62-87 */
+void orc_md_leaf(const F *xyzw, const uint8_t *prev, uint8_t *out) {
+    uint8_t data[64];
+    memcpy(data, xyzw, 64);
+    orc_blake3_hash(data, data);          /* first 32 bytes <- H1(x|y|z|w) */
+    memcpy(data + 32, prev, 32);
+    orc_blake3_hash(data, out);
+}
+/* H3: merkle_tree.cpp:255-287 — parent = H1(left ‖ LEFT) (the right child is never read) */
+static int create_tree(int n, uint8_t *flat) {          /* flat holds the leaves at offset 0 */
+    int lvls = 1; size_t prev = 0, cur = (size_t)n * 32;
+    for (int sz = n / 2; sz >= 1; sz /= 2) {
+        for (int i = 0; i < sz; i++) {
+            uint8_t data[64];
+            memcpy(data, flat + prev + (size_t)2 * i * 32, 32);
+            memcpy(data + 32, flat + prev + (size_t)2 * i * 32, 32);
+            orc_blake3_hash(data, flat + cur + (size_t)i * 32);
+        }
+        prev = cur; cur += (size_t)sz * 32; lvls++;
+    }
+    return lvls;
+}
+int orc_create_tree_blake(const uint8_t *leaves, int n, uint8_t *out) {
+    memcpy(out, leaves, (size_t)n * 32);
+    return create_tree(n, out);
+}
+/* H4: merkle_tree.cpp:193-221 */
+int orc_mt_commit_blake(const F *leafs, int N, uint8_t *out) {
+    for (int i = 0; i < N / 4; i++) orc_blake3_hash((const uint8_t *)(leafs + 4 * i), out + (size_t)i * 32);
+    return create_tree(N / 4, out);
+}
+
+/* ------------------------------------------------------------------ T1 ---
+ * PC_utils.cpp:66-123 (and its pointer twin :9-64): 2trs x (2n/trs) matrix,
+ * message in the top-left trs x n/trs block, rows NTT'd at length 2n/trs,
+ * then every column either NTT'd at length 2trs (RS) or expander-encoded. */
+static int ilog2(size_t x) { int l = 0; while (x >>= 1) l++; return l; }
+void orc_compute_tensorcode(const F *msg, size_t n, int trs, int lin, F *T) {
+    size_t cols = 2 * n / trs, rows = 2 * (size_t)trs;
+    memset(T, 0, rows * cols * sizeof(F));
+    for (int i = 0; i < trs; i++) memcpy(T + i * cols, msg + (size_t)i * (n / trs), (n / trs) * sizeof(F));
+    for (int i = 0; i < trs; i++) orc_fft(T + i * cols, ilog2(cols));
+    F *buf = (F *)malloc(rows * sizeof(F)), *buf2 = (F *)malloc(rows * sizeof(F));
+    for (size_t c = 0; c < cols; c++) {
+        if (!lin) {
+            for (size_t j = 0; j < rows; j++) buf[j] = j < (size_t)trs ? T[j * cols + c] : F0;
+            orc_fft(buf, ilog2(rows));
+            for (size_t j = 0; j < rows; j++) T[j * cols + c] = buf[j];
+        } else {
+            for (int j = 0; j < trs; j++) buf[j] = T[j * cols + c];
+            memset(buf2, 0, rows * sizeof(F));
+            orc_encode_monolithic(buf, buf2, trs);
+            for (size_t j = 0; j < rows; j++) T[j * cols + c] = buf2[j];
+        }
+    }
+    free(buf); free(buf2);
+}
+
+/* ------------------------------------------------------------------ C1 ---
+ * Our_PC.cpp:146-171 */
+void orc_commit_standard(const F *poly, size_t N, int K, int trs, int lin, uint8_t *levels_out, F *tensor_out) {
+    size_t B = N / K, cols = 2 * B / trs;
+    F *T = tensor_out ? NULL : (F *)malloc(4 * B * sizeof(F));
+    memset(levels_out, 0, B * 32);
+    for (int i = 0; i < K; i++) {
+        F *Ti = tensor_out ? tensor_out + (size_t)i * 4 * B : T;
+        orc_compute_tensorcode(poly + (size_t)i * B, B, trs, lin, Ti);
+        for (int j = 0; j < trs / 2; j++)
+            for (size_t k = 0; k < cols; k++) {
+                F q[4] = { Ti[(4 * j) * cols + k], Ti[(4 * j + 1) * cols + k], Ti[(4 * j + 2) * cols + k], Ti[(4 * j + 3) * cols + k] };
+                uint8_t *leaf = levels_out + (j * cols + k) * 32;
+                orc_md_leaf(q, leaf, leaf);
+            }
+    }
+    free(T);
+    create_tree((int)B, levels_out);
+}
+
+/* witness_stream.cpp:2405-2411: synthetic stream used by test_Elastic_PC */
+void orc_read_stream_pc_test(F *v, size_t n) {
+    F x = f_int(322322);
+    for (size_t i = 0; i < n; i++) { v[i] = x; x = f_add(f_mul(x, x), f_int((long long)i)); }
+}
+/* ------------------------------------------------------------------ C2 ---
+ * Elastic_PC.cpp:174-285 on stream "test".  Chunks i%4 in {0,1,2} are parked;
+ * chunk i%4==3 triggers h[pos] = H2(c0[pos],c1[pos],c2[pos],T[pos], h[pos]);
+ * trailing chunks (K%4 != 0) are never hashed. */
+void orc_elastic_commit(size_t N, size_t B, int trs, int lin, uint8_t *levels_out) {
+    F *buff = (F *)malloc(B * sizeof(F));
+    F *park[3], *T = (F *)malloc(4 * B * sizeof(F));
+    for (int i = 0; i < 3; i++) park[i] = (F *)malloc(4 * B * sizeof(F));
+    memset(levels_out, 0, 4 * B * 32);
+    for (size_t i = 0; i < N / B; i++) {
+        orc_read_stream_pc_test(buff, B);
+        int nz = 0;
+        for (size_t j = 0; j < B; j++) if (!f_eq(buff[j], F0)) { nz = 1; break; }
+        if (nz) orc_compute_tensorcode(buff, B, trs, lin, T); else memset(T, 0, 4 * B * sizeof(F));
+        if (i % 4 != 3) memcpy(park[i % 4], T, 4 * B * sizeof(F));
+        else for (size_t p = 0; p < 4 * B; p++) {
+            /* Elastic_PC.cpp:234-236 passes (c0[counter], c1[counter], c2[counter++], T[j][k]) as
+             * by-value arguments.  GCC evaluates them right to left, so the increment lands BEFORE
+             * c1 and c0 are read: the hashed tuple is (c0[p+1], c1[p+1], c2[p], T[p]).  At the last
+             * position the reference reads one element past both arrays (heap contents: zero when the
+             * blocks are mmap'd, allocator metadata otherwise); we define it as zero.  That leaf is a
+             * right child and, with the left‖left parent rule, influences nothing above it. */
+            F q[4] = { p + 1 < 4 * B ? park[0][p + 1] : F0, p + 1 < 4 * B ? park[1][p + 1] : F0, park[2][p], T[p] };
+            orc_md_leaf(q, levels_out + p * 32, levels_out + p * 32);
+        }
+    }
+    for (int i = 0; i < 3; i++) free(park[i]);
+    free(T); free(buff);
+    create_tree((int)(4 * B), levels_out);
+}
+
+/* ------------------------------------------------------------------ S9 ---
+ * utils.cpp:251-296: eq table; step i uses r[size-1-i] (last variable = LSB) */
+void orc_precompute_beta(const F *r, int nr, F *B) {
+    F *tmp = (F *)malloc(((size_t)1 << nr) * sizeof(F));
+    B[0] = F1;
+    for (int i = 0; i < nr; i++) {
+        memcpy(tmp, B, ((size_t)1 << i) * sizeof(F));
+        for (size_t j = 0; j < ((size_t)1 << i); j++) {
+            F t = f_mul(r[nr - 1 - i], tmp[j]);
+            B[2 * j] = f_sub(tmp[j], t);
+            B[2 * j + 1] = t;
+        }
+    }
+    free(tmp);
+}
+/* utils.cpp:789-802 */
+static F evaluate_vector(const F *vin, size_t n, const F *r) {
+    int nr = ilog2(n);
+    F *v = (F *)malloc(n * sizeof(F)); memcpy(v, vin, n * sizeof(F));
+    for (int i = 0; i < nr; i++) {
+        size_t L = (size_t)1 << (nr - 1 - i);
+        for (size_t j = 0; j < L; j++) v[j] = f_add(f_mul(f_sub(F1, r[i]), v[2 * j]), f_mul(r[i], v[2 * j + 1]));
+    }
+    F e = v[0]; free(v); return e;
+}
+void orc_evaluate_vector(const F *v, size_t n, const F *r, int nr, F *out) { (void)nr; *out = evaluate_vector(v, n, r); }
+
+/* ------------------------------------------------------------------ S1 ---
+ * sumcheck.cpp:2391-2460.  Round poly (a,b,c) of sum_j (d1 t + v1[2j])(d2 t + v2[2j]);
+ * challenge AFTER the polynomial: rand = mimc(mimc(mimc(rand,a),b),c); fold with it. */
+double orc_sumcheck2(const F *_v1, const F *_v2, size_t n, const F *prev_r, F *out) {
+    int rounds = ilog2(n); double ps = 0; size_t k = 0;
+    F *v1 = (F *)malloc(n * sizeof(F)), *v2 = (F *)malloc(n * sizeof(F));
+    memcpy(v1, _v1, n * sizeof(F)); memcpy(v2, _v2, n * sizeof(F));
+    F rand = *prev_r; F *rs = out + 3 * rounds;
+    for (int i = 0; i < rounds; i++) {
+        size_t L = (size_t)1 << (rounds - 1 - i);
+        F a = F0, b = F0, c = F0;
+        for (size_t j = 0; j < L; j++) {
+            F d1 = f_sub(v1[2 * j + 1], v1[2 * j]), d2 = f_sub(v2[2 * j + 1], v2[2 * j]);
+            a = f_add(a, f_mul(d1, d2));
+            b = f_add(b, f_add(f_mul(d1, v2[2 * j]), f_mul(d2, v1[2 * j])));
+            c = f_add(c, f_mul(v1[2 * j], v2[2 * j]));
+        }
+        rand = mimc(rand, a); rand = mimc(rand, b); rand = mimc(rand, c);
+        out[k++] = a; out[k++] = b; out[k++] = c; rs[i] = rand;
+        ps += 3 * 16 / 1024.0;
+        for (size_t j = 0; j < L; j++) {
+            v1[j] = f_add(v1[2 * j], f_mul(rand, f_sub(v1[2 * j + 1], v1[2 * j])));
+            v2[j] = f_add(v2[2 * j], f_mul(rand, f_sub(v2[2 * j + 1], v2[2 * j])));
+        }
+    }
+    rand = mimc(rand, v1[0]); rand = mimc(rand, v2[0]);
+    ps += 2 * 16 / 1024.0;
+    k += rounds; out[k++] = v1[0]; out[k++] = v2[0]; out[k++] = rand;
+    free(v1); free(v2);
+    return ps;
+}
+
+/* cubic coefficients of (d1 t + x1)(d2 t + x2)(d3 t + x3) accumulated into acc[4] = (a,b,c,d) */
+static inline void cubic_acc(F *acc, F x1, F y1, F x2, F y2, F x3, F y3) {
+    F d1 = f_sub(y1, x1), d2 = f_sub(y2, x2), d3 = f_sub(y3, x3);
+    F qa = f_mul(d1, d2), qb = f_add(f_mul(d1, x2), f_mul(d2, x1)), qc = f_mul(x1, x2);
+    acc[0] = f_add(acc[0], f_mul(qa, d3));
+    acc[1] = f_add(acc[1], f_add(f_mul(qa, x3), f_mul(qb, d3)));
+    acc[2] = f_add(acc[2], f_add(f_mul(qb, x3), f_mul(qc, d3)));
+    acc[3] = f_add(acc[3], f_mul(qc, x3));
+}
+/* ------------------------------------------------------------------ S2 ---
+ * sumcheck.cpp:1974-2058.  The fold of round i happens in the same loop as the
+ * polynomial accumulation and uses the INCOMING rand; randomness[0][i] is the
+ * rand before round i; 4 mimc per round afterwards. Tables are destroyed. */
+static double sumcheck3_inplace(F *v1, F *v2, F *v3, size_t n, F prev_r, F *out) {
+    int rounds = ilog2(n); double ps = 0; size_t k = 0;
+    F rand = prev_r; F *rs = out + 4 * rounds;
+    for (int i = 0; i < rounds; i++) {
+        size_t L = (size_t)1 << (rounds - 1 - i);
+        F acc[4] = { F0, F0, F0, F0 };
+        for (size_t j = 0; j < L; j++) {
+            cubic_acc(acc, v1[2 * j], v1[2 * j + 1], v2[2 * j], v2[2 * j + 1], v3[2 * j], v3[2 * j + 1]);
+            v1[j] = f_add(v1[2 * j], f_mul(rand, f_sub(v1[2 * j + 1], v1[2 * j])));
+            v2[j] = f_add(v2[2 * j], f_mul(rand, f_sub(v2[2 * j + 1], v2[2 * j])));
+            v3[j] = f_add(v3[2 * j], f_mul(rand, f_sub(v3[2 * j + 1], v3[2 * j])));
+        }
+        rs[i] = rand;
+        rand = mimc(rand, acc[0]); rand = mimc(rand, acc[1]); rand = mimc(rand, acc[2]); rand = mimc(rand, acc[3]);
+        ps += 5 * 16 / 1024.0;
+        for (int c = 0; c < 4; c++) out[k++] = acc[c];
+    }
+    rand = mimc(rand, v1[0]); rand = mimc(rand, v2[0]);
+    ps += 3 * 16 / 1024.0;
+    k += rounds; out[k++] = v1[0]; out[k++] = v2[0]; out[k++] = v3[0]; out[k++] = rand;
+    return ps;
+}
+double orc_sumcheck3(const F *_v1, const F *_v2, const F *_v3, size_t n, const F *prev_r, F *out) {
+    F *v = (F *)malloc(3 * n * sizeof(F));
+    memcpy(v, _v1, n * sizeof(F)); memcpy(v + n, _v2, n * sizeof(F)); memcpy(v + 2 * n, _v3, n * sizeof(F));
+    double ps = sumcheck3_inplace(v, v + n, v + 2 * n, n, *prev_r, out);
+    free(v); return ps;
+}
+
+/* ------------------------------------------------------------------ S3 ---
+ * sumcheck.cpp:275-372.  rand starts at F(312); exhausted batches continue as
+ * (1-rand)*v[0] with linear factors (-v0 t + v0); vr uses F(-1) as "unset". */
+double orc_batch_sumcheck3(const F *t1, const F *t2, const F *t3, const size_t *sizes, int batches, const F *a, F *out) {
+    size_t tot = 0, Lmax = 0;
+    for (int b = 0; b < batches; b++) { tot += sizes[b]; if (sizes[b] > Lmax) Lmax = sizes[b]; }
+    F *A = (F *)malloc(3 * tot * sizeof(F)), *B = A + tot, *C = A + 2 * tot;
+    memcpy(A, t1, tot * sizeof(F)); memcpy(B, t2, tot * sizeof(F)); memcpy(C, t3, tot * sizeof(F));
+    size_t *off = (size_t *)malloc(batches * sizeof(size_t));
+    for (int b = 0, o = 0; b < batches; b++) { off[b] = o; o += sizes[b]; }
+    int rounds = ilog2(Lmax); double ps = 0; size_t k = 0;
+    F rand = f_int(312), unset = f_int(-1);
+    F *rs = out + 4 * rounds, *vr = out + 5 * rounds;
+    for (int j = 0; j < 3 * batches; j++) vr[j] = unset;
+    for (int i = 0; i < rounds; i++) {
+        F poly[4] = { F0, F0, F0, F0 };
+        for (int j = 0; j < batches; j++) {
+            F *x1 = A + off[j], *x2 = B + off[j], *x3 = C + off[j];
+            int lg = ilog2(sizes[j]) - 1 - i;
+            F p[4] = { F0, F0, F0, F0 };
+            if (lg >= 0) {
+                size_t L = (size_t)1 << lg;
+                for (size_t q = 0; q < L; q++) cubic_acc(p, x1[2 * q], x1[2 * q + 1], x2[2 * q], x2[2 * q + 1], x3[2 * q], x3[2 * q + 1]);
+            } else {
+                if (f_eq(vr[3 * j], unset)) { vr[3 * j] = x1[0]; vr[3 * j + 1] = x2[0]; vr[3 * j + 2] = x3[0]; }
+                /* linear_poly(-v0, v0): value v0 at t=0 and 0 at t=1, i.e. pair (v0, 0) */
+                cubic_acc(p, x1[0], F0, x2[0], F0, x3[0], F0);
+            }
+            for (int c = 0; c < 4; c++) poly[c] = f_add(poly[c], f_mul(a[j], p[c]));
+        }
+        rand = mimc(rand, poly[0]); rand = mimc(rand, poly[1]); rand = mimc(rand, poly[2]); rand = mimc(rand, poly[3]);
+        rs[i] = rand;
+        for (int c = 0; c < 4; c++) out[k++] = poly[c];
+        ps += 4 * 16 / 1024.0;
+        for (int j = 0; j < batches; j++) {
+            F *x1 = A + off[j], *x2 = B + off[j], *x3 = C + off[j];
+            int lg = ilog2(sizes[j]) - 1 - i;
+            if (lg >= 0) {
+                size_t L = (size_t)1 << lg;
+                for (size_t q = 0; q < L; q++) {
+                    x1[q] = f_add(x1[2 * q], f_mul(rand, f_sub(x1[2 * q + 1], x1[2 * q])));
+                    x2[q] = f_add(x2[2 * q], f_mul(rand, f_sub(x2[2 * q + 1], x2[2 * q])));
+                    x3[q] = f_add(x3[2 * q], f_mul(rand, f_sub(x3[2 * q + 1], x3[2 * q])));
+                }
+            } else {
+                F om = f_sub(F1, rand);
+                x1[0] = f_mul(om, x1[0]); x2[0] = f_mul(om, x2[0]); x3[0] = f_mul(om, x3[0]);
+            }
+        }
+    }
+    for (int j = 0; j < batches; j++)
+        if (f_eq(vr[3 * j], unset)) { vr[3 * j] = A[off[j]]; vr[3 * j + 1] = B[off[j]]; vr[3 * j + 2] = C[off[j]]; }
+    ps += (3 * batches - batches) * 16 / 1024.0;
+    free(A); free(off);
+    return ps;
+}
+
+/* ------------------------------------------------------------------ S5 ---
+ * sumcheck.cpp:35-257 (prev_x empty).  Power-of-two inputs only here (the
+ * reference pads with F(1) / zero vectors otherwise). */
+size_t orc_mul_tree(const F *input, int vectors, size_t n, const F *prev_r, F *out, int *nfr_out, double *ps_out) {
+    int depth = ilog2(n); size_t total = (size_t)vectors * n; double ps = 0;
+    F **tr = (F **)malloc(depth * sizeof(F *)), **in1 = (F **)malloc(depth * sizeof(F *)), **in2 = (F **)malloc(depth * sizeof(F *));
+    for (int i = 0; i < depth; i++) {
+        size_t sz = total >> (i + 1);
+        tr[i] = (F *)malloc(sz * sizeof(F)); in1[i] = (F *)malloc(sz * sizeof(F)); in2[i] = (F *)malloc(sz * sizeof(F));
+        const F *src = i ? tr[i - 1] : input;
+        for (size_t j = 0; j < sz; j++) { in1[i][j] = src[2 * j]; in2[i][j] = src[2 * j + 1]; tr[i][j] = f_mul(src[2 * j], src[2 * j + 1]); }
+    }
+    size_t k = 0; F previous_r = *prev_r, sum;
+    int maxr = ilog2(total);
+    F *r = (F *)malloc((maxr + 1) * sizeof(F)); int nr = 0;
+    F *beta = (F *)malloc(total * sizeof(F));
+    F *pbuf = (F *)malloc((5 * (size_t)maxr + 8) * sizeof(F));
+    for (int v = 0; v < vectors; v++) out[k++] = tr[depth - 1][v];
+    size_t hdr = k;                 /* out_eval, final_r, final_eval are filled at the end */
+    size_t pk = 0; F *proofs = (F *)malloc(((size_t)depth * (5 * (size_t)maxr + 8)) * sizeof(F));
+    F out_eval;
+    if (vectors == 1) {
+        previous_r = mimc(previous_r, tr[depth - 1][0]);
+        sum = tr[depth - 1][0]; out_eval = sum;
+        for (int i = depth - 1; i >= 0; i--) {
+            if (nr == 0) {
+                F num = mimc(previous_r, in1[i][0]);
+                previous_r = mimc(num, in2[i][0]);
+                sum = f_add(f_mul(f_sub(F1, previous_r), in1[i][0]), f_mul(previous_r, in2[i][0]));
+                r[nr++] = previous_r;
+            } else {
+                orc_precompute_beta(r, nr, beta);
+                size_t sz = total >> (i + 1); int rounds = ilog2(sz);
+                ps += sumcheck3_inplace(in1[i], in2[i], beta, sz, previous_r, pbuf);
+                memcpy(proofs + pk, pbuf, 4 * rounds * sizeof(F)); pk += 4 * rounds;
+                memcpy(proofs + pk, pbuf + 5 * rounds, 4 * sizeof(F)); pk += 4;
+                previous_r = pbuf[5 * rounds + 3];
+                sum = f_add(f_mul(pbuf[5 * rounds], f_sub(F1, previous_r)), f_mul(pbuf[5 * rounds + 1], previous_r));
+                r[0] = previous_r; memcpy(r + 1, pbuf + 4 * rounds, rounds * sizeof(F)); nr = rounds + 1;
+            }
+        }
+    } else {
+        nr = ilog2(vectors);
+        orc_generate_randomness(nr, r);
+        sum = evaluate_vector(tr[depth - 1], vectors, r); out_eval = sum;
+        previous_r = mimc(r[nr - 1], sum);
+        for (int i = depth - 1; i >= 0; i--) {
+            orc_precompute_beta(r, nr, beta);
+            size_t sz = total >> (i + 1); int rounds = ilog2(sz);
+            ps += sumcheck3_inplace(in1[i], in2[i], beta, sz, previous_r, pbuf);
+            memcpy(proofs + pk, pbuf, 4 * rounds * sizeof(F)); pk += 4 * rounds;
+            memcpy(proofs + pk, pbuf + 5 * rounds, 4 * sizeof(F)); pk += 4;
+            previous_r = pbuf[5 * rounds + 3];
+            sum = f_add(f_mul(pbuf[5 * rounds], f_sub(F1, previous_r)), f_mul(pbuf[5 * rounds + 1], previous_r));
+            r[0] = previous_r; memcpy(r + 1, pbuf + 4 * rounds, rounds * sizeof(F)); nr = rounds + 1;
+        }
+        if (!f_eq(evaluate_vector(input, total, r), sum)) { printf("Error in mul tree final\n"); exit(-1); }
+    }
+    k = hdr; out[k++] = out_eval;
+    for (int i = 0; i < nr; i++) out[k++] = r[i];
+    out[k++] = sum;
+    memcpy(out + k, proofs, pk * sizeof(F)); k += pk;
+    *nfr_out = nr; *ps_out = ps;
+    for (int i = 0; i < depth; i++) { free(tr[i]); free(in1[i]); free(in2[i]); }
+    free(tr); free(in1); free(in2); free(r); free(beta); free(pbuf); free(proofs);
+    return k;
+}

@@ -1,0 +1,63 @@
+/* TEST INFRASTRUCTURE ONLY.
+ * CPU restatement (plain C) of the reference's hot-path algorithms.  It is the
+ * checker for the CUDA path: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg may load it.  The product library
+ * (hobbit_b200/libhobbit_b200.so) never links or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  Every function here is checked bit-for-bit against
+ * the unmodified reference compiled in place (oracle/_ref/libhobbit_ref.so,
+ * built by oracle/Makefile from /root/reference) in tests/test_oracle_vs_ref.py,
+ * and against the committed golden vectors in tests/golden/ (generated from
+ * the reference by tests/golden/make_golden.py).  The reference ships no test
+ * vectors of its own.
+ *
+ * All reference citations are relative to /root/reference/src/.
+ */
+#ifndef HOBBIT_ORACLE_H
+#define HOBBIT_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t re, im; } orc_F;   /* fieldElement.hpp:96-97 */
+
+/* F1/F2 */
+void orc_field_binop(int op, const orc_F *a, const orc_F *b, orc_F *c, size_t n); /* 0 add 1 sub 2 mul 3 neg 4 inv */
+void orc_root_of_unity(int n, orc_F *out);
+void orc_mimc_hash(const orc_F *in, const orc_F *k, orc_F *out);
+/* N1 */
+void orc_fft(orc_F *arr, int logn);
+/* RNG-driven (libc rand()/random(), same call order as the reference) */
+void orc_generate_randomness(int n, orc_F *out);
+/* E1/E2 */
+long long orc_expander_init_store(long long n);
+int  orc_expander_levels(long long n);
+long long orc_expander_dims(int which, int dep, long long *R, int *deg);
+void orc_expander_dump(int which, int dep, uint32_t *nbr, uint64_t *w);
+int  orc_encode_monolithic(const orc_F *src, orc_F *dst, long long n);
+/* H1..H4 */
+void orc_blake3_hash(const uint8_t *src64, uint8_t *dst32);
+void orc_md_leaf(const orc_F *xyzw, const uint8_t *prev, uint8_t *out);
+int  orc_mt_commit_blake(const orc_F *leafs, int N, uint8_t *out);
+int  orc_create_tree_blake(const uint8_t *leaves, int n, uint8_t *out);
+/* T1, C1, C2 */
+void orc_compute_tensorcode(const orc_F *msg, size_t n, int trs, int lin, orc_F *tensor_out);
+void orc_commit_standard(const orc_F *poly, size_t N, int K, int trs, int lin, uint8_t *levels_out, orc_F *tensor_out);
+void orc_read_stream_pc_test(orc_F *out, size_t n);
+void orc_elastic_commit(size_t N, size_t B, int trs, int lin, uint8_t *levels_out);
+/* S9 */
+void orc_precompute_beta(const orc_F *r, int nr, orc_F *out);
+void orc_evaluate_vector(const orc_F *v, size_t n, const orc_F *r, int nr, orc_F *out);
+/* S1/S2/S3/S5 — flat proof layouts identical to oracle/ref_shim.cpp */
+double orc_sumcheck2(const orc_F *v1, const orc_F *v2, size_t n, const orc_F *prev_r, orc_F *out);
+double orc_sumcheck3(const orc_F *v1, const orc_F *v2, const orc_F *v3, size_t n, const orc_F *prev_r, orc_F *out);
+double orc_batch_sumcheck3(const orc_F *t1, const orc_F *t2, const orc_F *t3, const size_t *sizes, int batches,
+                           const orc_F *a, orc_F *out);
+size_t orc_mul_tree(const orc_F *input, int vectors, size_t n, const orc_F *prev_r, orc_F *out, int *nfr_out, double *ps_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

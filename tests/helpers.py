@@ -1,0 +1,224 @@
+"""ctypes loaders for the two CHECKERS (test infrastructure, never the product):
+
+* ``Checker("orc")`` -> oracle/libhobbit_oracle.so  (plain-C restatement, oracle/hobbit_oracle.c)
+* ``Checker("ref")`` -> oracle/_ref/libhobbit_ref.so (the unmodified reference compiled in place
+  by oracle/Makefile; exists wherever it was prebuilt — it travels to the GPU box as a binary).
+
+Both export the same flat functions (prefix ``orc_`` / ``ref_``), so every parity test can be run
+against either.  F arrays are numpy uint64 of shape (n, 2) = (real, img), the reference's 16-byte POD.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P61 = (1 << 61) - 1
+_libc = ctypes.CDLL(None)
+
+
+def srand(seed=1):
+    """glibc rand()/random() share one state; seed 1 == a fresh process."""
+    _libc.srand(ctypes.c_uint(seed))
+
+
+def F(arr):
+    a = np.ascontiguousarray(np.asarray(arr, dtype=np.uint64))
+    return a.reshape(-1, 2)
+
+
+def fzeros(n):
+    return np.zeros((n, 2), dtype=np.uint64)
+
+
+def rand_field(rng, n, full=True):
+    """Canonical random F_{p^2} elements (full-width limbs unless full=False -> small reals)."""
+    if full:
+        return rng.integers(0, P61, size=(n, 2), dtype=np.uint64)
+    out = np.zeros((n, 2), dtype=np.uint64)
+    out[:, 0] = rng.integers(0, 1 << 32, size=n, dtype=np.uint64)
+    return out
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def ref_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhobbit_ref.so"))
+
+
+def ensure_oracle_built():
+    so = os.path.join(ROOT, "oracle", "libhobbit_oracle.so")
+    src = os.path.join(ROOT, "oracle", "hobbit_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class Checker:
+    def __init__(self, kind):
+        self.kind = kind
+        if kind == "orc":
+            self.lib = ctypes.CDLL(ensure_oracle_built())
+            self.pfx = "orc_"
+        elif kind == "ref":
+            self.lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libhobbit_ref.so"))
+            self.pfx = "ref_"
+            self.lib.ref_init()
+        else:
+            raise ValueError(kind)
+
+    def fn(self, name, restype=None):
+        f = getattr(self.lib, self.pfx + name)
+        f.restype = restype
+        return f
+
+    # ---- field ----
+    def binop(self, op, a, b):
+        a, b = F(a), F(b)
+        c = np.empty_like(a)
+        self.fn("field_binop")(op, _p(a), _p(b), _p(c), ctypes.c_size_t(len(a)))
+        return c
+
+    def root_of_unity(self, n):
+        c = fzeros(1)
+        self.fn("root_of_unity")(n, _p(c))
+        return c
+
+    def mimc(self, x, k):
+        x, k, c = F(x), F(k), fzeros(1)
+        self.fn("mimc_hash")(_p(x), _p(k), _p(c))
+        return c
+
+    def fft(self, arr, logn):
+        a = F(arr).copy()
+        self.fn("fft")(_p(a), logn)
+        return a
+
+    def generate_randomness(self, n):
+        c = fzeros(n)
+        self.fn("generate_randomness")(n, _p(c))
+        return c
+
+    # ---- expander ----
+    def expander_init_store(self, n):
+        return self.fn("expander_init_store", ctypes.c_longlong)(ctypes.c_longlong(n))
+
+    def expander_graphs(self, n):
+        """[(which, dep, L, R, deg, nbr[L*deg] u32, w[L*deg] u64)] in generation order is not needed; index by (which,dep)."""
+        out = {}
+        for dep in range(self.fn("expander_levels", ctypes.c_int)(ctypes.c_longlong(n))):
+            for which in (0, 1):
+                R, deg = ctypes.c_longlong(), ctypes.c_int()
+                L = self.fn("expander_dims", ctypes.c_longlong)(which, dep, ctypes.byref(R), ctypes.byref(deg))
+                nbr = np.zeros(L * deg.value, dtype=np.uint32)
+                w = np.zeros(L * deg.value, dtype=np.uint64)
+                self.fn("expander_dump")(which, dep, _p(nbr), _p(w))
+                out[(which, dep)] = (L, R.value, deg.value, nbr, w)
+        return out
+
+    def encode(self, src, n):
+        s = F(src)
+        d = fzeros(2 * n)
+        cw = self.fn("encode_monolithic", ctypes.c_int)(_p(s), _p(d), ctypes.c_longlong(n))
+        return d, cw
+
+    # ---- hashes ----
+    def blake3(self, src64):
+        s = np.ascontiguousarray(src64, dtype=np.uint8)
+        d = np.zeros(32, dtype=np.uint8)
+        self.fn("blake3_hash")(_p(s), _p(d))
+        return d
+
+    def md_leaf(self, xyzw, prev):
+        x, p = F(xyzw), np.ascontiguousarray(prev, dtype=np.uint8)
+        d = np.zeros(32, dtype=np.uint8)
+        self.fn("md_leaf")(_p(x), _p(p), _p(d))
+        return d
+
+    def mt_commit_blake(self, leafs):
+        x = F(leafs)
+        n = len(x) // 4
+        out = np.zeros((2 * n - 1, 32), dtype=np.uint8)
+        self.fn("mt_commit_blake", ctypes.c_int)(_p(x), len(x), _p(out))
+        return out
+
+    def create_tree(self, leaves):
+        lv = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+        n = len(lv)
+        out = np.zeros((2 * n - 1, 32), dtype=np.uint8)
+        self.fn("create_tree_blake", ctypes.c_int)(_p(lv), n, _p(out))
+        return out
+
+    # ---- tensor code / commits ----
+    def tensorcode(self, msg, trs, lin):
+        m = F(msg)
+        out = fzeros(4 * len(m))
+        self.fn("compute_tensorcode")(_p(m), ctypes.c_size_t(len(m)), trs, int(lin), _p(out))
+        return out
+
+    def commit_standard(self, poly, K, trs, lin, want_tensor=False):
+        p = F(poly)
+        N = len(p)
+        B = N // K
+        levels = np.zeros((2 * B - 1, 32), dtype=np.uint8)
+        tensor = fzeros(4 * N) if want_tensor else None
+        self.fn("commit_standard", ctypes.c_double)(_p(p), ctypes.c_size_t(N), K, trs, int(lin), _p(levels),
+                                                    _p(tensor) if want_tensor else None)
+        return levels, tensor
+
+    def read_stream_pc_test(self, n):
+        out = fzeros(n)
+        self.fn("read_stream_pc_test")(_p(out), ctypes.c_size_t(n))
+        return out
+
+    def elastic_commit(self, N, B, trs, lin):
+        levels = np.zeros((8 * B - 1, 32), dtype=np.uint8)
+        self.fn("elastic_commit", ctypes.c_double)(ctypes.c_size_t(N), ctypes.c_size_t(B), trs, int(lin), _p(levels))
+        return levels
+
+    # ---- eq table / MLE ----
+    def precompute_beta(self, r):
+        r = F(r)
+        out = fzeros(1 << len(r))
+        self.fn("precompute_beta")(_p(r), len(r), _p(out))
+        return out
+
+    def evaluate_vector(self, v, r):
+        v, r, out = F(v), F(r), fzeros(1)
+        self.fn("evaluate_vector")(_p(v), ctypes.c_size_t(len(v)), _p(r), len(r), _p(out))
+        return out
+
+    # ---- sumchecks: return (flat proof array, ps) ----
+    def sumcheck2(self, v1, v2, prev_r):
+        v1, v2, r = F(v1), F(v2), F(prev_r)
+        rounds = int(np.log2(len(v1)))
+        out = fzeros(4 * rounds + 3)
+        ps = self.fn("sumcheck2", ctypes.c_double)(_p(v1), _p(v2), ctypes.c_size_t(len(v1)), _p(r), _p(out))
+        return out, ps
+
+    def sumcheck3(self, v1, v2, v3, prev_r):
+        v1, v2, v3, r = F(v1), F(v2), F(v3), F(prev_r)
+        rounds = int(np.log2(len(v1)))
+        out = fzeros(5 * rounds + 4)
+        ps = self.fn("sumcheck3", ctypes.c_double)(_p(v1), _p(v2), _p(v3), ctypes.c_size_t(len(v1)), _p(r), _p(out))
+        return out, ps
+
+    def batch_sumcheck3(self, t1, t2, t3, sizes, a):
+        t1, t2, t3, a = F(t1), F(t2), F(t3), F(a)
+        sz = (ctypes.c_size_t * len(sizes))(*sizes)
+        rounds = int(np.log2(max(sizes)))
+        out = fzeros(5 * rounds + 3 * len(sizes))
+        ps = self.fn("batch_sumcheck3", ctypes.c_double)(_p(t1), _p(t2), _p(t3), sz, len(sizes), _p(a), _p(out))
+        return out, ps
+
+    def mul_tree(self, inp, vectors, prev_r):
+        x, r = F(inp), F(prev_r)
+        n = len(x) // vectors
+        out = fzeros(16 + vectors + 8 * int(np.log2(len(x)) + 2) ** 2)
+        nfr, ps = ctypes.c_int(), ctypes.c_double()
+        k = self.fn("mul_tree", ctypes.c_size_t)(_p(x), vectors, ctypes.c_size_t(n), _p(r), _p(out),
+                                                 ctypes.byref(nfr), ctypes.byref(ps))
+        return out[:k].copy(), nfr.value, ps.value
