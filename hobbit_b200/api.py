@@ -1,0 +1,281 @@
+"""ctypes binding of include/hobbit_b200.h.  F arrays are numpy uint64 of shape (n, 2) == the reference's
+16-byte ``virgo::fieldElement {real, img}``; digests are uint8 arrays of shape (n, 32) == ``_hash``."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_sz = ctypes.c_size_t
+c_vp = ctypes.c_void_p
+
+
+class HobbitError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libhobbit_b200.so")
+
+
+def load_library():
+    """Load the CUDA library.  Fails loudly when it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise HobbitError("%s is missing — run `python -m hobbit_b200.build` (nvcc, sm_100a)" % p)
+        L = ctypes.CDLL(p)
+        L.hb_last_error.restype = ctypes.c_char_p
+        L.hb_launch_count.restype = ctypes.c_uint64
+        L.hb_stream.restype = c_vp
+        L.hb_tensor_device.restype = c_vp
+        L.hb_expander_codeword_len.restype = ctypes.c_longlong
+        _LIB = L
+    return _LIB
+
+
+def _F(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+    return a.reshape(-1, 2)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):          # raw device pointer (e.g. torch tensor .data_ptr())
+        return c_vp(a)
+    return a.ctypes.data_as(c_vp)
+
+
+class Context:
+    """One CUDA device + stream.  Mirrors the reference's globals (tensor_row_size, linear_time, BUFFER_SPACE) as
+    explicit arguments."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = c_vp()
+        rc = self.lib.hb_ctx_create(ctypes.byref(h), int(device))
+        if rc:
+            raise HobbitError("hb_ctx_create failed (rc=%d): no CUDA device / bad ordinal — there is no CPU fallback" % rc)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise HobbitError(self.lib.hb_last_error(self.h).decode())
+
+    # ---- plumbing ----
+    def sync(self):
+        self._ck(self.lib.hb_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.hb_launch_count(self.h))
+
+    def profile(self, on=True):
+        self._ck(self.lib.hb_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self):
+        import json
+        self.lib.hb_profile_report.restype = c_sz
+        n = self.lib.hb_profile_report(self.h, None, c_sz(0))
+        buf = ctypes.create_string_buffer(n + 16)
+        self.lib.hb_profile_report(self.h, buf, c_sz(n + 16))
+        return json.loads(buf.value.decode())
+
+    def stream(self):
+        return int(self.lib.hb_stream(self.h) or 0)
+
+    def pinned(self, shape, dtype):
+        """numpy array backed by page-locked host memory (for e2e timing with real H2D/D2H)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = c_vp()
+        self._ck(self.lib.hb_malloc_pinned(self.h, ctypes.byref(p), c_sz(max(n, 1))))
+        buf = (ctypes.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr
+
+    # ---- field ----
+    def binop(self, op, a, b=None):
+        a = _F(a)
+        b = a if b is None else _F(b)
+        c = np.empty_like(a)
+        self._ck(self.lib.hb_field_binop(self.h, int(op), _ptr(a), _ptr(b), _ptr(c), c_sz(len(a))))
+        return c
+
+    def root_of_unity(self, logn):
+        o = np.zeros((1, 2), dtype=np.uint64)
+        self.lib.hb_root_of_unity(int(logn), _ptr(o))
+        return o
+
+    def mimc(self, x, k):
+        x, k, o = _F(x), _F(k), np.zeros((1, 2), dtype=np.uint64)
+        self.lib.hb_mimc_hash(_ptr(x), _ptr(k), _ptr(o))
+        return o
+
+    # ---- NTT ----
+    def fft(self, arr, logn, batch=1):
+        a = _F(arr).copy()
+        self._ck(self.lib.hb_ntt_batch(self.h, _ptr(a), int(logn), c_sz(batch), c_sz(1 << logn)))
+        return a
+
+    # ---- expander ----
+    def expander_set(self, n, graphs):
+        """graphs: {(which, dep): (L, R, deg, nbr u32[L*deg], w u64[L*deg])} with which 0 = C, 1 = D (reference _C/D)."""
+        levels = len(graphs) // 2
+        LL = ctypes.c_longlong * max(levels, 1)
+        PP = c_vp * max(levels, 1)
+        LC, RC, LD, RD, nC, wC, nD, wD = LL(), LL(), LL(), LL(), PP(), PP(), PP(), PP()
+        keep = []
+        degC, degD = 9, 12
+        for d in range(levels):
+            L, R, deg, nbr, w = graphs[(0, d)]
+            LC[d], RC[d], degC = L, R, deg
+            nbr = np.ascontiguousarray(nbr, dtype=np.uint32); w = np.ascontiguousarray(w, dtype=np.uint64)
+            keep += [nbr, w]; nC[d] = nbr.ctypes.data; wC[d] = w.ctypes.data
+            L, R, deg, nbr, w = graphs[(1, d)]
+            LD[d], RD[d], degD = L, R, deg
+            nbr = np.ascontiguousarray(nbr, dtype=np.uint32); w = np.ascontiguousarray(w, dtype=np.uint64)
+            keep += [nbr, w]; nD[d] = nbr.ctypes.data; wD[d] = w.ctypes.data
+        self._ck(self.lib.hb_expander_set(self.h, ctypes.c_longlong(n), levels, degC, degD, LC, RC, nC, wC, LD, RD, nD, wD))
+        return int(self.lib.hb_expander_codeword_len(self.h))
+
+    def encode(self, src, n, ncols):
+        """src: (n, ncols) row-major messages-as-columns -> (2n, ncols)."""
+        s = _F(src)
+        d = np.zeros((2 * n * ncols, 2), dtype=np.uint64)
+        self._ck(self.lib.hb_encode_batch(self.h, _ptr(s), _ptr(d), ctypes.c_longlong(n), c_sz(ncols)))
+        return d
+
+    # ---- hashes ----
+    def blake3(self, src):
+        s = np.ascontiguousarray(src, dtype=np.uint8).reshape(-1, 64)
+        d = np.zeros((len(s), 32), dtype=np.uint8)
+        self._ck(self.lib.hb_blake3_64(self.h, _ptr(s), _ptr(d), c_sz(len(s))))
+        return d
+
+    def create_tree(self, leaves):
+        lv = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+        n = len(lv)
+        out = np.zeros((2 * n - 1, 32), dtype=np.uint8)
+        out[:n] = lv
+        self._ck(self.lib.hb_merkle_tree(self.h, _ptr(out), c_sz(n)))
+        return out
+
+    def mt_commit_blake(self, leafs):
+        x = _F(leafs)
+        n = len(x) // 4
+        out = np.zeros((2 * n - 1, 32), dtype=np.uint8)
+        self._ck(self.lib.hb_mt_commit(self.h, _ptr(x), c_sz(len(x)), _ptr(out)))
+        return out
+
+    # ---- tensor code / commits ----
+    def tensorcode(self, msg, trs, lin):
+        m = _F(msg)
+        out = np.zeros((4 * len(m), 2), dtype=np.uint64)
+        self._ck(self.lib.hb_tensorcode(self.h, _ptr(m), c_sz(len(m)), int(trs), int(lin), _ptr(out)))
+        return out
+
+    def commit_standard(self, poly, K, trs, lin, want_tensor=False, levels_out=None, N=None):
+        """poly: numpy (N,2) host array, or an int device pointer with N given."""
+        if isinstance(poly, int):
+            p = poly
+        else:
+            p = _F(poly); N = len(p)
+        B = N // K
+        levels = levels_out if levels_out is not None else np.zeros((2 * B - 1, 32), dtype=np.uint8)
+        tensor = np.zeros((4 * N, 2), dtype=np.uint64) if want_tensor else None
+        self._ck(self.lib.hb_commit_standard(self.h, _ptr(p), c_sz(N), int(K), int(trs), int(lin), _ptr(levels), _ptr(tensor)))
+        return levels, tensor
+
+    def tensor_gather(self, col, row, K):
+        col = np.ascontiguousarray(col, dtype=np.uint32); row = np.ascontiguousarray(row, dtype=np.uint32)
+        out = np.zeros((len(col) * K, 2), dtype=np.uint64)
+        self._ck(self.lib.hb_tensor_gather(self.h, _ptr(col), _ptr(row), c_sz(len(col)), _ptr(out)))
+        return out.reshape(len(col), K, 2)
+
+    def aggregate(self, poly, K, beta, N=None):
+        b = _F(beta)
+        if poly is None:
+            p = None
+        else:
+            p = _F(poly); N = len(p)
+        out = np.zeros((N // K, 2), dtype=np.uint64)
+        self._ck(self.lib.hb_aggregate(self.h, _ptr(p), c_sz(N), int(K), _ptr(b), _ptr(out)))
+        return out
+
+    def stream_pc_test(self, n):
+        out = np.zeros((n, 2), dtype=np.uint64)
+        self._ck(self.lib.hb_stream_pc_test(self.h, _ptr(out), c_sz(n)))
+        return out
+
+    def elastic_commit(self, chunks, B, trs, lin):
+        """chunks: iterable of (B,2) arrays (the stream), pushed in order."""
+        self._ck(self.lib.hb_elastic_begin(self.h, c_sz(B), int(trs), int(lin)))
+        for c in chunks:
+            c = _F(c)
+            assert len(c) == B
+            self._ck(self.lib.hb_elastic_push(self.h, _ptr(c)))
+        levels = np.zeros((8 * B - 1, 32), dtype=np.uint8)
+        self._ck(self.lib.hb_elastic_finish(self.h, _ptr(levels)))
+        return levels
+
+    # ---- eq / MLE ----
+    def precompute_beta(self, r):
+        r = _F(r)
+        out = np.zeros((1 << len(r), 2), dtype=np.uint64)
+        self._ck(self.lib.hb_precompute_beta(self.h, _ptr(r), len(r), _ptr(out)))
+        return out
+
+    def evaluate_vector(self, v, r):
+        v, r, out = _F(v), _F(r), np.zeros((1, 2), dtype=np.uint64)
+        self._ck(self.lib.hb_evaluate_vector(self.h, _ptr(v), c_sz(len(v)), _ptr(r), _ptr(out)))
+        return out
+
+    # ---- sumchecks ----
+    def sumcheck2(self, v1, v2, prev_r):
+        v1, v2, r = _F(v1), _F(v2), _F(prev_r)
+        rounds = int(np.log2(len(v1)))
+        out = np.zeros((4 * rounds + 3, 2), dtype=np.uint64)
+        ps = ctypes.c_double(0)
+        self._ck(self.lib.hb_sumcheck2(self.h, _ptr(v1), _ptr(v2), c_sz(len(v1)), _ptr(r), _ptr(out), ctypes.byref(ps)))
+        return out, ps.value
+
+    def sumcheck3(self, v1, v2, v3, prev_r):
+        v1, v2, v3, r = _F(v1), _F(v2), _F(v3), _F(prev_r)
+        rounds = int(np.log2(len(v1)))
+        out = np.zeros((5 * rounds + 4, 2), dtype=np.uint64)
+        ps = ctypes.c_double(0)
+        self._ck(self.lib.hb_sumcheck3(self.h, _ptr(v1), _ptr(v2), _ptr(v3), c_sz(len(v1)), _ptr(r), _ptr(out), ctypes.byref(ps)))
+        return out, ps.value
+
+    def batch_sumcheck3(self, t1, t2, t3, sizes, a):
+        t1, t2, t3, a = _F(t1), _F(t2), _F(t3), _F(a)
+        sz = (c_sz * len(sizes))(*sizes)
+        rounds = int(np.log2(max(sizes)))
+        out = np.zeros((5 * rounds + 3 * len(sizes), 2), dtype=np.uint64)
+        ps = ctypes.c_double(0)
+        self._ck(self.lib.hb_batch_sumcheck3(self.h, _ptr(t1), _ptr(t2), _ptr(t3), sz, len(sizes), _ptr(a), _ptr(out), ctypes.byref(ps)))
+        return out, ps.value
+
+    def mul_tree(self, inp, vectors, prev_r, x_rand=None):
+        x, r = _F(inp), _F(prev_r)
+        n = len(x) // vectors
+        xr = _F(x_rand) if x_rand is not None else np.zeros((1, 2), dtype=np.uint64)
+        out = np.zeros((16 + vectors + 8 * int(np.log2(len(x)) + 2) ** 2, 2), dtype=np.uint64)
+        written, nfr, ps = c_sz(0), ctypes.c_int(0), ctypes.c_double(0)
+        self._ck(self.lib.hb_mul_tree(self.h, _ptr(x), int(vectors), c_sz(n), _ptr(r), _ptr(xr), _ptr(out),
+                                      ctypes.byref(written), ctypes.byref(nfr), ctypes.byref(ps)))
+        return out[: written.value].copy(), nfr.value, ps.value

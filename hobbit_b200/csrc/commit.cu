@@ -1,0 +1,384 @@
+// Context, field primitives and the commitment pipelines (T1, C1, C2) of the C ABI.
+// Reference: compute_tensorcode / _compute_tensorcode (src/PC_utils.cpp:9-123), commit_standard
+// (src/Our_PC.cpp:146-171), Elastic_PC commit (src/Elastic_PC.cpp:174-285).
+//
+// Data layout in HBM: the encoded tensor of chunk i is a dense row-major (2*trs) x (2B/trs) matrix of 16-byte F
+// at tensor + i*4B — the same order the reference's `_tensor[i][row][col]` flattens to.  Leaves/levels are one flat
+// array of 32-byte digests, level after level, leaves first (== the reference's MT_hashes[lvl][i]).
+#include "common.cuh"
+#include <new>
+#include <algorithm>
+
+namespace hb {
+
+// ---- F1 ------------------------------------------------------------------------------------------------
+__device__ F fpow_inv(F x) {                       // x^(p^2-2), fieldElement.cpp:206-209,322-334
+    // p^2 - 2 = 2^122 - 2^62 - 1 : bits 0..61 set except bit 61?  (2^122 - 2^62 - 1) = [bits 62..121 set] - 1 ...
+    // computed generically from the 128-bit exponent to stay obviously right
+    unsigned __int128 e = (unsigned __int128)P61 * P61 - 2;
+    F ret = mkF(1, 0), tmp = x;
+    while (e) { if (e & 1) ret = fmul(ret, tmp); tmp = fmul(tmp, tmp); e >>= 1; }
+    return ret;
+}
+__global__ void __launch_bounds__(256) field_binop_kernel(int op, const F *__restrict__ a, const F *__restrict__ b, F *__restrict__ c, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        F x = a[i], r;
+        switch (op) {
+            case 0: r = fadd(x, b[i]); break;
+            case 1: r = fsub(x, b[i]); break;
+            case 2: r = fmul(x, b[i]); break;
+            case 3: r = fneg(x); break;
+            default: r = fpow_inv(x); break;
+        }
+        c[i] = r;
+    }
+}
+
+// ---- O1 helpers ----------------------------------------------------------------------------------------
+// reply[q*K + i] = tensor[i][row[q]][col[q]]   (Our_PC.cpp:291-305)
+__global__ void tensor_gather_kernel(const F *__restrict__ tensor, size_t chunk_elems, size_t cols, int K,
+                                     const uint32_t *__restrict__ col, const uint32_t *__restrict__ row, size_t queries, F *__restrict__ reply) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= queries * K) return;
+    size_t q = t / K; int i = (int)(t % K);
+    reply[t] = tensor[(size_t)i * chunk_elems + (size_t)row[q] * cols + col[q]];
+}
+// agg[j] = sum_i beta[i] * poly[i*B + j]   (Our_PC.cpp:265-272); HBM-bound: 16 B read per coefficient
+__global__ void __launch_bounds__(256) aggregate_kernel(const F *__restrict__ poly, size_t B, int K, const F *__restrict__ beta, F *__restrict__ agg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F *sb = reinterpret_cast<F *>(smem_raw);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sb[i] = beta[i];
+    __syncthreads();
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x) {
+        F acc = mkF(0, 0);
+        for (int i = 0; i < K; i++) acc = fadd(acc, fmul(sb[i], poly[(size_t)i * B + j]));
+        agg[j] = acc;
+    }
+}
+
+__global__ void any_nonzero_kernel(const F *__restrict__ v, size_t n, int *flag) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (!fzero(v[i])) { *flag = 1; return; }
+}
+
+// ---- T1 ------------------------------------------------------------------------------------------------
+int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, uint8_t *leaves) {
+    if (trs <= 0 || n % trs) HB_FAIL(ctx, "tensorcode: n must be a multiple of tensor_row_size");
+    size_t cols = 2 * n / trs;
+    if (cols & (cols - 1)) HB_FAIL(ctx, "tensorcode: 2n/trs must be a power of two");
+    HB_TRY(ntt_rows_padded_dev(ctx, msg, n / trs, T, cols, ilog2(cols), trs));
+    if (lin) {
+        HB_TRY(encode_cols_dev(ctx, T, trs, cols, leaves));
+    } else {
+        size_t rows = 2 * (size_t)trs;
+        if (rows & (rows - 1)) HB_FAIL(ctx, "tensorcode: RS columns need a power-of-two tensor_row_size");
+        HB_TRY(ntt_cols_dev(ctx, T, ilog2(rows), cols, trs));
+        if (leaves) HB_TRY(md_leaves_standard_dev(ctx, T, rows, cols, leaves));
+    }
+    return 0;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+// =========================================================================================================
+extern "C" int hb_ctx_create(hb_ctx **out, int device) {
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "hobbit_b200: no CUDA device — this backend has no CPU fallback\n");
+        return 100;
+    }
+    if (device < 0 || device >= ndev) return 101;
+    if (cudaSetDevice(device) != cudaSuccess) return 102;
+    hb_ctx *c = new (std::nothrow) hb_ctx();
+    if (!c) return 103;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 104; }
+    // keep freed stream-ordered allocations cached instead of returning them to the driver on every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return 0;
+}
+
+static void elastic_free(hb_ctx *ctx) {
+    ElasticState &el = ctx->el;
+    for (int i = 0; i < 3; i++) if (el.park[i]) cudaFree(el.park[i]);
+    if (el.tensor) cudaFree(el.tensor);
+    if (el.msg) cudaFree(el.msg);
+    if (el.leaves) cudaFree(el.leaves);
+    if (el.nz_flag) cudaFree(el.nz_flag);
+    el = ElasticState();
+}
+
+extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &t : ctx->tw) if (t) cudaFree(t);
+    if (ctx->exp.d_stages) { cudaFree(ctx->exp.d_stages); cudaFree(ctx->exp.d_rowptr); cudaFree(ctx->exp.d_edges); }
+    if (ctx->tensor) cudaFree(ctx->tensor);
+    if (ctx->poly) cudaFree(ctx->poly);
+    if (ctx->red) cudaFree(ctx->red);
+    if (ctx->ticket) cudaFree(ctx->ticket);
+    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    elastic_free(ctx);
+    for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto &e : ctx->prof_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" const char *hb_last_error(hb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int hb_sync(hb_ctx *ctx) { HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
+extern "C" uint64_t hb_launch_count(hb_ctx *ctx) { return ctx->launches; }
+extern "C" void *hb_stream(hb_ctx *ctx) { return (void *)ctx->stream; }
+// ---- per-kernel timing -------------------------------------------------------------------------------------
+extern "C" int hb_profile_enable(hb_ctx *ctx, int on) {
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof_recs) { ctx->prof_pool.push_back(r.e0); ctx->prof_pool.push_back(r.e1); }
+    ctx->prof_recs.clear();
+    ctx->prof = on != 0;
+    return 0;
+}
+// JSON: {"kernel": {"launches": n, "total_ms": t}, ...}; returns the number of bytes needed (incl. NUL)
+extern "C" size_t hb_profile_report(hb_ctx *ctx, char *buf, size_t cap) {
+    cudaStreamSynchronize(ctx->stream);
+    struct Agg { std::string name; long n; double ms; };
+    std::vector<Agg> agg;
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0; cudaEventElapsedTime(&ms, r.e0, r.e1);
+        std::string nm = r.name;
+        size_t lt = nm.find('<'); if (nm[0] == '(') nm = nm.substr(1, nm.size() - 2);
+        lt = nm.find('<'); if (lt != std::string::npos) nm = nm.substr(0, lt);
+        size_t ns = nm.rfind("::"); if (ns != std::string::npos) nm = nm.substr(ns + 2);
+        bool found = false;
+        for (auto &a : agg) if (a.name == nm) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) agg.push_back({nm, 1, ms});
+    }
+    std::string js = "{";
+    for (size_t i = 0; i < agg.size(); i++) {
+        char tmp[256];
+        snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %ld, \"total_ms\": %.6f}", i ? ", " : "", agg[i].name.c_str(), agg[i].n, agg[i].ms);
+        js += tmp;
+    }
+    js += "}";
+    if (buf && cap) { size_t n = std::min(cap - 1, js.size()); memcpy(buf, js.data(), n); buf[n] = 0; }
+    return js.size() + 1;
+}
+
+extern "C" int hb_malloc_device(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMalloc(p, bytes)); return 0; }
+extern "C" int hb_free_device(hb_ctx *ctx, void *p) { HB_CHECK(ctx, cudaFree(p)); return 0; }
+extern "C" int hb_malloc_pinned(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMallocHost(p, bytes)); return 0; }
+extern "C" int hb_free_pinned(hb_ctx *ctx, void *p) { HB_CHECK(ctx, cudaFreeHost(p)); return 0; }
+extern "C" int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    HB_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- F1/F2 ---------------------------------------------------------------------------------------------
+extern "C" int hb_field_binop(hb_ctx *ctx, int op, const hb_F *a, const hb_F *b, hb_F *c, size_t n) {
+    if (op < 0 || op > 4) HB_FAIL(ctx, "hb_field_binop: unknown op");
+    if (n == 0) return 0;
+    Staged sa(ctx), sb(ctx), sc(ctx);
+    HB_TRY(sa.in(a, n * sizeof(F)));
+    HB_TRY(sb.in(op < 3 ? b : a, n * sizeof(F)));
+    HB_TRY(sc.outbuf(c, n * sizeof(F)));
+    unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    HB_LAUNCH(ctx, field_binop_kernel, grid, 256, 0, op, sa.as<F>(), sb.as<F>(), sc.as<F>(), n);
+    HB_TRY(sc.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" void hb_root_of_unity(int logn, hb_F *out) {          // utils.cpp:452-463
+    F rou = mkF(2147483648ULL, 1033321771269002680ULL);
+    for (int i = 0; i < 62 - logn; i++) rou = h_fmul(rou, rou);
+    out->real = rou.re; out->img = rou.im;
+}
+
+extern "C" void hb_mimc_hash(const hb_F *input, const hb_F *k, hb_F *out) {   // mimc.cpp:95-107, constants c_i = F(i) (:11-19)
+    F in = mkF(input->real, input->img), key = mkF(k->real, k->img), t, h = mkF(0, 0);
+    for (int i = 0; i < 161; i++) {
+        t = (i == 0) ? fadd(in, key) : fadd(fadd(h, key), mkF((u64)(i - 1), 0));
+        h = h_fmul(h_fmul(t, t), t);
+    }
+    h = fadd(h, key);
+    out->real = h.re; out->img = h.im;
+}
+
+// ---- T1 ------------------------------------------------------------------------------------------------
+extern "C" int hb_tensorcode(hb_ctx *ctx, const hb_F *msg, size_t n, int trs, int linear_time, hb_F *tensor) {
+    Staged m(ctx), t(ctx);
+    HB_TRY(m.in(msg, n * sizeof(F)));
+    HB_TRY(t.outbuf(tensor, 4 * n * sizeof(F)));
+    HB_TRY(tensorcode_dev(ctx, m.as<F>(), n, trs, linear_time, t.as<F>(), nullptr));
+    HB_TRY(t.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- C1 ------------------------------------------------------------------------------------------------
+extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K, int trs, int linear_time,
+                                  uint8_t *levels_out, hb_F *tensor_out) {
+    if (K <= 0 || N % K) HB_FAIL(ctx, "hb_commit_standard: N must be a multiple of K");
+    const size_t B = N / K;
+    if (B & (B - 1)) HB_FAIL(ctx, "hb_commit_standard: N/K must be a power of two");
+    if (trs < 2 || (2 * trs) % 4) HB_FAIL(ctx, "hb_commit_standard: tensor_row_size must be even");
+    // resident tensor (K chunks x 4B) — open_standard gathers from it
+    if (ctx->tensor_elems != 4 * N) {
+        if (ctx->tensor) cudaFree(ctx->tensor);
+        ctx->tensor = nullptr; ctx->tensor_elems = 0;
+        HB_CHECK(ctx, cudaMalloc(&ctx->tensor, 4 * N * sizeof(F)));
+        ctx->tensor_elems = 4 * N;
+    }
+    ctx->tensor_N = N; ctx->tensor_K = K; ctx->tensor_trs = trs;
+    Staged lv(ctx);
+    HB_TRY(lv.outbuf(levels_out, (2 * B - 1) * 32));
+    HB_CHECK(ctx, cudaMemsetAsync(lv.dev, 0, B * 32, ctx->stream));        // chain starts from all-zero digests (Our_PC.cpp:153)
+
+    const bool on_dev = is_device_ptr(poly);
+    if (!on_dev) {
+        // stage the polynomial chunk by chunk on the copy stream so the H2D of chunk i+1 overlaps the encode of chunk i;
+        // the device copy is kept for hb_aggregate (open_standard reads the polynomial again)
+        if (ctx->poly_elems != N) {
+            if (ctx->poly) cudaFree(ctx->poly);
+            ctx->poly = nullptr; ctx->poly_elems = 0;
+            HB_CHECK(ctx, cudaMalloc(&ctx->poly, N * sizeof(F)));
+            ctx->poly_elems = N;
+        }
+        ctx->poly_host = poly;
+    }
+    std::vector<cudaEvent_t> ev(on_dev ? 0 : K);
+    if (!on_dev) {
+        cudaEvent_t start;
+        HB_CHECK(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+        HB_CHECK(ctx, cudaEventRecord(start, ctx->stream));
+        HB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, start, 0));    // do not overwrite ctx->poly under earlier work
+        cudaEventDestroy(start);
+        for (int i = 0; i < K; i++) {
+            HB_CHECK(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            HB_CHECK(ctx, cudaMemcpyAsync(ctx->poly + (size_t)i * B, (const F *)poly + (size_t)i * B, B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
+            HB_CHECK(ctx, cudaEventRecord(ev[i], ctx->copy_stream));
+        }
+    }
+    const F *src = on_dev ? (const F *)poly : ctx->poly;
+    for (int i = 0; i < K; i++) {
+        if (!on_dev) HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ev[i], 0));
+        HB_TRY(tensorcode_dev(ctx, src + (size_t)i * B, B, trs, linear_time, ctx->tensor + (size_t)i * 4 * B, lv.as<uint8_t>()));
+    }
+    HB_TRY(merkle_tree_dev(ctx, lv.as<uint8_t>(), B));
+    HB_TRY(lv.finish());
+    if (tensor_out) HB_CHECK(ctx, cudaMemcpyAsync(tensor_out, ctx->tensor, 4 * N * sizeof(F), cudaMemcpyDefault, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return 0;
+}
+
+extern "C" const hb_F *hb_tensor_device(hb_ctx *ctx) { return (const hb_F *)ctx->tensor; }
+
+extern "C" int hb_tensor_gather(hb_ctx *ctx, const uint32_t *col, const uint32_t *row, size_t queries, hb_F *reply) {
+    if (!ctx->tensor) HB_FAIL(ctx, "hb_tensor_gather: no committed tensor in this context");
+    if (queries == 0) return 0;
+    const size_t B = ctx->tensor_N / ctx->tensor_K, cols = 2 * B / ctx->tensor_trs;
+    Staged c(ctx), r(ctx), o(ctx);
+    HB_TRY(c.in(col, queries * 4)); HB_TRY(r.in(row, queries * 4));
+    HB_TRY(o.outbuf(reply, queries * ctx->tensor_K * sizeof(F)));
+    size_t tot = queries * ctx->tensor_K;
+    HB_LAUNCH(ctx, tensor_gather_kernel, (unsigned)((tot + 255) / 256), 256, 0, ctx->tensor, 4 * B, cols, ctx->tensor_K,
+              c.as<uint32_t>(), r.as<uint32_t>(), queries, o.as<F>());
+    HB_TRY(o.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, const hb_F *beta, hb_F *agg) {
+    if (K <= 0 || N % K) HB_FAIL(ctx, "hb_aggregate: N must be a multiple of K");
+    const size_t B = N / K;
+    Staged p(ctx), b(ctx), o(ctx);
+    const F *src;
+    if (poly == nullptr || (!is_device_ptr(poly) && ctx->poly && ctx->poly_elems == N && ctx->poly_host == (const void *)poly)) {
+        if (!ctx->poly || ctx->poly_elems != N) HB_FAIL(ctx, "hb_aggregate: no resident polynomial of this size (pass poly)");
+        src = ctx->poly;                                   // device copy kept by hb_commit_standard
+    } else {
+        HB_TRY(p.in(poly, N * sizeof(F))); src = p.as<F>();
+    }
+    HB_TRY(b.in(beta, (size_t)K * sizeof(F)));
+    HB_TRY(o.outbuf(agg, B * sizeof(F)));
+    unsigned grid = (unsigned)std::min<size_t>((B + 255) / 256, (size_t)ctx->sm_count * 8);
+    HB_LAUNCH(ctx, aggregate_kernel, grid, 256, (size_t)K * sizeof(F), src, B, K, b.as<F>(), o.as<F>());
+    HB_TRY(o.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- C2 ------------------------------------------------------------------------------------------------
+extern "C" int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time) {
+    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_begin: BUFFER_SPACE must be a power of two");
+    elastic_free(ctx);
+    ElasticState &el = ctx->el;
+    el.B = B; el.trs = trs; el.lin = linear_time; el.chunk_idx = 0;
+    for (int i = 0; i < 3; i++) HB_CHECK(ctx, cudaMalloc(&el.park[i], 4 * B * sizeof(F)));
+    HB_CHECK(ctx, cudaMalloc(&el.tensor, 4 * B * sizeof(F)));
+    HB_CHECK(ctx, cudaMalloc(&el.msg, B * sizeof(F)));
+    HB_CHECK(ctx, cudaMalloc(&el.leaves, (8 * B - 1) * 32));
+    HB_CHECK(ctx, cudaMalloc(&el.nz_flag, sizeof(int)));
+    HB_CHECK(ctx, cudaMemsetAsync(el.leaves, 0, 4 * B * 32, ctx->stream));   // Elastic_PC.cpp:195-199
+    el.active = true;
+    return 0;
+}
+
+extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) {
+    ElasticState &el = ctx->el;
+    if (!el.active) HB_FAIL(ctx, "hb_elastic_push: call hb_elastic_begin first");
+    const size_t B = el.B;
+    const F *src = (const F *)chunk;
+    if (!is_device_ptr(chunk)) {
+        HB_CHECK(ctx, cudaMemcpyAsync(el.msg, chunk, B * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+        src = el.msg;
+    }
+    const unsigned slot = (unsigned)(el.chunk_idx % 4);
+    F *T = slot == 3 ? el.tensor : el.park[slot];          // encode straight into the parking slot: no copy
+    // all-zero chunk => all-zero tensor, no encode (Elastic_PC.cpp:206-222)
+    int nz = 0;
+    HB_CHECK(ctx, cudaMemsetAsync(el.nz_flag, 0, sizeof(int), ctx->stream));
+    HB_LAUNCH(ctx, any_nonzero_kernel, (unsigned)std::min<size_t>((B + 255) / 256, (size_t)ctx->sm_count * 4), 256, 0, src, B, el.nz_flag);
+    HB_CHECK(ctx, cudaMemcpyAsync(&nz, el.nz_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nz) HB_TRY(tensorcode_dev(ctx, src, B, el.trs, el.lin, T, nullptr));
+    else HB_CHECK(ctx, cudaMemsetAsync(T, 0, 4 * B * sizeof(F), ctx->stream));
+    if (slot == 3) HB_TRY(md_leaves_stream4_dev(ctx, el.park[0], el.park[1], el.park[2], el.tensor, 4 * B, el.leaves));
+    el.chunk_idx++;
+    return 0;
+}
+
+extern "C" int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out) {
+    ElasticState &el = ctx->el;
+    if (!el.active) HB_FAIL(ctx, "hb_elastic_finish: no commit in progress");
+    HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
+    HB_CHECK(ctx, cudaMemcpyAsync(levels_out, el.leaves, (8 * el.B - 1) * 32, cudaMemcpyDefault, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    elastic_free(ctx);
+    return 0;
+}
+
+// W1: synthetic default stream of read_stream_PC (witness_stream.cpp:2405-2411).  The recurrence is inherently
+// sequential (x <- x^2 + i), it is the INPUT GENERATOR of test_Elastic_PC, so it is evaluated once on the host.
+extern "C" int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n) {
+    std::vector<F> v(n);
+    F x = mkF(322322, 0);
+    for (size_t i = 0; i < n; i++) { v[i] = x; x = fadd(h_fmul(x, x), mkF((u64)i, 0)); }
+    HB_CHECK(ctx, cudaMemcpyAsync(out, v.data(), n * sizeof(F), cudaMemcpyDefault, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -1,0 +1,157 @@
+// Internal glue shared by the .cu translation units: the context object, error handling, host<->device
+// staging of caller buffers, and a launch counter.  Nothing here is part of the public C ABI.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/hobbit_b200.h"
+#include "field.cuh"
+
+namespace hb {
+
+static constexpr int kSMs = 148;        // B200: 2 dies x 74 SMs; grids for grid-stride kernels are multiples of this
+
+struct EncStage {                       // one sparse mat-vec of the expander encode: out[0..R) = G * in[0..L)
+    int in_off, out_off, L, R;          // offsets/sizes in codeword coordinates
+    int rowptr_base;                    // index into rowptr[] (R+1 entries)
+};
+
+struct ExpanderDev {
+    long long n = 0;
+    int cwlen = 0;
+    std::vector<EncStage> stages;       // execution order: C0..C_last, D_last..D0
+    EncStage *d_stages = nullptr;
+    int *d_rowptr = nullptr;            // CSR by target
+    uint2 *d_edges = nullptr;           // {absolute source index in the codeword, 32-bit weight}
+    size_t n_edges = 0;
+    int max_indeg = 0;
+};
+
+struct ElasticState {
+    bool active = false;
+    size_t B = 0; int trs = 0; int lin = 0;
+    size_t chunk_idx = 0;
+    F *park[3] = {nullptr, nullptr, nullptr};   // 3 parked encoded chunks (4B each), Elastic_PC.cpp:179-183
+    F *tensor = nullptr;                        // current encoded chunk (4B)
+    F *msg = nullptr;                           // staging for a host chunk
+    uint8_t *leaves = nullptr;                  // (2*4B-1)*32
+    int *nz_flag = nullptr;
+};
+
+}  // namespace hb
+
+struct hb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // compute
+    cudaStream_t copy_stream = nullptr; // H2D prefetch of the next chunk
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = hb::kSMs;
+    // twiddle tables w[k] = omega_len^k, k < len/2, cached per log2(len)
+    hb::F *tw[32] = {};
+    hb::ExpanderDev exp;
+    // resident tensor of the last commit_standard
+    hb::F *tensor = nullptr; size_t tensor_elems = 0; size_t tensor_N = 0; int tensor_K = 0; int tensor_trs = 0;
+    // device copy of the polynomial staged by the last commit_standard (open_standard's aggregate reads it again)
+    hb::F *poly = nullptr; size_t poly_elems = 0; const void *poly_host = nullptr;
+    hb::ElasticState el;
+    // sumcheck reduction scratch: per-CTA partial coefficients + ticket counter (device), result mailbox (pinned host)
+    hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr;
+    // optional per-kernel timing (hb_profile_*): CUDA events around every launch, on this context's stream
+    bool prof = false;
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+};
+namespace hb {
+inline cudaEvent_t prof_event(hb_ctx *ctx) {
+    cudaEvent_t e;
+    if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+}
+
+#define HB_CHECK(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                         std::to_string(__LINE__) + ")";                                      \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+#define HB_TRY(expr) do { int r__ = (expr); if (r__) return r__; } while (0)
+#define HB_FAIL(ctx, msg) do { (ctx)->err = (msg); return 2; } while (0)
+// every kernel launch goes through this so the launch counter is honest
+#define HB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                        \
+    do {                                                                                      \
+        cudaEvent_t pe0__ = nullptr, pe1__ = nullptr;                                         \
+        if ((ctx)->prof) { pe0__ = hb::prof_event(ctx); pe1__ = hb::prof_event(ctx); cudaEventRecord(pe0__, (ctx)->stream); } \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+        (ctx)->launches++;                                                                    \
+        if ((ctx)->prof) { cudaEventRecord(pe1__, (ctx)->stream); (ctx)->prof_recs.push_back({#kernel, pe0__, pe1__}); } \
+        HB_CHECK(ctx, cudaGetLastError());                                                    \
+    } while (0)
+
+namespace hb {
+
+inline bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// RAII staging of a caller buffer: device pointers pass through, host pointers get a stream-ordered temporary.
+struct Staged {
+    hb_ctx *ctx; void *dev = nullptr; void *host = nullptr; size_t bytes = 0; bool owned = false; bool out = false;
+    Staged(hb_ctx *c) : ctx(c) {}
+    int in(const void *p, size_t n) {
+        bytes = n;
+        if (n == 0) { dev = nullptr; return 0; }
+        if (is_device_ptr(p)) { dev = const_cast<void *>(p); return 0; }
+        owned = true; host = const_cast<void *>(p);
+        HB_CHECK(ctx, cudaMallocAsync(&dev, n, ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(dev, p, n, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    }
+    int outbuf(void *p, size_t n, bool copy_in = false) {
+        bytes = n; out = true;
+        if (n == 0) { dev = nullptr; return 0; }
+        if (is_device_ptr(p)) { dev = p; return 0; }
+        owned = true; host = p;
+        HB_CHECK(ctx, cudaMallocAsync(&dev, n, ctx->stream));
+        if (copy_in) HB_CHECK(ctx, cudaMemcpyAsync(dev, p, n, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    }
+    // copy back (if host output) and synchronise
+    int finish() {
+        if (owned && out && bytes) HB_CHECK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return 0;
+    }
+    ~Staged() { if (owned && dev) cudaFreeAsync(dev, ctx->stream); }
+    template <class T> T *as() { return reinterpret_cast<T *>(dev); }
+};
+
+inline int ilog2(size_t x) { int l = 0; while (x >>= 1) l++; return l; }
+
+// internal entry points implemented across the .cu files (all take DEVICE pointers)
+int get_twiddles(hb_ctx *ctx, int logn, const F **out);
+int ntt_rows_dev(hb_ctx *ctx, F *data, int logn, size_t batch, size_t stride);
+// rows of `in_len` elements (row r at src + r*in_len) zero-extended to 2^logn and transformed into dst + r*dst_stride
+int ntt_rows_padded_dev(hb_ctx *ctx, const F *src, size_t in_len, F *dst, size_t dst_stride, int logn, size_t batch);
+// column NTT of a (2^logn x cols) row-major matrix whose rows >= nz_rows are implicitly zero on input
+int ntt_cols_dev(hb_ctx *ctx, F *mat, int logn, size_t cols, size_t nz_rows);
+// expander-encode every column of T (rows [0,n) hold the messages); writes rows [n, 2n).
+// leaves != nullptr: fused Merkle–Damgård leaf update of commit_standard for these columns.
+int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, uint8_t *leaves);
+int md_leaves_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, uint8_t *leaves);
+int md_leaves_stream4_dev(hb_ctx *ctx, const F *c0, const F *c1, const F *c2, const F *T, size_t cells, uint8_t *leaves);
+int blake3_64_dev(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count);
+int merkle_tree_dev(hb_ctx *ctx, uint8_t *levels, size_t nleaves);
+int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, uint8_t *leaves_standard);
+
+}  // namespace hb

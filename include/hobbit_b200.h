@@ -1,0 +1,135 @@
+/* hobbit_b200 — C ABI of the B200-native backend for HOBBIT's data-parallel prover hot path.
+ *
+ * The reference (ChristodoulosPappas/HOBBIT-…, `/root/reference`) has no FFI layer: its "API" is a set of free
+ * C++ functions over STL containers.  This header is the flat boundary those functions forward
+ * to; the C++ shims with the reference's exact signatures live in hobbit_b200/host/hobbit_host.hpp and
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 on success, non-zero on error
+ *    (hb_last_error(ctx) gives the text).  No exceptions cross the boundary.
+ *  - hb_F is the reference's 16-byte POD `virgo::fieldElement {u64 real; u64 img}` (fieldElement.hpp:96-97),
+ *    canonical limbs in [0, 2^61-1).  Digests are 32 raw bytes == reference `_hash` (Blake3_hash.h:3-5).
+ *  - every DATA pointer may be host memory (pageable or pinned) or device memory; the library detects which
+ *    (cudaPointerGetAttributes) and stages copies on the context's stream.  Outputs are complete when the call
+ *    returns unless the function name ends in `_async`.
+ *  - a context is bound to one CUDA device and is thread-compatible (one caller at a time), like the reference's
+ *    non-reentrant entry points.
+ *  - there is NO CPU fallback: without a CUDA device hb_ctx_create fails.
+ */
+#ifndef HOBBIT_B200_H
+#define HOBBIT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_ctx hb_ctx;
+typedef struct { uint64_t real, img; } hb_F;
+
+/* ---- context / memory ------------------------------------------------------------------------------------ */
+int  hb_ctx_create(hb_ctx **out, int device);
+void hb_ctx_destroy(hb_ctx *ctx);
+const char *hb_last_error(hb_ctx *ctx);
+int  hb_sync(hb_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py reports the delta as gpu_launches) */
+uint64_t hb_launch_count(hb_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on — for event timing by the caller */
+void *hb_stream(hb_ctx *ctx);
+/* per-kernel timing: CUDA events around every launch on the context's stream.  enable(1) clears the records;
+ * report writes JSON {"kernel": {"launches": n, "total_ms": t}, ...} and returns the bytes needed. */
+int  hb_profile_enable(hb_ctx *ctx, int on);
+size_t hb_profile_report(hb_ctx *ctx, char *buf, size_t cap);
+int  hb_malloc_device(hb_ctx *ctx, void **p, size_t bytes);
+int  hb_free_device(hb_ctx *ctx, void *p);
+int  hb_malloc_pinned(hb_ctx *ctx, void **p, size_t bytes);
+int  hb_free_pinned(hb_ctx *ctx, void *p);
+int  hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes);   /* any direction, synchronous */
+
+/* ---- F1/F2: field (reference fieldElement.cpp:34-104, 206-209) ------------------------------------------- */
+/* op: 0 a+b, 1 a-b, 2 a*b, 3 -a, 4 a^-1 (b ignored for 3,4) */
+int hb_field_binop(hb_ctx *ctx, int op, const hb_F *a, const hb_F *b, hb_F *c, size_t n);
+/* getRootOfUnity (utils.cpp:452-463), mimc_hash (mimc.cpp:95-107): scalar, evaluated on the host */
+void hb_root_of_unity(int logn, hb_F *out);
+void hb_mimc_hash(const hb_F *input, const hb_F *k, hb_F *out);
+
+/* ---- N1: NTT == _fft(arr, logn, false) (utils.cpp:605-673), batched over rows ------------------------------ */
+/* `batch` rows of 2^logn elements each, row r starts at data + r*stride (elements); in place. */
+int hb_ntt_batch(hb_ctx *ctx, hb_F *data, int logn, size_t batch, size_t stride);
+
+/* ---- E1/E2: Orion/Spielman expander code (expanders.h:20-47,78-92; linear_code_encode.h:62-119) ------------ */
+/* Upload the graphs the HOST generated with libc rand()/random() (RNG order stays on the host).
+ * levels = recursion depth; for dep < levels: C graph (L_C[dep] x R_C[dep], degree deg_C) and D graph
+ * (L_D[dep] x R_D[dep], degree deg_D); nbr_X[dep][i*deg+j] = target, w_X[dep][i*deg+j] = weight (real, < 2^32). */
+int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, int deg_D,
+                    const long long *L_C, const long long *R_C, const uint32_t *const *nbr_C, const uint64_t *const *w_C,
+                    const long long *L_D, const long long *R_D, const uint32_t *const *nbr_D, const uint64_t *const *w_D);
+/* codeword length of the installed code (n + L + R), 0 if none */
+long long hb_expander_codeword_len(hb_ctx *ctx);
+/* encode_monolithic for `ncols` messages at once.  src: n x ncols row-major (message c = column c);
+ * dst: 2n x ncols row-major; rows >= codeword length are zero (the reference's caller buffer is 2n, zero tail). */
+int hb_encode_batch(hb_ctx *ctx, const hb_F *src, hb_F *dst, long long n, size_t ncols);
+
+/* ---- H1..H4: BLAKE3 leaves and the Merkle tree (Blake3_hash.cpp:5-10; merkle_tree.cpp:62-87,193-287) ------ */
+int hb_blake3_64(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count);       /* count x (64 B -> 32 B) */
+/* create_tree_blake: `levels` holds nleaves digests at offset 0 and room for (2*nleaves-1)*32 bytes; the upper
+ * levels are appended level by level.  Parent = H1(left || left), as in the reference (merkle_tree.cpp:275-280). */
+int hb_merkle_tree(hb_ctx *ctx, uint8_t *levels, size_t nleaves);
+/* MT_commit_Blake: leaf i = H1(leafs[4i..4i+3]); then the tree.  levels: (2*(N/4)-1)*32 bytes. */
+int hb_mt_commit(hb_ctx *ctx, const hb_F *leafs, size_t N, uint8_t *levels);
+
+/* ---- T1: tensor code (PC_utils.cpp:9-123) ------------------------------------------------------------------ */
+/* msg: n elements -> tensor: (2*trs) x (2n/trs) row-major.  linear_time != 0: rows RS (NTT), columns expander
+ * (needs hb_expander_set for n = trs); == 0: RS x RS. */
+int hb_tensorcode(hb_ctx *ctx, const hb_F *msg, size_t n, int trs, int linear_time, hb_F *tensor);
+
+/* ---- C1: commit_standard (Our_PC.cpp:146-171) -------------------------------------------------------------- */
+/* poly: N elements, K chunks.  levels_out: (2*(N/K)-1)*32 bytes (every level, leaves first).
+ * tensor_out: NULL, or K*4*(N/K) elements (chunk-major, then row-major) == the reference's `_tensor`.
+ * The encoded tensor always stays resident in the context for hb_open_standard_* (see hb_tensor_device). */
+int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K, int trs, int linear_time,
+                       uint8_t *levels_out, hb_F *tensor_out);
+/* device pointer to the resident `_tensor` of the last hb_commit_standard (K*4*(N/K) elements), or NULL */
+const hb_F *hb_tensor_device(hb_ctx *ctx);
+/* _compute_aggregation_reply (Our_PC.cpp:291-305): reply[q*K + i] = _tensor[i][row[q]][col[q]] */
+int hb_tensor_gather(hb_ctx *ctx, const uint32_t *col, const uint32_t *row, size_t queries, hb_F *reply);
+/* _aggregate's axpy (Our_PC.cpp:258-273): agg[j] = sum_i beta[i] * poly[i*(N/K) + j] */
+int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, const hb_F *beta, hb_F *agg);
+
+/* ---- C2: Elastic_PC commit (Elastic_PC.cpp:174-285), chunk at a time --------------------------------------- */
+/* begin: B = BUFFER_SPACE, trs = tensor_row_size.  push: one chunk of B elements (call N/B times, in order);
+ * all-zero chunks skip the encode like the reference (:206-222).  finish: levels_out (2*4B-1)*32 bytes. */
+int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time);
+int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk);
+int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out);
+/* read_stream_PC's synthetic default stream (witness_stream.cpp:2405-2411): v[0]=322322, v[i+1]=v[i]^2+i */
+int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n);
+
+/* ---- S9: eq table and MLE evaluation (utils.cpp:251-296, 789-802) ------------------------------------------ */
+int hb_precompute_beta(hb_ctx *ctx, const hb_F *r, int nr, hb_F *out);          /* out: 2^nr */
+int hb_evaluate_vector(hb_ctx *ctx, const hb_F *v, size_t n, const hb_F *r, hb_F *out);
+
+/* ---- S1/S2/S3/S5: sumcheck provers (sumcheck.cpp:2391-2460, 1974-2058, 275-372, 35-257) --------------------- */
+/* Flat proof layouts (hb_F units), rounds = log2(n):
+ *   S1: (a,b,c) x rounds | randomness x rounds | vr[2] | final_rand                       -> 4*rounds+3
+ *   S2: (a,b,c,d) x rounds | randomness x rounds | vr[3] | final_rand                     -> 5*rounds+4
+ *   S3: (a,b,c,d) x rounds | randomness x rounds | vr[3*batches]                          -> 5*rounds+3*batches
+ * *ps accumulates the reference's proof-size counter (KB).  Input tables are not modified. */
+int hb_sumcheck2(hb_ctx *ctx, const hb_F *v1, const hb_F *v2, size_t n, const hb_F *prev_r, hb_F *proof, double *ps);
+int hb_sumcheck3(hb_ctx *ctx, const hb_F *v1, const hb_F *v2, const hb_F *v3, size_t n, const hb_F *prev_r,
+                 hb_F *proof, double *ps);
+int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, const hb_F *t3, const size_t *sizes, int batches,
+                       const hb_F *a, hb_F *proof, double *ps);
+/* prove_multiplication_tree_new for `vectors` tables of n elements (powers of two).  x_rand: the log2(vectors)
+ * libc-drawn points (generate_randomness) when vectors > 1, ignored otherwise.  Output layout:
+ *   output[vectors] | out_eval | final_r[nfr] | final_eval | per layer: (a,b,c,d) x rounds | vr[3] | final_rand
+ * Returns the number of hb_F written in *written. */
+int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n, const hb_F *prev_r, const hb_F *x_rand,
+                hb_F *out, size_t *written, int *nfr, double *ps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOBBIT_B200_H */
