@@ -229,10 +229,14 @@ def main():
             ms = float(t.item())
         return ms, ctx.launch_count() - l0
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 5.0:     # nvidia-smi needs a moment to start streaming
+        time.sleep(0.05)
+    sampler.rows.clear()
     ctx.profile(True)
     ms, launches = timed(step_resident, args.steps)
     prof = ctx.profile_report()
@@ -250,8 +254,9 @@ def main():
     name, rec = dom
     per_launch_ms = rec["total_ms"] / rec["launches"]
     # algorithmic bytes per coefficient for this kernel: read the RS-encoded rows (2 cells = 32 B),
-    # write the parity rows + zero tail (32 B), leaf digest written once per leaf position in an ideal schedule (32/K B)
-    alg_bytes = {"encode_cols_kernel": (32 + 32 + 32.0 / K) * B, "ntt_tile_kernel": (16 + 32) * B}.get(name, 64.0 * B)
+    # write the parity rows + zero tail (32 B), write the inner leaf digest (one 32 B digest per coefficient and chunk)
+    coeffs_per_launch = float(N) * args.steps / rec["launches"]
+    alg_bytes = {"encode_cols_kernel": 32 + 32 + 32.0, "ntt_tile_kernel": 16 + 32, "md_chain_kernel": 32.0}.get(name, 64.0) * coeffs_per_launch
     peak, how = peaks()
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
     kernel_share = {k: round(v["total_ms"] / sum(x["total_ms"] for x in prof.values()), 4) for k, v in prof.items()}

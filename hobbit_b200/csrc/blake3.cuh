@@ -12,10 +12,41 @@ struct Digest { uint32_t w[8]; };   // 32 bytes, little-endian words == referenc
 
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int c) { return __funnelshift_r(x, x, c); }
 
-#define HB_G(a, b, c, d, x, y)                                              \
-    do {                                                                    \
-        a = a + b + (x); d = rotr(d ^ a, 16); c = c + d; b = rotr(b ^ c, 12); \
-        a = a + b + (y); d = rotr(d ^ a, 8);  c = c + d; b = rotr(b ^ c, 7);  \
+// Pipe balancing (measured on B200, tools/ubench_blake.cu): XOR and rotate can only issue on the ALU pipe (8 per G,
+// 2 cycles each per SM sub-partition), so the additions must stay off it.  ptxas fuses `a + b + m` into one 3-input
+// IADD3 on the ALU pipe (variant 0: 32.2 G compress/s, ALU pipe 96 % busy, FMA pipe 10 %).  Making `a + b` an opaque
+// IMAD (`a * one + b`, `one` read from %nctaid.z == 1, unknown to ptxas) leaves only 2-input adds, which ptxas emits
+// as IMAD.IADD on the FMA pipe: variant 3 reaches 38.9 G compress/s = the ALU floor of 466 LOP3/SHF per compression.
+// (Forcing every add through the register-form IMAD — variant 1 — is slower: 25.8 G/s.)
+__device__ __forceinline__ uint32_t hb_one() { uint32_t v; asm("mov.u32 %0, %%nctaid.z;" : "=r"(v)); return v; }
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b)); return d;
+}
+
+#ifndef HB_BLAKE_VARIANT
+#define HB_BLAKE_VARIANT 3
+#endif
+#if HB_BLAKE_VARIANT == 0      // plain adds (ptxas picks IADD3 on the ALU pipe)
+#define HB_ADD3(a, b, x) ((a) + (b) + (x))
+#define HB_ADD2(c, d) ((c) + (d))
+#elif HB_BLAKE_VARIANT == 1    // every add on the FMA pipe
+#define HB_ADD3(a, b, x) add_fma(add_fma(a, b, one), (x), one)
+#define HB_ADD2(c, d) add_fma(c, d, one)
+#elif HB_BLAKE_VARIANT == 2    // a+b+x stays one IADD3, c+d goes to the FMA pipe
+#define HB_ADD3(a, b, x) ((a) + (b) + (x))
+#define HB_ADD2(c, d) add_fma(c, d, one)
+#elif HB_BLAKE_VARIANT == 3    // a+b on the FMA pipe, the rest plain
+#define HB_ADD3(a, b, x) (add_fma(a, b, one) + (x))
+#define HB_ADD2(c, d) ((c) + (d))
+#else                          // two 2-input adds kept apart by an empty asm so that ptxas cannot fuse them into IADD3
+__device__ __forceinline__ uint32_t opaque(uint32_t v) { asm("" : "+r"(v)); return v; }
+#define HB_ADD3(a, b, x) (opaque((a) + (b)) + (x))
+#define HB_ADD2(c, d) ((c) + (d))
+#endif
+#define HB_G(a, b, c, d, x, y)                                                                          \
+    do {                                                                                                \
+        a = HB_ADD3(a, b, x); d = rotr(d ^ a, 16); c = HB_ADD2(c, d); b = rotr(b ^ c, 12); \
+        a = HB_ADD3(a, b, y); d = rotr(d ^ a, 8);  c = HB_ADD2(c, d); b = rotr(b ^ c, 7);  \
     } while (0)
 
 // schedule[r][i] = index into the ORIGINAL message words used at position i of round r
@@ -27,6 +58,7 @@ __device__ __forceinline__ uint32_t rotr(uint32_t x, int c) { return __funnelshi
     HB_G(v2, v7, v8,  v13, m[s12], m[s13]); HB_G(v3, v4, v9,  v14, m[s14], m[s15]);
 
 __device__ __forceinline__ void blake3_compress64(const uint32_t (&m)[16], uint32_t (&out)[8]) {
+    const uint32_t one = hb_one();
     uint32_t v0 = 0x6A09E667u, v1 = 0xBB67AE85u, v2 = 0x3C6EF372u, v3 = 0xA54FF53Au;
     uint32_t v4 = 0x510E527Fu, v5 = 0x9B05688Cu, v6 = 0x1F83D9ABu, v7 = 0x5BE0CD19u;
     uint32_t v8 = 0x6A09E667u, v9 = 0xBB67AE85u, v10 = 0x3C6EF372u, v11 = 0xA54FF53Au;

@@ -62,18 +62,18 @@ __global__ void any_nonzero_kernel(const F *__restrict__ v, size_t n, int *flag)
 }
 
 // ---- T1 ------------------------------------------------------------------------------------------------
-int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, uint8_t *leaves) {
+int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, size_t nchunks, uint8_t *inner) {
     if (trs <= 0 || n % trs) HB_FAIL(ctx, "tensorcode: n must be a multiple of tensor_row_size");
     size_t cols = 2 * n / trs;
     if (cols & (cols - 1)) HB_FAIL(ctx, "tensorcode: 2n/trs must be a power of two");
-    HB_TRY(ntt_rows_padded_dev(ctx, msg, n / trs, T, cols, ilog2(cols), trs));
+    HB_TRY(ntt_rows_padded_dev(ctx, msg, n / trs, T, cols, ilog2(cols), trs, nchunks, n, 4 * n));
     if (lin) {
-        HB_TRY(encode_cols_dev(ctx, T, trs, cols, leaves));
+        HB_TRY(encode_cols_dev(ctx, T, trs, cols, nchunks, 4 * n, inner));
     } else {
         size_t rows = 2 * (size_t)trs;
         if (rows & (rows - 1)) HB_FAIL(ctx, "tensorcode: RS columns need a power-of-two tensor_row_size");
-        HB_TRY(ntt_cols_dev(ctx, T, ilog2(rows), cols, trs));
-        if (leaves) HB_TRY(md_leaves_standard_dev(ctx, T, rows, cols, leaves));
+        for (size_t c = 0; c < nchunks; c++) HB_TRY(ntt_cols_dev(ctx, T + c * 4 * n, ilog2(rows), cols, trs));
+        if (inner) HB_TRY(md_inner_standard_dev(ctx, T, rows, cols, nchunks, 4 * n, inner));
     }
     return 0;
 }
@@ -222,7 +222,7 @@ extern "C" int hb_tensorcode(hb_ctx *ctx, const hb_F *msg, size_t n, int trs, in
     Staged m(ctx), t(ctx);
     HB_TRY(m.in(msg, n * sizeof(F)));
     HB_TRY(t.outbuf(tensor, 4 * n * sizeof(F)));
-    HB_TRY(tensorcode_dev(ctx, m.as<F>(), n, trs, linear_time, t.as<F>(), nullptr));
+    HB_TRY(tensorcode_dev(ctx, m.as<F>(), n, trs, linear_time, t.as<F>(), 1, nullptr));
     HB_TRY(t.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -259,24 +259,36 @@ extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K
         }
         ctx->poly_host = poly;
     }
-    std::vector<cudaEvent_t> ev(on_dev ? 0 : K);
+    // Chunks are processed in groups of G through ONE launch per kernel (grid.y = chunk): no per-chunk grid tail.
+    // The inner leaf digests of a group are staged in HBM (32 B per coefficient) and chained in chunk order afterwards.
+    // Host input: groups of 4 so the H2D of the next group overlaps this group's encode; resident input: up to 1 GiB of
+    // inner digests per group.
+    int G = on_dev ? (int)std::max<size_t>(1, std::min<size_t>((size_t)K, ((size_t)1 << 30) / (B * 32))) : std::min(K, 4);
+    uint8_t *inner;
+    HB_CHECK(ctx, cudaMallocAsync(&inner, (size_t)G * B * 32, ctx->stream));
+    const int ngroups = (K + G - 1) / G;
+    std::vector<cudaEvent_t> ev(on_dev ? 0 : ngroups);
     if (!on_dev) {
         cudaEvent_t start;
         HB_CHECK(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
         HB_CHECK(ctx, cudaEventRecord(start, ctx->stream));
         HB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, start, 0));    // do not overwrite ctx->poly under earlier work
         cudaEventDestroy(start);
-        for (int i = 0; i < K; i++) {
-            HB_CHECK(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-            HB_CHECK(ctx, cudaMemcpyAsync(ctx->poly + (size_t)i * B, (const F *)poly + (size_t)i * B, B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
-            HB_CHECK(ctx, cudaEventRecord(ev[i], ctx->copy_stream));
+        for (int g = 0; g < ngroups; g++) {
+            size_t c0 = (size_t)g * G, nc = std::min<size_t>(G, K - c0);
+            HB_CHECK(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+            HB_CHECK(ctx, cudaMemcpyAsync(ctx->poly + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
+            HB_CHECK(ctx, cudaEventRecord(ev[g], ctx->copy_stream));
         }
     }
     const F *src = on_dev ? (const F *)poly : ctx->poly;
-    for (int i = 0; i < K; i++) {
-        if (!on_dev) HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ev[i], 0));
-        HB_TRY(tensorcode_dev(ctx, src + (size_t)i * B, B, trs, linear_time, ctx->tensor + (size_t)i * 4 * B, lv.as<uint8_t>()));
+    for (int g = 0; g < ngroups; g++) {
+        size_t c0 = (size_t)g * G, nc = std::min<size_t>(G, K - c0);
+        if (!on_dev) HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ev[g], 0));
+        HB_TRY(tensorcode_dev(ctx, src + c0 * B, B, trs, linear_time, ctx->tensor + c0 * 4 * B, nc, inner));
+        HB_TRY(md_chain_dev(ctx, inner, nc, B, lv.as<uint8_t>()));
     }
+    cudaFreeAsync(inner, ctx->stream);
     HB_TRY(merkle_tree_dev(ctx, lv.as<uint8_t>(), B));
     HB_TRY(lv.finish());
     if (tensor_out) HB_CHECK(ctx, cudaMemcpyAsync(tensor_out, ctx->tensor, 4 * N * sizeof(F), cudaMemcpyDefault, ctx->stream));
@@ -355,7 +367,7 @@ extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) {
     HB_LAUNCH(ctx, any_nonzero_kernel, (unsigned)std::min<size_t>((B + 255) / 256, (size_t)ctx->sm_count * 4), 256, 0, src, B, el.nz_flag);
     HB_CHECK(ctx, cudaMemcpyAsync(&nz, el.nz_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (nz) HB_TRY(tensorcode_dev(ctx, src, B, el.trs, el.lin, T, nullptr));
+    if (nz) HB_TRY(tensorcode_dev(ctx, src, B, el.trs, el.lin, T, 1, nullptr));
     else HB_CHECK(ctx, cudaMemsetAsync(T, 0, 4 * B * sizeof(F), ctx->stream));
     if (slot == 3) HB_TRY(md_leaves_stream4_dev(ctx, el.park[0], el.park[1], el.park[2], el.tensor, 4 * B, el.leaves));
     el.chunk_idx++;

@@ -52,6 +52,7 @@ struct hb_ctx {
     int sm_count = hb::kSMs;
     // twiddle tables w[k] = omega_len^k, k < len/2, cached per log2(len)
     hb::F *tw[32] = {};
+    bool tw_j_neg[32] = {};             // omega_len^(len/4) == -i (else +i)
     hb::ExpanderDev exp;
     // resident tensor of the last commit_standard
     hb::F *tensor = nullptr; size_t tensor_elems = 0; size_t tensor_N = 0; int tensor_K = 0; int tensor_trs = 0;
@@ -142,16 +143,22 @@ inline int ilog2(size_t x) { int l = 0; while (x >>= 1) l++; return l; }
 int get_twiddles(hb_ctx *ctx, int logn, const F **out);
 int ntt_rows_dev(hb_ctx *ctx, F *data, int logn, size_t batch, size_t stride);
 // rows of `in_len` elements (row r at src + r*in_len) zero-extended to 2^logn and transformed into dst + r*dst_stride
-int ntt_rows_padded_dev(hb_ctx *ctx, const F *src, size_t in_len, F *dst, size_t dst_stride, int logn, size_t batch);
+// nchunks chunks of rows_per_chunk rows each; chunk c starts at src + c*src_chunk_stride / dst + c*dst_chunk_stride
+int ntt_rows_padded_dev(hb_ctx *ctx, const F *src, size_t in_len, F *dst, size_t dst_stride, int logn, size_t rows_per_chunk,
+                        size_t nchunks, size_t src_chunk_stride, size_t dst_chunk_stride);
 // column NTT of a (2^logn x cols) row-major matrix whose rows >= nz_rows are implicitly zero on input
 int ntt_cols_dev(hb_ctx *ctx, F *mat, int logn, size_t cols, size_t nz_rows);
-// expander-encode every column of T (rows [0,n) hold the messages); writes rows [n, 2n).
-// leaves != nullptr: fused Merkle–Damgård leaf update of commit_standard for these columns.
-int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, uint8_t *leaves);
-int md_leaves_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, uint8_t *leaves);
+// expander-encode every column of nchunks matrices T + c*chunk_stride (rows [0,n) hold the messages); writes rows [n, 2n).
+// inner != nullptr: also the inner leaf digests of commit_standard, chunk c at inner + c*(n/2*cols)*32.
+int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner);
+// inner digests H1(T[4j][k] | T[4j+1][k] | T[4j+2][k] | T[4j+3][k]) of nchunks matrices (rows x cols each)
+int md_inner_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner);
+// leaf[p] <- H1(inner[c][p] | leaf[p]) for c = 0..nchunks-1 in order (the Merkle–Damgård chain over chunks)
+int md_chain_dev(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);
 int md_leaves_stream4_dev(hb_ctx *ctx, const F *c0, const F *c1, const F *c2, const F *T, size_t cells, uint8_t *leaves);
 int blake3_64_dev(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count);
 int merkle_tree_dev(hb_ctx *ctx, uint8_t *levels, size_t nleaves);
-int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, uint8_t *leaves_standard);
+// nchunks messages of n elements (contiguous) -> nchunks tensors of 4n elements (contiguous); inner: see encode_cols_dev
+int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, size_t nchunks, uint8_t *inner);
 
 }  // namespace hb

@@ -11,28 +11,46 @@
 // the reference's scatter lists) so there are no atomics, and the 61x32-bit products are accumulated in 128 bits
 // and reduced once per target.  A quarter-warp reads one contiguous 16*CB-byte row -> conflict-free LDS.128.
 // The weights are 31-bit reals (expanders.h:37 `F weight = random()`), so F x weight is two 61x32 products.
-// The commit_standard leaf hashing (Our_PC.cpp:160-166) can be fused here: the CTA already holds every row of its
-// columns, so the 4-row quads are hashed straight out of shared memory and the tensor is never re-read.
+// The inner half of the commit_standard leaf hashing (Our_PC.cpp:160-166; H1 of each 4-row quad of a column) is fused
+// here: the CTA already holds every row of its columns, so the quads are hashed straight out of shared memory and the
+// tensor is never re-read.  The chunk-order-dependent half (H1(inner | previous leaf)) runs afterwards in
+// md_chain_kernel, which lets every chunk of a commit be encoded by ONE launch (grid.y = chunk) with no grid tail.
 #include "common.cuh"
 #include "blake3.cuh"
 #include <algorithm>
 
 namespace hb {
 
-struct Acc128 { u64 lo, hi; };
-__device__ __forceinline__ void acc_mul(Acc128 &a, u64 x, uint32_t w) {
-    u64 lo, hi; mul61x32_wide(x, w, lo, hi);
-    a.lo += lo; a.hi += hi + (a.lo < lo);
+// Sum of 61-bit x 32-bit products without carry chains through compares: the two 64-bit partial products
+// p0 = x.lo32 * w and p1 = x.hi32 * w (IMAD.WIDE, FMA pipe) are accumulated in two independent 96-bit accumulators
+// with add.cc/addc (3 IADD3 each, ALU pipe); value = U + V * 2^32.  Headroom: 2^32 terms.
+struct Acc { uint32_t u0, u1, u2, v0, v1, v2; };
+__device__ __forceinline__ void acc_mac(Acc &a, u64 x, uint32_t w) {
+    u64 p0 = (u64)(uint32_t)x * w, p1 = (u64)(uint32_t)(x >> 32) * w;
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(a.u0), "+r"(a.u1), "+r"(a.u2) : "r"((uint32_t)p0), "r"((uint32_t)(p0 >> 32)));
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(a.v0), "+r"(a.v1), "+r"(a.v2) : "r"((uint32_t)p1), "r"((uint32_t)(p1 >> 32)));
+}
+__device__ __forceinline__ u64 acc_reduce(const Acc &a) {
+    u64 u = red128(((u64)a.u1 << 32) | a.u0, a.u2);
+    u64 v = red128(((u64)a.v1 << 32) | a.v0, a.v2);
+    v = ((v << 32) & P61) | (v >> 29);                   // v * 2^32 mod p: rotate left by 32 inside 61 bits
+    return add61(u, v);
 }
 
-template <int CB, bool FUSE_LEAVES>
-__global__ void __launch_bounds__(512)
-encode_cols_kernel(F *__restrict__ T, size_t cols, int n, int cwlen,
+// grid: (cols / CB, nchunks).  inner != nullptr: also emit the inner leaf digests H1(T[4j][k] | .. | T[4j+3][k])
+// of this chunk (commit_standard hashes 4-row quads of every column, Our_PC.cpp:160-166); the Merkle–Damgård chaining
+// over chunks is done afterwards by md_chain_kernel so that all chunks can be encoded in one launch.
+template <int CB, bool INNER>
+__global__ void __launch_bounds__(1024)
+encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int n, int cwlen,
                    const EncStage *__restrict__ stages, int nstages,
                    const int *__restrict__ rowptr, const uint2 *__restrict__ edges,
-                   uint8_t *__restrict__ leaves) {
+                   uint8_t *__restrict__ inner_base, Digest zero_quad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *cw = reinterpret_cast<F *>(smem_raw);                   // cw[row * CB + c]
+    F *T = Tbase + (size_t)blockIdx.y * chunk_stride;
     const size_t col0 = (size_t)blockIdx.x * CB;
     const unsigned c = threadIdx.x % CB, t0 = threadIdx.x / CB, tstep = blockDim.x / CB;
 
@@ -44,15 +62,15 @@ encode_cols_kernel(F *__restrict__ T, size_t cols, int n, int cwlen,
         const int *rp = rowptr + st.rowptr_base;
         for (unsigned t = t0; t < (unsigned)st.R; t += tstep) {
             int e0 = __ldg(&rp[t]), e1 = __ldg(&rp[t + 1]);
-            Acc128 are = {0, 0}, aim = {0, 0};
+            Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
 #pragma unroll 4
             for (int e = e0; e < e1; e++) {
                 uint2 ed = __ldg(&edges[e]);
                 F x = cw[ed.x * CB + c];
-                acc_mul(are, x.re, ed.y);
-                acc_mul(aim, x.im, ed.y);
+                acc_mac(are, x.re, ed.y);
+                acc_mac(aim, x.im, ed.y);
             }
-            cw[(st.out_off + t) * CB + c] = mkF(red128(are.lo, are.hi), red128(aim.lo, aim.hi));
+            cw[(st.out_off + t) * CB + c] = mkF(acc_reduce(are), acc_reduce(aim));
         }
         __syncthreads();
     }
@@ -61,57 +79,70 @@ encode_cols_kernel(F *__restrict__ T, size_t cols, int n, int cwlen,
     for (unsigned r = n + t0; r < 2u * n; r += tstep)
         T[(size_t)r * cols + col0 + c] = (r < (unsigned)cwlen) ? cw[r * CB + c] : mkF(0, 0);
 
-    if (FUSE_LEAVES) {
-        // leaf (j, k) <- H1( H1(T[4j][k] | T[4j+1][k] | T[4j+2][k] | T[4j+3][k]) | leaf(j, k) ), j < n/2
+    if (INNER) {
+        uint8_t *inner = inner_base + (size_t)blockIdx.y * ((size_t)(n / 2) * cols) * 32;
         for (unsigned j = t0; j < (unsigned)n / 2; j += tstep) {
-            uint32_t m[16], prev[8], out[8];
+            uint32_t out[8];
+            if (4 * j >= (unsigned)cwlen) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                unsigned r = 4 * j + q;
-                F x = (r < (unsigned)cwlen) ? cw[r * CB + c] : mkF(0, 0);
-                m[4 * q] = (uint32_t)x.re; m[4 * q + 1] = (uint32_t)(x.re >> 32);
-                m[4 * q + 2] = (uint32_t)x.im; m[4 * q + 3] = (uint32_t)(x.im >> 32);
+                for (int q = 0; q < 8; q++) out[q] = zero_quad.w[q];       // H1(64 zero bytes), precomputed
+            } else {
+                uint32_t m[16];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    unsigned r = 4 * j + q;
+                    F x = (r < (unsigned)cwlen) ? cw[r * CB + c] : mkF(0, 0);
+                    m[4 * q] = (uint32_t)x.re; m[4 * q + 1] = (uint32_t)(x.re >> 32);
+                    m[4 * q + 2] = (uint32_t)x.im; m[4 * q + 3] = (uint32_t)(x.im >> 32);
+                }
+                blake3_compress64(m, out);
             }
-            uint4 *lp = reinterpret_cast<uint4 *>(leaves + ((size_t)j * cols + col0 + c) * 32);
-            uint4 p0 = lp[0], p1 = lp[1];
-            prev[0] = p0.x; prev[1] = p0.y; prev[2] = p0.z; prev[3] = p0.w;
-            prev[4] = p1.x; prev[5] = p1.y; prev[6] = p1.z; prev[7] = p1.w;
-            md_leaf(m, prev, out);
+            uint4 *lp = reinterpret_cast<uint4 *>(inner + ((size_t)j * cols + col0 + c) * 32);
             lp[0] = make_uint4(out[0], out[1], out[2], out[3]);
             lp[1] = make_uint4(out[4], out[5], out[6], out[7]);
         }
     }
 }
 
+// H1 of 64 zero bytes (blake3 KAT 4d006976...): the inner digest of every all-zero quad
+static Digest zero_quad_digest() {
+    static const uint8_t kat[32] = {0x4d, 0x00, 0x69, 0x76, 0x63, 0x6a, 0x86, 0x96, 0xd9, 0x09, 0xa6, 0x30, 0xa4, 0x08, 0x1a, 0xad,
+                                    0x4d, 0x7c, 0x50, 0xf8, 0x1a, 0xfd, 0xee, 0x04, 0x02, 0x0b, 0xf0, 0x50, 0x86, 0xab, 0x6a, 0x55};
+    Digest d; memcpy(d.w, kat, 32); return d;
+}
+
 template <int CB>
-static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, uint8_t *leaves) {
+static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner) {
     const ExpanderDev &ex = ctx->exp;
     size_t smem = (size_t)ex.cwlen * CB * sizeof(F);
-    unsigned grid = (unsigned)(cols / CB);
-    if (leaves) {
+    dim3 grid((unsigned)(cols / CB), (unsigned)nchunks);
+    // small codes: several CTAs per SM, 256 threads each; the big code (one 220 KB CTA per SM) gets 1024 threads
+    unsigned threads = smem > 100 * 1024 ? 1024 : 256;
+    if (inner) {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, 512, smem, T, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, leaves);
+        HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest());
     } else {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HB_LAUNCH(ctx, (encode_cols_kernel<CB, false>), grid, 512, smem, T, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, leaves);
+        HB_LAUNCH(ctx, (encode_cols_kernel<CB, false>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest());
     }
     return 0;
 }
 
-int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, uint8_t *leaves) {
+int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner) {
     const ExpanderDev &ex = ctx->exp;
     if (ex.n != n) HB_FAIL(ctx, "encode: no expander installed for this message length (call hb_expander_set / expander_init_store first)");
+    if (nchunks > 65535) HB_FAIL(ctx, "encode: too many chunks in one launch");
     const size_t kMaxSmem = 227 * 1024;
     size_t per_col = (size_t)ex.cwlen * sizeof(F);
     // widest column block that fits; prefer <= ~100 KB tiles when the code is small so several CTAs share an SM
-    if (cols % 32 == 0 && per_col * 32 <= 100 * 1024) return launch_encode<32>(ctx, T, n, cols, leaves);
-    if (cols % 16 == 0 && per_col * 16 <= 100 * 1024) return launch_encode<16>(ctx, T, n, cols, leaves);
-    if (cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, leaves);
-    if (cols % 4 == 0 && per_col * 4 <= kMaxSmem) return launch_encode<4>(ctx, T, n, cols, leaves);
-    if (cols % 2 == 0 && per_col * 2 <= kMaxSmem) return launch_encode<2>(ctx, T, n, cols, leaves);
-    if (per_col <= kMaxSmem) return launch_encode<1>(ctx, T, n, cols, leaves);
+    if (cols % 32 == 0 && per_col * 32 <= 100 * 1024) return launch_encode<32>(ctx, T, n, cols, nchunks, chunk_stride, inner);
+    if (cols % 16 == 0 && per_col * 16 <= 100 * 1024) return launch_encode<16>(ctx, T, n, cols, nchunks, chunk_stride, inner);
+    if (cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, nchunks, chunk_stride, inner);
+    if (cols % 4 == 0 && per_col * 4 <= kMaxSmem) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner);
+    if (cols % 2 == 0 && per_col * 2 <= kMaxSmem) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner);
+    if (per_col <= kMaxSmem) return launch_encode<1>(ctx, T, n, cols, nchunks, chunk_stride, inner);
     HB_FAIL(ctx, "encode: codeword does not fit in shared memory (message length too large for the column kernel)");
 }
 
@@ -187,7 +218,7 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_F *src, hb_F *dst, long lon
         // base case of the recursion: the codeword is the message (linear_code_encode.h:73-78)
         HB_CHECK(ctx, cudaMemsetAsync(d.as<F>() + (size_t)n * ncols, 0, (size_t)n * ncols * sizeof(F), ctx->stream));
     } else {
-        HB_TRY(encode_cols_dev(ctx, d.as<F>(), n, ncols, nullptr));
+        HB_TRY(encode_cols_dev(ctx, d.as<F>(), n, ncols, 1, 0, nullptr));
     }
     HB_TRY(d.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

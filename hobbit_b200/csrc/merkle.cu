@@ -36,17 +36,35 @@ __global__ void __launch_bounds__(256) blake3_64_kernel(const uint8_t *__restric
     store_digest(dst + i * 32, out);
 }
 
-// commit_standard leaves (Our_PC.cpp:160-166): leaf[j*cols+k] <- H2(T[4j][k],T[4j+1][k],T[4j+2][k],T[4j+3][k], leaf[j*cols+k])
-__global__ void __launch_bounds__(256) md_leaves_standard_kernel(const F *__restrict__ T, size_t rows, size_t cols, uint8_t *__restrict__ leaves) {
+// commit_standard leaves (Our_PC.cpp:160-166): leaf[j*cols+k] <- H1( H1(T[4j][k]|T[4j+1][k]|T[4j+2][k]|T[4j+3][k]) | leaf[j*cols+k] ),
+// chained over the chunks in order.  Split in two kernels: the inner digests of all chunks are independent ...
+__global__ void __launch_bounds__(256) md_inner_standard_kernel(const F *__restrict__ Tbase, size_t chunk_stride, size_t rows, size_t cols,
+                                                                uint8_t *__restrict__ inner_base) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (rows / 4) * cols) return;
+    size_t nl = (rows / 4) * cols;
+    if (i >= nl) return;
+    const F *T = Tbase + (size_t)blockIdx.y * chunk_stride;
     size_t j = i / cols, k = i % cols;
-    uint32_t m[16], prev[8], out[8];
+    uint32_t m[16], out[8];
 #pragma unroll
     for (int q = 0; q < 4; q++) cell_words(T[(4 * j + q) * cols + k], m + 4 * q);
-    load_digest(leaves + i * 32, prev);
-    md_leaf(m, prev, out);
-    store_digest(leaves + i * 32, out);
+    blake3_compress64(m, out);
+    store_digest(inner_base + ((size_t)blockIdx.y * nl + i) * 32, out);
+}
+// ... and only the outer compression is sequential in the chunk index (one thread walks one leaf position).
+__global__ void __launch_bounds__(256) md_chain_kernel(const uint8_t *__restrict__ inner, size_t nchunks, size_t nleaves, uint8_t *__restrict__ leaves) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nleaves) return;
+    uint32_t m[16], h[8];
+    load_digest(leaves + p * 32, h);
+    for (size_t c = 0; c < nchunks; c++) {
+        uint32_t in[8];
+        load_digest(inner + (c * nleaves + p) * 32, in);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { m[k] = in[k]; m[8 + k] = h[k]; }
+        blake3_compress64(m, h);
+    }
+    store_digest(leaves + p * 32, h);
 }
 
 // Elastic commit leaves (Elastic_PC.cpp:230-239).  The reference passes
@@ -128,9 +146,13 @@ int blake3_64_dev(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count) {
     if (count) HB_LAUNCH(ctx, blake3_64_kernel, blocks_for(count, 256), 256, 0, src, dst, count);
     return 0;
 }
-int md_leaves_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, uint8_t *leaves) {
+int md_inner_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner) {
     size_t n = (rows / 4) * cols;
-    if (n) HB_LAUNCH(ctx, md_leaves_standard_kernel, blocks_for(n, 256), 256, 0, T, rows, cols, leaves);
+    if (n && nchunks) HB_LAUNCH(ctx, md_inner_standard_kernel, dim3(blocks_for(n, 256), (unsigned)nchunks), 256, 0, T, chunk_stride, rows, cols, inner);
+    return 0;
+}
+int md_chain_dev(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves) {
+    if (nleaves && nchunks) HB_LAUNCH(ctx, md_chain_kernel, blocks_for(nleaves, 256), 256, 0, inner, nchunks, nleaves, leaves);
     return 0;
 }
 int md_leaves_stream4_dev(hb_ctx *ctx, const F *c0, const F *c1, const F *c2, const F *T, size_t cells, uint8_t *leaves) {

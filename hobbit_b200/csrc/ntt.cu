@@ -16,59 +16,98 @@ namespace hb {
 static constexpr int kLogTile = 12;             // 4096 elements * 16 B = 64 KB of shared memory
 
 // ---------------------------------------------------------------------------------------------------------
-// twiddles: computed once per length on the host with the same repeated multiplication as the reference
+// twiddles: the FULL period w[k] = omega^k, k < len (the radix-4 passes index up to 3*len/4), computed once per length
+// on the host with the same repeated multiplication as the reference
 int get_twiddles(hb_ctx *ctx, int logn, const F **out) {
-    if (logn < 1 || logn > 31) HB_FAIL(ctx, "get_twiddles: logn out of range");
+    if (logn < 1 || logn > 28) HB_FAIL(ctx, "get_twiddles: logn out of range");
     if (!ctx->tw[logn]) {
-        size_t half = (size_t)1 << (logn - 1);
-        std::vector<F> w(half);
+        size_t len = (size_t)1 << logn;
+        std::vector<F> w(len);
         hb_F rou; hb_root_of_unity(logn, &rou);
         F w1 = mkF(rou.real, rou.img);
         w[0] = mkF(1, 0);
-        for (size_t i = 1; i < half; i++) w[i] = h_fmul(w[i - 1], w1);
-        HB_CHECK(ctx, cudaMalloc(&ctx->tw[logn], half * sizeof(F)));
-        HB_CHECK(ctx, cudaMemcpyAsync(ctx->tw[logn], w.data(), half * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+        for (size_t i = 1; i < len; i++) w[i] = h_fmul(w[i - 1], w1);
+        HB_CHECK(ctx, cudaMalloc(&ctx->tw[logn], len * sizeof(F)));
+        HB_CHECK(ctx, cudaMemcpyAsync(ctx->tw[logn], w.data(), len * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
         HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // w is a local
+        // omega^(len/4) is a primitive 4th root of unity, i.e. +i or -i in F_p[i]: multiplying by it is a limb swap
+        if (logn >= 2) {
+            F j = w[len / 4];
+            if (j.re != 0 || (j.im != 1 && j.im != P61 - 1)) HB_FAIL(ctx, "get_twiddles: omega^(len/4) is not +-i");
+            ctx->tw_j_neg[logn] = (j.im != 1);
+        }
     }
     *out = ctx->tw[logn];
     return 0;
 }
 
+__device__ __forceinline__ F mul_j(F x, bool neg) {            // x * (+i) = (-im, re) ; x * (-i) = (im, -re)
+    return neg ? mkF(x.im, x.re ? P61 - x.re : 0) : mkF(x.im ? P61 - x.im : 0, x.re);
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// Tile kernel: stages 1..lb of a length-2^logn transform on positions [tile*2^lb, (tile+1)*2^lb) of row `r`.
+// Tile kernel: stages 1..lb of a length-2^logn transform on positions [tile*2^lb, (tile+1)*2^lb) of one row.
 // Loads src[rev(p)] (zero if rev(p) >= in_len), writes dst[p].  src may alias dst only when lb == logn
 // (then the CTA reads its whole row before it writes anything).
+//  * rows are grouped in chunks: row r -> chunk r / rows_per_chunk; chunk strides are given separately so that all
+//    chunks of a commit go through ONE launch (no per-chunk grid tail).
+//  * zero-extended input (in_len == len/2, the RS encoding of a message row): every odd bit-reversed position is
+//    zero, so stage 1 is a plain duplication and is done while loading.
+//  * stages are taken two at a time (radix-4): with X1 = x1*w1, X2 = x2*w2, X3 = x3*(w1*w2) and J = omega^(len/4) = +-i
+//        out0 = (x0+X1) + (X2+X3),  out2 = (x0+X1) - (X2+X3),  out1 = (x0-X1) + J(X2-X3),  out3 = (x0-X1) - J(X2-X3)
+//    i.e. 3 multiplications per 4 outputs per 2 stages instead of 4, and half the shared-memory round trips.
 __global__ void __launch_bounds__(512)
-ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t in_len, F *__restrict__ dst, size_t dst_stride,
-                int logn, int lb, const F *__restrict__ tw) {
+ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_stride, size_t in_len,
+                F *__restrict__ dst, size_t dst_stride, size_t dst_chunk_stride, unsigned rows_per_chunk,
+                int logn, int lb, const F *__restrict__ tw, bool j_neg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *s = reinterpret_cast<F *>(smem_raw);
     const unsigned tiles_per_row = 1u << (logn - lb);
     const size_t row = blockIdx.x / tiles_per_row;
     const unsigned tile = blockIdx.x % tiles_per_row;
     const unsigned tlen = 1u << lb, base = tile << lb;
-    const F *in = src + row * src_stride;
-    F *out = dst + row * dst_stride;
+    const size_t chunk = row / rows_per_chunk, rr = row % rows_per_chunk;
+    const F *in = src + chunk * src_chunk_stride + rr * src_stride;
+    F *out = dst + chunk * dst_chunk_stride + rr * dst_stride;
+    const unsigned len = 1u << logn;
 
-    for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) {
-        unsigned p = base + i;
-        unsigned q = __brev(p) >> (32 - logn);
-        s[i] = (q < in_len) ? in[q] : mkF(0, 0);
+    int st = 1;
+    if (in_len * 2 == len && lb >= 1) {
+        for (unsigned i = threadIdx.x; i < (tlen >> 1); i += blockDim.x) {
+            unsigned p = base + 2 * i;
+            F v = in[__brev(p) >> (32 - logn)];
+            s[2 * i] = v; s[2 * i + 1] = v;
+        }
+        st = 2;
+    } else {
+        for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) {
+            unsigned q = __brev(base + i) >> (32 - logn);
+            s[i] = (q < in_len) ? in[q] : mkF(0, 0);
+        }
     }
     __syncthreads();
-    const unsigned len_half_stride = 1u << logn;      // twiddle index = (len >> st) * k
-    for (int st = 1; st <= lb; st++) {
-        const unsigned half = 1u << (st - 1);
-        const unsigned tws = len_half_stride >> st;
+    for (; st + 1 <= lb; st += 2) {                       // radix-4 pass: stages st and st+1
+        const unsigned h = 1u << (st - 1);
+        const unsigned tws2 = len >> (st + 1);            // twiddle stride of stage st+1; stage st uses 2*tws2
+        for (unsigned q = threadIdx.x; q < (tlen >> 2); q += blockDim.x) {
+            unsigned k = q & (h - 1);
+            unsigned p0 = ((q >> (st - 1)) << (st + 1)) + k;
+            F x0 = s[p0], x1 = s[p0 + h], x2 = s[p0 + 2 * h], x3 = s[p0 + 3 * h];
+            size_t e = (size_t)tws2 * k;
+            F X1 = fmul(x1, ldgF(&tw[2 * e])), X2 = fmul(x2, ldgF(&tw[e])), X3 = fmul(x3, ldgF(&tw[3 * e]));
+            F a0 = fadd(x0, X1), a1 = fsub(x0, X1), b = fadd(X2, X3), c = mul_j(fsub(X2, X3), j_neg);
+            s[p0] = fadd(a0, b); s[p0 + 2 * h] = fsub(a0, b);
+            s[p0 + h] = fadd(a1, c); s[p0 + 3 * h] = fsub(a1, c);
+        }
+        __syncthreads();
+    }
+    if (st <= lb) {                                       // one radix-2 stage left
+        const unsigned half = 1u << (st - 1), tws = len >> st;
         for (unsigned b = threadIdx.x; b < (tlen >> 1); b += blockDim.x) {
             unsigned k = b & (half - 1);
-            unsigned j = (b >> (st - 1)) << st;
-            unsigned p0 = j + k, p1 = p0 + half;
-            F u = s[p0];
-            F x = s[p1];
-            F v = (k == 0) ? x : fmul(x, ldgF(&tw[(size_t)tws * k]));
-            s[p0] = fadd(u, v);
-            s[p1] = fsub(u, v);
+            unsigned p0 = ((b >> (st - 1)) << st) + k, p1 = p0 + half;
+            F u = s[p0], v = fmul(s[p1], ldgF(&tw[(size_t)tws * k]));
+            s[p0] = fadd(u, v); s[p1] = fsub(u, v);
         }
         __syncthreads();
     }
@@ -110,7 +149,8 @@ ntt_global_kernel(F *__restrict__ data, size_t stride, int logn, int s_lo, const
 }
 
 static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in_len, F *dst, size_t dst_stride,
-                         int logn, size_t batch) {
+                         int logn, size_t batch, size_t rows_per_chunk = 0, size_t src_chunk_stride = 0, size_t dst_chunk_stride = 0) {
+    if (rows_per_chunk == 0) { rows_per_chunk = batch ? batch : 1; }
     if (batch == 0) return 0;
     if (logn == 0) {
         if (src != dst) HB_CHECK(ctx, cudaMemcpy2DAsync(dst, dst_stride * sizeof(F), src, src_stride * sizeof(F), sizeof(F), batch,
@@ -126,11 +166,13 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
         HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
         attr_set = true;
     }
-    unsigned threads = 1u << (lb > 1 ? lb - 1 : 0);
+    unsigned threads = 1u << (lb > 2 ? lb - 2 : 0);          // one radix-4 butterfly per thread up to 512 threads
     if (threads > 512) threads = 512;
     if (threads < 32) threads = 32;
     size_t grid = batch << (logn - lb);
-    HB_LAUNCH(ctx, ntt_tile_kernel, (unsigned)grid, threads, smem, src, src_stride, in_len, dst, dst_stride, logn, lb, tw);
+    if (rows_per_chunk != batch && lb != logn) HB_FAIL(ctx, "ntt: chunked launch supports transforms up to one tile");
+    HB_LAUNCH(ctx, ntt_tile_kernel, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
+              (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn]);
     int s_lo = lb;
     while (s_lo < logn) {
         int cnt = logn - s_lo; if (cnt > 3) cnt = 3;
@@ -155,8 +197,14 @@ int ntt_rows_dev(hb_ctx *ctx, F *data, int logn, size_t batch, size_t stride) {
     return r;
 }
 
-int ntt_rows_padded_dev(hb_ctx *ctx, const F *src, size_t in_len, F *dst, size_t dst_stride, int logn, size_t batch) {
-    return ntt_rows_impl(ctx, src, in_len, in_len, dst, dst_stride, logn, batch);
+int ntt_rows_padded_dev(hb_ctx *ctx, const F *src, size_t in_len, F *dst, size_t dst_stride, int logn, size_t rows_per_chunk,
+                        size_t nchunks, size_t src_chunk_stride, size_t dst_chunk_stride) {
+    if (nchunks > 1 && logn > kLogTile) {       // long rows: one chunk per launch (the global passes address one matrix)
+        for (size_t c = 0; c < nchunks; c++)
+            HB_TRY(ntt_rows_impl(ctx, src + c * src_chunk_stride, in_len, in_len, dst + c * dst_chunk_stride, dst_stride, logn, rows_per_chunk));
+        return 0;
+    }
+    return ntt_rows_impl(ctx, src, in_len, in_len, dst, dst_stride, logn, rows_per_chunk * nchunks, rows_per_chunk, src_chunk_stride, dst_chunk_stride);
 }
 
 // ---------------------------------------------------------------------------------------------------------
