@@ -45,6 +45,14 @@ def build_library(force=False, verbose=False):
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode:
             raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))
+    # host-side C++ mirror of the reference API (plain g++, links against the C ABI)
+    host_src = os.path.join(HERE, "host", "hobbit_host.cpp")
+    host_lib = os.path.join(HERE, "libhobbit_host.so")
+    if force or _newer(host_src, host_lib) or _newer(os.path.join(HERE, "host", "hobbit_host.hpp"), host_lib) or _newer(LIB, host_lib):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", host_lib, host_src, "-L" + HERE, "-lhobbit_b200", "-Wl,-rpath,$ORIGIN"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode:
+            raise RuntimeError("host library build failed:\n%s\n%s" % (p.stdout, p.stderr))
     return LIB, log
 
 

@@ -1,0 +1,296 @@
+// See hobbit_host.hpp.  Host-side control code only: libc RNG call order, container marshalling, Fiat–Shamir scalars.
+// All table/tensor arithmetic happens on the GPU through the C ABI.
+#include "hobbit_host.hpp"
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace hobbit {
+
+static const unsigned long long P = 2305843009213693951ULL;
+int tensor_row_size = 128;
+size_t BUFFER_SPACE = 0;
+bool linear_time = false;
+bool materialize_tensor = false;
+
+static hb_ctx *g_ctx = nullptr;
+[[noreturn]] static void die(const char *what) {
+    printf("hobbit_b200: %s: %s\n", what, g_ctx ? hb_last_error(g_ctx) : "no context");
+    exit(-1);                                                   // the reference's error convention
+}
+#define CK(call) do { if (call) die(#call); } while (0)
+
+void init_backend(int device) {
+    if (g_ctx) return;
+    if (hb_ctx_create(&g_ctx, device)) { printf("hobbit_b200: no CUDA device (there is no CPU fallback)\n"); exit(-1); }
+}
+hb_ctx *backend() { if (!g_ctx) init_backend(0); return g_ctx; }
+
+// ---- F (host scalars only: challenges, a handful of coefficients) -----------------------------------------
+static inline unsigned long long mulm(unsigned long long a, unsigned long long b) {
+    unsigned __int128 x = (unsigned __int128)a * b;
+    unsigned long long lo = (unsigned long long)x & P, hi = (unsigned long long)(x >> 61);
+    unsigned long long s = lo + (hi & P) + (hi >> 61);
+    s = (s & P) + (s >> 61);
+    return s >= P ? s - P : s;
+}
+F F::operator+(const F &o) const { F r; r.real = real + o.real; if (r.real >= P) r.real -= P; r.img = img + o.img; if (r.img >= P) r.img -= P; return r; }
+F F::operator-(const F &o) const { F r; r.real = real >= o.real ? real - o.real : real + P - o.real; r.img = img >= o.img ? img - o.img : img + P - o.img; return r; }
+F F::operator-() const { return F(0) - *this; }
+F F::operator*(const F &o) const {
+    unsigned long long ac = mulm(real, o.real), bd = mulm(img, o.img), ad = mulm(real, o.img), bc = mulm(img, o.real);
+    F r; r.real = ac >= bd ? ac - bd : ac + P - bd; r.img = ad + bc; if (r.img >= P) r.img -= P; return r;
+}
+
+// utils.cpp:873-883 — same libc calls in the same order
+std::vector<F> generate_randomness(int size) {
+    std::vector<F> x; F c;
+    for (int i = 0; i < size; i++) {
+        if (i % 100 == 0) c = F(random());
+        x.push_back(c + F(rand()));
+    }
+    return x;
+}
+
+// expanders.h:20-47,78-92 — graphs drawn with rand() (target) then random() (weight), C_dep before the recursion,
+// D_dep after it; then uploaded in one call.
+namespace { struct Graph { long long L = 0, R = 0; std::vector<uint32_t> nbr; std::vector<uint64_t> w; }; Graph gC[100], gD[100]; }
+static const double kAlpha = 0.211, kR = 1.72; static const int kCn = 9, kDn = 12, kThreshold = (int)(1.0 / 0.07) - 1;
+static void gen(Graph &g, long long L, long long R, int d) {
+    g.L = L; g.R = R; g.nbr.resize(L * d); g.w.resize(L * d);
+    for (long long i = 0; i < L; i++) for (int j = 0; j < d; j++) { g.nbr[i * d + j] = (uint32_t)(rand() % R); g.w[i * d + j] = (uint64_t)random(); }
+}
+static long long init_rec(long long n, int dep, int &levels) {
+    if (n <= kThreshold) return n;
+    levels = dep + 1 > levels ? dep + 1 : levels;
+    gen(gC[dep], n, (long long)(kAlpha * n), kCn);
+    long long L = init_rec((long long)(kAlpha * n), dep + 1, levels);
+    gen(gD[dep], L, (long long)(n * (kR - 1) - L), kDn);
+    return n + L + (long long)(n * (kR - 1) - L);
+}
+long long expander_init_store(long long n, int dep) {
+    int levels = 0;
+    long long cw = init_rec(n, dep, levels);
+    long long LC[100], RC[100], LD[100], RD[100]; const uint32_t *nC[100], *nD[100]; const uint64_t *wC[100], *wD[100];
+    for (int d = 0; d < levels; d++) {
+        LC[d] = gC[d].L; RC[d] = gC[d].R; nC[d] = gC[d].nbr.data(); wC[d] = gC[d].w.data();
+        LD[d] = gD[d].L; RD[d] = gD[d].R; nD[d] = gD[d].nbr.data(); wD[d] = gD[d].w.data();
+    }
+    CK(hb_expander_set(backend(), n, levels, kCn, kDn, LC, RC, nC, wC, LD, RD, nD, wD));
+    return cw;
+}
+
+F mimc_hash(F input, F k) { F o; hb_mimc_hash((const hb_F *)&input, (const hb_F *)&k, (hb_F *)&o); return o; }
+void precompute_beta(std::vector<F> r, std::vector<F> &B) {
+    B.resize((size_t)1 << r.size());
+    CK(hb_precompute_beta(backend(), (const hb_F *)r.data(), (int)r.size(), (hb_F *)B.data()));
+}
+F evaluate_vector(std::vector<F> v, std::vector<F> r) {
+    F o; r.resize((size_t)std::log2((double)v.size()));
+    CK(hb_evaluate_vector(backend(), (const hb_F *)v.data(), v.size(), (const hb_F *)r.data(), (hb_F *)&o));
+    return o;
+}
+void _fft(F *arr, int logn, bool flag) {
+    if (flag) { printf("hobbit_b200: inverse _fft is not on the GPU path\n"); exit(-1); }
+    CK(hb_ntt_batch(backend(), (hb_F *)arr, logn, 1, (size_t)1 << logn));
+}
+
+// ---- Merkle ------------------------------------------------------------------------------------------------
+static void flat_to_levels(const std::vector<uint8_t> &flat, size_t nleaves, std::vector<std::vector<_hash>> &hashes) {
+    int lv = 0; size_t off = 0;
+    for (size_t n = nleaves; n >= 1; n /= 2, lv++) {
+        if ((int)hashes.size() <= lv) hashes.resize(lv + 1);
+        hashes[lv].resize(n);
+        memcpy(hashes[lv].data(), flat.data() + off * 32, n * 32);
+        off += n;
+        if (n == 1) break;
+    }
+}
+namespace merkle_tree { namespace merkle_tree_prover {
+void MT_commit_Blake(F *leafs, std::vector<std::vector<_hash>> &hashes, int N) {
+    std::vector<uint8_t> flat((2 * (size_t)(N / 4) - 1) * 32);
+    CK(hb_mt_commit(backend(), (const hb_F *)leafs, (size_t)N, flat.data()));
+    flat_to_levels(flat, N / 4, hashes);
+}
+void create_tree_blake(int ele_num, std::vector<std::vector<_hash>> &hashes, const int, bool) {
+    std::vector<uint8_t> flat((2 * (size_t)ele_num - 1) * 32);
+    memcpy(flat.data(), hashes[0].data(), (size_t)ele_num * 32);
+    CK(hb_merkle_tree(backend(), flat.data(), (size_t)ele_num));
+    flat_to_levels(flat, ele_num, hashes);
+}
+std::vector<_hash> open_tree_blake(std::vector<std::vector<_hash>> &MT_hashes, std::vector<size_t> c, int collumns) {   // merkle_tree.cpp:308-324
+    int pos = (int)((c[1] / 4) * collumns + c[0]);
+    if (pos >= (int)MT_hashes[0].size()) { printf("Error %d,%d\n", pos, (int)MT_hashes[0].size()); exit(-1); }
+    std::vector<_hash> path;
+    for (size_t i = 0; i + 1 < MT_hashes.size(); i++) {
+        if ((size_t)(2 * (pos / 2) + (1 - (pos % 2))) >= MT_hashes[i].size()) { printf("Error in open %d %d,%d\n", pos ^ 1, (int)i, (int)MT_hashes[i].size()); exit(-1); }
+        path.push_back(MT_hashes[i][2 * (pos / 2) + (1 - (pos % 2))]);
+        pos = pos / 2;
+    }
+    return path;
+}
+} }
+
+// ---- Our_PC --------------------------------------------------------------------------------------------------
+void commit_standard(std::vector<F> &poly, _hash &, std::vector<std::vector<_hash>> &MT_hashes,
+                     std::vector<std::vector<std::vector<F>>> &_tensor, int K) {
+    int B = (int)(poly.size() / K);
+    std::vector<uint8_t> flat((2 * (size_t)B - 1) * 32);
+    std::vector<F> tflat;
+    if (materialize_tensor) tflat.resize(4 * poly.size());
+    CK(hb_commit_standard(backend(), (const hb_F *)poly.data(), poly.size(), K, tensor_row_size, linear_time ? 1 : 0, flat.data(),
+                          materialize_tensor ? (hb_F *)tflat.data() : nullptr));
+    MT_hashes.clear();
+    flat_to_levels(flat, B, MT_hashes);
+    _tensor.resize(K);
+    if (materialize_tensor) {
+        size_t rows = 2 * (size_t)tensor_row_size, cols = 2 * (size_t)B / tensor_row_size;
+        for (int i = 0; i < K; i++) {
+            _tensor[i].resize(rows);
+            for (size_t r = 0; r < rows; r++) _tensor[i][r].assign(tflat.begin() + ((size_t)i * rows + r) * cols, tflat.begin() + ((size_t)i * rows + r + 1) * cols);
+        }
+    }
+}
+
+open_front open_standard_front(std::vector<F> &poly, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, int K) {
+    open_front o;
+    BUFFER_SPACE = poly.size() / K;
+    int queries = linear_time ? 5900 : 790;                                     // Our_PC.cpp:609-612
+    std::vector<F> x1;
+    for (int i = 0; i < (int)std::log2((double)(poly.size() / BUFFER_SPACE)); i++) x1.push_back(x[i]);
+    precompute_beta(x1, o.beta);
+    o.r_v0 = generate_randomness(1)[0];                                         // :625 (the powers r_v are unused downstream)
+    o.aggr_vector.resize(BUFFER_SPACE);
+    CK(hb_aggregate(backend(), (const hb_F *)poly.data(), poly.size(), K, (const hb_F *)o.beta.data(), (hb_F *)o.aggr_vector.data()));
+    o.I.resize(queries);
+    std::vector<uint32_t> col(queries), row(queries);
+    for (int i = 0; i < queries; i++) {                                         // :633-638, two rand() per query in this order
+        o.I[i].push_back(rand() % (2 * BUFFER_SPACE / tensor_row_size));
+        o.I[i].push_back(rand() % (2 * tensor_row_size));
+        col[i] = (uint32_t)o.I[i][0]; row[i] = (uint32_t)o.I[i][1];
+    }
+    std::vector<F> rep((size_t)queries * K);
+    CK(hb_tensor_gather(backend(), col.data(), row.data(), queries, (hb_F *)rep.data()));
+    o.reply.resize(queries);
+    for (int q = 0; q < queries; q++) o.reply[q].assign(rep.begin() + (size_t)q * K, rep.begin() + (size_t)(q + 1) * K);
+    for (int i = 0; i < queries; i++)
+        o.commitment_paths.push_back(merkle_tree::merkle_tree_prover::open_tree_blake(Commitment_MT, o.I[i], (int)(2 * BUFFER_SPACE / tensor_row_size)));
+    o.ps += (double)(o.reply.size() * o.reply[0].size() * sizeof(F)) / 1024.0;  // :650
+    return o;
+}
+
+// ---- Elastic_PC ------------------------------------------------------------------------------------------------
+void init_commitment(bool mod) {                                                // Elastic_PC.cpp:728-734
+    linear_time = mod;
+    tensor_row_size = (int)(BUFFER_SPACE / (1ULL << 11));
+    if (tensor_row_size == 0) tensor_row_size = 16;
+}
+void read_stream_PC(stream_descriptor &fd, F *v, int size) {                    // witness_stream.cpp:2356-2412, default branch only
+    if (fd.name == "PC_layer" || fd.name == "witness" || fd.name == "circuit") {
+        printf("hobbit_b200: stream '%s' needs the circuit evaluator (out of scope this round)\n", fd.name.c_str()); exit(-1);
+    }
+    CK(hb_stream_pc_test(backend(), (hb_F *)v, (size_t)size));
+}
+void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_hashes) {
+    if (fd.size / BUFFER_SPACE < 4) printf("Decrease buffer size %d\n", (int)(fd.size / BUFFER_SPACE));
+    std::vector<F> buff(BUFFER_SPACE);
+    CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
+    for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++) {
+        read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
+        CK(hb_elastic_push(backend(), (const hb_F *)buff.data()));
+    }
+    std::vector<uint8_t> flat((8 * BUFFER_SPACE - 1) * 32);
+    CK(hb_elastic_finish(backend(), flat.data()));
+    MT_hashes.clear();
+    flat_to_levels(flat, 4 * BUFFER_SPACE, MT_hashes);
+}
+
+// ---- sumcheck.h ------------------------------------------------------------------------------------------------
+proof generate_2product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, F previous_r, double &, double &ps) {
+    int rounds = (int)std::log2((double)v1.size());
+    std::vector<F> out(4 * rounds + 3);
+    CK(hb_sumcheck2(backend(), (const hb_F *)v1.data(), (const hb_F *)v2.data(), v1.size(), (const hb_F *)&previous_r, (hb_F *)out.data(), &ps));
+    proof P; P.randomness.resize(1);
+    for (int i = 0; i < rounds; i++) { P.q_poly.push_back({out[3 * i], out[3 * i + 1], out[3 * i + 2]}); P.randomness[0].push_back(out[3 * rounds + i]); }
+    P.vr = {out[4 * rounds], out[4 * rounds + 1]}; P.final_rand = out[4 * rounds + 2];
+    return P;
+}
+static proof unpack3(const std::vector<F> &out, int rounds, int nvr, bool has_final) {
+    proof P; P.randomness.resize(1);
+    for (int i = 0; i < rounds; i++) { P.c_poly.push_back({out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]}); P.randomness[0].push_back(out[4 * rounds + i]); }
+    for (int i = 0; i < nvr; i++) P.vr.push_back(out[5 * rounds + i]);
+    if (has_final) P.final_rand = out[5 * rounds + nvr];
+    return P;
+}
+proof _generate_3product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, std::vector<F> &v3, F previous_r, double &, double &ps) {
+    int rounds = (int)std::log2((double)v1.size());
+    std::vector<F> out(5 * rounds + 4);
+    CK(hb_sumcheck3(backend(), (const hb_F *)v1.data(), (const hb_F *)v2.data(), (const hb_F *)v3.data(), v1.size(), (const hb_F *)&previous_r, (hb_F *)out.data(), &ps));
+    // the reference folds v1..v3 in place; callers only rely on element 0 afterwards (= vr)
+    proof P = unpack3(out, rounds, 3, true);
+    if (!v1.empty()) { v1[0] = P.vr[0]; v2[0] = P.vr[1]; v3[0] = P.vr[2]; }
+    return P;
+}
+proof batch_3product_sumcheck(std::vector<std::vector<F>> &arr1, std::vector<std::vector<F>> &arr2, std::vector<std::vector<F>> &arr3,
+                              std::vector<F> a, double &, double &ps) {
+    std::vector<size_t> sizes; std::vector<F> t1, t2, t3; size_t L = 0;
+    for (size_t b = 0; b < arr1.size(); b++) {
+        sizes.push_back(arr1[b].size()); L = arr1[b].size() > L ? arr1[b].size() : L;
+        t1.insert(t1.end(), arr1[b].begin(), arr1[b].end()); t2.insert(t2.end(), arr2[b].begin(), arr2[b].end()); t3.insert(t3.end(), arr3[b].begin(), arr3[b].end());
+    }
+    int rounds = (int)std::log2((double)L), nb = (int)a.size();
+    std::vector<F> out(5 * rounds + 3 * nb);
+    CK(hb_batch_sumcheck3(backend(), (const hb_F *)t1.data(), (const hb_F *)t2.data(), (const hb_F *)t3.data(), sizes.data(), nb, (const hb_F *)a.data(), (hb_F *)out.data(), &ps));
+    return unpack3(out, rounds, 3 * nb, false);
+}
+mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input, F previous_r, std::vector<F> prev_x, double &, double &ps) {
+    int vectors = (int)input.size();
+    size_t size = input[0].size();
+    for (auto &v : input) if (v.size() != size) { printf("Error in mul tree sumcheck, no equal size vectors\n"); exit(-1); }
+    int depth = (int)std::log2((double)size);                                    // sumcheck.cpp:48-64: pad sizes / vector count
+    if (((size_t)1 << depth) != size) { depth++; size = (size_t)1 << depth; for (auto &v : input) v.resize(size, F(1)); }
+    if (vectors != 1 << ((int)std::log2((double)vectors))) {
+        int nv = 1 << ((int)std::log2((double)vectors) + 1);
+        for (int i = vectors; i < nv; i++) input.push_back(std::vector<F>(size, F(0)));
+        vectors = nv;
+    }
+    std::vector<F> flat; flat.reserve(vectors * size);
+    for (auto &v : input) flat.insert(flat.end(), v.begin(), v.end());
+    std::vector<F> xr;
+    if (vectors > 1) xr = prev_x.empty() ? generate_randomness((int)std::log2((double)vectors)) : prev_x;
+    if (vectors > 1 && !prev_x.empty()) { printf("hobbit_b200: prove_multiplication_tree_new with prev_x is not wired yet\n"); exit(-1); }
+    int maxr = (int)std::log2((double)flat.size());
+    std::vector<F> out(16 + vectors + 8 * (size_t)(maxr + 2) * (maxr + 2));
+    size_t written = 0; int nfr = 0;
+    CK(hb_mul_tree(backend(), (const hb_F *)flat.data(), vectors, size, (const hb_F *)&previous_r, (const hb_F *)(xr.empty() ? nullptr : xr.data()),
+                   (hb_F *)out.data(), &written, &nfr, &ps));
+    mul_tree_proof Pr; Pr.size = size; Pr.initial_randomness = previous_r;
+    size_t k = 0;
+    for (int v = 0; v < vectors; v++) Pr.output.push_back(out[k++]);
+    Pr.out_eval = out[k++];
+    for (int i = 0; i < nfr; i++) Pr.final_r.push_back(out[k++]);
+    Pr.final_eval = out[k++];
+    // layer proofs, top (smallest) layer first: rounds = log2(total >> (i+1))
+    size_t total = (size_t)vectors * size;
+    for (int i = depth - 1; i >= 0; i--) {
+        size_t sz = total >> (i + 1); int rounds = (int)std::log2((double)sz);
+        if (vectors == 1 && i == depth - 1) continue;                            // first layer of a single product has no sumcheck
+        proof P;
+        for (int q = 0; q < rounds; q++) { P.c_poly.push_back({out[k], out[k + 1], out[k + 2], out[k + 3]}); k += 4; }
+        P.vr = {out[k], out[k + 1], out[k + 2]}; P.final_rand = out[k + 3]; k += 4;
+        Pr.proofs.push_back(P);
+    }
+    int lg = (int)std::log2((double)size);
+    if (vectors == 1) {
+        for (int i = 0; i < lg; i++) Pr.individual_randomness.push_back(Pr.final_r[Pr.final_r.size() - lg + i]);
+        for (size_t i = 0; i + lg < Pr.final_r.size(); i++) Pr.global_randomness.push_back(Pr.final_r[i]);
+    } else {
+        for (int i = 0; i < lg; i++) Pr.individual_randomness.push_back(Pr.final_r[i]);
+        for (size_t i = 0; i + lg < Pr.final_r.size(); i++) Pr.global_randomness.push_back(Pr.final_r[i + lg]);
+    }
+    return Pr;
+}
+
+}  // namespace hobbit

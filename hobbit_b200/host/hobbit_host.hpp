@@ -1,0 +1,119 @@
+// hobbit_host — C++ host-side mirror of the reference's entry points for the GPU hot path.
+//
+// Every function below has the NAME, ARGUMENT MEANING and ERROR BEHAVIOUR (printf + exit(-1)) of the reference function
+// it replaces and forwards to the C ABI in include/hobbit_b200.h.  They live in namespace `hobbit` so that a test
+// binary can link the unmodified reference (global namespace) next to them and compare (tests/cpp/dropin_test.cpp).
+// A maintainer who wants the drop-in inside the reference tree removes the namespace.
+//
+//   reference                                                   here
+//   ---------------------------------------------------------   ------------------------------------------------
+//   virgo::fieldElement (fieldElement.hpp:15-97)                 hobbit::F  (same 16-byte layout)
+//   struct _hash (Blake3_hash.h:3-5)                             hobbit::_hash
+//   generate_randomness (utils.cpp:873-883)                      hobbit::generate_randomness   (libc rand()/random())
+//   expander_init_store (expanders.h:78-92) + _C/D               hobbit::expander_init_store   (same RNG order) + upload
+//   commit_standard / open_standard (Our_PC.cpp:146-171,604-692) hobbit::commit_standard / open_standard_queries
+//   init_commitment / commit (Elastic_PC.cpp:728-734,174-285)    hobbit::init_commitment / commit
+//   read_stream_PC default stream (witness_stream.cpp:2405-2411) hobbit::read_stream_PC
+//   merkle_tree_prover::{MT_commit_Blake,create_tree_blake,open_tree_blake}  hobbit::merkle_tree::merkle_tree_prover::…
+//   mimc_hash, precompute_beta, evaluate_vector                  same names
+//   generate_2product_sumcheck_proof, _generate_3product_sumcheck_proof, batch_3product_sumcheck,
+//   prove_multiplication_tree_new (sumcheck.cpp)                 same names, same `proof` / `mul_tree_proof` fields
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/hobbit_b200.h"
+
+namespace hobbit {
+
+struct F {                                     // virgo::fieldElement: {real, img}, canonical limbs
+    unsigned long long real = 0, img = 0;
+    F() {}
+    F(long long x) { real = x >= 0 ? (unsigned long long)x : 2305843009213693951ULL + x; img = 0; }
+    F(long long x, long long y) { real = x >= 0 ? x : 2305843009213693951ULL + x; img = y >= 0 ? y : 2305843009213693951ULL + y; }
+    F operator+(const F &o) const;
+    F operator-(const F &o) const;
+    F operator*(const F &o) const;
+    F operator-() const;
+    bool operator==(const F &o) const { return real == o.real && img == o.img; }
+    bool operator!=(const F &o) const { return !(*this == o); }
+};
+static_assert(sizeof(F) == sizeof(hb_F), "layout must match the C ABI");
+
+struct _hash { uint8_t arr[32]; };
+
+struct quadratic_poly { F a, b, c; F eval(const F &x) const { return (a * x + b) * x + c; } };
+struct cubic_poly { F a, b, c, d; F eval(const F &x) const { return ((a * x + b) * x + c) * x + d; } };
+
+struct proof {                                 // the fields of reference `struct proof` the hot path fills (sumcheck.h:21-43)
+    std::vector<std::vector<F>> randomness;
+    std::vector<quadratic_poly> q_poly;
+    std::vector<cubic_poly> c_poly;
+    std::vector<F> vr;
+    F final_rand;
+};
+struct mul_tree_proof {                        // sumcheck.h:8-20
+    F initial_randomness;
+    size_t size = 0;
+    F out_eval;
+    std::vector<proof> proofs;
+    std::vector<F> output, final_r, global_randomness, individual_randomness;
+    F final_eval;
+};
+
+struct stream_descriptor {                     // witness_stream.h:6-16
+    int idx = 0, offset = 0, stage = 0;
+    bool finished = false;
+    size_t pos = 0, pos_j = 0;
+    size_t data_size = 0, row_size = 0, col_size = 0, size = 0, layer = 0, tree_pos = 0;
+    std::string name;
+};
+
+// the reference's globals (main.cpp:31,38; Our_PC.cpp:21)
+extern int tensor_row_size;
+extern size_t BUFFER_SPACE;
+extern bool linear_time;
+
+// one-time setup: creates the GPU context (exits like the reference on failure: there is no CPU fallback)
+void init_backend(int device = 0);
+hb_ctx *backend();
+
+std::vector<F> generate_randomness(int size);
+long long expander_init_store(long long n, int dep = 0);
+F mimc_hash(F input, F k);
+void precompute_beta(std::vector<F> r, std::vector<F> &B);
+F evaluate_vector(std::vector<F> v, std::vector<F> r);
+void _fft(F *arr, int logn, bool flag);
+
+namespace merkle_tree { namespace merkle_tree_prover {
+void MT_commit_Blake(F *leafs, std::vector<std::vector<_hash>> &hashes, int N);
+void create_tree_blake(int ele_num, std::vector<std::vector<_hash>> &hashes, const int element_size = 32, bool alloc_required = false);
+std::vector<_hash> open_tree_blake(std::vector<std::vector<_hash>> &MT_hashes, std::vector<size_t> c, int collumns);
+} }
+
+// Our_PC.  `_tensor` is filled only when hobbit::materialize_tensor is true (the encoded tensor always stays resident
+// in HBM for the open phase; copying 64 B per coefficient back to the host is what the reference's layout implies
+// but not what its open needs).
+extern bool materialize_tensor;
+void commit_standard(std::vector<F> &poly, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes,
+                     std::vector<std::vector<std::vector<F>>> &_tensor, int K);
+// The data-parallel front half of open_standard (Our_PC.cpp:604-660): beta = eq(x1), aggregate, the rand()-drawn
+// queries I, the reply gather and the Merkle paths.  The recursion behind it (shockwave/WHIR) is the "next" row.
+struct open_front { std::vector<F> beta, aggr_vector; std::vector<std::vector<size_t>> I; std::vector<std::vector<F>> reply;
+                    std::vector<std::vector<_hash>> commitment_paths; F r_v0; double ps = 0; };
+open_front open_standard_front(std::vector<F> &poly, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, int K);
+
+// Elastic_PC
+void init_commitment(bool mod);
+void read_stream_PC(stream_descriptor &fd, F *v, int size);
+void commit(stream_descriptor fd, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes);
+
+// sumcheck.h
+proof generate_2product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, F previous_r, double &vt, double &ps);
+proof _generate_3product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, std::vector<F> &v3, F previous_r, double &vt, double &ps);
+proof batch_3product_sumcheck(std::vector<std::vector<F>> &arr1, std::vector<std::vector<F>> &arr2, std::vector<std::vector<F>> &arr3,
+                              std::vector<F> a, double &vt, double &ps);
+mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input, F previous_r, std::vector<F> prev_x, double &vt, double &ps);
+
+}  // namespace hobbit
