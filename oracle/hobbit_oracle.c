@@ -540,3 +540,134 @@ size_t orc_mul_tree(const F *input, int vectors, size_t n, const F *prev_r, F *o
     free(tr); free(in1); free(in2); free(r); free(beta); free(pbuf); free(proofs);
     return k;
 }
+
+/* ------------------------------------------------------------------ S4 ---
+ * generate_3product_sumcheck_beta_stream_batch_optimized (sumcheck.cpp:1150-1392) with batches = 1, distance = 1 — the
+ * configuration prove_multiplication_tree_stream_shallow uses whenever layers <= distance (all MLP/AES configs).
+ * The witness stream is given in its logical two-half form xy = [X | Y] (witness_stream.cpp:2276-2311 emits X-block | Y-block per
+ * read; read_mul_tree_data (:2461-2510) multiplies 2^layer-element segments inside each half).  With A = [seg(X) | seg(Y)]
+ * (S = total >> layer entries), E[j] = A[2j], O[j] = A[2j+1] split in blocks of B, the reference processes the blocks in the
+ * order X0 | Y0, X1, Y1, ... but indexes eq(r_high) by the NATURAL block number, and de-interleaves R afterwards
+ * (permute_partial_evals, :1138-1148).  libc draws: a = generate_randomness(1), b = generate_randomness(2), pad = random(). */
+static F *layer_array(const F *xy, size_t total, int layer) {
+    size_t S = total >> layer, seg = (size_t)1 << layer;
+    F *A = (F *)malloc(S * sizeof(F));
+    for (size_t i = 0; i < S; i++) { F p = xy[i * seg]; for (size_t j = 1; j < seg; j++) p = f_mul(p, xy[i * seg + j]); A[i] = p; }
+    return A;       /* segments never straddle the X|Y boundary: total/2 is a multiple of seg */
+}
+int orc_stream_sumcheck_layer(const F *xy, size_t total, size_t B, int layer_id, const F *r, int nr, const F *old_claim,
+                              F *new_claim, F *new_r, double *ps_out) {
+    (void)nr;
+    size_t S = total >> layer_id, nb = S / (2 * B);
+    int lgB = ilog2(B), lgnb = ilog2(nb);
+    F *A = layer_array(xy, total, layer_id);
+    F *eq_low = (F *)malloc(B * sizeof(F)), *eq_high = (F *)malloc(nb * sizeof(F));
+    orc_precompute_beta(r, lgB, eq_low); orc_precompute_beta(r + lgB, lgnb, eq_high);
+    F *f1 = (F *)malloc(3 * B * sizeof(F)), *f2 = f1 + B, *f3 = f2 + B;
+    double ps = 0;
+    F Kp = F0;
+    for (size_t j = 0; j < B; j++) { f1[j] = A[2 * j]; f2[j] = A[2 * j + 1]; f3[j] = eq_low[j]; Kp = f_add(Kp, f_mul(f_mul(f1[j], f2[j]), f3[j])); }
+    F a; orc_generate_randomness(1, &a);
+    F Kf = f_mul(a, Kp);
+    Kp = f_mul(Kp, eq_high[0]);
+    ps += 2 * 16 / 1024.0;
+    F *R = (F *)malloc(nb * sizeof(F)); size_t nR = 0; R[nR++] = F1;
+    for (size_t step = 1; step < nb; step++) {
+        /* processing order X0 | Y0, X1, Y1, ...: step 1 -> Y0, then (Xc, Yc) */
+        size_t c = (step + 1) / 2, g = (step % 2) ? nb / 2 + (step - 1) / 2 : step / 2;
+        (void)c;
+        const F *blk = A + 2 * g * B;
+        F K1 = F0, K2 = F0, K3 = F0;
+        for (size_t k = 0; k < B; k++) {
+            F b1 = blk[2 * k], b2 = blk[2 * k + 1], b3 = eq_low[k];
+            F t1 = f_add(f_mul(b1, f2[k]), f_mul(b2, f1[k])), t2 = f_mul(b1, b2);
+            K1 = f_add(K1, f_add(f_mul(f3[k], t1), f_mul(f_mul(b3, f1[k]), f2[k])));
+            K2 = f_add(K2, f_add(f_mul(b3, t1), f_mul(f3[k], t2)));
+            K3 = f_add(K3, f_mul(t2, b3));
+        }
+        K1 = f_mul(a, K1); K2 = f_mul(a, K2);
+        F rand = R[nR - 1];
+        rand = mimc(K1, rand); rand = mimc(K2, rand); rand = mimc(K3, rand);
+        F x1 = rand, x2 = f_mul(rand, x1), x3 = f_mul(rand, x2);
+        Kp = f_add(Kp, f_mul(eq_high[g], K3));
+        Kf = f_add(Kf, f_mul(f_mul(x3, a), K3));
+        Kf = f_add(Kf, f_add(f_mul(x2, K2), f_mul(x1, K1)));
+        R[nR++] = rand;
+        ps += 2 * 16 / 1024.0;
+        for (size_t k = 0; k < B; k++) {
+            f1[k] = f_add(f1[k], f_mul(rand, blk[2 * k])); f2[k] = f_add(f2[k], f_mul(rand, blk[2 * k + 1])); f3[k] = f_add(f3[k], f_mul(rand, eq_low[k]));
+        }
+    }
+    if (!f_eq(Kp, *old_claim)) printf("Error in sumcheck 0 %d\n", 0);
+    F *p1 = (F *)malloc((5 * (size_t)lgB + 8) * sizeof(F));
+    size_t szB = B;
+    ps += orc_batch_sumcheck3(f1, f2, f3, &szB, 1, &a, p1);
+    {   /* P1.c_poly[0].eval(0) + eval(1) == Kf */
+        F s = f_add(f_add(f_add(p1[0], p1[1]), f_add(p1[2], p1[3])), p1[3]);
+        if (!f_eq(s, Kf)) { printf("Error in sumcheck 1\n"); exit(-1); }
+    }
+    const F *P1r = p1 + 4 * lgB, *P1vr = p1 + 5 * lgB;
+    F *beta = (F *)malloc(B * sizeof(F));
+    orc_precompute_beta(P1r, lgB, beta);
+    F *PE0 = (F *)malloc(2 * nb * sizeof(F)), *PE1 = PE0 + nb;
+    for (size_t g = 0; g < nb; g++) {
+        F s0 = F0, s1 = F0; const F *blk = A + 2 * g * B;
+        for (size_t j = 0; j < B; j++) { s0 = f_add(s0, f_mul(beta[j], blk[2 * j])); s1 = f_add(s1, f_mul(beta[j], blk[2 * j + 1])); }
+        PE0[g] = s0; PE1[g] = s1;
+    }
+    F *Rp = (F *)malloc(nb * sizeof(F)); size_t cnt = 0;
+    for (size_t i = 0; i < nb / 2; i++) Rp[cnt++] = R[2 * i];
+    for (size_t i = 0; i < nb / 2; i++) Rp[cnt++] = R[2 * i + 1];
+    F b[2]; orc_generate_randomness(2, b);
+    F *aggr = (F *)malloc(nb * sizeof(F));
+    for (size_t j = 0; j < nb; j++) aggr[j] = f_add(f_mul(b[0], PE0[j]), f_mul(b[1], PE1[j]));
+    F *p2 = (F *)malloc((4 * (size_t)lgnb + 8) * sizeof(F));
+    F zero = F0;
+    ps += orc_sumcheck2(Rp, aggr, nb, &zero, p2);
+    {
+        F sum = f_add(f_mul(b[0], P1vr[0]), f_mul(b[1], P1vr[1]));
+        F q = f_add(f_add(p2[0], p2[1]), f_add(p2[2], p2[2]));
+        if (!f_eq(sum, q)) { printf("Error in sumcheck 2\n"); exit(-1); }
+    }
+    F pad = f_int(random());
+    size_t k = 0; new_r[k++] = pad;
+    for (int j = 0; j < lgB; j++) new_r[k++] = P1r[j];
+    const F *P2r = p2 + 3 * lgnb;
+    for (int j = 0; j < lgnb; j++) new_r[k++] = P2r[j];
+    *new_claim = f_add(f_mul(f_sub(F1, pad), evaluate_vector(PE0, nb, P2r)), f_mul(pad, evaluate_vector(PE1, nb, P2r)));
+    *ps_out = ps;
+    free(A); free(eq_low); free(eq_high); free(f1); free(R); free(p1); free(beta); free(PE0); free(Rp); free(aggr); free(p2);
+    return (int)k;
+}
+
+/* ------------------------------------------------------------------ S6 ---
+ * prove_multiplication_tree_stream_shallow (sumcheck.cpp:1746-1915), branches: whole stream fits (size*vectors <= 2B) and
+ * layers <= distance (or naive).  Returns ps; out = the `vectors` products. */
+double orc_mul_tree_stream(const F *xy, size_t total, int vectors, size_t B, int distance, int naive, const F *prev_r, F *out) {
+    int maxr = ilog2(total);
+    F *buf = (F *)malloc((64 + (size_t)vectors + 8 * (size_t)(maxr + 2) * (maxr + 2)) * sizeof(F));
+    int nfr; double ps = 0;
+    if (total <= 2 * B) {
+        orc_mul_tree(xy, vectors, total / vectors, prev_r, buf, &nfr, &ps);
+        memcpy(out, buf, vectors * sizeof(F)); free(buf); return ps;
+    }
+    int layers = ilog2(total / (2 * B));
+    if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance);
+    if (!(layers <= distance || naive)) { printf("orc_mul_tree_stream: batched layers (layers > distance) not restated\n"); exit(-1); }
+    F *top = layer_array(xy, total, layers);
+    size_t St = total >> layers;
+    orc_mul_tree(top, vectors, St / vectors, prev_r, buf, &nfr, &ps);
+    free(top);
+    memcpy(out, buf, vectors * sizeof(F));
+    F claim = buf[vectors + 1 + nfr];                 /* final_eval */
+    F *r = (F *)malloc((maxr + 2) * sizeof(F)), *nr = (F *)malloc((maxr + 2) * sizeof(F));
+    memcpy(r, buf + vectors + 1, nfr * sizeof(F));    /* vectors > 1: individual ++ global == final_r */
+    int n = nfr;
+    for (int i = layers - 1; i >= 0; i--) {
+        F nc; double p = 0;
+        n = orc_stream_sumcheck_layer(xy, total, B, i, r, n, &claim, &nc, nr, &p);
+        ps += p; claim = nc; memcpy(r, nr, n * sizeof(F));
+    }
+    free(r); free(nr); free(buf);
+    return ps;
+}

@@ -57,6 +57,12 @@ double orc_batch_sumcheck3(const orc_F *t1, const orc_F *t2, const orc_F *t3, co
                            const orc_F *a, orc_F *out);
 size_t orc_mul_tree(const orc_F *input, int vectors, size_t n, const orc_F *prev_r, orc_F *out, int *nfr_out, double *ps_out);
 
+/* S4/S6 — streaming folding sumcheck over one product-tree layer and the shallow streaming product tree.
+ * xy: the witness stream in its logical two-half form [X | Y] (total elements). */
+int orc_stream_sumcheck_layer(const orc_F *xy, size_t total, size_t B, int layer_id, const orc_F *r, int nr, const orc_F *old_claim,
+                              orc_F *new_claim, orc_F *new_r, double *ps_out);
+double orc_mul_tree_stream(const orc_F *xy, size_t total, int vectors, size_t B, int distance, int naive, const orc_F *prev_r, orc_F *out);
+
 #ifdef __cplusplus
 }
 #endif

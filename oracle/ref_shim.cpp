@@ -30,6 +30,9 @@ extern int tensor_row_size;
 extern size_t BUFFER_SPACE;
 void _fft(F *arr, int logn, bool flag);
 proof batch_3product_sumcheck(vector<vector<F>> &arr1, vector<vector<F>> &arr2, vector<vector<F>> &arr3, vector<F> a, double &vt, double &ps);
+void generate_3product_sumcheck_beta_stream_batch_optimized(stream_descriptor fd, vector<vector<F>> r, int batches, int distance, int layer_id,
+		vector<F> old_claims, vector<F> &new_claims, vector<vector<F>> &new_r, double &vt, double &ps);
+extern int BUFFER_SPACE_tr;
 
 static_assert(sizeof(F) == 16, "F must be the 16-byte {real,img} POD");
 
@@ -268,6 +271,32 @@ size_t ref_mul_tree(const uint64_t *input, int vectors, size_t n, const uint64_t
     }
     *nfr_out = (int)P.final_r.size(); *ps_out = ps;
     return k;
+}
+
+// ---- S4 / S6 on the synthetic default stream (read_stream default branch: v[i] = F(i%1024+1), witness_stream.cpp:2348-2352) ----
+// One layer of the streaming folding sumcheck (sumcheck.cpp:1150-1392), batches = 1, distance = 1.
+// r: log2((total >> layer_id)/2) points.  Writes new_claim (1 F) and new_r (returns its length).
+int ref_stream_sumcheck_layer(size_t total, size_t B, int layer_id, const uint64_t *r, int nr, const uint64_t *old_claim,
+                              uint64_t *new_claim, uint64_t *new_r, double *ps_out) {
+    BUFFER_SPACE = B; BUFFER_SPACE_tr = B / 8;
+    stream_descriptor fd; fd.name = "test"; fd.size = total; reset_stream(fd);
+    vector<vector<F>> rv(1), nr_out; rv[0].assign((const F *)r, (const F *)r + nr);
+    vector<F> oc(1, *(const F *)old_claim), nc(1);
+    double vt = 0, ps = 0;
+    generate_3product_sumcheck_beta_stream_batch_optimized(fd, rv, 1, 1, layer_id, oc, nc, nr_out, vt, ps);
+    memcpy(new_claim, &nc[0], 16);
+    memcpy(new_r, nr_out[0].data(), nr_out[0].size() * 16);
+    *ps_out = ps;
+    return (int)nr_out[0].size();
+}
+// prove_multiplication_tree_stream_shallow (sumcheck.cpp:1746-1915) on stream "test"; out: the `vectors` products.
+double ref_mul_tree_stream(size_t total, int vectors, size_t B, int distance, int naive, const uint64_t *prev_r, uint64_t *out) {
+    BUFFER_SPACE = B; BUFFER_SPACE_tr = B / 8;
+    stream_descriptor fd; fd.name = "test"; fd.size = total; reset_stream(fd);
+    vector<F> px; double vt = 0, ps = 0;
+    vector<F> o = prove_multiplication_tree_stream_shallow(fd, vectors, total / vectors, *(const F *)prev_r, distance, px, naive, vt, ps);
+    memcpy(out, o.data(), o.size() * 16);
+    return ps;
 }
 
 } // extern "C"

@@ -222,3 +222,41 @@ class Checker:
         k = self.fn("mul_tree", ctypes.c_size_t)(_p(x), vectors, ctypes.c_size_t(n), _p(r), _p(out),
                                                  ctypes.byref(nfr), ctypes.byref(ps))
         return out[:k].copy(), nfr.value, ps.value
+
+
+def synthetic_stream(total):
+    """read_stream's default branch (witness_stream.cpp:2348-2352): v[i] = F(i%1024 + 1), restarted on every read.  In the
+    logical two-half form [X | Y] both halves are the same periodic sequence as long as every read is a multiple of 2048
+    elements, i.e. BUFFER_SPACE >= 512 (smaller buffers make the reference's synthetic stream depend on the read size)."""
+    out = np.zeros((total, 2), dtype=np.uint64)
+    out[:, 0] = (np.arange(total, dtype=np.uint64) % 1024) + 1
+    return out
+
+
+def _stream_layer(self, xy, B, layer_id, r, old_claim):
+    """S4.  Checker('ref') ignores xy (it reads the synthetic stream itself)."""
+    xy, r, oc = F(xy), F(r), F(old_claim)
+    total = len(xy)
+    nc, nr = fzeros(1), fzeros(64)
+    ps = ctypes.c_double()
+    if self.kind == "ref":
+        n = self.fn("stream_sumcheck_layer", ctypes.c_int)(ctypes.c_size_t(total), ctypes.c_size_t(B), layer_id, _p(r), len(r), _p(oc),
+                                                           _p(nc), _p(nr), ctypes.byref(ps))
+    else:
+        n = self.fn("stream_sumcheck_layer", ctypes.c_int)(_p(xy), ctypes.c_size_t(total), ctypes.c_size_t(B), layer_id, _p(r), len(r), _p(oc),
+                                                           _p(nc), _p(nr), ctypes.byref(ps))
+    return nc, nr[:n].copy(), ps.value
+
+
+def _mul_tree_stream(self, xy, vectors, B, distance, naive, prev_r):
+    xy, pr = F(xy), F(prev_r)
+    out = fzeros(vectors)
+    if self.kind == "ref":
+        ps = self.fn("mul_tree_stream", ctypes.c_double)(ctypes.c_size_t(len(xy)), vectors, ctypes.c_size_t(B), distance, naive, _p(pr), _p(out))
+    else:
+        ps = self.fn("mul_tree_stream", ctypes.c_double)(_p(xy), ctypes.c_size_t(len(xy)), vectors, ctypes.c_size_t(B), distance, naive, _p(pr), _p(out))
+    return out, ps
+
+
+Checker.stream_layer = _stream_layer
+Checker.mul_tree_stream = _mul_tree_stream

@@ -4,7 +4,7 @@ binary was not prebuilt (the committed golden vectors in tests/golden/ still pin
 import numpy as np
 import pytest
 
-from helpers import Checker, F, P61, rand_field, ref_available, srand
+from helpers import Checker, F, P61, rand_field, ref_available, srand, synthetic_stream
 
 pytestmark = pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
 
@@ -143,3 +143,27 @@ def test_mul_tree(libs, vectors, n):
     srand(1); pb, nfb, psb = ref.mul_tree(x, vectors, pr)
     assert nfa == nfb and psa == psb
     assert np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("total,B,layer", [(1 << 13, 1 << 9, 0), (1 << 13, 1 << 9, 2), (1 << 15, 1 << 9, 1)])
+def test_stream_sumcheck_layer(libs, total, B, layer):
+    """S4 (sumcheck.cpp:1150-1392) on the reference's synthetic stream; the claim is deliberately arbitrary (the reference only
+    warns on a mismatch, :1246-1251) — what is compared is new_claim, new_r and the proof-size counter."""
+    orc, ref = libs
+    xy = synthetic_stream(total)
+    S = total >> layer
+    r = rand_field(np.random.default_rng(total + layer), int(np.log2(S // 2)))
+    oc = F([5, 0])
+    srand(4); a = orc.stream_layer(xy, B, layer, r, oc)
+    srand(4); b = ref.stream_layer(xy, B, layer, r, oc)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+
+
+@pytest.mark.parametrize("total,vectors,B", [(1 << 15, 8, 1 << 10), (1 << 12, 8, 1 << 11), (1 << 14, 2, 1 << 9)])
+def test_mul_tree_stream(libs, total, vectors, B):
+    """S6 (sumcheck.cpp:1746-1915): products and ps; the self-checks inside (Error in sumcheck 1/2 -> exit) pin the rest."""
+    orc, ref = libs
+    xy = synthetic_stream(total)
+    srand(2); a = orc.mul_tree_stream(xy, vectors, B, 5, 0, F([32, 0]))
+    srand(2); b = ref.mul_tree_stream(xy, vectors, B, 5, 0, F([32, 0]))
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
