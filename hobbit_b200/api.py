@@ -279,3 +279,20 @@ class Context:
         self._ck(self.lib.hb_mul_tree(self.h, _ptr(x), int(vectors), c_sz(n), _ptr(r), _ptr(xr), _ptr(out),
                                       ctypes.byref(written), ctypes.byref(nfr), ctypes.byref(ps)))
         return out[: written.value].copy(), nfr.value, ps.value
+
+    # ---- streaming folding sumcheck (S4) / shallow streaming product tree (S6) ----
+    def stream_layer(self, xy, B, layer_id, r, old_claim, rnd4):
+        xy, r, oc, rnd = _F(xy), _F(r), _F(old_claim), _F(rnd4)
+        nc, nr = np.zeros((1, 2), dtype=np.uint64), np.zeros((64, 2), dtype=np.uint64)
+        n, ps = ctypes.c_int(0), ctypes.c_double(0)
+        self._ck(self.lib.hb_stream_sumcheck_layer(self.h, _ptr(xy), c_sz(len(xy)), c_sz(B), int(layer_id), _ptr(r), len(r), _ptr(oc), _ptr(rnd),
+                                                   _ptr(nc), _ptr(nr), ctypes.byref(n), ctypes.byref(ps)))
+        return nc, nr[: n.value].copy(), ps.value
+
+    def mul_tree_stream(self, xy, vectors, B, distance, naive, prev_r, x_rand, rnd):
+        xy, pr, xr, rnd = _F(xy), _F(prev_r), _F(x_rand), _F(rnd)
+        out = np.zeros((vectors, 2), dtype=np.uint64)
+        layers, ps = ctypes.c_int(0), ctypes.c_double(0)
+        self._ck(self.lib.hb_mul_tree_stream(self.h, _ptr(xy), c_sz(len(xy)), int(vectors), c_sz(B), int(distance), int(naive), _ptr(pr), _ptr(xr),
+                                             _ptr(rnd), _ptr(out), ctypes.byref(layers), ctypes.byref(ps)))
+        return out, ps.value, layers.value

@@ -47,44 +47,10 @@ __device__ __forceinline__ F shfl_down_F(F v, int d) {
     F r; r.re = __shfl_down_sync(0xffffffffu, v.re, d); r.im = __shfl_down_sync(0xffffffffu, v.im, d); return r;
 }
 
-// INTERLEAVED: tables 0 and 1 are the even/odd entries of one array t.in[0] (product-tree layer: in1[j]=prev[2j],
-// in2[j]=prev[2j+1], sumcheck.cpp:84-101), so the layer is consumed in place without materialising in1/in2.
-template <int NT, int MODE, bool INTERLEAVED>
-__global__ void __launch_bounds__(256)
-sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
-    constexpr int NC = NT + 1;
-    F acc[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) acc[c] = mkF(0, 0);
-
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
-        F x[NT], y[NT];
-        if (MODE == FOLD_THEN_POLY) {
-#pragma unroll
-            for (int k = 0; k < NT; k++) {
-                const F *p = t.in[k] + 4 * j;
-                F a = p[0], b = p[1], c = p[2], d = p[3];
-                x[k] = fold1(a, b, r); y[k] = fold1(c, d, r);
-                t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y[k];
-            }
-        } else if (INTERLEAVED) {
-            const F *p = t.in[0] + 4 * j;
-            x[0] = p[0]; x[1] = p[1]; y[0] = p[2]; y[1] = p[3];
-#pragma unroll
-            for (int k = 2; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
-        }
-        if (MODE != FOLD_ONLY) poly_acc<NT>(acc, x, y);
-        if (MODE == POLY_AND_FOLD || MODE == FOLD_ONLY) {
-#pragma unroll
-            for (int k = 0; k < NT; k++) t.out[k][j] = fold1(x[k], y[k], r);
-        }
-    }
-    if (MODE == FOLD_ONLY) return;
-
-    // warp -> CTA -> grid reduction of the NC coefficients
+// warp -> CTA -> grid reduction of NC field accumulators: warp shuffles, shared memory across warps, per-CTA partials in
+// global memory, and the last CTA to take a ticket sums the partials and writes `result[0..NC)` (then re-arms the ticket).
+template <int NC>
+__device__ __forceinline__ void grid_reduce(F (&acc)[NC], F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
     __shared__ F sred[8][NC];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,6 +93,106 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__
         result[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *ticket = 0;
+}
+
+// INTERLEAVED: tables 0 and 1 are the even/odd entries of one array t.in[0] (product-tree layer: in1[j]=prev[2j],
+// in2[j]=prev[2j+1], sumcheck.cpp:84-101), so the layer is consumed in place without materialising in1/in2.
+template <int NT, int MODE, bool INTERLEAVED>
+__global__ void __launch_bounds__(256)
+sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    constexpr int NC = NT + 1;
+    F acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = mkF(0, 0);
+
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
+        F x[NT], y[NT];
+        if (MODE == FOLD_THEN_POLY) {
+#pragma unroll
+            for (int k = 0; k < NT; k++) {
+                const F *p = t.in[k] + 4 * j;
+                F a = p[0], b = p[1], c = p[2], d = p[3];
+                x[k] = fold1(a, b, r); y[k] = fold1(c, d, r);
+                t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y[k];
+            }
+        } else if (INTERLEAVED) {
+            const F *p = t.in[0] + 4 * j;
+            x[0] = p[0]; x[1] = p[1]; y[0] = p[2]; y[1] = p[3];
+#pragma unroll
+            for (int k = 2; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
+        }
+        if (MODE != FOLD_ONLY) poly_acc<NT>(acc, x, y);
+        if (MODE == POLY_AND_FOLD || MODE == FOLD_ONLY) {
+#pragma unroll
+            for (int k = 0; k < NT; k++) t.out[k][j] = fold1(x[k], y[k], r);
+        }
+    }
+    if (MODE == FOLD_ONLY) return;
+
+    grid_reduce<NC>(acc, partial, ticket, result);
+}
+
+// ---- S4: streaming folding sumcheck over one product-tree layer (sumcheck.cpp:1093-1136, 1150-1392) -----------------------
+// A block of the layer array holds B interleaved pairs (b1, b2) = (blk[2k], blk[2k+1]); b3 is the eq table of the low variables.
+// first block: fold tables := block, K = sum f1 f2 f3
+__global__ void __launch_bounds__(256)
+stream_init_kernel(const F *__restrict__ blk, const F *__restrict__ eq_low, F *__restrict__ f1, F *__restrict__ f2, F *__restrict__ f3, size_t B,
+                   F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[1] = {mkF(0, 0)};
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < B; k += (size_t)gridDim.x * blockDim.x) {
+        F b1 = blk[2 * k], b2 = blk[2 * k + 1], b3 = eq_low[k];
+        f1[k] = b1; f2[k] = b2; f3[k] = b3;
+        acc[0] = fadd(acc[0], fmul(fmul(b1, b2), b3));
+    }
+    grid_reduce<1>(acc, partial, ticket, result);
+}
+// error terms of folding one more block into (f1,f2,f3)  (batch_prod, :1103-1111):
+//   K1 = sum f3 (b1 f2 + b2 f1) + b3 f1 f2 ;  K2 = sum b3 (b1 f2 + b2 f1) + f3 b1 b2 ;  K3 = sum b1 b2 b3
+__global__ void __launch_bounds__(256)
+stream_err_kernel(const F *__restrict__ f1, const F *__restrict__ f2, const F *__restrict__ f3, const F *__restrict__ blk,
+                  const F *__restrict__ eq_low, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[3] = {mkF(0, 0), mkF(0, 0), mkF(0, 0)};
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < B; k += (size_t)gridDim.x * blockDim.x) {
+        F b1 = blk[2 * k], b2 = blk[2 * k + 1], b3 = eq_low[k], x1 = f1[k], x2 = f2[k], x3 = f3[k];
+        F t1 = fadd(fmul(b1, x2), fmul(b2, x1)), t2 = fmul(b1, b2);
+        acc[0] = fadd(acc[0], fadd(fmul(x3, t1), fmul(fmul(b3, x1), x2)));
+        acc[1] = fadd(acc[1], fadd(fmul(b3, t1), fmul(x3, t2)));
+        acc[2] = fadd(acc[2], fmul(t2, b3));
+    }
+    grid_reduce<3>(acc, partial, ticket, result);
+}
+// f += rho * block  (:1130-1135)
+__global__ void __launch_bounds__(256)
+stream_fold_kernel(F *__restrict__ f1, F *__restrict__ f2, F *__restrict__ f3, const F *__restrict__ blk, const F *__restrict__ eq_low, F rho, size_t B) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < B; k += (size_t)gridDim.x * blockDim.x) {
+        f1[k] = fadd(f1[k], fmul(rho, blk[2 * k]));
+        f2[k] = fadd(f2[k], fmul(rho, blk[2 * k + 1]));
+        f3[k] = fadd(f3[k], fmul(rho, eq_low[k]));
+    }
+}
+// pass B (:1327-1340): PE0[g] = sum_j beta[j] A[2(gB+j)], PE1[g] = sum_j beta[j] A[2(gB+j)+1]; grid (parts, nb), out[(g*parts+part)*2 + {0,1}]
+__global__ void __launch_bounds__(256)
+partial_evals_kernel(const F *__restrict__ A, const F *__restrict__ beta, size_t B, F *__restrict__ out) {
+    __shared__ F sred[8][2];
+    const F *blk = A + 2 * (size_t)blockIdx.y * B;
+    F a0 = mkF(0, 0), a1 = mkF(0, 0);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x) {
+        F bj = beta[j];
+        a0 = fadd(a0, fmul(bj, blk[2 * j])); a1 = fadd(a1, fmul(bj, blk[2 * j + 1]));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { a0 = fadd(a0, shfl_down_F(a0, d)); a1 = fadd(a1, shfl_down_F(a1, d)); }
+    if (lane == 0) { sred[warp][0] = a0; sred[warp][1] = a1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        F v = sred[0][threadIdx.x];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = fadd(v, sred[w][threadIdx.x]);
+        out[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = v;
+    }
 }
 
 // product-tree level: out[j] = in[2j] * in[2j+1]   (sumcheck.cpp:84-101)
@@ -355,8 +421,9 @@ extern "C" int hb_sumcheck3(hb_ctx *ctx, const hb_F *v1, const hb_F *v2, const h
     return rc;
 }
 
-extern "C" int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, const hb_F *t3, const size_t *sizes, int batches,
-                                  const hb_F *a_in, hb_F *proof, double *ps) {
+// S3 on DEVICE tables (batch b at d1/d2/d3 + sum of earlier sizes); a: host.  Inputs are not modified.
+static int batch_sumcheck3_dev(hb_ctx *ctx, const F *d1, const F *d2, const F *d3, const size_t *sizes, int batches,
+                               const F *a_host, hb_F *proof, double *ps) {
     HB_TRY(ensure_scratch(ctx));
     size_t tot = 0, Lmax = 0;
     for (int b = 0; b < batches; b++) {
@@ -364,10 +431,7 @@ extern "C" int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, c
         tot += sizes[b]; Lmax = std::max(Lmax, sizes[b]);
     }
     int rounds = ilog2(Lmax);
-    Staged s1(ctx), s2(ctx), s3(ctx);
-    HB_TRY(s1.in(t1, tot * sizeof(F))); HB_TRY(s2.in(t2, tot * sizeof(F))); HB_TRY(s3.in(t3, tot * sizeof(F)));
-    std::vector<F> a(batches);
-    HB_CHECK(ctx, cudaMemcpy(a.data(), a_in, batches * sizeof(F), cudaMemcpyDefault));
+    std::vector<F> a(a_host, a_host + batches);
     // per batch: ping-pong scratch of size/2 + size/4 per table
     F *scratch; HB_CHECK(ctx, cudaMallocAsync(&scratch, (3 * tot + 8) * sizeof(F), ctx->stream));
     struct Bt { const F *cur[3]; F *A[3], *B[3]; size_t size; bool exhausted; F x[3]; };
@@ -375,7 +439,7 @@ extern "C" int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, c
     size_t off = 0, soff = 0;
     for (int b = 0; b < batches; b++) {
         Bt &q = bt[b]; q.size = sizes[b]; q.exhausted = false;
-        const F *base[3] = {s1.as<F>() + off, s2.as<F>() + off, s3.as<F>() + off};
+        const F *base[3] = {d1 + off, d2 + off, d3 + off};
         for (int k = 0; k < 3; k++) { q.cur[k] = base[k]; q.A[k] = scratch + soff; q.B[k] = q.A[k] + sizes[b] / 2; soff += sizes[b] / 2 + sizes[b] / 4 + 1; }
         off += sizes[b];
     }
@@ -454,6 +518,17 @@ extern "C" int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, c
     *ps += (3 * batches - batches) * 16 / 1024.0;
     for (int j = 0; j < 3 * batches; j++) proof[5 * rounds + j] = toabi(vr[j]);
     return 0;
+}
+
+extern "C" int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, const hb_F *t3, const size_t *sizes, int batches,
+                                  const hb_F *a_in, hb_F *proof, double *ps) {
+    size_t tot = 0;
+    for (int b = 0; b < batches; b++) tot += sizes[b];
+    Staged s1(ctx), s2(ctx), s3(ctx);
+    HB_TRY(s1.in(t1, tot * sizeof(F))); HB_TRY(s2.in(t2, tot * sizeof(F))); HB_TRY(s3.in(t3, tot * sizeof(F)));
+    std::vector<F> a(batches);
+    HB_CHECK(ctx, cudaMemcpy(a.data(), a_in, batches * sizeof(F), cudaMemcpyDefault));
+    return batch_sumcheck3_dev(ctx, s1.as<F>(), s2.as<F>(), s3.as<F>(), sizes, batches, a.data(), proof, ps);
 }
 
 extern "C" int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n, const hb_F *prev_r, const hb_F *x_rand,
@@ -545,4 +620,173 @@ extern "C" int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n
     for (auto &x : proofs) out[k++] = x;
     *written = k; *nfr = (int)r.size();
     return 0;
+}
+
+// =========================================================================================================
+// S4 on a layer array A (device, S entries, natural [seg(X) | seg(Y)] order).  rnd4 = (a, b0, b1, pad) drawn by the host with
+// libc in the reference's order.  r: log2(S/2) host points.  Outputs on the host.
+static inline F fromabi(const hb_F &x) { return mkF(x.real, x.img); }
+static int read_result(hb_ctx *ctx, int nc, F *out) {
+    HB_CHECK(ctx, cudaMemcpyAsync(ctx->mailbox, ctx->mailbox_dev, nc * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < nc; c++) out[c] = ctx->mailbox[c];
+    return 0;
+}
+static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F *r, F old_claim, const F *rnd4,
+                            F *new_claim, std::vector<F> &new_r, double *ps) {
+    HB_TRY(ensure_scratch(ctx));
+    if (S < 4 * B || (S & (S - 1)) || (B & (B - 1))) HB_FAIL(ctx, "stream layer: need a power-of-two layer of at least 4*BUFFER_SPACE entries");
+    const size_t nb = S / (2 * B);
+    const int lgB = ilog2(B), lgnb = ilog2(nb);
+    F *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, (5 * B + nb + 64) * sizeof(F), ctx->stream));
+    F *eq_low = buf, *f1 = buf + B, *f2 = f1 + B, *f3 = f2 + B, *beta = f3 + B, *eqh_dev = beta + B, *r_dev = eqh_dev + nb;
+    auto fail = [&](int rc) { cudaFreeAsync(buf, ctx->stream); return rc; };
+    int rc;
+    HB_CHECK(ctx, cudaMemcpyAsync(r_dev, r, (lgB + lgnb) * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = beta_dev(ctx, r_dev, lgB, eq_low))) return fail(rc);
+    if ((rc = beta_dev(ctx, r_dev + lgB, lgnb, eqh_dev))) return fail(rc);
+    std::vector<F> eq_high(nb);
+    HB_CHECK(ctx, cudaMemcpyAsync(eq_high.data(), eqh_dev, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    const unsigned grid = grid_for(ctx, B);
+    F Kp;
+    HB_LAUNCH(ctx, stream_init_kernel, grid, 256, 0, A, eq_low, f1, f2, f3, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    if ((rc = read_result(ctx, 1, &Kp))) return fail(rc);                 // also completes the eq_high download
+    const F a = rnd4[0];
+    F Kf = h_fmul(a, Kp);
+    Kp = h_fmul(Kp, eq_high[0]);
+    *ps += 2 * 16 / 1024.0;
+    std::vector<F> R; R.push_back(mkF(1, 0));
+    for (size_t step = 1; step < nb; step++) {
+        // processing order of the reference: X0 | Y0, X1, Y1, ...   (natural block index g selects eq_high)
+        const size_t g = (step % 2) ? nb / 2 + (step - 1) / 2 : step / 2;
+        const F *blk = A + 2 * g * B;
+        F K[3];
+        HB_LAUNCH(ctx, stream_err_kernel, grid, 256, 0, f1, f2, f3, blk, eq_low, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+        if ((rc = read_result(ctx, 3, K))) return fail(rc);
+        F K1 = h_fmul(a, K[0]), K2 = h_fmul(a, K[1]), K3 = K[2];
+        F rand = R.back();
+        rand = h_mimc(K1, rand); rand = h_mimc(K2, rand); rand = h_mimc(K3, rand);     // argument order (value, rand): N7
+        F x1 = rand, x2 = h_fmul(rand, x1), x3 = h_fmul(rand, x2);
+        Kp = fadd(Kp, h_fmul(eq_high[g], K3));
+        Kf = fadd(Kf, h_fmul(h_fmul(x3, a), K3));
+        Kf = fadd(Kf, fadd(h_fmul(x2, K2), h_fmul(x1, K1)));
+        R.push_back(rand);
+        *ps += 2 * 16 / 1024.0;
+        HB_LAUNCH(ctx, stream_fold_kernel, grid, 256, 0, f1, f2, f3, blk, eq_low, rand, B);
+    }
+    if (!feq(Kp, old_claim)) printf("Error in sumcheck 0 %d\n", 0);           // the reference only warns (sumcheck.cpp:1246-1251)
+    std::vector<hb_F> p1(5 * (size_t)lgB + 8);
+    size_t szB = B;
+    if ((rc = batch_sumcheck3_dev(ctx, f1, f2, f3, &szB, 1, &a, p1.data(), ps))) return fail(rc);
+    {
+        F s = fadd(fadd(fadd(fromabi(p1[0]), fromabi(p1[1])), fadd(fromabi(p1[2]), fromabi(p1[3]))), fromabi(p1[3]));
+        if (!feq(s, Kf)) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in sumcheck 1"); }
+    }
+    // pass B: per-block partial evaluations against eq(P1.randomness[0 .. log2 B))
+    std::vector<F> P1r(lgB);
+    for (int j = 0; j < lgB; j++) P1r[j] = fromabi(p1[4 * lgB + j]);
+    HB_CHECK(ctx, cudaMemcpyAsync(r_dev, P1r.data(), lgB * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = beta_dev(ctx, r_dev, lgB, beta))) return fail(rc);
+    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((B + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
+    F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, nb * parts * 2 * sizeof(F), ctx->stream));
+    HB_LAUNCH(ctx, partial_evals_kernel, dim3(parts, (unsigned)nb), 256, 0, A, beta, B, pe_dev);
+    std::vector<F> pe(nb * parts * 2);
+    HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(pe_dev, ctx->stream);
+    cudaFreeAsync(buf, ctx->stream);
+    std::vector<F> PE0(nb, mkF(0, 0)), PE1(nb, mkF(0, 0));
+    for (size_t g = 0; g < nb; g++) for (unsigned q = 0; q < parts; q++) { PE0[g] = fadd(PE0[g], pe[(g * parts + q) * 2]); PE1[g] = fadd(PE1[g], pe[(g * parts + q) * 2 + 1]); }
+    // de-interleave R (permute_partial_evals) -> natural block order
+    std::vector<F> Rp; Rp.reserve(nb);
+    for (size_t i = 0; i < nb / 2; i++) Rp.push_back(R[2 * i]);
+    for (size_t i = 0; i < nb / 2; i++) Rp.push_back(R[2 * i + 1]);
+    const F b0 = rnd4[1], b1 = rnd4[2], pad = rnd4[3];
+    std::vector<F> aggr(nb);
+    for (size_t j = 0; j < nb; j++) aggr[j] = fadd(h_fmul(b0, PE0[j]), h_fmul(b1, PE1[j]));
+    std::vector<hb_F> p2(4 * (size_t)lgnb + 8);
+    hb_F zero{0, 0};
+    HB_TRY(hb_sumcheck2(ctx, (const hb_F *)Rp.data(), (const hb_F *)aggr.data(), nb, &zero, p2.data(), ps));
+    {
+        F sum = fadd(h_fmul(b0, fromabi(p1[5 * lgB])), h_fmul(b1, fromabi(p1[5 * lgB + 1])));
+        F q = fadd(fadd(fromabi(p2[0]), fromabi(p2[1])), fadd(fromabi(p2[2]), fromabi(p2[2])));
+        if (!feq(sum, q)) HB_FAIL(ctx, "Error in sumcheck 2");
+    }
+    new_r.clear(); new_r.push_back(pad);
+    for (int j = 0; j < lgB; j++) new_r.push_back(P1r[j]);
+    std::vector<F> P2r(lgnb);
+    for (int j = 0; j < lgnb; j++) { P2r[j] = fromabi(p2[3 * lgnb + j]); new_r.push_back(P2r[j]); }
+    auto eval_small = [&](std::vector<F> v) { for (int q = 0; q < lgnb; q++) for (size_t j = 0; j < (nb >> (q + 1)); j++) v[j] = h_fold(v[2 * j], v[2 * j + 1], P2r[q]); return v[0]; };
+    *new_claim = fadd(h_fmul(fsub(mkF(1, 0), pad), eval_small(PE0)), h_fmul(pad, eval_small(PE1)));
+    return 0;
+}
+
+// layer arrays of a resident stream: lv[0] = xy, lv[l+1][j] = lv[l][2j] * lv[l][2j+1]  (segments never straddle X|Y)
+static int build_layers(hb_ctx *ctx, const F *xy, size_t total, int layers, std::vector<const F *> &lv, F **owned) {
+    lv.assign(layers + 1, nullptr); lv[0] = xy; *owned = nullptr;
+    if (layers == 0) return 0;
+    HB_CHECK(ctx, cudaMallocAsync(owned, total * sizeof(F), ctx->stream));
+    F *p = *owned;
+    for (int l = 0; l < layers; l++) {
+        size_t sz = total >> (l + 1);
+        HB_LAUNCH(ctx, prod_level_kernel, (unsigned)std::min<size_t>((sz + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, lv[l], p, sz);
+        lv[l + 1] = p; p += sz;
+    }
+    return 0;
+}
+
+extern "C" int hb_stream_sumcheck_layer(hb_ctx *ctx, const hb_F *xy, size_t total, size_t B, int layer_id, const hb_F *r, int nr,
+                                        const hb_F *old_claim, const hb_F *rnd4, hb_F *new_claim, hb_F *new_r, int *n_new_r, double *ps) {
+    if (total == 0 || (total & (total - 1))) HB_FAIL(ctx, "hb_stream_sumcheck_layer: stream size must be a power of two");
+    Staged sx(ctx);
+    HB_TRY(sx.in(xy, total * sizeof(F)));
+    std::vector<const F *> lv; F *owned;
+    HB_TRY(build_layers(ctx, sx.as<F>(), total, layer_id, lv, &owned));
+    size_t S = total >> layer_id;
+    if (nr != ilog2(S / 2)) { if (owned) cudaFreeAsync(owned, ctx->stream); HB_FAIL(ctx, "hb_stream_sumcheck_layer: r must hold log2(S/2) points"); }
+    std::vector<F> nrv; F nc;
+    int rc = stream_layer_dev(ctx, lv[layer_id], S, B, (const F *)r, fromabi(*old_claim), (const F *)rnd4, &nc, nrv, ps);
+    if (owned) cudaFreeAsync(owned, ctx->stream);
+    if (rc) return rc;
+    *new_claim = toabi(nc);
+    for (size_t i = 0; i < nrv.size(); i++) new_r[i] = toabi(nrv[i]);
+    *n_new_r = (int)nrv.size();
+    return 0;
+}
+
+// S6: prove_multiplication_tree_stream_shallow (sumcheck.cpp:1746-1915) with the stream resident in HBM.
+// x_rand: log2(vectors) points for the product tree; rnd: 4 values (a, b0, b1, pad) per streamed layer, top layer first.
+extern "C" int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int vectors, size_t B, int distance, int naive,
+                                  const hb_F *prev_r, const hb_F *x_rand, const hb_F *rnd, hb_F *out, int *layers_out, double *ps) {
+    if (total == 0 || (total & (total - 1)) || vectors < 2 || (vectors & (vectors - 1))) HB_FAIL(ctx, "hb_mul_tree_stream: sizes must be powers of two, vectors >= 2");
+    Staged sx(ctx);
+    HB_TRY(sx.in(xy, total * sizeof(F)));
+    const int maxr = ilog2(total);
+    std::vector<hb_F> buf(64 + vectors + 8 * (size_t)(maxr + 2) * (maxr + 2));
+    size_t written; int nfr;
+    if (total <= 2 * B) {                                            // the whole stream fits the buffer: plain product tree (:1756-1773)
+        HB_TRY(hb_mul_tree(ctx, (const hb_F *)sx.as<F>(), vectors, total / vectors, prev_r, x_rand, buf.data(), &written, &nfr, ps));
+        memcpy(out, buf.data(), vectors * sizeof(hb_F)); *layers_out = 0;
+        return 0;
+    }
+    int layers = ilog2(total / (2 * B));
+    if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance);
+    if (!(layers <= distance || naive)) HB_FAIL(ctx, "hb_mul_tree_stream: layers > distance needs the committed intermediate layers (commit_layers/open_layers), not built yet");
+    std::vector<const F *> lv; F *owned;
+    HB_TRY(build_layers(ctx, sx.as<F>(), total, layers, lv, &owned));
+    size_t St = total >> layers;
+    int rc = hb_mul_tree(ctx, (const hb_F *)lv[layers], vectors, St / vectors, prev_r, x_rand, buf.data(), &written, &nfr, ps);
+    if (rc) { cudaFreeAsync(owned, ctx->stream); return rc; }
+    memcpy(out, buf.data(), vectors * sizeof(hb_F));
+    F claim = fromabi(buf[vectors + 1 + nfr]);
+    std::vector<F> r(nfr), nrv;
+    for (int i = 0; i < nfr; i++) r[i] = fromabi(buf[vectors + 1 + i]);
+    for (int i = layers - 1, q = 0; i >= 0 && !rc; i--, q++) {
+        F nc;
+        rc = stream_layer_dev(ctx, lv[i], total >> i, B, r.data(), claim, (const F *)rnd + 4 * q, &nc, nrv, ps);
+        claim = nc; r = nrv;
+    }
+    cudaFreeAsync(owned, ctx->stream);
+    *layers_out = layers;
+    return rc;
 }

@@ -129,6 +129,20 @@ int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, const hb_F *
 int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n, const hb_F *prev_r, const hb_F *x_rand,
                 hb_F *out, size_t *written, int *nfr, double *ps);
 
+/* ---- S4/S6: streaming folding sumcheck with the witness stream resident in HBM (sumcheck.cpp:1093-1392, 1746-1915) --------- */
+/* xy: the stream in its logical two-half form [X | Y] (`total` elements; what read_stream emits as X-block | Y-block per read,
+ * witness_stream.cpp:2276-2311).  Layer l is [seg_l(X) | seg_l(Y)] with 2^l-element segment products (read_mul_tree_data).
+ * hb_stream_sumcheck_layer = generate_3product_sumcheck_beta_stream_batch_optimized with batches = 1, distance = 1:
+ *   r: log2((total>>layer_id)/2) points; rnd4 = (a, b0, b1, pad): generate_randomness(1), generate_randomness(2), random() drawn by
+ *   the HOST in that order; new_r gets 1 + log2(total>>layer_id) - 1 points.  Error checks behave like the reference
+ *   ("Error in sumcheck 0" warns, 1 and 2 fail).
+ * hb_mul_tree_stream = prove_multiplication_tree_stream_shallow for layers <= distance (or naive): out = the `vectors` products;
+ *   x_rand: log2(vectors) points; rnd: 4 per streamed layer (top layer first); *layers_out = number of streamed layers. */
+int hb_stream_sumcheck_layer(hb_ctx *ctx, const hb_F *xy, size_t total, size_t B, int layer_id, const hb_F *r, int nr,
+                             const hb_F *old_claim, const hb_F *rnd4, hb_F *new_claim, hb_F *new_r, int *n_new_r, double *ps);
+int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int vectors, size_t B, int distance, int naive,
+                       const hb_F *prev_r, const hb_F *x_rand, const hb_F *rnd, hb_F *out, int *layers_out, double *ps);
+
 #ifdef __cplusplus
 }
 #endif

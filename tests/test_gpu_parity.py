@@ -4,7 +4,9 @@ where the prebuilt reference binary travelled with the repo (oracle/_ref), the u
 import numpy as np
 import pytest
 
-from helpers import Checker, F, P61, rand_field, ref_available, srand
+import ctypes
+
+from helpers import Checker, F, P61, rand_field, ref_available, srand, synthetic_stream
 
 pytestmark = pytest.mark.gpu
 
@@ -233,3 +235,53 @@ def test_mul_tree(ctx, chk, vectors, n):
     pb, nfb, psb = chk.mul_tree(x, vectors, pr)
     assert nfa == nfb and psa == psb
     assert np.array_equal(pa, pb)
+
+
+def libc_random():
+    f = ctypes.CDLL(None).random
+    f.restype = ctypes.c_long
+    return int(f())
+
+
+def draw_layer_randomness(orc):
+    """(a, b0, b1, pad) in the reference's order: generate_randomness(1), generate_randomness(2), random()."""
+    a = orc.generate_randomness(1)
+    b = orc.generate_randomness(2)
+    pad = F([libc_random(), 0])
+    return np.concatenate([a, b, pad])
+
+
+@pytest.mark.parametrize("total,B,layer,synthetic", [(1 << 13, 1 << 9, 0, True), (1 << 13, 1 << 9, 2, True), (1 << 15, 1 << 9, 1, True),
+                                                     (1 << 14, 1 << 8, 0, False), (1 << 16, 1 << 10, 3, False)])
+def test_stream_sumcheck_layer(ctx, chk, total, B, layer, synthetic):
+    """S4.  The reference can only read its synthetic stream; the C oracle (and the GPU) take any resident stream."""
+    if chk.kind == "ref" and not synthetic:
+        pytest.skip("the reference only has its synthetic stream")
+    xy = synthetic_stream(total) if synthetic else rand_field(np.random.default_rng(total), total)
+    S = total >> layer
+    r = rand_field(np.random.default_rng(total + layer), int(np.log2(S // 2)))
+    oc = F([5, 0])
+    orc = Checker("orc")
+    srand(4); rnd = draw_layer_randomness(orc)
+    got = ctx.stream_layer(xy, B, layer, r, oc, rnd)
+    srand(4); want = chk.stream_layer(xy, B, layer, r, oc)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] == want[2]
+
+
+@pytest.mark.parametrize("total,vectors,B,synthetic", [(1 << 15, 8, 1 << 10, True), (1 << 12, 8, 1 << 11, True), (1 << 14, 2, 1 << 9, True),
+                                                       (1 << 17, 8, 1 << 12, False)])
+def test_mul_tree_stream(ctx, chk, total, vectors, B, synthetic):
+    """S6 with the stream resident in HBM: products, ps, and (through the provers' own self-checks) every layer claim."""
+    if chk.kind == "ref" and not synthetic:
+        pytest.skip("the reference only has its synthetic stream")
+    xy = synthetic_stream(total) if synthetic else rand_field(np.random.default_rng(total), total)
+    orc = Checker("orc")
+    layers = max(0, int(np.log2(total // (2 * B)))) if total > 2 * B else 0
+    srand(2)
+    xr = orc.generate_randomness(int(np.log2(vectors)))
+    rnd = np.concatenate([draw_layer_randomness(orc) for _ in range(layers)]) if layers else np.zeros((4, 2), dtype=np.uint64)
+    got = ctx.mul_tree_stream(xy, vectors, B, 5, 0, F([32, 0]), xr, rnd)
+    srand(2)
+    want = chk.mul_tree_stream(xy, vectors, B, 5, 0, F([32, 0]))
+    assert got[2] == layers
+    assert np.array_equal(got[0], want[0]) and got[1] == want[1]
