@@ -14,8 +14,9 @@ A "step" is one whole commit of that polynomial.
     cpu_baseline : the unmodified reference (oracle/_ref, built from /root/reference) on a bounded sample
 
 `--impl reference` times the reference's own CPU implementation of the same call on the host cores.
-N > 1 (torchrun): every rank commits its own polynomial (independent commitments, no data-path collective) ->
-weak scaling; timing = max over ranks.
+N > 1 (torchrun): ONE commitment of N*2^26 coefficients (32*N chunks of the same size) sharded over the ranks
+(hobbit_b200/dist.py: chunks by rank, inner leaf digests all_to_all by leaf range, subtree levels all_gather) -> weak
+scaling (fixed work per GPU); timing = max over ranks.
 """
 import argparse
 import ctypes
@@ -192,6 +193,8 @@ def main():
     orc.expander_init_store(trs)
     cw = ctx.expander_set(trs, orc.expander_graphs(trs))
 
+    # N > 1: ONE commitment of N*world coefficients (K*world chunks of the same size) sharded over the ranks: rank g owns chunks
+    # [g*K, (g+1)*K) and the leaf range [g*B/world, (g+1)*B/world) (hobbit_b200/dist.py); N == 1: the plain C-ABI call.
     poly_host = ctx.pinned((N, 2), np.uint64)
     poly_host[:] = make_poly(N, 1234 + rank)
     levels_host = ctx.pinned((2 * B - 1, 32), np.uint8)
@@ -201,11 +204,24 @@ def main():
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(ctx.stream())
 
+    if world > 1:
+        from hobbit_b200.dist import GpuBackend, commit_standard_sharded
+        be = GpuBackend(ctx, torch.device("cuda", local))
+
     def step_resident():
-        ctx.commit_standard(poly_dev.data_ptr(), K, trs, 1, levels_out=levels_dev.data_ptr(), N=N)
+        if world > 1:
+            commit_standard_sharded(be, poly_dev.data_ptr(), K * world, B, trs, 1)
+        else:
+            ctx.commit_standard(poly_dev.data_ptr(), K, trs, 1, levels_out=levels_dev.data_ptr(), N=N)
 
     def step_e2e():
-        ctx.commit_standard(poly_host, K, trs, 1, levels_out=levels_host)
+        if world > 1:
+            lv = commit_standard_sharded(be, poly_host, K * world, B, trs, 1)
+            levels_host_t.copy_(lv, non_blocking=False)
+        else:
+            ctx.commit_standard(poly_host, K, trs, 1, levels_out=levels_host)
+
+    levels_host_t = torch.from_numpy(levels_host)
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,6 +236,8 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             fn()
+        if world > 1:
+            torch.cuda.synchronize()          # the sharded step also runs torch/NCCL work on torch's streams
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -271,7 +289,8 @@ def main():
            "dtype": "u64 (F_p^2, p=2^61-1) + u32 BLAKE3", "data": "synthetic",
            "config": {"workload": "Our_PC commit_standard N=2^%d K=%d trs=%d linear_time (RS rows + Orion expander columns) + BLAKE3 Merkle (test_PC option 4 commit)" % (args.logn, K, trs),
                       "codeword_len": cw, "l2": "inputs larger than L2 (1 GiB polynomial, 4 GiB tensor per step)",
-                      "multi_gpu": "each rank commits its own polynomial (independent commitments; no data-path collective)" if world > 1 else "single GPU"},
+                      "multi_gpu": ("ONE commitment of 2^%d x %d coefficients: chunks sharded by rank, inner leaf digests exchanged by leaf range (NCCL all_to_all), "
+                                    "subtree levels all_gathered" % (args.logn, world)) if world > 1 else "single GPU"},
            "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(poly_host.nbytes),
                    "d2h_bytes_per_step": int(levels_host.nbytes)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}

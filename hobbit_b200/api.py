@@ -296,3 +296,25 @@ class Context:
         self._ck(self.lib.hb_mul_tree_stream(self.h, _ptr(xy), c_sz(len(xy)), int(vectors), c_sz(B), int(distance), int(naive), _ptr(pr), _ptr(xr),
                                              _ptr(rnd), _ptr(out), ctypes.byref(layers), ctypes.byref(ps)))
         return out, ps.value, layers.value
+
+    # ---- sharded commit building blocks (hobbit_b200/dist.py) ----
+    def commit_encode_chunks(self, poly, nchunks, B, trs, lin, inner_out=None):
+        """poly / inner_out: numpy arrays or int device pointers.  Returns inner digests (nchunks*B, 32) when inner_out is None."""
+        p = poly if isinstance(poly, int) else _F(poly)
+        ret = None
+        if inner_out is None:
+            ret = np.zeros((nchunks * B, 32), dtype=np.uint8)
+            inner_out = ret
+        self._ck(self.lib.hb_commit_encode_chunks(self.h, _ptr(p), c_sz(nchunks), c_sz(B), int(trs), int(lin), _ptr(inner_out)))
+        return ret
+
+    def md_chain(self, inner, nchunks, nleaves, leaves):
+        """leaves: numpy (nleaves, 32) uint8 or int device pointer; updated in place."""
+        i = inner if isinstance(inner, int) else np.ascontiguousarray(inner, dtype=np.uint8)
+        self._ck(self.lib.hb_md_chain(self.h, _ptr(i), c_sz(nchunks), c_sz(nleaves), _ptr(leaves)))
+        return leaves
+
+    def merkle_tree_inplace(self, levels, nleaves):
+        """levels: int device pointer or numpy (2*nleaves-1, 32) with the leaves already at the front."""
+        self._ck(self.lib.hb_merkle_tree(self.h, _ptr(levels), c_sz(nleaves)))
+        return levels

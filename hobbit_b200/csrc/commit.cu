@@ -297,6 +297,43 @@ extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K
     return 0;
 }
 
+// ---- C1, sharded form: the chunk-independent part and the chunk-ordered chain as two calls -----------------------
+extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out) {
+    if (nchunks == 0) return 0;
+    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_commit_encode_chunks: chunk size must be a power of two");
+    if (trs < 2 || (2 * trs) % 4) HB_FAIL(ctx, "hb_commit_encode_chunks: tensor_row_size must be even");
+    const size_t N = nchunks * B;
+    if (ctx->tensor_elems != 4 * N) {
+        if (ctx->tensor) cudaFree(ctx->tensor);
+        ctx->tensor = nullptr; ctx->tensor_elems = 0;
+        HB_CHECK(ctx, cudaMalloc(&ctx->tensor, 4 * N * sizeof(F)));
+        ctx->tensor_elems = 4 * N;
+    }
+    ctx->tensor_N = N; ctx->tensor_K = (int)nchunks; ctx->tensor_trs = trs;
+    Staged p(ctx), in(ctx);
+    HB_TRY(p.in(poly, N * sizeof(F)));
+    HB_TRY(in.outbuf(inner_out, N * 32));
+    // groups bound the size of one launch (grid.y) and keep the working set in L2-friendly pieces
+    const size_t G = std::max<size_t>(1, std::min<size_t>(nchunks, ((size_t)1 << 30) / (B * 32)));
+    for (size_t c0 = 0; c0 < nchunks; c0 += G) {
+        size_t nc = std::min(G, nchunks - c0);
+        HB_TRY(tensorcode_dev(ctx, p.as<F>() + c0 * B, B, trs, linear_time, ctx->tensor + c0 * 4 * B, nc, in.as<uint8_t>() + c0 * B * 32));
+    }
+    HB_TRY(in.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_md_chain(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves) {
+    Staged in(ctx), lv(ctx);
+    HB_TRY(in.in(inner, nchunks * nleaves * 32));
+    HB_TRY(lv.outbuf(leaves, nleaves * 32, true));
+    HB_TRY(md_chain_dev(ctx, in.as<uint8_t>(), nchunks, nleaves, lv.as<uint8_t>()));
+    HB_TRY(lv.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" const hb_F *hb_tensor_device(hb_ctx *ctx) { return (const hb_F *)ctx->tensor; }
 
 extern "C" int hb_tensor_gather(hb_ctx *ctx, const uint32_t *col, const uint32_t *row, size_t queries, hb_F *reply) {

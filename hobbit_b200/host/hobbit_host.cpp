@@ -293,4 +293,40 @@ mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input,
     return Pr;
 }
 
+void reset_stream(stream_descriptor &fd) { fd.pos = 0; fd.idx = 0; fd.stage = 0; fd.offset = 0; fd.finished = false; }   // witness_stream.cpp:228-234
+void read_stream(stream_descriptor &fd, std::vector<F> &v, int size) {                                                   // :2106-2353, default branch
+    static const char *circuit_names[] = {"input", "circuit", "witness", "wiring_consistency_check", "wiring_consistency_check_opt",
+                                          "lookup_basic", "lookup_witness_basic", "transcript_stream"};
+    for (const char *n : circuit_names)
+        if (fd.name == n) { printf("hobbit_b200: stream '%s' needs the circuit evaluator (out of scope this round)\n", n); exit(-1); }
+    for (int i = 0; i < size; i++) v[i] = F((i % 1024) + 1);
+}
+
+std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, int vectors, int size, F previous_r, int distance,
+                                                        std::vector<F> prev_x, bool naive, double &, double &ps) {
+    if (!prev_x.empty()) { printf("hobbit_b200: prove_multiplication_tree_stream_shallow with prev_x is not wired yet\n"); exit(-1); }
+    const size_t total = (size_t)size * vectors;
+    // the stream in its logical two-half form [X | Y]: one read of the whole stream (a two-half producer emits X-block | Y-block)
+    std::vector<F> xy(total);
+    reset_stream(fd);
+    read_stream(fd, xy, (int)total);
+    int layers = 0;
+    if (total > 2 * BUFFER_SPACE) {
+        layers = (int)std::log2((double)(total / (2 * BUFFER_SPACE)));
+        if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance);
+    }
+    // libc draws in the reference's order: the product tree's points, then per streamed layer a, (b0, b1), pad
+    std::vector<F> xr = generate_randomness((int)std::log2((double)vectors)), rnd;
+    for (int i = 0; i < layers; i++) {
+        F a = generate_randomness(1)[0]; std::vector<F> b = generate_randomness(2); F pad = F(random());
+        rnd.push_back(a); rnd.push_back(b[0]); rnd.push_back(b[1]); rnd.push_back(pad);
+    }
+    if (rnd.empty()) rnd.resize(4);
+    std::vector<F> out(vectors);
+    int got_layers = 0;
+    CK(hb_mul_tree_stream(backend(), (const hb_F *)xy.data(), total, vectors, BUFFER_SPACE, distance, naive ? 1 : 0, (const hb_F *)&previous_r,
+                          (const hb_F *)xr.data(), (const hb_F *)rnd.data(), (hb_F *)out.data(), &got_layers, &ps));
+    return out;
+}
+
 }  // namespace hobbit

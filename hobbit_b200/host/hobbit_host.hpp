@@ -115,5 +115,13 @@ proof _generate_3product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, 
 proof batch_3product_sumcheck(std::vector<std::vector<F>> &arr1, std::vector<std::vector<F>> &arr2, std::vector<std::vector<F>> &arr3,
                               std::vector<F> a, double &vt, double &ps);
 mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input, F previous_r, std::vector<F> prev_x, double &vt, double &ps);
+// witness_stream.h: name-dispatched producer.  Only the synthetic default stream (v[i] = F(i%1024+1)) exists without the
+// circuit evaluator; circuit streams ("wiring_consistency_check_opt", ...) are the next row.
+void read_stream(stream_descriptor &fd, std::vector<F> &v, int size);
+void reset_stream(stream_descriptor &fd);
+// sumcheck.cpp:1746-1915.  The stream is materialised ONCE into HBM (instead of being re-generated per pass) and every layer is
+// proven there; supported: size*vectors <= 2*BUFFER_SPACE, or layers <= distance, or naive.
+std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, int vectors, int size, F previous_r, int distance,
+                                                        std::vector<F> prev_x, bool naive, double &vt, double &ps);
 
 }  // namespace hobbit

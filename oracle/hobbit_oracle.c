@@ -671,3 +671,27 @@ double orc_mul_tree_stream(const F *xy, size_t total, int vectors, size_t B, int
     free(r); free(nr); free(buf);
     return ps;
 }
+
+/* C1 split for sharding (same arithmetic as orc_commit_standard): inner digests of `nchunks` chunks, and the chain. */
+void orc_commit_encode_chunks(const F *poly, size_t nchunks, size_t B, int trs, int lin, uint8_t *inner_out) {
+    size_t cols = 2 * B / trs;
+    F *T = (F *)malloc(4 * B * sizeof(F));
+    for (size_t c = 0; c < nchunks; c++) {
+        orc_compute_tensorcode(poly + c * B, B, trs, lin, T);
+        for (int j = 0; j < trs / 2; j++)
+            for (size_t k = 0; k < cols; k++) {
+                F q[4] = { T[(4 * j) * cols + k], T[(4 * j + 1) * cols + k], T[(4 * j + 2) * cols + k], T[(4 * j + 3) * cols + k] };
+                orc_blake3_hash((const uint8_t *)q, inner_out + (c * B + j * cols + k) * 32);
+            }
+    }
+    free(T);
+}
+void orc_md_chain(const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves) {
+    for (size_t c = 0; c < nchunks; c++)
+        for (size_t p = 0; p < nleaves; p++) {
+            uint8_t data[64];
+            memcpy(data, inner + (c * nleaves + p) * 32, 32);
+            memcpy(data + 32, leaves + p * 32, 32);
+            orc_blake3_hash(data, leaves + p * 32);
+        }
+}

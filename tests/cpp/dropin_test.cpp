@@ -164,6 +164,22 @@ int main() {
         for (size_t i = 0; ok && i < M.global_randomness.size(); i++) ok = eqF(M.global_randomness[i], HM.global_randomness[i]);
         CHECK(ok, "prove_multiplication_tree_new (8 x 512): output, out_eval, layer proofs, final_r, final_eval, ps");
     }
+    // ---- streaming product tree on the synthetic stream (MLP-shaped: 8 vectors, 4 streamed layers) ----------------------------
+    {
+        BUFFER_SPACE = 1 << 10; hobbit::BUFFER_SPACE = BUFFER_SPACE;
+        extern int BUFFER_SPACE_tr; BUFFER_SPACE_tr = BUFFER_SPACE / 8;
+        const size_t total = 1 << 15;
+        double vt = 0, ps = 0, hps = 0;
+        stream_descriptor fd; fd.name = "test"; fd.size = total; reset_stream(fd);
+        srand(31); vector<F> o = prove_multiplication_tree_stream_shallow(fd, 8, total / 8, F(32), 5, vector<F>(), 0, vt, ps);
+        int r1 = rand();
+        hobbit::stream_descriptor hfd; hfd.name = "test"; hfd.size = total;
+        srand(31); vector<hobbit::Fe> ho = hobbit::prove_multiplication_tree_stream_shallow(hfd, 8, total / 8, hobbit::Fe(32), 5, vector<hobbit::Fe>(), 0, vt, hps);
+        int r2 = rand();
+        bool ok = o.size() == ho.size() && ps == hps && r1 == r2;
+        for (size_t i = 0; ok && i < o.size(); i++) ok = eqF(o[i], ho[i]);
+        CHECK(ok, "prove_multiplication_tree_stream_shallow (8 x 4096, 4 streamed layers): products, ps, RNG state");
+    }
     printf(failures ? "DROPIN: %d FAILURES\n" : "DROPIN: all identical\n", failures);
     return failures ? 1 : 0;
 }

@@ -1,0 +1,72 @@
+"""N > 1 orchestration of the sharded commitment (hobbit_b200/dist.py) on CPU: world_size 2 and 4 over gloo, the compute backend
+being the C oracle.  Checks the exchange layout / chunk order / subtree assembly against the single-process oracle commitment.
+(The same orchestration with GpuBackend + NCCL is exercised by tests/test_dist_gpu.py and bench.py --gpus N.)"""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import Checker, _p, rand_field, srand
+
+
+class OracleBackend:
+    def __init__(self):
+        self.orc = Checker("orc")
+
+    def zeros(self, *shape):
+        return torch.zeros(shape, dtype=torch.uint8)
+
+    def encode_chunks(self, poly, nchunks, B, trs, lin):
+        inner = np.zeros((nchunks, B, 32), dtype=np.uint8)
+        self.orc.fn("commit_encode_chunks")(_p(poly), ctypes.c_size_t(nchunks), ctypes.c_size_t(B), trs, int(lin), _p(inner))
+        return torch.from_numpy(inner)
+
+    def chain(self, inner, leaves):
+        i = np.ascontiguousarray(inner.numpy()); l = leaves.numpy()
+        self.orc.fn("md_chain")(_p(i), ctypes.c_size_t(i.shape[0]), ctypes.c_size_t(i.shape[1]), _p(l))
+        return leaves
+
+    def tree(self, leaves):
+        return torch.from_numpy(self.orc.create_tree(np.ascontiguousarray(leaves.numpy())))
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def worker(rank, world, port, lin, K, B, trs, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hobbit_b200.dist import commit_standard_sharded
+    be = OracleBackend()
+    if lin:
+        srand(1); be.orc.expander_init_store(trs)
+    poly = rand_field(np.random.default_rng(77), K * B, full=False)
+    kl = K // world
+    levels = commit_standard_sharded(be, np.ascontiguousarray(poly[rank * kl * B:(rank + 1) * kl * B]), K, B, trs, lin)
+    want, _ = be.orc.commit_standard(poly, K, trs, lin)
+    ok = np.array_equal(levels.numpy(), want)
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,lin", [(2, 1), (2, 0), (4, 1)])
+def test_sharded_commit_gloo(world, lin):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, lin, 8, 1 << 10, 16, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1

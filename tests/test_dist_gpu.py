@@ -1,0 +1,70 @@
+"""Sharded commitment on real GPUs: GpuBackend pieces on one GPU (== the monolithic hb_commit_standard), and — when the box has
+at least 2 GPUs — 2 ranks over NCCL against the single-GPU commitment."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import Checker, rand_field, srand
+
+pytestmark = pytest.mark.gpu
+
+
+def setup_ctx(dev, trs):
+    import hobbit_b200
+    ctx = hobbit_b200.Context(dev)
+    orc = Checker("orc")
+    srand(1); orc.expander_init_store(trs)
+    ctx.expander_set(trs, orc.expander_graphs(trs))
+    return ctx
+
+
+def test_backend_pieces_equal_monolithic_commit():
+    import torch
+    from hobbit_b200.dist import GpuBackend, commit_standard_sharded
+    K, B, trs = 8, 1 << 12, 16
+    ctx = setup_ctx(0, trs)
+    poly = rand_field(np.random.default_rng(5), K * B, full=False)
+    want, _ = ctx.commit_standard(poly, K, trs, 1)
+    got = commit_standard_sharded(GpuBackend(ctx, torch.device("cuda", 0)), poly, K, B, trs, 1)
+    assert np.array_equal(got.cpu().numpy(), want)
+    ctx.close()
+
+
+def _worker(rank, world, port, K, B, trs, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from hobbit_b200.dist import GpuBackend, commit_standard_sharded
+    ctx = setup_ctx(rank, trs)
+    poly = rand_field(np.random.default_rng(6), K * B, full=False)
+    kl = K // world
+    got = commit_standard_sharded(GpuBackend(ctx, torch.device("cuda", rank)), np.ascontiguousarray(poly[rank * kl * B:(rank + 1) * kl * B]), K, B, trs, 1)
+    want, _ = ctx.commit_standard(poly, K, trs, 1)
+    ok = np.array_equal(got.cpu().numpy(), want)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+    ctx.close()
+
+
+def test_sharded_commit_nccl_2gpus():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2); the CPU/gloo twin is tests/test_dist_gloo.py")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    c = mp.get_context("spawn")
+    ret = c.Queue()
+    procs = [c.Process(target=_worker, args=(r, 2, port, 8, 1 << 12, 16, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1
