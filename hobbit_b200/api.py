@@ -318,3 +318,10 @@ class Context:
         """levels: int device pointer or numpy (2*nleaves-1, 32) with the leaves already at the front."""
         self._ck(self.lib.hb_merkle_tree(self.h, _ptr(levels), c_sz(nleaves)))
         return levels
+
+    def gate_consistency(self, L, R, O, add, r):
+        L, R, O, add, r = _F(L), _F(R), _F(O), _F(add), _F(r)
+        rounds = int(np.log2(len(L)))
+        out = np.zeros((6 * rounds + 6, 2), dtype=np.uint64)
+        self._ck(self.lib.hb_gate_consistency_standard(self.h, _ptr(L), _ptr(R), _ptr(O), _ptr(add), c_sz(len(L)), _ptr(r), _ptr(out)))
+        return out

@@ -195,6 +195,47 @@ partial_evals_kernel(const F *__restrict__ A, const F *__restrict__ beta, size_t
     }
 }
 
+// ---- gate consistency (sumcheck.cpp:434-501 and the final phase of :796-981): degree-4 round polynomial of
+//      beta(X) * ( mul(X) L(X) R(X) + add(X) (L(X) + R(X)) - O(X) ),  mul = 1 - add  (so mul needs no table of its own).
+// Tables: 0 add, 1 beta, 2 L, 3 R, 4 O.  Same fused fold-then-accumulate structure as sc_round_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+gate_round_kernel(Tabs<5> t, size_t L, F r, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) acc[c] = mkF(0, 0);
+    const F one = mkF(1, 0);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
+        F x[5], y[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            if (MODE == FOLD_THEN_POLY) {
+                const F *p = t.in[k] + 4 * j;
+                F a = p[0], b = p[1], c = p[2], d = p[3];
+                x[k] = fold1(a, b, r); y[k] = fold1(c, d, r);
+                t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y[k];
+            } else { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
+        }
+        F a0 = x[0], a1 = fsub(y[0], x[0]), m0 = fsub(one, a0), m1 = fneg(a1);
+        F b0 = x[1], b1 = fsub(y[1], x[1]), l0 = x[2], l1 = fsub(y[2], x[2]), r0 = x[3], r1 = fsub(y[3], x[3]), o0 = x[4], o1 = fsub(y[4], x[4]);
+        F ml2 = fmul(m1, l1), ml1 = fadd(fmul(m1, l0), fmul(m0, l1)), ml0 = fmul(m0, l0);
+        F q3 = fmul(ml2, r1);
+        F q2 = fadd(fmul(ml2, r0), fmul(ml1, r1));
+        F q1 = fadd(fmul(ml1, r0), fmul(ml0, r1));
+        F q0 = fmul(ml0, r0);
+        F s0 = fadd(l0, r0), s1 = fadd(l1, r1);
+        q2 = fadd(q2, fmul(a1, s1));
+        q1 = fsub(fadd(q1, fadd(fmul(a1, s0), fmul(a0, s1))), o1);
+        q0 = fsub(fadd(q0, fmul(a0, s0)), o0);
+        acc[0] = fadd(acc[0], fmul(b1, q3));
+        acc[1] = fadd(acc[1], fadd(fmul(b1, q2), fmul(b0, q3)));
+        acc[2] = fadd(acc[2], fadd(fmul(b1, q1), fmul(b0, q2)));
+        acc[3] = fadd(acc[3], fadd(fmul(b1, q0), fmul(b0, q1)));
+        acc[4] = fadd(acc[4], fmul(b0, q0));
+    }
+    grid_reduce<5>(acc, partial, ticket, result);
+}
+
 // product-tree level: out[j] = in[2j] * in[2j+1]   (sumcheck.cpp:84-101)
 __global__ void __launch_bounds__(256) prod_level_kernel(const F *__restrict__ in, F *__restrict__ out, size_t n_out) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (size_t)gridDim.x * blockDim.x)
@@ -225,11 +266,11 @@ __global__ void __launch_bounds__(256) beta_combine_kernel(const F *__restrict__
 // ---------------------------------------------------------------------------------------------------------
 static int ensure_scratch(hb_ctx *ctx) {
     if (!ctx->red) {
-        HB_CHECK(ctx, cudaMalloc(&ctx->red, (size_t)kMaxRedBlocks * 4 * sizeof(F) + 4 * sizeof(F)));
+        HB_CHECK(ctx, cudaMalloc(&ctx->red, (size_t)kMaxRedBlocks * 8 * sizeof(F) + 8 * sizeof(F)));
         HB_CHECK(ctx, cudaMalloc(&ctx->ticket, sizeof(unsigned)));
         HB_CHECK(ctx, cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
         HB_CHECK(ctx, cudaMallocHost(&ctx->mailbox, 64 * sizeof(F)));
-        ctx->mailbox_dev = ctx->red + (size_t)kMaxRedBlocks * 4;
+        ctx->mailbox_dev = ctx->red + (size_t)kMaxRedBlocks * 8;
     }
     return 0;
 }
@@ -789,4 +830,50 @@ extern "C" int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int
     cudaFreeAsync(owned, ctx->stream);
     *layers_out = layers;
     return rc;
+}
+
+// prove_gate_consistency_standard (sumcheck.cpp:434-501).  out: (a,b,c,d,e,rand) per round, then the final add, L, R, O, mul, beta.
+extern "C" int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *add_gate, size_t n,
+                                            const hb_F *r, hb_F *out) {
+    if (n < 2 || (n & (n - 1))) HB_FAIL(ctx, "hb_gate_consistency_standard: n must be a power of two >= 2");
+    HB_TRY(ensure_scratch(ctx));
+    const int rounds = ilog2(n);
+    Staged sl(ctx), sr(ctx), so(ctx), sa(ctx), srr(ctx);
+    HB_TRY(sl.in(L, n * sizeof(F))); HB_TRY(sr.in(R, n * sizeof(F))); HB_TRY(so.in(O, n * sizeof(F))); HB_TRY(sa.in(add_gate, n * sizeof(F)));
+    HB_TRY(srr.in(r, rounds * sizeof(F)));
+    F *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, (n + 5 * (n / 2 + n / 4 + 2)) * sizeof(F), ctx->stream));
+    F *beta = buf;
+    int rc = beta_dev(ctx, srr.as<F>(), rounds, beta);
+    const F *cur[5] = {sa.as<F>(), beta, sl.as<F>(), sr.as<F>(), so.as<F>()};
+    F *A[5], *Bf[5];
+    for (int k = 0; k < 5; k++) { A[k] = buf + n + (size_t)k * (n / 2 + n / 4 + 2); Bf[k] = A[k] + n / 2 + 1; }
+    F rand = mkF(213, 0);
+    for (int i = 0; i < rounds && !rc; i++) {
+        size_t Lp = n >> (i + 1);
+        F co[5];
+        Tabs<5> t;
+        for (int k = 0; k < 5; k++) { t.in[k] = cur[k]; t.out[k] = A[k]; }
+        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, ctx->red, ctx->ticket, ctx->mailbox_dev); }
+        else {
+            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, ctx->red, ctx->ticket, ctx->mailbox_dev);
+            for (int k = 0; k < 5; k++) { cur[k] = A[k]; std::swap(A[k], Bf[k]); }
+        }
+        rc = read_result(ctx, 5, co);
+        for (int c = 0; c < 5; c++) { rand = h_mimc(co[c], rand); out[6 * i + c] = toabi(co[c]); }     // mimc_hash(value, rand): N7
+        out[6 * i + 5] = toabi(rand);
+    }
+    F fin[5];
+    if (!rc) {
+        Tabs<5> t;
+        for (int k = 0; k < 5; k++) { t.in[k] = cur[k]; t.out[k] = A[k]; }
+        rc = launch_round<5, FOLD_ONLY, false>(ctx, t, 1, rand, nullptr);
+        if (!rc) rc = fetch_heads(ctx, A, 5, fin);
+    }
+    cudaFreeAsync(buf, ctx->stream);
+    if (rc) return rc;
+    hb_F *o = out + 6 * rounds;
+    o[0] = toabi(fin[0]); o[1] = toabi(fin[2]); o[2] = toabi(fin[3]); o[3] = toabi(fin[4]);
+    o[4] = toabi(fsub(mkF(1, 0), fin[0]));                   // mul = 1 - add folds to 1 - fold(add)
+    o[5] = toabi(fin[1]);
+    return 0;
 }

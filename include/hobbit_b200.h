@@ -138,6 +138,13 @@ int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, const hb_F *
 int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n, const hb_F *prev_r, const hb_F *x_rand,
                 hb_F *out, size_t *written, int *nfr, double *ps);
 
+/* ---- gate consistency, in-memory form: prove_gate_consistency_standard (sumcheck.cpp:434-501) --------------------------------- */
+/* Degree-4 sumcheck of beta(x) (mul(x) L(x) R(x) + add(x) (L(x)+R(x)) - O(x)), mul = 1 - add, beta = eq(r), rand_0 = F(213).
+ * The reference folds its arguments in place and returns nothing; here the inputs are untouched and
+ * out = (a,b,c,d,e,rand) per round [6*log2 n] | final add, L, R, O, mul, beta [6]. */
+int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *add_gate, size_t n,
+                                 const hb_F *r, hb_F *out);
+
 /* ---- S4/S6: streaming folding sumcheck with the witness stream resident in HBM (sumcheck.cpp:1093-1392, 1746-1915) --------- */
 /* xy: the stream in its logical two-half form [X | Y] (`total` elements; what read_stream emits as X-block | Y-block per read,
  * witness_stream.cpp:2276-2311).  Layer l is [seg_l(X) | seg_l(Y)] with 2^l-element segment products (read_mul_tree_data).

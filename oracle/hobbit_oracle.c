@@ -695,3 +695,59 @@ void orc_md_chain(const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t 
             orc_blake3_hash(data, leaves + p * 32);
         }
 }
+
+/* -------------------------------------------------------- gate consistency ---
+ * prove_gate_consistency_standard (sumcheck.cpp:434-501): degree-4 sumcheck of
+ *     sum_x beta(x) * ( mul(x) L(x) R(x) + add(x) (L(x) + R(x)) - O(x) ),  mul = 1 - add, beta = eq(r),
+ * rand starts at F(213); per round rand = mimc(e, mimc(d, mimc(c, mimc(b, mimc(a, rand))))) with the (value, rand) argument order;
+ * the tables are folded with the new rand.  The reference returns nothing (tables are folded in place); out gets, per round,
+ * (a,b,c,d,e) and rand [6*rounds], then the final add, L, R, O, mul, beta values [6]. */
+void orc_gate_consistency_standard(const F *L_in, const F *R_in, const F *O_in, const F *add_in, size_t n, const F *r, F *out) {
+    int rounds = ilog2(n);
+    F *t = (F *)malloc(6 * n * sizeof(F));
+    F *A = t, *Bt = t + n, *L = t + 2 * n, *R = t + 3 * n, *O = t + 4 * n, *M = t + 5 * n;
+    memcpy(A, add_in, n * sizeof(F)); memcpy(L, L_in, n * sizeof(F)); memcpy(R, R_in, n * sizeof(F)); memcpy(O, O_in, n * sizeof(F));
+    for (size_t i = 0; i < n; i++) M[i] = f_sub(F1, A[i]);
+    orc_precompute_beta(r, rounds, Bt);
+    F rand = f_int(213);
+    size_t k = 0;
+    for (int i = 0; i < rounds; i++) {
+        size_t half = (size_t)1 << (rounds - 1 - i);
+        F p[5] = { F0, F0, F0, F0, F0 };             /* a (X^4) .. e (X^0) */
+        for (size_t j = 0; j < half; j++) {
+            /* linear factors: value at 0 and slope */
+            F a0 = A[2 * j], a1 = f_sub(A[2 * j + 1], a0), m0 = M[2 * j], m1 = f_sub(M[2 * j + 1], m0);
+            F b0 = Bt[2 * j], b1 = f_sub(Bt[2 * j + 1], b0), l0 = L[2 * j], l1 = f_sub(L[2 * j + 1], l0);
+            F r0 = R[2 * j], r1 = f_sub(R[2 * j + 1], r0), o0 = O[2 * j], o1 = f_sub(O[2 * j + 1], o0);
+            /* q(X) = m(X) l(X) r(X) + a(X) (l(X) + r(X)) - o(X)  (cubic: q3..q0) */
+            F ml2 = f_mul(m1, l1), ml1 = f_add(f_mul(m1, l0), f_mul(m0, l1)), ml0 = f_mul(m0, l0);
+            F q3 = f_mul(ml2, r1);
+            F q2 = f_add(f_mul(ml2, r0), f_mul(ml1, r1));
+            F q1 = f_add(f_mul(ml1, r0), f_mul(ml0, r1));
+            F q0 = f_mul(ml0, r0);
+            F s0 = f_add(l0, r0), s1 = f_add(l1, r1);
+            q2 = f_add(q2, f_mul(a1, s1));
+            q1 = f_add(q1, f_add(f_mul(a1, s0), f_mul(a0, s1)));
+            q0 = f_add(q0, f_mul(a0, s0));
+            q1 = f_sub(q1, o1); q0 = f_sub(q0, o0);
+            /* times beta(X) */
+            p[0] = f_add(p[0], f_mul(b1, q3));
+            p[1] = f_add(p[1], f_add(f_mul(b1, q2), f_mul(b0, q3)));
+            p[2] = f_add(p[2], f_add(f_mul(b1, q1), f_mul(b0, q2)));
+            p[3] = f_add(p[3], f_add(f_mul(b1, q0), f_mul(b0, q1)));
+            p[4] = f_add(p[4], f_mul(b0, q0));
+        }
+        for (int c = 0; c < 5; c++) { rand = mimc(p[c], rand); out[k++] = p[c]; }
+        out[k++] = rand;
+        for (size_t j = 0; j < half; j++) {
+            A[j] = f_add(A[2 * j], f_mul(rand, f_sub(A[2 * j + 1], A[2 * j])));
+            L[j] = f_add(L[2 * j], f_mul(rand, f_sub(L[2 * j + 1], L[2 * j])));
+            R[j] = f_add(R[2 * j], f_mul(rand, f_sub(R[2 * j + 1], R[2 * j])));
+            O[j] = f_add(O[2 * j], f_mul(rand, f_sub(O[2 * j + 1], O[2 * j])));
+            M[j] = f_add(M[2 * j], f_mul(rand, f_sub(M[2 * j + 1], M[2 * j])));
+            Bt[j] = f_add(Bt[2 * j], f_mul(rand, f_sub(Bt[2 * j + 1], Bt[2 * j])));
+        }
+    }
+    out[k++] = A[0]; out[k++] = L[0]; out[k++] = R[0]; out[k++] = O[0]; out[k++] = M[0]; out[k++] = Bt[0];
+    free(t);
+}

@@ -63,6 +63,8 @@ int orc_stream_sumcheck_layer(const orc_F *xy, size_t total, size_t B, int layer
                               orc_F *new_claim, orc_F *new_r, double *ps_out);
 double orc_mul_tree_stream(const orc_F *xy, size_t total, int vectors, size_t B, int distance, int naive, const orc_F *prev_r, orc_F *out);
 
+/* prove_gate_consistency_standard (sumcheck.cpp:434-501); out: (a,b,c,d,e,rand) x rounds | final add, L, R, O, mul, beta */
+void orc_gate_consistency_standard(const orc_F *L, const orc_F *R, const orc_F *O, const orc_F *add_gate, size_t n, const orc_F *r, orc_F *out);
 /* C1 split for sharding: inner leaf digests of chunks, and the Merkle–Damgård chain over chunks */
 void orc_commit_encode_chunks(const orc_F *poly, size_t nchunks, size_t B, int trs, int lin, uint8_t *inner_out);
 void orc_md_chain(const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);

@@ -299,4 +299,16 @@ double ref_mul_tree_stream(size_t total, int vectors, size_t B, int distance, in
     return ps;
 }
 
+// prove_gate_consistency_standard (sumcheck.cpp:434-501) folds its arguments in place and returns nothing: out4 = the final
+// add_gate[0], arr_L[0], arr_R[0], arr_O[0] (they depend on every round polynomial through the challenge chain).
+void ref_gate_consistency_standard(const uint64_t *L, const uint64_t *R, const uint64_t *O, const uint64_t *add_gate, size_t n, const uint64_t *r, uint64_t *out4) {
+    vector<F> l((const F *)L, (const F *)L + n), rr((const F *)R, (const F *)R + n), o((const F *)O, (const F *)O + n), a((const F *)add_gate, (const F *)add_gate + n);
+    int nr = 0; while (((size_t)1 << nr) < n) nr++;
+    vector<F> rv((const F *)r, (const F *)r + nr);
+    double vt = 0, ps = 0;
+    prove_gate_consistency_standard(l, rr, o, a, rv, vt, ps);
+    F res[4] = { a[0], l[0], rr[0], o[0] };
+    memcpy(out4, res, 64);
+}
+
 } // extern "C"

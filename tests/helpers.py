@@ -260,3 +260,20 @@ def _mul_tree_stream(self, xy, vectors, B, distance, naive, prev_r):
 
 Checker.stream_layer = _stream_layer
 Checker.mul_tree_stream = _mul_tree_stream
+
+
+def _gate_consistency(self, L, R, O, add, r):
+    """Returns (final add, L, R, O) [4 F] for 'ref'; the full transcript (6*rounds + 6 F) for 'orc'."""
+    L, R, O, add, r = F(L), F(R), F(O), F(add), F(r)
+    n = len(L)
+    rounds = int(np.log2(n))
+    if self.kind == "ref":
+        out = fzeros(4)
+        self.fn("gate_consistency_standard")(_p(L), _p(R), _p(O), _p(add), ctypes.c_size_t(n), _p(r), _p(out))
+        return out
+    out = fzeros(6 * rounds + 6)
+    self.fn("gate_consistency_standard")(_p(L), _p(R), _p(O), _p(add), ctypes.c_size_t(n), _p(r), _p(out))
+    return out
+
+
+Checker.gate_consistency = _gate_consistency

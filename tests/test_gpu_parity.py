@@ -285,3 +285,20 @@ def test_mul_tree_stream(ctx, chk, total, vectors, B, synthetic):
     want = chk.mul_tree_stream(xy, vectors, B, 5, 0, F([32, 0]))
     assert got[2] == layers
     assert np.array_equal(got[0], want[0]) and got[1] == want[1]
+
+
+@pytest.mark.parametrize("n", [2, 64, 1 << 14])
+def test_gate_consistency_standard(ctx, chk, n):
+    rng = np.random.default_rng(n)
+    orc = Checker("orc")
+    L, R, add = rand_field(rng, n), rand_field(rng, n), np.zeros((n, 2), dtype=np.uint64)
+    add[:, 0] = rng.integers(0, 2, n)
+    O = np.where(add[:, :1] == 1, orc.binop(0, L, R), orc.binop(2, L, R))
+    r = rand_field(rng, int(np.log2(n)))
+    got = ctx.gate_consistency(L, R, O, add, r)
+    want = chk.gate_consistency(L, R, O, add, r)
+    rounds = int(np.log2(n))
+    if chk.kind == "ref":
+        assert np.array_equal(got[6 * rounds:6 * rounds + 4], want)      # the reference exposes only the folded tables
+    else:
+        assert np.array_equal(got, want)

@@ -167,3 +167,21 @@ def test_mul_tree_stream(libs, total, vectors, B):
     srand(2); a = orc.mul_tree_stream(xy, vectors, B, 5, 0, F([32, 0]))
     srand(2); b = ref.mul_tree_stream(xy, vectors, B, 5, 0, F([32, 0]))
     assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+
+
+@pytest.mark.parametrize("n", [2, 64, 1024])
+def test_gate_consistency_standard(libs, n):
+    orc, ref = libs
+    rng = np.random.default_rng(n)
+    L, R, add = rand_field(rng, n), rand_field(rng, n), np.zeros((n, 2), dtype=np.uint64)
+    add[:, 0] = rng.integers(0, 2, n)                       # selector: 1 = add gate, 0 = mul gate
+    O = np.where(add[:, :1] == 1, orc.binop(0, L, R), orc.binop(2, L, R))
+    r = rand_field(rng, int(np.log2(n)))
+    full = orc.gate_consistency(L, R, O, add, r)
+    want = ref.gate_consistency(L, R, O, add, r)
+    rounds = int(np.log2(n))
+    assert np.array_equal(full[6 * rounds:6 * rounds + 4], want)
+    # a consistent circuit sums to zero: first round polynomial p(0) + p(1) == 0
+    a, b, c, d, e = (full[i:i + 1] for i in range(5))
+    s = orc.binop(0, orc.binop(0, orc.binop(0, a, b), orc.binop(0, c, d)), orc.binop(0, e, e))
+    assert not s.any()
