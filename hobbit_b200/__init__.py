@@ -4,6 +4,6 @@ The product is the CUDA library ``libhobbit_b200.so`` behind the C ABI in ``incl
 thin ctypes binding plus the Python mirror of the reference's entry points.  There is no CPU fallback: importing works
 anywhere (so the build can be checked), but creating a Context without the built library or without a GPU raises.
 """
-from .api import Context, HobbitError, lib_path, load_library  # noqa: F401
+from .api import Context, DevF, HobbitError, lib_path, load_library  # noqa: F401
 
-__all__ = ["Context", "HobbitError", "lib_path", "load_library"]
+__all__ = ["Context", "DevF", "HobbitError", "lib_path", "load_library"]

@@ -37,7 +37,25 @@ def load_library():
     return _LIB
 
 
+class DevF:
+    """A device-resident F array: (raw device pointer, element count).  Accepted wherever a numpy F array is; build it from a
+    torch CUDA tensor with DevF.from_torch(t) (t: int64/uint64 tensor of shape (n, 2))."""
+
+    def __init__(self, ptr, n, keep=None):
+        self.ptr, self.n, self.keep = int(ptr), int(n), keep
+
+    @classmethod
+    def from_torch(cls, t):
+        assert t.is_cuda and t.is_contiguous() and t.shape[-1] == 2 and t.element_size() == 8
+        return cls(t.data_ptr(), t.numel() // 2, keep=t)
+
+    def __len__(self):
+        return self.n
+
+
 def _F(a):
+    if isinstance(a, DevF):
+        return a
     a = np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
     return a.reshape(-1, 2)
 
@@ -45,6 +63,8 @@ def _F(a):
 def _ptr(a):
     if a is None:
         return None
+    if isinstance(a, DevF):
+        return c_vp(a.ptr)
     if isinstance(a, int):          # raw device pointer (e.g. torch tensor .data_ptr())
         return c_vp(a)
     return a.ctypes.data_as(c_vp)
@@ -325,3 +345,13 @@ class Context:
         out = np.zeros((6 * rounds + 6, 2), dtype=np.uint64)
         self._ck(self.lib.hb_gate_consistency_standard(self.h, _ptr(L), _ptr(R), _ptr(O), _ptr(add), c_sz(len(L)), _ptr(r), _ptr(out)))
         return out
+
+    def gate_consistency_stream(self, L, R, O, S, B, r, rnd10):
+        L, R, O, S, r, rnd = _F(L), _F(R), _F(O), _F(S), _F(r), _F(rnd10)
+        cs = len(L); nch = cs // B
+        lgB, lgn = int(np.log2(B)), int(np.log2(nch))
+        out = np.zeros((nch + 6 * lgB + 6 + 6 * nch + 4 * lgn + 3, 2), dtype=np.uint64)
+        ps = ctypes.c_double(0)
+        self._ck(self.lib.hb_gate_consistency_stream(self.h, _ptr(L), _ptr(R), _ptr(O), _ptr(S), c_sz(cs), c_sz(B), _ptr(r), _ptr(rnd),
+                                                     _ptr(out), ctypes.byref(ps)))
+        return out, ps.value

@@ -111,11 +111,10 @@ extern "C" int hb_ctx_create(hb_ctx **out, int device) {
 
 static void elastic_free(hb_ctx *ctx) {
     ElasticState &el = ctx->el;
-    for (int i = 0; i < 3; i++) if (el.park[i]) cudaFree(el.park[i]);
-    if (el.tensor) cudaFree(el.tensor);
-    if (el.msg) cudaFree(el.msg);
-    if (el.leaves) cudaFree(el.leaves);
-    if (el.nz_flag) cudaFree(el.nz_flag);
+    for (int i = 0; i < 3; i++) if (el.park[i]) cudaFreeAsync(el.park[i], ctx->stream);
+    if (el.tensor) cudaFreeAsync(el.tensor, ctx->stream);
+    if (el.msg) cudaFreeAsync(el.msg, ctx->stream);
+    if (el.leaves) cudaFreeAsync(el.leaves, ctx->stream);
     el = ElasticState();
 }
 
@@ -377,11 +376,11 @@ extern "C" int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time)
     elastic_free(ctx);
     ElasticState &el = ctx->el;
     el.B = B; el.trs = trs; el.lin = linear_time; el.chunk_idx = 0;
-    for (int i = 0; i < 3; i++) HB_CHECK(ctx, cudaMalloc(&el.park[i], 4 * B * sizeof(F)));
-    HB_CHECK(ctx, cudaMalloc(&el.tensor, 4 * B * sizeof(F)));
-    HB_CHECK(ctx, cudaMalloc(&el.msg, B * sizeof(F)));
-    HB_CHECK(ctx, cudaMalloc(&el.leaves, (8 * B - 1) * 32));
-    HB_CHECK(ctx, cudaMalloc(&el.nz_flag, sizeof(int)));
+    // stream-ordered pool allocations: a commit per call must not pay cudaMalloc/cudaFree (milliseconds each)
+    for (int i = 0; i < 3; i++) HB_CHECK(ctx, cudaMallocAsync(&el.park[i], 4 * B * sizeof(F), ctx->stream));
+    HB_CHECK(ctx, cudaMallocAsync(&el.tensor, 4 * B * sizeof(F), ctx->stream));
+    HB_CHECK(ctx, cudaMallocAsync(&el.msg, B * sizeof(F), ctx->stream));
+    HB_CHECK(ctx, cudaMallocAsync(&el.leaves, (8 * B - 1) * 32, ctx->stream));
     HB_CHECK(ctx, cudaMemsetAsync(el.leaves, 0, 4 * B * 32, ctx->stream));   // Elastic_PC.cpp:195-199
     el.active = true;
     return 0;
@@ -398,14 +397,9 @@ extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) {
     }
     const unsigned slot = (unsigned)(el.chunk_idx % 4);
     F *T = slot == 3 ? el.tensor : el.park[slot];          // encode straight into the parking slot: no copy
-    // all-zero chunk => all-zero tensor, no encode (Elastic_PC.cpp:206-222)
-    int nz = 0;
-    HB_CHECK(ctx, cudaMemsetAsync(el.nz_flag, 0, sizeof(int), ctx->stream));
-    HB_LAUNCH(ctx, any_nonzero_kernel, (unsigned)std::min<size_t>((B + 255) / 256, (size_t)ctx->sm_count * 4), 256, 0, src, B, el.nz_flag);
-    HB_CHECK(ctx, cudaMemcpyAsync(&nz, el.nz_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (nz) HB_TRY(tensorcode_dev(ctx, src, B, el.trs, el.lin, T, 1, nullptr));
-    else HB_CHECK(ctx, cudaMemsetAsync(T, 0, 4 * B * sizeof(F), ctx->stream));
+    // The reference skips the encode of an all-zero chunk and zero-fills the tensor (Elastic_PC.cpp:206-222).  Both codes are
+    // linear, so encoding the zero chunk yields exactly that all-zero tensor: no test, no host round trip, same bits.
+    HB_TRY(tensorcode_dev(ctx, src, B, el.trs, el.lin, T, 1, nullptr));
     if (slot == 3) HB_TRY(md_leaves_stream4_dev(ctx, el.park[0], el.park[1], el.park[2], el.tensor, 4 * B, el.leaves));
     el.chunk_idx++;
     return 0;

@@ -60,7 +60,7 @@ struct hb_ctx {
     hb::F *poly = nullptr; size_t poly_elems = 0; const void *poly_host = nullptr;
     hb::ElasticState el;
     // sumcheck reduction scratch: per-CTA partial coefficients + ticket counter (device), result mailbox (pinned host)
-    hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr;
+    hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr; unsigned long long seq = 0;
     // optional per-kernel timing (hb_profile_*): CUDA events around every launch, on this context's stream
     bool prof = false;
     struct ProfRec { const char *name; cudaEvent_t e0, e1; };

@@ -67,16 +67,18 @@ __device__ __forceinline__ F fmul(F a, F b) {
 // a * real scalar s (s canonical)
 __device__ __forceinline__ F fmul_real(F a, u64 s) { return mkF(mul61(a.re, s), mul61(a.im, s)); }
 
-// host twins (used by the host-side control code: MiMC, twiddle tables, eq tables for tiny sizes)
-static inline u64 h_mul61(u64 a, u64 b) {
-    unsigned __int128 x = (unsigned __int128)a * b;
-    u64 lo = (u64)x & P61, hi = (u64)(x >> 61);
-    u64 s = lo + (hi & P61) + (hi >> 61);
+// host twins (host-side control code: MiMC chain, twiddle tables, a handful of scalar combinations per round).
+// MiMC is 322 dependent multiplications per hash and sits on the critical path between sumcheck rounds, so the host
+// multiply does one 128-bit reduction per output limb: re = ac + (p^2 - bd), im = ad + bc.
+static inline u64 h_red128(unsigned __int128 x) {          // x < 2^124 -> canonical
+    u64 s = ((u64)x & P61) + ((u64)(x >> 61) & P61) + (u64)(x >> 122);
     return canon61(fold61(s));
 }
+static inline u64 h_mul61(u64 a, u64 b) { return h_red128((unsigned __int128)a * b); }
 static inline F h_fmul(F a, F b) {
-    u64 ac = h_mul61(a.re, b.re), bd = h_mul61(a.im, b.im), ad = h_mul61(a.re, b.im), bc = h_mul61(a.im, b.re);
-    return mkF(sub61(ac, bd), add61(ad, bc));
+    typedef unsigned __int128 u128;
+    const u128 p2 = (u128)P61 * P61;
+    u128 ac = (u128)a.re * b.re, bd = (u128)a.im * b.im, ad = (u128)a.re * b.im, bc = (u128)a.im * b.re;
+    return mkF(h_red128(ac + (p2 - bd)), h_red128(ad + bc));
 }
-
 }  // namespace hb

@@ -49,6 +49,8 @@ __device__ __forceinline__ F shfl_down_F(F v, int d) {
 
 // warp -> CTA -> grid reduction of NC field accumulators: warp shuffles, shared memory across warps, per-CTA partials in
 // global memory, and the last CTA to take a ticket sums the partials and writes `result[0..NC)` (then re-arms the ticket).
+// `result` is a host-mapped (pinned) mailbox: the coefficients are written straight into host memory, followed by a sequence
+// number the host spins on — no D2H copy and no stream synchronisation on the round-to-round critical path.
 template <int NC>
 __device__ __forceinline__ void grid_reduce(F (&acc)[NC], F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
     __shared__ F sred[8][NC];
@@ -90,9 +92,19 @@ __device__ __forceinline__ void grid_reduce(F (&acc)[NC], F *__restrict__ partia
     if (threadIdx.x < NC) {
         F v = sred[0][threadIdx.x];
         for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = fadd(v, sred[w][threadIdx.x]);
-        result[threadIdx.x] = v;
+        volatile u64 *rv = reinterpret_cast<volatile u64 *>(result + threadIdx.x);
+        rv[0] = v.re; rv[1] = v.im;
+        __threadfence_system();
     }
-    if (threadIdx.x == 0) *ticket = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile u64 *seq = reinterpret_cast<volatile u64 *>(result + 15);       // mailbox slot 15 = sequence number
+        ticket[0] = 0;
+        unsigned next = ticket[1] + 1;                                            // launch counter kept in device memory
+        ticket[1] = next;
+        __threadfence_system();
+        seq[0] = next;
+    }
 }
 
 // INTERLEAVED: tables 0 and 1 are the even/odd entries of one array t.in[0] (product-tree layer: in1[j]=prev[2j],
@@ -198,13 +210,16 @@ partial_evals_kernel(const F *__restrict__ A, const F *__restrict__ beta, size_t
 // ---- gate consistency (sumcheck.cpp:434-501 and the final phase of :796-981): degree-4 round polynomial of
 //      beta(X) * ( mul(X) L(X) R(X) + add(X) (L(X) + R(X)) - O(X) ),  mul = 1 - add  (so mul needs no table of its own).
 // Tables: 0 add, 1 beta, 2 L, 3 R, 4 O.  Same fused fold-then-accumulate structure as sc_round_kernel.
+// General form (streaming variant, :877-935): beta(X) * ( w.a2 * mul(X) L(X) R(X) + add(X) (w.a0 L(X) + w.a1 R(X)) + w.a3 O(X) ) with
+// mul = w.c - add (the folded selector tables satisfy fold_mul = (sum of the fold challenges) - fold_add).  The in-memory prover is
+// a0 = a1 = a2 = 1, a3 = -1, c = 1.
+struct GateW { F a0, a1, a2, a3, c; };
 template <int MODE>
 __global__ void __launch_bounds__(256)
-gate_round_kernel(Tabs<5> t, size_t L, F r, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+gate_round_kernel(Tabs<5> t, size_t L, F r, GateW w, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
     F acc[5];
 #pragma unroll
     for (int c = 0; c < 5; c++) acc[c] = mkF(0, 0);
-    const F one = mkF(1, 0);
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
         F x[5], y[5];
 #pragma unroll
@@ -216,17 +231,17 @@ gate_round_kernel(Tabs<5> t, size_t L, F r, F *__restrict__ partial, unsigned *_
                 t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y[k];
             } else { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
         }
-        F a0 = x[0], a1 = fsub(y[0], x[0]), m0 = fsub(one, a0), m1 = fneg(a1);
+        F a0 = x[0], a1 = fsub(y[0], x[0]), m0 = fmul(w.a2, fsub(w.c, a0)), m1 = fmul(w.a2, fneg(a1));     // a2 * mul(X)
         F b0 = x[1], b1 = fsub(y[1], x[1]), l0 = x[2], l1 = fsub(y[2], x[2]), r0 = x[3], r1 = fsub(y[3], x[3]), o0 = x[4], o1 = fsub(y[4], x[4]);
         F ml2 = fmul(m1, l1), ml1 = fadd(fmul(m1, l0), fmul(m0, l1)), ml0 = fmul(m0, l0);
         F q3 = fmul(ml2, r1);
         F q2 = fadd(fmul(ml2, r0), fmul(ml1, r1));
         F q1 = fadd(fmul(ml1, r0), fmul(ml0, r1));
         F q0 = fmul(ml0, r0);
-        F s0 = fadd(l0, r0), s1 = fadd(l1, r1);
+        F s0 = fadd(fmul(w.a0, l0), fmul(w.a1, r0)), s1 = fadd(fmul(w.a0, l1), fmul(w.a1, r1));
         q2 = fadd(q2, fmul(a1, s1));
-        q1 = fsub(fadd(q1, fadd(fmul(a1, s0), fmul(a0, s1))), o1);
-        q0 = fsub(fadd(q0, fmul(a0, s0)), o0);
+        q1 = fadd(fadd(q1, fadd(fmul(a1, s0), fmul(a0, s1))), fmul(w.a3, o1));
+        q0 = fadd(fadd(q0, fmul(a0, s0)), fmul(w.a3, o0));
         acc[0] = fadd(acc[0], fmul(b1, q3));
         acc[1] = fadd(acc[1], fadd(fmul(b1, q2), fmul(b0, q3)));
         acc[2] = fadd(acc[2], fadd(fmul(b1, q1), fmul(b0, q2)));
@@ -234,6 +249,96 @@ gate_round_kernel(Tabs<5> t, size_t L, F r, F *__restrict__ partial, unsigned *_
         acc[4] = fadd(acc[4], fmul(b0, q0));
     }
     grid_reduce<5>(acc, partial, ticket, result);
+}
+
+// ---- S7 streaming pass (sumcheck.cpp:796-870): fold tables 0 add(S), 1 beta, 2 L, 3 R, 4 O; fold_mul = csum - fold_add ---------
+// chunk 0: folds := chunk, Kf_O, Kf_L, Kf_R, Kf_M (:815-824)
+__global__ void __launch_bounds__(256)
+gs_init_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
+               F *__restrict__ fA, F *__restrict__ fB, F *__restrict__ fL, F *__restrict__ fR, F *__restrict__ fO, size_t B,
+               F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[4] = {mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0)};
+    const F one = mkF(1, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
+        F l = L[i], r = R[i], o = O[i], s = S[i], b = beta[i];
+        fA[i] = s; fB[i] = b; fL[i] = l; fR[i] = r; fO[i] = o;
+        F bl = fmul(b, l), br = fmul(b, r);
+        acc[0] = fadd(acc[0], fmul(b, o));
+        acc[1] = fadd(acc[1], fmul(bl, s));
+        acc[2] = fadd(acc[2], fmul(br, s));
+        acc[3] = fadd(acc[3], fmul(fmul(br, l), fsub(one, s)));
+    }
+    grid_reduce<4>(acc, partial, ticket, result);
+}
+// the 12 error terms of folding one more chunk (compute2p/3p/4p_error_terms, :374-432): K1_O K2_O | K1_L K2_L K3_L | K1_R K2_R K3_R | K1_M..K4_M
+__global__ void __launch_bounds__(256)
+gs_err_kernel(const F *__restrict__ bL, const F *__restrict__ bR, const F *__restrict__ bO, const F *__restrict__ bS, const F *__restrict__ beta,
+              const F *__restrict__ fA, const F *__restrict__ fB, const F *__restrict__ fL, const F *__restrict__ fR, const F *__restrict__ fO,
+              F csum, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) acc[c] = mkF(0, 0);
+    const F one = mkF(1, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
+        F xl = bL[i], xr = bR[i], xo = bO[i], g = bS[i], ng = fsub(one, g), be = beta[i];
+        F a = fA[i], fb = fB[i], l = fL[i], r = fR[i], o = fO[i], m = fsub(csum, a);
+        acc[0] = fadd(acc[0], fadd(fmul(xo, fb), fmul(be, o)));
+        acc[1] = fadd(acc[1], fmul(xo, be));
+        F t1 = fadd(fmul(xl, a), fmul(g, l)), t2 = fmul(xl, g);
+        acc[2] = fadd(acc[2], fadd(fmul(fb, t1), fmul(fmul(be, l), a)));
+        acc[3] = fadd(acc[3], fadd(fmul(be, t1), fmul(fb, t2)));
+        acc[4] = fadd(acc[4], fmul(t2, be));
+        t1 = fadd(fmul(xr, a), fmul(g, r)); t2 = fmul(xr, g);
+        acc[5] = fadd(acc[5], fadd(fmul(fb, t1), fmul(fmul(be, r), a)));
+        acc[6] = fadd(acc[6], fadd(fmul(be, t1), fmul(fb, t2)));
+        acc[7] = fadd(acc[7], fmul(t2, be));
+        F u1 = fadd(fmul(l, xr), fmul(r, xl)), u2 = fadd(fmul(fb, ng), fmul(m, be));
+        F u3 = fmul(xl, xr), u4 = fmul(ng, be), u5 = fmul(l, r), u6 = fmul(fb, m);
+        acc[8] = fadd(acc[8], fadd(fmul(u1, u6), fmul(u2, u5)));
+        acc[9] = fadd(acc[9], fadd(fadd(fmul(u1, u2), fmul(u3, u6)), fmul(u4, u5)));
+        acc[10] = fadd(acc[10], fadd(fmul(u1, u4), fmul(u2, u3)));
+        acc[11] = fadd(acc[11], fmul(u3, u4));
+    }
+    grid_reduce<12>(acc, partial, ticket, result);
+}
+__global__ void __launch_bounds__(256)
+gs_fold_kernel(const F *__restrict__ bL, const F *__restrict__ bR, const F *__restrict__ bO, const F *__restrict__ bS, const F *__restrict__ beta,
+               F *__restrict__ fA, F *__restrict__ fB, F *__restrict__ fL, F *__restrict__ fR, F *__restrict__ fO, F rho, size_t B) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
+        fA[i] = fadd(fA[i], fmul(rho, bS[i])); fB[i] = fadd(fB[i], fmul(rho, beta[i]));
+        fL[i] = fadd(fL[i], fmul(rho, bL[i])); fR[i] = fadd(fR[i], fmul(rho, bR[i])); fO[i] = fadd(fO[i], fmul(rho, bO[i]));
+    }
+}
+// pass B (:943-955): per chunk c the dot products of eq(sumcheck_rand) with L, R, O, S; grid (parts, nch), out[(c*parts+part)*4 + k];
+// chunk-independent sums (sum beta1, sum beta1*beta) are appended by part 0.. of an extra pseudo-chunk (blockIdx.y == nch).
+__global__ void __launch_bounds__(256)
+gs_peval_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
+                const F *__restrict__ beta1, size_t B, unsigned nch, F *__restrict__ out) {
+    __shared__ F sred[8][4];
+    const size_t base = (size_t)blockIdx.y * B;
+    const bool extra = blockIdx.y == nch;
+    F a[4] = {mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0)};
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x) {
+        F b1 = beta1[j];
+        if (extra) { a[0] = fadd(a[0], b1); a[1] = fadd(a[1], fmul(b1, beta[j])); }
+        else {
+            a[0] = fadd(a[0], fmul(b1, L[base + j])); a[1] = fadd(a[1], fmul(b1, R[base + j]));
+            a[2] = fadd(a[2], fmul(b1, O[base + j])); a[3] = fadd(a[3], fmul(b1, S[base + j]));
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a[k] = fadd(a[k], shfl_down_F(a[k], d));
+        if (lane == 0) sred[warp][k] = a[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        F v = sred[0][threadIdx.x];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = fadd(v, sred[w][threadIdx.x]);
+        out[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = v;
+    }
 }
 
 // product-tree level: out[j] = in[2j] * in[2j+1]   (sumcheck.cpp:84-101)
@@ -266,12 +371,32 @@ __global__ void __launch_bounds__(256) beta_combine_kernel(const F *__restrict__
 // ---------------------------------------------------------------------------------------------------------
 static int ensure_scratch(hb_ctx *ctx) {
     if (!ctx->red) {
-        HB_CHECK(ctx, cudaMalloc(&ctx->red, (size_t)kMaxRedBlocks * 8 * sizeof(F) + 8 * sizeof(F)));
-        HB_CHECK(ctx, cudaMalloc(&ctx->ticket, sizeof(unsigned)));
-        HB_CHECK(ctx, cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
-        HB_CHECK(ctx, cudaMallocHost(&ctx->mailbox, 64 * sizeof(F)));
-        ctx->mailbox_dev = ctx->red + (size_t)kMaxRedBlocks * 8;
+        HB_CHECK(ctx, cudaMalloc(&ctx->red, (size_t)kMaxRedBlocks * 12 * sizeof(F)));
+        HB_CHECK(ctx, cudaMalloc(&ctx->ticket, 2 * sizeof(unsigned)));
+        HB_CHECK(ctx, cudaMemset(ctx->ticket, 0, 2 * sizeof(unsigned)));
+        HB_CHECK(ctx, cudaHostAlloc(&ctx->mailbox, 64 * sizeof(F), cudaHostAllocMapped));
+        memset(ctx->mailbox, 0, 64 * sizeof(F));
+        HB_CHECK(ctx, cudaHostGetDevicePointer(&ctx->mailbox_dev, ctx->mailbox, 0));
+        ctx->seq = 0;
     }
+    return 0;
+}
+// Wait for the reduction kernel launched last: its final CTA writes the coefficients into the host-mapped mailbox and then bumps the
+// sequence number (grid_reduce).  Spinning on host memory avoids a D2H copy + stream synchronisation per sumcheck round.
+static int read_result(hb_ctx *ctx, int nc, F *out) {
+    const u64 expect = ++ctx->seq;
+    volatile u64 *flag = reinterpret_cast<volatile u64 *>(ctx->mailbox + 15);
+    unsigned long spins = 0;
+    while (*flag != expect) {
+        if ((++spins & 0x3fff) == 0) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) { if (*flag == expect) break; HB_FAIL(ctx, "sumcheck: reduction kernel finished without publishing its result"); }
+            if (q != cudaErrorNotReady) HB_CHECK(ctx, q);
+        }
+    }
+    __sync_synchronize();
+    const volatile u64 *m = reinterpret_cast<const volatile u64 *>(ctx->mailbox);
+    for (int c = 0; c < nc; c++) { out[c].re = m[2 * c]; out[c].im = m[2 * c + 1]; }
     return 0;
 }
 static inline unsigned grid_for(hb_ctx *ctx, size_t L) {
@@ -284,11 +409,7 @@ template <int NT, int MODE, bool IL>
 static int launch_round(hb_ctx *ctx, const Tabs<NT> &t, size_t L, F r, F *coeffs_host /* NT+1, may be null for FOLD_ONLY */) {
     HB_TRY(ensure_scratch(ctx));
     HB_LAUNCH(ctx, (sc_round_kernel<NT, MODE, IL>), grid_for(ctx, L), 256, 0, t, L, r, ctx->red, ctx->ticket, ctx->mailbox_dev);
-    if (MODE != FOLD_ONLY) {
-        HB_CHECK(ctx, cudaMemcpyAsync(ctx->mailbox, ctx->mailbox_dev, (NT + 1) * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
-        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int c = 0; c <= NT; c++) coeffs_host[c] = ctx->mailbox[c];
-    }
+    if (MODE != FOLD_ONLY) HB_TRY(read_result(ctx, NT + 1, coeffs_host));
     return 0;
 }
 
@@ -667,12 +788,6 @@ extern "C" int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n
 // S4 on a layer array A (device, S entries, natural [seg(X) | seg(Y)] order).  rnd4 = (a, b0, b1, pad) drawn by the host with
 // libc in the reference's order.  r: log2(S/2) host points.  Outputs on the host.
 static inline F fromabi(const hb_F &x) { return mkF(x.real, x.img); }
-static int read_result(hb_ctx *ctx, int nc, F *out) {
-    HB_CHECK(ctx, cudaMemcpyAsync(ctx->mailbox, ctx->mailbox_dev, nc * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int c = 0; c < nc; c++) out[c] = ctx->mailbox[c];
-    return 0;
-}
 static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F *r, F old_claim, const F *rnd4,
                             F *new_claim, std::vector<F> &new_r, double *ps) {
     HB_TRY(ensure_scratch(ctx));
@@ -853,9 +968,10 @@ extern "C" int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb
         F co[5];
         Tabs<5> t;
         for (int k = 0; k < 5; k++) { t.in[k] = cur[k]; t.out[k] = A[k]; }
-        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, ctx->red, ctx->ticket, ctx->mailbox_dev); }
+        const GateW w = {mkF(1, 0), mkF(1, 0), mkF(1, 0), mkF(P61 - 1, 0), mkF(1, 0)};
+        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev); }
         else {
-            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, ctx->red, ctx->ticket, ctx->mailbox_dev);
+            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev);
             for (int k = 0; k < 5; k++) { cur[k] = A[k]; std::swap(A[k], Bf[k]); }
         }
         rc = read_result(ctx, 5, co);
@@ -875,5 +991,119 @@ extern "C" int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb
     o[0] = toabi(fin[0]); o[1] = toabi(fin[2]); o[2] = toabi(fin[3]); o[3] = toabi(fin[4]);
     o[4] = toabi(fsub(mkF(1, 0), fin[0]));                   // mul = 1 - add folds to 1 - fold(add)
     o[5] = toabi(fin[1]);
+    return 0;
+}
+
+// S7: prove_gate_consistency (sumcheck.cpp:796-981, no lookups) on a transcript resident in HBM.
+// rnd10 = a[4] (generate_randomness(4)) | b[6] (generate_randomness(6)), drawn by the host in that order.
+// out: R[nch] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add,mul,beta | Peval[6][nch] | P2 flat proof (4*log2 nch + 3).
+extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B,
+                                          const hb_F *r, const hb_F *rnd10, hb_F *out, double *ps) {
+    if (B < 2 || (B & (B - 1)) || cs < B || (cs & (cs - 1))) HB_FAIL(ctx, "hb_gate_consistency_stream: sizes must be powers of two, cs >= B >= 2");
+    HB_TRY(ensure_scratch(ctx));
+    const size_t nch = cs / B; const int lgB = ilog2(B), lgn = ilog2(nch);
+    Staged sl(ctx), sr(ctx), so(ctx), ss(ctx), srr(ctx);
+    HB_TRY(sl.in(L, cs * sizeof(F))); HB_TRY(sr.in(R, cs * sizeof(F))); HB_TRY(so.in(O, cs * sizeof(F))); HB_TRY(ss.in(S, cs * sizeof(F)));
+    HB_TRY(srr.in(r, lgB * sizeof(F)));
+    const F *dL = sl.as<F>(), *dR = sr.as<F>(), *dO = so.as<F>(), *dS = ss.as<F>();
+    F *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, (7 * B + 5 * (B / 2 + B / 4 + 2) + 64) * sizeof(F), ctx->stream));
+    F *beta = buf, *fA = buf + B, *fB = fA + B, *fL = fB + B, *fR = fL + B, *fO = fR + B, *beta1 = fO + B, *pp = beta1 + B, *r_dev = pp + 5 * (B / 2 + B / 4 + 2);
+    auto fail = [&](int rc) { cudaFreeAsync(buf, ctx->stream); return rc; };
+    int rc;
+    if ((rc = beta_dev(ctx, srr.as<F>(), lgB, beta))) return fail(rc);
+    const unsigned grid = grid_for(ctx, B);
+    F Kf[4];                                                    // Kf_O, Kf_L, Kf_R, Kf_M
+    HB_LAUNCH(ctx, gs_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, fA, fB, fL, fR, fO, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    if ((rc = read_result(ctx, 4, Kf))) return fail(rc);
+    *ps += 4 * 16 / 1024.0;
+    std::vector<F> Rv; Rv.push_back(mkF(1, 0));
+    F rand = mkF(0, 0), csum = mkF(1, 0);
+    for (size_t c = 1; c < nch; c++) {
+        const F *bL = dL + c * B, *bR = dR + c * B, *bO = dO + c * B, *bS = dS + c * B;
+        F K[12];
+        HB_LAUNCH(ctx, gs_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, fA, fB, fL, fR, fO, csum, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+        if ((rc = read_result(ctx, 12, K))) return fail(rc);
+        if (!fzero(fsub(fadd(fadd(K[11], K[4]), K[7]), K[1]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 1"); }
+        for (int q = 0; q < 8; q++) rand = h_mimc(K[q], rand);                          // K*_M are not hashed (:844-851)
+        Rv.push_back(rand);
+        F x1 = rand, x2 = h_fmul(rand, x1), x3 = h_fmul(rand, x2), x4 = h_fmul(rand, x3);
+        Kf[0] = fadd(Kf[0], fadd(h_fmul(x1, K[0]), h_fmul(x2, K[1])));
+        Kf[1] = fadd(Kf[1], fadd(fadd(h_fmul(x1, K[2]), h_fmul(x2, K[3])), h_fmul(x3, K[4])));
+        Kf[2] = fadd(Kf[2], fadd(fadd(h_fmul(x1, K[5]), h_fmul(x2, K[6])), h_fmul(x3, K[7])));
+        Kf[3] = fadd(Kf[3], fadd(fadd(fadd(h_fmul(x1, K[8]), h_fmul(x2, K[9])), h_fmul(x3, K[10])), h_fmul(x4, K[11])));
+        *ps += 12 * 16 / 1024.0;
+        HB_LAUNCH(ctx, gs_fold_kernel, grid, 256, 0, bL, bR, bO, bS, beta, fA, fB, fL, fR, fO, rand, B);
+        csum = fadd(csum, rand);
+    }
+    size_t k = 0;
+    for (auto &x : Rv) out[k++] = toabi(x);
+    const F *a = (const F *)rnd10, *b = a + 4;
+    F sum = fadd(fadd(h_fmul(a[0], Kf[1]), h_fmul(a[1], Kf[2])), fadd(h_fmul(a[2], Kf[3]), h_fmul(Kf[0], a[3])));
+    // degree-4 sumcheck over the folds (:877-935)
+    const F *cur[5] = {fA, fB, fL, fR, fO};
+    F *A5[5], *B5[5];
+    for (int q = 0; q < 5; q++) { A5[q] = pp + (size_t)q * (B / 2 + B / 4 + 2); B5[q] = A5[q] + B / 2 + 1; }
+    const GateW w = {a[0], a[1], a[2], a[3], csum};
+    std::vector<F> srnd;
+    for (int i = 0; i < lgB; i++) {
+        size_t Lp = B >> (i + 1);
+        F co[5];
+        Tabs<5> t;
+        for (int q = 0; q < 5; q++) { t.in[q] = cur[q]; t.out[q] = A5[q]; }
+        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev); }
+        else {
+            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev);
+            for (int q = 0; q < 5; q++) { cur[q] = A5[q]; std::swap(A5[q], B5[q]); }
+        }
+        if ((rc = read_result(ctx, 5, co))) return fail(rc);
+        for (int q = 0; q < 5; q++) { rand = h_mimc(co[q], rand); out[k++] = toabi(co[q]); }
+        out[k++] = toabi(rand);
+        F s01 = fadd(fadd(fadd(co[0], co[1]), fadd(co[2], co[3])), fadd(co[4], co[4]));
+        if (!feq(s01, sum)) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 2"); }
+        sum = fadd(h_fmul(fadd(h_fmul(fadd(h_fmul(fadd(h_fmul(co[0], rand), co[1]), rand), co[2]), rand), co[3]), rand), co[4]);
+        srnd.push_back(rand);
+        *ps += 5 * 16 / 1024.0;
+    }
+    F fin[5];
+    {
+        Tabs<5> t;
+        for (int q = 0; q < 5; q++) { t.in[q] = cur[q]; t.out[q] = A5[q]; }
+        if ((rc = launch_round<5, FOLD_ONLY, false>(ctx, t, 1, rand, nullptr))) return fail(rc);
+        if ((rc = fetch_heads(ctx, A5, 5, fin))) return fail(rc);
+    }
+    const F f_add = fin[0], f_beta = fin[1], f_L = fin[2], f_R = fin[3], f_O = fin[4], f_mul = fsub(csum, fin[0]);
+    out[k++] = toabi(f_L); out[k++] = toabi(f_R); out[k++] = toabi(f_O); out[k++] = toabi(f_add); out[k++] = toabi(f_mul); out[k++] = toabi(f_beta);
+    // pass B: partial evaluations per chunk against eq(sumcheck_rand)
+    HB_CHECK(ctx, cudaMemcpyAsync(r_dev, srnd.data(), lgB * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = beta_dev(ctx, r_dev, lgB, beta1))) return fail(rc);
+    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((B + 2047) / 2048, (size_t)(2 * ctx->sm_count) / (nch + 1) + 1));
+    F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, (nch + 1) * parts * 4 * sizeof(F), ctx->stream));
+    HB_LAUNCH(ctx, gs_peval_kernel, dim3(parts, (unsigned)nch + 1), 256, 0, dL, dR, dO, dS, beta, beta1, B, (unsigned)nch, pe_dev);
+    std::vector<F> pe((nch + 1) * parts * 4);
+    HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(pe_dev, ctx->stream);
+    cudaFreeAsync(buf, ctx->stream);
+    std::vector<F> Pe(6 * nch, mkF(0, 0));
+    F sb1 = mkF(0, 0), sbb = mkF(0, 0);
+    for (unsigned q = 0; q < parts; q++) { sb1 = fadd(sb1, pe[(nch * parts + q) * 4]); sbb = fadd(sbb, pe[(nch * parts + q) * 4 + 1]); }
+    for (size_t c = 0; c < nch; c++) {
+        for (unsigned q = 0; q < parts; q++) for (int t = 0; t < 4; t++) Pe[t * nch + c] = fadd(Pe[t * nch + c], pe[((c * parts + q) * 4) + t]);
+        Pe[4 * nch + c] = fsub(sb1, Pe[3 * nch + c]);              // sum beta1 (1 - S) = sum beta1 - sum beta1 S
+        Pe[5 * nch + c] = sbb;                                     // sum beta1 beta is the same for every chunk
+    }
+    for (auto &x : Pe) out[k++] = toabi(x);
+    std::vector<F> pv(nch, mkF(0, 0));
+    for (size_t j = 0; j < nch; j++) for (int i = 0; i < 6; i++) pv[j] = fadd(pv[j], h_fmul(b[i], Pe[i * nch + j]));
+    std::vector<hb_F> p2(4 * (size_t)lgn + 8);
+    hb_F rabi = toabi(rand);
+    HB_TRY(hb_sumcheck2(ctx, (const hb_F *)Rv.data(), (const hb_F *)pv.data(), nch, &rabi, p2.data(), ps));
+    *ps += 5 * 16 / 1024.0;
+    F s2 = fadd(fadd(fadd(h_fmul(f_L, b[0]), h_fmul(f_R, b[1])), fadd(h_fmul(f_O, b[2]), h_fmul(b[3], f_add))), fadd(h_fmul(b[4], f_mul), h_fmul(b[5], f_beta)));
+    if (lgn) {
+        F qv = fadd(fadd(fromabi(p2[0]), fromabi(p2[1])), fadd(fromabi(p2[2]), fromabi(p2[2])));
+        if (!feq(qv, s2)) HB_FAIL(ctx, "Error in gate consistency 3");
+    }
+    for (int i = 0; i < 4 * lgn + 3; i++) out[k++] = p2[i];
     return 0;
 }

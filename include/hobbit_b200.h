@@ -145,6 +145,14 @@ int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n, const hb_
 int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *add_gate, size_t n,
                                  const hb_F *r, hb_F *out);
 
+/* S7: prove_gate_consistency (sumcheck.cpp:796-981, no lookups) with the transcript resident in HBM: L, R, O (gate wire values) and
+ * S (F(1) = add gate, F(0) = mul gate), `cs` entries as read_trace emits them (witness_stream.cpp:1701-1807), processed in chunks of
+ * B = BUFFER_SPACE.  r: log2 B points; rnd10 = generate_randomness(4) | generate_randomness(6), drawn by the HOST in that order.
+ * The reference returns nothing; out = R[cs/B] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add,mul,beta | Peval[6][cs/B] |
+ * flat 2-product proof (4*log2(cs/B)+3).  The reference's self-checks ("Error in gate consistency 1/2/3") fail the call. */
+int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B,
+                               const hb_F *r, const hb_F *rnd10, hb_F *out, double *ps);
+
 /* ---- S4/S6: streaming folding sumcheck with the witness stream resident in HBM (sumcheck.cpp:1093-1392, 1746-1915) --------- */
 /* xy: the stream in its logical two-half form [X | Y] (`total` elements; what read_stream emits as X-block | Y-block per read,
  * witness_stream.cpp:2276-2311).  Layer l is [seg_l(X) | seg_l(Y)] with 2^l-element segment products (read_mul_tree_data).

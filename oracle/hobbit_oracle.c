@@ -751,3 +751,136 @@ void orc_gate_consistency_standard(const F *L_in, const F *R_in, const F *O_in, 
     out[k++] = A[0]; out[k++] = L[0]; out[k++] = R[0]; out[k++] = O[0]; out[k++] = M[0]; out[k++] = Bt[0];
     free(t);
 }
+
+/* ------------------------------------------------------------------ S7 ---
+ * prove_gate_consistency (sumcheck.cpp:796-981, has_lookups = false) with the transcript stream given as resident arrays
+ * L, R, O, S (S[i] = F(1) for an add gate, F(0) for a mul gate; read_trace, witness_stream.cpp:1701-1807), cs entries, buffer B.
+ * libc draws: a = generate_randomness(4) after the streaming pass, b = generate_randomness(6) after the partial evaluations.
+ * The reference returns nothing; out gets  R[nch] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add,mul,beta | Peval[6][nch] |
+ * P2 flat proof (4*log2 nch + 3).  Returns ps. */
+double orc_gate_consistency_stream(const F *L, const F *R, const F *O, const F *S, size_t cs, size_t B, const F *r, F *out) {
+    size_t nch = cs / B; int lgB = ilog2(B), lgn = ilog2(nch);
+    double ps = 0; size_t k = 0;
+    F *beta = (F *)malloc(B * sizeof(F));
+    orc_precompute_beta(r, lgB, beta);
+    F *fL = (F *)malloc(6 * B * sizeof(F)), *fR = fL + B, *fO = fR + B, *fA = fO + B, *fM = fA + B, *fB = fM + B;
+    F KfO = F0, KfL = F0, KfR = F0, KfM = F0;
+    for (size_t i = 0; i < B; i++) {
+        fL[i] = L[i]; fR[i] = R[i]; fO[i] = O[i]; fA[i] = S[i]; fM[i] = f_sub(F1, S[i]); fB[i] = beta[i];
+        KfO = f_add(KfO, f_mul(beta[i], fO[i]));
+        KfL = f_add(KfL, f_mul(f_mul(beta[i], fL[i]), fA[i]));
+        KfR = f_add(KfR, f_mul(f_mul(beta[i], fR[i]), fA[i]));
+        KfM = f_add(KfM, f_mul(f_mul(f_mul(beta[i], fR[i]), fL[i]), fM[i]));
+    }
+    ps += 4 * 16 / 1024.0;
+    F *Rv = (F *)malloc(nch * sizeof(F)); size_t nR = 0; Rv[nR++] = F1;
+    F rand = F0;
+    for (size_t c = 1; c < nch; c++) {
+        const F *bL = L + c * B, *bR = R + c * B, *bO = O + c * B, *bS = S + c * B;
+        F K1O = F0, K2O = F0, K1L = F0, K2L = F0, K3L = F0, K1R = F0, K2R = F0, K3R = F0, K1M = F0, K2M = F0, K3M = F0, K4M = F0;
+        for (size_t i = 0; i < B; i++) {
+            F gate = bS[i], ngate = f_sub(F1, bS[i]), t1, t2, t3, t4, t5, t6;
+            K1O = f_add(K1O, f_add(f_mul(bO[i], fB[i]), f_mul(beta[i], fO[i])));
+            K2O = f_add(K2O, f_mul(bO[i], beta[i]));
+            t1 = f_add(f_mul(bL[i], fA[i]), f_mul(gate, fL[i])); t2 = f_mul(bL[i], gate);
+            K1L = f_add(K1L, f_add(f_mul(fB[i], t1), f_mul(f_mul(beta[i], fL[i]), fA[i])));
+            K2L = f_add(K2L, f_add(f_mul(beta[i], t1), f_mul(fB[i], t2)));
+            K3L = f_add(K3L, f_mul(t2, beta[i]));
+            t1 = f_add(f_mul(bR[i], fA[i]), f_mul(gate, fR[i])); t2 = f_mul(bR[i], gate);
+            K1R = f_add(K1R, f_add(f_mul(fB[i], t1), f_mul(f_mul(beta[i], fR[i]), fA[i])));
+            K2R = f_add(K2R, f_add(f_mul(beta[i], t1), f_mul(fB[i], t2)));
+            K3R = f_add(K3R, f_mul(t2, beta[i]));
+            t1 = f_add(f_mul(fL[i], bR[i]), f_mul(fR[i], bL[i]));
+            t2 = f_add(f_mul(fB[i], ngate), f_mul(fM[i], beta[i]));
+            t3 = f_mul(bL[i], bR[i]); t4 = f_mul(ngate, beta[i]); t5 = f_mul(fL[i], fR[i]); t6 = f_mul(fB[i], fM[i]);
+            K1M = f_add(K1M, f_add(f_mul(t1, t6), f_mul(t2, t5)));
+            K2M = f_add(K2M, f_add(f_add(f_mul(t1, t2), f_mul(t3, t6)), f_mul(t4, t5)));
+            K3M = f_add(K3M, f_add(f_mul(t1, t4), f_mul(t2, t3)));
+            K4M = f_add(K4M, f_mul(t3, t4));
+        }
+        if (!f_eq(f_sub(f_add(f_add(K4M, K3L), K3R), K2O), F0)) { printf("Error in gate consistency 1 : %d\n", (int)c); exit(-1); }
+        rand = mimc(K1O, rand); rand = mimc(K2O, rand); rand = mimc(K1L, rand); rand = mimc(K2L, rand); rand = mimc(K3L, rand);
+        rand = mimc(K1R, rand); rand = mimc(K2R, rand); rand = mimc(K3R, rand);
+        Rv[nR++] = rand;
+        F x1 = rand, x2 = f_mul(rand, x1), x3 = f_mul(rand, x2), x4 = f_mul(rand, x3);
+        KfO = f_add(KfO, f_add(f_mul(x1, K1O), f_mul(x2, K2O)));
+        KfL = f_add(KfL, f_add(f_add(f_mul(x1, K1L), f_mul(x2, K2L)), f_mul(x3, K3L)));
+        KfR = f_add(KfR, f_add(f_add(f_mul(x1, K1R), f_mul(x2, K2R)), f_mul(x3, K3R)));
+        KfM = f_add(KfM, f_add(f_add(f_add(f_mul(x1, K1M), f_mul(x2, K2M)), f_mul(x3, K3M)), f_mul(x4, K4M)));
+        ps += 12 * 16 / 1024.0;
+        for (size_t i = 0; i < B; i++) {
+            fA[i] = f_add(fA[i], f_mul(rand, bS[i])); fL[i] = f_add(fL[i], f_mul(rand, bL[i])); fR[i] = f_add(fR[i], f_mul(rand, bR[i]));
+            fO[i] = f_add(fO[i], f_mul(rand, bO[i])); fM[i] = f_add(fM[i], f_mul(rand, f_sub(F1, bS[i]))); fB[i] = f_add(fB[i], f_mul(rand, beta[i]));
+        }
+    }
+    for (size_t i = 0; i < nch; i++) out[k++] = Rv[i];
+    F a[4]; orc_generate_randomness(4, a);
+    F sum = f_add(f_add(f_mul(a[0], KfL), f_mul(a[1], KfR)), f_add(f_mul(a[2], KfM), f_mul(KfO, a[3])));
+    F *srand_ = (F *)malloc(lgB * sizeof(F));
+    for (int i = lgB - 1, q = 0; i >= 0; i--, q++) {
+        F p[5] = { F0, F0, F0, F0, F0 };
+        for (size_t j = 0; j < ((size_t)1 << i); j++) {
+            F a0 = fA[2 * j], a1 = f_sub(fA[2 * j + 1], a0), m0 = fM[2 * j], m1 = f_sub(fM[2 * j + 1], m0);
+            F b0 = fB[2 * j], b1 = f_sub(fB[2 * j + 1], b0), l0 = fL[2 * j], l1 = f_sub(fL[2 * j + 1], l0);
+            F r0 = fR[2 * j], r1 = f_sub(fR[2 * j + 1], r0), o0 = fO[2 * j], o1 = f_sub(fO[2 * j + 1], o0);
+            F ml2 = f_mul(m1, l1), ml1 = f_add(f_mul(m1, l0), f_mul(m0, l1)), ml0 = f_mul(m0, l0);
+            F q3 = f_mul(a[2], f_mul(ml2, r1));
+            F q2 = f_mul(a[2], f_add(f_mul(ml2, r0), f_mul(ml1, r1)));
+            F q1 = f_mul(a[2], f_add(f_mul(ml1, r0), f_mul(ml0, r1)));
+            F q0 = f_mul(a[2], f_mul(ml0, r0));
+            F s0 = f_add(f_mul(a[0], l0), f_mul(a[1], r0)), s1 = f_add(f_mul(a[0], l1), f_mul(a[1], r1));
+            q2 = f_add(q2, f_mul(a1, s1));
+            q1 = f_add(q1, f_add(f_mul(a1, s0), f_mul(a0, s1)));
+            q0 = f_add(q0, f_mul(a0, s0));
+            q1 = f_add(q1, f_mul(a[3], o1)); q0 = f_add(q0, f_mul(a[3], o0));
+            p[0] = f_add(p[0], f_mul(b1, q3));
+            p[1] = f_add(p[1], f_add(f_mul(b1, q2), f_mul(b0, q3)));
+            p[2] = f_add(p[2], f_add(f_mul(b1, q1), f_mul(b0, q2)));
+            p[3] = f_add(p[3], f_add(f_mul(b1, q0), f_mul(b0, q1)));
+            p[4] = f_add(p[4], f_mul(b0, q0));
+        }
+        for (int c = 0; c < 5; c++) { rand = mimc(p[c], rand); out[k++] = p[c]; }
+        out[k++] = rand;
+        {   /* sum == poly(0) + poly(1) */
+            F s = f_add(f_add(f_add(p[0], p[1]), f_add(p[2], p[3])), f_add(p[4], p[4]));
+            if (!f_eq(s, sum)) { printf("Error in gate consistency 2: %d\n", i); exit(-1); }
+        }
+        sum = f_add(f_mul(f_add(f_mul(f_add(f_mul(f_add(f_mul(p[0], rand), p[1]), rand), p[2]), rand), p[3]), rand), p[4]);
+        srand_[q] = rand;
+        ps += 5 * 16 / 1024.0;
+        for (size_t j = 0; j < ((size_t)1 << i); j++) {
+            fA[j] = f_add(fA[2 * j], f_mul(rand, f_sub(fA[2 * j + 1], fA[2 * j]))); fL[j] = f_add(fL[2 * j], f_mul(rand, f_sub(fL[2 * j + 1], fL[2 * j])));
+            fR[j] = f_add(fR[2 * j], f_mul(rand, f_sub(fR[2 * j + 1], fR[2 * j]))); fO[j] = f_add(fO[2 * j], f_mul(rand, f_sub(fO[2 * j + 1], fO[2 * j])));
+            fM[j] = f_add(fM[2 * j], f_mul(rand, f_sub(fM[2 * j + 1], fM[2 * j]))); fB[j] = f_add(fB[2 * j], f_mul(rand, f_sub(fB[2 * j + 1], fB[2 * j])));
+        }
+    }
+    out[k++] = fL[0]; out[k++] = fR[0]; out[k++] = fO[0]; out[k++] = fA[0]; out[k++] = fM[0]; out[k++] = fB[0];
+    F *beta1 = (F *)malloc(B * sizeof(F));
+    orc_precompute_beta(srand_, lgB, beta1);
+    F *Pe = (F *)calloc(6 * nch, sizeof(F));
+    for (size_t c = 0; c < nch; c++)
+        for (size_t j = 0; j < B; j++) {
+            F s = S[c * B + j];
+            Pe[0 * nch + c] = f_add(Pe[0 * nch + c], f_mul(beta1[j], L[c * B + j]));
+            Pe[1 * nch + c] = f_add(Pe[1 * nch + c], f_mul(beta1[j], R[c * B + j]));
+            Pe[2 * nch + c] = f_add(Pe[2 * nch + c], f_mul(beta1[j], O[c * B + j]));
+            Pe[3 * nch + c] = f_add(Pe[3 * nch + c], f_mul(beta1[j], s));
+            Pe[4 * nch + c] = f_add(Pe[4 * nch + c], f_mul(beta1[j], f_sub(F1, s)));
+            Pe[5 * nch + c] = f_add(Pe[5 * nch + c], f_mul(beta1[j], beta[j]));
+        }
+    for (size_t i = 0; i < 6 * nch; i++) out[k++] = Pe[i];
+    F b[6]; orc_generate_randomness(6, b);
+    F *pe = (F *)malloc(nch * sizeof(F));
+    for (size_t j = 0; j < nch; j++) { pe[j] = F0; for (int i = 0; i < 6; i++) pe[j] = f_add(pe[j], f_mul(b[i], Pe[i * nch + j])); }
+    F *p2 = (F *)malloc((4 * (size_t)lgn + 8) * sizeof(F));
+    ps += orc_sumcheck2(Rv, pe, nch, &rand, p2);
+    ps += 5 * 16 / 1024.0;
+    {
+        F s2 = f_add(f_add(f_add(f_mul(fL[0], b[0]), f_mul(fR[0], b[1])), f_add(f_mul(fO[0], b[2]), f_mul(b[3], fA[0]))), f_add(f_mul(b[4], fM[0]), f_mul(b[5], fB[0])));
+        F qv = lgn ? f_add(f_add(p2[0], p2[1]), f_add(p2[2], p2[2])) : s2;
+        if (!f_eq(qv, s2)) { printf("Error in gate consistency 3\n"); exit(-1); }
+    }
+    for (int i = 0; i < 4 * lgn + 3; i++) out[k++] = p2[i];
+    free(beta); free(fL); free(Rv); free(srand_); free(beta1); free(Pe); free(pe); free(p2);
+    return ps;
+}

@@ -65,6 +65,8 @@ double orc_mul_tree_stream(const orc_F *xy, size_t total, int vectors, size_t B,
 
 /* prove_gate_consistency_standard (sumcheck.cpp:434-501); out: (a,b,c,d,e,rand) x rounds | final add, L, R, O, mul, beta */
 void orc_gate_consistency_standard(const orc_F *L, const orc_F *R, const orc_F *O, const orc_F *add_gate, size_t n, const orc_F *r, orc_F *out);
+/* S7: prove_gate_consistency (sumcheck.cpp:796-981) on a resident transcript (L, R, O, S); out layout in hobbit_oracle.c */
+double orc_gate_consistency_stream(const orc_F *L, const orc_F *R, const orc_F *O, const orc_F *S, size_t cs, size_t B, const orc_F *r, orc_F *out);
 /* C1 split for sharding: inner leaf digests of chunks, and the Merkle–Damgård chain over chunks */
 void orc_commit_encode_chunks(const orc_F *poly, size_t nchunks, size_t B, int trs, int lin, uint8_t *inner_out);
 void orc_md_chain(const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);

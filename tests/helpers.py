@@ -277,3 +277,25 @@ def _gate_consistency(self, L, R, O, add, r):
 
 
 Checker.gate_consistency = _gate_consistency
+
+
+def _gate_stream(self, L, R, O, S, B, r):
+    assert self.kind == "orc", "the reference's prove_gate_consistency needs its circuit evaluator thread"
+    L, R, O, S, r = F(L), F(R), F(O), F(S), F(r)
+    cs = len(L); nch = cs // B
+    lgB, lgn = int(np.log2(B)), int(np.log2(nch))
+    out = fzeros(nch + 6 * lgB + 6 + 6 * nch + 4 * lgn + 3)
+    ps = self.fn("gate_consistency_stream", ctypes.c_double)(_p(L), _p(R), _p(O), _p(S), ctypes.c_size_t(cs), ctypes.c_size_t(B), _p(r), _p(out))
+    return out, ps
+
+
+Checker.gate_stream = _gate_stream
+
+
+def consistent_trace(rng, orc, cs):
+    """A gate transcript that satisfies O = S ? L+R : L*R, i.e. what read_trace emits for a correctly evaluated circuit."""
+    L, R = rand_field(rng, cs), rand_field(rng, cs)
+    S = np.zeros((cs, 2), dtype=np.uint64)
+    S[:, 0] = rng.integers(0, 2, cs)
+    O = np.where(S[:, :1] == 1, orc.binop(0, L, R), orc.binop(2, L, R))
+    return L, R, O, S

@@ -6,7 +6,7 @@ import pytest
 
 import ctypes
 
-from helpers import Checker, F, P61, rand_field, ref_available, srand, synthetic_stream
+from helpers import Checker, F, P61, consistent_trace, rand_field, ref_available, srand, synthetic_stream
 
 pytestmark = pytest.mark.gpu
 
@@ -302,3 +302,30 @@ def test_gate_consistency_standard(ctx, chk, n):
         assert np.array_equal(got[6 * rounds:6 * rounds + 4], want)      # the reference exposes only the folded tables
     else:
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("cs,B", [(1 << 12, 1 << 9), (1 << 10, 1 << 10), (1 << 16, 1 << 12), (1 << 6, 2)])
+def test_gate_consistency_stream(ctx, cs, B):
+    """S7 against the C oracle (the reference's prove_gate_consistency returns nothing and reads its input from the circuit
+    evaluator thread, so the oracle is pinned by its three internal consistency identities and the deterministic ps)."""
+    orc = Checker("orc")
+    rng = np.random.default_rng(cs + B)
+    L, R, O, S = consistent_trace(rng, orc, cs)
+    r = rand_field(rng, int(np.log2(B)))
+    srand(3)
+    want, wps = orc.gate_stream(L, R, O, S, B, r)
+    srand(3)
+    rnd = np.concatenate([orc.generate_randomness(4), orc.generate_randomness(6)])
+    got, gps = ctx.gate_consistency_stream(L, R, O, S, B, r, rnd)
+    assert gps == wps
+    assert np.array_equal(got, want)
+
+
+def test_gate_consistency_stream_rejects_bad_trace(ctx):
+    import hobbit_b200
+    orc = Checker("orc")
+    rng = np.random.default_rng(1)
+    L, R, O, S = consistent_trace(rng, orc, 1 << 10)
+    O[700, 0] ^= 1                                   # one wrong gate output in the second chunk
+    with pytest.raises(hobbit_b200.HobbitError, match="gate consistency"):
+        ctx.gate_consistency_stream(L, R, O, S, 1 << 9, rand_field(rng, 9), rand_field(rng, 10))
