@@ -355,3 +355,17 @@ class Context:
         self._ck(self.lib.hb_gate_consistency_stream(self.h, _ptr(L), _ptr(R), _ptr(O), _ptr(S), c_sz(cs), c_sz(B), _ptr(r), _ptr(rnd),
                                                      _ptr(out), ctypes.byref(ps)))
         return out, ps.value
+
+    def elastic_open_front(self, chunks, betas, B, trs, lin, col, row):
+        """O2 front: returns (agg (B,2), reply (queries, nchunks, 2))."""
+        col = np.ascontiguousarray(col, dtype=np.uint32); row = np.ascontiguousarray(row, dtype=np.uint32)
+        chunks = list(chunks); betas = _F(betas)
+        self._ck(self.lib.hb_elastic_open_begin(self.h, c_sz(B), int(trs), int(lin), _ptr(col), _ptr(row), c_sz(len(col)), c_sz(len(chunks))))
+        for i, c in enumerate(chunks):
+            c = _F(c)
+            b = np.ascontiguousarray(betas[i:i + 1])
+            self._ck(self.lib.hb_elastic_open_push(self.h, _ptr(c), _ptr(b)))
+        agg = np.zeros((B, 2), dtype=np.uint64)
+        reply = np.zeros((len(col) * len(chunks), 2), dtype=np.uint64)
+        self._ck(self.lib.hb_elastic_open_finish(self.h, _ptr(agg), _ptr(reply)))
+        return agg, reply.reshape(len(col), len(chunks), 2)

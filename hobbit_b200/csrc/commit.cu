@@ -56,6 +56,18 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const F *__restrict__ po
     }
 }
 
+// agg[j] += beta * chunk[j]   (Elastic_PC.cpp:326-333, one chunk of the streaming aggregate)
+__global__ void __launch_bounds__(256) axpy_kernel(F *__restrict__ agg, const F *__restrict__ chunk, F beta, size_t B) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x)
+        agg[j] = fadd(agg[j], fmul(beta, chunk[j]));
+}
+// reply[q * nchunks + idx] = T[row[q]][col[q]]   (update_reply, Elastic_PC.cpp:59-110)
+__global__ void reply_gather_kernel(const F *__restrict__ T, size_t cols, const uint32_t *__restrict__ col, const uint32_t *__restrict__ row,
+                                    size_t queries, size_t nchunks, size_t idx, F *__restrict__ reply) {
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < queries) reply[q * nchunks + idx] = T[(size_t)row[q] * cols + col[q]];
+}
+
 __global__ void any_nonzero_kernel(const F *__restrict__ v, size_t n, int *flag) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         if (!fzero(v[i])) { *flag = 1; return; }
@@ -423,5 +435,48 @@ extern "C" int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n) {
     for (size_t i = 0; i < n; i++) { v[i] = x; x = fadd(h_fmul(x, x), mkF((u64)i, 0)); }
     HB_CHECK(ctx, cudaMemcpyAsync(out, v.data(), n * sizeof(F), cudaMemcpyDefault, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- O2 (front half): Elastic_PC open = aggregate + compute_aggregation_reply (Elastic_PC.cpp:316-333, 487-533), chunk at a time ----
+extern "C" int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, const uint32_t *col, const uint32_t *row, size_t queries, size_t nchunks) {
+    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_open_begin: BUFFER_SPACE must be a power of two");
+    ElasticOpen &eo = ctx->eo;
+    if (eo.active) { cudaFreeAsync(eo.buf, ctx->stream); eo = ElasticOpen(); }
+    eo.B = B; eo.trs = trs; eo.lin = linear_time; eo.queries = queries; eo.nchunks = nchunks; eo.idx = 0;
+    size_t bytes = (B + 4 * B + B + queries * nchunks) * sizeof(F) + 2 * queries * sizeof(uint32_t);
+    HB_CHECK(ctx, cudaMallocAsync(&eo.buf, bytes, ctx->stream));
+    eo.agg = (F *)eo.buf; eo.tensor = eo.agg + B; eo.msg = eo.tensor + 4 * B; eo.reply = eo.msg + B;
+    eo.col = (uint32_t *)(eo.reply + queries * nchunks); eo.row = eo.col + queries;
+    HB_CHECK(ctx, cudaMemsetAsync(eo.agg, 0, B * sizeof(F), ctx->stream));
+    HB_CHECK(ctx, cudaMemsetAsync(eo.reply, 0, queries * nchunks * sizeof(F), ctx->stream));
+    HB_CHECK(ctx, cudaMemcpyAsync(eo.col, col, queries * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
+    HB_CHECK(ctx, cudaMemcpyAsync(eo.row, row, queries * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
+    eo.active = true;
+    return 0;
+}
+extern "C" int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *beta_i) {
+    ElasticOpen &eo = ctx->eo;
+    if (!eo.active || eo.idx >= eo.nchunks) HB_FAIL(ctx, "hb_elastic_open_push: no open in progress / too many chunks");
+    const size_t B = eo.B;
+    const F *src = (const F *)chunk;
+    if (!is_device_ptr(chunk)) { HB_CHECK(ctx, cudaMemcpyAsync(eo.msg, chunk, B * sizeof(F), cudaMemcpyHostToDevice, ctx->stream)); src = eo.msg; }
+    F beta = mkF(beta_i->real, beta_i->img);
+    unsigned grid = (unsigned)std::min<size_t>((B + 255) / 256, (size_t)ctx->sm_count * 8);
+    HB_LAUNCH(ctx, axpy_kernel, grid, 256, 0, eo.agg, src, beta, B);
+    HB_TRY(tensorcode_dev(ctx, src, B, eo.trs, eo.lin, eo.tensor, 1, nullptr));
+    if (eo.queries) HB_LAUNCH(ctx, reply_gather_kernel, (unsigned)((eo.queries + 255) / 256), 256, 0, eo.tensor, 2 * B / eo.trs, eo.col, eo.row,
+                              eo.queries, eo.nchunks, eo.idx, eo.reply);
+    eo.idx++;
+    return 0;
+}
+extern "C" int hb_elastic_open_finish(hb_ctx *ctx, hb_F *agg_out, hb_F *reply_out) {
+    ElasticOpen &eo = ctx->eo;
+    if (!eo.active) HB_FAIL(ctx, "hb_elastic_open_finish: no open in progress");
+    HB_CHECK(ctx, cudaMemcpyAsync(agg_out, eo.agg, eo.B * sizeof(F), cudaMemcpyDefault, ctx->stream));
+    if (eo.queries) HB_CHECK(ctx, cudaMemcpyAsync(reply_out, eo.reply, eo.queries * eo.nchunks * sizeof(F), cudaMemcpyDefault, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(eo.buf, ctx->stream);
+    eo = ElasticOpen();
     return 0;
 }

@@ -41,6 +41,12 @@ struct ElasticState {
     int *nz_flag = nullptr;
 };
 
+struct ElasticOpen {
+    bool active = false;
+    size_t B = 0, queries = 0, nchunks = 0, idx = 0; int trs = 0, lin = 0;
+    void *buf = nullptr; F *agg = nullptr, *tensor = nullptr, *msg = nullptr, *reply = nullptr; uint32_t *col = nullptr, *row = nullptr;
+};
+
 }  // namespace hb
 
 struct hb_ctx {
@@ -59,6 +65,7 @@ struct hb_ctx {
     // device copy of the polynomial staged by the last commit_standard (open_standard's aggregate reads it again)
     hb::F *poly = nullptr; size_t poly_elems = 0; const void *poly_host = nullptr;
     hb::ElasticState el;
+    hb::ElasticOpen eo;
     // sumcheck reduction scratch: per-CTA partial coefficients + ticket counter (device), result mailbox (pinned host)
     hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr; unsigned long long seq = 0;
     // optional per-kernel timing (hb_profile_*): CUDA events around every launch, on this context's stream

@@ -113,6 +113,15 @@ int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, const hb_F *bet
 int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time);
 int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk);
 int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out);
+/* ---- O2, data-parallel front half of Elastic_PC open (Elastic_PC.cpp:316-333 aggregate, 487-533 compute_aggregation_reply) --------
+ * begin: the `queries` cells (col[q], row[q]) drawn by the host (Elastic_PC.cpp:649-655), nchunks = N/B.  push chunk i with beta[i]:
+ *   agg[j] += beta[i] * chunk[j]  and  reply[q*nchunks + i] = tensorcode(chunk)[row[q]][col[q]].  finish: agg (B), reply (queries*nchunks).
+ * RS columns (linear_time = 0) match update_reply (:59-110) exactly.  For linear_time != 0 the reference's update_reply_spielman
+ * (:431-486) groups replies by sorted column and reads past its buffer for parity rows (undefined behaviour); here every reply is
+ * simply the encoded tensor cell, in query order. */
+int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, const uint32_t *col, const uint32_t *row, size_t queries, size_t nchunks);
+int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *beta_i);
+int hb_elastic_open_finish(hb_ctx *ctx, hb_F *agg_out, hb_F *reply_out);
 /* read_stream_PC's synthetic default stream (witness_stream.cpp:2405-2411): v[0]=322322, v[i+1]=v[i]^2+i */
 int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n);
 

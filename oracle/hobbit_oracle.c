@@ -884,3 +884,19 @@ double orc_gate_consistency_stream(const F *L, const F *R, const F *O, const F *
     free(beta); free(fL); free(Rv); free(srand_); free(beta1); free(Pe); free(pe); free(p2);
     return ps;
 }
+
+/* O2 front (Elastic_PC.cpp:316-333 aggregate's axpy, :487-533 compute_aggregation_reply + update_reply :59-110):
+ * stream = nchunks chunks of B elements; agg[j] = sum_i beta[i] stream[i][j]; reply[q*nchunks + i] = tensorcode(chunk i)[row[q]][col[q]]. */
+void orc_elastic_open_front(const F *stream, size_t nchunks, size_t B, int trs, int lin, const F *beta, const uint32_t *col, const uint32_t *row,
+                            size_t queries, F *agg, F *reply) {
+    size_t cols = 2 * B / trs;
+    F *T = (F *)malloc(4 * B * sizeof(F));
+    for (size_t j = 0; j < B; j++) agg[j] = F0;
+    for (size_t i = 0; i < nchunks; i++) {
+        const F *c = stream + i * B;
+        for (size_t j = 0; j < B; j++) agg[j] = f_add(agg[j], f_mul(beta[i], c[j]));
+        orc_compute_tensorcode(c, B, trs, lin, T);
+        for (size_t q = 0; q < queries; q++) reply[q * nchunks + i] = T[(size_t)row[q] * cols + col[q]];
+    }
+    free(T);
+}

@@ -33,6 +33,9 @@ proof batch_3product_sumcheck(vector<vector<F>> &arr1, vector<vector<F>> &arr2, 
 void generate_3product_sumcheck_beta_stream_batch_optimized(stream_descriptor fd, vector<vector<F>> r, int batches, int distance, int layer_id,
 		vector<F> old_claims, vector<F> &new_claims, vector<vector<F>> &new_r, double &vt, double &ps);
 extern int BUFFER_SPACE_tr;
+extern int aggregation_queries;
+void compute_aggregation_reply(stream_descriptor fd, vector<vector<size_t>> &I, vector<vector<F>> &reply);
+void aggregate(stream_descriptor fd, vector<F> beta1, vector<F> random_points, vector<vector<_hash>> &MT_hashes, vector<F> &aggregated_vector, vector<vector<F>> &aggregated_tensor);
 
 static_assert(sizeof(F) == 16, "F must be the 16-byte {real,img} POD");
 
@@ -309,6 +312,27 @@ void ref_gate_consistency_standard(const uint64_t *L, const uint64_t *R, const u
     prove_gate_consistency_standard(l, rr, o, a, rv, vt, ps);
     F res[4] = { a[0], l[0], rr[0], o[0] };
     memcpy(out4, res, 64);
+}
+
+// O2 front on the synthetic default stream (read_stream: v[i] = F(i%1024+1)), RS columns (linear_time = false):
+// compute_aggregation_reply (Elastic_PC.cpp:487-533) and the aggregated vector of aggregate (:316-345; it also runs shockwave_commit).
+void ref_elastic_open_front_rs(size_t N, size_t B, int trs, const uint64_t *beta, const uint32_t *col, const uint32_t *row, size_t queries,
+                               uint64_t *agg, uint64_t *reply) {
+    BUFFER_SPACE = B; BUFFER_SPACE_tr = B / 8; tensor_row_size = trs; linear_time = false; aggregation_queries = (int)queries;
+    size_t nch = N / B;
+    stream_descriptor fd; fd.name = "test"; fd.size = N; reset_stream(fd);
+    vector<vector<size_t>> I(queries);
+    for (size_t q = 0; q < queries; q++) { I[q].push_back(col[q]); I[q].push_back(row[q]); }
+    vector<vector<F>> rep;
+    compute_aggregation_reply(fd, I, rep);
+    for (size_t q = 0; q < queries; q++) {
+        if (rep[q].size() != nch) { printf("ref_shim: reply row %zu has %zu entries\n", q, rep[q].size()); exit(-1); }
+        memcpy(reply + 2 * q * nch, rep[q].data(), nch * 16);
+    }
+    vector<F> b((const F *)beta, (const F *)beta + nch), rv(nch, F(1)), av; vector<vector<_hash>> MT; vector<vector<F>> at;
+    reset_stream(fd);
+    aggregate(fd, b, rv, MT, av, at);
+    memcpy(agg, av.data(), B * 16);
 }
 
 } // extern "C"

@@ -299,3 +299,29 @@ def consistent_trace(rng, orc, cs):
     S[:, 0] = rng.integers(0, 2, cs)
     O = np.where(S[:, :1] == 1, orc.binop(0, L, R), orc.binop(2, L, R))
     return L, R, O, S
+
+
+def _elastic_open_front(self, stream, B, trs, lin, beta, col, row):
+    """O2 front.  'ref': RS columns only, reads its own synthetic stream (stream is ignored)."""
+    stream, beta = F(stream), F(beta)
+    col = np.ascontiguousarray(col, dtype=np.uint32); row = np.ascontiguousarray(row, dtype=np.uint32)
+    nch = len(stream) // B
+    agg, reply = fzeros(B), fzeros(len(col) * nch)
+    if self.kind == "ref":
+        assert not lin
+        self.fn("elastic_open_front_rs")(ctypes.c_size_t(len(stream)), ctypes.c_size_t(B), trs, _p(beta), _p(col), _p(row), ctypes.c_size_t(len(col)),
+                                         _p(agg), _p(reply))
+    else:
+        self.fn("elastic_open_front")(_p(stream), ctypes.c_size_t(nch), ctypes.c_size_t(B), trs, int(lin), _p(beta), _p(col), _p(row),
+                                      ctypes.c_size_t(len(col)), _p(agg), _p(reply))
+    return agg, reply.reshape(len(col), nch, 2)
+
+
+Checker.elastic_open_front = _elastic_open_front
+
+
+def synthetic_chunks(nch, B):
+    """read_stream's default stream, chunk by chunk: every read restarts at i = 0 (witness_stream.cpp:2348-2352)."""
+    c = np.zeros((B, 2), dtype=np.uint64)
+    c[:, 0] = (np.arange(B, dtype=np.uint64) % 1024) + 1
+    return np.concatenate([c] * nch)

@@ -6,7 +6,7 @@ import pytest
 
 import ctypes
 
-from helpers import Checker, F, P61, consistent_trace, rand_field, ref_available, srand, synthetic_stream
+from helpers import Checker, F, P61, consistent_trace, rand_field, ref_available, srand, synthetic_chunks, synthetic_stream
 
 pytestmark = pytest.mark.gpu
 
@@ -329,3 +329,20 @@ def test_gate_consistency_stream_rejects_bad_trace(ctx):
     O[700, 0] ^= 1                                   # one wrong gate output in the second chunk
     with pytest.raises(hobbit_b200.HobbitError, match="gate consistency"):
         ctx.gate_consistency_stream(L, R, O, S, 1 << 9, rand_field(rng, 9), rand_field(rng, 10))
+
+
+@pytest.mark.parametrize("lin,trs,synthetic", [(0, 16, True), (0, 128, False), (1, 16, False)])
+def test_elastic_open_front(ctx, chk, lin, trs, synthetic):
+    """O2 front half: streaming aggregate + query replies (the reference only for RS columns on its synthetic stream)."""
+    if chk.kind == "ref" and (lin or not synthetic):
+        pytest.skip("reference: RS columns on its synthetic stream only (its Spielman reply path reads out of bounds)")
+    N, B, Q = 1 << 14, 1 << 11, 300
+    rng = np.random.default_rng(8 + trs)
+    if lin:
+        install_expander(ctx, chk, trs)
+    col = rng.integers(0, 2 * B // trs, Q); row = rng.integers(0, 2 * trs, Q)
+    beta = rand_field(rng, N // B)
+    stream = synthetic_chunks(N // B, B) if synthetic else rand_field(rng, N)
+    got = ctx.elastic_open_front([stream[i * B:(i + 1) * B] for i in range(N // B)], beta, B, trs, lin, col, row)
+    want = chk.elastic_open_front(stream, B, trs, lin, beta, col, row)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])

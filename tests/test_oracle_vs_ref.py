@@ -4,7 +4,7 @@ binary was not prebuilt (the committed golden vectors in tests/golden/ still pin
 import numpy as np
 import pytest
 
-from helpers import Checker, F, P61, rand_field, ref_available, srand, synthetic_stream
+from helpers import Checker, F, P61, rand_field, ref_available, srand, synthetic_chunks, synthetic_stream
 
 pytestmark = pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
 
@@ -185,3 +185,35 @@ def test_gate_consistency_standard(libs, n):
     a, b, c, d, e = (full[i:i + 1] for i in range(5))
     s = orc.binop(0, orc.binop(0, orc.binop(0, a, b), orc.binop(0, c, d)), orc.binop(0, e, e))
     assert not s.any()
+
+
+def test_elastic_open_front_rs(libs):
+    """O2 front half, RS columns: compute_aggregation_reply + the aggregate axpy on the reference's synthetic stream."""
+    orc, ref = libs
+    N, B, trs, Q = 1 << 14, 1 << 11, 16, 300
+    rng = np.random.default_rng(8)
+    col = rng.integers(0, 2 * B // trs, Q); row = rng.integers(0, 2 * trs, Q)
+    beta = rand_field(rng, N // B)
+    stream = synthetic_chunks(N // B, B)
+    a = orc.elastic_open_front(stream, B, trs, 0, beta, col, row)
+    b = ref.elastic_open_front(stream, B, trs, 0, beta, col, row)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_gate_consistency_stream_oracle_selfchecks():
+    """S7 restatement: the reference's prove_gate_consistency (sumcheck.cpp:796-981) returns nothing and reads its input from the
+    circuit-evaluator thread, so it cannot be diffed directly.  The restatement is pinned by (1) the three algebraic identities
+    the reference itself asserts (a violation exits the process) on a consistent trace, (2) the deterministic proof-size counter:
+    ps = [4 + 12 (nch-1) + 5 log2 B + (3 log2 nch + 2) + 5] * 16 / 1024 KB, (3) its libc draws (4 then 6 elements)."""
+    from helpers import consistent_trace
+    import ctypes
+    orc = Checker("orc")
+    cs, B = 1 << 12, 1 << 8
+    L, R, O, S = consistent_trace(np.random.default_rng(2), orc, cs)
+    srand(5)
+    out, ps = orc.gate_stream(L, R, O, S, B, rand_field(np.random.default_rng(3), 8))
+    nch = cs // B
+    assert ps == (4 + 12 * (nch - 1) + 5 * 8 + (3 * 4 + 2) + 5) * 16 / 1024.0
+    nxt = orc.generate_randomness(1)
+    srand(5); orc.generate_randomness(4); orc.generate_randomness(6)
+    assert np.array_equal(nxt, orc.generate_randomness(1))
