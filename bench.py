@@ -222,6 +222,12 @@ def main():
             ctx.commit_standard(poly_host, K, trs, 1, levels_out=levels_host)
 
     levels_host_t = torch.from_numpy(levels_host)
+    if world > 1 and os.environ.get("HB_DIST_TIMING"):
+        tm = []
+        for _ in range(3):
+            commit_standard_sharded(be, poly_dev.data_ptr(), K * world, B, trs, 1, timing=tm)
+        if rank == 0:
+            print("dist phases (encode+exchange, chain+subtree, gather+top) ms:", [[round(1e3 * x, 2) for x in t] for t in tm], file=sys.stderr)
 
     def barrier():
         torch.cuda.synchronize()

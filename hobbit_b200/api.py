@@ -318,14 +318,16 @@ class Context:
         return out, ps.value, layers.value
 
     # ---- sharded commit building blocks (hobbit_b200/dist.py) ----
-    def commit_encode_chunks(self, poly, nchunks, B, trs, lin, inner_out=None):
-        """poly / inner_out: numpy arrays or int device pointers.  Returns inner digests (nchunks*B, 32) when inner_out is None."""
+    def commit_encode_chunks(self, poly, nchunks, B, trs, lin, inner_out=None, leaf_parts=1, first_chunk=0, total_chunks=0):
+        """poly / inner_out: numpy arrays or int device pointers.  Returns inner digests (nchunks*B, 32) when inner_out is None.
+        leaf_parts > 1 writes the exchange layout [part][chunk][leaf in part] (see include/hobbit_b200.h)."""
         p = poly if isinstance(poly, int) else _F(poly)
         ret = None
         if inner_out is None:
             ret = np.zeros((nchunks * B, 32), dtype=np.uint8)
             inner_out = ret
-        self._ck(self.lib.hb_commit_encode_chunks(self.h, _ptr(p), c_sz(nchunks), c_sz(B), int(trs), int(lin), _ptr(inner_out)))
+        self._ck(self.lib.hb_commit_encode_chunks(self.h, _ptr(p), c_sz(nchunks), c_sz(B), int(trs), int(lin), _ptr(inner_out),
+                                                  c_sz(leaf_parts), c_sz(first_chunk), c_sz(total_chunks)))
         return ret
 
     def md_chain(self, inner, nchunks, nleaves, leaves):

@@ -74,18 +74,18 @@ __global__ void any_nonzero_kernel(const F *__restrict__ v, size_t n, int *flag)
 }
 
 // ---- T1 ------------------------------------------------------------------------------------------------
-int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, size_t nchunks, uint8_t *inner) {
+int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, size_t nchunks, uint8_t *inner, InnerLayout lay) {
     if (trs <= 0 || n % trs) HB_FAIL(ctx, "tensorcode: n must be a multiple of tensor_row_size");
     size_t cols = 2 * n / trs;
     if (cols & (cols - 1)) HB_FAIL(ctx, "tensorcode: 2n/trs must be a power of two");
     HB_TRY(ntt_rows_padded_dev(ctx, msg, n / trs, T, cols, ilog2(cols), trs, nchunks, n, 4 * n));
     if (lin) {
-        HB_TRY(encode_cols_dev(ctx, T, trs, cols, nchunks, 4 * n, inner));
+        HB_TRY(encode_cols_dev(ctx, T, trs, cols, nchunks, 4 * n, inner, lay));
     } else {
         size_t rows = 2 * (size_t)trs;
         if (rows & (rows - 1)) HB_FAIL(ctx, "tensorcode: RS columns need a power-of-two tensor_row_size");
         for (size_t c = 0; c < nchunks; c++) HB_TRY(ntt_cols_dev(ctx, T + c * 4 * n, ilog2(rows), cols, trs));
-        if (inner) HB_TRY(md_inner_standard_dev(ctx, T, rows, cols, nchunks, 4 * n, inner));
+        if (inner) HB_TRY(md_inner_standard_dev(ctx, T, rows, cols, nchunks, 4 * n, inner, lay));
     }
     return 0;
 }
@@ -309,26 +309,33 @@ extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K
 }
 
 // ---- C1, sharded form: the chunk-independent part and the chunk-ordered chain as two calls -----------------------
-extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out) {
+extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out,
+                                       size_t leaf_parts, size_t first_chunk, size_t total_chunks) {
     if (nchunks == 0) return 0;
     if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_commit_encode_chunks: chunk size must be a power of two");
     if (trs < 2 || (2 * trs) % 4) HB_FAIL(ctx, "hb_commit_encode_chunks: tensor_row_size must be even");
-    const size_t N = nchunks * B;
-    if (ctx->tensor_elems != 4 * N) {
+    if (leaf_parts == 0) leaf_parts = 1;
+    if (total_chunks == 0) { total_chunks = nchunks; first_chunk = 0; }
+    if (B % leaf_parts || first_chunk + nchunks > total_chunks) HB_FAIL(ctx, "hb_commit_encode_chunks: bad leaf_parts / chunk range");
+    // the resident tensor covers ALL of this rank's chunks (total_chunks); this call fills [first_chunk, first_chunk + nchunks)
+    const size_t Nt = total_chunks * B;
+    if (ctx->tensor_elems != 4 * Nt) {
         if (ctx->tensor) cudaFree(ctx->tensor);
         ctx->tensor = nullptr; ctx->tensor_elems = 0;
-        HB_CHECK(ctx, cudaMalloc(&ctx->tensor, 4 * N * sizeof(F)));
-        ctx->tensor_elems = 4 * N;
+        HB_CHECK(ctx, cudaMalloc(&ctx->tensor, 4 * Nt * sizeof(F)));
+        ctx->tensor_elems = 4 * Nt;
     }
-    ctx->tensor_N = N; ctx->tensor_K = (int)nchunks; ctx->tensor_trs = trs;
+    ctx->tensor_N = Nt; ctx->tensor_K = (int)total_chunks; ctx->tensor_trs = trs;
+    const size_t N = nchunks * B;
     Staged p(ctx), in(ctx);
     HB_TRY(p.in(poly, N * sizeof(F)));
     HB_TRY(in.outbuf(inner_out, N * 32));
-    // groups bound the size of one launch (grid.y) and keep the working set in L2-friendly pieces
+    // groups bound the size of one launch (grid.y)
     const size_t G = std::max<size_t>(1, std::min<size_t>(nchunks, ((size_t)1 << 30) / (B * 32)));
     for (size_t c0 = 0; c0 < nchunks; c0 += G) {
         size_t nc = std::min(G, nchunks - c0);
-        HB_TRY(tensorcode_dev(ctx, p.as<F>() + c0 * B, B, trs, linear_time, ctx->tensor + c0 * 4 * B, nc, in.as<uint8_t>() + c0 * B * 32));
+        InnerLayout lay; lay.part_leaves = B / leaf_parts; lay.chunks_total = nchunks; lay.chunk0 = c0;
+        HB_TRY(tensorcode_dev(ctx, p.as<F>() + c0 * B, B, trs, linear_time, ctx->tensor + (first_chunk + c0) * 4 * B, nc, in.as<uint8_t>(), lay));
     }
     HB_TRY(in.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

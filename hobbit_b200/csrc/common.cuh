@@ -19,6 +19,20 @@ struct EncStage {                       // one sparse mat-vec of the expander en
     int rowptr_base;                    // index into rowptr[] (R+1 entries)
 };
 
+// Where the inner leaf digest of (chunk c of this launch, leaf position p) goes.  Plain: [chunk][leaf].  Sharded exchange layout
+// (hobbit_b200/dist.py): [leaf part][chunk of the whole call][leaf inside the part], so that the slice for destination rank h is
+// contiguous and no permute pass is needed before the all_to_all.
+struct InnerLayout {
+    size_t part_leaves = 0;      // leaves per part (0 = unset)
+    size_t chunks_total = 0;     // chunks in the whole call
+    size_t chunk0 = 0;           // index of this launch's first chunk inside the call
+    __host__ __device__ size_t offset(size_t chunk_in_launch, size_t p) const {
+        size_t part = p / part_leaves, off = p - part * part_leaves;
+        return (part * chunks_total + chunk0 + chunk_in_launch) * part_leaves + off;
+    }
+    static InnerLayout plain(size_t leaves, size_t chunks) { InnerLayout l; l.part_leaves = leaves; l.chunks_total = chunks; l.chunk0 = 0; return l; }
+};
+
 struct ExpanderDev {
     long long n = 0;
     int cwlen = 0;
@@ -157,15 +171,15 @@ int ntt_rows_padded_dev(hb_ctx *ctx, const F *src, size_t in_len, F *dst, size_t
 int ntt_cols_dev(hb_ctx *ctx, F *mat, int logn, size_t cols, size_t nz_rows);
 // expander-encode every column of nchunks matrices T + c*chunk_stride (rows [0,n) hold the messages); writes rows [n, 2n).
 // inner != nullptr: also the inner leaf digests of commit_standard, chunk c at inner + c*(n/2*cols)*32.
-int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner);
+int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner, InnerLayout lay);
 // inner digests H1(T[4j][k] | T[4j+1][k] | T[4j+2][k] | T[4j+3][k]) of nchunks matrices (rows x cols each)
-int md_inner_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner);
+int md_inner_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner, InnerLayout lay);
 // leaf[p] <- H1(inner[c][p] | leaf[p]) for c = 0..nchunks-1 in order (the Merkle–Damgård chain over chunks)
 int md_chain_dev(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);
 int md_leaves_stream4_dev(hb_ctx *ctx, const F *c0, const F *c1, const F *c2, const F *T, size_t cells, uint8_t *leaves);
 int blake3_64_dev(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count);
 int merkle_tree_dev(hb_ctx *ctx, uint8_t *levels, size_t nleaves);
 // nchunks messages of n elements (contiguous) -> nchunks tensors of 4n elements (contiguous); inner: see encode_cols_dev
-int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, size_t nchunks, uint8_t *inner);
+int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, size_t nchunks, uint8_t *inner, InnerLayout lay = InnerLayout());
 
 }  // namespace hb

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(1024)
 encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int n, int cwlen,
                    const EncStage *__restrict__ stages, int nstages,
                    const int *__restrict__ rowptr, const uint2 *__restrict__ edges,
-                   uint8_t *__restrict__ inner_base, Digest zero_quad) {
+                   uint8_t *__restrict__ inner_base, Digest zero_quad, InnerLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *cw = reinterpret_cast<F *>(smem_raw);                   // cw[row * CB + c]
     F *T = Tbase + (size_t)blockIdx.y * chunk_stride;
@@ -80,7 +80,6 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
         T[(size_t)r * cols + col0 + c] = (r < (unsigned)cwlen) ? cw[r * CB + c] : mkF(0, 0);
 
     if (INNER) {
-        uint8_t *inner = inner_base + (size_t)blockIdx.y * ((size_t)(n / 2) * cols) * 32;
         for (unsigned j = t0; j < (unsigned)n / 2; j += tstep) {
             uint32_t out[8];
             if (4 * j >= (unsigned)cwlen) {
@@ -97,7 +96,7 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
                 }
                 blake3_compress64(m, out);
             }
-            uint4 *lp = reinterpret_cast<uint4 *>(inner + ((size_t)j * cols + col0 + c) * 32);
+            uint4 *lp = reinterpret_cast<uint4 *>(inner_base + lay.offset(blockIdx.y, (size_t)j * cols + col0 + c) * 32);
             lp[0] = make_uint4(out[0], out[1], out[2], out[3]);
             lp[1] = make_uint4(out[4], out[5], out[6], out[7]);
         }
@@ -112,7 +111,7 @@ static Digest zero_quad_digest() {
 }
 
 template <int CB>
-static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner) {
+static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner, InnerLayout lay) {
     const ExpanderDev &ex = ctx->exp;
     size_t smem = (size_t)ex.cwlen * CB * sizeof(F);
     dim3 grid((unsigned)(cols / CB), (unsigned)nchunks);
@@ -121,28 +120,29 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     if (inner) {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest());
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay);
     } else {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, false>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest());
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay);
     }
     return 0;
 }
 
-int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner) {
+int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner, InnerLayout lay) {
+    if (lay.part_leaves == 0) lay = InnerLayout::plain((size_t)(n / 2) * cols, nchunks);
     const ExpanderDev &ex = ctx->exp;
     if (ex.n != n) HB_FAIL(ctx, "encode: no expander installed for this message length (call hb_expander_set / expander_init_store first)");
     if (nchunks > 65535) HB_FAIL(ctx, "encode: too many chunks in one launch");
     const size_t kMaxSmem = 227 * 1024;
     size_t per_col = (size_t)ex.cwlen * sizeof(F);
     // widest column block that fits; prefer <= ~100 KB tiles when the code is small so several CTAs share an SM
-    if (cols % 32 == 0 && per_col * 32 <= 100 * 1024) return launch_encode<32>(ctx, T, n, cols, nchunks, chunk_stride, inner);
-    if (cols % 16 == 0 && per_col * 16 <= 100 * 1024) return launch_encode<16>(ctx, T, n, cols, nchunks, chunk_stride, inner);
-    if (cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, nchunks, chunk_stride, inner);
-    if (cols % 4 == 0 && per_col * 4 <= kMaxSmem) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner);
-    if (cols % 2 == 0 && per_col * 2 <= kMaxSmem) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner);
-    if (per_col <= kMaxSmem) return launch_encode<1>(ctx, T, n, cols, nchunks, chunk_stride, inner);
+    if (cols % 32 == 0 && per_col * 32 <= 100 * 1024) return launch_encode<32>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+    if (cols % 16 == 0 && per_col * 16 <= 100 * 1024) return launch_encode<16>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+    if (cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+    if (cols % 4 == 0 && per_col * 4 <= kMaxSmem) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+    if (cols % 2 == 0 && per_col * 2 <= kMaxSmem) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+    if (per_col <= kMaxSmem) return launch_encode<1>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     HB_FAIL(ctx, "encode: codeword does not fit in shared memory (message length too large for the column kernel)");
 }
 
@@ -218,7 +218,7 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_F *src, hb_F *dst, long lon
         // base case of the recursion: the codeword is the message (linear_code_encode.h:73-78)
         HB_CHECK(ctx, cudaMemsetAsync(d.as<F>() + (size_t)n * ncols, 0, (size_t)n * ncols * sizeof(F), ctx->stream));
     } else {
-        HB_TRY(encode_cols_dev(ctx, d.as<F>(), n, ncols, 1, 0, nullptr));
+        HB_TRY(encode_cols_dev(ctx, d.as<F>(), n, ncols, 1, 0, nullptr, InnerLayout()));
     }
     HB_TRY(d.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

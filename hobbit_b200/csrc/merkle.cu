@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) blake3_64_kernel(const uint8_t *__restric
 // commit_standard leaves (Our_PC.cpp:160-166): leaf[j*cols+k] <- H1( H1(T[4j][k]|T[4j+1][k]|T[4j+2][k]|T[4j+3][k]) | leaf[j*cols+k] ),
 // chained over the chunks in order.  Split in two kernels: the inner digests of all chunks are independent ...
 __global__ void __launch_bounds__(256) md_inner_standard_kernel(const F *__restrict__ Tbase, size_t chunk_stride, size_t rows, size_t cols,
-                                                                uint8_t *__restrict__ inner_base) {
+                                                                uint8_t *__restrict__ inner_base, InnerLayout lay) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t nl = (rows / 4) * cols;
     if (i >= nl) return;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) md_inner_standard_kernel(const F *__restr
 #pragma unroll
     for (int q = 0; q < 4; q++) cell_words(T[(4 * j + q) * cols + k], m + 4 * q);
     blake3_compress64(m, out);
-    store_digest(inner_base + ((size_t)blockIdx.y * nl + i) * 32, out);
+    store_digest(inner_base + lay.offset(blockIdx.y, i) * 32, out);
 }
 // ... and only the outer compression is sequential in the chunk index (one thread walks one leaf position).
 __global__ void __launch_bounds__(256) md_chain_kernel(const uint8_t *__restrict__ inner, size_t nchunks, size_t nleaves, uint8_t *__restrict__ leaves) {
@@ -146,9 +146,10 @@ int blake3_64_dev(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count) {
     if (count) HB_LAUNCH(ctx, blake3_64_kernel, blocks_for(count, 256), 256, 0, src, dst, count);
     return 0;
 }
-int md_inner_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner) {
+int md_inner_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner, InnerLayout lay) {
     size_t n = (rows / 4) * cols;
-    if (n && nchunks) HB_LAUNCH(ctx, md_inner_standard_kernel, dim3(blocks_for(n, 256), (unsigned)nchunks), 256, 0, T, chunk_stride, rows, cols, inner);
+    if (lay.part_leaves == 0) lay = InnerLayout::plain(n, nchunks);
+    if (n && nchunks) HB_LAUNCH(ctx, md_inner_standard_kernel, dim3(blocks_for(n, 256), (unsigned)nchunks), 256, 0, T, chunk_stride, rows, cols, inner, lay);
     return 0;
 }
 int md_chain_dev(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves) {

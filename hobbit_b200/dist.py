@@ -29,10 +29,18 @@ class GpuBackend:
     def zeros(self, *shape):
         return torch.zeros(shape, dtype=torch.uint8, device=self.device)
 
-    def encode_chunks(self, poly, nchunks, B, trs, lin):
-        """poly: int device pointer / numpy host array of nchunks*B elements."""
-        inner = self.empty(nchunks, B, 32)
-        self.ctx.commit_encode_chunks(poly, nchunks, B, trs, lin, inner_out=inner.data_ptr())
+    def sync(self):
+        torch.cuda.synchronize()
+
+    def encode_chunks(self, poly, nchunks, B, trs, lin, first=0, parts=1, total=0):
+        """poly: int device pointer / numpy host array holding this rank's chunks; encodes chunks [first, first+nchunks).
+        Returns the inner digests in the exchange layout [parts][nchunks][B/parts][32] (written so by the kernel itself)."""
+        inner = self.empty(parts, nchunks, B // parts, 32)
+        if isinstance(poly, int):
+            src = poly + first * B * 16
+        else:
+            src = poly[first * B:(first + nchunks) * B]
+        self.ctx.commit_encode_chunks(src, nchunks, B, trs, lin, inner_out=inner.data_ptr(), leaf_parts=parts, first_chunk=first, total_chunks=total)
         return inner
 
     # torch (and NCCL) work is ordered on torch's streams, the library's on its own stream: every hand-over is a full
@@ -51,24 +59,45 @@ class GpuBackend:
         return lv
 
 
-def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None):
-    """poly_local: this rank's K/G consecutive chunks (chunk range [rank*K/G, (rank+1)*K/G)).
-    Returns every Merkle level of the commitment as one (2B-1, 32) uint8 tensor on every rank (== MT_hashes, leaves first)."""
+def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None, groups=4, timing=None):
+    """poly_local: this rank's K/G consecutive chunks (chunk range [rank*K/G, (rank+1)*K/G)); numpy host array, int device
+    pointer, or anything backend.encode_chunks accepts together with an element offset.
+    Returns every Merkle level of the commitment as one (2B-1, 32) uint8 tensor on every rank (== MT_hashes, leaves first).
+
+    The local chunks are encoded in `groups` pieces; the all_to_all of piece i runs (async, NCCL stream) while piece i+1 is being
+    encoded, so the exchange hides behind the encode except for the last piece."""
+    import time
     G = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     assert K % G == 0 and B % G == 0, "chunks and leaves must split evenly across ranks"
     kl, Bp = K // G, B // G
-    inner = backend.encode_chunks(poly_local, kl, B, trs, lin)                       # [kl, B, 32]
-    if G > 1:
-        # to rank h: my chunks, h's leaf range.  [kl, G, Bp, 32] -> [G, kl, Bp, 32]
-        send = inner.view(kl, G, Bp, 32).permute(1, 0, 2, 3).contiguous()
-        recv = torch.empty_like(send)                                                # [G(src rank), kl, Bp, 32] == global chunk order
-        dist.all_to_all_single(recv, send, group=group)
-        inner_all = recv.view(K, Bp, 32)
+    t0 = time.perf_counter()
+    if G == 1:
+        inner_all = backend.encode_chunks(poly_local, kl, B, trs, lin, 0).view(kl, B, 32)
     else:
-        inner_all = inner
+        groups = max(1, min(groups, kl))
+        while kl % groups:
+            groups -= 1
+        kg = kl // groups
+        recv = backend.empty(G, kl, Bp, 32)                      # [source rank][its local chunk][my leaf range] == global chunk order
+        works = []
+        for g in range(groups):
+            send = backend.encode_chunks(poly_local, kg, B, trs, lin, g * kg, parts=G, total=kl)   # [G, kg, Bp, 32]: slice h -> rank h
+            if dist.get_backend(group) == "nccl":
+                # receive straight into the final [source rank][chunk] slots: no staging copy
+                outs = [recv[h, g * kg:(g + 1) * kg] for h in range(G)]
+                works.append((dist.all_to_all(outs, list(send.unbind(0)), group=group, async_op=True), send, None, g))
+            else:                                                                     # gloo (CPU tests): single-buffer form + copy
+                rbuf = backend.empty(G, kg, Bp, 32)
+                works.append((dist.all_to_all_single(rbuf, send, group=group, async_op=True), send, rbuf, g))
+        for w, _send, rbuf, g in works:
+            w.wait()
+            if rbuf is not None:
+                recv[:, g * kg:(g + 1) * kg] = rbuf
+        inner_all = recv.view(K, Bp, 32)
+    t1 = time.perf_counter()
     leaves = backend.chain(inner_all, backend.zeros(Bp, 32))                         # chain starts from all-zero digests
     sub = backend.tree(leaves)                                                       # [(2Bp-1), 32]
+    t2 = time.perf_counter()
     if G == 1:
         return sub
     allsub = [torch.empty_like(sub) for _ in range(G)]
@@ -81,4 +110,8 @@ def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None):
     roots = out[-1]                                                                  # G subtree roots == level log2(Bp) of the global tree
     top = backend.tree(roots)                                                        # top log2(G) levels (every rank, G-1 compressions)
     out.append(top[G:])
-    return torch.cat(out, dim=0)
+    res = torch.cat(out, dim=0)
+    if timing is not None:
+        backend.sync()
+        timing.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
+    return res

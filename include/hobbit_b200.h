@@ -94,11 +94,16 @@ int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K, int trs, 
 /* commit_standard split for sharding across GPUs: the leaf of position p is the Merkle–Damgård chain
  *   leaf[p] <- H1( H1(4-row quad of chunk c at p) | leaf[p] ),  c = 0..K-1 in order, starting from 32 zero bytes.
  * hb_commit_encode_chunks: the chunk-independent part for `nchunks` consecutive chunks of B coefficients — tensor code (kept
- *   resident, like hb_commit_standard) and the INNER digests, inner_out[c*B + p] (32 bytes each).
+ *   resident, like hb_commit_standard: this call fills chunks [first_chunk, first_chunk+nchunks) of a tensor of total_chunks;
+ *   total_chunks = 0 means "just these") and the INNER digests (32 bytes each) in the layout
+ *   inner_out[(part * nchunks + c) * (B/leaf_parts) + off] for leaf position p = part * (B/leaf_parts) + off:
+ *   leaf_parts = 1 is the plain [chunk][leaf] order; leaf_parts = G makes the slice for each destination rank contiguous, so
+ *   the all_to_all needs no permute pass.
  * hb_md_chain: leaves[p] <- chain over inner[c*nleaves + p], c = 0..nchunks-1, continuing from the current leaves[p].
  * A rank that owns a chunk range calls the first; after exchanging inner digests by leaf range, the owner of a leaf range calls the
  * second and hb_merkle_tree on its subtree (hobbit_b200/dist.py). */
-int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out);
+int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out,
+                            size_t leaf_parts, size_t first_chunk, size_t total_chunks);
 int hb_md_chain(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);
 /* device pointer to the resident `_tensor` of the last hb_commit_standard (K*4*(N/K) elements), or NULL */
 const hb_F *hb_tensor_device(hb_ctx *ctx);

@@ -21,10 +21,18 @@ class OracleBackend:
     def zeros(self, *shape):
         return torch.zeros(shape, dtype=torch.uint8)
 
-    def encode_chunks(self, poly, nchunks, B, trs, lin):
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=torch.uint8)
+
+    def sync(self):
+        pass
+
+    def encode_chunks(self, poly, nchunks, B, trs, lin, first=0, parts=1, total=0):
         inner = np.zeros((nchunks, B, 32), dtype=np.uint8)
-        self.orc.fn("commit_encode_chunks")(_p(poly), ctypes.c_size_t(nchunks), ctypes.c_size_t(B), trs, int(lin), _p(inner))
-        return torch.from_numpy(inner)
+        src = np.ascontiguousarray(poly[first * B:(first + nchunks) * B])
+        self.orc.fn("commit_encode_chunks")(_p(src), ctypes.c_size_t(nchunks), ctypes.c_size_t(B), trs, int(lin), _p(inner))
+        # exchange layout [parts][nchunks][B/parts][32] (the CUDA kernel writes it directly)
+        return torch.from_numpy(np.ascontiguousarray(inner.reshape(nchunks, parts, B // parts, 32).transpose(1, 0, 2, 3)))
 
     def chain(self, inner, leaves):
         i = np.ascontiguousarray(inner.numpy()); l = leaves.numpy()
