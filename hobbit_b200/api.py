@@ -371,3 +371,10 @@ class Context:
         reply = np.zeros((len(col) * len(chunks), 2), dtype=np.uint64)
         self._ck(self.lib.hb_elastic_open_finish(self.h, _ptr(agg), _ptr(reply)))
         return agg, reply.reshape(len(col), len(chunks), 2)
+
+    def sc3_round(self, ins, outs, L, rand):
+        """ins/outs: 3 int device pointers each; returns the 4 cubic coefficients (4,2) of this slice."""
+        r, co = _F(rand), np.zeros((4, 2), dtype=np.uint64)
+        self._ck(self.lib.hb_sc3_round(self.h, c_vp(ins[0]), c_vp(ins[1]), c_vp(ins[2]), c_vp(outs[0]), c_vp(outs[1]), c_vp(outs[2]), c_sz(L),
+                                       _ptr(r), _ptr(co)))
+        return co

@@ -1107,3 +1107,19 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
     for (int i = 0; i < 4 * lgn + 3; i++) out[k++] = p2[i];
     return 0;
 }
+
+// One round of the 3-product sumcheck on DEVICE tables, for callers that own the round loop (multi-GPU sharding by hypercube prefix,
+// hobbit_b200/dist.py): accumulates the cubic coefficients of sum_j prod_t (in_t[2j] + X (in_t[2j+1] - in_t[2j])) over L pairs and
+// writes out_t[j] = in_t[2j] + rand * (in_t[2j+1] - in_t[2j])  (the S2 schedule: fold with the incoming challenge, sumcheck.cpp:1987-2014).
+extern "C" int hb_sc3_round(hb_ctx *ctx, const hb_F *in1, const hb_F *in2, const hb_F *in3, hb_F *out1, hb_F *out2, hb_F *out3, size_t L,
+                            const hb_F *rand, hb_F *coeffs4) {
+    HB_TRY(ensure_scratch(ctx));
+    if (!is_device_ptr(in1) || !is_device_ptr(out1)) HB_FAIL(ctx, "hb_sc3_round: tables must be device memory");
+    Tabs<3> t;
+    t.in[0] = (const F *)in1; t.in[1] = (const F *)in2; t.in[2] = (const F *)in3;
+    t.out[0] = (F *)out1; t.out[1] = (F *)out2; t.out[2] = (F *)out3;
+    F co[4];
+    HB_TRY((launch_round<3, POLY_AND_FOLD, false>(ctx, t, L, fromabi(*rand), co)));
+    for (int c = 0; c < 4; c++) coeffs4[c] = toabi(co[c]);
+    return 0;
+}

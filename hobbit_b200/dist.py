@@ -115,3 +115,98 @@ def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None, gro
         backend.sync()
         timing.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Sumcheck sharded by hypercube prefix: rank g holds the contiguous slice [g*n/G, (g+1)*n/G) of every table.  Adjacent-pair
+# folding keeps pairs rank-local for the first log2(n/G) rounds; per round the only communication is the all-reduce of the 4
+# round-polynomial coefficients (64 B; summed as uint64 limbs — each limb < 2^61 and G <= 8, so the sum cannot overflow — then reduced
+# mod p), after which every rank derives the same MiMC challenge.  Once a slice is down to one entry the G values per table are
+# all-gathered and the last log2 G rounds run redundantly on every rank.
+P61 = (1 << 61) - 1
+
+
+def _mod_p(a):
+    a = (a & np.uint64(P61)) + (a >> np.uint64(61))
+    return np.where(a >= np.uint64(P61), a - np.uint64(P61), a)
+
+
+def _fadd(a, b):
+    s = a + b
+    return np.where(s >= np.uint64(P61), s - np.uint64(P61), s)
+
+
+def sumcheck3_sharded(backend, tables, n_local, prev_r, mimc, group=None):
+    """_generate_3product_sumcheck_proof (sumcheck.cpp:1974-2058) over tables of n = n_local * G entries.
+    tables: backend-specific handles of this rank's 3 slices.  mimc(x, k) -> (1,2) uint64.
+    Returns the flat proof (5*rounds + 4, 2) uint64, identical on every rank and identical to the single-device prover."""
+    G = dist.get_world_size(group) if dist.is_initialized() else 1
+    rounds_local = int(np.log2(n_local))
+    rounds = rounds_local + int(np.log2(G))
+    proof = np.zeros((5 * rounds + 4, 2), dtype=np.uint64)
+    rand = np.ascontiguousarray(prev_r, dtype=np.uint64).reshape(1, 2)
+    cur = tables
+    for i in range(rounds_local):
+        L = n_local >> (i + 1)
+        co, cur = backend.sc3_round(cur, L, rand)                                    # (4,2) uint64 partial coefficients
+        if G > 1:
+            t = backend.to_comm(co)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)                    # limb-wise uint64 sums (< 8 * 2^61)
+            co = _mod_p(backend.from_comm(t))
+        proof[4 * rounds + i] = rand
+        for c in range(4):
+            proof[4 * i + c] = co[c]
+            rand = mimc(rand, co[c:c + 1])
+    heads = backend.heads(cur)                                                       # (3,2): the single remaining entry of each slice
+    if G > 1:
+        t = backend.to_comm(heads)
+        allh = [torch.empty_like(t) for _ in range(G)]
+        dist.all_gather(allh, t, group=group)
+        small = np.stack([backend.from_comm(x) for x in allh], axis=1)               # (3, G, 2): rank order == index order
+        cur = backend.tables_from(small)                                             # G entries per table, on every rank
+        for i in range(int(np.log2(G))):
+            co, cur = backend.sc3_round(cur, G >> (i + 1), rand)
+            r_i = rounds_local + i
+            proof[4 * rounds + r_i] = rand
+            for c in range(4):
+                proof[4 * r_i + c] = co[c]
+                rand = mimc(rand, co[c:c + 1])
+        heads = backend.heads(cur)
+    rand = mimc(rand, heads[0:1]); rand = mimc(rand, heads[1:2])
+    proof[5 * rounds:5 * rounds + 3] = heads
+    proof[5 * rounds + 3] = rand
+    return proof
+
+
+class GpuSumcheckBackend:
+    """Round kernel = hb_sc3_round on device slices (ping-pong scratch); NCCL moves 64 bytes per round."""
+
+    def __init__(self, ctx, device):
+        self.ctx, self.device = ctx, device
+        self.scratch = None
+
+    def sc3_round(self, cur, L, rand):
+        if self.scratch is None:
+            n = cur[0].shape[0]
+            self.scratch = [[torch.empty((max(n // 2, 1), 2), dtype=torch.int64, device=self.device) for _ in range(3)],
+                            [torch.empty((max(n // 4, 1), 2), dtype=torch.int64, device=self.device) for _ in range(3)]]
+            self.flip = 0
+        out = self.scratch[self.flip]
+        self.flip ^= 1
+        torch.cuda.synchronize()
+        co = self.ctx.sc3_round([t.data_ptr() for t in cur], [t.data_ptr() for t in out], L, rand)
+        return co, [t[:L] for t in out]
+
+    def heads(self, cur):
+        torch.cuda.synchronize()
+        return np.stack([t[0].cpu().numpy().view(np.uint64) for t in cur])
+
+    def tables_from(self, small):
+        self.scratch = None                                                          # new (tiny) ping-pong buffers
+        return [torch.from_numpy(np.ascontiguousarray(small[k]).view(np.int64)).to(self.device) for k in range(3)]
+
+    def to_comm(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(self.device)
+
+    def from_comm(self, t):
+        return t.cpu().numpy().view(np.uint64)

@@ -152,6 +152,12 @@ int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, const hb_F *
 int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n, const hb_F *prev_r, const hb_F *x_rand,
                 hb_F *out, size_t *written, int *nfr, double *ps);
 
+/* One S2 round on device tables, for callers that own the round loop (sumcheck sharded across GPUs by hypercube prefix:
+ * every rank runs this on its contiguous slice and the 4 coefficients are all-reduced, hobbit_b200/dist.py).
+ * coeffs4 = cubic coefficients (a,b,c,d) over the L pairs of the slice; out_t[j] = in_t[2j] + rand*(in_t[2j+1]-in_t[2j]). */
+int hb_sc3_round(hb_ctx *ctx, const hb_F *in1, const hb_F *in2, const hb_F *in3, hb_F *out1, hb_F *out2, hb_F *out3, size_t L,
+                 const hb_F *rand, hb_F *coeffs4);
+
 /* ---- gate consistency, in-memory form: prove_gate_consistency_standard (sumcheck.cpp:434-501) --------------------------------- */
 /* Degree-4 sumcheck of beta(x) (mul(x) L(x) R(x) + add(x) (L(x)+R(x)) - O(x)), mul = 1 - add, beta = eq(r), rand_0 = F(213).
  * The reference folds its arguments in place and returns nothing; here the inputs are untouched and

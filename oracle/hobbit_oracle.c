@@ -900,3 +900,15 @@ void orc_elastic_open_front(const F *stream, size_t nchunks, size_t B, int trs, 
     }
     free(T);
 }
+
+/* one S2 round on a slice (for the sharded-sumcheck orchestration tests): coefficients of the slice + fold with `rand` */
+void orc_sc3_round(const F *v1, const F *v2, const F *v3, F *o1, F *o2, F *o3, size_t L, const F *rand, F *coeffs4) {
+    F acc[4] = { F0, F0, F0, F0 };
+    for (size_t j = 0; j < L; j++) {
+        cubic_acc(acc, v1[2 * j], v1[2 * j + 1], v2[2 * j], v2[2 * j + 1], v3[2 * j], v3[2 * j + 1]);
+        o1[j] = f_add(v1[2 * j], f_mul(*rand, f_sub(v1[2 * j + 1], v1[2 * j])));
+        o2[j] = f_add(v2[2 * j], f_mul(*rand, f_sub(v2[2 * j + 1], v2[2 * j])));
+        o3[j] = f_add(v3[2 * j], f_mul(*rand, f_sub(v3[2 * j + 1], v3[2 * j])));
+    }
+    memcpy(coeffs4, acc, sizeof acc);
+}

@@ -78,3 +78,60 @@ def test_sharded_commit_gloo(world, lin):
         p.join(300)
         assert p.exitcode == 0
     assert ret.get(timeout=10) == 1
+
+
+class OracleSumcheckBackend:
+    def __init__(self):
+        self.orc = Checker("orc")
+
+    def sc3_round(self, cur, L, rand):
+        outs = [np.zeros((L, 2), dtype=np.uint64) for _ in range(3)]
+        co = np.zeros((4, 2), dtype=np.uint64)
+        r = np.ascontiguousarray(rand, dtype=np.uint64)
+        cur = [np.ascontiguousarray(c) for c in cur]
+        self.orc.fn("sc3_round")(_p(cur[0]), _p(cur[1]), _p(cur[2]), _p(outs[0]), _p(outs[1]), _p(outs[2]), ctypes.c_size_t(L), _p(r), _p(co))
+        return co, outs
+
+    def heads(self, cur):
+        return np.stack([c[0] for c in cur])
+
+    def tables_from(self, small):
+        return [np.ascontiguousarray(small[k]) for k in range(3)]
+
+    def to_comm(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy())
+
+    def from_comm(self, t):
+        return t.numpy().view(np.uint64)
+
+
+def sc_worker(rank, world, port, n, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hobbit_b200.dist import sumcheck3_sharded
+    be = OracleSumcheckBackend()
+    rng = np.random.default_rng(3)
+    v = [rand_field(rng, n) for _ in range(3)]
+    pr = rand_field(rng, 1)
+    nl = n // world
+    got = sumcheck3_sharded(be, [x[rank * nl:(rank + 1) * nl] for x in v], nl, pr, be.orc.mimc)
+    want, _ = be.orc.sumcheck3(v[0], v[1], v[2], pr)
+    t = torch.tensor([1 if np.array_equal(got, want) else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 256), (4, 64), (2, 2)])
+def test_sharded_sumcheck_gloo(world, n):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=sc_worker, args=(r, world, port, n, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1

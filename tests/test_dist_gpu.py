@@ -68,3 +68,44 @@ def test_sharded_commit_nccl_2gpus():
         p.join(300)
         assert p.exitcode == 0
     assert ret.get(timeout=10) == 1
+
+
+def _sc_worker(rank, world, port, n, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import hobbit_b200
+    from hobbit_b200.dist import GpuSumcheckBackend, sumcheck3_sharded
+    ctx = hobbit_b200.Context(rank)
+    rng = np.random.default_rng(3)
+    v = [rand_field(rng, n) for _ in range(3)]
+    pr = rand_field(rng, 1)
+    nl = n // world
+    dev = [torch.from_numpy(np.ascontiguousarray(x[rank * nl:(rank + 1) * nl]).view(np.int64)).cuda() for x in v]
+    got = sumcheck3_sharded(GpuSumcheckBackend(ctx, torch.device("cuda", rank)), dev, nl, pr, ctx.mimc)
+    want, _ = ctx.sumcheck3(v[0], v[1], v[2], pr)
+    t = torch.tensor([1 if np.array_equal(got, want) else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+    ctx.close()
+
+
+def test_sharded_sumcheck_nccl_2gpus():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2); the CPU/gloo twin is tests/test_dist_gloo.py")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    c = mp.get_context("spawn")
+    ret = c.Queue()
+    procs = [c.Process(target=_sc_worker, args=(r, 2, port, 1 << 16, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1
