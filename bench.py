@@ -283,9 +283,15 @@ def main():
     alg_bytes = {"encode_cols_kernel": 32 + 32 + 32.0, "ntt_tile_kernel": 16 + 32, "md_chain_kernel": 32.0}.get(name, 64.0) * coeffs_per_launch
     peak, how = peaks()
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")        # dram bytes per coefficient from the committed ncu --set full capture
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get(name)
+        if tj:
+            traffic = tj["dram_bytes_per_coefficient"] * coeffs_per_launch
     kernel_share = {k: round(v["total_ms"] / sum(x["total_ms"] for x in prof.values()), 4) for k, v in prof.items()}
     roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": how, "avg_launch_ms": per_launch_ms, "launches_timed": rec["launches"],
+                "traffic": traffic, "peak_source": how, "avg_launch_ms": per_launch_ms, "launches_timed": rec["launches"],
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_time_share": kernel_share,
                 "note": "integer-pipe-bound kernel (61-bit modular multiply-adds + BLAKE3 compressions, SURVEY §8d): the HBM fraction is low by "
                         "construction; the ncu pipe utilisation is in profiles/"}
