@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <vector>
 #include <chrono>
+#include <mutex>
+#include <thread>
 #include "config_pc.hpp"
 #include "utils.hpp"
 #include "mimc.h"
@@ -34,6 +36,15 @@ void generate_3product_sumcheck_beta_stream_batch_optimized(stream_descriptor fd
 		vector<F> old_claims, vector<F> &new_claims, vector<vector<F>> &new_r, double &vt, double &ps);
 extern int BUFFER_SPACE_tr;
 extern int aggregation_queries;
+// circuit front end (main.cpp globals / Seval.cpp producer thread)
+extern int fun;
+extern size_t circuit_size;
+extern F a_w, b_w;
+extern std::mutex mtx, mtx2;
+extern std::vector<int> layer_size;
+void Seval_Oracle();
+void init_stream(int b, int n, int d);
+
 void compute_aggregation_reply(stream_descriptor fd, vector<vector<size_t>> &I, vector<vector<F>> &reply);
 void aggregate(stream_descriptor fd, vector<F> beta1, vector<F> random_points, vector<vector<_hash>> &MT_hashes, vector<F> &aggregated_vector, vector<vector<F>> &aggregated_tensor);
 
@@ -333,6 +344,72 @@ void ref_elastic_open_front_rs(size_t N, size_t B, int trs, const uint64_t *beta
     reset_stream(fd);
     aggregate(fd, b, rv, MT, av, at);
     memcpy(agg, av.data(), B * 16);
+}
+
+// ---- circuit streams: the reference's producer thread (Seval_Oracle) + its named streams ------------------------------------
+// One circuit per process (the reference keeps everything in globals and the producer thread never exits): callers run this in a
+// subprocess.  Mirrors main() (main.cpp:1171-1233): init_hash, lock both mutexes, start the producer, init_stream, draw a_w/b_w.
+static bool g_circuit_started = false;
+size_t ref_circuit_start(int fun_, int b, int n, int d, const int *extra, int nextra) {
+    if (g_circuit_started) { printf("ref_shim: one circuit per process\n"); exit(-1); }
+    g_circuit_started = true;
+    init_hash();
+    mtx.lock(); mtx2.lock();
+    fun = fun_;
+    if (fun == 9) for (int i = 0; i < nextra; i++) layer_size.push_back(extra[i]);
+    std::thread t(Seval_Oracle);
+    t.detach();
+    init_stream(b, n, d);
+    a_w = random(); b_w = random();
+    return circuit_size;
+}
+void ref_circuit_ab(uint64_t *out2) { memcpy(out2, &a_w, 16); memcpy(out2 + 2, &b_w, 16); }
+size_t ref_buffer_space() { return BUFFER_SPACE; }
+// read `total` elements of stream `name` in reads of `block` elements (read_stream, witness_stream.cpp:2106-2353)
+void ref_dump_stream(const char *name, size_t total, size_t block, uint64_t *out) {
+    stream_descriptor fd; fd.name = name; fd.size = total; reset_stream(fd);
+    vector<F> v(block);
+    for (size_t off = 0; off < total; off += block) { read_stream(fd, v, (int)block); memcpy(out + 2 * off, v.data(), block * 16); }
+}
+// the gate transcript (read_trace, witness_stream.cpp:1701-1807): cs entries in reads of B
+void ref_dump_trace(size_t cs, size_t B, uint64_t *L, uint64_t *R, uint64_t *O, uint64_t *S) {
+    stream_descriptor fd; fd.name = "transcript_stream"; fd.size = cs; reset_stream(fd);
+    vector<F> l(B), r(B), o(B); vector<int> s(B);
+    for (size_t off = 0; off < cs; off += B) {
+        read_trace(fd, l, r, o, s);
+        memcpy(L + 2 * off, l.data(), B * 16); memcpy(R + 2 * off, r.data(), B * 16); memcpy(O + 2 * off, o.data(), B * 16);
+        for (size_t i = 0; i < B; i++) { S[2 * (off + i)] = (uint64_t)s[i]; S[2 * (off + i) + 1] = 0; }
+    }
+}
+// the reference's own provers on the live streams (prove_circuit, main.cpp:862-886)
+double ref_circuit_commit_witness(uint8_t *levels_out) {
+    stream_descriptor fd; fd.name = "witness"; fd.size = 4 * circuit_size; reset_stream(fd);
+    init_commitment(false);
+    vector<vector<_hash>> MT; _hash comm;
+    auto t0 = std::chrono::steady_clock::now();
+    commit(fd, comm, MT);
+    auto t1 = std::chrono::steady_clock::now();
+    levels_to_flat(MT, levels_out);
+    return std::chrono::duration_cast<std::chrono::duration<double>>(t1 - t0).count();
+}
+double ref_circuit_mul_tree(uint64_t *out8, double *ps_out) {
+    stream_descriptor fd; fd.name = "wiring_consistency_check_opt"; fd.size = 8 * circuit_size; reset_stream(fd);
+    vector<F> px; double vt = 0, ps = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    vector<F> o = prove_multiplication_tree_stream_shallow(fd, 8, fd.size / 8, F(32), 5, px, 0, vt, ps);
+    auto t1 = std::chrono::steady_clock::now();
+    memcpy(out8, o.data(), o.size() * 16); *ps_out = ps;
+    return std::chrono::duration_cast<std::chrono::duration<double>>(t1 - t0).count();
+}
+double ref_circuit_gate_consistency(const uint64_t *r, int nr, double *ps_out) {
+    stream_descriptor fd; fd.name = "transcript_stream"; fd.size = circuit_size; reset_stream(fd);
+    vector<F> rv((const F *)r, (const F *)r + nr);
+    double vt = 0, ps = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    prove_gate_consistency(fd, rv, vt, ps);
+    auto t1 = std::chrono::steady_clock::now();
+    *ps_out = ps;
+    return std::chrono::duration_cast<std::chrono::duration<double>>(t1 - t0).count();
 }
 
 } // extern "C"
