@@ -70,6 +70,12 @@ static long long init_rec(long long n, int dep, int &levels) {
     gen(gD[dep], L, (long long)(n * (kR - 1) - L), kDn);
     return n + L + (long long)(n * (kR - 1) - L);
 }
+const host_graph &expander_graph(int which, int dep) {
+    static host_graph g;
+    const Graph &s = which ? gD[dep] : gC[dep];
+    g.L = s.L; g.R = s.R; g.deg = which ? kDn : kCn; g.nbr = s.nbr.data(); g.w = s.w.data();
+    return g;
+}
 long long expander_init_store(long long n, int dep) {
     int levels = 0;
     long long cw = init_rec(n, dep, levels);

@@ -104,6 +104,43 @@ struct open_front { std::vector<F> beta, aggr_vector; std::vector<std::vector<si
                     std::vector<std::vector<_hash>> commitment_paths; F r_v0; double ps = 0; };
 open_front open_standard_front(std::vector<F> &poly, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, int K);
 
+// ---- the opening recursion (hobbit_open.cpp) -------------------------------------------------------------------------
+// Same names and call order as the reference; the containers that hold TABLES are handles to HBM-resident data instead of host
+// vectors (a maintainer dropping this into the reference keeps the call sites: they only pass these objects around).
+struct host_graph { long long L = 0, R = 0; int deg = 0; const uint32_t *nbr = nullptr; const uint64_t *w = nullptr; };
+const host_graph &expander_graph(int which /*0 = _C, 1 = D*/, int dep);      // the graphs expander_init_store drew (expanders.h:18)
+struct shockwave_data {                        // Virgo.h:27-51; matrix / encoded_matrix / MT live on the device
+    int k = 0; size_t N = 0;
+    F *matrix = nullptr, *encoded_matrix = nullptr;     // k x N/k and k x 2N/k, row-major
+    uint8_t *MT = nullptr;                               // 2N/k leaves, every level, leaves first
+    ~shockwave_data();
+    std::vector<std::vector<_hash>> MT_host() const;     // for tests / serving paths
+    std::vector<F> encoded_host() const;
+};
+struct Whir_data {                             // Virgo.h:52-60
+    int k = 0; size_t N = 0;
+    F *poly = nullptr, *poly_com = nullptr; uint8_t *MT = nullptr;
+    std::vector<F *> FRI_poly; std::vector<uint8_t *> FRI_MT; std::vector<size_t> FRI_size;
+    Whir_data() {}
+    Whir_data(const Whir_data &) = delete; Whir_data &operator=(const Whir_data &) = delete;
+    ~Whir_data();
+    std::vector<std::vector<_hash>> MT_host() const;
+    std::vector<std::vector<_hash>> FRI_MT_host(int i) const;
+    std::vector<F> poly_host() const;
+};
+extern shockwave_data *C_f, *C_c;              // PC_utils.cpp:6-7
+shockwave_data *shockwave_commit(std::vector<F> &poly, int k);
+void shockwave_prove(shockwave_data *data, std::vector<F> x, double &vt, double &ps);        // deletes data, like the reference
+void whir_commit(std::vector<F> &poly, Whir_data &data);
+void _whir_prove(Whir_data &data, std::vector<F> x, double &vt, double &ps);
+proof prove_fft(std::vector<F> &m, std::vector<F> r, F previous_sum, double &vt, double &ps);
+proof prove_fft_matrix(std::vector<std::vector<F>> M, std::vector<F> r, F previous_sum, double &vt, double &ps);
+proof prove_linear_code(std::vector<F> &codeword, int n, double &vt, double &ps);
+void recursive_prover_Spielman(std::vector<F> &input, std::vector<std::vector<F>> &C, std::vector<size_t> I, double &vt, double &ps);
+void recursive_prover_RS(std::vector<F> &aggregated_vector, std::vector<std::vector<size_t>> I, double &vt, double &ps);
+void open_standard(std::vector<F> &poly, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT,
+                   std::vector<std::vector<std::vector<F>>> &_tensor, int K, double &vt, double &ps);
+
 // Elastic_PC
 void init_commitment(bool mod);
 void read_stream_PC(stream_descriptor &fd, F *v, int size);

@@ -187,6 +187,36 @@ int hb_stream_sumcheck_layer(hb_ctx *ctx, const hb_F *xy, size_t total, size_t B
 int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int vectors, size_t B, int distance, int naive,
                        const hb_F *prev_r, const hb_F *x_rand, const hb_F *rnd, hb_F *out, int *layers_out, double *ps);
 
+/* ---- 8f.1: building blocks of the opening recursion behind open_standard / Elastic_PC open ----------------------------------------
+ * (shockwave_commit / shockwave_prove Virgo.cpp:120-157,435-517; whir_commit / _whir_prove :160-178,519-686; recursive_prover_Spielman
+ *  / _RS PC_utils.cpp:290-512; prove_fft / prove_fft_matrix sumcheck.cpp:2975-3027).  The host mirror (hobbit_b200/host/hobbit_open.cpp)
+ * owns the libc RNG order and the Fiat–Shamir scalars and calls these on tables that stay resident in HBM (device pointers). */
+int hb_vec_zero(hb_ctx *ctx, hb_F *v, size_t n);
+/* `rows` rows of in_len elements (contiguous), each zero-extended to 2^logn and transformed (_fft) into dst (rows x 2^logn) */
+int hb_rs_encode_rows(hb_ctx *ctx, const hb_F *src, size_t in_len, size_t rows, hb_F *dst, int logn);
+/* out[j] = sum_i w[i] M[i*stride + j] (j < cols)  — shockwave_prove's aggregation (:446-456), prepare_matrix(transpose(M), r) with
+ * w = eq(r) (utils.cpp:758-775), the column evaluations of the recursive provers (PC_utils.cpp:332-340) */
+int hb_matvec_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *w, hb_F *out);
+/* out[i] = sum_j s[j] M[i*stride + j] (i < rows)  — aggr_c of recursive_prover_Spielman (PC_utils.cpp:318-328), dot products */
+int hb_matvec_rows(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *s, hb_F *out);
+int hb_axpy(hb_ctx *ctx, hb_F *y, const hb_F *x, const hb_F *a, size_t n);                     /* y += a * x */
+/* out[0..n) = 0, then out[idx[k]] = val[k]; idx must be unique (the host resolves the reference's sequential duplicate semantics) */
+int hb_scatter(hb_ctx *ctx, hb_F *out, size_t n, const uint64_t *idx, const hb_F *val, size_t m);
+/* out[q*rows + j] = M[j*stride + col[q]]  — column replies (Virgo.cpp:468-472) */
+int hb_gather_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out);
+/* phiGInit(phi_g, r, F(1), n, false) (utils.cpp:694-755): out has 2^n entries, the upper half stays zero like the reference's */
+int hb_phi_g_init(hb_ctx *ctx, const hb_F *r, int n, hb_F *out);
+/* shockwave_commit's leaves: leaves[c] = root of MT_commit_Blake over the k cells enc[0..k)[c] of column c (Virgo.cpp:140-152) */
+int hb_shockwave_leaves(hb_ctx *ctx, const hb_F *enc, int k, size_t cols, uint8_t *leaves);
+int hb_change_form(hb_ctx *ctx, hb_F *poly, int logn);                                          /* Virgo.cpp:104-118, in place */
+int hb_regroup(hb_ctx *ctx, const hb_F *in, size_t n, int k, hb_F *out);                        /* out[j*2^k + t] = in[j + t*(n>>k)] (:168-175) */
+/* one WHIR sumcheck round over the pairs (j, j+L) of (poly, beta) (Virgo.cpp:548-568): coefficients (a,b,c), then the in-place fold */
+int hb_whir_poly(hb_ctx *ctx, const hb_F *poly, const hb_F *beta, size_t L, hb_F *coeffs3);
+int hb_whir_fold(hb_ctx *ctx, hb_F *poly, hb_F *beta, size_t L, const hb_F *a);
+/* out-of-domain / shift queries of one WHIR iteration (:597-623): zetas = repeats x v points, y[i] = sum_j eq(z_i)[j] poly[j],
+ * beta[j] += sum_i pows[i] eq(z_i)[j]   (poly, beta: 2^v entries) */
+int hb_whir_zeta(hb_ctx *ctx, const hb_F *poly, hb_F *beta, int v, const hb_F *zetas, int repeats, const hb_F *pows, hb_F *y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,238 @@
+// TEST INFRASTRUCTURE ONLY — CPU emulation of (a subset of) the C ABI in include/hobbit_b200.h on top of the C oracle.
+//
+// Purpose: (1) lets the host-side logic of the C++ mirror (hobbit_b200/host/*.cpp: libc RNG order, Fiat–Shamir scalars, proof-size
+// accounting, container marshalling) be tested against the unmodified reference on a machine WITHOUT a GPU (tests/cpp/open_test.cpp
+// built against this library instead of libhobbit_b200.so); (2) serves as the plain restatement of the 8f.1 building blocks
+// (hb_matvec_*, hb_phi_g_init, hb_change_form, hb_whir_*, hb_shockwave_leaves ...) that tests/test_gpu_open.py checks the CUDA
+// kernels against.  Never linked into the product: libhobbit_host.so links libhobbit_b200.so, which fails without a CUDA device.
+//
+// Each function follows the reference lines cited next to its declaration in include/hobbit_b200.h.
+#include "../include/hobbit_b200.h"
+#include "hobbit_oracle.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+typedef orc_F F;
+struct hb_ctx {
+    std::string err;
+    std::vector<F> tensor; size_t tN = 0; int tK = 0, ttrs = 0;
+    std::vector<F> poly; const void *poly_host = nullptr;
+    long long exp_n = 0, exp_cw = 0;
+};
+static const uint64_t P = 2305843009213693951ULL;
+static inline F fadd(F a, F b) { F c; orc_field_binop(0, &a, &b, &c, 1); return c; }
+static inline F fsub(F a, F b) { F c; orc_field_binop(1, &a, &b, &c, 1); return c; }
+static inline F fmul(F a, F b) { F c; orc_field_binop(2, &a, &b, &c, 1); return c; }
+static inline F mk(uint64_t re, uint64_t im = 0) { F r; r.re = re; r.im = im; return r; }
+static inline const F *cF(const hb_F *p) { return reinterpret_cast<const F *>(p); }
+static inline F *mF(hb_F *p) { return reinterpret_cast<F *>(p); }
+static int ilog2(size_t x) { int l = 0; while (x >>= 1) l++; return l; }
+#define FAIL(ctx, msg) do { (ctx)->err = (msg); return 2; } while (0)
+
+extern "C" {
+
+int hb_ctx_create(hb_ctx **out, int) { *out = new hb_ctx; return 0; }
+void hb_ctx_destroy(hb_ctx *ctx) { delete ctx; }
+const char *hb_last_error(hb_ctx *ctx) { return ctx->err.c_str(); }
+int hb_sync(hb_ctx *) { return 0; }
+uint64_t hb_launch_count(hb_ctx *) { return 0; }
+int hb_malloc_device(hb_ctx *, void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : 1; }
+int hb_free_device(hb_ctx *, void *p) { free(p); return 0; }
+int hb_memcpy(hb_ctx *, void *dst, const void *src, size_t bytes) { memmove(dst, src, bytes); return 0; }
+
+void hb_root_of_unity(int logn, hb_F *out) { orc_root_of_unity(logn, mF(out)); }
+void hb_mimc_hash(const hb_F *input, const hb_F *k, hb_F *out) { orc_mimc_hash(cF(input), cF(k), mF(out)); }
+int hb_field_binop(hb_ctx *, int op, const hb_F *a, const hb_F *b, hb_F *c, size_t n) { orc_field_binop(op, cF(a), cF(b), mF(c), n); return 0; }
+
+int hb_ntt_batch(hb_ctx *, hb_F *data, int logn, size_t batch, size_t stride) {
+    for (size_t r = 0; r < batch; r++) orc_fft(mF(data) + r * stride, logn);
+    return 0;
+}
+int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, int deg_D, const long long *L_C, const long long *R_C,
+                    const uint32_t *const *nbr_C, const uint64_t *const *w_C, const long long *L_D, const long long *R_D,
+                    const uint32_t *const *nbr_D, const uint64_t *const *w_D) {
+    for (int d = 0; d < levels; d++) {
+        orc_expander_install(0, d, L_C[d], R_C[d], deg_C, nbr_C[d], w_C[d]);
+        orc_expander_install(1, d, L_D[d], R_D[d], deg_D, nbr_D[d], w_D[d]);
+    }
+    ctx->exp_n = n;
+    std::vector<F> src(n), dst(2 * n);
+    memset(src.data(), 0, n * sizeof(F)); memset(dst.data(), 0, 2 * n * sizeof(F));
+    ctx->exp_cw = orc_encode_monolithic(src.data(), dst.data(), n);
+    return 0;
+}
+long long hb_expander_codeword_len(hb_ctx *ctx) { return ctx->exp_cw; }
+
+int hb_blake3_64(hb_ctx *, const uint8_t *src, uint8_t *dst, size_t count) { for (size_t i = 0; i < count; i++) orc_blake3_hash(src + 64 * i, dst + 32 * i); return 0; }
+int hb_merkle_tree(hb_ctx *, uint8_t *levels, size_t nleaves) {
+    std::vector<uint8_t> lv(nleaves * 32); memcpy(lv.data(), levels, nleaves * 32);
+    orc_create_tree_blake(lv.data(), (int)nleaves, levels);
+    return 0;
+}
+int hb_mt_commit(hb_ctx *, const hb_F *leafs, size_t N, uint8_t *levels) { orc_mt_commit_blake(cF(leafs), (int)N, levels); return 0; }
+int hb_tensorcode(hb_ctx *, const hb_F *msg, size_t n, int trs, int lin, hb_F *tensor) { orc_compute_tensorcode(cF(msg), n, trs, lin, mF(tensor)); return 0; }
+int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K, int trs, int lin, uint8_t *levels_out, hb_F *tensor_out) {
+    ctx->tensor.resize(4 * N); ctx->tN = N; ctx->tK = K; ctx->ttrs = trs;
+    orc_commit_standard(cF(poly), N, K, trs, lin, levels_out, ctx->tensor.data());
+    if (tensor_out) memcpy(tensor_out, ctx->tensor.data(), 4 * N * sizeof(F));
+    ctx->poly.assign(cF(poly), cF(poly) + N); ctx->poly_host = poly;
+    return 0;
+}
+const hb_F *hb_tensor_device(hb_ctx *ctx) { return ctx->tensor.empty() ? nullptr : reinterpret_cast<const hb_F *>(ctx->tensor.data()); }
+int hb_tensor_gather(hb_ctx *ctx, const uint32_t *col, const uint32_t *row, size_t queries, hb_F *reply) {
+    if (ctx->tensor.empty()) FAIL(ctx, "hb_tensor_gather: no committed tensor in this context");
+    size_t B = ctx->tN / ctx->tK, cols = 2 * B / ctx->ttrs;
+    for (size_t q = 0; q < queries; q++)
+        for (int i = 0; i < ctx->tK; i++) mF(reply)[q * ctx->tK + i] = ctx->tensor[(size_t)i * 4 * B + (size_t)row[q] * cols + col[q]];
+    return 0;
+}
+int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, const hb_F *beta, hb_F *agg) {
+    const F *src = poly ? cF(poly) : ctx->poly.data();
+    size_t B = N / K;
+    for (size_t j = 0; j < B; j++) {
+        F a = mk(0);
+        for (int i = 0; i < K; i++) a = fadd(a, fmul(cF(beta)[i], src[(size_t)i * B + j]));
+        mF(agg)[j] = a;
+    }
+    return 0;
+}
+int hb_stream_pc_test(hb_ctx *, hb_F *out, size_t n) { orc_read_stream_pc_test(mF(out), n); return 0; }
+
+int hb_precompute_beta(hb_ctx *, const hb_F *r, int nr, hb_F *out) { orc_precompute_beta(cF(r), nr, mF(out)); return 0; }
+int hb_evaluate_vector(hb_ctx *, const hb_F *v, size_t n, const hb_F *r, hb_F *out) { orc_evaluate_vector(cF(v), n, cF(r), ilog2(n), mF(out)); return 0; }
+int hb_sumcheck2(hb_ctx *, const hb_F *v1, const hb_F *v2, size_t n, const hb_F *prev_r, hb_F *proof, double *ps) {
+    *ps += orc_sumcheck2(cF(v1), cF(v2), n, cF(prev_r), mF(proof)); return 0;
+}
+
+int hb_sumcheck3(hb_ctx *, const hb_F *v1, const hb_F *v2, const hb_F *v3, size_t n, const hb_F *prev_r, hb_F *proof, double *ps) {
+    *ps += orc_sumcheck3(cF(v1), cF(v2), cF(v3), n, cF(prev_r), mF(proof)); return 0;
+}
+int hb_batch_sumcheck3(hb_ctx *, const hb_F *t1, const hb_F *t2, const hb_F *t3, const size_t *sizes, int batches, const hb_F *a, hb_F *proof, double *ps) {
+    *ps += orc_batch_sumcheck3(cF(t1), cF(t2), cF(t3), sizes, batches, cF(a), mF(proof)); return 0;
+}
+/* not emulated (the oracle draws libc randomness inside these; the host mirror draws it outside): GPU-only in the drop-in tests */
+int hb_mul_tree(hb_ctx *ctx, const hb_F *, int, size_t, const hb_F *, const hb_F *, hb_F *, size_t *, int *, double *) { FAIL(ctx, "hb_mul_tree: not emulated"); }
+int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *, size_t, int, size_t, int, int, const hb_F *, const hb_F *, const hb_F *, hb_F *, int *, double *) { FAIL(ctx, "hb_mul_tree_stream: not emulated"); }
+int hb_elastic_begin(hb_ctx *ctx, size_t, int, int) { FAIL(ctx, "hb_elastic_begin: not emulated"); }
+int hb_elastic_push(hb_ctx *ctx, const hb_F *) { FAIL(ctx, "hb_elastic_push: not emulated"); }
+int hb_elastic_finish(hb_ctx *ctx, uint8_t *) { FAIL(ctx, "hb_elastic_finish: not emulated"); }
+
+/* ---- 8f.1 building blocks: plain restatements ------------------------------------------------------------------------------------ */
+int hb_vec_zero(hb_ctx *, hb_F *v, size_t n) { memset(v, 0, n * sizeof(F)); return 0; }
+int hb_rs_encode_rows(hb_ctx *, const hb_F *src, size_t in_len, size_t rows, hb_F *dst, int logn) {
+    size_t len = (size_t)1 << logn;
+    for (size_t r = 0; r < rows; r++) {
+        F *d = mF(dst) + r * len;
+        memset(d, 0, len * sizeof(F)); memcpy(d, cF(src) + r * in_len, in_len * sizeof(F));
+        orc_fft(d, logn);
+    }
+    return 0;
+}
+int hb_matvec_cols(hb_ctx *, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *w, hb_F *out) {
+    for (size_t j = 0; j < cols; j++) {
+        F a = mk(0);
+        for (size_t i = 0; i < rows; i++) a = fadd(a, fmul(cF(w)[i], cF(M)[i * stride + j]));
+        mF(out)[j] = a;
+    }
+    return 0;
+}
+int hb_matvec_rows(hb_ctx *, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *s, hb_F *out) {
+    for (size_t i = 0; i < rows; i++) {
+        F a = mk(0);
+        for (size_t j = 0; j < cols; j++) a = fadd(a, fmul(cF(s)[j], cF(M)[i * stride + j]));
+        mF(out)[i] = a;
+    }
+    return 0;
+}
+int hb_axpy(hb_ctx *, hb_F *y, const hb_F *x, const hb_F *a, size_t n) {
+    for (size_t i = 0; i < n; i++) mF(y)[i] = fadd(mF(y)[i], fmul(*cF(a), cF(x)[i]));
+    return 0;
+}
+int hb_scatter(hb_ctx *, hb_F *out, size_t n, const uint64_t *idx, const hb_F *val, size_t m) {
+    memset(out, 0, n * sizeof(F));
+    for (size_t k = 0; k < m; k++) out[idx[k]] = val[k];
+    return 0;
+}
+int hb_gather_cols(hb_ctx *, const hb_F *M, size_t rows, size_t, size_t stride, const uint64_t *col, size_t m, hb_F *out) {
+    for (size_t q = 0; q < m; q++) for (size_t j = 0; j < rows; j++) out[q * rows + j] = M[j * stride + col[q]];
+    return 0;
+}
+/* utils.cpp:677-755 (forward transform), loop for loop */
+int hb_phi_g_init(hb_ctx *, const hb_F *r, int n, hb_F *out) {
+    size_t N = (size_t)1 << n;
+    std::vector<F> pm(N);
+    F rou; orc_root_of_unity(n, &rou);
+    pm[0] = mk(1);
+    for (size_t i = 1; i < N; i++) pm[i] = fmul(pm[i - 1], rou);
+    F *g = mF(out); const F *rx = cF(r);
+    memset(g, 0, N * sizeof(F));
+    g[0] = mk(1);
+    for (int i = 1; i < n; i++)
+        for (size_t b = 0; b < ((size_t)1 << (i - 1)); b++) {
+            size_t l = b, rr = b ^ ((size_t)1 << (i - 1)); int m = n - i;
+            F t1 = fsub(mk(1), rx[m]), t2 = fmul(rx[m], pm[b << m]);
+            g[rr] = fmul(g[l], fsub(t1, t2));
+            g[l] = fmul(g[l], fadd(t1, t2));
+        }
+    for (size_t b = 0; b < ((size_t)1 << (n - 1)); b++) {
+        F t1 = fsub(mk(1), rx[0]), t2 = fmul(rx[0], pm[b]);
+        g[b] = fmul(g[b], fadd(t1, t2));
+    }
+    return 0;
+}
+/* Virgo.cpp:140-152: the full per-column MT_commit_Blake, root taken */
+int hb_shockwave_leaves(hb_ctx *, const hb_F *enc, int k, size_t cols, uint8_t *leaves) {
+    std::vector<F> buf(k); std::vector<uint8_t> lv((size_t)(2 * (k / 4) - 1) * 32);
+    for (size_t c = 0; c < cols; c++) {
+        for (int j = 0; j < k; j++) buf[j] = cF(enc)[(size_t)j * cols + c];
+        orc_mt_commit_blake(buf.data(), k, lv.data());
+        memcpy(leaves + c * 32, lv.data() + (size_t)(2 * (k / 4) - 2) * 32, 32);
+    }
+    return 0;
+}
+/* Virgo.cpp:104-118, recursively as written */
+static void change_form_rec(F *poly, int logn, int l, size_t pos) {
+    size_t S = (size_t)1 << (logn - l);
+    std::vector<F> buff(S);
+    for (size_t i = 0; i < S / 2; i++) { buff[i] = poly[pos + 2 * i]; buff[i + S / 2] = fsub(poly[pos + 2 * i + 1], poly[pos + 2 * i]); }
+    memcpy(poly + pos, buff.data(), S * sizeof(F));
+    if (l + 1 == logn) return;
+    change_form_rec(poly, logn, l + 1, pos);
+    change_form_rec(poly, logn, l + 1, pos + S / 2);
+}
+int hb_change_form(hb_ctx *, hb_F *poly, int logn) { change_form_rec(mF(poly), logn, 0, 0); return 0; }
+int hb_regroup(hb_ctx *, const hb_F *in, size_t n, int k, hb_F *out) {
+    size_t K = (size_t)1 << k, c = 0;
+    for (size_t j = 0; j < n / K; j++) for (size_t t = 0; t < K; t++) out[c++] = in[j + t * (n / K)];
+    return 0;
+}
+int hb_whir_poly(hb_ctx *, const hb_F *poly, const hb_F *beta, size_t L, hb_F *coeffs3) {
+    F a = mk(0), b = mk(0), c = mk(0); const F *p = cF(poly), *q = cF(beta);
+    for (size_t j = 0; j < L; j++) {
+        F d1 = fsub(p[j + L], p[j]), d2 = fsub(q[j + L], q[j]);
+        a = fadd(a, fmul(d1, d2)); b = fadd(b, fadd(fmul(d1, q[j]), fmul(d2, p[j]))); c = fadd(c, fmul(p[j], q[j]));
+    }
+    mF(coeffs3)[0] = a; mF(coeffs3)[1] = b; mF(coeffs3)[2] = c;
+    return 0;
+}
+int hb_whir_fold(hb_ctx *, hb_F *poly, hb_F *beta, size_t L, const hb_F *a) {
+    F *p = mF(poly), *q = mF(beta);
+    for (size_t j = 0; j < L; j++) { p[j] = fadd(p[j], fmul(*cF(a), fsub(p[j + L], p[j]))); q[j] = fadd(q[j], fmul(*cF(a), fsub(q[j + L], q[j]))); }
+    return 0;
+}
+int hb_whir_zeta(hb_ctx *, const hb_F *poly, hb_F *beta, int v, const hb_F *zetas, int repeats, const hb_F *pows, hb_F *y) {
+    size_t n = (size_t)1 << v; std::vector<F> eq(n);
+    for (int i = 0; i < repeats; i++) {
+        orc_precompute_beta(cF(zetas) + (size_t)i * v, v, eq.data());
+        F acc = mk(0);
+        for (size_t j = 0; j < n; j++) acc = fadd(acc, fmul(eq[j], cF(poly)[j]));
+        mF(y)[i] = acc;
+        for (size_t j = 0; j < n; j++) mF(beta)[j] = fadd(mF(beta)[j], fmul(cF(pows)[i], eq[j]));
+    }
+    return 0;
+}
+
+}  // extern "C"

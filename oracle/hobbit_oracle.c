@@ -146,6 +146,16 @@ void orc_expander_dump(int which, int dep, uint32_t *nbr, uint64_t *w) {
     memcpy(nbr, g->nbr, (size_t)g->L * g->deg * sizeof(uint32_t));
     memcpy(w, g->w, (size_t)g->L * g->deg * sizeof(uint64_t));
 }
+/* install host-generated graphs (used by the CPU emulation of the C ABI, oracle/hb_emul.cpp: the host mirror draws them itself) */
+void orc_expander_install(int which, int dep, long long L, long long R, int deg, const uint32_t *nbr, const uint64_t *w) {
+    orc_graph *g = which ? &gD[dep] : &gC[dep];
+    free(g->nbr); free(g->w);
+    g->L = L; g->R = R; g->deg = deg;
+    g->nbr = (uint32_t *)malloc((size_t)L * deg * sizeof(uint32_t));
+    g->w = (uint64_t *)malloc((size_t)L * deg * sizeof(uint64_t));
+    memcpy(g->nbr, nbr, (size_t)L * deg * sizeof(uint32_t));
+    memcpy(g->w, w, (size_t)L * deg * sizeof(uint64_t));
+}
 static long long encode_rec(const F *src, F *dst, long long n, int dep) {
     if (n <= kDistThreshold) { for (long long i = 0; i < n; i++) dst[i] = src[i]; return n; }
     for (long long i = 0; i < n; i++) dst[i] = src[i];

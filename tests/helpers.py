@@ -325,3 +325,108 @@ def synthetic_chunks(nch, B):
     c = np.zeros((B, 2), dtype=np.uint64)
     c[:, 0] = (np.arange(B, dtype=np.uint64) % 1024) + 1
     return np.concatenate([c] * nch)
+
+
+# ---- the 8f.1 building blocks through the raw C ABI: the same ctypes calls against the CUDA library and against the CPU emulation
+# (oracle/libhb_emul.so, test infrastructure), so each kernel is compared with its plain restatement -----------------------------
+class RawABI:
+    def __init__(self, kind):
+        if kind == "gpu":
+            path = os.path.join(ROOT, "hobbit_b200", "libhobbit_b200.so")
+        elif kind == "emul":
+            path = os.path.join(ROOT, "oracle", "libhb_emul.so")
+            src = [os.path.join(ROOT, "oracle", f) for f in ("hb_emul.cpp", "hobbit_oracle.c")]
+            if not os.path.exists(path) or any(os.path.getmtime(path) < os.path.getmtime(s) for s in src):
+                subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle"], stdout=subprocess.DEVNULL)
+        else:
+            raise ValueError(kind)
+        self.lib = ctypes.CDLL(path)
+        self.lib.hb_last_error.restype = ctypes.c_char_p
+        self.ctx = ctypes.c_void_p()
+        if self.lib.hb_ctx_create(ctypes.byref(self.ctx), 0):
+            raise RuntimeError("hb_ctx_create failed")
+
+    def call(self, name, *args):
+        conv = []
+        for a in args:
+            if isinstance(a, np.ndarray):
+                conv.append(_p(a))
+            elif isinstance(a, int):
+                conv.append(ctypes.c_size_t(a))
+            else:
+                conv.append(a)
+        rc = getattr(self.lib, name)(self.ctx, *conv)
+        if rc:
+            raise RuntimeError("%s: %s" % (name, self.lib.hb_last_error(self.ctx).decode()))
+
+    def rs_encode_rows(self, src, in_len, rows, logn):
+        out = fzeros(rows << logn)
+        self.call("hb_rs_encode_rows", F(src), in_len, rows, out, ctypes.c_int(logn))
+        return out
+
+    def matvec_cols(self, M, rows, cols, w):
+        out = fzeros(cols)
+        self.call("hb_matvec_cols", F(M), rows, cols, cols, F(w), out)
+        return out
+
+    def matvec_rows(self, M, rows, cols, s):
+        out = fzeros(rows)
+        self.call("hb_matvec_rows", F(M), rows, cols, cols, F(s), out)
+        return out
+
+    def axpy(self, y, x, a):
+        y = F(y).copy()
+        self.call("hb_axpy", y, F(x), F(a), len(y))
+        return y
+
+    def scatter(self, n, idx, val):
+        out = fzeros(n)
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        self.call("hb_scatter", out, n, idx, F(val), len(idx))
+        return out
+
+    def gather_cols(self, M, rows, cols, col):
+        col = np.ascontiguousarray(col, dtype=np.uint64)
+        out = fzeros(len(col) * rows)
+        self.call("hb_gather_cols", F(M), rows, cols, cols, col, len(col), out)
+        return out
+
+    def phi_g_init(self, r):
+        r = F(r)
+        out = fzeros(1 << len(r))
+        self.call("hb_phi_g_init", r, ctypes.c_int(len(r)), out)
+        return out
+
+    def shockwave_leaves(self, enc, k, cols):
+        out = np.zeros((cols, 32), dtype=np.uint8)
+        self.call("hb_shockwave_leaves", F(enc), ctypes.c_int(k), cols, out)
+        return out
+
+    def change_form(self, poly):
+        p = F(poly).copy()
+        self.call("hb_change_form", p, ctypes.c_int(int(np.log2(len(p)))))
+        return p
+
+    def regroup(self, v, k):
+        v = F(v)
+        out = fzeros(len(v))
+        self.call("hb_regroup", v, len(v), ctypes.c_int(k), out)
+        return out
+
+    def whir_poly(self, poly, beta, L):
+        out = fzeros(3)
+        self.call("hb_whir_poly", F(poly), F(beta), L, out)
+        return out
+
+    def whir_fold(self, poly, beta, L, a):
+        p, b = F(poly).copy(), F(beta).copy()
+        self.call("hb_whir_fold", p, b, L, F(a))
+        return p, b
+
+    def whir_zeta(self, poly, beta, zetas, pows):
+        poly, b = F(poly), F(beta).copy()
+        v = int(np.log2(len(poly)))
+        pows = F(pows)
+        y = fzeros(len(pows))
+        self.call("hb_whir_zeta", poly, b, ctypes.c_int(v), F(zetas), ctypes.c_int(len(pows)), pows, y)
+        return b, y

@@ -1,0 +1,86 @@
+"""8f.1 building blocks (csrc/open.cu) against their plain CPU restatements (oracle/hb_emul.cpp), same calls through the C ABI.
+Bit-exact: field elements are canonical, digests are bytes."""
+import numpy as np
+import pytest
+
+from helpers import RawABI, rand_field
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def abis():
+    return RawABI("gpu"), RawABI("emul")
+
+
+def test_rs_encode_rows(abis):
+    g, e = abis
+    rng = np.random.default_rng(1)
+    for in_len, rows, logn in [(8, 5, 4), (256, 32, 9), (100, 3, 7), (2048, 4, 12), (8192, 2, 14), (16, 7, 4)]:
+        src = rand_field(rng, in_len * rows)
+        assert np.array_equal(g.rs_encode_rows(src, in_len, rows, logn), e.rs_encode_rows(src, in_len, rows, logn)), (in_len, rows, logn)
+
+
+def test_matvec(abis):
+    g, e = abis
+    rng = np.random.default_rng(2)
+    for rows, cols in [(32, 512), (1, 1000), (2048, 64), (33, 4097), (16, 32), (512, 4096)]:
+        M, w, s = rand_field(rng, rows * cols), rand_field(rng, rows), rand_field(rng, cols)
+        assert np.array_equal(g.matvec_cols(M, rows, cols, w), e.matvec_cols(M, rows, cols, w)), ("cols", rows, cols)
+        assert np.array_equal(g.matvec_rows(M, rows, cols, s), e.matvec_rows(M, rows, cols, s)), ("rows", rows, cols)
+
+
+def test_axpy_scatter_gather(abis):
+    g, e = abis
+    rng = np.random.default_rng(3)
+    y, x, a = rand_field(rng, 5000), rand_field(rng, 5000), rand_field(rng, 1)
+    assert np.array_equal(g.axpy(y, x, a), e.axpy(y, x, a))
+    idx = rng.permutation(1 << 14)[:3000]
+    val = rand_field(rng, 3000)
+    assert np.array_equal(g.scatter(1 << 14, idx, val), e.scatter(1 << 14, idx, val))
+    assert np.array_equal(g.scatter(64, np.zeros(0, dtype=np.uint64), rand_field(rng, 0)), np.zeros((64, 2), dtype=np.uint64))
+    M = rand_field(rng, 32 * 1024)
+    col = rng.integers(0, 1024, size=240)
+    assert np.array_equal(g.gather_cols(M, 32, 1024, col), e.gather_cols(M, 32, 1024, col))
+
+
+def test_phi_g_init(abis):
+    g, e = abis
+    rng = np.random.default_rng(4)
+    for n in [1, 2, 5, 11, 12, 13, 16]:
+        r = rand_field(rng, n)
+        a, b = g.phi_g_init(r), e.phi_g_init(r)
+        assert np.array_equal(a, b), n
+        assert not a[len(a) // 2:].any()
+
+
+def test_shockwave_leaves(abis):
+    g, e = abis
+    rng = np.random.default_rng(5)
+    for k, cols in [(32, 300), (4, 64), (16, 1000)]:
+        enc = rand_field(rng, k * cols)
+        assert np.array_equal(g.shockwave_leaves(enc, k, cols), e.shockwave_leaves(enc, k, cols)), (k, cols)
+
+
+def test_whir_blocks(abis):
+    g, e = abis
+    rng = np.random.default_rng(6)
+    for logn in [1, 4, 10, 15]:
+        p = rand_field(rng, 1 << logn)
+        assert np.array_equal(g.change_form(p), e.change_form(p)), logn
+    for logn in [4, 11]:
+        p = rand_field(rng, 1 << logn)
+        assert np.array_equal(g.regroup(p, 4), e.regroup(p, 4))
+    for L in [1, 8, 1 << 12, 1 << 16]:
+        p, b, a = rand_field(rng, 2 * L), rand_field(rng, 2 * L), rand_field(rng, 1)
+        assert np.array_equal(g.whir_poly(p, b, L), e.whir_poly(p, b, L)), L
+        gp, gb = g.whir_fold(p, b, L, a)
+        ep, eb = e.whir_fold(p, b, L, a)
+        assert np.array_equal(gp, ep) and np.array_equal(gb, eb), L
+    for v, repeats in [(1, 3), (6, 100), (9, 100), (13, 33)]:
+        p, b = rand_field(rng, 1 << v), rand_field(rng, 1 << v)
+        z, pw = rand_field(rng, repeats * v), rand_field(rng, repeats)
+        gb, gy = g.whir_zeta(p, b, z, pw)
+        eb, ey = e.whir_zeta(p, b, z, pw)
+        assert np.array_equal(gy, ey), (v, repeats)
+        assert np.array_equal(gb, eb), (v, repeats)
