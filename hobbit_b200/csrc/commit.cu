@@ -189,11 +189,14 @@ extern "C" size_t hb_profile_report(hb_ctx *ctx, char *buf, size_t cap) {
 
 extern "C" int hb_malloc_device(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMalloc(p, bytes)); return 0; }
 extern "C" int hb_free_device(hb_ctx *ctx, void *p) { HB_CHECK(ctx, cudaFree(p)); return 0; }
+// stream-ordered scratch from the context's pool (release threshold = never): no device synchronisation, microseconds per call
+extern "C" int hb_malloc_stream(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream)); return 0; }
+extern "C" int hb_free_stream(hb_ctx *ctx, void *p) { if (p) HB_CHECK(ctx, cudaFreeAsync(p, ctx->stream)); return 0; }
 extern "C" int hb_malloc_pinned(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMallocHost(p, bytes)); return 0; }
 extern "C" int hb_free_pinned(hb_ctx *ctx, void *p) { HB_CHECK(ctx, cudaFreeHost(p)); return 0; }
 extern "C" int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     HB_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!(is_device_ptr(dst) && is_device_ptr(src))) HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // device-to-device stays stream-ordered
     return 0;
 }
 

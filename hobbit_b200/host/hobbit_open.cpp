@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <unordered_map>
 
@@ -32,19 +33,27 @@ static inline int lg2(size_t x) { int l = 0; while (x >>= 1) l++; return l; }
 static inline const hb_F *abi(const F *p) { return reinterpret_cast<const hb_F *>(p); }
 static inline hb_F *abi(F *p) { return reinterpret_cast<hb_F *>(p); }
 
+// HOBBIT_TRACE=1: wall time of each phase of the opening on stderr (the C ABI calls are synchronous, so wall time is GPU + host time)
+struct Trace {
+    const char *what; double t0; static bool on() { static int v = -1; if (v < 0) v = getenv("HOBBIT_TRACE") ? 1 : 0; return v; }
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    explicit Trace(const char *w) : what(w), t0(on() ? now() : 0) {}
+    ~Trace() { if (on()) fprintf(stderr, "[hobbit trace] %-28s %8.3f ms\n", what, (now() - t0) * 1e3); }
+};
+
 // ---- a table resident in HBM ---------------------------------------------------------------------------------------------------
 struct DV {
     F *p = nullptr; size_t n = 0;
     DV() {}
     explicit DV(size_t n_, bool zero = false) : n(n_) {
-        void *q = nullptr; CK(hb_malloc_device(backend(), &q, (n ? n : 1) * sizeof(F))); p = (F *)q;
+        void *q = nullptr; CK(hb_malloc_stream(backend(), &q, (n ? n : 1) * sizeof(F))); p = (F *)q;
         if (zero && n) CK(hb_vec_zero(backend(), abi(p), n));
     }
     DV(const DV &) = delete; DV &operator=(const DV &) = delete;
     DV(DV &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DV &operator=(DV &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~DV() { release(); }
-    void release() { if (p) hb_free_device(backend(), p); p = nullptr; n = 0; }
+    void release() { if (p) hb_free_stream(backend(), p); p = nullptr; n = 0; }
     void upload(const F *src, size_t cnt, size_t at = 0) { if (cnt) CK(hb_memcpy(backend(), p + at, src, cnt * sizeof(F))); }
     std::vector<F> download(size_t cnt, size_t at = 0) const { std::vector<F> v(cnt); if (cnt) CK(hb_memcpy(backend(), v.data(), p + at, cnt * sizeof(F))); return v; }
     static DV from(const std::vector<F> &v) { DV d(v.size()); d.upload(v.data(), v.size()); return d; }
@@ -99,9 +108,9 @@ static std::vector<std::vector<_hash>> levels_host(const uint8_t *dev, size_t nl
 
 // ---- shockwave (Virgo.cpp:120-157, 435-517) ---------------------------------------------------------------------------------------
 shockwave_data::~shockwave_data() {
-    if (matrix) hb_free_device(backend(), matrix);
-    if (encoded_matrix) hb_free_device(backend(), encoded_matrix);
-    if (MT) hb_free_device(backend(), MT);
+    if (matrix) hb_free_stream(backend(), matrix);
+    if (encoded_matrix) hb_free_stream(backend(), encoded_matrix);
+    if (MT) hb_free_stream(backend(), MT);
 }
 std::vector<std::vector<_hash>> shockwave_data::MT_host() const { return levels_host(MT, 2 * N / k); }
 std::vector<F> shockwave_data::encoded_host() const { std::vector<F> v(2 * N); CK(hb_memcpy(backend(), v.data(), encoded_matrix, 2 * N * sizeof(F))); return v; }
@@ -112,9 +121,9 @@ static shockwave_data *shockwave_commit_ptr(const F *poly, size_t N, int k) {
     d->k = k; d->N = N;
     const size_t cols = N / k;
     void *q;
-    CK(hb_malloc_device(backend(), &q, N * sizeof(F))); d->matrix = (F *)q;
-    CK(hb_malloc_device(backend(), &q, 2 * N * sizeof(F))); d->encoded_matrix = (F *)q;
-    CK(hb_malloc_device(backend(), &q, (4 * cols - 1) * 32)); d->MT = (uint8_t *)q;
+    CK(hb_malloc_stream(backend(), &q, N * sizeof(F))); d->matrix = (F *)q;
+    CK(hb_malloc_stream(backend(), &q, 2 * N * sizeof(F))); d->encoded_matrix = (F *)q;
+    CK(hb_malloc_stream(backend(), &q, (4 * cols - 1) * 32)); d->MT = (uint8_t *)q;
     dcopy(d->matrix, poly, N);
     CK(hb_rs_encode_rows(backend(), abi(d->matrix), cols, (size_t)k, abi(d->encoded_matrix), lg2(2 * cols)));   // zero rows stay zero
     CK(hb_shockwave_leaves(backend(), abi(d->encoded_matrix), k, 2 * cols, d->MT));
@@ -125,10 +134,10 @@ shockwave_data *shockwave_commit(std::vector<F> &poly, int k) { return shockwave
 
 // ---- WHIR (Virgo.cpp:160-178, 519-686) -----------------------------------------------------------------------------------------------
 Whir_data::~Whir_data() {
-    for (F *q : {poly, poly_com}) if (q) hb_free_device(backend(), q);
-    if (MT) hb_free_device(backend(), MT);
-    for (F *q : FRI_poly) if (q) hb_free_device(backend(), q);
-    for (uint8_t *q : FRI_MT) if (q) hb_free_device(backend(), q);
+    for (F *q : {poly, poly_com}) if (q) hb_free_stream(backend(), q);
+    if (MT) hb_free_stream(backend(), MT);
+    for (F *q : FRI_poly) if (q) hb_free_stream(backend(), q);
+    for (uint8_t *q : FRI_MT) if (q) hb_free_stream(backend(), q);
 }
 std::vector<std::vector<_hash>> Whir_data::MT_host() const { return levels_host(MT, 2 * N / 4); }
 std::vector<std::vector<_hash>> Whir_data::FRI_MT_host(int i) const { return levels_host(FRI_MT[i], FRI_size[i] / 4); }
@@ -141,18 +150,18 @@ static void whir_encode(const F *src, size_t n, size_t ext, bool keep_regrouped,
     dcopy(cf.p, src, n);
     CK(hb_change_form(backend(), abi(cf.p), lg2(n)));
     void *q;
-    CK(hb_malloc_device(backend(), &q, ext * sizeof(F))); F *code = (F *)q;
+    CK(hb_malloc_stream(backend(), &q, ext * sizeof(F))); F *code = (F *)q;
     CK(hb_rs_encode_rows(backend(), abi(cf.p), n, 1, abi(code), lg2(ext)));
     DV re(ext);
     CK(hb_regroup(backend(), abi(code), ext, 4, abi(re.p)));
-    CK(hb_malloc_device(backend(), &q, (2 * (ext / 4) - 1) * 32)); uint8_t *mt = (uint8_t *)q;
+    CK(hb_malloc_stream(backend(), &q, (2 * (ext / 4) - 1) * 32)); uint8_t *mt = (uint8_t *)q;
     CK(hb_mt_commit(backend(), abi(re.p), ext, mt));
     if (keep_regrouped) { dcopy(code, re.p, ext); }          // whir_commit overwrites poly_com with the regrouped order (:173-175)
     *code_out = code; *mt_out = mt;
 }
 static void whir_commit_ptr(const F *poly, size_t N, Whir_data &data) {
     data.k = 4; data.N = N;
-    void *q; CK(hb_malloc_device(backend(), &q, N * sizeof(F))); data.poly = (F *)q;
+    void *q; CK(hb_malloc_stream(backend(), &q, N * sizeof(F))); data.poly = (F *)q;
     dcopy(data.poly, poly, N);
     whir_encode(data.poly, N, 2 * N, true, &data.poly_com, &data.MT);
 }
@@ -187,6 +196,7 @@ static void whir_verify_iteration(Whir_data &data, const std::vector<int> &r, in
 }
 
 void _whir_prove(Whir_data &data, std::vector<F> x, double &vt, double &ps) {
+    Trace tw("      _whir_prove");
     (void)vt;
     const int k = 4;
     const size_t N = data.N;
@@ -327,6 +337,7 @@ proof prove_linear_code(std::vector<F> &codeword, int n, double &vt, double &ps)
 
 // ---- shockwave_prove (Virgo.cpp:435-517) ---------------------------------------------------------------------------------------------
 void shockwave_prove(shockwave_data *data, std::vector<F> x, double &vt, double &ps) {
+    Trace tsw("    shockwave_prove");
     const int k = data->k, query_points = 240;
     const size_t n = data->N / k;
     std::vector<F> r1;
@@ -365,13 +376,15 @@ static void recursive_prover_Spielman_dev(const F *input, const F *T, size_t trs
     DV s_dev = DV::from(s);
     std::vector<F> aggr_c(rows2);
     CK(hb_matvec_rows(backend(), abi(T), rows2, cols, cols, abi(s_dev.p), abi(aggr_c.data())));
-    proof P1 = prove_linear_code(aggr_c, (int)trs, vt, ps);
+    proof P1;
+    { Trace t("    prove_linear_code"); P1 = prove_linear_code(aggr_c, (int)trs, vt, ps); }
     DV evals(cols);
     { DV b1 = eq_dev(P1.randomness[0]); CK(hb_matvec_cols(backend(), abi(T), rows2, cols, cols, abi(b1.p), abi(evals.p))); }
     proof P2 = sc2(s_dev.p, evals.p, cols, F(021), ps);
     if (P2.q_poly[0].eval(F(0)) + P2.q_poly[0].eval(F(1)) != P1.vr[1]) { printf("Error recursion 1\n"); exit(-1); }
     proof P3;
     {
+        Trace t("    P3 (query sumcheck)");
         std::vector<F> vals(I.size());
         F s2 = F(random());
         vals[0] = s2;
@@ -384,6 +397,7 @@ static void recursive_prover_Spielman_dev(const F *input, const F *T, size_t trs
     r.insert(r.end(), P1.randomness[0].begin(), P1.randomness[0].end());
     proof P4;
     {
+        Trace t("    P4 (eq sumcheck)");
         DV b1 = eq_dev(r), b2 = eq_dev(P3.randomness[0]);
         CK(hb_axpy(backend(), abi(b1.p), abi(b2.p), abi(&a), total));
         b2.release();
@@ -462,19 +476,25 @@ void recursive_prover_RS(std::vector<F> &aggregated_vector, std::vector<std::vec
 void open_standard(std::vector<F> &poly, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT,
                    std::vector<std::vector<std::vector<F>>> &_tensor, int K, double &vt, double &ps) {
     (void)_tensor;                                               // the encoded tensor is resident in HBM since commit_standard
-    open_front o = open_standard_front(poly, x, Commitment_MT, K);
+    Trace tall("open_standard total");
+    open_front o;
+    { Trace t("  front (aggregate, queries)"); o = open_standard_front(poly, x, Commitment_MT, K); }
     const size_t B = BUFFER_SPACE, trs = (size_t)tensor_row_size, cols = 2 * B / trs;
     // _aggregate's commitments (Our_PC.cpp:258-289); none of this draws randomness, so doing it after the query draw keeps the RNG order
     DV agg = DV::from(o.aggr_vector);
-    C_f = shockwave_commit_ptr(agg.p, B, 32);
     DV T;
-    if (linear_time) {
-        T = DV(4 * B);
-        CK(hb_tensorcode(backend(), abi(agg.p), B, (int)trs, 1, abi(T.p)));
-        C_c = shockwave_commit_ptr(T.p + 2 * B, 2 * B, 32);      // the upper tensor_row_size rows
+    {
+        Trace t("  shockwave commits");
+        C_f = shockwave_commit_ptr(agg.p, B, 32);
+        if (linear_time) {
+            T = DV(4 * B);
+            CK(hb_tensorcode(backend(), abi(agg.p), B, (int)trs, 1, abi(T.p)));
+            C_c = shockwave_commit_ptr(T.p + 2 * B, 2 * B, 32);      // the upper tensor_row_size rows
+        }
     }
     ps += o.ps;
     printf(">> %lf Kb\n", o.ps);
+    Trace trec("  recursion");
     if (!linear_time) recursive_prover_RS_dev(agg.p, B, o.I, vt, ps);
     else {
         std::vector<size_t> I_v(o.I.size());

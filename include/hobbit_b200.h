@@ -44,9 +44,12 @@ int  hb_profile_enable(hb_ctx *ctx, int on);
 size_t hb_profile_report(hb_ctx *ctx, char *buf, size_t cap);
 int  hb_malloc_device(hb_ctx *ctx, void **p, size_t bytes);
 int  hb_free_device(hb_ctx *ctx, void *p);
+/* stream-ordered scratch for tables that live between calls of one proof (the context's pool; valid for use by later hb_* calls) */
+int  hb_malloc_stream(hb_ctx *ctx, void **p, size_t bytes);
+int  hb_free_stream(hb_ctx *ctx, void *p);
 int  hb_malloc_pinned(hb_ctx *ctx, void **p, size_t bytes);
 int  hb_free_pinned(hb_ctx *ctx, void *p);
-int  hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes);   /* any direction, synchronous */
+int  hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes);   /* any direction; synchronous unless device-to-device */
 
 /* ---- F1/F2: field (reference fieldElement.cpp:34-104, 206-209) ------------------------------------------- */
 /* op: 0 a+b, 1 a-b, 2 a*b, 3 -a, 4 a^-1 (b ignored for 3,4) */

@@ -41,6 +41,8 @@ int hb_sync(hb_ctx *) { return 0; }
 uint64_t hb_launch_count(hb_ctx *) { return 0; }
 int hb_malloc_device(hb_ctx *, void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : 1; }
 int hb_free_device(hb_ctx *, void *p) { free(p); return 0; }
+int hb_malloc_stream(hb_ctx *, void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : 1; }
+int hb_free_stream(hb_ctx *, void *p) { free(p); return 0; }
 int hb_memcpy(hb_ctx *, void *dst, const void *src, size_t bytes) { memmove(dst, src, bytes); return 0; }
 
 void hb_root_of_unity(int logn, hb_F *out) { orc_root_of_unity(logn, mF(out)); }
