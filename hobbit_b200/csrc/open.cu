@@ -76,6 +76,29 @@ gather_cols_kernel(const F *__restrict__ M, size_t rows, size_t stride, const un
     out[t] = M[j * stride + col[q]];
 }
 
+// out[j*m + q] = M[j*stride + col[q]]: the selected columns as a rows x m matrix (message q = column q, the layout hb_encode_batch takes)
+__global__ void __launch_bounds__(256)
+select_cols_kernel(const F *__restrict__ M, size_t rows, size_t stride, const unsigned long long *__restrict__ col, size_t m, F *__restrict__ out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * rows) return;
+    size_t j = t / m, q = t - j * m;
+    out[t] = M[j * stride + col[q]];
+}
+// out (cols x rows) = in (rows x cols)^T, 32 x 32 tiles through shared memory (both sides coalesced)
+__global__ void __launch_bounds__(256) transpose_kernel(const F *__restrict__ in, size_t rows, size_t cols, F *__restrict__ out) {
+    __shared__ F tile[32][33];
+    const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (unsigned k = ty; k < 32; k += 8) if (r0 + k < rows && c0 + tx < cols) tile[k][tx] = in[(r0 + k) * cols + c0 + tx];
+    __syncthreads();
+    for (unsigned k = ty; k < 32; k += 8) if (c0 + k < cols && r0 + tx < rows) out[(c0 + k) * rows + r0 + tx] = tile[tx][k];
+}
+__global__ void __launch_bounds__(256) vec_nonzero_kernel(const F *__restrict__ v, size_t n, int *__restrict__ flag) {
+    bool nz = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) nz |= !fzero(v[i]);
+    if (__syncthreads_or(nz) && threadIdx.x == 0) *flag = 1;
+}
+
 // ---- phiGInit (utils.cpp:694-755, forward transform): the multilinear extension of the NTT matrix row selected by r ---------------
 // phi_g[0] = 1; level i = 1..n-1 doubles the filled prefix: with m = n-i, t1 = 1 - r[m], t2 = r[m] * w^(b << m):
 //   phi_g[b + 2^(i-1)] = phi_g[b] (t1 - t2),  phi_g[b] = phi_g[b] (t1 + t2),   b < 2^(i-1);
@@ -312,6 +335,47 @@ extern "C" int hb_gather_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     HB_LAUNCH(ctx, gather_cols_kernel, (unsigned)((m * rows + 255) / 256), 256, 0, sm.as<F>(), rows, stride, sc.as<unsigned long long>(), m, so.as<F>());
     HB_TRY(so.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_select_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out) {
+    if (m == 0 || rows == 0) return 0;
+    Staged sm(ctx), sc(ctx), so(ctx);
+    HB_TRY(sm.in(M, ((rows - 1) * stride + cols) * sizeof(F)));
+    HB_TRY(sc.in(col, m * sizeof(uint64_t)));
+    HB_TRY(so.outbuf(out, m * rows * sizeof(F)));
+    HB_LAUNCH(ctx, select_cols_kernel, (unsigned)((m * rows + 255) / 256), 256, 0, sm.as<F>(), rows, stride, sc.as<unsigned long long>(), m, so.as<F>());
+    HB_TRY(so.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_transpose(hb_ctx *ctx, const hb_F *in, size_t rows, size_t cols, hb_F *out) {
+    if (rows == 0 || cols == 0) return 0;
+    Staged si(ctx), so(ctx);
+    HB_TRY(si.in(in, rows * cols * sizeof(F)));
+    HB_TRY(so.outbuf(out, rows * cols * sizeof(F)));
+    HB_LAUNCH(ctx, transpose_kernel, dim3((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), 256, 0, si.as<F>(), rows, cols, so.as<F>());
+    HB_TRY(so.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_any_nonzero(hb_ctx *ctx, const hb_F *v, size_t n, int *out) {
+    *out = 0;
+    if (n == 0) return 0;
+    if (!is_device_ptr(v)) {                       // host chunk: a linear scan on the host beats a round trip
+        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint64_t *w = reinterpret_cast<const uint64_t *>(v);
+        for (size_t i = 0; i < 2 * n; i++) if (w[i]) { *out = 1; break; }
+        return 0;
+    }
+    int *flag; HB_CHECK(ctx, cudaMallocAsync(&flag, sizeof(int), ctx->stream));
+    HB_CHECK(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    HB_LAUNCH(ctx, vec_nonzero_kernel, grid_1d(ctx, n), 256, 0, reinterpret_cast<const F *>(v), n, flag);
+    HB_CHECK(ctx, cudaMemcpyAsync(out, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(flag, ctx->stream);
     return 0;
 }
 

@@ -308,6 +308,12 @@ void read_stream(stream_descriptor &fd, std::vector<F> &v, int size) {          
     for (int i = 0; i < size; i++) v[i] = F((i % 1024) + 1);
 }
 
+const F *stream_chunk(stream_descriptor &fd, size_t, size_t B, std::vector<F> &buff) {
+    buff.resize(B);
+    read_stream(fd, buff, (int)B);
+    return buff.data();
+}
+
 std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, int vectors, int size, F previous_r, int distance,
                                                         std::vector<F> prev_x, bool naive, double &, double &ps) {
     if (!prev_x.empty()) { printf("hobbit_b200: prove_multiplication_tree_stream_shallow with prev_x is not wired yet\n"); exit(-1); }

@@ -145,6 +145,10 @@ void open_standard(std::vector<F> &poly, std::vector<F> x, std::vector<std::vect
 void init_commitment(bool mod);
 void read_stream_PC(stream_descriptor &fd, F *v, int size);
 void commit(stream_descriptor fd, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes);
+extern std::vector<std::vector<size_t>> I;                      // Elastic_PC.cpp:314
+void open(stream_descriptor fd, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, double &vt, double &ps);
+// chunk i (BUFFER_SPACE elements) of a stream as read_stream emits it: a pointer into HBM for resident circuit streams, else `buff`
+const F *stream_chunk(stream_descriptor &fd, size_t i, size_t B, std::vector<F> &buff);
 
 // sumcheck.h
 proof generate_2product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, F previous_r, double &vt, double &ps);

@@ -509,4 +509,120 @@ void open_standard(std::vector<F> &poly, std::vector<F> x, std::vector<std::vect
     ps += MT_ps;
 }
 
+// ---- Elastic_PC open (Elastic_PC.cpp:316-429, 487-533, 625-726; recursive_prover_Spielman_stream PC_utils.cpp:168-287) ----------------
+std::vector<std::vector<size_t>> I;            // Elastic_PC.cpp:314: the queries are a global, drawn before the aggregate pass
+// remaining_columns (:376-391 and PC_utils.cpp:188-203): queried columns with at least one query in a parity row
+static std::vector<size_t> remaining_columns_of(const std::vector<std::vector<size_t>> &Iq, size_t trs) {
+    std::map<size_t, bool> parity;
+    for (auto &q : Iq) { bool &p = parity[q[0]]; p = p || q[1] >= trs; }
+    std::vector<size_t> rc;
+    for (auto &kv : parity) if (kv.second) rc.push_back(kv.first);           // std::map iterates in sorted column order
+    return rc;
+}
+// input: B message elements; M: tensor_row_size x cols RS rows; codewords: aux_commit as an (nrc x 2trs) row-major table, padded to a
+// power of two (`cw_pad` elements).  All on the device.
+static void recursive_prover_Spielman_stream_dev(const F *input, const F *M, size_t trs, size_t cols, const F *codewords, size_t nrc, size_t cw_pad,
+                                                 const std::vector<std::vector<size_t>> &Iq, double &vt, double &ps) {
+    std::vector<size_t> remaining = remaining_columns_of(Iq, trs);
+    std::vector<F> s(nrc);
+    s[0] = F(random());
+    for (size_t i = 1; i < nrc; i++) s[i] = s[i - 1] * s[0];
+    std::vector<F> aggr_c(2 * trs);
+    { DV sd = DV::from(s); CK(hb_matvec_cols(backend(), abi(codewords), nrc, 2 * trs, 2 * trs, abi(sd.p), abi(aggr_c.data()))); }
+    proof P1 = prove_linear_code(aggr_c, (int)trs, vt, ps);
+    DV evals(cols);
+    { DV b1 = eq_dev(P1.randomness[0]); CK(hb_matvec_cols(backend(), abi(M), trs, cols, cols, abi(b1.p), abi(evals.p))); }   // rows j < trs only (:230-234)
+    proof P2;
+    {
+        std::vector<F> vals(remaining.size());
+        for (size_t j = 0; j < remaining.size(); j++) vals[j] = s[j];
+        DV sM = sparse_dev(cols, remaining, vals);
+        P2 = sc2(sM.p, evals.p, cols, F(021), ps);
+    }
+    proof P3;
+    {
+        std::vector<size_t> idx(Iq.size()); std::vector<F> vals(Iq.size());
+        F s2 = F(random());
+        for (size_t i = 0; i < Iq.size(); i++) { idx[i] = i; vals[i] = s2; s2 = s2 * s2; }          // buff2[i] = s2; s2 = s2*s2 (:247-250)
+        if (cw_pad < Iq.size()) { printf("hobbit_b200: aux commitment smaller than the query count (the reference writes out of bounds here)\n"); exit(-1); }
+        DV buff2 = sparse_dev(cw_pad, idx, vals);
+        P3 = sc2(codewords, buff2.p, cw_pad, F(121), ps);
+    }
+    shockwave_prove(C_c, P3.randomness[0], vt, ps); C_c = nullptr;
+    std::vector<F> r = P1.randomness[0];
+    r.insert(r.end(), P2.randomness[0].begin(), P2.randomness[0].end());
+    F y1;
+    CK(hb_evaluate_vector(backend(), abi(M), trs * cols, abi(r.data()), abi(&y1)));
+    proof P5 = prove_fft_matrix_ptr(input, trs, cols / 2, r, y1, ps);
+    P5.randomness[0].pop_back();
+    shockwave_prove(C_f, P5.randomness[0], vt, ps); C_f = nullptr;
+}
+
+void open(stream_descriptor fd, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, double &vt, double &ps) {
+    Trace tall("open (Elastic_PC) total");
+    const size_t B = BUFFER_SPACE, trs = (size_t)tensor_row_size, cols = 2 * B / trs, K = fd.size / B;
+    const int queries = linear_time ? 5900 : 700;                               // :626-629
+    std::vector<F> x1;
+    for (int i = 0; i < lg2(K); i++) x1.push_back(x[i]);
+    std::vector<F> beta; precompute_beta(x1, beta);
+    generate_randomness(1);                                                      // r_v[0] (:643); its powers are never used
+    // :649-655 verbatim: `I` is a global that is resized and push_back'ed, never cleared — on a second open in the same process the two
+    // rand() draws are appended BEHIND the previous call's pair and I[i][0], I[i][1] keep their old values (prove_circuit opens twice).
+    I.resize(queries);
+    std::vector<uint32_t> col(queries), row(queries);
+    for (int i = 0; i < queries; i++) {
+        I[i].push_back(rand() % (2 * B / trs)); I[i].push_back(rand() % (2 * trs));
+        col[i] = (uint32_t)I[i][0]; row[i] = (uint32_t)I[i][1];
+    }
+    // aggregate (:316-333) and compute_aggregation_reply (:487-533) read the stream twice in the reference; here ONE pass feeds both
+    DV agg(B), reply((size_t)queries * K);
+    size_t nonzero_chunks = 0;
+    {
+        Trace t("  stream pass (aggregate + replies)");
+        CK(hb_elastic_open_begin(backend(), B, (int)trs, linear_time ? 1 : 0, col.data(), row.data(), (size_t)queries, K));
+        std::vector<F> buff;
+        reset_stream(fd);
+        for (size_t i = 0; i < K; i++) {
+            const F *chunk = stream_chunk(fd, i, B, buff);
+            int nz = 0; CK(hb_any_nonzero(backend(), abi(chunk), B, &nz));
+            nonzero_chunks += nz ? 1 : 0;
+            CK(hb_elastic_open_push(backend(), abi(chunk), abi(&beta[i])));
+        }
+        CK(hb_elastic_open_finish(backend(), abi(agg.p), abi(reply.p)));
+    }
+    DV Mrs, aux; size_t nrc = 0, cw_pad = 0;
+    {
+        Trace t("  shockwave commits");
+        C_f = shockwave_commit_ptr(agg.p, B, 32);
+        if (linear_time) {                                                      // :338-414
+            std::vector<size_t> remaining = remaining_columns_of(I, trs);
+            nrc = remaining.size();
+            Mrs = DV(trs * cols);
+            CK(hb_rs_encode_rows(backend(), abi(agg.p), cols / 2, trs, abi(Mrs.p), lg2(cols)));
+            std::vector<uint64_t> rc64(remaining.begin(), remaining.end());
+            DV sel(trs * nrc), enc(2 * trs * nrc);
+            CK(hb_select_cols(backend(), abi(Mrs.p), trs, cols, cols, rc64.data(), nrc, abi(sel.p)));
+            CK(hb_encode_batch(backend(), abi(sel.p), abi(enc.p), (long long)trs, nrc));
+            cw_pad = next_pow2(nrc * 2 * trs);
+            aux = DV(cw_pad, true);
+            CK(hb_transpose(backend(), abi(enc.p), 2 * trs, nrc, abi(aux.p)));          // aux_commit[i][j] = encode(column i)[j]
+            printf("%d\n", (int)(nrc * 2 * trs));
+            C_c = shockwave_commit_ptr(aux.p, cw_pad, 32);
+        }
+    }
+    std::vector<bool> visited(Commitment_MT[0].size() * 2, false);
+    double MT_ps = 0.0;
+    for (size_t i = 0; i < I.size(); i++) mt_ps((int)Commitment_MT.size(), Commitment_MT[0].size(), (I[i][1] / 4) * cols + I[i][0], visited, MT_ps);
+    for (auto &lv : Commitment_MT) { lv.clear(); std::vector<_hash>(lv).swap(lv); }                 // :693-698: the caller's tree is freed
+    Commitment_MT.clear();
+    ps += (double)((size_t)queries * nonzero_chunks * sizeof(F)) / 1024.0;          // reply[k] has one entry per non-zero chunk (:509-518)
+    {
+        Trace t("  recursion");
+        if (!linear_time) recursive_prover_RS_dev(agg.p, B, I, vt, ps);
+        else recursive_prover_Spielman_stream_dev(agg.p, Mrs.p, trs, cols, aux.p, nrc, cw_pad, I, vt, ps);
+    }
+    ps += MT_ps;
+    printf("PC : ps = %lf, vt = %lf\n", ps, vt);
+}
+
 }  // namespace hobbit

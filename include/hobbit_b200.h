@@ -207,6 +207,11 @@ int hb_axpy(hb_ctx *ctx, hb_F *y, const hb_F *x, const hb_F *a, size_t n);      
 int hb_scatter(hb_ctx *ctx, hb_F *out, size_t n, const uint64_t *idx, const hb_F *val, size_t m);
 /* out[q*rows + j] = M[j*stride + col[q]]  — column replies (Virgo.cpp:468-472) */
 int hb_gather_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out);
+/* out[j*m + q] = M[j*stride + col[q]] (rows x m: message q = column q, the layout hb_encode_batch takes); out (cols x rows) = in^T;
+ * *out = 1 iff some element of v is non-zero (Elastic_PC's all-zero chunk test, Elastic_PC.cpp:206-213, 509-516) */
+int hb_select_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out);
+int hb_transpose(hb_ctx *ctx, const hb_F *in, size_t rows, size_t cols, hb_F *out);
+int hb_any_nonzero(hb_ctx *ctx, const hb_F *v, size_t n, int *out);
 /* phiGInit(phi_g, r, F(1), n, false) (utils.cpp:694-755): out has 2^n entries, the upper half stays zero like the reference's */
 int hb_phi_g_init(hb_ctx *ctx, const hb_F *r, int n, hb_F *out);
 /* shockwave_commit's leaves: leaves[c] = root of MT_commit_Blake over the k cells enc[0..k)[c] of column c (Virgo.cpp:140-152) */

@@ -21,6 +21,7 @@ struct hb_ctx {
     std::vector<F> tensor; size_t tN = 0; int tK = 0, ttrs = 0;
     std::vector<F> poly; const void *poly_host = nullptr;
     long long exp_n = 0, exp_cw = 0;
+    size_t eB = 0; int etrs = 0, elin = 0; std::vector<F> estream, ebeta; std::vector<uint32_t> ecol, erow;
 };
 static const uint64_t P = 2305843009213693951ULL;
 static inline F fadd(F a, F b) { F c; orc_field_binop(0, &a, &b, &c, 1); return c; }
@@ -118,9 +119,25 @@ int hb_batch_sumcheck3(hb_ctx *, const hb_F *t1, const hb_F *t2, const hb_F *t3,
 /* not emulated (the oracle draws libc randomness inside these; the host mirror draws it outside): GPU-only in the drop-in tests */
 int hb_mul_tree(hb_ctx *ctx, const hb_F *, int, size_t, const hb_F *, const hb_F *, hb_F *, size_t *, int *, double *) { FAIL(ctx, "hb_mul_tree: not emulated"); }
 int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *, size_t, int, size_t, int, int, const hb_F *, const hb_F *, const hb_F *, hb_F *, int *, double *) { FAIL(ctx, "hb_mul_tree_stream: not emulated"); }
-int hb_elastic_begin(hb_ctx *ctx, size_t, int, int) { FAIL(ctx, "hb_elastic_begin: not emulated"); }
-int hb_elastic_push(hb_ctx *ctx, const hb_F *) { FAIL(ctx, "hb_elastic_push: not emulated"); }
-int hb_elastic_finish(hb_ctx *ctx, uint8_t *) { FAIL(ctx, "hb_elastic_finish: not emulated"); }
+/* Elastic_PC commit / open front: chunks are buffered and handed to the oracle's restatement at finish */
+int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int lin) { ctx->eB = B; ctx->etrs = trs; ctx->elin = lin; ctx->estream.clear(); return 0; }
+int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) { ctx->estream.insert(ctx->estream.end(), cF(chunk), cF(chunk) + ctx->eB); return 0; }
+int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out) {
+    orc_elastic_commit_stream(ctx->estream.data(), ctx->estream.size(), ctx->eB, ctx->etrs, ctx->elin, levels_out);
+    ctx->estream.clear(); return 0;
+}
+int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int lin, const uint32_t *col, const uint32_t *row, size_t queries, size_t nchunks) {
+    ctx->eB = B; ctx->etrs = trs; ctx->elin = lin; ctx->estream.clear(); ctx->ebeta.clear();
+    ctx->ecol.assign(col, col + queries); ctx->erow.assign(row, row + queries); (void)nchunks; return 0;
+}
+int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *beta_i) {
+    ctx->estream.insert(ctx->estream.end(), cF(chunk), cF(chunk) + ctx->eB); ctx->ebeta.push_back(*cF(beta_i)); return 0;
+}
+int hb_elastic_open_finish(hb_ctx *ctx, hb_F *agg_out, hb_F *reply_out) {
+    orc_elastic_open_front(ctx->estream.data(), ctx->ebeta.size(), ctx->eB, ctx->etrs, ctx->elin, ctx->ebeta.data(), ctx->ecol.data(),
+                           ctx->erow.data(), ctx->ecol.size(), mF(agg_out), mF(reply_out));
+    ctx->estream.clear(); return 0;
+}
 
 /* ---- 8f.1 building blocks: plain restatements ------------------------------------------------------------------------------------ */
 int hb_vec_zero(hb_ctx *, hb_F *v, size_t n) { memset(v, 0, n * sizeof(F)); return 0; }
@@ -160,6 +177,29 @@ int hb_scatter(hb_ctx *, hb_F *out, size_t n, const uint64_t *idx, const hb_F *v
 }
 int hb_gather_cols(hb_ctx *, const hb_F *M, size_t rows, size_t, size_t stride, const uint64_t *col, size_t m, hb_F *out) {
     for (size_t q = 0; q < m; q++) for (size_t j = 0; j < rows; j++) out[q * rows + j] = M[j * stride + col[q]];
+    return 0;
+}
+int hb_select_cols(hb_ctx *, const hb_F *M, size_t rows, size_t, size_t stride, const uint64_t *col, size_t m, hb_F *out) {
+    for (size_t j = 0; j < rows; j++) for (size_t q = 0; q < m; q++) out[j * m + q] = M[j * stride + col[q]];
+    return 0;
+}
+int hb_transpose(hb_ctx *, const hb_F *in, size_t rows, size_t cols, hb_F *out) {
+    for (size_t i = 0; i < rows; i++) for (size_t j = 0; j < cols; j++) out[j * rows + i] = in[i * cols + j];
+    return 0;
+}
+int hb_any_nonzero(hb_ctx *, const hb_F *v, size_t n, int *out) {
+    *out = 0;
+    for (size_t i = 0; i < n; i++) if (v[i].real | v[i].img) { *out = 1; break; }
+    return 0;
+}
+int hb_encode_batch(hb_ctx *, const hb_F *src, hb_F *dst, long long n, size_t ncols) {
+    std::vector<F> m(n), cw(2 * n);
+    for (size_t c = 0; c < ncols; c++) {
+        for (long long j = 0; j < n; j++) m[j] = cF(src)[(size_t)j * ncols + c];
+        memset(cw.data(), 0, 2 * n * sizeof(F));
+        orc_encode_monolithic(m.data(), cw.data(), n);
+        for (long long j = 0; j < 2 * n; j++) mF(dst)[(size_t)j * ncols + c] = cw[j];
+    }
     return 0;
 }
 /* utils.cpp:677-755 (forward transform), loop for loop */

@@ -298,13 +298,16 @@ void orc_read_stream_pc_test(F *v, size_t n) {
  * Elastic_PC.cpp:174-285 on stream "test".  Chunks i%4 in {0,1,2} are parked;
  * chunk i%4==3 triggers h[pos] = H2(c0[pos],c1[pos],c2[pos],T[pos], h[pos]);
  * trailing chunks (K%4 != 0) are never hashed. */
-void orc_elastic_commit(size_t N, size_t B, int trs, int lin, uint8_t *levels_out) {
+void orc_elastic_commit_stream(const F *stream, size_t N, size_t B, int trs, int lin, uint8_t *levels_out);
+void orc_elastic_commit(size_t N, size_t B, int trs, int lin, uint8_t *levels_out) { orc_elastic_commit_stream(NULL, N, B, trs, lin, levels_out); }
+/* stream == NULL: the synthetic "test" stream (every chunk restarts the recurrence); else N consecutive elements */
+void orc_elastic_commit_stream(const F *stream, size_t N, size_t B, int trs, int lin, uint8_t *levels_out) {
     F *buff = (F *)malloc(B * sizeof(F));
     F *park[3], *T = (F *)malloc(4 * B * sizeof(F));
     for (int i = 0; i < 3; i++) park[i] = (F *)malloc(4 * B * sizeof(F));
     memset(levels_out, 0, 4 * B * 32);
     for (size_t i = 0; i < N / B; i++) {
-        orc_read_stream_pc_test(buff, B);
+        if (stream) memcpy(buff, stream + i * B, B * sizeof(F)); else orc_read_stream_pc_test(buff, B);
         int nz = 0;
         for (size_t j = 0; j < B; j++) if (!f_eq(buff[j], F0)) { nz = 1; break; }
         if (nz) orc_compute_tensorcode(buff, B, trs, lin, T); else memset(T, 0, 4 * B * sizeof(F));

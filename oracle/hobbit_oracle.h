@@ -48,6 +48,7 @@ void orc_compute_tensorcode(const orc_F *msg, size_t n, int trs, int lin, orc_F 
 void orc_commit_standard(const orc_F *poly, size_t N, int K, int trs, int lin, uint8_t *levels_out, orc_F *tensor_out);
 void orc_read_stream_pc_test(orc_F *out, size_t n);
 void orc_elastic_commit(size_t N, size_t B, int trs, int lin, uint8_t *levels_out);
+void orc_elastic_commit_stream(const orc_F *stream, size_t N, size_t B, int trs, int lin, uint8_t *levels_out);
 /* S9 */
 void orc_precompute_beta(const orc_F *r, int nr, orc_F *out);
 void orc_evaluate_vector(const orc_F *v, size_t n, const orc_F *r, int nr, orc_F *out);

@@ -227,6 +227,34 @@ int main(int argc, char **argv) {
         printf("      ps %f / %f KB\n", ps, hps);
         if (big && lin) CHECK(hps == 3839.078125, "test_PC(2^20, 4, 32): ps == 3839.078125 KB (SURVEY §9 KAT)");
     }
+    // ---- Elastic_PC commit + open on the synthetic stream (test_Elastic_PC flow, Elastic_PC.cpp:736-785), both column codes ------------------
+    for (int lin = 0; lin < 2; lin++) {
+        const size_t N = 1 << 17; BUFFER_SPACE = 1 << 14; hobbit::BUFFER_SPACE = BUFFER_SPACE;
+        srand(3);
+        init_commitment(lin); tensor_row_size = 16;
+        if (lin) { __encode_initialized = false; expander_init_store(tensor_row_size); }
+        stream_descriptor fd; fd.name = "test"; fd.size = N;
+        _hash comm; vector<vector<_hash>> MT; commit(fd, comm, MT);
+        vector<vector<_hash>> MT0 = MT;
+        double ps = 0, hps = 0;
+        vector<F> x = generate_randomness(17);
+        open(fd, x, MT, vt, ps);
+        int r1 = rand();
+        srand(3);
+        hobbit::init_commitment(lin); hobbit::tensor_row_size = 16;
+        if (lin) hobbit::expander_init_store(hobbit::tensor_row_size);
+        hobbit::stream_descriptor hfd; hfd.name = "test"; hfd.size = N;
+        hobbit::_hash hcomm; vector<vector<hobbit::_hash>> hMT; hobbit::commit(hfd, hcomm, hMT);
+        vector<vector<hobbit::_hash>> hMT0 = hMT;
+        vector<hobbit::Fe> hx = hobbit::generate_randomness(17);
+        hobbit::open(hfd, hx, hMT, vt, hps);
+        int r2 = rand();
+        MT0[0].back() = _hash(); memset(&hMT0[0].back(), 0, 32);          // the reference's last leaf reads past its buffers
+        CHECK(same_levels(MT0, hMT0), lin ? "Elastic commit (Orion columns): every level" : "Elastic commit (RS columns): every level");
+        CHECK(ps == hps && r1 == r2 && MT.empty() && hMT.empty(), lin ? "Elastic open (Orion columns, Spielman_stream recursion): ps, RNG state, tree freed"
+                                                                      : "Elastic open (RS columns): ps, RNG state, tree freed");
+        printf("      ps %f / %f KB\n", ps, hps);
+    }
     printf(failures ? "OPEN: %d FAILURES\n" : "OPEN: all identical\n", failures);
     return failures ? 1 : 0;
 }

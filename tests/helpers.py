@@ -430,3 +430,20 @@ class RawABI:
         y = fzeros(len(pows))
         self.call("hb_whir_zeta", poly, b, ctypes.c_int(v), F(zetas), ctypes.c_int(len(pows)), pows, y)
         return b, y
+
+    def select_cols(self, M, rows, cols, col):
+        col = np.ascontiguousarray(col, dtype=np.uint64)
+        out = fzeros(len(col) * rows)
+        self.call("hb_select_cols", F(M), rows, cols, cols, col, len(col), out)
+        return out
+
+    def transpose(self, M, rows, cols):
+        out = fzeros(rows * cols)
+        self.call("hb_transpose", F(M), rows, cols, out)
+        return out
+
+    def any_nonzero(self, v):
+        v = F(v)
+        flag = ctypes.c_int(7)
+        self.call("hb_any_nonzero", v, len(v), ctypes.byref(flag))
+        return flag.value

@@ -84,3 +84,26 @@ def test_whir_blocks(abis):
         eb, ey = e.whir_zeta(p, b, z, pw)
         assert np.array_equal(gy, ey), (v, repeats)
         assert np.array_equal(gb, eb), (v, repeats)
+
+
+def test_select_transpose_nonzero(abis):
+    g, e = abis
+    rng = np.random.default_rng(7)
+    M = rand_field(rng, 16 * 300)
+    col = rng.integers(0, 300, size=77)
+    assert np.array_equal(g.select_cols(M, 16, 300, col), e.select_cols(M, 16, 300, col))
+    for rows, cols in [(32, 77), (1, 5), (100, 33), (64, 64)]:
+        M = rand_field(rng, rows * cols)
+        assert np.array_equal(g.transpose(M, rows, cols), e.transpose(M, rows, cols)), (rows, cols)
+    z = np.zeros((5000, 2), dtype=np.uint64)
+    assert g.any_nonzero(z) == 0 and e.any_nonzero(z) == 0
+    z[4999, 1] = 1
+    assert g.any_nonzero(z) == 1 and e.any_nonzero(z) == 1
+    import torch
+    t = torch.zeros((1 << 16, 2), dtype=torch.int64, device="cuda")
+    flag = __import__("ctypes").c_int(7)
+    g.call("hb_any_nonzero", __import__("ctypes").c_void_p(t.data_ptr()), 1 << 16, __import__("ctypes").byref(flag))
+    assert flag.value == 0
+    t[12345, 0] = 3
+    g.call("hb_any_nonzero", __import__("ctypes").c_void_p(t.data_ptr()), 1 << 16, __import__("ctypes").byref(flag))
+    assert flag.value == 1
