@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhobbit_b200.so")
-SOURCES = ["ntt.cu", "encode.cu", "merkle.cu", "commit.cu", "sumcheck.cu", "open.cu"]
+SOURCES = ["ntt.cu", "encode.cu", "merkle.cu", "commit.cu", "sumcheck.cu", "open.cu", "trace.cu"]
 HEADERS = ["common.cuh", "field.cuh", "blake3.cuh", "reduce.cuh", os.path.join("..", "..", "include", "hobbit_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -46,7 +46,7 @@ def build_library(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))
     # host-side C++ mirror of the reference API (plain g++, links against the C ABI)
-    host_srcs = [os.path.join(HERE, "host", f) for f in ("hobbit_host.cpp", "hobbit_open.cpp")]
+    host_srcs = [os.path.join(HERE, "host", f) for f in ("hobbit_host.cpp", "hobbit_open.cpp", "hobbit_circuit.cpp")]
     host_lib = os.path.join(HERE, "libhobbit_host.so")
     if force or any(_newer(f, host_lib) for f in host_srcs) or _newer(os.path.join(HERE, "host", "hobbit_host.hpp"), host_lib) or _newer(LIB, host_lib):
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", host_lib] + host_srcs + ["-L" + HERE, "-lhobbit_b200", "-Wl,-rpath,$ORIGIN"]

@@ -138,6 +138,8 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     if (ctx->exp.d_stages) { cudaFree(ctx->exp.d_stages); cudaFree(ctx->exp.d_rowptr); cudaFree(ctx->exp.d_edges); }
     if (ctx->tensor) cudaFree(ctx->tensor);
     if (ctx->poly) cudaFree(ctx->poly);
+    if (ctx->trace.tuples) cudaFree(ctx->trace.tuples);
+    if (ctx->trace.pos) cudaFree(ctx->trace.pos);
     if (ctx->red) cudaFree(ctx->red);
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);

@@ -61,6 +61,13 @@ struct ElasticOpen {
     void *buf = nullptr; F *agg = nullptr, *tensor = nullptr, *msg = nullptr, *reply = nullptr; uint32_t *col = nullptr, *row = nullptr;
 };
 
+// one pass of the circuit evaluator's trace, resident in HBM (trace.cu)
+struct TraceState {
+    void *tuples = nullptr; size_t capacity = 0, n = 0, n_ops = 0, n_del = 0;
+    bool done = false, indexed = false;
+    unsigned *pos = nullptr;            // is_op | is_del | op_pos | del_pos, n entries each
+};
+
 }  // namespace hb
 
 struct hb_ctx {
@@ -80,6 +87,7 @@ struct hb_ctx {
     hb::F *poly = nullptr; size_t poly_elems = 0; const void *poly_host = nullptr;
     hb::ElasticState el;
     hb::ElasticOpen eo;
+    hb::TraceState trace;
     // sumcheck reduction scratch: per-CTA partial coefficients + ticket counter (device), result mailbox (pinned host)
     hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr; unsigned long long seq = 0;
     // optional per-kernel timing (hb_profile_*): CUDA events around every launch, on this context's stream

@@ -1,0 +1,202 @@
+// W1/W2 — the circuit witness streams derived on the GPU from the evaluator's trace.
+// Reference: tr_tuple (src/Seval.h:4-9), the stateful readers read_witness / _read_witness (src/witness_stream.cpp:768-874, 1260-1338),
+// read_trace (:1701-1807), read_memory_opt / read_memory_trancript / read_final_memory_trancript (:1055-1258, 1620-1698) and the
+// "wiring_consistency_check_opt" branch of read_stream (:2276-2311).
+//
+// The reference re-executes the circuit once per pass over a stream (a producer thread refills an 80-byte-per-gate ring buffer and
+// the readers above pull from it under a mutex hand-off: "streaming time", about 20 % of its prover time).  Here ONE pass of the
+// trace is uploaded and kept in HBM (80 B per tuple: 160 MiB for the 2^20-gate MLP) and every named stream is a pure function of it:
+// a stream position is the rank of an op tuple (type 1..254) or of a delete tuple (type 0), so two exclusive scans over the type byte
+// give every element its destination and the streams are written by one scatter kernel each — HBM-bound, 80 B read per tuple.
+#include "common.cuh"
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+
+namespace hb {
+
+struct TrTuple {                       // == reference tr_tuple: 3 F, 3 idx, 3 access counters, type; 80 bytes
+    F value_o, value_l, value_r;
+    int idx_o, idx_l, idx_r;
+    int access_o, access_l, access_r;
+    uint8_t type; uint8_t pad_[7];
+};
+static_assert(sizeof(TrTuple) == 80, "tr_tuple layout");
+
+__device__ __forceinline__ F f_int(int x) { return mkF(x >= 0 ? (u64)x : P61 - (u64)(-(long long)x), 0); }
+
+__global__ void __launch_bounds__(256) trace_flags_kernel(const TrTuple *__restrict__ tr, size_t n, unsigned *__restrict__ is_op, unsigned *__restrict__ is_del) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t t = tr[i].type;
+    is_op[i] = (t > 0 && t != 255) ? 1u : 0u;
+    is_del[i] = (t == 0) ? 1u : 0u;
+}
+// "witness" (4cs): [ (l, r, o) of op tuple p at 3p.. | value_o of delete tuple q at 3cs + q ], zero padded (memset by the caller)
+__global__ void __launch_bounds__(256)
+trace_witness_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__restrict__ op_pos, const unsigned *__restrict__ del_pos, size_t cs, F *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrTuple &t = tr[i];
+    if (t.type == 0) out[3 * cs + del_pos[i]] = t.value_o;
+    else if (t.type != 255) { size_t p = 3 * (size_t)op_pos[i]; out[p] = t.value_l; out[p + 1] = t.value_r; out[p + 2] = t.value_o; }
+}
+// "transcript_stream" (read_trace): L, R, O and the selector S (no lookups: add 1 / mul 0; lookups: add 0 / mul 1 / table 2)
+__global__ void __launch_bounds__(256)
+trace_transcript_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__restrict__ op_pos, int has_lookups,
+                        F *__restrict__ L, F *__restrict__ R, F *__restrict__ O, F *__restrict__ S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrTuple &t = tr[i];
+    if (t.type == 0 || t.type == 255) return;
+    size_t p = op_pos[i];
+    L[p] = t.value_l; R[p] = t.value_r; O[p] = t.value_o;
+    int s = t.type == 1 ? (has_lookups ? 0 : 1) : t.type == 2 ? (has_lookups ? 1 : 0) : 2;
+    S[p] = mkF((u64)s, 0);
+}
+// "wiring_consistency_check_opt" in its logical two-half form [X | Y] (4cs each):
+//   X[3p+c] = idx+1 + a_w value + b_w access (read set), Y = X + b_w (write set), or 1 where X == 1
+//   X[3cs+q] = idx_o+1 + a_w value_o (init set), Y = X + b_w access_o (final set); padding positions are 1 in both halves.
+__device__ __forceinline__ F wire_entry(int idx, F value, int access, F a_w, F b_w) {
+    return fadd(fadd(fadd(f_int(idx), mkF(1, 0)), fmul(a_w, value)), fmul(b_w, f_int(access)));
+}
+__global__ void __launch_bounds__(256)
+trace_wiring_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__restrict__ op_pos, const unsigned *__restrict__ del_pos, size_t cs,
+                    F a_w, F b_w, F *__restrict__ X, F *__restrict__ Y) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrTuple &t = tr[i];
+    const F one = mkF(1, 0);
+    if (t.type == 0) {
+        size_t q = 3 * cs + del_pos[i];
+        F x = fadd(fadd(f_int(t.idx_o), one), fmul(a_w, t.value_o));
+        X[q] = x; Y[q] = fadd(x, fmul(b_w, f_int(t.access_o)));
+    } else if (t.type != 255) {
+        size_t p = 3 * (size_t)op_pos[i];
+        F x0 = wire_entry(t.idx_l, t.value_l, t.access_l, a_w, b_w), x1 = wire_entry(t.idx_r, t.value_r, t.access_r, a_w, b_w),
+          x2 = wire_entry(t.idx_o, t.value_o, t.access_o, a_w, b_w);
+        X[p] = x0; X[p + 1] = x1; X[p + 2] = x2;
+        Y[p] = feq(x0, one) ? x0 : fadd(x0, b_w); Y[p + 1] = feq(x1, one) ? x1 : fadd(x1, b_w); Y[p + 2] = feq(x2, one) ? x2 : fadd(x2, b_w);
+    }
+}
+__global__ void __launch_bounds__(256) fill_kernel(F *__restrict__ v, size_t n, F x) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] = x;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" int hb_trace_begin(hb_ctx *ctx, size_t capacity) {
+    TraceState &t = ctx->trace;
+    if (t.tuples && t.capacity < capacity) { cudaFree(t.tuples); t.tuples = nullptr; }
+    if (!t.tuples) { HB_CHECK(ctx, cudaMalloc(&t.tuples, std::max<size_t>(capacity, 1) * 80)); t.capacity = std::max<size_t>(capacity, 1); }
+    if (t.pos) { cudaFree(t.pos); t.pos = nullptr; }
+    t.n = 0; t.n_ops = t.n_del = 0; t.done = false; t.indexed = false;
+    return 0;
+}
+
+extern "C" int hb_trace_push(hb_ctx *ctx, const void *tuples, size_t n, int *done) {
+    TraceState &t = ctx->trace;
+    if (!t.tuples) HB_FAIL(ctx, "hb_trace_push: call hb_trace_begin first");
+    if (done) *done = t.done ? 1 : 0;
+    if (t.done || n == 0) return 0;
+    if (is_device_ptr(tuples)) HB_FAIL(ctx, "hb_trace_push: the producer's buffer is host memory");
+    const TrTuple *src = reinterpret_cast<const TrTuple *>(tuples);
+    size_t take = n;
+    for (size_t i = 0; i < n; i++) if (src[i].type == 255) { take = i; t.done = true; break; }      // end-of-circuit marker (Seval.cpp:1273-1283)
+    if (t.n + take > t.capacity) {                                                                   // grow geometrically
+        size_t cap = std::max(t.capacity * 2, t.n + take);
+        void *p; HB_CHECK(ctx, cudaMalloc(&p, cap * 80));
+        HB_CHECK(ctx, cudaMemcpyAsync(p, t.tuples, t.n * 80, cudaMemcpyDeviceToDevice, ctx->stream));
+        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(t.tuples); t.tuples = p; t.capacity = cap;
+    }
+    // the producer reuses its buffer as soon as we return: the copy must have left the host buffer before that
+    HB_CHECK(ctx, cudaMemcpyAsync((char *)t.tuples + t.n * 80, src, take * 80, cudaMemcpyHostToDevice, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    t.n += take;
+    if (done) *done = t.done ? 1 : 0;
+    return 0;
+}
+
+static int trace_index(hb_ctx *ctx) {
+    TraceState &t = ctx->trace;
+    if (t.indexed) return 0;
+    const size_t n = std::max<size_t>(t.n, 1);
+    HB_CHECK(ctx, cudaMalloc(&t.pos, 4 * n * sizeof(unsigned)));
+    unsigned *is_op = t.pos, *is_del = t.pos + n, *op_pos = t.pos + 2 * n, *del_pos = t.pos + 3 * n;
+    if (t.n) {
+        HB_LAUNCH(ctx, trace_flags_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, is_op, is_del);
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, is_op, op_pos, (int)t.n, ctx->stream);
+        void *tmp; HB_CHECK(ctx, cudaMallocAsync(&tmp, tmp_bytes, ctx->stream));
+        HB_CHECK(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_op, op_pos, (int)t.n, ctx->stream));
+        HB_CHECK(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_del, del_pos, (int)t.n, ctx->stream));
+        ctx->launches += 2;
+        cudaFreeAsync(tmp, ctx->stream);
+        unsigned last[4];
+        HB_CHECK(ctx, cudaMemcpyAsync(&last[0], is_op + t.n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(&last[1], op_pos + t.n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(&last[2], is_del + t.n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(&last[3], del_pos + t.n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        t.n_ops = (size_t)last[0] + last[1]; t.n_del = (size_t)last[2] + last[3];
+    }
+    t.indexed = true;
+    return 0;
+}
+
+extern "C" int hb_trace_finish(hb_ctx *ctx, size_t *n_tuples, size_t *n_ops, size_t *n_deletes) {
+    if (!ctx->trace.tuples) HB_FAIL(ctx, "hb_trace_finish: no trace");
+    HB_TRY(trace_index(ctx));
+    if (n_tuples) *n_tuples = ctx->trace.n;
+    if (n_ops) *n_ops = ctx->trace.n_ops;
+    if (n_deletes) *n_deletes = ctx->trace.n_del;
+    return 0;
+}
+
+static int trace_check(hb_ctx *ctx, size_t cs, const char *who) {
+    HB_TRY(trace_index(ctx));
+    if (cs == 0 || (cs & (cs - 1))) HB_FAIL(ctx, std::string(who) + ": circuit_size must be a power of two");
+    if (ctx->trace.n_ops > cs || ctx->trace.n_del > cs) HB_FAIL(ctx, std::string(who) + ": the trace has more op / delete tuples than circuit_size");
+    return 0;
+}
+
+extern "C" int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out) {
+    HB_TRY(trace_check(ctx, cs, "hb_trace_witness"));
+    TraceState &t = ctx->trace;
+    Staged so(ctx);
+    HB_TRY(so.outbuf(out, 4 * cs * sizeof(F)));
+    HB_CHECK(ctx, cudaMemsetAsync(so.dev, 0, 4 * cs * sizeof(F), ctx->stream));
+    if (t.n) HB_LAUNCH(ctx, trace_witness_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, t.pos + 3 * t.n, cs, so.as<F>());
+    HB_TRY(so.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S) {
+    HB_TRY(trace_check(ctx, cs, "hb_trace_transcript"));
+    TraceState &t = ctx->trace;
+    Staged sl(ctx), sr(ctx), so(ctx), ss(ctx);
+    HB_TRY(sl.outbuf(L, cs * sizeof(F))); HB_TRY(sr.outbuf(R, cs * sizeof(F))); HB_TRY(so.outbuf(O, cs * sizeof(F))); HB_TRY(ss.outbuf(S, cs * sizeof(F)));
+    for (Staged *s : {&sl, &sr, &so, &ss}) HB_CHECK(ctx, cudaMemsetAsync(s->dev, 0, cs * sizeof(F), ctx->stream));
+    if (t.n) HB_LAUNCH(ctx, trace_transcript_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, has_lookups,
+                       sl.as<F>(), sr.as<F>(), so.as<F>(), ss.as<F>());
+    for (Staged *s : {&sl, &sr, &so, &ss}) HB_TRY(s->finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy) {
+    HB_TRY(trace_check(ctx, cs, "hb_trace_wiring"));
+    TraceState &t = ctx->trace;
+    Staged so(ctx);
+    HB_TRY(so.outbuf(xy, 8 * cs * sizeof(F)));
+    F *X = so.as<F>(), *Y = X + 4 * cs;
+    HB_LAUNCH(ctx, fill_kernel, (unsigned)std::min<size_t>((8 * cs + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, X, 8 * cs, mkF(1, 0));
+    if (t.n) HB_LAUNCH(ctx, trace_wiring_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, t.pos + 3 * t.n, cs,
+                       mkF(a_w->real, a_w->img), mkF(b_w->real, b_w->img), X, Y);
+    HB_TRY(so.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

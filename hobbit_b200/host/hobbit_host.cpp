@@ -194,8 +194,9 @@ void init_commitment(bool mod) {                                                
     if (tensor_row_size == 0) tensor_row_size = 16;
 }
 void read_stream_PC(stream_descriptor &fd, F *v, int size) {                    // witness_stream.cpp:2356-2412, default branch only
-    if (fd.name == "PC_layer" || fd.name == "witness" || fd.name == "circuit") {
-        printf("hobbit_b200: stream '%s' needs the circuit evaluator (out of scope this round)\n", fd.name.c_str()); exit(-1);
+    if (fd.name == "witness") { std::vector<F> buf(size); read_stream(fd, buf, size); memcpy(v, buf.data(), (size_t)size * sizeof(F)); return; }   // :2357-2364
+    if (fd.name == "PC_layer" || fd.name == "circuit") {
+        printf("hobbit_b200: stream '%s' is not built (commit_layers / circuit description stream)\n", fd.name.c_str()); exit(-1);
     }
     CK(hb_stream_pc_test(backend(), (hb_F *)v, (size_t)size));
 }
@@ -203,7 +204,9 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     if (fd.size / BUFFER_SPACE < 4) printf("Decrease buffer size %d\n", (int)(fd.size / BUFFER_SPACE));
     std::vector<F> buff(BUFFER_SPACE);
     CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
+    const F *res = resident_stream(fd);                                          // circuit streams: chunks are slices of the HBM-resident stream
     for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++) {
+        if (res) { CK(hb_elastic_push(backend(), (const hb_F *)(res + i * BUFFER_SPACE))); continue; }
         read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
         CK(hb_elastic_push(backend(), (const hb_F *)buff.data()));
     }
@@ -301,14 +304,15 @@ mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input,
 
 void reset_stream(stream_descriptor &fd) { fd.pos = 0; fd.idx = 0; fd.stage = 0; fd.offset = 0; fd.finished = false; }   // witness_stream.cpp:228-234
 void read_stream(stream_descriptor &fd, std::vector<F> &v, int size) {                                                   // :2106-2353, default branch
-    static const char *circuit_names[] = {"input", "circuit", "witness", "wiring_consistency_check", "wiring_consistency_check_opt",
-                                          "lookup_basic", "lookup_witness_basic", "transcript_stream"};
+    if (read_circuit_stream(fd, v, size)) return;
+    static const char *circuit_names[] = {"input", "circuit", "wiring_consistency_check", "lookup_basic", "lookup_witness_basic", "transcript_stream"};
     for (const char *n : circuit_names)
-        if (fd.name == n) { printf("hobbit_b200: stream '%s' needs the circuit evaluator (out of scope this round)\n", n); exit(-1); }
+        if (fd.name == n) { printf("hobbit_b200: stream '%s' is not built (use read_trace for the gate transcript)\n", n); exit(-1); }
     for (int i = 0; i < size; i++) v[i] = F((i % 1024) + 1);
 }
 
-const F *stream_chunk(stream_descriptor &fd, size_t, size_t B, std::vector<F> &buff) {
+const F *stream_chunk(stream_descriptor &fd, size_t i, size_t B, std::vector<F> &buff) {
+    if (fd.name == "witness") return resident_stream(fd) + i * B;
     buff.resize(B);
     read_stream(fd, buff, (int)B);
     return buff.data();
@@ -319,9 +323,9 @@ std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, in
     if (!prev_x.empty()) { printf("hobbit_b200: prove_multiplication_tree_stream_shallow with prev_x is not wired yet\n"); exit(-1); }
     const size_t total = (size_t)size * vectors;
     // the stream in its logical two-half form [X | Y]: one read of the whole stream (a two-half producer emits X-block | Y-block)
-    std::vector<F> xy(total);
-    reset_stream(fd);
-    read_stream(fd, xy, (int)total);
+    std::vector<F> xy;
+    const F *xy_ptr = resident_stream(fd);                                       // circuit stream: already [X | Y] in HBM
+    if (!xy_ptr) { xy.resize(total); reset_stream(fd); read_stream(fd, xy, (int)total); xy_ptr = xy.data(); }
     int layers = 0;
     if (total > 2 * BUFFER_SPACE) {
         layers = (int)std::log2((double)(total / (2 * BUFFER_SPACE)));
@@ -336,7 +340,7 @@ std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, in
     if (rnd.empty()) rnd.resize(4);
     std::vector<F> out(vectors);
     int got_layers = 0;
-    CK(hb_mul_tree_stream(backend(), (const hb_F *)xy.data(), total, vectors, BUFFER_SPACE, distance, naive ? 1 : 0, (const hb_F *)&previous_r,
+    CK(hb_mul_tree_stream(backend(), (const hb_F *)xy_ptr, total, vectors, BUFFER_SPACE, distance, naive ? 1 : 0, (const hb_F *)&previous_r,
                           (const hb_F *)xr.data(), (const hb_F *)rnd.data(), (hb_F *)out.data(), &got_layers, &ps));
     return out;
 }

@@ -150,6 +150,27 @@ void open(stream_descriptor fd, std::vector<F> x, std::vector<std::vector<_hash>
 // chunk i (BUFFER_SPACE elements) of a stream as read_stream emits it: a pointer into HBM for resident circuit streams, else `buff`
 const F *stream_chunk(stream_descriptor &fd, size_t i, size_t B, std::vector<F> &buff);
 
+// ---- circuit streams (hobbit_circuit.cpp): ONE pass of the evaluator's trace goes to HBM, every named stream is derived
+// there and stays resident ------------------------------------------------------------------------------------------------------------
+struct tr_tuple {                              // Seval.h:4-9
+    F value_o, value_l, value_r;
+    int idx_o, idx_l, idx_r;
+    int access_o, access_l, access_r;
+    uint8_t type;
+};
+extern size_t circuit_size;                    // main.cpp:36
+extern F a_w, b_w;                             // main.cpp:63
+extern bool has_lookups;                       // main.cpp:67
+// the consumer side of the producer hand-off (what read_tr does, main.cpp:283-300): call trace_append with each refilled tr[] buffer until
+// it returns true (type 255 seen); trace_end() sets and returns circuit_size (get_circuit_size, main.cpp:303-321)
+void trace_begin(size_t capacity_hint = 0);
+bool trace_append(const tr_tuple *buf, size_t n);
+size_t trace_end();
+const F *resident_stream(const stream_descriptor &fd);          // the whole logical stream in HBM, nullptr for non-circuit streams
+bool read_circuit_stream(stream_descriptor &fd, std::vector<F> &v, int size);
+void read_trace(stream_descriptor &fd, std::vector<F> &buff_L, std::vector<F> &buff_R, std::vector<F> &buff_O, std::vector<int> &buff_S);
+void prove_gate_consistency(stream_descriptor tr, std::vector<F> r, double &vt, double &ps);
+
 // sumcheck.h
 proof generate_2product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, F previous_r, double &vt, double &ps);
 proof _generate_3product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, std::vector<F> &v3, F previous_r, double &vt, double &ps);

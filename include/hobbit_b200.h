@@ -225,6 +225,24 @@ int hb_whir_fold(hb_ctx *ctx, hb_F *poly, hb_F *beta, size_t L, const hb_F *a);
  * beta[j] += sum_i pows[i] eq(z_i)[j]   (poly, beta: 2^v entries) */
 int hb_whir_zeta(hb_ctx *ctx, const hb_F *poly, hb_F *beta, int v, const hb_F *zetas, int repeats, const hb_F *pows, hb_F *y);
 
+/* ---- W1/W2 (8f.2): circuit witness streams derived on the GPU from ONE pass of the evaluator's trace ------------------------------------
+ * A trace record is the reference's 80-byte `tr_tuple` (Seval.h:4-9): F value_o, value_l, value_r; int idx_o, idx_l, idx_r;
+ * int access_o, access_l, access_r; uint8_t type (0 delete/output, 1 add, 2 mul, >= 3 lookup, 255 end of circuit).
+ * begin / push (the producer's host buffers, in order; everything from the first type-255 record on is ignored and *done becomes 1) /
+ * finish (counts).  The trace stays resident in the context; each stream below is what the reference's stateful readers emit when the
+ * stream is read front to back (witness_stream.cpp:768-874, 1055-1338, 1620-1807, 2276-2311), `cs` = circuit_size = ops = gates:
+ *   witness     4cs : (value_l, value_r, value_o) per op record, zero padded to 3cs | value_o per delete record, zero padded to cs
+ *   transcript  cs  : L, R, O = values per op record; S = F(1) add / F(0) mul  (has_lookups: 0 add / 1 mul / 2 table), zero padded
+ *   wiring      8cs : "wiring_consistency_check_opt" in its logical two-half form [X | Y] (what hb_mul_tree_stream takes):
+ *                     X = idx+1 + a_w value + b_w access over (l, r, o) of op records (3cs) | idx_o+1 + a_w value_o over deletes (cs);
+ *                     Y = X + b_w (or 1 where X == 1) | X + b_w access_o; padding = 1 */
+int hb_trace_begin(hb_ctx *ctx, size_t capacity_records);
+int hb_trace_push(hb_ctx *ctx, const void *records, size_t n, int *done);
+int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_deletes);
+int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out);
+int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S);
+int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@ struct hb_ctx {
     std::vector<F> tensor; size_t tN = 0; int tK = 0, ttrs = 0;
     std::vector<F> poly; const void *poly_host = nullptr;
     long long exp_n = 0, exp_cw = 0;
+    std::vector<unsigned char> trace; size_t tr_n = 0; bool tr_done = false;
     size_t eB = 0; int etrs = 0, elin = 0; std::vector<F> estream, ebeta; std::vector<uint32_t> ecol, erow;
 };
 static const uint64_t P = 2305843009213693951ULL;
@@ -116,9 +117,32 @@ int hb_sumcheck3(hb_ctx *, const hb_F *v1, const hb_F *v2, const hb_F *v3, size_
 int hb_batch_sumcheck3(hb_ctx *, const hb_F *t1, const hb_F *t2, const hb_F *t3, const size_t *sizes, int batches, const hb_F *a, hb_F *proof, double *ps) {
     *ps += orc_batch_sumcheck3(cF(t1), cF(t2), cF(t3), sizes, batches, cF(a), mF(proof)); return 0;
 }
-/* not emulated (the oracle draws libc randomness inside these; the host mirror draws it outside): GPU-only in the drop-in tests */
-int hb_mul_tree(hb_ctx *ctx, const hb_F *, int, size_t, const hb_F *, const hb_F *, hb_F *, size_t *, int *, double *) { FAIL(ctx, "hb_mul_tree: not emulated"); }
-int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *, size_t, int, size_t, int, int, const hb_F *, const hb_F *, const hb_F *, hb_F *, int *, double *) { FAIL(ctx, "hb_mul_tree_stream: not emulated"); }
+/* The host mirror draws the libc values in the reference's order and hands them over; the oracle's provers replay them (injection). */
+int hb_mul_tree(hb_ctx *, const hb_F *input, int vectors, size_t n, const hb_F *prev_r, const hb_F *x_rand, hb_F *out, size_t *written, int *nfr, double *ps) {
+    orc_inject_randomness(cF(x_rand), vectors > 1 ? (size_t)ilog2((size_t)vectors) : 0);
+    double p = 0; *written = orc_mul_tree(cF(input), vectors, n, cF(prev_r), mF(out), nfr, &p); *ps += p;
+    orc_inject_randomness(nullptr, 0);
+    return 0;
+}
+int hb_mul_tree_stream(hb_ctx *, const hb_F *xy, size_t total, int vectors, size_t B, int distance, int naive, const hb_F *prev_r, const hb_F *x_rand,
+                       const hb_F *rnd, hb_F *out, int *layers_out, double *ps) {
+    int layers = 0;
+    if (total > 2 * B) { layers = ilog2(total / (2 * B)); if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance); }
+    std::vector<F> q(cF(x_rand), cF(x_rand) + ilog2((size_t)vectors));
+    q.insert(q.end(), cF(rnd), cF(rnd) + 4 * (size_t)layers);
+    orc_inject_randomness(q.data(), q.size());
+    *ps += orc_mul_tree_stream(cF(xy), total, vectors, B, distance, naive, cF(prev_r), mF(out));
+    orc_inject_randomness(nullptr, 0);
+    if (layers_out) *layers_out = layers;
+    return 0;
+}
+int hb_gate_consistency_stream(hb_ctx *, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B, const hb_F *r, const hb_F *rnd10,
+                               hb_F *out, double *ps) {
+    orc_inject_randomness(cF(rnd10), 10);
+    *ps += orc_gate_consistency_stream(cF(L), cF(R), cF(O), cF(S), cs, B, cF(r), mF(out));
+    orc_inject_randomness(nullptr, 0);
+    return 0;
+}
 /* Elastic_PC commit / open front: chunks are buffered and handed to the oracle's restatement at finish */
 int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int lin) { ctx->eB = B; ctx->etrs = trs; ctx->elin = lin; ctx->estream.clear(); return 0; }
 int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) { ctx->estream.insert(ctx->estream.end(), cF(chunk), cF(chunk) + ctx->eB); return 0; }
@@ -273,6 +297,70 @@ int hb_whir_zeta(hb_ctx *, const hb_F *poly, hb_F *beta, int v, const hb_F *zeta
         for (size_t j = 0; j < n; j++) acc = fadd(acc, fmul(eq[j], cF(poly)[j]));
         mF(y)[i] = acc;
         for (size_t j = 0; j < n; j++) mF(beta)[j] = fadd(mF(beta)[j], fmul(cF(pows)[i], eq[j]));
+    }
+    return 0;
+}
+
+/* ---- W1/W2: the named circuit streams as the reference's readers emit them front to back (witness_stream.cpp:768-874, 1055-1338,
+ * 1620-1807, 2276-2311), restated sequentially over one pass of the trace */
+struct emu_tuple { F value_o, value_l, value_r; int idx_o, idx_l, idx_r; int access_o, access_l, access_r; uint8_t type; };
+static_assert(sizeof(emu_tuple) == 80, "tr_tuple layout");
+static F f_int(long long x) { return mk(x >= 0 ? (uint64_t)x : P - (uint64_t)(-x)); }
+int hb_trace_begin(hb_ctx *ctx, size_t) { ctx->trace.clear(); ctx->tr_n = 0; ctx->tr_done = false; return 0; }
+int hb_trace_push(hb_ctx *ctx, const void *records, size_t n, int *done) {
+    const emu_tuple *t = (const emu_tuple *)records;
+    for (size_t i = 0; i < n && !ctx->tr_done; i++) {
+        if (t[i].type == 255) { ctx->tr_done = true; break; }
+        ctx->trace.insert(ctx->trace.end(), (const unsigned char *)&t[i], (const unsigned char *)&t[i] + 80); ctx->tr_n++;
+    }
+    if (done) *done = ctx->tr_done ? 1 : 0;
+    return 0;
+}
+int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_deletes) {
+    const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); size_t o = 0, d = 0;
+    for (size_t i = 0; i < ctx->tr_n; i++) { if (t[i].type == 0) d++; else o++; }
+    if (n_records) *n_records = ctx->tr_n; if (n_ops) *n_ops = o; if (n_deletes) *n_deletes = d;
+    return 0;
+}
+int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out) {
+    const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); F *w = mF(out);
+    memset(w, 0, 4 * cs * sizeof(F));
+    size_t c = 0;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type > 0) { w[c++] = t[i].value_l; w[c++] = t[i].value_r; w[c++] = t[i].value_o; }   /* stage 0 */
+    c = 3 * cs;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type == 0) w[c++] = t[i].value_o;                                                  /* stage 1 */
+    return 0;
+}
+int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S) {
+    const emu_tuple *t = (const emu_tuple *)ctx->trace.data();
+    for (hb_F *p : {L, R, O, S}) memset(p, 0, cs * sizeof(F));
+    size_t c = 0;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type > 0) {
+        mF(L)[c] = t[i].value_l; mF(R)[c] = t[i].value_r; mF(O)[c] = t[i].value_o;
+        int s = t[i].type == 1 ? (has_lookups ? 0 : 1) : t[i].type == 2 ? (has_lookups ? 1 : 0) : 2;
+        mF(S)[c++] = mk((uint64_t)s);
+    }
+    return 0;
+}
+int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy) {
+    const emu_tuple *t = (const emu_tuple *)ctx->trace.data();
+    std::vector<F> addr(4 * cs, mk(0)), val(4 * cs, mk(0)), freq(4 * cs, mk(0));
+    size_t c = 0;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type > 0) {
+        addr[c] = f_int(t[i].idx_l); val[c] = t[i].value_l; freq[c++] = f_int(t[i].access_l);
+        addr[c] = f_int(t[i].idx_r); val[c] = t[i].value_r; freq[c++] = f_int(t[i].access_r);
+        addr[c] = f_int(t[i].idx_o); val[c] = t[i].value_o; freq[c++] = f_int(t[i].access_o);
+    }
+    c = 3 * cs;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type == 0) { addr[c] = f_int(t[i].idx_o); val[c] = t[i].value_o; freq[c++] = f_int(t[i].access_o); }
+    F *X = mF(xy), *Y = X + 4 * cs; const F a = *cF(a_w), b = *cF(b_w), one = mk(1);
+    for (size_t i = 0; i < 3 * cs; i++) {                                  /* stage 0 (:2291-2301) */
+        X[i] = fadd(fadd(fadd(addr[i], one), fmul(a, val[i])), fmul(b, freq[i]));
+        Y[i] = (X[i].re == 1 && X[i].im == 0) ? X[i] : fadd(X[i], b);
+    }
+    for (size_t i = 3 * cs; i < 4 * cs; i++) {                             /* stage 1 (:2302-2309) */
+        X[i] = fadd(fadd(addr[i], one), fmul(a, val[i]));
+        Y[i] = fadd(X[i], fmul(b, freq[i]));
     }
     return 0;
 }

@@ -102,6 +102,19 @@ void orc_fft(F *arr, int logn) {
 }
 
 /* utils.cpp:873-883: c = random() every 100 elements; x_i = c + F(rand()) */
+/* Injected randomness (used only by the CPU emulation of the C ABI, oracle/hb_emul.cpp): the host mirror draws the libc values itself,
+ * in the reference's order, and hands them to the C ABI; the provers below then take their draws from this queue instead of libc. */
+static const F *inj_q = NULL; static size_t inj_n = 0, inj_pos = 0;
+void orc_inject_randomness(const F *q, size_t n) { inj_q = q; inj_n = n; inj_pos = 0; }
+static void prover_randomness(int n, F *out) {
+    if (inj_q) { for (int i = 0; i < n; i++) { if (inj_pos >= inj_n) { printf("orc: injected randomness exhausted\n"); exit(-1); } out[i] = inj_q[inj_pos++]; } return; }
+    orc_generate_randomness(n, out);
+}
+static F prover_random(void) {
+    if (inj_q) { F o; prover_randomness(1, &o); return o; }
+    F o = { (uint64_t)random(), 0 }; return o;
+}
+void orc_generate_randomness(int n, F *out);
 void orc_generate_randomness(int n, F *out) {
     F c = F0;
     for (int i = 0; i < n; i++) {
@@ -529,7 +542,7 @@ size_t orc_mul_tree(const F *input, int vectors, size_t n, const F *prev_r, F *o
         }
     } else {
         nr = ilog2(vectors);
-        orc_generate_randomness(nr, r);
+        prover_randomness(nr, r);
         sum = evaluate_vector(tr[depth - 1], vectors, r); out_eval = sum;
         previous_r = mimc(r[nr - 1], sum);
         for (int i = depth - 1; i >= 0; i--) {
@@ -580,7 +593,7 @@ int orc_stream_sumcheck_layer(const F *xy, size_t total, size_t B, int layer_id,
     double ps = 0;
     F Kp = F0;
     for (size_t j = 0; j < B; j++) { f1[j] = A[2 * j]; f2[j] = A[2 * j + 1]; f3[j] = eq_low[j]; Kp = f_add(Kp, f_mul(f_mul(f1[j], f2[j]), f3[j])); }
-    F a; orc_generate_randomness(1, &a);
+    F a; prover_randomness(1, &a);
     F Kf = f_mul(a, Kp);
     Kp = f_mul(Kp, eq_high[0]);
     ps += 2 * 16 / 1024.0;
@@ -631,7 +644,7 @@ int orc_stream_sumcheck_layer(const F *xy, size_t total, size_t B, int layer_id,
     F *Rp = (F *)malloc(nb * sizeof(F)); size_t cnt = 0;
     for (size_t i = 0; i < nb / 2; i++) Rp[cnt++] = R[2 * i];
     for (size_t i = 0; i < nb / 2; i++) Rp[cnt++] = R[2 * i + 1];
-    F b[2]; orc_generate_randomness(2, b);
+    F b[2]; prover_randomness(2, b);
     F *aggr = (F *)malloc(nb * sizeof(F));
     for (size_t j = 0; j < nb; j++) aggr[j] = f_add(f_mul(b[0], PE0[j]), f_mul(b[1], PE1[j]));
     F *p2 = (F *)malloc((4 * (size_t)lgnb + 8) * sizeof(F));
@@ -642,7 +655,7 @@ int orc_stream_sumcheck_layer(const F *xy, size_t total, size_t B, int layer_id,
         F q = f_add(f_add(p2[0], p2[1]), f_add(p2[2], p2[2]));
         if (!f_eq(sum, q)) { printf("Error in sumcheck 2\n"); exit(-1); }
     }
-    F pad = f_int(random());
+    F pad = prover_random();
     size_t k = 0; new_r[k++] = pad;
     for (int j = 0; j < lgB; j++) new_r[k++] = P1r[j];
     const F *P2r = p2 + 3 * lgnb;
@@ -827,7 +840,7 @@ double orc_gate_consistency_stream(const F *L, const F *R, const F *O, const F *
         }
     }
     for (size_t i = 0; i < nch; i++) out[k++] = Rv[i];
-    F a[4]; orc_generate_randomness(4, a);
+    F a[4]; prover_randomness(4, a);
     F sum = f_add(f_add(f_mul(a[0], KfL), f_mul(a[1], KfR)), f_add(f_mul(a[2], KfM), f_mul(KfO, a[3])));
     F *srand_ = (F *)malloc(lgB * sizeof(F));
     for (int i = lgB - 1, q = 0; i >= 0; i--, q++) {
@@ -882,7 +895,7 @@ double orc_gate_consistency_stream(const F *L, const F *R, const F *O, const F *
             Pe[5 * nch + c] = f_add(Pe[5 * nch + c], f_mul(beta1[j], beta[j]));
         }
     for (size_t i = 0; i < 6 * nch; i++) out[k++] = Pe[i];
-    F b[6]; orc_generate_randomness(6, b);
+    F b[6]; prover_randomness(6, b);
     F *pe = (F *)malloc(nch * sizeof(F));
     for (size_t j = 0; j < nch; j++) { pe[j] = F0; for (int i = 0; i < 6; i++) pe[j] = f_add(pe[j], f_mul(b[i], Pe[i * nch + j])); }
     F *p2 = (F *)malloc((4 * (size_t)lgn + 8) * sizeof(F));

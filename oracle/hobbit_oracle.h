@@ -31,6 +31,7 @@ void orc_mimc_hash(const orc_F *in, const orc_F *k, orc_F *out);
 void orc_fft(orc_F *arr, int logn);
 /* RNG-driven (libc rand()/random(), same call order as the reference) */
 void orc_generate_randomness(int n, orc_F *out);
+void orc_inject_randomness(const orc_F *q, size_t n);   /* NULL: back to libc */
 /* E1/E2 */
 long long orc_expander_init_store(long long n);
 int  orc_expander_levels(long long n);

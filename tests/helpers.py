@@ -447,3 +447,43 @@ class RawABI:
         flag = ctypes.c_int(7)
         self.call("hb_any_nonzero", v, len(v), ctypes.byref(flag))
         return flag.value
+
+    # ---- W1/W2: streams from a trace (records: numpy structured array with the 80-byte tr_tuple layout) ----
+    def trace_load(self, records, split=3):
+        self.call("hb_trace_begin", 0)
+        done = ctypes.c_int(0)
+        n = len(records)
+        step = max(1, n // split)
+        for off in range(0, n, step):
+            part = np.ascontiguousarray(records[off:off + step])
+            self.call("hb_trace_push", part.ctypes.data_as(ctypes.c_void_p), len(part), ctypes.byref(done))
+        cnt = (ctypes.c_size_t * 3)()
+        self.call("hb_trace_finish", ctypes.byref(cnt, 0), ctypes.byref(cnt, 8), ctypes.byref(cnt, 16))
+        return tuple(cnt), done.value
+
+    def trace_streams(self, cs, a_w, b_w, has_lookups=0):
+        w, xy = fzeros(4 * cs), fzeros(8 * cs)
+        L, R, O, S = fzeros(cs), fzeros(cs), fzeros(cs), fzeros(cs)
+        self.call("hb_trace_witness", cs, w)
+        self.call("hb_trace_transcript", cs, ctypes.c_int(has_lookups), L, R, O, S)
+        self.call("hb_trace_wiring", cs, F(a_w), F(b_w), xy)
+        return w, L, R, O, S, xy
+
+
+TR_TUPLE = np.dtype([("value_o", np.uint64, 2), ("value_l", np.uint64, 2), ("value_r", np.uint64, 2), ("idx_o", np.int32), ("idx_l", np.int32),
+                     ("idx_r", np.int32), ("access_o", np.int32), ("access_l", np.int32), ("access_r", np.int32), ("type", np.uint8), ("pad", np.uint8, 7)])
+assert TR_TUPLE.itemsize == 80
+
+
+def synthetic_trace(rng, n, lookups=False):
+    """n records of a made-up trace (types 0/1/2, optionally 3..5) followed by the end marker and some garbage that must be ignored."""
+    t = np.zeros(n + 5, dtype=TR_TUPLE)
+    for f in ("value_o", "value_l", "value_r"):
+        t[f] = rng.integers(0, P61, size=(n + 5, 2), dtype=np.uint64)
+    for f in ("idx_o", "idx_l", "idx_r"):
+        t[f] = rng.integers(0, 1 << 20, size=n + 5)
+    for f in ("access_o", "access_l", "access_r"):
+        t[f] = rng.integers(0, 50, size=n + 5)
+    t["type"] = rng.choice([0, 1, 2, 3, 4, 5] if lookups else [0, 1, 2], size=n + 5)
+    t["type"][n] = 255
+    return t

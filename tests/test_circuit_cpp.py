@@ -1,0 +1,33 @@
+"""Circuit streams + the prove_circuit flow on an MLP (BASELINE config 3): tests/cpp/circ_test.cpp runs the unmodified
+reference (live producer thread, one circuit per process) next to the host mirror fed with ONE pass of the trace resident in HBM;
+every named stream, the witness commitment, the wiring product tree, gate consistency and the opening must agree (ps, RNG state)."""
+import os
+import subprocess
+
+import pytest
+
+from helpers import ROOT
+
+EMUL = os.path.join(ROOT, "oracle", "_ref", "circ_test_emul")
+GPU = os.path.join(ROOT, "oracle", "_ref", "circ_test")
+
+
+def _run(binary, *args, timeout=900):
+    p = subprocess.run([binary, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+    tail = "\n".join(l for l in p.stdout.splitlines() if l.startswith(("ok:", "FAIL", "CIRC", " ", "{", "circuit_size")))
+    print(tail[-6000:])
+    assert p.returncode == 0, tail[-3000:] + p.stderr[-2000:]
+    assert "CIRC: all identical" in p.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(EMUL), reason="oracle/_ref/circ_test_emul not prebuilt (needs /root/reference at build time)")
+@pytest.mark.parametrize("args", [(12, 64, 32, 16), (11, 128, 16, 8)])
+def test_mlp_circuit_host_logic_vs_reference(args):
+    _run(EMUL, *args)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(GPU), reason="oracle/_ref/circ_test not prebuilt (needs /root/reference at build time)")
+@pytest.mark.parametrize("args", [(12, 64, 32, 16), (11, 128, 16, 8), (14, 256, 64, 64, 16)])
+def test_mlp_circuit_gpu_vs_reference(args):
+    _run(GPU, *args)

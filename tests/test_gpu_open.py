@@ -107,3 +107,20 @@ def test_select_transpose_nonzero(abis):
     t[12345, 0] = 3
     g.call("hb_any_nonzero", __import__("ctypes").c_void_p(t.data_ptr()), 1 << 16, __import__("ctypes").byref(flag))
     assert flag.value == 1
+
+
+def test_trace_streams(abis):
+    """W1/W2: witness / transcript / wiring streams derived from a trace on the GPU vs the sequential restatement."""
+    from helpers import synthetic_trace
+    g, e = abis
+    rng = np.random.default_rng(8)
+    for n, cs, lookups in [(3000, 2048, False), (50000, 32768, True), (10, 16, False)]:
+        tr = synthetic_trace(rng, n, lookups)
+        while (tr["type"][:n] == 0).sum() > cs or (tr["type"][:n] != 0).sum() > cs:
+            tr = synthetic_trace(rng, n, lookups)
+        cg, dg = g.trace_load(tr)
+        ce, de = e.trace_load(tr)
+        assert cg == ce and dg == de == 1 and cg[0] == n
+        a_w, b_w = rand_field(rng, 1), rand_field(rng, 1)
+        for x, y in zip(g.trace_streams(cs, a_w, b_w, int(lookups)), e.trace_streams(cs, a_w, b_w, int(lookups))):
+            assert np.array_equal(x, y)
