@@ -12,7 +12,7 @@ EMUL = os.path.join(ROOT, "oracle", "_ref", "circ_test_emul")
 GPU = os.path.join(ROOT, "oracle", "_ref", "circ_test")
 
 
-def _run(binary, *args, timeout=900):
+def _run(binary, *args, timeout=300):
     p = subprocess.run([binary, *map(str, args)], capture_output=True, text=True, timeout=timeout)
     tail = "\n".join(l for l in p.stdout.splitlines() if l.startswith(("ok:", "FAIL", "CIRC", " ", "{", "circuit_size")))
     print(tail[-6000:])

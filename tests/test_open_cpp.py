@@ -11,7 +11,7 @@ EMUL = os.path.join(ROOT, "oracle", "_ref", "open_test_emul")
 GPU = os.path.join(ROOT, "oracle", "_ref", "open_test")
 
 
-def _run(binary, *args, timeout=900):
+def _run(binary, *args, timeout=300):
     p = subprocess.run([binary, *args], capture_output=True, text=True, timeout=timeout)
     tail = "\n".join(l for l in p.stdout.splitlines() if l.startswith(("ok:", "FAIL", "OPEN", " ")))
     print(tail[-6000:])
