@@ -82,9 +82,19 @@ class Context:
             raise HobbitError("hb_ctx_create failed (rc=%d): no CUDA device / bad ordinal — there is no CPU fallback" % rc)
         self.h = h
 
+    @classmethod
+    def from_handle(cls, handle):
+        """Wrap an existing hb_ctx* (e.g. the host mirror's: libhobbit_host.so hobbit_c_backend) without owning it."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.h = c_vp(handle)
+        self.borrowed = True
+        return self
+
     def close(self):
         if getattr(self, "h", None):
-            self.lib.hb_ctx_destroy(self.h)
+            if not getattr(self, "borrowed", False):
+                self.lib.hb_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -329,6 +339,12 @@ class Context:
         self._ck(self.lib.hb_commit_encode_chunks(self.h, _ptr(p), c_sz(nchunks), c_sz(B), int(trs), int(lin), _ptr(inner_out),
                                                   c_sz(leaf_parts), c_sz(first_chunk), c_sz(total_chunks)))
         return ret
+
+    def elastic_encode_groups(self, chunks, ngroups, B, trs, lin, inner_out, leaf_parts=1, first_group=0, total_groups=0):
+        """chunks: numpy F array or int device pointer (ngroups*4*B coefficients); inner_out: int device pointer or numpy uint8."""
+        c = chunks if isinstance(chunks, int) else _F(chunks)
+        self._ck(self.lib.hb_elastic_encode_groups(self.h, _ptr(c), c_sz(ngroups), c_sz(B), int(trs), int(lin), _ptr(inner_out),
+                                                   c_sz(leaf_parts), c_sz(first_group), c_sz(total_groups)))
 
     def md_chain(self, inner, nchunks, nleaves, leaves):
         """leaves: numpy (nleaves, 32) uint8 or int device pointer; updated in place."""

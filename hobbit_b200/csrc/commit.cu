@@ -347,6 +347,34 @@ extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nch
     return 0;
 }
 
+// Elastic_PC commit split for sharding: `ngroups` groups of 4 consecutive chunks -> inner digests of the 4B positions of each group
+extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t ngroups, size_t B, int trs, int linear_time, uint8_t *inner_out,
+                                        size_t leaf_parts, size_t first_group, size_t total_groups) {
+    if (ngroups == 0) return 0;
+    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_encode_groups: BUFFER_SPACE must be a power of two");
+    if (leaf_parts == 0) leaf_parts = 1;
+    if (total_groups == 0) { total_groups = ngroups; first_group = 0; }
+    const size_t cells = 4 * B;
+    if (cells % leaf_parts || first_group + ngroups > total_groups) HB_FAIL(ctx, "hb_elastic_encode_groups: bad leaf_parts / group range");
+    Staged p(ctx), in(ctx);
+    HB_TRY(p.in(chunks, ngroups * 4 * B * sizeof(F)));
+    HB_TRY(in.outbuf(inner_out, ngroups * cells * 32));
+    // a launch covers up to 1 GiB of encoded tensors (64 B per coefficient)
+    const size_t G = std::max<size_t>(1, std::min<size_t>(ngroups, ((size_t)1 << 30) / (16 * B * sizeof(F))));
+    F *T4; HB_CHECK(ctx, cudaMallocAsync(&T4, G * 16 * B * sizeof(F), ctx->stream));
+    for (size_t g0 = 0; g0 < ngroups; g0 += G) {
+        size_t ng = std::min(G, ngroups - g0);
+        int rc = tensorcode_dev(ctx, p.as<F>() + g0 * 4 * B, B, trs, linear_time, T4, 4 * ng, nullptr);
+        InnerLayout lay; lay.part_leaves = cells / leaf_parts; lay.chunks_total = ngroups; lay.chunk0 = g0;
+        if (!rc) rc = md_inner_stream4_dev(ctx, T4, cells, ng, in.as<uint8_t>(), lay);
+        if (rc) { cudaFreeAsync(T4, ctx->stream); return rc; }
+    }
+    cudaFreeAsync(T4, ctx->stream);
+    HB_TRY(in.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int hb_md_chain(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves) {
     Staged in(ctx), lv(ctx);
     HB_TRY(in.in(inner, nchunks * nleaves * 32));

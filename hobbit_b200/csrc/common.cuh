@@ -184,6 +184,7 @@ int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks,
 int md_inner_standard_dev(hb_ctx *ctx, const F *T, size_t rows, size_t cols, size_t nchunks, size_t chunk_stride, uint8_t *inner, InnerLayout lay);
 // leaf[p] <- H1(inner[c][p] | leaf[p]) for c = 0..nchunks-1 in order (the Merkle–Damgård chain over chunks)
 int md_chain_dev(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);
+int md_inner_stream4_dev(hb_ctx *ctx, const F *T4, size_t cells, size_t ngroups, uint8_t *inner, InnerLayout lay);
 int md_leaves_stream4_dev(hb_ctx *ctx, const F *c0, const F *c1, const F *c2, const F *T, size_t cells, uint8_t *leaves);
 int blake3_64_dev(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count);
 int merkle_tree_dev(hb_ctx *ctx, uint8_t *levels, size_t nleaves);

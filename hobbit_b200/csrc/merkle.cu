@@ -85,6 +85,23 @@ __global__ void __launch_bounds__(256) md_leaves_stream4_kernel(const F *__restr
     store_digest(leaves + p * 32, out);
 }
 
+// The same tuple WITHOUT the chunk-order-dependent half: inner[p] = H1(c0[p+1] | c1[p+1] | c2[p] | T[p]) of one group of 4 encoded chunks
+// (tensors contiguous at T4, 4B cells each).  The chain leaf <- H1(inner | leaf) over the groups is md_chain_kernel's job, so groups can be
+// encoded on different GPUs and only 32 B per position cross NVLink (hobbit_b200/dist.py).  grid.y = group.
+__global__ void __launch_bounds__(256) md_inner_stream4_kernel(const F *__restrict__ T4, size_t cells, uint8_t *__restrict__ inner, InnerLayout lay) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= cells) return;
+    const F *c0 = T4 + (size_t)blockIdx.y * 4 * cells, *c1 = c0 + cells, *c2 = c1 + cells, *T = c2 + cells;
+    uint32_t m[16], out[8];
+    F z = mkF(0, 0);
+    cell_words(p + 1 < cells ? c0[p + 1] : z, m);
+    cell_words(p + 1 < cells ? c1[p + 1] : z, m + 4);
+    cell_words(c2[p], m + 8);
+    cell_words(T[p], m + 12);
+    blake3_compress64(m, out);
+    store_digest(inner + lay.offset(blockIdx.y, p) * 32, out);
+}
+
 // MT_commit_Blake leaves: leaf i = H1(leafs[4i..4i+3])
 __global__ void __launch_bounds__(256) mt_leaves_kernel(const F *__restrict__ x, size_t nleaves, uint8_t *__restrict__ leaves) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,6 +175,10 @@ int md_chain_dev(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleav
 }
 int md_leaves_stream4_dev(hb_ctx *ctx, const F *c0, const F *c1, const F *c2, const F *T, size_t cells, uint8_t *leaves) {
     if (cells) HB_LAUNCH(ctx, md_leaves_stream4_kernel, blocks_for(cells, 256), 256, 0, c0, c1, c2, T, cells, leaves);
+    return 0;
+}
+int md_inner_stream4_dev(hb_ctx *ctx, const F *T4, size_t cells, size_t ngroups, uint8_t *inner, InnerLayout lay) {
+    if (cells && ngroups) HB_LAUNCH(ctx, md_inner_stream4_kernel, dim3(blocks_for(cells, 256), (unsigned)ngroups), 256, 0, T4, cells, inner, lay);
     return 0;
 }
 int merkle_tree_dev(hb_ctx *ctx, uint8_t *levels, size_t nleaves) {

@@ -43,6 +43,13 @@ class GpuBackend:
         self.ctx.commit_encode_chunks(src, nchunks, B, trs, lin, inner_out=inner.data_ptr(), leaf_parts=parts, first_chunk=first, total_chunks=total)
         return inner
 
+    def encode_groups(self, chunks, ngroups, B, trs, lin, first=0, parts=1, total=0):
+        """Elastic commit: groups [first, first+ngroups) of 4 chunks each -> inner digests [parts][ngroups][4B/parts][32]."""
+        inner = self.empty(parts, ngroups, 4 * B // parts, 32)
+        src = chunks + first * 4 * B * 16 if isinstance(chunks, int) else chunks[first * 4 * B:(first + ngroups) * 4 * B]
+        self.ctx.elastic_encode_groups(src, ngroups, B, trs, lin, inner.data_ptr(), parts, first, total)
+        return inner
+
     # torch (and NCCL) work is ordered on torch's streams, the library's on its own stream: every hand-over is a full
     # device synchronisation (each C-ABI call also synchronises its stream before returning).
     def chain(self, inner, leaves):
@@ -59,7 +66,14 @@ class GpuBackend:
         return lv
 
 
-def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None, groups=4, timing=None):
+def elastic_commit_sharded(backend, chunks_local, ngroups, B, trs, lin, group=None, groups=4, timing=None):
+    """Elastic_PC commit (Elastic_PC.cpp:174-285) sharded the same way: the unit is a GROUP of 4 consecutive chunks of B coefficients
+    (leaf[p] <- H1( H1(c0[p+1] | c1[p+1] | c2[p] | c3[p]) | leaf[p] ) over the groups in order, 4B leaf positions).
+    chunks_local: this rank's ngroups/G consecutive groups (4*B*ngroups/G coefficients).  Returns all (8B-1, 32) levels on every rank."""
+    return commit_standard_sharded(backend, chunks_local, ngroups, 4 * B, trs, lin, group=group, groups=groups, timing=timing, elastic_B=B)
+
+
+def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None, groups=4, timing=None, elastic_B=None):
     """poly_local: this rank's K/G consecutive chunks (chunk range [rank*K/G, (rank+1)*K/G)); numpy host array, int device
     pointer, or anything backend.encode_chunks accepts together with an element offset.
     Returns every Merkle level of the commitment as one (2B-1, 32) uint8 tensor on every rank (== MT_hashes, leaves first).
@@ -70,9 +84,13 @@ def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None, gro
     G = dist.get_world_size(group) if dist.is_initialized() else 1
     assert K % G == 0 and B % G == 0, "chunks and leaves must split evenly across ranks"
     kl, Bp = K // G, B // G
+    if elastic_B is None:
+        encode = lambda first, n, parts, total: backend.encode_chunks(poly_local, n, B, trs, lin, first, parts=parts, total=total)
+    else:                                                    # units are groups of 4 chunks, B is the number of leaf positions (4 * BUFFER_SPACE)
+        encode = lambda first, n, parts, total: backend.encode_groups(poly_local, n, elastic_B, trs, lin, first, parts=parts, total=total)
     t0 = time.perf_counter()
     if G == 1:
-        inner_all = backend.encode_chunks(poly_local, kl, B, trs, lin, 0).view(kl, B, 32)
+        inner_all = encode(0, kl, 1, 0).view(kl, B, 32)
     else:
         groups = max(1, min(groups, kl))
         while kl % groups:
@@ -81,7 +99,7 @@ def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None, gro
         recv = backend.empty(G, kl, Bp, 32)                      # [source rank][its local chunk][my leaf range] == global chunk order
         works = []
         for g in range(groups):
-            send = backend.encode_chunks(poly_local, kg, B, trs, lin, g * kg, parts=G, total=kl)   # [G, kg, Bp, 32]: slice h -> rank h
+            send = encode(g * kg, kg, G, kl)                                          # [G, kg, Bp, 32]: slice h -> rank h
             if dist.get_backend(group) == "nccl":
                 # receive straight into the final [source rank][chunk] slots: no staging copy
                 outs = [recv[h, g * kg:(g + 1) * kg] for h in range(G)]

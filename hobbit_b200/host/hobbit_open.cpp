@@ -558,6 +558,43 @@ static void recursive_prover_Spielman_stream_dev(const F *input, const F *M, siz
     shockwave_prove(C_f, P5.randomness[0], vt, ps); C_f = nullptr;
 }
 
+// Everything of `open` behind the stream pass: the shockwave / aux commitments of aggregate() (:334-414), the Merkle-path accounting, the
+// recursion.  agg: the aggregated vector (B elements, device); the queries are the global `I`.  Split out so that a sharded stream pass
+// (hobbit_b200/dist.py: every GPU aggregates its chunk range, partial aggregates summed over NVLink) can hand over to one GPU here.
+static void open_tail(const F *agg, size_t B, size_t trs, size_t nonzero_chunks, size_t mt_leaves, int mt_levels, double &vt, double &ps) {
+    const size_t cols = 2 * B / trs;
+    DV Mrs, aux; size_t nrc = 0, cw_pad = 0;
+    {
+        Trace t("  shockwave commits");
+        C_f = shockwave_commit_ptr(agg, B, 32);
+        if (linear_time) {                                                      // :338-414
+            std::vector<size_t> remaining = remaining_columns_of(I, trs);
+            nrc = remaining.size();
+            Mrs = DV(trs * cols);
+            CK(hb_rs_encode_rows(backend(), abi(agg), cols / 2, trs, abi(Mrs.p), lg2(cols)));
+            std::vector<uint64_t> rc64(remaining.begin(), remaining.end());
+            DV sel(trs * nrc), enc(2 * trs * nrc);
+            CK(hb_select_cols(backend(), abi(Mrs.p), trs, cols, cols, rc64.data(), nrc, abi(sel.p)));
+            CK(hb_encode_batch(backend(), abi(sel.p), abi(enc.p), (long long)trs, nrc));
+            cw_pad = next_pow2(nrc * 2 * trs);
+            aux = DV(cw_pad, true);
+            CK(hb_transpose(backend(), abi(enc.p), 2 * trs, nrc, abi(aux.p)));          // aux_commit[i][j] = encode(column i)[j]
+            printf("%d\n", (int)(nrc * 2 * trs));
+            C_c = shockwave_commit_ptr(aux.p, cw_pad, 32);
+        }
+    }
+    std::vector<bool> visited(mt_leaves * 2, false);
+    double MT_ps = 0.0;
+    for (size_t i = 0; i < I.size(); i++) mt_ps(mt_levels, mt_leaves, (I[i][1] / 4) * cols + I[i][0], visited, MT_ps);
+    ps += (double)(I.size() * nonzero_chunks * sizeof(F)) / 1024.0;          // reply[k] has one entry per non-zero chunk (:509-518)
+    {
+        Trace t("  recursion");
+        if (!linear_time) recursive_prover_RS_dev(agg, B, I, vt, ps);
+        else recursive_prover_Spielman_stream_dev(agg, Mrs.p, trs, cols, aux.p, nrc, cw_pad, I, vt, ps);
+    }
+    ps += MT_ps;
+}
+
 void open(stream_descriptor fd, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, double &vt, double &ps) {
     Trace tall("open (Elastic_PC) total");
     const size_t B = BUFFER_SPACE, trs = (size_t)tensor_row_size, cols = 2 * B / trs, K = fd.size / B;
@@ -590,39 +627,32 @@ void open(stream_descriptor fd, std::vector<F> x, std::vector<std::vector<_hash>
         }
         CK(hb_elastic_open_finish(backend(), abi(agg.p), abi(reply.p)));
     }
-    DV Mrs, aux; size_t nrc = 0, cw_pad = 0;
-    {
-        Trace t("  shockwave commits");
-        C_f = shockwave_commit_ptr(agg.p, B, 32);
-        if (linear_time) {                                                      // :338-414
-            std::vector<size_t> remaining = remaining_columns_of(I, trs);
-            nrc = remaining.size();
-            Mrs = DV(trs * cols);
-            CK(hb_rs_encode_rows(backend(), abi(agg.p), cols / 2, trs, abi(Mrs.p), lg2(cols)));
-            std::vector<uint64_t> rc64(remaining.begin(), remaining.end());
-            DV sel(trs * nrc), enc(2 * trs * nrc);
-            CK(hb_select_cols(backend(), abi(Mrs.p), trs, cols, cols, rc64.data(), nrc, abi(sel.p)));
-            CK(hb_encode_batch(backend(), abi(sel.p), abi(enc.p), (long long)trs, nrc));
-            cw_pad = next_pow2(nrc * 2 * trs);
-            aux = DV(cw_pad, true);
-            CK(hb_transpose(backend(), abi(enc.p), 2 * trs, nrc, abi(aux.p)));          // aux_commit[i][j] = encode(column i)[j]
-            printf("%d\n", (int)(nrc * 2 * trs));
-            C_c = shockwave_commit_ptr(aux.p, cw_pad, 32);
-        }
-    }
-    std::vector<bool> visited(Commitment_MT[0].size() * 2, false);
-    double MT_ps = 0.0;
-    for (size_t i = 0; i < I.size(); i++) mt_ps((int)Commitment_MT.size(), Commitment_MT[0].size(), (I[i][1] / 4) * cols + I[i][0], visited, MT_ps);
+    open_tail(agg.p, B, trs, nonzero_chunks, Commitment_MT[0].size(), (int)Commitment_MT.size(), vt, ps);
     for (auto &lv : Commitment_MT) { lv.clear(); std::vector<_hash>(lv).swap(lv); }                 // :693-698: the caller's tree is freed
     Commitment_MT.clear();
-    ps += (double)((size_t)queries * nonzero_chunks * sizeof(F)) / 1024.0;          // reply[k] has one entry per non-zero chunk (:509-518)
-    {
-        Trace t("  recursion");
-        if (!linear_time) recursive_prover_RS_dev(agg.p, B, I, vt, ps);
-        else recursive_prover_Spielman_stream_dev(agg.p, Mrs.p, trs, cols, aux.p, nrc, cw_pad, I, vt, ps);
-    }
-    ps += MT_ps;
     printf("PC : ps = %lf, vt = %lf\n", ps, vt);
 }
 
 }  // namespace hobbit
+
+// ---- flat C entry points for non-C++ callers of the host mirror (hobbit_b200/dist.py, tools/bench_elastic.py) ---------------------------
+extern "C" {
+void *hobbit_c_backend(int device) { hobbit::init_backend(device); return hobbit::backend(); }
+void hobbit_c_set_globals(size_t buffer_space, int trs, int lin) { hobbit::BUFFER_SPACE = buffer_space; hobbit::tensor_row_size = trs; hobbit::linear_time = lin != 0; }
+long long hobbit_c_expander_init_store(long long n) { return hobbit::expander_init_store(n); }
+void hobbit_c_generate_randomness(int n, hb_F *out) { std::vector<hobbit::F> v = hobbit::generate_randomness(n); memcpy(out, v.data(), (size_t)n * sizeof(hb_F)); }
+// the queries of Elastic_PC open (:649-655), drawn with rand() into the global I; col/row receive I[i][0], I[i][1]
+void hobbit_c_elastic_draw_queries(int queries, uint32_t *col, uint32_t *row) {
+    const size_t B = hobbit::BUFFER_SPACE, trs = (size_t)hobbit::tensor_row_size;
+    hobbit::I.resize(queries);
+    for (int i = 0; i < queries; i++) {
+        hobbit::I[i].push_back(rand() % (2 * B / trs)); hobbit::I[i].push_back(rand() % (2 * trs));
+        col[i] = (uint32_t)hobbit::I[i][0]; row[i] = (uint32_t)hobbit::I[i][1];
+    }
+}
+// Elastic_PC open behind the stream pass (see open_tail); returns ps (KB) accumulated into *ps
+void hobbit_c_elastic_open_tail(const hb_F *agg_dev, size_t nonzero_chunks, size_t mt_leaves, int mt_levels, double *ps) {
+    double vt = 0;
+    hobbit::open_tail(reinterpret_cast<const hobbit::F *>(agg_dev), hobbit::BUFFER_SPACE, (size_t)hobbit::tensor_row_size, nonzero_chunks, mt_leaves, mt_levels, vt, *ps);
+}
+}

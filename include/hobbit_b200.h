@@ -108,6 +108,11 @@ int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K, int trs, 
 int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out,
                             size_t leaf_parts, size_t first_chunk, size_t total_chunks);
 int hb_md_chain(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);
+/* The same split for Elastic_PC commit (Elastic_PC.cpp:174-285): `ngroups` groups of 4 consecutive chunks of B coefficients ->
+ * inner[g][p] = H1(c0[p+1] | c1[p+1] | c2[p] | T[p]) for the 4B positions of each group (same exchange layouts as above with 4B leaves);
+ * the leaves are then hb_md_chain over the groups in order, and hb_merkle_tree over 4B leaves. */
+int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t ngroups, size_t B, int trs, int linear_time, uint8_t *inner_out,
+                             size_t leaf_parts, size_t first_group, size_t total_groups);
 /* device pointer to the resident `_tensor` of the last hb_commit_standard (K*4*(N/K) elements), or NULL */
 const hb_F *hb_tensor_device(hb_ctx *ctx);
 /* _compute_aggregation_reply (Our_PC.cpp:291-305): reply[q*K + i] = _tensor[i][row[q]][col[q]] */

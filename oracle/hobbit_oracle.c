@@ -341,6 +341,20 @@ void orc_elastic_commit_stream(const F *stream, size_t N, size_t B, int trs, int
     create_tree((int)(4 * B), levels_out);
 }
 
+/* Elastic commit split for sharding: inner digests of `ngroups` groups of 4 chunks, plain [group][position] order */
+void orc_elastic_encode_groups(const F *chunks, size_t ngroups, size_t B, int trs, int lin, uint8_t *inner_out) {
+    size_t cells = 4 * B;
+    F *T = (F *)malloc(4 * cells * sizeof(F));
+    for (size_t g = 0; g < ngroups; g++) {
+        for (int c = 0; c < 4; c++) orc_compute_tensorcode(chunks + (g * 4 + c) * B, B, trs, lin, T + c * cells);
+        for (size_t p = 0; p < cells; p++) {
+            F q[4] = { p + 1 < cells ? T[p + 1] : F0, p + 1 < cells ? T[cells + p + 1] : F0, T[2 * cells + p], T[3 * cells + p] };
+            orc_blake3_hash((const uint8_t *)q, inner_out + (g * cells + p) * 32);
+        }
+    }
+    free(T);
+}
+
 /* ------------------------------------------------------------------ S9 ---
  * utils.cpp:251-296: eq table; step i uses r[size-1-i] (last variable = LSB) */
 void orc_precompute_beta(const F *r, int nr, F *B) {

@@ -77,6 +77,7 @@ void orc_elastic_open_front(const orc_F *stream, size_t nchunks, size_t B, int t
 void orc_sc3_round(const orc_F *v1, const orc_F *v2, const orc_F *v3, orc_F *o1, orc_F *o2, orc_F *o3, size_t L, const orc_F *rand, orc_F *coeffs4);
 /* C1 split for sharding: inner leaf digests of chunks, and the Merkle–Damgård chain over chunks */
 void orc_commit_encode_chunks(const orc_F *poly, size_t nchunks, size_t B, int trs, int lin, uint8_t *inner_out);
+void orc_elastic_encode_groups(const orc_F *chunks, size_t ngroups, size_t B, int trs, int lin, uint8_t *inner_out);
 void orc_md_chain(const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves);
 
 #ifdef __cplusplus

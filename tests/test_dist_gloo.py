@@ -34,6 +34,12 @@ class OracleBackend:
         # exchange layout [parts][nchunks][B/parts][32] (the CUDA kernel writes it directly)
         return torch.from_numpy(np.ascontiguousarray(inner.reshape(nchunks, parts, B // parts, 32).transpose(1, 0, 2, 3)))
 
+    def encode_groups(self, chunks, ngroups, B, trs, lin, first=0, parts=1, total=0):
+        inner = np.zeros((ngroups, 4 * B, 32), dtype=np.uint8)
+        src = np.ascontiguousarray(chunks[first * 4 * B:(first + ngroups) * 4 * B])
+        self.orc.fn("elastic_encode_groups")(_p(src), ctypes.c_size_t(ngroups), ctypes.c_size_t(B), trs, int(lin), _p(inner))
+        return torch.from_numpy(np.ascontiguousarray(inner.reshape(ngroups, parts, 4 * B // parts, 32).transpose(1, 0, 2, 3)))
+
     def chain(self, inner, leaves):
         i = np.ascontiguousarray(inner.numpy()); l = leaves.numpy()
         self.orc.fn("md_chain")(_p(i), ctypes.c_size_t(i.shape[0]), ctypes.c_size_t(i.shape[1]), _p(l))
@@ -64,6 +70,42 @@ def worker(rank, world, port, lin, K, B, trs, ret):
     if rank == 0:
         ret.put(int(t.item()))
     dist.destroy_process_group()
+
+
+def elastic_worker(rank, world, port, lin, ngroups, B, trs, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hobbit_b200.dist import elastic_commit_sharded
+    be = OracleBackend()
+    if lin:
+        srand(1); be.orc.expander_init_store(trs)
+    stream = rand_field(np.random.default_rng(78), ngroups * 4 * B, full=False)
+    stream[5 * B:6 * B] = 0                                   # an all-zero chunk (the reference skips its encode)
+    gl = ngroups // world
+    levels = elastic_commit_sharded(be, np.ascontiguousarray(stream[rank * gl * 4 * B:(rank + 1) * gl * 4 * B]), ngroups, B, trs, lin)
+    want = np.zeros((8 * B - 1, 32), dtype=np.uint8)
+    be.orc.fn("elastic_commit_stream")(_p(stream), ctypes.c_size_t(len(stream)), ctypes.c_size_t(B), trs, int(lin), _p(want))
+    ok = np.array_equal(levels.numpy(), want)
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,lin", [(2, 1), (4, 0)])
+def test_sharded_elastic_commit_gloo(world, lin):
+    """Elastic_PC commit sharded by groups of 4 chunks == the single-process restatement (every level)."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=elastic_worker, args=(r, world, port, lin, 4, 1 << 9, 16, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1
 
 
 @pytest.mark.parametrize("world,lin", [(2, 1), (2, 0), (4, 1)])
