@@ -139,6 +139,9 @@ int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks,
     // widest column block that fits; prefer <= ~100 KB tiles when the code is small so several CTAs share an SM
     if (cols % 32 == 0 && per_col * 32 <= 100 * 1024) return launch_encode<32>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 16 == 0 && per_col * 16 <= 100 * 1024) return launch_encode<16>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+    // Measured on B200 at n = 1024 (bench.py, ms per launch of 16 chunks): 8 columns per CTA (one 220 KB CTA per SM) 3.58; 4 columns (two
+    // CTAs per SM, max carveout) 3.62; 2 columns (four CTAs) 4.43; fetching each edge once per 8-lane group and passing it round with
+    // shuffles 5.01.  The kernel is bound by instruction issue (multiply-add chains + BLAKE3), not by occupancy or by the edge loads.
     if (cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 4 == 0 && per_col * 4 <= kMaxSmem) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 2 == 0 && per_col * 2 <= kMaxSmem) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);

@@ -107,7 +107,7 @@ def test_tensorcode(ctx, chk, lin, trs, n):
     assert np.array_equal(ctx.tensorcode(msg, trs, lin), chk.tensorcode(msg, trs, lin))
 
 
-@pytest.mark.parametrize("lin,trs,N,K", [(1, 16, 1 << 14, 4), (1, 64, 1 << 15, 2), (0, 16, 1 << 13, 4), (1, 16, 1 << 12, 1)])
+@pytest.mark.parametrize("lin,trs,N,K", [(1, 16, 1 << 14, 4), (1, 64, 1 << 15, 2), (0, 16, 1 << 13, 4), (1, 16, 1 << 12, 1), (1, 1024, 1 << 18, 2)])
 def test_commit_standard(ctx, chk, lin, trs, N, K):
     if lin:
         install_expander(ctx, chk, trs)
