@@ -23,19 +23,21 @@ static inline hb_F *abi(F *p) { return reinterpret_cast<hb_F *>(p); }
 size_t circuit_size = 0;                       // main.cpp:36
 F a_w, b_w;                                    // main.cpp:63
 bool has_lookups = false;                      // main.cpp:67
+std::vector<F> lookup_rand;                    // main.cpp:70 (4 values, drawn by prove_circuit after the witness commitment)
 static_assert(sizeof(tr_tuple) == 80, "tr_tuple must match the reference layout (Seval.h:4-9)");
 
 namespace {
 struct Resident { F *p = nullptr; size_t n = 0; void ensure(size_t want) { if (n != want) { if (p) hb_free_device(backend(), p); void *q; CK(hb_malloc_device(backend(), &q, want * sizeof(F))); p = (F *)q; n = want; } } };
-Resident g_witness, g_trL, g_trR, g_trO, g_trS, g_wiring;
-bool have_witness = false, have_transcript = false, have_wiring = false, tr_lookups = false;
+Resident g_witness, g_trL, g_trR, g_trO, g_trS, g_wiring, g_lkp_basic, g_lkp_wit;
+bool have_witness = false, have_transcript = false, have_wiring = false, tr_lookups = false, have_lkp_basic = false, have_lkp_wit = false;
 F wiring_a, wiring_b;
+std::vector<F> lkp_rand_basic, lkp_rand_wit;
 bool trace_loaded = false;
 }
 
 void trace_begin(size_t capacity_hint) {
     CK(hb_trace_begin(backend(), capacity_hint));
-    have_witness = have_transcript = have_wiring = trace_loaded = false;
+    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = false;
 }
 bool trace_append(const tr_tuple *buf, size_t n) {
     int done = 0;
@@ -79,10 +81,34 @@ static const F *wiring_dev() {
     return g_wiring.p;
 }
 
+static void need_lookup_rand() {
+    if (lookup_rand.size() < 4) { printf("hobbit_b200: lookup streams need lookup_rand (4 values, main.cpp:911)\n"); exit(-1); }
+}
+static const F *lookup_basic_dev() {
+    need_trace("lookup_basic"); need_lookup_rand();
+    if (!have_lkp_basic || lkp_rand_basic != lookup_rand) {
+        g_lkp_basic.ensure(2 * circuit_size);
+        CK(hb_trace_lookup_basic(backend(), circuit_size, abi(lookup_rand.data()), abi(g_lkp_basic.p)));
+        have_lkp_basic = true; lkp_rand_basic = lookup_rand;
+    }
+    return g_lkp_basic.p;
+}
+static const F *lookup_witness_dev() {
+    need_trace("lookup_witness_basic"); need_lookup_rand();
+    if (!have_lkp_wit || lkp_rand_wit != lookup_rand) {
+        g_lkp_wit.ensure(2 * circuit_size);
+        CK(hb_trace_lookup_witness(backend(), circuit_size, abi(lookup_rand.data()), abi(g_lkp_wit.p)));
+        have_lkp_wit = true; lkp_rand_wit = lookup_rand;
+    }
+    return g_lkp_wit.p;
+}
+
 // the whole logical stream in HBM, or nullptr when `fd` is not a circuit stream
 const F *resident_stream(const stream_descriptor &fd) {
     if (fd.name == "witness") return witness_dev();
     if (fd.name == "wiring_consistency_check_opt") return wiring_dev();
+    if (fd.name == "lookup_basic") return lookup_basic_dev();
+    if (fd.name == "lookup_witness_basic") return lookup_witness_dev();
     return nullptr;
 }
 
@@ -97,13 +123,23 @@ bool read_circuit_stream(stream_descriptor &fd, std::vector<F> &v, int size) {
         fd.pos = (fd.pos + 1) % (4 * circuit_size / size);
         return true;
     }
-    if (fd.name == "wiring_consistency_check_opt") {
-        const F *xy = wiring_dev();
+    if (fd.name == "wiring_consistency_check_opt" || fd.name == "lookup_basic") {           // two-half streams: X block | Y block per read
+        const bool wiring = fd.name == "wiring_consistency_check_opt";
+        const F *xy = wiring ? wiring_dev() : lookup_basic_dev();
+        const size_t half_len = wiring ? 4 * circuit_size : circuit_size;
         size_t h = (size_t)size / 2, off = fd.pos * h;
-        if (off + h > 4 * circuit_size) { printf("hobbit_b200: read past the end of stream 'wiring_consistency_check_opt'\n"); exit(-1); }
+        if (off + h > half_len) { printf("hobbit_b200: read past the end of stream '%s'\n", fd.name.c_str()); exit(-1); }
         CK(hb_memcpy(backend(), v.data(), xy + off, h * sizeof(F)));
-        CK(hb_memcpy(backend(), v.data() + h, xy + 4 * circuit_size + off, h * sizeof(F)));
-        fd.pos = (fd.pos + 1) % (4 * circuit_size / h);
+        CK(hb_memcpy(backend(), v.data() + h, xy + half_len + off, h * sizeof(F)));
+        fd.pos = (fd.pos + 1) % (half_len / h);
+        return true;
+    }
+    if (fd.name == "lookup_witness_basic") {
+        const F *w = lookup_witness_dev();
+        size_t off = fd.pos * (size_t)size;
+        if (off + size > 2 * circuit_size) { printf("hobbit_b200: read past the end of stream 'lookup_witness_basic'\n"); exit(-1); }
+        CK(hb_memcpy(backend(), v.data(), w + off, (size_t)size * sizeof(F)));
+        fd.pos = (fd.pos + 1) % (2 * circuit_size / size);
         return true;
     }
     return false;
@@ -126,7 +162,7 @@ void read_trace(stream_descriptor &fd, std::vector<F> &buff_L, std::vector<F> &b
 // for the batching of the degree-4 sumcheck (:877-880), generate_randomness(6) for the Peval combination (:958).
 void prove_gate_consistency(stream_descriptor tr, std::vector<F> r, double &vt, double &ps) {
     (void)vt;
-    if (has_lookups) { printf("hobbit_b200: prove_gate_consistency_lookups is the lookup variant (not built)\n"); exit(-1); }
+    if (has_lookups) { printf("hobbit_b200: with has_lookups call prove_gate_consistency_lookups\n"); exit(-1); }
     transcript_dev();
     const size_t cs = tr.size, B = BUFFER_SPACE, nch = cs / B;
     const int lgB = (int)std::log2((double)B), lgn = (int)std::log2((double)nch);
@@ -135,6 +171,21 @@ void prove_gate_consistency(stream_descriptor tr, std::vector<F> r, double &vt, 
     std::vector<F> out(nch + 6 * (size_t)lgB + 6 + 6 * nch + 4 * (size_t)lgn + 3);
     CK(hb_gate_consistency_stream(backend(), abi(g_trL.p), abi(g_trR.p), abi(g_trO.p), abi(g_trS.p), cs, B, abi(r.data()), abi(rnd.data()),
                                   abi(out.data()), &ps));
+}
+
+// prove_gate_consistency_lookups (sumcheck.cpp:503-794).  libc draws: generate_randomness(5) (:637), generate_randomness(8) (:770).
+void prove_gate_consistency_lookups(stream_descriptor tr, std::vector<F> r, double &vt, double &ps) {
+    (void)vt;
+    if (!has_lookups) { printf("hobbit_b200: prove_gate_consistency_lookups needs has_lookups\n"); exit(-1); }
+    need_lookup_rand();
+    transcript_dev();
+    const size_t cs = tr.size, B = BUFFER_SPACE, nch = cs / B;
+    const int lgB = (int)std::log2((double)B), lgn = (int)std::log2((double)nch);
+    std::vector<F> rnd = generate_randomness(5), b8 = generate_randomness(8);
+    rnd.insert(rnd.end(), b8.begin(), b8.end());
+    std::vector<F> out(nch + 6 * (size_t)lgB + 9 + 8 * nch + 4 * (size_t)lgn + 3);
+    CK(hb_gate_consistency_lookups_stream(backend(), abi(g_trL.p), abi(g_trR.p), abi(g_trO.p), abi(g_trS.p), cs, B, abi(r.data()), abi(lookup_rand.data()),
+                                          abi(rnd.data()), abi(out.data()), &ps));
 }
 
 }  // namespace hobbit

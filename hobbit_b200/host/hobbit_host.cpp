@@ -194,7 +194,9 @@ void init_commitment(bool mod) {                                                
     if (tensor_row_size == 0) tensor_row_size = 16;
 }
 void read_stream_PC(stream_descriptor &fd, F *v, int size) {                    // witness_stream.cpp:2356-2412, default branch only
-    if (fd.name == "witness") { std::vector<F> buf(size); read_stream(fd, buf, size); memcpy(v, buf.data(), (size_t)size * sizeof(F)); return; }   // :2357-2364
+    // :2357-2370: only "witness" is forwarded to read_stream.  Any other name — including "lookup_witness_basic", which prove_circuit
+    // commits (main.cpp:913) — falls through to the synthetic default stream below, exactly as in the reference.
+    if (fd.name == "witness") { std::vector<F> buf(size); read_stream(fd, buf, size); memcpy(v, buf.data(), (size_t)size * sizeof(F)); return; }
     if (fd.name == "PC_layer" || fd.name == "circuit") {
         printf("hobbit_b200: stream '%s' is not built (commit_layers / circuit description stream)\n", fd.name.c_str()); exit(-1);
     }
@@ -204,7 +206,7 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     if (fd.size / BUFFER_SPACE < 4) printf("Decrease buffer size %d\n", (int)(fd.size / BUFFER_SPACE));
     std::vector<F> buff(BUFFER_SPACE);
     CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
-    const F *res = resident_stream(fd);                                          // circuit streams: chunks are slices of the HBM-resident stream
+    const F *res = fd.name == "witness" ? resident_stream(fd) : nullptr;         // what read_stream_PC forwards (:2365-2370): slices of the HBM-resident stream
     for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++) {
         if (res) { CK(hb_elastic_push(backend(), (const hb_F *)(res + i * BUFFER_SPACE))); continue; }
         read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
@@ -305,14 +307,14 @@ mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input,
 void reset_stream(stream_descriptor &fd) { fd.pos = 0; fd.idx = 0; fd.stage = 0; fd.offset = 0; fd.finished = false; }   // witness_stream.cpp:228-234
 void read_stream(stream_descriptor &fd, std::vector<F> &v, int size) {                                                   // :2106-2353, default branch
     if (read_circuit_stream(fd, v, size)) return;
-    static const char *circuit_names[] = {"input", "circuit", "wiring_consistency_check", "lookup_basic", "lookup_witness_basic", "transcript_stream"};
+    static const char *circuit_names[] = {"input", "circuit", "wiring_consistency_check", "transcript_stream"};
     for (const char *n : circuit_names)
         if (fd.name == n) { printf("hobbit_b200: stream '%s' is not built (use read_trace for the gate transcript)\n", n); exit(-1); }
     for (int i = 0; i < size; i++) v[i] = F((i % 1024) + 1);
 }
 
 const F *stream_chunk(stream_descriptor &fd, size_t i, size_t B, std::vector<F> &buff) {
-    if (fd.name == "witness") return resident_stream(fd) + i * B;
+    if (fd.name == "witness" || fd.name == "lookup_witness_basic") return resident_stream(fd) + i * B;
     buff.resize(B);
     read_stream(fd, buff, (int)B);
     return buff.data();

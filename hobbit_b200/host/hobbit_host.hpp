@@ -161,6 +161,7 @@ struct tr_tuple {                              // Seval.h:4-9
 extern size_t circuit_size;                    // main.cpp:36
 extern F a_w, b_w;                             // main.cpp:63
 extern bool has_lookups;                       // main.cpp:67
+extern std::vector<F> lookup_rand;             // main.cpp:70
 // the consumer side of the producer hand-off (what read_tr does, main.cpp:283-300): call trace_append with each refilled tr[] buffer until
 // it returns true (type 255 seen); trace_end() sets and returns circuit_size (get_circuit_size, main.cpp:303-321)
 void trace_begin(size_t capacity_hint = 0);
@@ -170,6 +171,7 @@ const F *resident_stream(const stream_descriptor &fd);          // the whole log
 bool read_circuit_stream(stream_descriptor &fd, std::vector<F> &v, int size);
 void read_trace(stream_descriptor &fd, std::vector<F> &buff_L, std::vector<F> &buff_R, std::vector<F> &buff_O, std::vector<int> &buff_S);
 void prove_gate_consistency(stream_descriptor tr, std::vector<F> r, double &vt, double &ps);
+void prove_gate_consistency_lookups(stream_descriptor tr, std::vector<F> r, double &vt, double &ps);
 
 // sumcheck.h
 proof generate_2product_sumcheck_proof(std::vector<F> &v1, std::vector<F> &v2, F previous_r, double &vt, double &ps);

@@ -181,6 +181,12 @@ int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb_F *R, cons
 int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B,
                                const hb_F *r, const hb_F *rnd10, hb_F *out, double *ps);
 
+/* S8: prove_gate_consistency_lookups (sumcheck.cpp:503-794): as above with S = F(0) add / F(1) mul / F(2) lookup, lookup_rand2 = lookup_rand[0..1],
+ * rnd13 = generate_randomness(5) | generate_randomness(8).  out = R[cs/B] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add_L,add_R,mul,lkp,lkp_O,beta |
+ * Peval[8][cs/B] | flat 2-product proof (4*log2(cs/B)+3). */
+int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B,
+                                       const hb_F *r, const hb_F *lookup_rand2, const hb_F *rnd13, hb_F *out, double *ps);
+
 /* ---- S4/S6: streaming folding sumcheck with the witness stream resident in HBM (sumcheck.cpp:1093-1392, 1746-1915) --------- */
 /* xy: the stream in its logical two-half form [X | Y] (`total` elements; what read_stream emits as X-block | Y-block per read,
  * witness_stream.cpp:2276-2311).  Layer l is [seg_l(X) | seg_l(Y)] with 2^l-element segment products (read_mul_tree_data).
@@ -247,6 +253,13 @@ int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_del
 int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out);
 int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S);
 int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy);
+/* lookup streams (witness_stream.cpp:920-1053, 2198-2247); access = number of EARLIER lookups of the same table entry in the pass
+ * (table = type-3, entry = value_l for the range table (type 3), value_l + 256 value_r otherwise):
+ *   lookup_basic    2cs [X | Y]: per op record X = 1 + value_l + lr0 value_r + lr1 value_o + lr2 access + lr3 type on lookup records, 1 elsewhere;
+ *                                Y = X + lr2, or 1 where X == 1
+ *   lookup_witness  2cs        : per LOOKUP record (value_o + lr0 value_l + lr1 value_r, access), zero padded */
+int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand4, hb_F *xy);
+int hb_trace_lookup_witness(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand2, hb_F *out);
 
 #ifdef __cplusplus
 }

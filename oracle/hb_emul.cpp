@@ -342,6 +342,54 @@ int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *
     }
     return 0;
 }
+/* access_table semantics (witness_stream.cpp:920-1053): the count of EARLIER lookups of the same table entry in this pass */
+static std::vector<uint64_t> lookup_access_counts(const emu_tuple *t, size_t n) {
+    std::vector<uint64_t> acc(n, 0);
+    std::vector<std::vector<uint64_t>> table(256);
+    for (size_t i = 0; i < n; i++) if (t[i].type >= 3) {
+        size_t key = t[i].type == 3 ? t[i].value_l.re : t[i].value_l.re + 256 * t[i].value_r.re;
+        auto &tb = table[t[i].type - 3];
+        if (tb.size() <= key) tb.resize(key + 1, 0);
+        acc[i] = tb[key]++;
+    }
+    return acc;
+}
+int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand4, hb_F *xy) {
+    const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); const F *lr = cF(lookup_rand4);
+    std::vector<uint64_t> acc = lookup_access_counts(t, ctx->tr_n);
+    F *X = mF(xy), *Y = X + cs; const F one = mk(1);
+    for (size_t i = 0; i < 2 * cs; i++) X[i] = one;
+    size_t c = 0;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type > 0) {
+        if (t[i].type >= 3) {
+            F v = fadd(one, t[i].value_l);
+            v = fadd(v, fmul(lr[0], t[i].value_r)); v = fadd(v, fmul(lr[1], t[i].value_o));
+            v = fadd(v, fmul(lr[2], mk(acc[i]))); v = fadd(v, fmul(lr[3], mk(t[i].type)));
+            X[c] = v; Y[c] = (v.re == 1 && v.im == 0) ? v : fadd(v, lr[2]);
+        }
+        c++;
+    }
+    return 0;
+}
+int hb_trace_lookup_witness(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand2, hb_F *out) {
+    const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); const F *lr = cF(lookup_rand2);
+    std::vector<uint64_t> acc = lookup_access_counts(t, ctx->tr_n);
+    memset(out, 0, 2 * cs * sizeof(F));
+    size_t q = 0;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type >= 3) {
+        mF(out)[2 * q] = fadd(fadd(t[i].value_o, fmul(lr[0], t[i].value_l)), fmul(lr[1], t[i].value_r));
+        mF(out)[2 * q + 1] = mk(acc[i]);
+        q++;
+    }
+    return 0;
+}
+int hb_gate_consistency_lookups_stream(hb_ctx *, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B, const hb_F *r,
+                                       const hb_F *lookup_rand2, const hb_F *rnd13, hb_F *out, double *ps) {
+    orc_inject_randomness(cF(rnd13), 13);
+    *ps += orc_gate_consistency_lookups_stream(cF(L), cF(R), cF(O), cF(S), cs, B, cF(r), cF(lookup_rand2), mF(out));
+    orc_inject_randomness(nullptr, 0);
+    return 0;
+}
 int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy) {
     const emu_tuple *t = (const emu_tuple *)ctx->trace.data();
     std::vector<F> addr(4 * cs, mk(0)), val(4 * cs, mk(0)), freq(4 * cs, mk(0));

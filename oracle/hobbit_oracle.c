@@ -925,6 +925,159 @@ double orc_gate_consistency_stream(const F *L, const F *R, const F *O, const F *
     return ps;
 }
 
+/* ------------------------------------------------------------------ S8 ---
+ * prove_gate_consistency_lookups (sumcheck.cpp:503-794, has_lookups = true) on a resident transcript: L, R, O and the selector
+ * S (F(0) add, F(1) mul, F(2) lookup; read_trace with has_lookups).  lr = lookup_rand[0..1].  Per element the reference derives
+ *   gate_L = 1 / 0 / lr0,  gate_R = 1 / 0 / lr1,  gate_mul = 0 / 1 / 0,  gate_lkp = 0 / 0 / 1   for S = 0 / 1 / 2
+ *   lkp_O = lr0 L + lr1 R - O on lookup rows, 0 elsewhere
+ * (the in-place rewrites of buff_S to 3, -1, 4 at :568-586 select exactly these through compute3p/4p_error_terms, :382-432).
+ * libc draws: a = generate_randomness(5) after the streaming pass, b = generate_randomness(8) after the partial evaluations.
+ * out: R[nch] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add_L,add_R,mul,lkp,lkp_O,beta | Peval[8][nch] | P2 flat (4*log2 nch + 3). */
+static inline void s8_gates(F s, const F *lr, F *gL, F *gR, F *gM, F *gK) {
+    if (s.re == 0) { *gL = F1; *gR = F1; *gM = F0; *gK = F0; }
+    else if (s.re == 1) { *gL = F0; *gR = F0; *gM = F1; *gK = F0; }
+    else { *gL = lr[0]; *gR = lr[1]; *gM = F0; *gK = F1; }
+}
+static inline void err3(F b1, F gate, F f1, F f2, F fb, F be, F *K) {        /* compute3p_error_terms */
+    F t1 = f_add(f_mul(b1, f2), f_mul(gate, f1)), t2 = f_mul(b1, gate);
+    K[0] = f_add(K[0], f_add(f_mul(fb, t1), f_mul(f_mul(be, f1), f2)));
+    K[1] = f_add(K[1], f_add(f_mul(be, t1), f_mul(fb, t2)));
+    K[2] = f_add(K[2], f_mul(t2, be));
+}
+double orc_gate_consistency_lookups_stream(const F *L, const F *R, const F *O, const F *S, size_t cs, size_t B, const F *r, const F *lr, F *out) {
+    size_t nch = cs / B; int lgB = ilog2(B), lgn = ilog2(nch);
+    double ps = 0; size_t k = 0;
+    F *beta = (F *)malloc(B * sizeof(F));
+    orc_precompute_beta(r, lgB, beta);
+    F *fL = (F *)malloc(9 * B * sizeof(F)), *fR = fL + B, *fO = fR + B, *fAL = fO + B, *fAR = fAL + B, *fM = fAR + B, *fK = fM + B, *fKO = fK + B, *fB = fKO + B;
+    F Kf[5] = { F0, F0, F0, F0, F0 };               /* O, L, R, M, lkp */
+    for (size_t i = 0; i < B; i++) {
+        F gL, gR, gM, gK; s8_gates(S[i], lr, &gL, &gR, &gM, &gK);
+        fL[i] = L[i]; fR[i] = R[i]; fO[i] = O[i]; fAL[i] = gL; fAR[i] = gR; fM[i] = gM; fK[i] = gK; fB[i] = beta[i];
+        fKO[i] = gK.re ? f_sub(f_add(f_mul(lr[0], L[i]), f_mul(lr[1], R[i])), O[i]) : F0;
+        Kf[0] = f_add(Kf[0], f_mul(beta[i], fO[i]));
+        Kf[1] = f_add(Kf[1], f_mul(f_mul(beta[i], fL[i]), fAL[i]));
+        Kf[2] = f_add(Kf[2], f_mul(f_mul(beta[i], fR[i]), fAR[i]));
+        Kf[4] = f_add(Kf[4], f_mul(f_mul(beta[i], fKO[i]), fK[i]));
+        Kf[3] = f_add(Kf[3], f_mul(f_mul(f_mul(beta[i], fR[i]), fL[i]), fM[i]));
+    }
+    if (!f_eq(f_sub(f_sub(f_add(f_add(Kf[3], Kf[1]), Kf[2]), Kf[4]), Kf[0]), F0)) { printf("Error\n"); exit(-1); }
+    ps += 5 * 16 / 1024.0;
+    F *Rv = (F *)malloc(nch * sizeof(F)); size_t nR = 0; Rv[nR++] = F1;
+    F rand = F0;
+    for (size_t c = 1; c < nch; c++) {
+        const F *bL = L + c * B, *bR = R + c * B, *bO = O + c * B, *bS = S + c * B;
+        F KO[2] = { F0, F0 }, KL[3] = { F0, F0, F0 }, KR[3] = { F0, F0, F0 }, KK[3] = { F0, F0, F0 }, KM[4] = { F0, F0, F0, F0 };
+        for (size_t i = 0; i < B; i++) {
+            F gL, gR, gM, gK; s8_gates(bS[i], lr, &gL, &gR, &gM, &gK);
+            F bK = gK.re ? f_sub(f_add(f_mul(lr[0], bL[i]), f_mul(lr[1], bR[i])), bO[i]) : F0;
+            KO[0] = f_add(KO[0], f_add(f_mul(bO[i], fB[i]), f_mul(beta[i], fO[i])));
+            KO[1] = f_add(KO[1], f_mul(bO[i], beta[i]));
+            err3(bL[i], gL, fL[i], fAL[i], fB[i], beta[i], KL);
+            err3(bR[i], gR, fR[i], fAR[i], fB[i], beta[i], KR);
+            err3(bK, gK, fKO[i], fK[i], fB[i], beta[i], KK);
+            F t1 = f_add(f_mul(fL[i], bR[i]), f_mul(fR[i], bL[i])), t2 = f_add(f_mul(fB[i], gM), f_mul(fM[i], beta[i]));
+            F t3 = f_mul(bL[i], bR[i]), t4 = f_mul(gM, beta[i]), t5 = f_mul(fL[i], fR[i]), t6 = f_mul(fB[i], fM[i]);
+            KM[0] = f_add(KM[0], f_add(f_mul(t1, t6), f_mul(t2, t5)));
+            KM[1] = f_add(KM[1], f_add(f_add(f_mul(t1, t2), f_mul(t3, t6)), f_mul(t4, t5)));
+            KM[2] = f_add(KM[2], f_add(f_mul(t1, t4), f_mul(t2, t3)));
+            KM[3] = f_add(KM[3], f_mul(t3, t4));
+        }
+        if (!f_eq(f_sub(f_sub(f_add(f_add(KM[3], KL[2]), KR[2]), KK[2]), KO[1]), F0)) { printf("Error in gate consistency 1 : %d\n", (int)c); exit(-1); }
+        rand = mimc(KO[0], rand); rand = mimc(KO[1], rand); rand = mimc(KL[0], rand); rand = mimc(KL[1], rand); rand = mimc(KL[2], rand);
+        rand = mimc(KR[0], rand); rand = mimc(KR[1], rand); rand = mimc(KR[2], rand);
+        Rv[nR++] = rand;
+        F x1 = rand, x2 = f_mul(rand, x1), x3 = f_mul(rand, x2), x4 = f_mul(rand, x3);
+        Kf[0] = f_add(Kf[0], f_add(f_mul(x1, KO[0]), f_mul(x2, KO[1])));
+        Kf[4] = f_add(Kf[4], f_add(f_add(f_mul(x1, KK[0]), f_mul(x2, KK[1])), f_mul(x3, KK[2])));
+        Kf[1] = f_add(Kf[1], f_add(f_add(f_mul(x1, KL[0]), f_mul(x2, KL[1])), f_mul(x3, KL[2])));
+        Kf[2] = f_add(Kf[2], f_add(f_add(f_mul(x1, KR[0]), f_mul(x2, KR[1])), f_mul(x3, KR[2])));
+        Kf[3] = f_add(Kf[3], f_add(f_add(f_add(f_mul(x1, KM[0]), f_mul(x2, KM[1])), f_mul(x3, KM[2])), f_mul(x4, KM[3])));
+        ps += 15 * 16 / 1024.0;
+        F chk = F0;
+        for (size_t i = 0; i < B; i++) {
+            F gL, gR, gM, gK; s8_gates(bS[i], lr, &gL, &gR, &gM, &gK);
+            F bK = gK.re ? f_sub(f_add(f_mul(lr[0], bL[i]), f_mul(lr[1], bR[i])), bO[i]) : F0;
+            fAL[i] = f_add(fAL[i], f_mul(rand, gL)); fAR[i] = f_add(fAR[i], f_mul(rand, gR)); fM[i] = f_add(fM[i], f_mul(rand, gM)); fK[i] = f_add(fK[i], f_mul(rand, gK));
+            fL[i] = f_add(fL[i], f_mul(rand, bL[i])); fR[i] = f_add(fR[i], f_mul(rand, bR[i])); fO[i] = f_add(fO[i], f_mul(rand, bO[i]));
+            fKO[i] = f_add(fKO[i], f_mul(rand, bK)); fB[i] = f_add(fB[i], f_mul(rand, beta[i]));
+            chk = f_add(chk, f_mul(f_mul(f_mul(fB[i], fM[i]), fR[i]), fL[i]));
+        }
+        if (!f_eq(chk, Kf[3])) { printf("ERRRROR %d\n", (int)c); exit(-1); }
+    }
+    for (size_t i = 0; i < nch; i++) out[k++] = Rv[i];
+    F a[5]; prover_randomness(5, a);
+    F sum = f_add(f_add(f_add(f_mul(a[0], Kf[1]), f_mul(a[1], Kf[2])), f_add(f_mul(a[2], Kf[3]), f_mul(Kf[0], a[3]))), f_mul(Kf[4], a[4]));
+    F *srand_ = (F *)malloc((lgB + 1) * sizeof(F));
+    F *tabs[9] = { fAL, fAR, fM, fK, fL, fR, fO, fKO, fB };
+    for (int i = lgB - 1, q = 0; i >= 0; i--, q++) {
+        F p[5] = { F0, F0, F0, F0, F0 };
+        for (size_t j = 0; j < ((size_t)1 << i); j++) {
+            F x[9], d[9];
+            for (int t = 0; t < 9; t++) { x[t] = tabs[t][2 * j]; d[t] = f_sub(tabs[t][2 * j + 1], x[t]); }
+            /* q(X) = a2 mul L R + a0 addL L + a1 addR R + a4 lkp lkpO + a3 O  (degree 3), then times beta(X) */
+            F m0 = f_mul(a[2], x[2]), m1 = f_mul(a[2], d[2]);
+            F ml2 = f_mul(m1, d[4]), ml1 = f_add(f_mul(m1, x[4]), f_mul(m0, d[4])), ml0 = f_mul(m0, x[4]);
+            F q3 = f_mul(ml2, d[5]);
+            F q2 = f_add(f_mul(ml2, x[5]), f_mul(ml1, d[5]));
+            F q1 = f_add(f_mul(ml1, x[5]), f_mul(ml0, d[5]));
+            F q0 = f_mul(ml0, x[5]);
+            const int sel[3] = { 0, 1, 3 }, val[3] = { 4, 5, 7 }, wi[3] = { 0, 1, 4 };
+            for (int u = 0; u < 3; u++) {
+                F s0 = f_mul(a[wi[u]], x[sel[u]]), s1 = f_mul(a[wi[u]], d[sel[u]]);
+                q2 = f_add(q2, f_mul(s1, d[val[u]]));
+                q1 = f_add(q1, f_add(f_mul(s1, x[val[u]]), f_mul(s0, d[val[u]])));
+                q0 = f_add(q0, f_mul(s0, x[val[u]]));
+            }
+            q1 = f_add(q1, f_mul(a[3], d[6])); q0 = f_add(q0, f_mul(a[3], x[6]));
+            p[0] = f_add(p[0], f_mul(d[8], q3));
+            p[1] = f_add(p[1], f_add(f_mul(d[8], q2), f_mul(x[8], q3)));
+            p[2] = f_add(p[2], f_add(f_mul(d[8], q1), f_mul(x[8], q2)));
+            p[3] = f_add(p[3], f_add(f_mul(d[8], q0), f_mul(x[8], q1)));
+            p[4] = f_add(p[4], f_mul(x[8], q0));
+        }
+        for (int c = 0; c < 5; c++) { rand = mimc(p[c], rand); out[k++] = p[c]; }
+        out[k++] = rand;
+        {
+            F s = f_add(f_add(f_add(p[0], p[1]), f_add(p[2], p[3])), f_add(p[4], p[4]));
+            if (!f_eq(s, sum)) { printf("Error in gate consistency 2: %d\n", i); exit(-1); }
+        }
+        sum = f_add(f_mul(f_add(f_mul(f_add(f_mul(f_add(f_mul(p[0], rand), p[1]), rand), p[2]), rand), p[3]), rand), p[4]);
+        srand_[q] = rand;
+        ps += 5 * 16 / 1024.0;
+        for (size_t j = 0; j < ((size_t)1 << i); j++)
+            for (int t = 0; t < 9; t++) tabs[t][j] = f_add(tabs[t][2 * j], f_mul(rand, f_sub(tabs[t][2 * j + 1], tabs[t][2 * j])));
+    }
+    out[k++] = fL[0]; out[k++] = fR[0]; out[k++] = fO[0]; out[k++] = fAL[0]; out[k++] = fAR[0]; out[k++] = fM[0]; out[k++] = fK[0]; out[k++] = fKO[0]; out[k++] = fB[0];
+    F *beta1 = (F *)malloc(B * sizeof(F));
+    orc_precompute_beta(srand_, lgB, beta1);
+    F *Pe = (F *)calloc(8 * nch, sizeof(F));
+    for (size_t c = 0; c < nch; c++)
+        for (size_t j = 0; j < B; j++) {
+            F l = L[c * B + j], rr = R[c * B + j], o = O[c * B + j], gL, gR, gM, gK;
+            s8_gates(S[c * B + j], lr, &gL, &gR, &gM, &gK);
+            F bK = gK.re ? f_sub(f_add(f_mul(lr[0], l), f_mul(lr[1], rr)), o) : F0;
+            const F v[8] = { l, rr, o, gL, gR, gM, gK, bK };
+            for (int t = 0; t < 8; t++) Pe[t * nch + c] = f_add(Pe[t * nch + c], f_mul(beta1[j], v[t]));
+        }
+    for (size_t i = 0; i < 8 * nch; i++) out[k++] = Pe[i];
+    F b[8]; prover_randomness(8, b);
+    F *pe = (F *)malloc(nch * sizeof(F));
+    for (size_t j = 0; j < nch; j++) { pe[j] = F0; for (int i = 0; i < 8; i++) pe[j] = f_add(pe[j], f_mul(b[i], Pe[i * nch + j])); }
+    F *p2 = (F *)malloc((4 * (size_t)lgn + 8) * sizeof(F));
+    ps += orc_sumcheck2(Rv, pe, nch, &rand, p2);
+    ps += 5 * 16 / 1024.0;
+    {
+        const F fin[8] = { fL[0], fR[0], fO[0], fAL[0], fAR[0], fM[0], fK[0], fKO[0] };
+        F s2 = F0; for (int t = 0; t < 8; t++) s2 = f_add(s2, f_mul(fin[t], b[t]));
+        F qv = lgn ? f_add(f_add(p2[0], p2[1]), f_add(p2[2], p2[2])) : s2;
+        if (!f_eq(qv, s2)) { printf("Error in gate consistency 3\n"); exit(-1); }
+    }
+    for (int i = 0; i < 4 * lgn + 3; i++) out[k++] = p2[i];
+    free(beta); free(fL); free(Rv); free(srand_); free(beta1); free(Pe); free(pe); free(p2);
+    return ps;
+}
+
 /* O2 front (Elastic_PC.cpp:316-333 aggregate's axpy, :487-533 compute_aggregation_reply + update_reply :59-110):
  * stream = nchunks chunks of B elements; agg[j] = sum_i beta[i] stream[i][j]; reply[q*nchunks + i] = tensorcode(chunk i)[row[q]][col[q]]. */
 void orc_elastic_open_front(const F *stream, size_t nchunks, size_t B, int trs, int lin, const F *beta, const uint32_t *col, const uint32_t *row,

@@ -70,6 +70,9 @@ double orc_mul_tree_stream(const orc_F *xy, size_t total, int vectors, size_t B,
 void orc_gate_consistency_standard(const orc_F *L, const orc_F *R, const orc_F *O, const orc_F *add_gate, size_t n, const orc_F *r, orc_F *out);
 /* S7: prove_gate_consistency (sumcheck.cpp:796-981) on a resident transcript (L, R, O, S); out layout in hobbit_oracle.c */
 double orc_gate_consistency_stream(const orc_F *L, const orc_F *R, const orc_F *O, const orc_F *S, size_t cs, size_t B, const orc_F *r, orc_F *out);
+/* S8: prove_gate_consistency_lookups (sumcheck.cpp:503-794) on a resident transcript; S = F(0) add / F(1) mul / F(2) lookup; lr = lookup_rand[0..1] */
+double orc_gate_consistency_lookups_stream(const orc_F *L, const orc_F *R, const orc_F *O, const orc_F *S, size_t cs, size_t B, const orc_F *r,
+                                           const orc_F *lr, orc_F *out);
 /* O2 front: streaming aggregate + query replies */
 void orc_elastic_open_front(const orc_F *stream, size_t nchunks, size_t B, int trs, int lin, const orc_F *beta, const uint32_t *col,
                             const uint32_t *row, size_t queries, orc_F *agg, orc_F *reply);

@@ -4,6 +4,8 @@
 // of the trace uploaded to HBM.  Every named stream, every Merkle level, the product-tree outputs, ps and the libc RNG state must agree.
 // One circuit per process (the reference's producer thread never exits).  Built twice like open_test (GPU / CPU emulation).
 // usage: circ_test <log2 BUFFER_SPACE> <layer sizes...>      e.g. circ_test 12 64 32 16   (MLP, `pigeon 9 b b 1 n l0 l1 ...`)
+//        circ_test <log2 BUFFER_SPACE> aes <n> <d>           e.g. circ_test 19 aes 8 1    (`pigeon 5 19 8 1`, lookups; main.cpp:887-917)
+//        circ_test <log2 BUFFER_SPACE> sql <n> <d>           e.g. circ_test 19 sql 17 1   (`pigeon 6 19 17 1`)
 #include "../../hobbit_b200/host/hobbit_host.hpp"
 namespace hobbit { typedef F Fe; }
 #include "config_pc.hpp"
@@ -29,7 +31,9 @@ extern tr_tuple *tr;
 extern int BUFFER_SPACE_tr;
 extern size_t BUFFER_SPACE;
 extern bool has_lookups;
+extern vector<F> lookup_rand;
 void Seval_Oracle();
+void prove_gate_consistency_lookups(stream_descriptor tr, vector<F> r, double &vt, double &ps);
 void init_stream(int b, int n, int d);
 extern bool linear_time;
 extern int tensor_row_size;
@@ -49,11 +53,17 @@ int main(int argc, char **argv) {
     init_hash();
     hobbit::init_backend(0);
     mtx.lock(); mtx2.lock();                                       // main.cpp:1172-1174
-    fun = 9;
-    for (int i = 2; i < argc; i++) layer_size.push_back(atoi(argv[i]));
-    if (layer_size.empty()) layer_size = {64, 32, 16};
+    bool lookups = false; int n_arg = b, d_arg = 1;
+    if (argc > 2 && (!strcmp(argv[2], "aes") || !strcmp(argv[2], "sql"))) {
+        fun = !strcmp(argv[2], "aes") ? 5 : 6; lookups = true;
+        n_arg = argc > 3 ? atoi(argv[3]) : 8; d_arg = argc > 4 ? atoi(argv[4]) : 1;
+    } else {
+        fun = 9;
+        for (int i = 2; i < argc; i++) layer_size.push_back(atoi(argv[i]));
+        if (layer_size.empty()) layer_size = {64, 32, 16};
+    }
     std::thread t(Seval_Oracle); t.detach();
-    init_stream(b, b, 1);
+    init_stream(b, n_arg, d_arg);
     const size_t cs = circuit_size, B = BUFFER_SPACE;
     printf("circuit_size 2^%d, BUFFER_SPACE 2^%d\n", (int)log2(cs), (int)log2(B));
 
@@ -67,10 +77,11 @@ int main(int argc, char **argv) {
     size_t hcs = hobbit::trace_end();
     double t_trace = now() - t0;
     CHECK(hcs == cs, "circuit_size from the trace == get_circuit_size()");
-    hobbit::BUFFER_SPACE = B; hobbit::has_lookups = false; has_lookups = false;
+    hobbit::BUFFER_SPACE = B; hobbit::has_lookups = lookups; has_lookups = lookups;
 
     srand(7); a_w = random(); b_w = random();
     hobbit::a_w = hobbit::Fe(a_w.real, a_w.img); hobbit::b_w = hobbit::Fe(b_w.real, b_w.img);
+    if (lookups) { lookup_rand = generate_randomness(4); hobbit::lookup_rand = conv(lookup_rand); }
     double vt = 0, tr_ref[4] = {0, 0, 0, 0}, tr_gpu[4] = {0, 0, 0, 0};
 
     // ---- the named streams, element by element ---------------------------------------------------------------------------------------
@@ -93,6 +104,18 @@ int main(int argc, char **argv) {
             ok = ok && !memcmp(l.data(), hl.data(), B * 16) && !memcmp(r.data(), hr.data(), B * 16) && !memcmp(o.data(), ho.data(), B * 16) && s == hs;
         }
         CHECK(ok, "gate transcript via read_trace (L, R, O, selector)");
+        if (lookups) {
+            stream_descriptor fl; fl.name = "lookup_basic"; fl.size = 2 * cs; reset_stream(fl);
+            hobbit::stream_descriptor hfl; hfl.name = "lookup_basic"; hfl.size = 2 * cs;
+            ok = true;
+            for (size_t off = 0; off < 2 * cs; off += 2 * B) { read_stream(fl, w, (int)(2 * B)); hobbit::read_stream(hfl, hw, (int)(2 * B)); ok = ok && !memcmp(w.data(), hw.data(), 2 * B * 16); }
+            CHECK(ok, "stream \"lookup_basic\" (2 cs), blocks of 2 BUFFER_SPACE (X half | Y half), access counters");
+            stream_descriptor fq; fq.name = "lookup_witness_basic"; fq.size = 2 * cs; reset_stream(fq);
+            hobbit::stream_descriptor hfq; hfq.name = "lookup_witness_basic"; hfq.size = 2 * cs;
+            ok = true;
+            for (size_t off = 0; off < 2 * cs; off += B) { read_stream(fq, v, (int)B); hobbit::read_stream(hfq, hv, (int)B); ok = ok && !memcmp(v.data(), hv.data(), B * 16); }
+            CHECK(ok, "stream \"lookup_witness_basic\" (2 cs), blocks of BUFFER_SPACE");
+        }
     }
     // ---- commit(witness) ---------------------------------------------------------------------------------------------------------------
     vector<vector<_hash>> MT; vector<vector<hobbit::_hash>> hMT;
@@ -106,6 +129,16 @@ int main(int argc, char **argv) {
         vector<vector<_hash>> A = MT; vector<vector<hobbit::_hash>> Bm = hMT;
         A[0].back() = _hash(); memset(&Bm[0].back(), 0, 32);              // the reference's last leaf reads past its buffers
         CHECK(same_levels(A, Bm), "commit(witness): every Merkle level");
+    }
+    vector<vector<_hash>> MTl; vector<vector<hobbit::_hash>> hMTl;
+    if (lookups) {          // main.cpp:913: read_stream_PC does not know this name and commits its synthetic default stream; so does the mirror
+        stream_descriptor fd; fd.name = "lookup_witness_basic"; fd.size = 2 * cs; reset_stream(fd);
+        _hash comm; commit(fd, comm, MTl);
+        hobbit::stream_descriptor hfd; hfd.name = "lookup_witness_basic"; hfd.size = 2 * cs;
+        hobbit::_hash hcomm; hobbit::commit(hfd, hcomm, hMTl);
+        vector<vector<_hash>> A = MTl; vector<vector<hobbit::_hash>> Bm = hMTl;
+        A[0].back() = _hash(); memset(&Bm[0].back(), 0, 32);
+        CHECK(same_levels(A, Bm), "commit(lookup_witness_basic): every Merkle level");
     }
     // ---- prove_multiplication_tree_stream_shallow(wiring, 8 vectors) ---------------------------------------------------------------------
     {
@@ -122,14 +155,31 @@ int main(int argc, char **argv) {
         CHECK(rd == wr, "memory consistency holds: prod(read set) * prod(final) == prod(write set) * prod(init)");
         printf("      ps %f / %f KB\n", ps, hps);
     }
+    if (lookups) {          // main.cpp:916: the lookup argument's product tree, 2 vectors
+        stream_descriptor fd; fd.name = "lookup_basic"; fd.size = 2 * cs; reset_stream(fd);
+        hobbit::stream_descriptor hfd; hfd.name = "lookup_basic"; hfd.size = 2 * cs;
+        double ps = 0, hps = 0; vector<F> px;
+        srand(12); t0 = now(); vector<F> o = prove_multiplication_tree_stream_shallow(fd, 2, fd.size / 2, F(32), 5, px, 0, vt, ps); tr_ref[1] += now() - t0; int r1 = rand();
+        srand(12); t0 = now(); vector<hobbit::Fe> ho = hobbit::prove_multiplication_tree_stream_shallow(hfd, 2, (int)(hfd.size / 2), hobbit::Fe(32), 5, vector<hobbit::Fe>(), 0, vt, hps);
+        tr_gpu[1] += now() - t0; int r2 = rand();
+        bool ok = o.size() == ho.size() && ps == hps && r1 == r2;
+        for (size_t i = 0; ok && i < o.size(); i++) ok = o[i].real == ho[i].real && o[i].img == ho[i].img;
+        CHECK(ok, "lookup product tree: 2 products, ps, RNG state");
+        printf("      ps %f / %f KB\n", ps, hps);
+    }
     // ---- prove_gate_consistency(transcript) ----------------------------------------------------------------------------------------------
     {
         stream_descriptor fd; fd.name = "transcript_stream"; fd.size = cs; reset_stream(fd);
         hobbit::stream_descriptor hfd; hfd.name = "transcript_stream"; hfd.size = cs;
         double ps = 0, hps = 0;
-        srand(13); vector<F> r = generate_randomness((int)log2(cs)); t0 = now(); prove_gate_consistency(fd, r, vt, ps); tr_ref[2] = now() - t0; int r1 = rand();
-        srand(13); vector<hobbit::Fe> hr = hobbit::generate_randomness((int)log2(cs)); t0 = now(); hobbit::prove_gate_consistency(hfd, hr, vt, hps); tr_gpu[2] = now() - t0; int r2 = rand();
-        CHECK(ps == hps && r1 == r2, "prove_gate_consistency: ps, RNG state (the prover's own three identities hold on both sides)");
+        srand(13); vector<F> r = generate_randomness((int)log2(cs)); t0 = now();
+        if (lookups) prove_gate_consistency_lookups(fd, r, vt, ps); else prove_gate_consistency(fd, r, vt, ps);
+        tr_ref[2] = now() - t0; int r1 = rand();
+        srand(13); vector<hobbit::Fe> hr = hobbit::generate_randomness((int)log2(cs)); t0 = now();
+        if (lookups) hobbit::prove_gate_consistency_lookups(hfd, hr, vt, hps); else hobbit::prove_gate_consistency(hfd, hr, vt, hps);
+        tr_gpu[2] = now() - t0; int r2 = rand();
+        CHECK(ps == hps && r1 == r2, lookups ? "prove_gate_consistency_lookups: ps, RNG state (the prover's own identities hold on both sides)"
+                                             : "prove_gate_consistency: ps, RNG state (the prover's own three identities hold on both sides)");
         printf("      ps %f / %f KB\n", ps, hps);
     }
     // ---- open(witness) ---------------------------------------------------------------------------------------------------------------------
@@ -142,9 +192,18 @@ int main(int argc, char **argv) {
         CHECK(ps == hps && r1 == r2, "open(witness): ps, RNG state");
         printf("      ps %f / %f KB\n", ps, hps);
     }
-    printf("{\"workload\": \"MLP circuit 2^%d gates, BUFFER_SPACE 2^%d\", \"trace_upload_s\": %.4f, \"ref_s\": {\"commit\": %.4f, \"mul_tree\": %.4f, \"gate\": %.4f, \"open\": %.4f}, "
+    if (lookups) {          // main.cpp:919: the second open of the process (the global query vector I keeps the first call's positions)
+        stream_descriptor fd; fd.name = "lookup_witness_basic"; fd.size = 2 * cs; reset_stream(fd);
+        hobbit::stream_descriptor hfd; hfd.name = "lookup_witness_basic"; hfd.size = 2 * cs;
+        double ps = 0, hps = 0;
+        srand(19); vector<F> x = generate_randomness((int)log2(fd.size)); t0 = now(); open(fd, x, MTl, vt, ps); tr_ref[3] += now() - t0; int r1 = rand();
+        srand(19); vector<hobbit::Fe> hx = hobbit::generate_randomness((int)log2(hfd.size)); t0 = now(); hobbit::open(hfd, hx, hMTl, vt, hps); tr_gpu[3] += now() - t0; int r2 = rand();
+        CHECK(ps == hps && r1 == r2, "open(lookup_witness_basic): ps, RNG state");
+        printf("      ps %f / %f KB\n", ps, hps);
+    }
+    printf("{\"workload\": \"%s circuit 2^%d gates, BUFFER_SPACE 2^%d\", \"trace_upload_s\": %.4f, \"ref_s\": {\"commit\": %.4f, \"mul_tree\": %.4f, \"gate\": %.4f, \"open\": %.4f}, "
            "\"gpu_s\": {\"commit\": %.4f, \"mul_tree\": %.4f, \"gate\": %.4f, \"open\": %.4f}, \"identical\": %s}\n",
-           (int)log2(cs), (int)log2(B), t_trace, tr_ref[0], tr_ref[1], tr_ref[2], tr_ref[3], tr_gpu[0], tr_gpu[1], tr_gpu[2], tr_gpu[3], failures ? "false" : "true");
+           fun == 9 ? "MLP" : fun == 5 ? "AES" : "SQL", (int)log2(cs), (int)log2(B), t_trace, tr_ref[0], tr_ref[1], tr_ref[2], tr_ref[3], tr_gpu[0], tr_gpu[1], tr_gpu[2], tr_gpu[3], failures ? "false" : "true");
     printf(failures ? "CIRC: %d FAILURES\n" : "CIRC: all identical\n", failures);
     fflush(stdout);
     _exit(failures ? 1 : 0);                                          // the producer thread is still blocked on its mutex
