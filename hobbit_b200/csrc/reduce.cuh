@@ -74,7 +74,7 @@ __device__ __forceinline__ void grid_reduce(F (&acc)[NC], F *__restrict__ partia
 
 inline int ensure_scratch(hb_ctx *ctx) {
     if (!ctx->red) {
-        HB_CHECK(ctx, cudaMalloc(&ctx->red, (size_t)kMaxRedBlocks * 12 * sizeof(F)));
+        HB_CHECK(ctx, cudaMalloc(&ctx->red, (size_t)kMaxRedBlocks * 16 * sizeof(F)));
         HB_CHECK(ctx, cudaMalloc(&ctx->ticket, 2 * sizeof(unsigned)));
         HB_CHECK(ctx, cudaMemset(ctx->ticket, 0, 2 * sizeof(unsigned)));
         HB_CHECK(ctx, cudaHostAlloc(&ctx->mailbox, 64 * sizeof(F), cudaHostAllocMapped));

@@ -277,6 +277,152 @@ gs_peval_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__res
     }
 }
 
+// ---- S8: prove_gate_consistency_lookups (sumcheck.cpp:503-794) ---------------------------------------------------------------------
+// Nine fold tables: 0 add_L, 1 add_R, 2 mul, 3 lkp, 4 L, 5 R, 6 O, 7 lkp_O, 8 beta.  Everything a chunk contributes is derived on the fly
+// from (L, R, O, S) — S = 0 add / 1 mul / 2 lookup — and lookup_rand[0..1]:
+//   gate_L = 1 / 0 / lr0, gate_R = 1 / 0 / lr1, gate_mul = 0 / 1 / 0, gate_lkp = 0 / 0 / 1, lkp_O = lr0 L + lr1 R - O on lookup rows
+// (what the reference's in-place rewrites of buff_S to 3, -1, 4 select through compute3p/4p_error_terms, :568-586, :382-432).
+struct S8Row { F l, r, o, gL, gR, gM, gK, bK; };
+__device__ __forceinline__ S8Row s8_row(const F *L, const F *R, const F *O, const F *S, size_t i, F lr0, F lr1) {
+    S8Row x; x.l = L[i]; x.r = R[i]; x.o = O[i];
+    const u64 s = S[i].re;
+    const F one = mkF(1, 0), zero = mkF(0, 0);
+    x.gL = s == 0 ? one : s == 1 ? zero : lr0;
+    x.gR = s == 0 ? one : s == 1 ? zero : lr1;
+    x.gM = s == 1 ? one : zero;
+    x.gK = s >= 2 ? one : zero;
+    x.bK = s >= 2 ? fsub(fadd(fmul(lr0, x.l), fmul(lr1, x.r)), x.o) : zero;
+    return x;
+}
+struct S8Folds { F *t[9]; };
+// chunk 0: folds := chunk; Kf_O, Kf_L, Kf_R, Kf_M, Kf_lkp (:538-546)
+__global__ void __launch_bounds__(256)
+gl_init_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
+               S8Folds f, F lr0, F lr1, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[5] = {mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0)};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
+        S8Row x = s8_row(L, R, O, S, i, lr0, lr1); F b = beta[i];
+        f.t[0][i] = x.gL; f.t[1][i] = x.gR; f.t[2][i] = x.gM; f.t[3][i] = x.gK; f.t[4][i] = x.l; f.t[5][i] = x.r; f.t[6][i] = x.o; f.t[7][i] = x.bK; f.t[8][i] = b;
+        F bl = fmul(b, x.l), br = fmul(b, x.r);
+        acc[0] = fadd(acc[0], fmul(b, x.o));
+        acc[1] = fadd(acc[1], fmul(bl, x.gL));
+        acc[2] = fadd(acc[2], fmul(br, x.gR));
+        acc[3] = fadd(acc[3], fmul(fmul(br, x.l), x.gM));
+        acc[4] = fadd(acc[4], fmul(fmul(b, x.bK), x.gK));
+    }
+    grid_reduce<5>(acc, partial, ticket, result);
+}
+__device__ __forceinline__ void s8_err3(F b1, F gate, F f1, F f2, F fb, F be, F &k1, F &k2, F &k3) {
+    F t1 = fadd(fmul(b1, f2), fmul(gate, f1)), t2 = fmul(b1, gate);
+    k1 = fadd(k1, fadd(fmul(fb, t1), fmul(fmul(be, f1), f2)));
+    k2 = fadd(k2, fadd(fmul(be, t1), fmul(fb, t2)));
+    k3 = fadd(k3, fmul(t2, be));
+}
+// the 15 error terms of folding one more chunk: K1_O K2_O | K1..3_L | K1..3_R | K1..3_lkp | K1..4_M  (:560-588)
+__global__ void __launch_bounds__(256)
+gl_err_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
+              S8Folds f, F lr0, F lr1, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[15];
+#pragma unroll
+    for (int c = 0; c < 15; c++) acc[c] = mkF(0, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
+        S8Row x = s8_row(L, R, O, S, i, lr0, lr1); const F be = beta[i];
+        const F fAL = f.t[0][i], fAR = f.t[1][i], fM = f.t[2][i], fK = f.t[3][i], fL = f.t[4][i], fR = f.t[5][i], fO = f.t[6][i], fKO = f.t[7][i], fB = f.t[8][i];
+        acc[0] = fadd(acc[0], fadd(fmul(x.o, fB), fmul(be, fO)));
+        acc[1] = fadd(acc[1], fmul(x.o, be));
+        s8_err3(x.l, x.gL, fL, fAL, fB, be, acc[2], acc[3], acc[4]);
+        s8_err3(x.r, x.gR, fR, fAR, fB, be, acc[5], acc[6], acc[7]);
+        s8_err3(x.bK, x.gK, fKO, fK, fB, be, acc[8], acc[9], acc[10]);
+        F u1 = fadd(fmul(fL, x.r), fmul(fR, x.l)), u2 = fadd(fmul(fB, x.gM), fmul(fM, be));
+        F u3 = fmul(x.l, x.r), u4 = fmul(x.gM, be), u5 = fmul(fL, fR), u6 = fmul(fB, fM);
+        acc[11] = fadd(acc[11], fadd(fmul(u1, u6), fmul(u2, u5)));
+        acc[12] = fadd(acc[12], fadd(fadd(fmul(u1, u2), fmul(u3, u6)), fmul(u4, u5)));
+        acc[13] = fadd(acc[13], fadd(fmul(u1, u4), fmul(u2, u3)));
+        acc[14] = fadd(acc[14], fmul(u3, u4));
+    }
+    grid_reduce<15>(acc, partial, ticket, result);
+}
+__global__ void __launch_bounds__(256)
+gl_fold_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
+               S8Folds f, F lr0, F lr1, F rho, size_t B) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
+        S8Row x = s8_row(L, R, O, S, i, lr0, lr1);
+        const F v[9] = {x.gL, x.gR, x.gM, x.gK, x.l, x.r, x.o, x.bK, beta[i]};
+#pragma unroll
+        for (int t = 0; t < 9; t++) f.t[t][i] = fadd(f.t[t][i], fmul(rho, v[t]));
+    }
+}
+// degree-4 round polynomial of beta(X) * ( a2 mul L R + a0 add_L L + a1 add_R R + a4 lkp lkp_O + a3 O )   (:646-712)
+struct S8W { F a[5]; };
+template <int MODE>
+__global__ void __launch_bounds__(256)
+gatel_round_kernel(Tabs<9> t, size_t L, F r, S8W w, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+    F acc[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) acc[c] = mkF(0, 0);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
+        F x[9], d[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            F y;
+            if (MODE == FOLD_THEN_POLY) {
+                const F *p = t.in[k] + 4 * j;
+                F a = p[0], b = p[1], c = p[2], e = p[3];
+                x[k] = fold1(a, b, r); y = fold1(c, e, r);
+                t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y;
+            } else { x[k] = t.in[k][2 * j]; y = t.in[k][2 * j + 1]; }
+            d[k] = fsub(y, x[k]);
+        }
+        F m0 = fmul(w.a[2], x[2]), m1 = fmul(w.a[2], d[2]);
+        F ml2 = fmul(m1, d[4]), ml1 = fadd(fmul(m1, x[4]), fmul(m0, d[4])), ml0 = fmul(m0, x[4]);
+        F q3 = fmul(ml2, d[5]);
+        F q2 = fadd(fmul(ml2, x[5]), fmul(ml1, d[5]));
+        F q1 = fadd(fmul(ml1, x[5]), fmul(ml0, d[5]));
+        F q0 = fmul(ml0, x[5]);
+#define HB_S8_TERM(W, SEL, VAL) { F s0 = fmul(w.a[W], x[SEL]), s1 = fmul(w.a[W], d[SEL]);                                     \
+            q2 = fadd(q2, fmul(s1, d[VAL])); q1 = fadd(q1, fadd(fmul(s1, x[VAL]), fmul(s0, d[VAL]))); q0 = fadd(q0, fmul(s0, x[VAL])); }
+        HB_S8_TERM(0, 0, 4) HB_S8_TERM(1, 1, 5) HB_S8_TERM(4, 3, 7)
+#undef HB_S8_TERM
+        q1 = fadd(q1, fmul(w.a[3], d[6])); q0 = fadd(q0, fmul(w.a[3], x[6]));
+        acc[0] = fadd(acc[0], fmul(d[8], q3));
+        acc[1] = fadd(acc[1], fadd(fmul(d[8], q2), fmul(x[8], q3)));
+        acc[2] = fadd(acc[2], fadd(fmul(d[8], q1), fmul(x[8], q2)));
+        acc[3] = fadd(acc[3], fadd(fmul(d[8], q0), fmul(x[8], q1)));
+        acc[4] = fadd(acc[4], fmul(x[8], q0));
+    }
+    grid_reduce<5>(acc, partial, ticket, result);
+}
+// pass B (:737-768): per chunk the dot products of eq(sumcheck_rand) with L, R, O, gate_L, gate_R, gate_mul, gate_lkp, lkp_O;
+// grid (parts, nch), out[(c*parts+part)*8 + k]
+__global__ void __launch_bounds__(256)
+gl_peval_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta1,
+                F lr0, F lr1, size_t B, F *__restrict__ out) {
+    __shared__ F sred[8][8];
+    const size_t base = (size_t)blockIdx.y * B;
+    F a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = mkF(0, 0);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x) {
+        S8Row x = s8_row(L, R, O, S, base + j, lr0, lr1); const F b1 = beta1[j];
+        const F v[8] = {x.l, x.r, x.o, x.gL, x.gR, x.gM, x.gK, x.bK};
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fadd(a[k], fmul(b1, v[k]));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) a[k] = fadd(a[k], shfl_down_F(a[k], dd));
+        if (lane == 0) sred[warp][k] = a[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        F v = sred[0][threadIdx.x];
+        for (int wq = 1; wq < (int)(blockDim.x >> 5); wq++) v = fadd(v, sred[wq][threadIdx.x]);
+        out[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
+    }
+}
+
 // product-tree level: out[j] = in[2j] * in[2j+1]   (sumcheck.cpp:84-101)
 __global__ void __launch_bounds__(256) prod_level_kernel(const F *__restrict__ in, F *__restrict__ out, size_t n_out) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (size_t)gridDim.x * blockDim.x)
@@ -1027,5 +1173,116 @@ extern "C" int hb_sc3_round(hb_ctx *ctx, const hb_F *in1, const hb_F *in2, const
     F co[4];
     HB_TRY((launch_round<3, POLY_AND_FOLD, false>(ctx, t, L, fromabi(*rand), co)));
     for (int c = 0; c < 4; c++) coeffs4[c] = toabi(co[c]);
+    return 0;
+}
+
+// S8: prove_gate_consistency_lookups (sumcheck.cpp:503-794) on a transcript resident in HBM.  rnd13 = a[5] | b[8], lookup_rand2 = lookup_rand[0..1].
+// out: R[nch] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add_L,add_R,mul,lkp,lkp_O,beta | Peval[8][nch] | P2 flat proof (4*log2 nch + 3).
+extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B,
+                                                  const hb_F *r, const hb_F *lookup_rand2, const hb_F *rnd13, hb_F *out, double *ps) {
+    if (B < 2 || (B & (B - 1)) || cs < B || (cs & (cs - 1))) HB_FAIL(ctx, "hb_gate_consistency_lookups_stream: sizes must be powers of two, cs >= B >= 2");
+    HB_TRY(ensure_scratch(ctx));
+    const size_t nch = cs / B; const int lgB = ilog2(B), lgn = ilog2(nch);
+    Staged sl(ctx), sr(ctx), so(ctx), ss(ctx), srr(ctx);
+    HB_TRY(sl.in(L, cs * sizeof(F))); HB_TRY(sr.in(R, cs * sizeof(F))); HB_TRY(so.in(O, cs * sizeof(F))); HB_TRY(ss.in(S, cs * sizeof(F)));
+    HB_TRY(srr.in(r, lgB * sizeof(F)));
+    const F *dL = sl.as<F>(), *dR = sr.as<F>(), *dO = so.as<F>(), *dS = ss.as<F>();
+    const F lr0 = fromabi(lookup_rand2[0]), lr1 = fromabi(lookup_rand2[1]);
+    const size_t pps = B / 2 + B / 4 + 2;
+    F *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, (11 * B + 9 * pps + 64) * sizeof(F), ctx->stream));
+    F *beta = buf, *beta1 = buf + B, *pp = buf + 11 * B, *r_dev = pp + 9 * pps;
+    S8Folds f; for (int q = 0; q < 9; q++) f.t[q] = buf + (size_t)(2 + q) * B;
+    auto fail = [&](int rc) { cudaFreeAsync(buf, ctx->stream); return rc; };
+    int rc;
+    if ((rc = beta_dev(ctx, srr.as<F>(), lgB, beta))) return fail(rc);
+    const unsigned grid = grid_for(ctx, B);
+    F Kf[5];                                                    // Kf_O, Kf_L, Kf_R, Kf_M, Kf_lkp
+    HB_LAUNCH(ctx, gl_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, f, lr0, lr1, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    if ((rc = read_result(ctx, 5, Kf))) return fail(rc);
+    if (!fzero(fsub(fsub(fadd(fadd(Kf[3], Kf[1]), Kf[2]), Kf[4]), Kf[0]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error (gate consistency with lookups, first chunk)"); }
+    *ps += 5 * 16 / 1024.0;
+    std::vector<F> Rv; Rv.push_back(mkF(1, 0));
+    F rand = mkF(0, 0);
+    for (size_t c = 1; c < nch; c++) {
+        const F *bL = dL + c * B, *bR = dR + c * B, *bO = dO + c * B, *bS = dS + c * B;
+        F K[15];
+        HB_LAUNCH(ctx, gl_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, f, lr0, lr1, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+        if ((rc = read_result(ctx, 15, K))) return fail(rc);
+        if (!fzero(fsub(fsub(fadd(fadd(K[14], K[4]), K[7]), K[10]), K[1]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 1"); }
+        for (int q = 0; q < 8; q++) rand = h_mimc(K[q], rand);                          // only the O, L, R terms are hashed (:589-597)
+        Rv.push_back(rand);
+        F x1 = rand, x2 = h_fmul(rand, x1), x3 = h_fmul(rand, x2), x4 = h_fmul(rand, x3);
+        Kf[0] = fadd(Kf[0], fadd(h_fmul(x1, K[0]), h_fmul(x2, K[1])));
+        Kf[1] = fadd(Kf[1], fadd(fadd(h_fmul(x1, K[2]), h_fmul(x2, K[3])), h_fmul(x3, K[4])));
+        Kf[2] = fadd(Kf[2], fadd(fadd(h_fmul(x1, K[5]), h_fmul(x2, K[6])), h_fmul(x3, K[7])));
+        Kf[4] = fadd(Kf[4], fadd(fadd(h_fmul(x1, K[8]), h_fmul(x2, K[9])), h_fmul(x3, K[10])));
+        Kf[3] = fadd(Kf[3], fadd(fadd(fadd(h_fmul(x1, K[11]), h_fmul(x2, K[12])), h_fmul(x3, K[13])), h_fmul(x4, K[14])));
+        *ps += 15 * 16 / 1024.0;
+        HB_LAUNCH(ctx, gl_fold_kernel, grid, 256, 0, bL, bR, bO, bS, beta, f, lr0, lr1, rand, B);
+    }
+    size_t k = 0;
+    for (auto &x : Rv) out[k++] = toabi(x);
+    const F *a = (const F *)rnd13, *b = a + 5;
+    F sum = fadd(fadd(fadd(h_fmul(a[0], Kf[1]), h_fmul(a[1], Kf[2])), fadd(h_fmul(a[2], Kf[3]), h_fmul(Kf[0], a[3]))), h_fmul(Kf[4], a[4]));
+    const F *cur[9]; F *A9[9], *B9[9];
+    for (int q = 0; q < 9; q++) { cur[q] = f.t[q]; A9[q] = pp + (size_t)q * pps; B9[q] = A9[q] + B / 2 + 1; }
+    S8W w; for (int q = 0; q < 5; q++) w.a[q] = a[q];
+    std::vector<F> srnd;
+    for (int i = 0; i < lgB; i++) {
+        size_t Lp = B >> (i + 1);
+        F co[5];
+        Tabs<9> t;
+        for (int q = 0; q < 9; q++) { t.in[q] = cur[q]; t.out[q] = A9[q]; }
+        if (i == 0) { HB_LAUNCH(ctx, gatel_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev); }
+        else {
+            HB_LAUNCH(ctx, gatel_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev);
+            for (int q = 0; q < 9; q++) { cur[q] = A9[q]; std::swap(A9[q], B9[q]); }
+        }
+        if ((rc = read_result(ctx, 5, co))) return fail(rc);
+        for (int q = 0; q < 5; q++) { rand = h_mimc(co[q], rand); out[k++] = toabi(co[q]); }
+        out[k++] = toabi(rand);
+        F s01 = fadd(fadd(fadd(co[0], co[1]), fadd(co[2], co[3])), fadd(co[4], co[4]));
+        if (!feq(s01, sum)) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 2"); }
+        sum = fadd(h_fmul(fadd(h_fmul(fadd(h_fmul(fadd(h_fmul(co[0], rand), co[1]), rand), co[2]), rand), co[3]), rand), co[4]);
+        srnd.push_back(rand);
+        *ps += 5 * 16 / 1024.0;
+    }
+    F fin[9];
+    {
+        Tabs<9> t;
+        for (int q = 0; q < 9; q++) { t.in[q] = cur[q]; t.out[q] = A9[q]; }
+        if ((rc = launch_round<9, FOLD_ONLY, false>(ctx, t, 1, rand, nullptr))) return fail(rc);
+        if ((rc = fetch_heads(ctx, A9, 9, fin))) return fail(rc);
+    }
+    // final L, R, O, add_L, add_R, mul, lkp, lkp_O, beta
+    const F fo[9] = {fin[4], fin[5], fin[6], fin[0], fin[1], fin[2], fin[3], fin[7], fin[8]};
+    for (int q = 0; q < 9; q++) out[k++] = toabi(fo[q]);
+    HB_CHECK(ctx, cudaMemcpyAsync(r_dev, srnd.data(), lgB * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = beta_dev(ctx, r_dev, lgB, beta1))) return fail(rc);
+    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((B + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nch + 1));
+    F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, nch * parts * 8 * sizeof(F), ctx->stream));
+    HB_LAUNCH(ctx, gl_peval_kernel, dim3(parts, (unsigned)nch), 256, 0, dL, dR, dO, dS, beta1, lr0, lr1, B, pe_dev);
+    std::vector<F> pe(nch * parts * 8);
+    HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(pe_dev, ctx->stream);
+    cudaFreeAsync(buf, ctx->stream);
+    std::vector<F> Pe(8 * nch, mkF(0, 0));
+    for (size_t c = 0; c < nch; c++)
+        for (unsigned q = 0; q < parts; q++) for (int t = 0; t < 8; t++) Pe[t * nch + c] = fadd(Pe[t * nch + c], pe[((c * parts + q) * 8) + t]);
+    for (auto &x : Pe) out[k++] = toabi(x);
+    std::vector<F> pv(nch, mkF(0, 0));
+    for (size_t j = 0; j < nch; j++) for (int i = 0; i < 8; i++) pv[j] = fadd(pv[j], h_fmul(b[i], Pe[i * nch + j]));
+    std::vector<hb_F> p2(4 * (size_t)lgn + 8);
+    hb_F rabi = toabi(rand);
+    HB_TRY(hb_sumcheck2(ctx, (const hb_F *)Rv.data(), (const hb_F *)pv.data(), nch, &rabi, p2.data(), ps));
+    *ps += 5 * 16 / 1024.0;
+    F s2 = mkF(0, 0);
+    for (int q = 0; q < 8; q++) s2 = fadd(s2, h_fmul(fo[q], b[q]));
+    if (lgn) {
+        F qv = fadd(fadd(fromabi(p2[0]), fromabi(p2[1])), fadd(fromabi(p2[2]), fromabi(p2[2])));
+        if (!feq(qv, s2)) HB_FAIL(ctx, "Error in gate consistency 3");
+    }
+    for (int i = 0; i < 4 * lgn + 3; i++) out[k++] = p2[i];
     return 0;
 }

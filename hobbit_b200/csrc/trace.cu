@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace hb {
 
@@ -77,6 +78,59 @@ trace_wiring_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__
         X[p] = x0; X[p + 1] = x1; X[p + 2] = x2;
         Y[p] = feq(x0, one) ? x0 : fadd(x0, b_w); Y[p + 1] = feq(x1, one) ? x1 : fadd(x1, b_w); Y[p + 2] = feq(x2, one) ? x2 : fadd(x2, b_w);
     }
+}
+// ---- lookup streams (witness_stream.cpp:920-1053, 2198-2247) -------------------------------------------------------------------------
+// The reference threads a mutable access_table through the pass: a lookup record carries the number of EARLIER lookups of the same table
+// entry.  On the GPU that is the rank of the record among equal (table, entry) keys in trace order: a stable radix sort of the keys,
+// a max-scan of the run starts, and a scatter of (position - run start) back to trace order.
+__global__ void __launch_bounds__(256)
+lookup_keys_kernel(const TrTuple *__restrict__ tr, size_t n, unsigned long long *__restrict__ keys, unsigned *__restrict__ idx, unsigned *__restrict__ is_lkp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrTuple &t = tr[i];
+    const bool lk = t.type >= 3 && t.type != 255;
+    unsigned long long entry = t.type == 3 ? t.value_l.re : t.value_l.re + 256ull * t.value_r.re;
+    keys[i] = lk ? (((unsigned long long)t.type << 40) | (entry & ((1ull << 40) - 1))) : ~0ull;
+    idx[i] = (unsigned)i;
+    is_lkp[i] = lk ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) run_start_kernel(const unsigned long long *__restrict__ keys, size_t n, unsigned *__restrict__ start) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    start[i] = (i == 0 || keys[i] != keys[i - 1]) ? (unsigned)i : 0u;
+}
+__global__ void __launch_bounds__(256)
+access_scatter_kernel(const unsigned *__restrict__ idx_sorted, const unsigned *__restrict__ start, size_t n, unsigned *__restrict__ access) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    access[idx_sorted[i]] = (unsigned)i - start[i];
+}
+struct MaxOp { __device__ __forceinline__ unsigned operator()(unsigned a, unsigned b) const { return a > b ? a : b; } };
+// "lookup_basic": X = 1 + value_l + lr0 value_r + lr1 value_o + lr2 access + lr3 type at the op rank of a lookup record (1 elsewhere), Y = X + lr2
+__global__ void __launch_bounds__(256)
+lookup_basic_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__restrict__ op_pos, const unsigned *__restrict__ access,
+                    F lr0, F lr1, F lr2, F lr3, F *__restrict__ X, F *__restrict__ Y) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrTuple &t = tr[i];
+    if (t.type < 3 || t.type == 255) return;
+    F v = fadd(mkF(1, 0), t.value_l);
+    v = fadd(v, fmul(lr0, t.value_r)); v = fadd(v, fmul(lr1, t.value_o));
+    v = fadd(v, fmul(lr2, mkF(access[i], 0))); v = fadd(v, fmul(lr3, mkF(t.type, 0)));
+    const size_t p = op_pos[i];
+    X[p] = v; Y[p] = feq(v, mkF(1, 0)) ? v : fadd(v, lr2);
+}
+// "lookup_witness_basic": (value_o + lr0 value_l + lr1 value_r, access) at the rank of the record among the lookup records
+__global__ void __launch_bounds__(256)
+lookup_witness_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__restrict__ lkp_pos, const unsigned *__restrict__ access,
+                      F lr0, F lr1, F *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrTuple &t = tr[i];
+    if (t.type < 3 || t.type == 255) return;
+    const size_t q = lkp_pos[i];
+    out[2 * q] = fadd(fadd(t.value_o, fmul(lr0, t.value_l)), fmul(lr1, t.value_r));
+    out[2 * q + 1] = mkF(access[i], 0);
 }
 __global__ void __launch_bounds__(256) fill_kernel(F *__restrict__ v, size_t n, F x) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] = x;
@@ -196,6 +250,68 @@ extern "C" int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb
     HB_LAUNCH(ctx, fill_kernel, (unsigned)std::min<size_t>((8 * cs + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, X, 8 * cs, mkF(1, 0));
     if (t.n) HB_LAUNCH(ctx, trace_wiring_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, t.pos + 3 * t.n, cs,
                        mkF(a_w->real, a_w->img), mkF(b_w->real, b_w->img), X, Y);
+    HB_TRY(so.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// access counters + rank among lookup records; caller frees *scratch with cudaFreeAsync
+static int lookup_index(hb_ctx *ctx, unsigned **access, unsigned **lkp_pos, void **scratch) {
+    TraceState &t = ctx->trace;
+    const size_t n = std::max<size_t>(t.n, 1);
+    // layout: keys[n] keys_sorted[n] (u64) | idx[n] idx_sorted[n] start[n] access[n] is_lkp[n] lkp_pos[n] (u32)
+    char *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, n * (2 * 8 + 6 * 4), ctx->stream));
+    unsigned long long *keys = (unsigned long long *)buf, *keys_s = keys + n;
+    unsigned *idx = (unsigned *)(keys_s + n), *idx_s = idx + n, *start = idx_s + n, *acc = start + n, *is_lkp = acc + n, *lpos = is_lkp + n;
+    *scratch = buf; *access = acc; *lkp_pos = lpos;
+    if (!t.n) return 0;
+    const unsigned g = (unsigned)((t.n + 255) / 256);
+    HB_LAUNCH(ctx, lookup_keys_kernel, g, 256, 0, (const TrTuple *)t.tuples, t.n, keys, idx, is_lkp);
+    size_t b1 = 0, b2 = 0, b3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_s, idx, idx_s, (int)t.n, 0, 48, ctx->stream);
+    cub::DeviceScan::InclusiveScan(nullptr, b2, start, start, MaxOp(), (int)t.n, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, b3, is_lkp, lpos, (int)t.n, ctx->stream);
+    void *tmp; HB_CHECK(ctx, cudaMallocAsync(&tmp, std::max(b1, std::max(b2, b3)), ctx->stream));
+    HB_CHECK(ctx, cub::DeviceRadixSort::SortPairs(tmp, b1, keys, keys_s, idx, idx_s, (int)t.n, 0, 48, ctx->stream));      // stable: trace order inside a run
+    HB_LAUNCH(ctx, run_start_kernel, g, 256, 0, keys_s, t.n, start);
+    HB_CHECK(ctx, cub::DeviceScan::InclusiveScan(tmp, b2, start, start, MaxOp(), (int)t.n, ctx->stream));
+    HB_LAUNCH(ctx, access_scatter_kernel, g, 256, 0, idx_s, start, t.n, acc);
+    HB_CHECK(ctx, cub::DeviceScan::ExclusiveSum(tmp, b3, is_lkp, lpos, (int)t.n, ctx->stream));
+    ctx->launches += 3;
+    cudaFreeAsync(tmp, ctx->stream);
+    return 0;
+}
+
+extern "C" int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand4, hb_F *xy) {
+    HB_TRY(trace_check(ctx, cs, "hb_trace_lookup_basic"));
+    TraceState &t = ctx->trace;
+    Staged so(ctx);
+    HB_TRY(so.outbuf(xy, 2 * cs * sizeof(F)));
+    F *X = so.as<F>(), *Y = X + cs;
+    HB_LAUNCH(ctx, fill_kernel, (unsigned)std::min<size_t>((2 * cs + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, X, 2 * cs, mkF(1, 0));
+    unsigned *access, *lpos; void *scratch;
+    HB_TRY(lookup_index(ctx, &access, &lpos, &scratch));
+    const hb_F *lr = lookup_rand4;
+    if (t.n) HB_LAUNCH(ctx, lookup_basic_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, access,
+                       mkF(lr[0].real, lr[0].img), mkF(lr[1].real, lr[1].img), mkF(lr[2].real, lr[2].img), mkF(lr[3].real, lr[3].img), X, Y);
+    cudaFreeAsync(scratch, ctx->stream);
+    HB_TRY(so.finish());
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hb_trace_lookup_witness(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand2, hb_F *out) {
+    HB_TRY(trace_check(ctx, cs, "hb_trace_lookup_witness"));
+    TraceState &t = ctx->trace;
+    Staged so(ctx);
+    HB_TRY(so.outbuf(out, 2 * cs * sizeof(F)));
+    HB_CHECK(ctx, cudaMemsetAsync(so.dev, 0, 2 * cs * sizeof(F), ctx->stream));
+    unsigned *access, *lpos; void *scratch;
+    HB_TRY(lookup_index(ctx, &access, &lpos, &scratch));
+    const hb_F *lr = lookup_rand2;
+    if (t.n) HB_LAUNCH(ctx, lookup_witness_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, lpos, access,
+                       mkF(lr[0].real, lr[0].img), mkF(lr[1].real, lr[1].img), so.as<F>());
+    cudaFreeAsync(scratch, ctx->stream);
     HB_TRY(so.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -469,6 +469,27 @@ class RawABI:
         self.call("hb_trace_wiring", cs, F(a_w), F(b_w), xy)
         return w, L, R, O, S, xy
 
+    def trace_lookup_streams(self, cs, lookup_rand4):
+        lb, lw = fzeros(2 * cs), fzeros(2 * cs)
+        self.call("hb_trace_lookup_basic", cs, F(lookup_rand4), lb)
+        self.call("hb_trace_lookup_witness", cs, F(lookup_rand4), lw)
+        return lb, lw
+
+    def binop(self, op, a, b):
+        a, b = F(a), F(b)
+        c = np.empty_like(a)
+        self.call("hb_field_binop", ctypes.c_int(op), a, b, c, len(a))
+        return c
+
+    def gate_consistency_lookups(self, L, R, O, S, B, r, lookup_rand2, rnd13):
+        L, R, O, S = F(L), F(R), F(O), F(S)
+        cs = len(L); nch = cs // B
+        lgB, lgn = int(np.log2(B)), int(np.log2(nch))
+        out = fzeros(nch + 6 * lgB + 9 + 8 * nch + 4 * lgn + 3)
+        ps = ctypes.c_double(0)
+        self.call("hb_gate_consistency_lookups_stream", L, R, O, S, cs, B, F(r), F(lookup_rand2), F(rnd13), out, ctypes.byref(ps))
+        return out, ps.value
+
 
 TR_TUPLE = np.dtype([("value_o", np.uint64, 2), ("value_l", np.uint64, 2), ("value_r", np.uint64, 2), ("idx_o", np.int32), ("idx_l", np.int32),
                      ("idx_r", np.int32), ("access_o", np.int32), ("access_l", np.int32), ("access_r", np.int32), ("type", np.uint8), ("pad", np.uint8, 7)])
@@ -486,4 +507,10 @@ def synthetic_trace(rng, n, lookups=False):
         t[f] = rng.integers(0, 50, size=n + 5)
     t["type"] = rng.choice([0, 1, 2, 3, 4, 5] if lookups else [0, 1, 2], size=n + 5)
     t["type"][n] = 255
+    if lookups:                      # table entries are small integers (value_l, or value_l + 256 value_r): many repeats -> access counters
+        lk = t["type"] >= 3
+        t["value_l"][lk] = 0
+        t["value_r"][lk] = 0
+        t["value_l"][lk, 0] = rng.integers(0, 40, size=int(lk.sum()))
+        t["value_r"][lk, 0] = rng.integers(0, 3, size=int(lk.sum()))
     return t

@@ -123,3 +123,26 @@ def test_trace_streams(abis):
         a_w, b_w = rand_field(rng, 1), rand_field(rng, 1)
         for x, y in zip(g.trace_streams(cs, a_w, b_w, int(lookups)), e.trace_streams(cs, a_w, b_w, int(lookups))):
             assert np.array_equal(x, y)
+        if lookups:
+            lr = rand_field(rng, 4)
+            for x, y in zip(g.trace_lookup_streams(cs, lr), e.trace_lookup_streams(cs, lr)):
+                assert np.array_equal(x, y)
+            assert (e.trace_lookup_streams(cs, lr)[1][1::2, 0] > 0).any()         # some repeated table entries -> non-zero access counters
+
+
+@pytest.mark.parametrize("cs,B", [(1 << 10, 1 << 8), (1 << 12, 1 << 12), (1 << 14, 1 << 10)])
+def test_gate_consistency_lookups(abis, cs, B):
+    """S8 on a consistent random transcript (add / mul / lookup rows): every output of the GPU prover == the restatement."""
+    g, e = abis
+    rng = np.random.default_rng(cs + B)
+    L, R = rand_field(rng, cs), rand_field(rng, cs)
+    S = np.zeros((cs, 2), dtype=np.uint64); S[:, 0] = rng.integers(0, 3, size=cs)
+    O = rand_field(rng, cs)
+    add, mul = S[:, 0] == 0, S[:, 0] == 1
+    O[add] = e.binop(0, L, R)[add]
+    O[mul] = e.binop(2, L, R)[mul]
+    r, lr, rnd = rand_field(rng, int(np.log2(B))), rand_field(rng, 2), rand_field(rng, 13)
+    og, pg = g.gate_consistency_lookups(L, R, O, S, B, r, lr, rnd)
+    oe, pe = e.gate_consistency_lookups(L, R, O, S, B, r, lr, rnd)
+    assert pg == pe
+    assert np.array_equal(og, oe)
