@@ -143,6 +143,24 @@ partial_evals_kernel(const F *__restrict__ A, const F *__restrict__ beta, size_t
     }
 }
 
+// generate_claims_opt (:1014-1055): per half-chunk g the sum over k of eq_low[k] A[2(gB+k)] A[2(gB+k)+1]; grid (parts, nb), out[g*parts+part]
+__global__ void __launch_bounds__(256)
+layer_claim_kernel(const F *__restrict__ A, const F *__restrict__ eq_low, size_t B, F *__restrict__ out) {
+    __shared__ F sred[8];
+    const F *blk = A + 2 * (size_t)blockIdx.y * B;
+    F a = mkF(0, 0);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x)
+        a = fadd(a, fmul(fmul(eq_low[j], blk[2 * j]), blk[2 * j + 1]));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a = fadd(a, shfl_down_F(a, d));
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) a = fadd(a, sred[w]);
+        out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = a;
+    }
+}
+
 // ---- gate consistency (sumcheck.cpp:434-501 and the final phase of :796-981): degree-4 round polynomial of
 //      beta(X) * ( mul(X) L(X) R(X) + add(X) (L(X) + R(X)) - O(X) ),  mul = 1 - add  (so mul needs no table of its own).
 // Tables: 0 add, 1 beta, 2 L, 3 R, 4 O.  Same fused fold-then-accumulate structure as sc_round_kernel.
@@ -929,6 +947,143 @@ static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F
     return 0;
 }
 
+// The batched form (generate_3product_sumcheck_beta_stream_batch_optimized with batches > 1, as called when layers > distance,
+// sumcheck.cpp:1893-1900): batch j is the layer array A[j] (layer_id + j*distance) with block size B >> (j*distance); all batches have
+// the same number nb of half-chunks and share the challenges.  r[j]: log2(B_j) + log2(nb) points.  rnd = a[batches] | b[2*batches] | pad.
+static int stream_batch_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B, int distance, int batches, const std::vector<std::vector<F>> &r,
+                            const F *old_claims, const F *rnd, F *new_claims, std::vector<std::vector<F>> &new_r, double *ps) {
+    HB_TRY(ensure_scratch(ctx));
+    enum { MAXB = 8 };
+    if (batches < 1 || batches > MAXB) HB_FAIL(ctx, "stream batch: 1..8 batches");
+    if (S0 < 4 * B || (S0 & (S0 - 1)) || (B & (B - 1)) || (B >> ((batches - 1) * distance)) < 2) HB_FAIL(ctx, "stream batch: bad sizes");
+    const size_t nb = S0 / (2 * B);
+    const int lgnb = ilog2(nb);
+    size_t Bj[MAXB], tot = 0; int lgBj[MAXB];
+    for (int j = 0; j < batches; j++) { Bj[j] = B >> (j * distance); lgBj[j] = ilog2(Bj[j]); tot += Bj[j]; }
+    // per batch: eq_low | f1 | f2 | f3 | beta (5 * B_j) ; folds of all batches contiguous per table for the batched sumcheck: f1[all] f2[all] f3[all]
+    F *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, (5 * tot + nb + 64) * sizeof(F), ctx->stream));
+    F *eq_low[MAXB], *f1[MAXB], *f2[MAXB], *f3[MAXB], *beta[MAXB];
+    { F *p = buf; size_t off = 0;
+      for (int j = 0; j < batches; j++) { f1[j] = p + off; f2[j] = p + tot + off; f3[j] = p + 2 * tot + off; eq_low[j] = p + 3 * tot + off; beta[j] = p + 4 * tot + off; off += Bj[j]; } }
+    F *eqh_dev = buf + 5 * tot, *r_dev = eqh_dev + nb;
+    auto fail = [&](int rc) { cudaFreeAsync(buf, ctx->stream); return rc; };
+    int rc;
+    std::vector<std::vector<F>> eq_high(batches, std::vector<F>(nb));
+    F Kp[MAXB];
+    for (int j = 0; j < batches; j++) {
+        if ((int)r[j].size() < lgBj[j] + lgnb) return fail((ctx->err = "stream batch: point too short", 2));
+        HB_CHECK(ctx, cudaMemcpyAsync(r_dev, r[j].data(), (lgBj[j] + lgnb) * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = beta_dev(ctx, r_dev, lgBj[j], eq_low[j]))) return fail(rc);
+        if ((rc = beta_dev(ctx, r_dev + lgBj[j], lgnb, eqh_dev))) return fail(rc);
+        HB_CHECK(ctx, cudaMemcpyAsync(eq_high[j].data(), eqh_dev, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+        HB_LAUNCH(ctx, stream_init_kernel, grid_for(ctx, Bj[j]), 256, 0, A[j], eq_low[j], f1[j], f2[j], f3[j], Bj[j], ctx->red, ctx->ticket, ctx->mailbox_dev);
+        if ((rc = read_result(ctx, 1, &Kp[j]))) return fail(rc);
+        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));                 // eq_high[j] is on the host; r_dev / eqh_dev are reused by the next batch
+    }
+    const F *a = rnd, *b = rnd + batches; const F pad = rnd[3 * batches];
+    F Kf = mkF(0, 0);
+    for (int j = 0; j < batches; j++) { Kf = fadd(Kf, h_fmul(a[j], Kp[j])); Kp[j] = h_fmul(Kp[j], eq_high[j][0]); }
+    *ps += (1 + batches) * 16 / 1024.0;
+    std::vector<F> R; R.push_back(mkF(1, 0));
+    for (size_t step = 1; step < nb; step++) {
+        const size_t g = (step % 2) ? nb / 2 + (step - 1) / 2 : step / 2;
+        F K1 = mkF(0, 0), K2 = mkF(0, 0), K3[MAXB];
+        for (int j = 0; j < batches; j++) {
+            F K[3];
+            HB_LAUNCH(ctx, stream_err_kernel, grid_for(ctx, Bj[j]), 256, 0, f1[j], f2[j], f3[j], A[j] + 2 * g * Bj[j], eq_low[j], Bj[j], ctx->red, ctx->ticket, ctx->mailbox_dev);
+            if ((rc = read_result(ctx, 3, K))) return fail(rc);
+            K1 = fadd(K1, h_fmul(a[j], K[0])); K2 = fadd(K2, h_fmul(a[j], K[1])); K3[j] = K[2];
+        }
+        F rand = R.back();
+        rand = h_mimc(K1, rand); rand = h_mimc(K2, rand);
+        for (int j = 0; j < batches; j++) rand = h_mimc(K3[j], rand);
+        F x1 = rand, x2 = h_fmul(rand, x1), x3 = h_fmul(rand, x2);
+        for (int j = 0; j < batches; j++) { Kp[j] = fadd(Kp[j], h_fmul(eq_high[j][g], K3[j])); Kf = fadd(Kf, h_fmul(h_fmul(x3, a[j]), K3[j])); }
+        Kf = fadd(Kf, fadd(h_fmul(x2, K2), h_fmul(x1, K1)));
+        R.push_back(rand);
+        *ps += (1 + batches) * 16 / 1024.0;
+        for (int j = 0; j < batches; j++)
+            HB_LAUNCH(ctx, stream_fold_kernel, grid_for(ctx, Bj[j]), 256, 0, f1[j], f2[j], f3[j], A[j] + 2 * g * Bj[j], eq_low[j], rand, Bj[j]);
+    }
+    for (int j = 0; j < batches; j++) if (!feq(Kp[j], old_claims[j])) printf("Error in sumcheck 0 %d\n", j);   // the reference only warns (:1246-1251)
+    const int lgB = lgBj[0];
+    std::vector<hb_F> p1(5 * (size_t)lgB + 3 * batches + 8);
+    if ((rc = batch_sumcheck3_dev(ctx, f1[0], f2[0], f3[0], Bj, batches, a, p1.data(), ps))) return fail(rc);
+    {
+        F s = fadd(fadd(fadd(fromabi(p1[0]), fromabi(p1[1])), fadd(fromabi(p1[2]), fromabi(p1[3]))), fromabi(p1[3]));
+        if (!feq(s, Kf)) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in sumcheck 1"); }
+    }
+    if (nb < 2) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "stream batch: single-chunk layers belong to the in-memory prover"); }
+    std::vector<F> P1r(lgB);
+    for (int q = 0; q < lgB; q++) P1r[q] = fromabi(p1[4 * lgB + q]);
+    HB_CHECK(ctx, cudaMemcpyAsync(r_dev, P1r.data(), lgB * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<std::vector<F>> PE(2 * batches, std::vector<F>(nb, mkF(0, 0)));
+    for (int j = 0; j < batches; j++) {
+        if ((rc = beta_dev(ctx, r_dev, lgBj[j], beta[j]))) return fail(rc);
+        unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((Bj[j] + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
+        F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, nb * parts * 2 * sizeof(F), ctx->stream));
+        HB_LAUNCH(ctx, partial_evals_kernel, dim3(parts, (unsigned)nb), 256, 0, A[j], beta[j], Bj[j], pe_dev);
+        std::vector<F> pe(nb * parts * 2);
+        HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeAsync(pe_dev, ctx->stream);
+        for (size_t g = 0; g < nb; g++) for (unsigned q = 0; q < parts; q++) {
+            PE[2 * j][g] = fadd(PE[2 * j][g], pe[(g * parts + q) * 2]); PE[2 * j + 1][g] = fadd(PE[2 * j + 1][g], pe[(g * parts + q) * 2 + 1]);
+        }
+    }
+    cudaFreeAsync(buf, ctx->stream);
+    std::vector<F> Rp; Rp.reserve(nb);
+    for (size_t i = 0; i < nb / 2; i++) Rp.push_back(R[2 * i]);
+    for (size_t i = 0; i < nb / 2; i++) Rp.push_back(R[2 * i + 1]);
+    std::vector<F> aggr(nb, mkF(0, 0));
+    for (int i = 0; i < 2 * batches; i++) for (size_t g = 0; g < nb; g++) aggr[g] = fadd(aggr[g], h_fmul(b[i], PE[i][g]));
+    std::vector<hb_F> p2(4 * (size_t)lgnb + 8);
+    hb_F zero{0, 0};
+    HB_TRY(hb_sumcheck2(ctx, (const hb_F *)Rp.data(), (const hb_F *)aggr.data(), nb, &zero, p2.data(), ps));
+    {
+        F sum = mkF(0, 0);
+        for (int i = 0; i < batches; i++) sum = fadd(sum, fadd(h_fmul(b[2 * i], fromabi(p1[5 * lgB + 3 * i])), h_fmul(b[2 * i + 1], fromabi(p1[5 * lgB + 3 * i + 1]))));
+        F q = fadd(fadd(fromabi(p2[0]), fromabi(p2[1])), fadd(fromabi(p2[2]), fromabi(p2[2])));
+        if (!feq(sum, q)) HB_FAIL(ctx, "Error in sumcheck 2");
+    }
+    std::vector<F> P2r(lgnb);
+    for (int q = 0; q < lgnb; q++) P2r[q] = fromabi(p2[3 * lgnb + q]);
+    auto eval_small = [&](std::vector<F> v) { for (int q = 0; q < lgnb; q++) for (size_t j = 0; j < (nb >> (q + 1)); j++) v[j] = h_fold(v[2 * j], v[2 * j + 1], P2r[q]); return v[0]; };
+    new_r.assign(batches, std::vector<F>());
+    for (int j = 0; j < batches; j++) {
+        new_r[j].push_back(pad);
+        for (int q = 0; q < lgBj[j]; q++) new_r[j].push_back(P1r[q]);
+        for (int q = 0; q < lgnb; q++) new_r[j].push_back(P2r[q]);
+        new_claims[j] = fadd(h_fmul(fsub(mkF(1, 0), pad), eval_small(PE[2 * j])), h_fmul(pad, eval_small(PE[2 * j + 1])));
+    }
+    return 0;
+}
+
+// generate_claims_opt (sumcheck.cpp:1014-1055) on the resident layer arrays
+static int layer_claims_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B, int distance, int batches, const std::vector<F> &r, F *claims) {
+    const size_t nb = S0 / (2 * B); const int lgnb = ilog2(nb);
+    for (int j = 0; j < batches; j++) {
+        const size_t Bj = B >> (j * distance); const int lgBj = ilog2(Bj);
+        F *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, (Bj + 2 * nb + 64) * sizeof(F), ctx->stream));
+        F *lo = buf, *hi = buf + Bj, *r_dev = hi + nb;
+        int rc;
+        HB_CHECK(ctx, cudaMemcpyAsync(r_dev, r.data(), (lgBj + lgnb) * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = beta_dev(ctx, r_dev, lgBj, lo)) || (rc = beta_dev(ctx, r_dev + lgBj, lgnb, hi))) { cudaFreeAsync(buf, ctx->stream); return rc; }
+        unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((Bj + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
+        F *out_dev; HB_CHECK(ctx, cudaMallocAsync(&out_dev, nb * parts * sizeof(F), ctx->stream));
+        HB_LAUNCH(ctx, layer_claim_kernel, dim3(parts, (unsigned)nb), 256, 0, A[j], lo, Bj, out_dev);
+        std::vector<F> part(nb * parts), eh(nb);
+        HB_CHECK(ctx, cudaMemcpyAsync(part.data(), out_dev, part.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(eh.data(), hi, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeAsync(out_dev, ctx->stream); cudaFreeAsync(buf, ctx->stream);
+        F c = mkF(0, 0);
+        for (size_t g = 0; g < nb; g++) { F sg = mkF(0, 0); for (unsigned q = 0; q < parts; q++) sg = fadd(sg, part[g * parts + q]); c = fadd(c, h_fmul(eh[g], sg)); }
+        claims[j] = c;
+    }
+    return 0;
+}
+
 // layer arrays of a resident stream: lv[0] = xy, lv[l+1][j] = lv[l][2j] * lv[l][2j+1]  (segments never straddle X|Y)
 static int build_layers(hb_ctx *ctx, const F *xy, size_t total, int layers, std::vector<const F *> &lv, F **owned) {
     lv.assign(layers + 1, nullptr); lv[0] = xy; *owned = nullptr;
@@ -979,7 +1134,6 @@ extern "C" int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int
     }
     int layers = ilog2(total / (2 * B));
     if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance);
-    if (!(layers <= distance || naive)) HB_FAIL(ctx, "hb_mul_tree_stream: layers > distance needs the committed intermediate layers (commit_layers/open_layers), not built yet");
     std::vector<const F *> lv; F *owned;
     HB_TRY(build_layers(ctx, sx.as<F>(), total, layers, lv, &owned));
     size_t St = total >> layers;
@@ -989,10 +1143,33 @@ extern "C" int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int
     F claim = fromabi(buf[vectors + 1 + nfr]);
     std::vector<F> r(nfr), nrv;
     for (int i = 0; i < nfr; i++) r[i] = fromabi(buf[vectors + 1 + i]);
-    for (int i = layers - 1, q = 0; i >= 0 && !rc; i--, q++) {
-        F nc;
-        rc = stream_layer_dev(ctx, lv[i], total >> i, B, r.data(), claim, (const F *)rnd + 4 * q, &nc, nrv, ps);
-        claim = nc; r = nrv;
+    if (layers <= distance || naive) {
+        for (int i = layers - 1, q = 0; i >= 0 && !rc; i--, q++) {
+            F nc;
+            rc = stream_layer_dev(ctx, lv[i], total >> i, B, r.data(), claim, (const F *)rnd + 4 * q, &nc, nrv, ps);
+            claim = nc; r = nrv;
+        }
+    } else {
+        // layers > distance (:1871-1908): `batches` layers, `distance` apart, are proven together in `distance` batched passes.
+        // rnd = generate_randomness(layers - distance) | per pass a[batches], b[2*batches], pad.  commit_layers / open_layers (the Elastic_PC
+        // commitment to the intermediate layers, :983-1011) are separate calls made by the host mirror around this one.
+        const int batches = layers / distance, extra = layers - distance;
+        if (batches > 8) { cudaFreeAsync(owned, ctx->stream); HB_FAIL(ctx, "hb_mul_tree_stream: more than 8 batches"); }
+        const F *rq = (const F *)rnd;
+        for (int i = 0; i < extra; i++) r.push_back(rq[i]);
+        rq += extra;
+        std::vector<std::vector<F>> rb(batches, r), nrb;
+        F claims[8], nclaims[8];
+        const F *Aj[8];
+        for (int j = 0; j < batches; j++) Aj[j] = lv[distance - 1 + j * distance];
+        rc = layer_claims_dev(ctx, Aj, total >> (distance - 1), B, distance, batches, r, claims);
+        for (int i = distance - 1; i >= 0 && !rc; i--) {
+            for (int j = 0; j < batches; j++) Aj[j] = lv[i + j * distance];
+            rc = stream_batch_dev(ctx, Aj, total >> i, B, distance, batches, rb, claims, rq, nclaims, nrb, ps);
+            rq += 3 * batches + 1;
+            for (int j = 0; j < batches; j++) claims[j] = nclaims[j];
+            rb = nrb;
+        }
     }
     cudaFreeAsync(owned, ctx->stream);
     *layers_out = layers;

@@ -197,9 +197,23 @@ void read_stream_PC(stream_descriptor &fd, F *v, int size) {                    
     // :2357-2370: only "witness" is forwarded to read_stream.  Any other name — including "lookup_witness_basic", which prove_circuit
     // commits (main.cpp:913) — falls through to the synthetic default stream below, exactly as in the reference.
     if (fd.name == "witness") { std::vector<F> buf(size); read_stream(fd, buf, size); memcpy(v, buf.data(), (size_t)size * sizeof(F)); return; }
-    if (fd.name == "PC_layer" || fd.name == "circuit") {
-        printf("hobbit_b200: stream '%s' is not built (commit_layers / circuit description stream)\n", fd.name.c_str()); exit(-1);
+    if (fd.name == "PC_layer") {
+        // :2357-2364 + read_mul_tree_layer (:2415-2459): the name "PC_layer" is unknown to read_stream, so the layer is built from the
+        // synthetic DEFAULT stream (v[i] = F(i%1024+1), restarted on every read of 2*size elements): products of 2^layer consecutive
+        // entries, the first size/2^layer of them tiled into the first half of the chunk, the ones starting at offset `size` into the
+        // second half.  Every chunk is the same; O(size) host multiplications.
+        const size_t seg = (size_t)1 << fd.layer, per = (size_t)size / seg;
+        if (per == 0 || per > (size_t)size / 2) { printf("hobbit_b200: PC_layer: layer %d does not fit a chunk of %d\n", (int)fd.layer, size); exit(-1); }
+        std::vector<F> P(per), Q(per);
+        for (size_t i = 0; i < per; i++) {
+            F p(1), q(1);
+            for (size_t j = 0; j < seg; j++) { p = p * F((long long)((i * seg + j) % 1024 + 1)); q = q * F((long long)((i * seg + j + size) % 1024 + 1)); }
+            P[i] = p; Q[i] = q;
+        }
+        for (size_t c = 0; c < (size_t)size / 2; c++) { v[c] = P[c % per]; v[c + size / 2] = Q[c % per]; }
+        return;
     }
+    if (fd.name == "circuit") { printf("hobbit_b200: stream 'circuit' (the circuit description) is not built\n"); exit(-1); }
     CK(hb_stream_pc_test(backend(), (hb_F *)v, (size_t)size));
 }
 void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_hashes) {
@@ -320,8 +334,29 @@ const F *stream_chunk(stream_descriptor &fd, size_t i, size_t B, std::vector<F> 
     return buff.data();
 }
 
+// commit_layers / open_layers (sumcheck.cpp:983-1011): Elastic_PC commitments to every `distance`-th intermediate layer of a deep product tree
+static void commit_layers(stream_descriptor fd, std::vector<stream_descriptor> &fd_com, std::vector<std::vector<std::vector<_hash>>> &MT_hashes,
+                          int batches, int layer_id, int distance) {
+    printf("%lld,%d\n", (long long)fd.size, (int)(1ULL << layer_id));
+    size_t size = fd.size / (1ULL << layer_id);
+    if (batches - 1 <= 0) return;
+    fd_com.resize(batches - 1); MT_hashes.resize(batches - 1);
+    for (int i = 0; i < batches - 1; i++) {
+        fd_com[i].name = "PC_layer"; fd_com[i].size = size / (1ULL << (distance * i)); fd_com[i].layer = layer_id + i * distance;
+        reset_stream(fd_com[i]);
+        _hash comm;
+        init_commitment(false);
+        printf("Committing to: %d\n", (int)fd_com[i].size);
+        if (fd_com[i].size > BUFFER_SPACE) commit(fd_com[i], comm, MT_hashes[i]);
+    }
+}
+static void open_layers(std::vector<stream_descriptor> &fd_com, std::vector<std::vector<std::vector<_hash>>> &MT_hashes, double &vt, double &ps) {
+    for (size_t i = 0; i < fd_com.size(); i++)
+        if (fd_com[i].size > BUFFER_SPACE) open(fd_com[i], generate_randomness((int)std::log2((double)fd_com[i].size)), MT_hashes[i], vt, ps);
+}
+
 std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, int vectors, int size, F previous_r, int distance,
-                                                        std::vector<F> prev_x, bool naive, double &, double &ps) {
+                                                        std::vector<F> prev_x, bool naive, double &vt, double &ps) {
     if (!prev_x.empty()) { printf("hobbit_b200: prove_multiplication_tree_stream_shallow with prev_x is not wired yet\n"); exit(-1); }
     const size_t total = (size_t)size * vectors;
     // the stream in its logical two-half form [X | Y]: one read of the whole stream (a two-half producer emits X-block | Y-block)
@@ -333,17 +368,32 @@ std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, in
         layers = (int)std::log2((double)(total / (2 * BUFFER_SPACE)));
         if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance);
     }
-    // libc draws in the reference's order: the product tree's points, then per streamed layer a, (b0, b1), pad
+    const bool deep = layers > distance && !naive;
+    std::vector<stream_descriptor> fd_com; std::vector<std::vector<std::vector<_hash>>> MT_hashes;
+    if (!naive && total > 2 * BUFFER_SPACE) commit_layers(fd, fd_com, MT_hashes, layers / distance, distance - 1, distance);   // :1786-1789 (no libc draws)
+    // libc draws in the reference's order: the product tree's points, then per streamed layer a, (b0, b1), pad — or, for a deep tree
+    // (layers > distance): the tail of r_temp (:1875), then per batched pass a[batches], b[2*batches], pad
     std::vector<F> xr = generate_randomness((int)std::log2((double)vectors)), rnd;
-    for (int i = 0; i < layers; i++) {
-        F a = generate_randomness(1)[0]; std::vector<F> b = generate_randomness(2); F pad = F(random());
-        rnd.push_back(a); rnd.push_back(b[0]); rnd.push_back(b[1]); rnd.push_back(pad);
+    if (!deep) {
+        for (int i = 0; i < layers; i++) {
+            F a = generate_randomness(1)[0]; std::vector<F> b = generate_randomness(2); F pad = F(random());
+            rnd.push_back(a); rnd.push_back(b[0]); rnd.push_back(b[1]); rnd.push_back(pad);
+        }
+    } else {
+        const int batches = layers / distance;
+        std::vector<F> tail = generate_randomness(layers - distance);
+        rnd.insert(rnd.end(), tail.begin(), tail.end());
+        for (int i = 0; i < distance; i++) {
+            std::vector<F> a = generate_randomness(batches), b = generate_randomness(2 * batches); F pad = F(random());
+            rnd.insert(rnd.end(), a.begin(), a.end()); rnd.insert(rnd.end(), b.begin(), b.end()); rnd.push_back(pad);
+        }
     }
     if (rnd.empty()) rnd.resize(4);
     std::vector<F> out(vectors);
     int got_layers = 0;
     CK(hb_mul_tree_stream(backend(), (const hb_F *)xy_ptr, total, vectors, BUFFER_SPACE, distance, naive ? 1 : 0, (const hb_F *)&previous_r,
                           (const hb_F *)xr.data(), (const hb_F *)rnd.data(), (hb_F *)out.data(), &got_layers, &ps));
+    if (!naive) open_layers(fd_com, MT_hashes, vt, ps);                          // :1909-1911
     return out;
 }
 

@@ -129,7 +129,9 @@ int hb_mul_tree_stream(hb_ctx *, const hb_F *xy, size_t total, int vectors, size
     int layers = 0;
     if (total > 2 * B) { layers = ilog2(total / (2 * B)); if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance); }
     std::vector<F> q(cF(x_rand), cF(x_rand) + ilog2((size_t)vectors));
-    q.insert(q.end(), cF(rnd), cF(rnd) + 4 * (size_t)layers);
+    size_t nrnd = 4 * (size_t)layers;                                        /* per streamed layer: a, b0, b1, pad */
+    if (layers > distance && !naive) { int batches = layers / distance; nrnd = (size_t)(layers - distance) + (size_t)distance * (3 * batches + 1); }
+    q.insert(q.end(), cF(rnd), cF(rnd) + nrnd);
     orc_inject_randomness(q.data(), q.size());
     *ps += orc_mul_tree_stream(cF(xy), total, vectors, B, distance, naive, cF(prev_r), mF(out));
     orc_inject_randomness(nullptr, 0);

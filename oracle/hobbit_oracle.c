@@ -680,6 +680,152 @@ int orc_stream_sumcheck_layer(const F *xy, size_t total, size_t B, int layer_id,
     return (int)k;
 }
 
+/* ------------------------------------------------------------------ S4, batched ---
+ * generate_3product_sumcheck_beta_stream_batch_optimized (sumcheck.cpp:1150-1392) with `batches` layers proven together: batch j is the
+ * product-tree layer layer_id + j*distance with block size B >> (j*distance) (read_mul_tree_data, witness_stream.cpp:2461-2510: every
+ * batch has the same number of half-chunks nb).  r[j]: the point of batch j (log2(B_j) + log2(nb) entries used).
+ * libc draws: a = generate_randomness(batches), b = generate_randomness(2*batches), pad = random().
+ * new_r[j] gets 1 + log2(B_j) + log2(nb) entries (row stride rs).  Returns the entries written for batch 0. */
+static int stream_sumcheck_batch(const F *xy, size_t total, size_t B, int layer_id, int distance, int batches, const F *r, int rs,
+                                 const F *old_claims, F *new_claims, F *new_r, double *ps_out) {
+    enum { MAXB = 8 };
+    if (batches > MAXB) { printf("stream_sumcheck_batch: too many batches\n"); exit(-1); }
+    size_t S0 = total >> layer_id, nb = S0 / (2 * B);
+    int lgnb = ilog2(nb);
+    F *A[MAXB], *eq_low[MAXB], *eq_high[MAXB], *f1[MAXB], *f2[MAXB], *f3[MAXB];
+    size_t Bj[MAXB]; int lgBj[MAXB];
+    F Kp[MAXB], a[MAXB];
+    double ps = 0;
+    for (int j = 0; j < batches; j++) {
+        Bj[j] = B >> (j * distance); lgBj[j] = ilog2(Bj[j]);
+        A[j] = layer_array(xy, total, layer_id + j * distance);
+        eq_low[j] = (F *)malloc(Bj[j] * sizeof(F)); eq_high[j] = (F *)malloc(nb * sizeof(F));
+        orc_precompute_beta(r + (size_t)j * rs, lgBj[j], eq_low[j]); orc_precompute_beta(r + (size_t)j * rs + lgBj[j], lgnb, eq_high[j]);
+        f1[j] = (F *)malloc(3 * Bj[j] * sizeof(F)); f2[j] = f1[j] + Bj[j]; f3[j] = f2[j] + Bj[j];
+        Kp[j] = F0;
+        for (size_t k = 0; k < Bj[j]; k++) {
+            f1[j][k] = A[j][2 * k]; f2[j][k] = A[j][2 * k + 1]; f3[j][k] = eq_low[j][k];
+            Kp[j] = f_add(Kp[j], f_mul(f_mul(f1[j][k], f2[j][k]), f3[j][k]));
+        }
+    }
+    prover_randomness(batches, a);
+    F Kf = F0;
+    for (int j = 0; j < batches; j++) { Kf = f_add(Kf, f_mul(a[j], Kp[j])); Kp[j] = f_mul(Kp[j], eq_high[j][0]); }
+    ps += (1 + batches) * 16 / 1024.0;
+    F *R = (F *)malloc(nb * sizeof(F)); size_t nR = 0; R[nR++] = F1;
+    for (size_t step = 1; step < nb; step++) {
+        size_t g = (step % 2) ? nb / 2 + (step - 1) / 2 : step / 2;       /* X0 | Y0, X1, Y1, ...: natural half-chunk index */
+        F K1 = F0, K2 = F0, K3[MAXB];
+        for (int j = 0; j < batches; j++) {
+            const F *blk = A[j] + 2 * g * Bj[j];
+            F k1 = F0, k2 = F0; K3[j] = F0;
+            for (size_t k = 0; k < Bj[j]; k++) {
+                F b1 = blk[2 * k], b2 = blk[2 * k + 1], b3 = eq_low[j][k];
+                F t1 = f_add(f_mul(b1, f2[j][k]), f_mul(b2, f1[j][k])), t2 = f_mul(b1, b2);
+                k1 = f_add(k1, f_add(f_mul(f3[j][k], t1), f_mul(f_mul(b3, f1[j][k]), f2[j][k])));
+                k2 = f_add(k2, f_add(f_mul(b3, t1), f_mul(f3[j][k], t2)));
+                K3[j] = f_add(K3[j], f_mul(t2, b3));
+            }
+            K1 = f_add(K1, f_mul(a[j], k1)); K2 = f_add(K2, f_mul(a[j], k2));
+        }
+        F rand = R[nR - 1];
+        rand = mimc(K1, rand); rand = mimc(K2, rand);
+        for (int j = 0; j < batches; j++) rand = mimc(K3[j], rand);
+        F x1 = rand, x2 = f_mul(rand, x1), x3 = f_mul(rand, x2);
+        for (int j = 0; j < batches; j++) { Kp[j] = f_add(Kp[j], f_mul(eq_high[j][g], K3[j])); Kf = f_add(Kf, f_mul(f_mul(x3, a[j]), K3[j])); }
+        Kf = f_add(Kf, f_add(f_mul(x2, K2), f_mul(x1, K1)));
+        R[nR++] = rand;
+        ps += (1 + batches) * 16 / 1024.0;
+        for (int j = 0; j < batches; j++) {
+            const F *blk = A[j] + 2 * g * Bj[j];
+            for (size_t k = 0; k < Bj[j]; k++) {
+                f1[j][k] = f_add(f1[j][k], f_mul(rand, blk[2 * k])); f2[j][k] = f_add(f2[j][k], f_mul(rand, blk[2 * k + 1]));
+                f3[j][k] = f_add(f3[j][k], f_mul(rand, eq_low[j][k]));
+            }
+        }
+    }
+    for (int j = 0; j < batches; j++) if (!f_eq(Kp[j], old_claims[j])) printf("Error in sumcheck 0 %d\n", j);
+    /* batch_3product_sumcheck over the folds */
+    size_t tot = 0, sizes[MAXB]; for (int j = 0; j < batches; j++) { sizes[j] = Bj[j]; tot += Bj[j]; }
+    F *t1 = (F *)malloc(3 * tot * sizeof(F)), *t2 = t1 + tot, *t3 = t2 + tot; size_t off = 0;
+    for (int j = 0; j < batches; j++) { memcpy(t1 + off, f1[j], Bj[j] * sizeof(F)); memcpy(t2 + off, f2[j], Bj[j] * sizeof(F)); memcpy(t3 + off, f3[j], Bj[j] * sizeof(F)); off += Bj[j]; }
+    int lgB = lgBj[0];
+    F *p1 = (F *)malloc((5 * (size_t)lgB + 3 * batches + 8) * sizeof(F));
+    ps += orc_batch_sumcheck3(t1, t2, t3, sizes, batches, a, p1);
+    free(t1);
+    {
+        F s = f_add(f_add(f_add(p1[0], p1[1]), f_add(p1[2], p1[3])), p1[3]);
+        if (!f_eq(s, Kf)) { printf("Error in sumcheck 1\n"); exit(-1); }
+    }
+    const F *P1r = p1 + 4 * lgB, *P1vr = p1 + 5 * lgB;
+    if (nb < 2) { printf("stream_sumcheck_batch: single-chunk layers are handled by the in-memory prover\n"); exit(-1); }
+    F *PE = (F *)malloc(2 * (size_t)batches * nb * sizeof(F));        /* PE[(2j+h)*nb + g] */
+    for (int j = 0; j < batches; j++) {
+        F *beta = (F *)malloc(Bj[j] * sizeof(F));
+        orc_precompute_beta(P1r, lgBj[j], beta);
+        for (size_t g = 0; g < nb; g++) {
+            F s0 = F0, s1 = F0; const F *blk = A[j] + 2 * g * Bj[j];
+            for (size_t k = 0; k < Bj[j]; k++) { s0 = f_add(s0, f_mul(beta[k], blk[2 * k])); s1 = f_add(s1, f_mul(beta[k], blk[2 * k + 1])); }
+            PE[(2 * j) * nb + g] = s0; PE[(2 * j + 1) * nb + g] = s1;
+        }
+        free(beta);
+    }
+    F *Rp = (F *)malloc(nb * sizeof(F)); size_t cnt = 0;
+    for (size_t i = 0; i < nb / 2; i++) Rp[cnt++] = R[2 * i];
+    for (size_t i = 0; i < nb / 2; i++) Rp[cnt++] = R[2 * i + 1];
+    F b[2 * MAXB]; prover_randomness(2 * batches, b);
+    F *aggr = (F *)malloc(nb * sizeof(F));
+    for (size_t g = 0; g < nb; g++) { aggr[g] = F0; for (int i = 0; i < 2 * batches; i++) aggr[g] = f_add(aggr[g], f_mul(b[i], PE[(size_t)i * nb + g])); }
+    F *p2 = (F *)malloc((4 * (size_t)lgnb + 8) * sizeof(F));
+    F zero = F0;
+    ps += orc_sumcheck2(Rp, aggr, nb, &zero, p2);
+    {
+        F sum = F0;
+        for (int i = 0; i < batches; i++) sum = f_add(sum, f_add(f_mul(b[2 * i], P1vr[3 * i]), f_mul(b[2 * i + 1], P1vr[3 * i + 1])));
+        F q = f_add(f_add(p2[0], p2[1]), f_add(p2[2], p2[2]));
+        if (!f_eq(sum, q)) { printf("Error in sumcheck 2\n"); exit(-1); }
+    }
+    F pad = prover_random();
+    const F *P2r = p2 + 3 * lgnb;
+    int n0 = 0;
+    for (int j = 0; j < batches; j++) {
+        F *nr = new_r + (size_t)j * rs; int k = 0;
+        nr[k++] = pad;
+        for (int q = 0; q < lgBj[j]; q++) nr[k++] = P1r[q];
+        for (int q = 0; q < lgnb; q++) nr[k++] = P2r[q];
+        if (j == 0) n0 = k;
+        new_claims[j] = f_add(f_mul(f_sub(F1, pad), evaluate_vector(PE + (size_t)(2 * j) * nb, nb, P2r)), f_mul(pad, evaluate_vector(PE + (size_t)(2 * j + 1) * nb, nb, P2r)));
+    }
+    *ps_out = ps;
+    for (int j = 0; j < batches; j++) { free(A[j]); free(eq_low[j]); free(eq_high[j]); free(f1[j]); }
+    free(R); free(p1); free(PE); free(Rp); free(aggr); free(p2);
+    return n0;
+}
+int orc_stream_sumcheck_batch(const F *xy, size_t total, size_t B, int layer_id, int distance, int batches, const F *r, int rs, const int *rlen,
+                              const F *old_claims, F *new_claims, F *new_r, double *ps_out) {
+    (void)rlen;
+    return stream_sumcheck_batch(xy, total, B, layer_id, distance, batches, r, rs, old_claims, new_claims, new_r, ps_out);
+}
+/* generate_claims_opt (sumcheck.cpp:1014-1055): claims[j] = sum over the layer layer_id + j*distance of eq(r)(x) * A[2x] * A[2x+1], with the
+ * half-chunk order of the two-half stream (chunk i <-> eq_high[i] for X halves, eq_high[i + nb/2] for Y halves == natural index) */
+static void generate_claims_opt(const F *xy, size_t total, size_t B, int layer_id, int distance, int batches, const F *r, F *claims) {
+    size_t S0 = total >> layer_id, nb = S0 / (2 * B); int lgnb = ilog2(nb);
+    for (int j = 0; j < batches; j++) {
+        size_t Bj = B >> (j * distance); int lgBj = ilog2(Bj);
+        F *A = layer_array(xy, total, layer_id + j * distance);
+        F *lo = (F *)malloc(Bj * sizeof(F)), *hi = (F *)malloc(nb * sizeof(F));
+        orc_precompute_beta(r, lgBj, lo); orc_precompute_beta(r + lgBj, lgnb, hi);
+        F c = F0;
+        for (size_t g = 0; g < nb; g++) {
+            F s = F0; const F *blk = A + 2 * g * Bj;
+            for (size_t k = 0; k < Bj; k++) s = f_add(s, f_mul(f_mul(lo[k], blk[2 * k]), blk[2 * k + 1]));
+            c = f_add(c, f_mul(hi[g], s));
+        }
+        claims[j] = c;
+        free(A); free(lo); free(hi);
+    }
+}
+
 /* ------------------------------------------------------------------ S6 ---
  * prove_multiplication_tree_stream_shallow (sumcheck.cpp:1746-1915), branches: whole stream fits (size*vectors <= 2B) and
  * layers <= distance (or naive).  Returns ps; out = the `vectors` products. */
@@ -693,7 +839,6 @@ double orc_mul_tree_stream(const F *xy, size_t total, int vectors, size_t B, int
     }
     int layers = ilog2(total / (2 * B));
     if (layers % distance != 0 && layers > distance) layers = distance + layers - (layers % distance);
-    if (!(layers <= distance || naive)) { printf("orc_mul_tree_stream: batched layers (layers > distance) not restated\n"); exit(-1); }
     F *top = layer_array(xy, total, layers);
     size_t St = total >> layers;
     orc_mul_tree(top, vectors, St / vectors, prev_r, buf, &nfr, &ps);
@@ -703,10 +848,29 @@ double orc_mul_tree_stream(const F *xy, size_t total, int vectors, size_t B, int
     F *r = (F *)malloc((maxr + 2) * sizeof(F)), *nr = (F *)malloc((maxr + 2) * sizeof(F));
     memcpy(r, buf + vectors + 1, nfr * sizeof(F));    /* vectors > 1: individual ++ global == final_r */
     int n = nfr;
-    for (int i = layers - 1; i >= 0; i--) {
-        F nc; double p = 0;
-        n = orc_stream_sumcheck_layer(xy, total, B, i, r, n, &claim, &nc, nr, &p);
-        ps += p; claim = nc; memcpy(r, nr, n * sizeof(F));
+    if (layers <= distance || naive) {
+        for (int i = layers - 1; i >= 0; i--) {
+            F nc; double p = 0;
+            n = orc_stream_sumcheck_layer(xy, total, B, i, r, n, &claim, &nc, nr, &p);
+            ps += p; claim = nc; memcpy(r, nr, n * sizeof(F));
+        }
+    } else {
+        /* layers > distance (:1871-1908): `batches` layers, `distance` apart, are proven together.  NOT included here: commit_layers /
+         * open_layers (:983-1011), i.e. the Elastic_PC commit + open of the intermediate layers — their only trace in the reference's
+         * outputs is ps and libc draws; the host mirror runs them around this call (hobbit_host.cpp). */
+        int batches = layers / distance, rs = maxr + 2;
+        int extra = ilog2(total >> distance) - nfr;                  /* r_temp = individual | global | generate_randomness(extra) */
+        prover_randomness(extra, r + nfr);
+        F *rb = (F *)calloc((size_t)batches * rs, sizeof(F)), *nrb = (F *)calloc((size_t)batches * rs, sizeof(F));
+        for (int j = 0; j < batches; j++) memcpy(rb + (size_t)j * rs, r, (nfr + extra) * sizeof(F));
+        F claims[8], nclaims[8];
+        generate_claims_opt(xy, total, B, distance - 1, distance, batches, r, claims);
+        for (int i = distance - 1; i >= 0; i--) {
+            double p = 0;
+            stream_sumcheck_batch(xy, total, B, i, distance, batches, rb, rs, claims, nclaims, nrb, &p);
+            ps += p; memcpy(claims, nclaims, sizeof claims); memcpy(rb, nrb, (size_t)batches * rs * sizeof(F));
+        }
+        free(rb); free(nrb);
     }
     free(r); free(nr); free(buf);
     return ps;

@@ -64,6 +64,8 @@ size_t orc_mul_tree(const orc_F *input, int vectors, size_t n, const orc_F *prev
  * xy: the witness stream in its logical two-half form [X | Y] (total elements). */
 int orc_stream_sumcheck_layer(const orc_F *xy, size_t total, size_t B, int layer_id, const orc_F *r, int nr, const orc_F *old_claim,
                               orc_F *new_claim, orc_F *new_r, double *ps_out);
+int orc_stream_sumcheck_batch(const orc_F *xy, size_t total, size_t B, int layer_id, int distance, int batches, const orc_F *r, int rs, const int *rlen,
+                              const orc_F *old_claims, orc_F *new_claims, orc_F *new_r, double *ps_out);
 double orc_mul_tree_stream(const orc_F *xy, size_t total, int vectors, size_t B, int distance, int naive, const orc_F *prev_r, orc_F *out);
 
 /* prove_gate_consistency_standard (sumcheck.cpp:434-501); out: (a,b,c,d,e,rand) x rounds | final add, L, R, O, mul, beta */

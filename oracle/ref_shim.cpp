@@ -303,6 +303,22 @@ int ref_stream_sumcheck_layer(size_t total, size_t B, int layer_id, const uint64
     *ps_out = ps;
     return (int)nr_out[0].size();
 }
+// The batched form (batches > 1, as used when layers > distance): r = batches rows of `rs` points (row j: log2(B >> j*distance) + log2(nb)
+// used); writes new_claims[batches] and new_r (batches rows of rs); returns the length of row 0.
+int ref_stream_sumcheck_batch(size_t total, size_t B, int layer_id, int distance, int batches, const uint64_t *r, int rs, const int *rlen,
+                              const uint64_t *old_claims, uint64_t *new_claims, uint64_t *new_r, double *ps_out) {
+    BUFFER_SPACE = B; BUFFER_SPACE_tr = B / 8;
+    stream_descriptor fd; fd.name = "test"; fd.size = total; reset_stream(fd);
+    vector<vector<F>> rv(batches), nr_out;
+    for (int j = 0; j < batches; j++) rv[j].assign((const F *)r + (size_t)j * rs, (const F *)r + (size_t)j * rs + rlen[j]);
+    vector<F> oc((const F *)old_claims, (const F *)old_claims + batches), nc(batches);
+    double vt = 0, ps = 0;
+    generate_3product_sumcheck_beta_stream_batch_optimized(fd, rv, batches, distance, layer_id, oc, nc, nr_out, vt, ps);
+    memcpy(new_claims, nc.data(), batches * 16);
+    for (int j = 0; j < batches; j++) memcpy(new_r + 2 * (size_t)j * rs, nr_out[j].data(), nr_out[j].size() * 16);
+    *ps_out = ps;
+    return (int)nr_out[0].size();
+}
 // prove_multiplication_tree_stream_shallow (sumcheck.cpp:1746-1915) on stream "test"; out: the `vectors` products.
 double ref_mul_tree_stream(size_t total, int vectors, size_t B, int distance, int naive, const uint64_t *prev_r, uint64_t *out) {
     BUFFER_SPACE = B; BUFFER_SPACE_tr = B / 8;

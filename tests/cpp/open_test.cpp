@@ -61,6 +61,32 @@ int main(int argc, char **argv) {
     hobbit::init_backend(0);
     double vt = 0;
 
+    if (argc > 1 && !strcmp(argv[1], "deep")) {
+        // Runs in its OWN process: open_layers opens with BUFFER_SPACE 2^9, and the reference's global query vector `I` (Elastic_PC.cpp:314)
+        // would still hold positions of earlier, larger openings (its own "Error pos,size" exit).
+    // ---- deep streaming product tree (layers > distance): batched layers + commit_layers / open_layers (sumcheck.cpp:983-1011, 1871-1911) ----
+        for (int cfg = 0; cfg < 2; cfg++) {
+            // the reference's top-layer read (read_mul_tree_layer, witness_stream.cpp:2415-2459) needs total >> layers >= 2^layers, else it spins
+            BUFFER_SPACE = 1 << 9; hobbit::BUFFER_SPACE = BUFFER_SPACE;
+            extern int BUFFER_SPACE_tr; BUFFER_SPACE_tr = BUFFER_SPACE / 8;
+            const size_t total = 1 << 20; const int vectors = cfg ? 2 : 8;                      // layers = 10 -> 2 batches of 5
+            double ps = 0, hps = 0;
+            stream_descriptor fd; fd.name = "test"; fd.size = total; reset_stream(fd);
+            srand(33); vector<F> o = prove_multiplication_tree_stream_shallow(fd, vectors, total / vectors, F(32), 5, vector<F>(), 0, vt, ps);
+            int r1 = rand();
+            hobbit::stream_descriptor hfd; hfd.name = "test"; hfd.size = total;
+            srand(33); vector<hobbit::Fe> ho = hobbit::prove_multiplication_tree_stream_shallow(hfd, vectors, total / vectors, hobbit::Fe(32), 5, vector<hobbit::Fe>(), 0, vt, hps);
+            int r2 = rand();
+            bool ok = o.size() == ho.size() && ps == hps && r1 == r2;
+            for (size_t i = 0; ok && i < o.size(); i++) ok = eqF(o[i], ho[i]);
+            CHECK(ok, cfg ? "deep product tree (2 x 2^19, BUFFER_SPACE 2^9: 2 batched layers, committed layer): products, ps, RNG state"
+                          : "deep product tree (8 x 2^17, BUFFER_SPACE 2^9: 2 batched layers, committed layer): products, ps, RNG state");
+            printf("      ps %f / %f KB\n", ps, hps);
+        }
+        printf(failures ? "OPEN: %d FAILURES\n" : "OPEN: all identical\n", failures);
+        return failures ? 1 : 0;
+    }
+
     // ---- shockwave_commit ---------------------------------------------------------------------------------------------------------
     {
         srand(41);

@@ -233,6 +233,30 @@ def synthetic_stream(total):
     return out
 
 
+def _stream_batch(self, xy, B, layer, distance, batches, r_rows, old_claims):
+    """batched S4; r_rows: list of (len_j, 2) arrays.  Returns (new_claims (batches,2), [new_r rows], ps)."""
+    xy = F(xy)
+    rs = max(len(x) for x in r_rows) + 4
+    r = np.zeros((batches, rs, 2), dtype=np.uint64)
+    rlen = (ctypes.c_int * batches)(*[len(x) for x in r_rows])
+    for j, x in enumerate(r_rows):
+        r[j, :len(x)] = x
+    oc = F(old_claims)
+    nc, nr = fzeros(batches), np.zeros((batches, rs, 2), dtype=np.uint64)
+    ps = ctypes.c_double(0)
+    if self.kind == "orc":
+        n0 = self.fn("stream_sumcheck_batch", ctypes.c_int)(_p(xy), ctypes.c_size_t(len(xy)), ctypes.c_size_t(B), layer, distance, batches, _p(r), rs, rlen,
+                                                           _p(oc), _p(nc), _p(nr), ctypes.byref(ps))
+    else:
+        n0 = self.fn("stream_sumcheck_batch", ctypes.c_int)(ctypes.c_size_t(len(xy)), ctypes.c_size_t(B), layer, distance, batches, _p(r), rs, rlen,
+                                                           _p(oc), _p(nc), _p(nr), ctypes.byref(ps))
+    rows = [nr[j, :n0 - j * distance].copy() for j in range(batches)]
+    return nc, rows, ps.value
+
+
+Checker.stream_batch = _stream_batch
+
+
 def _stream_layer(self, xy, B, layer_id, r, old_claim):
     """S4.  Checker('ref') ignores xy (it reads the synthetic stream itself)."""
     xy, r, oc = F(xy), F(r), F(old_claim)
@@ -514,3 +538,15 @@ def synthetic_trace(rng, n, lookups=False):
         t["value_l"][lk, 0] = rng.integers(0, 40, size=int(lk.sum()))
         t["value_r"][lk, 0] = rng.integers(0, 3, size=int(lk.sum()))
     return t
+
+
+def _raw_mul_tree_stream(self, xy, vectors, B, distance, naive, prev_r, x_rand, rnd):
+    xy = F(xy)
+    out = fzeros(vectors)
+    layers, ps = ctypes.c_int(0), ctypes.c_double(0)
+    self.call("hb_mul_tree_stream", xy, len(xy), ctypes.c_int(vectors), B, ctypes.c_int(distance), ctypes.c_int(naive), F(prev_r), F(x_rand), F(rnd), out,
+              ctypes.byref(layers), ctypes.byref(ps))
+    return out, ps.value, layers.value
+
+
+RawABI.mul_tree_stream = _raw_mul_tree_stream

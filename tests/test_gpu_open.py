@@ -146,3 +146,23 @@ def test_gate_consistency_lookups(abis, cs, B):
     oe, pe = e.gate_consistency_lookups(L, R, O, S, B, r, lr, rnd)
     assert pg == pe
     assert np.array_equal(og, oe)
+
+
+@pytest.mark.parametrize("total,vectors,B,distance", [(1 << 16, 8, 1 << 8, 3), (1 << 18, 2, 1 << 9, 4), (1 << 20, 8, 1 << 9, 5)])
+def test_mul_tree_stream_deep(abis, total, vectors, B, distance):
+    """8f.3: layers > distance — batched streaming sumchecks on the GPU vs the restatement (products, ps; the provers' own checks
+    'Error in sumcheck 1/2' fail the call on either side)."""
+    g, e = abis
+    rng = np.random.default_rng(total + vectors)
+    xy = rand_field(rng, total)
+    layers = int(np.log2(total // (2 * B)))
+    if layers % distance and layers > distance:
+        layers = distance + layers - layers % distance
+    assert layers > distance
+    batches = layers // distance
+    rnd = rand_field(rng, (layers - distance) + distance * (3 * batches + 1))
+    pr, xr = rand_field(rng, 1), rand_field(rng, int(np.log2(vectors)))
+    og, pg, lg = g.mul_tree_stream(xy, vectors, B, distance, 0, pr, xr, rnd)
+    oe, pe, le = e.mul_tree_stream(xy, vectors, B, distance, 0, pr, xr, rnd)
+    assert lg == le == layers and pg == pe
+    assert np.array_equal(og, oe)

@@ -24,6 +24,18 @@ def test_open_recursion_host_logic_vs_reference():
     _run(EMUL)
 
 
+@pytest.mark.skipif(not os.path.exists(EMUL), reason="oracle/_ref/open_test_emul not prebuilt (needs /root/reference at build time)")
+def test_deep_product_tree_host_logic_vs_reference():
+    """layers > distance: batched streaming sumchecks + commit_layers / open_layers (sumcheck.cpp:983-1011, 1871-1911)."""
+    _run(EMUL, "deep")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(GPU), reason="oracle/_ref/open_test not prebuilt")
+def test_deep_product_tree_gpu_vs_reference():
+    _run(GPU, "deep")
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(GPU), reason="oracle/_ref/open_test not prebuilt (needs /root/reference at build time)")
 def test_open_recursion_gpu_vs_reference():

@@ -159,6 +159,23 @@ def test_stream_sumcheck_layer(libs, total, B, layer):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
 
 
+@pytest.mark.parametrize("total,B,layer,distance,batches", [(1 << 15, 1 << 9, 1, 2, 2), (1 << 16, 1 << 9, 0, 2, 3), (1 << 16, 1 << 10, 2, 5, 2)])
+def test_stream_sumcheck_batched(libs, total, B, layer, distance, batches):
+    """The batched form of S4 (batches > 1: layers `distance` apart proven together, sumcheck.cpp:1150-1392 as called from :1893-1900)."""
+    orc, ref = libs
+    xy = synthetic_stream(total)
+    nb = (total >> layer) // (2 * B)
+    rng = np.random.default_rng(total + layer + batches)
+    r0 = rand_field(rng, int(np.log2(B)) + int(np.log2(nb)))
+    rows = [np.concatenate([r0[:int(np.log2(B)) - j * distance], rand_field(rng, int(np.log2(nb)))]) for j in range(batches)]
+    oc = rand_field(rng, batches)
+    srand(4); a = orc.stream_batch(xy, B, layer, distance, batches, rows, oc)
+    srand(4); b = ref.stream_batch(xy, B, layer, distance, batches, rows, oc)
+    assert np.array_equal(a[0], b[0]) and a[2] == b[2]
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x, y)
+
+
 @pytest.mark.parametrize("total,vectors,B", [(1 << 15, 8, 1 << 10), (1 << 12, 8, 1 << 11), (1 << 14, 2, 1 << 9)])
 def test_mul_tree_stream(libs, total, vectors, B):
     """S6 (sumcheck.cpp:1746-1915): products and ps; the self-checks inside (Error in sumcheck 1/2 -> exit) pin the rest."""
