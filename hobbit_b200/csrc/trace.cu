@@ -136,9 +136,146 @@ __global__ void __launch_bounds__(256) fill_kernel(F *__restrict__ v, size_t n, 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] = x;
 }
 
+// ---- 8f.4: the MLP circuit evaluator on the GPU (Seval.cpp:1238-1286 MLP_inference, :1462-1489 the fun == 9 driver) --------------------
+// The evaluator is sequential only in its bookkeeping: every field of every trace record is a closed-form function of (layer, neuron, input)
+// except the running sums, which are a per-neuron prefix scan.  One CTA per neuron; the records land exactly where the CPU evaluator's
+// single pass would put them, labels and access counters included:
+//   labels   : 1.. weights (layer, neuron, input order) | inputs | zero | then gates in creation order (1 per first product, 2 per later input)
+//   neuron j : mul(w_0, x_0) ; then per k >= 1: mul(w_k, x_k), add(sum, product), delete(product), delete(old sum)
+//   access   : a weight is read once; input k of a layer is read by every neuron (access_r = a0 + j, a0 = 0 for the network inputs, 1 for
+//              hidden values, which are born with access 1); sums and products are read once (deleted with access 2)
+struct MlpLayer {
+    int n, m, a0;                 // inputs, neurons, initial access counter of the inputs
+    int layer;                    // i (the weight value is (j + i + k) % 256)
+    long long w_label0;           // label of weight (i, 0, 0)
+    long long g_label0;           // label of the first gate of this layer
+    size_t rec0;                  // first record of this layer
+};
+__global__ void __launch_bounds__(256)
+mlp_layer_kernel(TrTuple *__restrict__ tr, MlpLayer L, const F *__restrict__ in_val, const int *__restrict__ in_idx, F *__restrict__ out_val, int *__restrict__ out_idx) {
+    __shared__ F sc[256];
+    __shared__ F carry;
+    const int j = blockIdx.x, n = L.n;
+    const size_t per = 1 + 4 * (size_t)(n - 1);
+    TrTuple *base = tr + L.rec0 + (size_t)j * per;
+    const long long gl = L.g_label0 + (long long)j * (2 * n - 1);
+    if (threadIdx.x == 0) carry = mkF(0, 0);
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        F w = mkF(0, 0), x = mkF(0, 0), p = mkF(0, 0);
+        if (k < n) { w = mkF((u64)((j + L.layer + k) % 256), 0); x = in_val[k]; p = fmul(w, x); }
+        sc[threadIdx.x] = p;
+        __syncthreads();
+        for (int d = 1; d < (int)blockDim.x; d <<= 1) {                    // inclusive scan of the products
+            F v = sc[threadIdx.x];
+            if ((int)threadIdx.x >= d) v = fadd(v, sc[threadIdx.x - d]);
+            __syncthreads();
+            sc[threadIdx.x] = v;
+            __syncthreads();
+        }
+        const F c = carry;
+        const F sum = fadd(c, sc[threadIdx.x]);                             // w_0 x_0 + .. + w_k x_k
+        const F prev = (threadIdx.x == 0) ? c : fadd(c, sc[threadIdx.x - 1]);
+        if (k < n) {
+            const int widx = (int)(L.w_label0 + (long long)j * n + k);
+            TrTuple t;
+            t.type = 2; t.value_l = w; t.value_r = x; t.value_o = p;
+            t.idx_l = widx; t.idx_r = in_idx[k]; t.access_l = 0; t.access_r = L.a0 + j; t.access_o = 0;
+            for (int q = 0; q < 7; q++) t.pad_[q] = 0;
+            if (k == 0) { t.idx_o = (int)gl; base[0] = t; }
+            else {
+                const int ml = (int)(gl + 1 + 2 * (long long)(k - 1)), hl = (k == 1) ? (int)gl : ml - 1;     // product label, label of the old sum
+                TrTuple *r = base + 1 + 4 * (size_t)(k - 1);
+                t.idx_o = ml; r[0] = t;
+                TrTuple a = t;
+                a.type = 1; a.value_l = prev; a.value_r = p; a.value_o = sum; a.idx_l = hl; a.idx_r = ml; a.idx_o = ml + 1; a.access_l = 1; a.access_r = 1; a.access_o = 0;
+                r[1] = a;
+                TrTuple d1 = a; d1.type = 0; d1.idx_o = ml; d1.value_o = p; d1.access_o = 2; r[2] = d1;
+                TrTuple d2 = a; d2.type = 0; d2.idx_o = hl; d2.value_o = prev; d2.access_o = 2; r[3] = d2;
+            }
+            if (k == n - 1) { out_val[j] = sum; out_idx[j] = (n == 1) ? (int)gl : (int)(gl + 2 * (long long)n - 2); }
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = sum;
+        __syncthreads();
+    }
+}
+// delete records: idx/value from arrays (or the weight formula), constant access counter
+__global__ void __launch_bounds__(256)
+mlp_delete_kernel(TrTuple *__restrict__ tr, size_t n, const F *__restrict__ val, const int *__restrict__ idx, int access) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrTuple t; memset(&t, 0, sizeof t);
+    t.type = 0; t.idx_o = idx[i]; t.value_o = val[i]; t.access_o = access;
+    tr[i] = t;
+}
+__global__ void __launch_bounds__(256) mlp_delete_weights_kernel(TrTuple *__restrict__ tr, int layer, int m, int n, long long w_label0) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)m * n) return;
+    const int j = (int)(i / n), k = (int)(i % n);
+    TrTuple t; memset(&t, 0, sizeof t);
+    t.type = 0; t.idx_o = (int)(w_label0 + (long long)i); t.value_o = mkF((u64)((j + layer + k) % 256), 0); t.access_o = 1;
+    tr[i] = t;
+}
+__global__ void __launch_bounds__(256) mlp_inputs_kernel(F *__restrict__ val, int *__restrict__ idx, int n, long long label0) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { val[k] = mkF((u64)((k + 1) % 256), 0); idx[k] = (int)(label0 + k); }
+}
+
 }  // namespace hb
 
 using namespace hb;
+
+// MLP_inference on the GPU: fills the context's resident trace as if the producer had been drained (hb_trace_begin/push), one pass.
+extern "C" int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t *n_records) {
+    if (nsizes < 2) HB_FAIL(ctx, "hb_trace_generate_mlp: need at least an input and an output layer");
+    size_t recs = 0, wt = 0; int maxw = 0;
+    for (int i = 0; i + 1 < nsizes; i++) {
+        const size_t n = (size_t)layer_size[i], m = (size_t)layer_size[i + 1];
+        if (n < 1 || m < 1) HB_FAIL(ctx, "hb_trace_generate_mlp: layer sizes must be positive");
+        recs += m * (1 + 4 * (n - 1)) + n; wt += m * n;
+    }
+    for (int i = 0; i < nsizes; i++) maxw = std::max(maxw, layer_size[i]);
+    recs += wt + (size_t)layer_size[nsizes - 1] + 1;                               // weight deletes, output deletes, zero
+    if (wt + recs >= ((size_t)1 << 31)) HB_FAIL(ctx, "hb_trace_generate_mlp: labels do not fit the reference's int");
+    HB_TRY(hb_trace_begin(ctx, recs));
+    TraceState &t = ctx->trace;
+    TrTuple *tr = (TrTuple *)t.tuples;
+    F *val; HB_CHECK(ctx, cudaMallocAsync(&val, 2 * (size_t)maxw * (sizeof(F) + sizeof(int)), ctx->stream));
+    F *va = val, *vb = val + maxw; int *ia = (int *)(vb + maxw), *ib = ia + maxw;
+    const long long in_label0 = (long long)wt + 1, zero_label = in_label0 + layer_size[0];
+    long long g_label = zero_label + 1, w_label = 1;
+    HB_LAUNCH(ctx, mlp_inputs_kernel, (unsigned)((layer_size[0] + 255) / 256), 256, 0, va, ia, layer_size[0], in_label0);
+    size_t rec = 0;
+    for (int i = 0; i + 1 < nsizes; i++) {
+        MlpLayer L; L.n = layer_size[i]; L.m = layer_size[i + 1]; L.a0 = i ? 1 : 0; L.layer = i; L.w_label0 = w_label; L.g_label0 = g_label; L.rec0 = rec;
+        HB_LAUNCH(ctx, mlp_layer_kernel, (unsigned)L.m, 256, 0, tr, L, va, ia, vb, ib);
+        rec += (size_t)L.m * (1 + 4 * (size_t)(L.n - 1));
+        HB_LAUNCH(ctx, mlp_delete_kernel, (unsigned)((L.n + 255) / 256), 256, 0, tr + rec, (size_t)L.n, va, ia, L.a0 + L.m);     // the layer's inputs
+        rec += (size_t)L.n;
+        w_label += (long long)L.m * L.n; g_label += (long long)L.m * (2 * (long long)L.n - 1);
+        std::swap(va, vb); std::swap(ia, ib);
+    }
+    w_label = 1;
+    for (int i = 0; i + 1 < nsizes; i++) {
+        const int n = layer_size[i], m = layer_size[i + 1];
+        HB_LAUNCH(ctx, mlp_delete_weights_kernel, (unsigned)(((size_t)m * n + 255) / 256), 256, 0, tr + rec, i, m, n, w_label);
+        rec += (size_t)m * n; w_label += (long long)m * n;
+    }
+    const int nout = layer_size[nsizes - 1];
+    HB_LAUNCH(ctx, mlp_delete_kernel, (unsigned)((nout + 255) / 256), 256, 0, tr + rec, (size_t)nout, va, ia, 1);                 // the outputs (never read)
+    rec += (size_t)nout;
+    TrTuple z; memset(&z, 0, sizeof z); z.type = 0; z.idx_o = (int)zero_label; z.access_o = 0;
+    HB_CHECK(ctx, cudaMemcpyAsync(tr + rec, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+    rec += 1;
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(val, ctx->stream);
+    if (rec != recs) HB_FAIL(ctx, "hb_trace_generate_mlp: record count mismatch");
+    t.n = rec; t.done = true;
+    if (n_records) *n_records = rec;
+    return 0;
+}
 
 extern "C" int hb_trace_begin(hb_ctx *ctx, size_t capacity) {
     TraceState &t = ctx->trace;

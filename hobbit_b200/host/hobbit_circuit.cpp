@@ -44,6 +44,12 @@ bool trace_append(const tr_tuple *buf, size_t n) {
     CK(hb_trace_push(backend(), buf, n, &done));
     return done != 0;
 }
+// 8f.4: for the MLP circuit (fun == 9) the trace can be produced on the GPU instead of by the producer thread; follow with trace_end()
+void trace_generate_mlp(const std::vector<int> &layer_size) {
+    size_t n = 0;
+    CK(hb_trace_generate_mlp(backend(), layer_size.data(), (int)layer_size.size(), &n));
+    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = false;
+}
 // get_circuit_size (main.cpp:303-321): the number of delete records, rounded up to a power of two
 size_t trace_end() {
     size_t n = 0, ops = 0, dels = 0;

@@ -167,6 +167,7 @@ extern std::vector<F> lookup_rand;             // main.cpp:70
 void trace_begin(size_t capacity_hint = 0);
 bool trace_append(const tr_tuple *buf, size_t n);
 size_t trace_end();
+void trace_generate_mlp(const std::vector<int> &layer_size);   // 8f.4: MLP_inference (Seval.cpp:1238-1286) evaluated on the GPU; then trace_end()
 const F *resident_stream(const stream_descriptor &fd);          // the whole logical stream in HBM, nullptr for non-circuit streams
 bool read_circuit_stream(stream_descriptor &fd, std::vector<F> &v, int size);
 void read_trace(stream_descriptor &fd, std::vector<F> &buff_L, std::vector<F> &buff_R, std::vector<F> &buff_O, std::vector<int> &buff_S);

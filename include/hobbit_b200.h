@@ -250,6 +250,10 @@ int hb_whir_zeta(hb_ctx *ctx, const hb_F *poly, hb_F *beta, int v, const hb_F *z
 int hb_trace_begin(hb_ctx *ctx, size_t capacity_records);
 int hb_trace_push(hb_ctx *ctx, const void *records, size_t n, int *done);
 int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_deletes);
+/* 8f.4: the MLP circuit evaluated on the GPU instead of by the producer thread (Seval.cpp:1238-1286 MLP_inference under the fun == 9
+ * driver, :1462-1489: weights F((j+i+k)%256), inputs F((k+1)%256)): fills the resident trace with exactly the records, labels and access
+ * counters one pass of the CPU evaluator emits.  layer_size: the network shape (`pigeon 9 ... n l0 l1 ...`). */
+int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t *n_records);
 int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out);
 int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S);
 int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy);

@@ -318,6 +318,53 @@ int hb_trace_push(hb_ctx *ctx, const void *records, size_t n, int *done) {
     if (done) *done = ctx->tr_done ? 1 : 0;
     return 0;
 }
+/* Seval.cpp:20-24, 97-170, 1238-1286, 1462-1489 restated gate by gate */
+namespace {
+struct emu_gt { F value; int idx; int access; };
+struct MlpEval {
+    hb_ctx *ctx; int labels = 1;
+    void emit(const emu_tuple &t) { ctx->trace.insert(ctx->trace.end(), (const unsigned char *)&t, (const unsigned char *)&t + 80); ctx->tr_n++; }
+    void init(emu_gt &g, F v) { g.value = v; g.idx = labels++; g.access = 0; }
+    void del(emu_gt &g) { emu_tuple t; memset(&t, 0, sizeof t); t.type = 0; t.idx_o = g.idx; t.value_o = g.value; t.access_o = g.access; emit(t); }
+    emu_gt op(emu_gt &g1, emu_gt &g2, int type) {
+        emu_gt g; g.value = type == 1 ? fadd(g1.value, g2.value) : fmul(g1.value, g2.value); g.idx = labels++;
+        emu_tuple t; memset(&t, 0, sizeof t);
+        t.type = (uint8_t)type; t.idx_o = g.idx; t.value_o = g.value; t.idx_l = g1.idx; t.value_l = g1.value; t.idx_r = g2.idx; t.value_r = g2.value;
+        t.access_l = g1.access; g1.access++; t.access_r = g2.access; t.access_o = 0; g2.access++;
+        g.access = 1; emit(t);
+        return g;
+    }
+};
+}
+int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t *n_records) {
+    ctx->trace.clear(); ctx->tr_n = 0;
+    MlpEval E; E.ctx = ctx;
+    std::vector<emu_gt> input(layer_size[0]);
+    std::vector<std::vector<std::vector<emu_gt>>> W(nsizes - 1);
+    for (int i = 0; i + 1 < nsizes; i++) {
+        W[i].assign(layer_size[i + 1], std::vector<emu_gt>(layer_size[i]));
+        for (int j = 0; j < layer_size[i + 1]; j++) for (int k = 0; k < layer_size[i]; k++) E.init(W[i][j][k], mk((uint64_t)((j + i + k) % 256)));
+    }
+    for (int k = 0; k < layer_size[0]; k++) E.init(input[k], mk((uint64_t)((k + 1) % 256)));
+    emu_gt zero; E.init(zero, mk(0));
+    std::vector<emu_gt> inp = input;
+    for (size_t i = 0; i < W.size(); i++) {
+        std::vector<emu_gt> hidden(W[i].size());
+        for (size_t j = 0; j < W[i].size(); j++)
+            for (size_t k = 0; k < W[i][0].size(); k++) {
+                if (k == 0) hidden[j] = E.op(W[i][j][k], inp[k], 2);
+                else { emu_gt temp = E.op(W[i][j][k], inp[k], 2); emu_gt ts = E.op(hidden[j], temp, 1); E.del(temp); E.del(hidden[j]); hidden[j] = ts; }
+            }
+        for (auto &g : inp) E.del(g);
+        inp = hidden;
+    }
+    for (auto &Wi : W) for (auto &Wj : Wi) for (auto &g : Wj) E.del(g);
+    for (auto &g : inp) E.del(g);
+    E.del(zero);
+    ctx->tr_done = true;
+    if (n_records) *n_records = ctx->tr_n;
+    return 0;
+}
 int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_deletes) {
     const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); size_t o = 0, d = 0;
     for (size_t i = 0; i < ctx->tr_n; i++) { if (t[i].type == 0) d++; else o++; }

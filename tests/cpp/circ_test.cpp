@@ -117,6 +117,31 @@ int main(int argc, char **argv) {
             CHECK(ok, "stream \"lookup_witness_basic\" (2 cs), blocks of BUFFER_SPACE");
         }
     }
+    // ---- 8f.4: the same trace produced by the GPU evaluator instead of the producer thread (MLP only): every stream again ----------------
+    if (fun == 9) {
+        t0 = now();
+        hobbit::trace_generate_mlp(layer_size);
+        size_t gcs = hobbit::trace_end();
+        double t_eval = now() - t0;
+        CHECK(gcs == cs, "GPU MLP evaluator: circuit_size");
+        stream_descriptor fd; fd.name = "witness"; fd.size = 4 * cs; reset_stream(fd);
+        hobbit::stream_descriptor hfd; hfd.name = "witness"; hfd.size = 4 * cs;
+        vector<F> v(B); vector<hobbit::Fe> hv(B); bool ok = true;
+        for (size_t off = 0; off < 4 * cs; off += B) { read_stream(fd, v, (int)B); hobbit::read_stream(hfd, hv, (int)B); ok = ok && !memcmp(v.data(), hv.data(), B * 16); }
+        stream_descriptor fw; fw.name = "wiring_consistency_check_opt"; fw.size = 8 * cs; reset_stream(fw);
+        hobbit::stream_descriptor hfw; hfw.name = "wiring_consistency_check_opt"; hfw.size = 8 * cs;
+        vector<F> w(2 * B); vector<hobbit::Fe> hw(2 * B);
+        for (size_t off = 0; off < 8 * cs; off += 2 * B) { read_stream(fw, w, (int)(2 * B)); hobbit::read_stream(hfw, hw, (int)(2 * B)); ok = ok && !memcmp(w.data(), hw.data(), 2 * B * 16); }
+        stream_descriptor ft; ft.name = "transcript_stream"; ft.size = cs; reset_stream(ft);
+        hobbit::stream_descriptor hft; hft.name = "transcript_stream"; hft.size = cs;
+        vector<F> l(B), r(B), o(B); vector<int> sv(B); vector<hobbit::Fe> hl(B), hr(B), ho(B); vector<int> hs(B);
+        for (size_t off = 0; off < cs; off += B) {
+            read_trace(ft, l, r, o, sv); hobbit::read_trace(hft, hl, hr, ho, hs);
+            ok = ok && !memcmp(l.data(), hl.data(), B * 16) && !memcmp(r.data(), hr.data(), B * 16) && !memcmp(o.data(), ho.data(), B * 16) && sv == hs;
+        }
+        CHECK(ok, "GPU MLP evaluator (8f.4): witness, wiring and transcript streams identical to the reference's (labels, access counters, values)");
+        printf("      trace on the GPU in %.4f s (producer thread + upload: %.4f s)\n", t_eval, t_trace);
+    }
     // ---- commit(witness) ---------------------------------------------------------------------------------------------------------------
     vector<vector<_hash>> MT; vector<vector<hobbit::_hash>> hMT;
     {

@@ -550,3 +550,15 @@ def _raw_mul_tree_stream(self, xy, vectors, B, distance, naive, prev_r, x_rand, 
 
 
 RawABI.mul_tree_stream = _raw_mul_tree_stream
+
+
+def _raw_trace_generate_mlp(self, layer_size):
+    ls = (ctypes.c_int * len(layer_size))(*layer_size)
+    n = ctypes.c_size_t(0)
+    self.call("hb_trace_generate_mlp", ls, ctypes.c_int(len(layer_size)), ctypes.byref(n))
+    cnt = (ctypes.c_size_t * 3)()
+    self.call("hb_trace_finish", ctypes.byref(cnt, 0), ctypes.byref(cnt, 8), ctypes.byref(cnt, 16))
+    return tuple(cnt)
+
+
+RawABI.trace_generate_mlp = _raw_trace_generate_mlp

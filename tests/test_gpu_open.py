@@ -166,3 +166,19 @@ def test_mul_tree_stream_deep(abis, total, vectors, B, distance):
     oe, pe, le = e.mul_tree_stream(xy, vectors, B, distance, 0, pr, xr, rnd)
     assert lg == le == layers and pg == pe
     assert np.array_equal(og, oe)
+
+
+@pytest.mark.parametrize("shape", [(64, 32, 16), (300, 7, 1, 5), (1, 4, 1), (1024, 256, 16), (513, 2)])
+def test_mlp_evaluator(abis, shape):
+    """8f.4: the MLP circuit evaluated on the GPU == the gate-by-gate restatement of MLP_inference (every derived stream, hence every
+    label, access counter and value of the trace)."""
+    g, e = abis
+    cg, ce = g.trace_generate_mlp(shape), e.trace_generate_mlp(shape)
+    assert cg == ce
+    cs = 1
+    while cs < ce[2]:
+        cs *= 2
+    rng = np.random.default_rng(len(shape))
+    a_w, b_w = rand_field(rng, 1), rand_field(rng, 1)
+    for x, y in zip(g.trace_streams(cs, a_w, b_w, 0), e.trace_streams(cs, a_w, b_w, 0)):
+        assert np.array_equal(x, y)
