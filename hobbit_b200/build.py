@@ -53,6 +53,14 @@ def build_library(force=False, verbose=False):
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode:
             raise RuntimeError("host library build failed:\n%s\n%s" % (p.stdout, p.stderr))
+    # reference-free example / bench binary (tools/mlp_prove.cpp)
+    tool_src = os.path.join(HERE, "..", "tools", "mlp_prove.cpp")
+    tool_bin = os.path.join(HERE, "mlp_prove")
+    if os.path.exists(tool_src) and (force or _newer(tool_src, tool_bin) or _newer(host_lib, tool_bin)):
+        cmd = ["g++", "-O2", "-std=c++17", "-o", tool_bin, tool_src, "-L" + HERE, "-lhobbit_host", "-lhobbit_b200", "-Wl,-rpath,$ORIGIN"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode:
+            raise RuntimeError("mlp_prove build failed:\n%s\n%s" % (p.stdout, p.stderr))
     return LIB, log
 
 
