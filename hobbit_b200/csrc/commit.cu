@@ -467,6 +467,23 @@ extern "C" int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out) {
     return 0;
 }
 
+// The same, written level by level straight into the caller's per-level arrays (== MT_hashes[l].data(): no intermediate flat copy of the
+// 8B digests on the host).  level_ptrs[l] receives 4B >> l digests, l = 0 .. log2(4B).
+extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels) {
+    ElasticState &el = ctx->el;
+    if (!el.active) HB_FAIL(ctx, "hb_elastic_finish_levels: no commit in progress");
+    if (nlevels != ilog2(4 * el.B) + 1) HB_FAIL(ctx, "hb_elastic_finish_levels: expected log2(4B)+1 levels");
+    HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
+    size_t off = 0, n = 4 * el.B;
+    for (int l = 0; l < nlevels; l++, n /= 2) {
+        HB_CHECK(ctx, cudaMemcpyAsync(level_ptrs[l], el.leaves + off * 32, n * 32, cudaMemcpyDefault, ctx->stream));
+        off += n;
+    }
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    elastic_free(ctx);
+    return 0;
+}
+
 // W1: synthetic default stream of read_stream_PC (witness_stream.cpp:2405-2411).  The recurrence is inherently
 // sequential (x <- x^2 + i), it is the INPUT GENERATOR of test_Elastic_PC, so it is evaluated once on the host.
 extern "C" int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n) {

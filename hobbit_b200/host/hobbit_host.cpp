@@ -221,15 +221,18 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     std::vector<F> buff(BUFFER_SPACE);
     CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
     const F *res = fd.name == "witness" ? resident_stream(fd) : nullptr;         // what read_stream_PC forwards (:2365-2370): slices of the HBM-resident stream
+    const bool same_chunks = fd.name == "PC_layer";                              // built from the synthetic default stream: every chunk is the same
     for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++) {
         if (res) { CK(hb_elastic_push(backend(), (const hb_F *)(res + i * BUFFER_SPACE))); continue; }
-        read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
+        if (!(same_chunks && i > 0)) read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
         CK(hb_elastic_push(backend(), (const hb_F *)buff.data()));
     }
-    std::vector<uint8_t> flat((8 * BUFFER_SPACE - 1) * 32);
-    CK(hb_elastic_finish(backend(), flat.data()));
+    // every level goes straight from HBM into the caller's MT_hashes[l] (no intermediate flat copy of the 8B digests on the host)
     MT_hashes.clear();
-    flat_to_levels(flat, 4 * BUFFER_SPACE, MT_hashes);
+    std::vector<uint8_t *> ptrs;
+    for (size_t n = 4 * BUFFER_SPACE;; n /= 2) { MT_hashes.emplace_back(n); if (n == 1) break; }
+    for (auto &lv : MT_hashes) ptrs.push_back((uint8_t *)lv.data());
+    CK(hb_elastic_finish_levels(backend(), ptrs.data(), (int)ptrs.size()));
 }
 
 // ---- sumcheck.h ------------------------------------------------------------------------------------------------

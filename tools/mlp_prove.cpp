@@ -29,7 +29,8 @@ int main(int argc, char **argv) {
         double t1 = now();
         BUFFER_SPACE = (size_t)1 << b; if (BUFFER_SPACE > cs) BUFFER_SPACE = cs / 4;
         has_lookups = false;
-        a_w = F(random()); b_w = F(random());
+        a_w = F(random()); b_w = F(random());                 // main() (main.cpp:1227) ...
+        a_w = F(random()); b_w = F(random());                 // ... and again in prove_circuit (:873): same libc position as `pigeon 9 ...`
         double vt = 0; ps = 0;
         stream_descriptor fd1; fd1.name = "transcript_stream"; fd1.size = cs;
         stream_descriptor fd2; fd2.name = "wiring_consistency_check_opt"; fd2.size = 8 * cs;
