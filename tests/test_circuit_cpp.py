@@ -31,3 +31,19 @@ def test_mlp_circuit_host_logic_vs_reference(args):
 @pytest.mark.parametrize("args", [(12, 64, 32, 16), (11, 128, 16, 8), (14, 256, 64, 64, 16), (19, "aes", 4, 1), (11, "sql", 9, 1)])
 def test_mlp_circuit_gpu_vs_reference(args):
     _run(GPU, *args)
+
+
+@pytest.mark.gpu
+def test_mlp_prove_reference_free_ps_kat():
+    """Reference-free flow (GPU evaluator -> streams -> commit, product tree, gate consistency, open) at the libc position of
+    `pigeon 9 18 18 1 4 1024 256 256 16`: the proof-size counter must be the reference's 559.000000 KB (SURVEY §9 full-run KAT)."""
+    import json
+    binary = os.path.join(ROOT, "hobbit_b200", "mlp_prove")
+    if not os.path.exists(binary):
+        pytest.skip("hobbit_b200/mlp_prove not built")
+    p = subprocess.run([binary, "18", "1024", "256", "256", "16", "--reps", "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    print(line)
+    assert d["ps_kb"] == 559.0
