@@ -213,7 +213,7 @@ extern "C" int hb_field_binop(hb_ctx *ctx, int op, const hb_F *a, const hb_F *b,
     unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
     HB_LAUNCH(ctx, field_binop_kernel, grid, 256, 0, op, sa.as<F>(), sb.as<F>(), sc.as<F>(), n);
     HB_TRY(sc.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -240,7 +240,7 @@ extern "C" int hb_tensorcode(hb_ctx *ctx, const hb_F *msg, size_t n, int trs, in
     HB_TRY(t.outbuf(tensor, 4 * n * sizeof(F)));
     HB_TRY(tensorcode_dev(ctx, m.as<F>(), n, trs, linear_time, t.as<F>(), 1, nullptr));
     HB_TRY(t.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 

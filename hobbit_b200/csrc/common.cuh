@@ -76,6 +76,7 @@ struct hb_ctx {
     cudaStream_t copy_stream = nullptr; // H2D prefetch of the next chunk
     std::string err;
     uint64_t launches = 0;
+    bool sync_needed = false;           // set while a call has host-visible outputs (or pinned host inputs) in flight: see hb::end_call
     int sm_count = hb::kSMs;
     // twiddle tables w[k] = omega_len^k, k < len/2, cached per log2(len)
     hb::F *tw[32] = {};
@@ -134,6 +135,22 @@ inline bool is_device_ptr(const void *p) {
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+inline bool is_pinned_host_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+// End of a C-ABI call whose results may all live in device memory: the stream is synchronised only if something host-visible is in flight
+// (a host output buffer, or a pinned host input that a truly asynchronous copy is still reading; pageable inputs are copied to the driver's
+// staging buffer before cudaMemcpyAsync returns).  Calls on HBM-resident tables therefore stay stream-ordered and return immediately.
+inline int end_call(hb_ctx *ctx) {
+    if (ctx->sync_needed) {
+        ctx->sync_needed = false;
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e); return 1; }
+    }
+    return 0;
+}
 
 // RAII staging of a caller buffer: device pointers pass through, host pointers get a stream-ordered temporary.
 struct Staged {
@@ -144,6 +161,7 @@ struct Staged {
         if (n == 0) { dev = nullptr; return 0; }
         if (is_device_ptr(p)) { dev = const_cast<void *>(p); return 0; }
         owned = true; host = const_cast<void *>(p);
+        if (is_pinned_host_ptr(p)) ctx->sync_needed = true;
         HB_CHECK(ctx, cudaMallocAsync(&dev, n, ctx->stream));
         HB_CHECK(ctx, cudaMemcpyAsync(dev, p, n, cudaMemcpyHostToDevice, ctx->stream));
         return 0;
@@ -152,7 +170,7 @@ struct Staged {
         bytes = n; out = true;
         if (n == 0) { dev = nullptr; return 0; }
         if (is_device_ptr(p)) { dev = p; return 0; }
-        owned = true; host = p;
+        owned = true; host = p; ctx->sync_needed = true;
         HB_CHECK(ctx, cudaMallocAsync(&dev, n, ctx->stream));
         if (copy_in) HB_CHECK(ctx, cudaMemcpyAsync(dev, p, n, cudaMemcpyHostToDevice, ctx->stream));
         return 0;

@@ -224,6 +224,6 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_F *src, hb_F *dst, long lon
         HB_TRY(encode_cols_dev(ctx, d.as<F>(), n, ncols, 1, 0, nullptr, InnerLayout()));
     }
     HB_TRY(d.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }

@@ -201,7 +201,7 @@ extern "C" int hb_blake3_64(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_
     HB_TRY(s.in(src, count * 64)); HB_TRY(d.outbuf(dst, count * 32));
     HB_TRY(blake3_64_dev(ctx, s.as<uint8_t>(), d.as<uint8_t>(), count));
     HB_TRY(d.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -212,7 +212,7 @@ extern "C" int hb_merkle_tree(hb_ctx *ctx, uint8_t *levels, size_t nleaves) {
     HB_TRY(d.outbuf(levels, (2 * nleaves - 1) * 32, true));
     HB_TRY(merkle_tree_dev(ctx, d.as<uint8_t>(), nleaves));
     HB_TRY(d.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -225,6 +225,6 @@ extern "C" int hb_mt_commit(hb_ctx *ctx, const hb_F *leafs, size_t N, uint8_t *l
     HB_LAUNCH(ctx, mt_leaves_kernel, blocks_for(nl, 256), 256, 0, s.as<F>(), nl, d.as<uint8_t>());
     HB_TRY(merkle_tree_dev(ctx, d.as<uint8_t>(), nl));
     HB_TRY(d.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }

@@ -272,6 +272,6 @@ extern "C" int hb_ntt_batch(hb_ctx *ctx, hb_F *data, int logn, size_t batch, siz
     HB_TRY(d.outbuf(data, ((batch - 1) * stride + len) * sizeof(F), true));
     HB_TRY(ntt_rows_dev(ctx, d.as<F>(), logn, batch, stride));
     HB_TRY(d.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }

@@ -258,7 +258,7 @@ extern "C" int hb_rs_encode_rows(hb_ctx *ctx, const hb_F *src, size_t in_len, si
     HB_TRY(d.outbuf(dst, rows * len * sizeof(F)));
     HB_TRY(ntt_rows_padded_dev(ctx, s.as<F>(), in_len, d.as<F>(), len, logn, rows, 1, 0, 0));
     HB_TRY(d.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -282,7 +282,7 @@ extern "C" int hb_matvec_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
         cudaFreeAsync(part, ctx->stream);
     }
     HB_TRY(o.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -295,7 +295,7 @@ extern "C" int hb_matvec_rows(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     HB_TRY(o.outbuf(out, rows * sizeof(F)));
     HB_LAUNCH(ctx, matvec_rows_kernel, (unsigned)rows, 256, 0, m.as<F>(), cols, stride, ss.as<F>(), o.as<F>());
     HB_TRY(o.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -307,7 +307,7 @@ extern "C" int hb_axpy(hb_ctx *ctx, hb_F *y, const hb_F *x, const hb_F *a, size_
     hb_F ah; HB_CHECK(ctx, cudaMemcpy(&ah, a, sizeof(F), cudaMemcpyDefault));
     HB_LAUNCH(ctx, axpy_vec_kernel, grid_1d(ctx, n), 256, 0, sy.as<F>(), sx.as<F>(), mkF(ah.real, ah.img), n);
     HB_TRY(sy.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -322,7 +322,7 @@ extern "C" int hb_scatter(hb_ctx *ctx, hb_F *out, size_t n, const uint64_t *idx,
         HB_LAUNCH(ctx, scatter_kernel, (unsigned)((m + 255) / 256), 256, 0, so.as<F>(), si.as<unsigned long long>(), sv.as<F>(), m);
     }
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -334,7 +334,7 @@ extern "C" int hb_gather_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     HB_TRY(so.outbuf(out, m * rows * sizeof(F)));
     HB_LAUNCH(ctx, gather_cols_kernel, (unsigned)((m * rows + 255) / 256), 256, 0, sm.as<F>(), rows, stride, sc.as<unsigned long long>(), m, so.as<F>());
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -346,7 +346,7 @@ extern "C" int hb_select_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     HB_TRY(so.outbuf(out, m * rows * sizeof(F)));
     HB_LAUNCH(ctx, select_cols_kernel, (unsigned)((m * rows + 255) / 256), 256, 0, sm.as<F>(), rows, stride, sc.as<unsigned long long>(), m, so.as<F>());
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -357,7 +357,7 @@ extern "C" int hb_transpose(hb_ctx *ctx, const hb_F *in, size_t rows, size_t col
     HB_TRY(so.outbuf(out, rows * cols * sizeof(F)));
     HB_LAUNCH(ctx, transpose_kernel, dim3((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), 256, 0, si.as<F>(), rows, cols, so.as<F>());
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -393,7 +393,7 @@ extern "C" int hb_phi_g_init(hb_ctx *ctx, const hb_F *r, int n, hb_F *out) {
         HB_LAUNCH(ctx, phi_g_level_kernel, grid_1d(ctx, (size_t)1 << (i - 1)), 256, 0, sr.as<F>(), n, i, tw, so.as<F>());
     HB_LAUNCH(ctx, phi_g_final_kernel, grid_1d(ctx, N / 2), 256, 0, sr.as<F>(), n, tw, so.as<F>());
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -405,7 +405,7 @@ extern "C" int hb_shockwave_leaves(hb_ctx *ctx, const hb_F *enc, int k, size_t c
     HB_TRY(sl.outbuf(leaves, cols * 32));
     HB_LAUNCH(ctx, shockwave_leaves_kernel, (unsigned)((cols + 255) / 256), 256, 0, se.as<F>(), ilog2((size_t)k / 4), cols, sl.as<uint8_t>());
     HB_TRY(sl.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -423,7 +423,7 @@ extern "C" int hb_change_form(hb_ctx *ctx, hb_F *poly, int logn) {
     if (a != sp.as<F>()) HB_CHECK(ctx, cudaMemcpyAsync(sp.dev, a, n * sizeof(F), cudaMemcpyDeviceToDevice, ctx->stream));
     cudaFreeAsync(tmp, ctx->stream);
     HB_TRY(sp.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -434,7 +434,7 @@ extern "C" int hb_regroup(hb_ctx *ctx, const hb_F *in, size_t n, int k, hb_F *ou
     HB_TRY(so.outbuf(out, n * sizeof(F)));
     HB_LAUNCH(ctx, regroup_kernel, grid_1d(ctx, n), 256, 0, si.as<F>(), so.as<F>(), n, k);
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -455,7 +455,7 @@ extern "C" int hb_whir_fold(hb_ctx *ctx, hb_F *poly, hb_F *beta, size_t L, const
     HB_TRY(sp.outbuf(poly, 2 * L * sizeof(F), true)); HB_TRY(sb.outbuf(beta, 2 * L * sizeof(F), true));
     HB_LAUNCH(ctx, whir_fold_kernel, grid_1d(ctx, L), 256, 0, sp.as<F>(), sb.as<F>(), L, mkF(a->real, a->img));
     HB_TRY(sp.finish()); HB_TRY(sb.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -477,6 +477,6 @@ extern "C" int hb_whir_zeta(hb_ctx *ctx, const hb_F *poly, hb_F *beta, int v, co
     HB_LAUNCH(ctx, whir_zeta_beta_kernel, grid_1d(ctx, n), 256, 0, sb.as<F>(), n, repeats, hlo, v, lo, hi, spw.as<F>());
     cudaFreeAsync(tab, ctx->stream);
     HB_TRY(sy.finish()); HB_TRY(sb.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }

@@ -580,7 +580,7 @@ extern "C" int hb_precompute_beta(hb_ctx *ctx, const hb_F *r, int nr, hb_F *out)
     HB_TRY(so.outbuf(out, sizeof(F) << nr));
     HB_TRY(beta_dev(ctx, sr.as<F>(), nr, so.as<F>()));
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 

@@ -361,7 +361,7 @@ extern "C" int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out) {
     HB_CHECK(ctx, cudaMemsetAsync(so.dev, 0, 4 * cs * sizeof(F), ctx->stream));
     if (t.n) HB_LAUNCH(ctx, trace_witness_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, t.pos + 3 * t.n, cs, so.as<F>());
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -374,7 +374,7 @@ extern "C" int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F
     if (t.n) HB_LAUNCH(ctx, trace_transcript_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, has_lookups,
                        sl.as<F>(), sr.as<F>(), so.as<F>(), ss.as<F>());
     for (Staged *s : {&sl, &sr, &so, &ss}) HB_TRY(s->finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -388,7 +388,7 @@ extern "C" int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb
     if (t.n) HB_LAUNCH(ctx, trace_wiring_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, t.pos + 3 * t.n, cs,
                        mkF(a_w->real, a_w->img), mkF(b_w->real, b_w->img), X, Y);
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -433,7 +433,7 @@ extern "C" int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_
                        mkF(lr[0].real, lr[0].img), mkF(lr[1].real, lr[1].img), mkF(lr[2].real, lr[2].img), mkF(lr[3].real, lr[3].img), X, Y);
     cudaFreeAsync(scratch, ctx->stream);
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }
 
@@ -450,6 +450,6 @@ extern "C" int hb_trace_lookup_witness(hb_ctx *ctx, size_t cs, const hb_F *looku
                        mkF(lr[0].real, lr[0].img), mkF(lr[1].real, lr[1].img), so.as<F>());
     cudaFreeAsync(scratch, ctx->stream);
     HB_TRY(so.finish());
-    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    HB_TRY(end_call(ctx));
     return 0;
 }

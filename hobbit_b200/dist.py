@@ -63,6 +63,7 @@ class GpuBackend:
         lv[:n] = leaves
         torch.cuda.synchronize()
         self.ctx.merkle_tree_inplace(lv.data_ptr(), n)
+        self.ctx.sync()                  # device-pointer calls are stream-ordered on the library's stream: hand back to torch's
         return lv
 
 

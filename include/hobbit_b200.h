@@ -11,8 +11,11 @@
  *  - hb_F is the reference's 16-byte POD `virgo::fieldElement {u64 real; u64 img}` (fieldElement.hpp:96-97),
  *    canonical limbs in [0, 2^61-1).  Digests are 32 raw bytes == reference `_hash` (Blake3_hash.h:3-5).
  *  - every DATA pointer may be host memory (pageable or pinned) or device memory; the library detects which
- *    (cudaPointerGetAttributes) and stages copies on the context's stream.  Outputs are complete when the call
- *    returns unless the function name ends in `_async`.
+ *    (cudaPointerGetAttributes) and stages copies on the context's stream.  HOST outputs are complete when the call
+ *    returns.  The building-block calls (field, NTT, encode, Merkle, eq tables, the 8f.1 and trace primitives) whose data pointers
+ *    are ALL device memory are stream-ordered on the context's stream and return without synchronising it, so that a chain of
+ *    them on HBM-resident tables costs launches only; use hb_sync (or hb_stream + events) before touching such results from
+ *    another stream.  The provers and the commit entry points always synchronise.
  *  - a context is bound to one CUDA device and is thread-compatible (one caller at a time), like the reference's
  *    non-reentrant entry points.
  *  - there is NO CPU fallback: without a CUDA device hb_ctx_create fails.
