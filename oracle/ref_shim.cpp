@@ -25,6 +25,7 @@
 #include "witness_stream.h"
 #include "Elastic_PC.hpp"
 #include "sumcheck.h"
+#include "Virgo.h"
 #include "PC_utils.h"
 
 extern bool linear_time;
@@ -426,6 +427,43 @@ double ref_circuit_gate_consistency(const uint64_t *r, int nr, double *ps_out) {
     auto t1 = std::chrono::steady_clock::now();
     *ps_out = ps;
     return std::chrono::duration_cast<std::chrono::duration<double>>(t1 - t0).count();
+}
+
+// ---- 8f.1 building blocks, for golden vectors (tests/golden/make_golden.py) ------------------------------------------------------------
+void ref_phi_g_init(const uint64_t *r, int n, uint64_t *out) {                 // utils.cpp:694-755, forward transform, scale 1
+    vector<F> rv((const F *)r, (const F *)r + n), g((size_t)1 << n, F(0));
+    phiGInit(g, rv.begin(), F(1), n, false);
+    memcpy(out, g.data(), g.size() * 16);
+}
+void ref_change_form(uint64_t *poly, int logn) {                                // Virgo.cpp:104-118
+    vector<F> p((const F *)poly, (const F *)poly + ((size_t)1 << logn));
+    change_form(p, logn, 0, 0);
+    memcpy(poly, p.data(), p.size() * 16);
+}
+// shockwave_commit (Virgo.cpp:120-157): encoded matrix (k x 2N/k) and every Merkle level (leaves first)
+void ref_shockwave_commit(const uint64_t *poly, size_t N, int k, uint64_t *encoded, uint8_t *levels) {
+    vector<F> p((const F *)poly, (const F *)poly + N);
+    shockwave_data *d = shockwave_commit(p, k);
+    for (int i = 0; i < k; i++) memcpy(encoded + 2 * (size_t)i * (2 * N / k), d->encoded_matrix[i], (2 * N / k) * 16);
+    levels_to_flat(d->MT, levels);
+    delete d;
+}
+void ref_whir_commit(const uint64_t *poly, size_t N, uint8_t *levels) {          // Virgo.cpp:160-178
+    vector<F> p((const F *)poly, (const F *)poly + N);
+    Whir_data D; whir_commit(p, D);
+    levels_to_flat(D.MT, levels);
+}
+// prove_fft (sumcheck.cpp:2975-2987): flat 2-product proof of 4*rounds+3 elements (rounds = log2(2n)); randomness as returned (last popped -> zeroed)
+double ref_prove_fft(const uint64_t *m, size_t n, const uint64_t *r, const uint64_t *prev_sum, uint64_t *out) {
+    vector<F> mv((const F *)m, (const F *)m + n); int rounds = 0; while (((size_t)1 << rounds) < 2 * n) rounds++;
+    vector<F> rv((const F *)r, (const F *)r + rounds);
+    double vt = 0, ps = 0;
+    proof P = prove_fft(mv, rv, *(const F *)prev_sum, vt, ps);
+    F *o = (F *)out; size_t k = 0;
+    for (int i = 0; i < rounds; i++) { o[k++] = P.q_poly[i].a; o[k++] = P.q_poly[i].b; o[k++] = P.q_poly[i].c; }
+    for (int i = 0; i < rounds; i++) o[k++] = i < (int)P.randomness[0].size() ? P.randomness[0][i] : F(0);
+    o[k++] = P.vr[0]; o[k++] = P.vr[1]; o[k++] = P.final_rand;
+    return ps;
 }
 
 } // extern "C"
