@@ -356,18 +356,50 @@ extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t 
     if (total_groups == 0) { total_groups = ngroups; first_group = 0; }
     const size_t cells = 4 * B;
     if (cells % leaf_parts || first_group + ngroups > total_groups) HB_FAIL(ctx, "hb_elastic_encode_groups: bad leaf_parts / group range");
-    Staged p(ctx), in(ctx);
-    HB_TRY(p.in(chunks, ngroups * 4 * B * sizeof(F)));
+    Staged in(ctx);
     HB_TRY(in.outbuf(inner_out, ngroups * cells * 32));
     // a launch covers up to 1 GiB of encoded tensors (64 B per coefficient)
-    const size_t G = std::max<size_t>(1, std::min<size_t>(ngroups, ((size_t)1 << 30) / (16 * B * sizeof(F))));
+    size_t G = std::max<size_t>(1, std::min<size_t>(ngroups, ((size_t)1 << 30) / (16 * B * sizeof(F))));
+    if (const char *cap = getenv("HB_ELASTIC_GROUPS_PER_LAUNCH")) G = std::max<size_t>(1, std::min<size_t>(G, (size_t)atoll(cap)));   // tests: force several launches
     F *T4; HB_CHECK(ctx, cudaMallocAsync(&T4, G * 16 * B * sizeof(F), ctx->stream));
+    const bool on_dev = is_device_ptr(chunks);
+    // Host stream (pinned memory for full PCIe rate): the chunks of launch g+1 are copied on the copy stream into the other half of a
+    // double buffer while launch g is encoded — the witness never has to be resident, 16 B per coefficient cross PCIe exactly once.
+    F *stage[2] = {nullptr, nullptr}; cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    if (!on_dev) {
+        for (int q = 0; q < 2; q++) {
+            HB_CHECK(ctx, cudaMallocAsync(&stage[q], G * 4 * B * sizeof(F), ctx->stream));
+            HB_CHECK(ctx, cudaEventCreateWithFlags(&copied[q], cudaEventDisableTiming));
+            HB_CHECK(ctx, cudaEventCreateWithFlags(&freed[q], cudaEventDisableTiming));
+            HB_CHECK(ctx, cudaEventRecord(freed[q], ctx->stream));                       // the buffers exist (stream-ordered allocation) from here on
+        }
+        ctx->sync_needed = true;
+    }
+    auto prefetch = [&](size_t g0) -> int {
+        const int q = (int)((g0 / G) & 1); const size_t ng = std::min(G, ngroups - g0);
+        HB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, freed[q], 0));
+        HB_CHECK(ctx, cudaMemcpyAsync(stage[q], (const F *)chunks + g0 * 4 * B, ng * 4 * B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
+        HB_CHECK(ctx, cudaEventRecord(copied[q], ctx->copy_stream));
+        return 0;
+    };
+    if (!on_dev) HB_TRY(prefetch(0));
     for (size_t g0 = 0; g0 < ngroups; g0 += G) {
         size_t ng = std::min(G, ngroups - g0);
-        int rc = tensorcode_dev(ctx, p.as<F>() + g0 * 4 * B, B, trs, linear_time, T4, 4 * ng, nullptr);
+        const int q = (int)((g0 / G) & 1);
+        const F *src = on_dev ? (const F *)chunks + g0 * 4 * B : stage[q];
+        if (!on_dev) {
+            HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, copied[q], 0));
+            if (g0 + G < ngroups) HB_TRY(prefetch(g0 + G));                              // overlaps the encode below
+        }
+        int rc = tensorcode_dev(ctx, src, B, trs, linear_time, T4, 4 * ng, nullptr);
+        if (!on_dev) HB_CHECK(ctx, cudaEventRecord(freed[q], ctx->stream));              // stage[q] may be overwritten once this encode has read it
         InnerLayout lay; lay.part_leaves = cells / leaf_parts; lay.chunks_total = ngroups; lay.chunk0 = g0;
         if (!rc) rc = md_inner_stream4_dev(ctx, T4, cells, ng, in.as<uint8_t>(), lay);
         if (rc) { cudaFreeAsync(T4, ctx->stream); return rc; }
+    }
+    if (!on_dev) {
+        HB_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        for (int q = 0; q < 2; q++) { cudaFreeAsync(stage[q], ctx->stream); cudaEventDestroy(copied[q]); cudaEventDestroy(freed[q]); }
     }
     cudaFreeAsync(T4, ctx->stream);
     HB_TRY(in.finish());

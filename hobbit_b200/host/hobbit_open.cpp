@@ -80,11 +80,15 @@ static DV eq_dev(const std::vector<F> &r) {
 }
 static F fpow(F b, unsigned long long e) { F r(1); while (e) { if (e & 1) r = r * b; b = b * b; e >>= 1; } return r; }
 // zero table with the listed entries set; the reference writes sequentially, so for duplicate positions the LAST write wins
-static DV sparse_dev(size_t n, const std::vector<size_t> &idx, const std::vector<F> &val) {
-    std::unordered_map<size_t, size_t> last;
-    for (size_t i = 0; i < idx.size(); i++) last[idx[i]] = i;
-    std::vector<uint64_t> ui; std::vector<F> uv; ui.reserve(last.size()); uv.reserve(last.size());
-    for (auto &kv : last) { ui.push_back(kv.first); uv.push_back(val[kv.second]); }
+static DV sparse_dev(size_t n, const std::vector<size_t> &idx, const std::vector<F> &val, bool unique = false) {
+    std::vector<uint64_t> ui; std::vector<F> uv;
+    if (unique) { ui.assign(idx.begin(), idx.end()); uv = val; }                    // positions distinct by construction: no de-duplication pass
+    else {
+        std::unordered_map<size_t, size_t> last;
+        for (size_t i = 0; i < idx.size(); i++) last[idx[i]] = i;
+        ui.reserve(last.size()); uv.reserve(last.size());
+        for (auto &kv : last) { ui.push_back(kv.first); uv.push_back(val[kv.second]); }
+    }
     DV d(n);
     CK(hb_scatter(backend(), abi(d.p), n, ui.data(), abi(uv.data()), ui.size()));
     return d;
@@ -429,6 +433,7 @@ static void recursive_prover_RS_dev(const F *agg, size_t B, const std::vector<st
     collumns.push_back(I_t[0]);
     for (size_t i = 1; i < I_t.size(); i++) if (I_t[i] != I_t[i - 1]) collumns.push_back(I_t[i]);
     const size_t ncu = collumns.size(), np2 = next_pow2(ncu);
+    Trace trs_("    recursive_prover_RS");
     DV out_1(trs * cols);
     CK(hb_rs_encode_rows(backend(), abi(agg), half, trs, abi(out_1.p), lg2(cols)));
     DV selected(np2 * trs, true);                                 // selected_collumns[i][j] = out_1[j][collumns[i]]
@@ -439,6 +444,7 @@ static void recursive_prover_RS_dev(const F *agg, size_t B, const std::vector<st
     std::vector<F> r = generate_randomness((int)I.size());
     proof P0;
     {
+        Trace t("      P0 (query sumcheck)");
         std::map<size_t, F> acc;                                  // beta[counter*2trs + I[i][1]] += r[i]   (:437-446)
         size_t counter = 0;
         for (size_t i = 0; i < I.size(); i++) {
@@ -453,18 +459,21 @@ static void recursive_prover_RS_dev(const F *agg, size_t B, const std::vector<st
         DV beta = sparse_dev(np2 * 2 * trs, idx, val);
         P0 = sc2(out_3.p, beta.p, np2 * 2 * trs, F(323), ps);
     }
-    proof P2 = prove_fft_matrix_ptr(selected.p, np2, trs, P0.randomness[0], P0.vr[0], ps);
+    proof P2;
+    { Trace t("      P2 (fft matrix)"); P2 = prove_fft_matrix_ptr(selected.p, np2, trs, P0.randomness[0], P0.vr[0], ps); }
     std::vector<F> r_point;
     for (size_t i = lg2(trs); i < P2.randomness[0].size(); i++) r_point.push_back(P2.randomness[0][i]);
     r.clear(); precompute_beta(r_point, r);
     proof P3;
     {
+        Trace t("      P3 (column sumcheck)");
         std::vector<size_t> idx; std::vector<F> val;
         for (size_t i = 0; i < ncu; i++) for (size_t j = 0; j < trs; j++) { idx.push_back(collumns[i] + j * cols); val.push_back(r[i]); }
-        DV beta = sparse_dev(trs * cols, idx, val);
+        DV beta = sparse_dev(trs * cols, idx, val, true);
         P3 = sc2(out_1.p, beta.p, trs * cols, F(323), ps);
     }
-    proof P5 = prove_fft_matrix_ptr(agg, trs, half, P3.randomness[0], P3.vr[0], ps);
+    proof P5;
+    { Trace t("      P5 (fft matrix)"); P5 = prove_fft_matrix_ptr(agg, trs, half, P3.randomness[0], P3.vr[0], ps); }
     shockwave_prove(C_f, P5.randomness[0], vt, ps); C_f = nullptr;
 }
 void recursive_prover_RS(std::vector<F> &aggregated_vector, std::vector<std::vector<size_t>> I, double &vt, double &ps) {

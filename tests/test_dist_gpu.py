@@ -56,6 +56,21 @@ def test_elastic_group_pieces_equal_streaming_commit(lin):
     ctx.close()
 
 
+def test_elastic_groups_from_pinned_host_double_buffered(monkeypatch):
+    """The stream in pinned HOST memory, one group per launch: the copy of launch g+1 overlaps the encode of launch g (two staging buffers)."""
+    import torch
+    from hobbit_b200.dist import GpuBackend, elastic_commit_sharded
+    monkeypatch.setenv("HB_ELASTIC_GROUPS_PER_LAUNCH", "1")
+    ngroups, B, trs = 5, 1 << 12, 16
+    ctx = setup_ctx(0, trs)
+    stream = rand_field(np.random.default_rng(17), ngroups * 4 * B, full=True)
+    want = _elastic_levels(ctx, stream, B, trs, 1)
+    pinned = torch.from_numpy(stream.view(np.int64)).pin_memory()
+    got = elastic_commit_sharded(GpuBackend(ctx, torch.device("cuda", 0)), pinned.data_ptr(), ngroups, B, trs, 1)
+    assert np.array_equal(got.cpu().numpy(), want)
+    ctx.close()
+
+
 def _elastic_worker(rank, world, port, ngroups, B, trs, ret):
     import torch
     import torch.distributed as dist

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--lin", type=int, default=1)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--pinned", action="store_true", help="commit: stream this rank's chunks from pinned host memory (double buffered) instead of HBM")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -64,6 +65,9 @@ def main():
     gl = ngroups // world
     local_stream = torch.from_numpy(chunk.view(np.int64)).to(dev).repeat(4 * gl, 1)      # (4*gl*B, 2)
     torch.cuda.synchronize()
+    host_stream = None
+    if a.pinned:
+        host_stream = torch.from_numpy(chunk.view(np.int64)).repeat(4 * gl, 1).pin_memory()
 
     def barrier():
         torch.cuda.synchronize()
@@ -74,7 +78,7 @@ def main():
     t_commit, t_open, levels = [], [], None
     for rep in range(a.reps + 1):
         barrier(); t0 = time.perf_counter()
-        levels = elastic_commit_sharded(be, local_stream.data_ptr(), ngroups, B, trs, a.lin)
+        levels = elastic_commit_sharded(be, host_stream.data_ptr() if a.pinned else local_stream.data_ptr(), ngroups, B, trs, a.lin)
         barrier(); t1 = time.perf_counter()
         # ---- open (Elastic_PC.cpp:625-726) ----
         x = np.zeros((a.logn, 2), dtype=np.uint64)
@@ -127,7 +131,7 @@ def main():
         c, o = min(t_commit), min(t_open)
         print(json.dumps({"workload": "test_Elastic_PC(2^%d, %s), BUFFER_SPACE 2^%d, tensor_row_size %d" % (a.logn, "Orion columns" if a.lin else "RS columns", a.logb, trs),
                           "n_gpus": world, "commit_s": round(c, 5), "open_s": round(o, 5), "commit_field_elems_per_s": round(N / c, 1),
-                          "commit_open_field_elems_per_s": round(N / (c + o), 1), "open_ps_kb": ps.value, "stream": "resident in HBM (one chunk replicated)",
+                          "commit_open_field_elems_per_s": round(N / (c + o), 1), "open_ps_kb": ps.value, "stream": ("commit from pinned host memory, double buffered; open from HBM" if a.pinned else "resident in HBM (one chunk replicated)"),
                           "levels_equal_oracle": ok}))
     if world > 1:
         dist.destroy_process_group()
