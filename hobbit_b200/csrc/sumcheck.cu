@@ -26,20 +26,34 @@ template <int NT> struct Tabs { const F *in[NT]; F *out[NT]; };
 
 __device__ __forceinline__ F fold1(F x, F y, F r) { return fadd(x, fmul(r, fsub(y, x))); }
 
-// coefficients of prod_t (d_t * X + x_t), highest degree first, accumulated into acc[NT+1]
+// Round polynomial prod_t (x_t + X (y_t - x_t)) accumulated in EVALUATION form — fewer multiplications than its coefficients:
+//   NT = 2: acc = { P(inf) = d1 d2, P(1) = y1 y2, P(0) = x1 x2 }                                  (3 instead of 4)
+//   NT = 3: acc = { P(inf) = d1 d2 d3, P(1) = y1 y2 y3, P(-1) = (2x1-y1)(2x2-y2)(2x3-y3), P(0) }    (8 instead of 10)
+// The sums over all pairs are linear in these, so the coefficients (a, b, c[, d]) the reference accumulates directly are recovered
+// exactly on the host from the reduced sums (coeffs_from_evals); all arithmetic is exact in F_p^2, so the bits are the same.
 template <int NT> __device__ __forceinline__ void poly_acc(F (&acc)[NT + 1], const F (&x)[NT], const F (&y)[NT]) {
     if (NT == 2) {
         F d1 = fsub(y[0], x[0]), d2 = fsub(y[1], x[1]);
         acc[0] = fadd(acc[0], fmul(d1, d2));
-        acc[1] = fadd(acc[1], fadd(fmul(d1, x[1]), fmul(d2, x[0])));
+        acc[1] = fadd(acc[1], fmul(y[0], y[1]));
         acc[2] = fadd(acc[2], fmul(x[0], x[1]));
     } else if (NT == 3) {
         F d1 = fsub(y[0], x[0]), d2 = fsub(y[1], x[1]), d3 = fsub(y[2], x[2]);
-        F qa = fmul(d1, d2), qb = fadd(fmul(d1, x[1]), fmul(d2, x[0])), qc = fmul(x[0], x[1]);
-        acc[0] = fadd(acc[0], fmul(qa, d3));
-        acc[1] = fadd(acc[1], fadd(fmul(qa, x[2]), fmul(qb, d3)));
-        acc[2] = fadd(acc[2], fadd(fmul(qb, x[2]), fmul(qc, d3)));
-        acc[3] = fadd(acc[3], fmul(qc, x[2]));
+        F m1 = fsub(x[0], d1), m2 = fsub(x[1], d2), m3 = fsub(x[2], d3);
+        acc[0] = fadd(acc[0], fmul(fmul(d1, d2), d3));
+        acc[1] = fadd(acc[1], fmul(fmul(y[0], y[1]), y[2]));
+        acc[2] = fadd(acc[2], fmul(fmul(m1, m2), m3));
+        acc[3] = fadd(acc[3], fmul(fmul(x[0], x[1]), x[2]));
+    }
+}
+// host side: evaluation sums -> coefficients, highest degree first (1/2 = 2^60 mod p)
+template <int NT> static inline void coeffs_from_evals(F *co) {
+    if (NT == 2) co[1] = fsub(fsub(co[1], co[0]), co[2]);
+    else if (NT == 3) {
+        const F inv2 = mkF((u64)1 << 60, 0);
+        const F a = co[0], p1 = co[1], pm1 = co[2], d = co[3];
+        co[1] = fsub(h_fmul(fadd(p1, pm1), inv2), d);
+        co[2] = fsub(h_fmul(fsub(p1, pm1), inv2), a);
     }
 }
 
@@ -479,7 +493,7 @@ template <int NT, int MODE, bool IL>
 static int launch_round(hb_ctx *ctx, const Tabs<NT> &t, size_t L, F r, F *coeffs_host /* NT+1, may be null for FOLD_ONLY */) {
     HB_TRY(ensure_scratch(ctx));
     HB_LAUNCH(ctx, (sc_round_kernel<NT, MODE, IL>), grid_for(ctx, L), 256, 0, t, L, r, ctx->red, ctx->ticket, ctx->mailbox_dev);
-    if (MODE != FOLD_ONLY) HB_TRY(read_result(ctx, NT + 1, coeffs_host));
+    if (MODE != FOLD_ONLY) { HB_TRY(read_result(ctx, NT + 1, coeffs_host)); coeffs_from_evals<NT>(coeffs_host); }
     return 0;
 }
 
