@@ -79,6 +79,25 @@ trace_wiring_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__
         Y[p] = feq(x0, one) ? x0 : fadd(x0, b_w); Y[p + 1] = feq(x1, one) ? x1 : fadd(x1, b_w); Y[p + 2] = feq(x2, one) ? x2 : fadd(x2, b_w);
     }
 }
+// "circuit" (16cs, no lookups; witness_stream.cpp:2123-2162 with read_circuit_trace :2021-2104 and read_memory_circuit :1812-2019):
+//   [ selector per op record: 1 add / 0 mul (cs) | (idx, access) pairs of (l, r, o) per op record (6cs) | (idx_o, access_o) pairs per
+//     delete record (2cs) | zeros (7cs) ]   — zero padded inside each section (memset by the caller)
+__global__ void __launch_bounds__(256)
+trace_circuit_kernel(const TrTuple *__restrict__ tr, size_t n, const unsigned *__restrict__ op_pos, const unsigned *__restrict__ del_pos, size_t cs, F *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrTuple &t = tr[i];
+    if (t.type == 255) return;
+    if (t.type == 0) {
+        F *m = out + cs + 6 * cs + 2 * (size_t)del_pos[i];
+        m[0] = f_int(t.idx_o); m[1] = f_int(t.access_o);
+    } else {
+        const size_t p = op_pos[i];
+        out[p] = mkF(t.type == 1 ? 1 : 0, 0);
+        F *m = out + cs + 6 * p;
+        m[0] = f_int(t.idx_l); m[1] = f_int(t.access_l); m[2] = f_int(t.idx_r); m[3] = f_int(t.access_r); m[4] = f_int(t.idx_o); m[5] = f_int(t.access_o);
+    }
+}
 // ---- lookup streams (witness_stream.cpp:920-1053, 2198-2247) -------------------------------------------------------------------------
 // The reference threads a mutable access_table through the pass: a lookup record carries the number of EARLIER lookups of the same table
 // entry.  On the GPU that is the rank of the record among equal (table, entry) keys in trace order: a stable radix sort of the keys,
@@ -360,6 +379,18 @@ extern "C" int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out) {
     HB_TRY(so.outbuf(out, 4 * cs * sizeof(F)));
     HB_CHECK(ctx, cudaMemsetAsync(so.dev, 0, 4 * cs * sizeof(F), ctx->stream));
     if (t.n) HB_LAUNCH(ctx, trace_witness_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, t.pos + 3 * t.n, cs, so.as<F>());
+    HB_TRY(so.finish());
+    HB_TRY(end_call(ctx));
+    return 0;
+}
+
+extern "C" int hb_trace_circuit(hb_ctx *ctx, size_t cs, hb_F *out) {
+    HB_TRY(trace_check(ctx, cs, "hb_trace_circuit"));
+    TraceState &t = ctx->trace;
+    Staged so(ctx);
+    HB_TRY(so.outbuf(out, 16 * cs * sizeof(F)));
+    HB_CHECK(ctx, cudaMemsetAsync(so.dev, 0, 16 * cs * sizeof(F), ctx->stream));
+    if (t.n) HB_LAUNCH(ctx, trace_circuit_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, t.pos + 2 * t.n, t.pos + 3 * t.n, cs, so.as<F>());
     HB_TRY(so.finish());
     HB_TRY(end_call(ctx));
     return 0;

@@ -28,7 +28,8 @@ static_assert(sizeof(tr_tuple) == 80, "tr_tuple must match the reference layout 
 
 namespace {
 struct Resident { F *p = nullptr; size_t n = 0; void ensure(size_t want) { if (n != want) { if (p) hb_free_device(backend(), p); void *q; CK(hb_malloc_device(backend(), &q, want * sizeof(F))); p = (F *)q; n = want; } } };
-Resident g_witness, g_trL, g_trR, g_trO, g_trS, g_wiring, g_lkp_basic, g_lkp_wit;
+Resident g_witness, g_trL, g_trR, g_trO, g_trS, g_wiring, g_lkp_basic, g_lkp_wit, g_circuit;
+bool have_circuit = false;
 bool have_witness = false, have_transcript = false, have_wiring = false, tr_lookups = false, have_lkp_basic = false, have_lkp_wit = false;
 F wiring_a, wiring_b;
 std::vector<F> lkp_rand_basic, lkp_rand_wit;
@@ -37,7 +38,7 @@ bool trace_loaded = false;
 
 void trace_begin(size_t capacity_hint) {
     CK(hb_trace_begin(backend(), capacity_hint));
-    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = false;
+    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
 }
 bool trace_append(const tr_tuple *buf, size_t n) {
     int done = 0;
@@ -48,7 +49,7 @@ bool trace_append(const tr_tuple *buf, size_t n) {
 void trace_generate_mlp(const std::vector<int> &layer_size) {
     size_t n = 0;
     CK(hb_trace_generate_mlp(backend(), layer_size.data(), (int)layer_size.size(), &n));
-    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = false;
+    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
 }
 // get_circuit_size (main.cpp:303-321): the number of delete records, rounded up to a power of two
 size_t trace_end() {
@@ -87,6 +88,12 @@ static const F *wiring_dev() {
     return g_wiring.p;
 }
 
+static const F *circuit_dev() {
+    need_trace("circuit");
+    if (has_lookups) { printf("hobbit_b200: stream 'circuit' with lookups is not built\n"); exit(-1); }
+    if (!have_circuit) { g_circuit.ensure(16 * circuit_size); CK(hb_trace_circuit(backend(), circuit_size, abi(g_circuit.p))); have_circuit = true; }
+    return g_circuit.p;
+}
 static void need_lookup_rand() {
     if (lookup_rand.size() < 4) { printf("hobbit_b200: lookup streams need lookup_rand (4 values, main.cpp:911)\n"); exit(-1); }
 }
@@ -113,6 +120,7 @@ static const F *lookup_witness_dev() {
 const F *resident_stream(const stream_descriptor &fd) {
     if (fd.name == "witness") return witness_dev();
     if (fd.name == "wiring_consistency_check_opt") return wiring_dev();
+    if (fd.name == "circuit") return circuit_dev();
     if (fd.name == "lookup_basic") return lookup_basic_dev();
     if (fd.name == "lookup_witness_basic") return lookup_witness_dev();
     return nullptr;
@@ -121,12 +129,14 @@ const F *resident_stream(const stream_descriptor &fd) {
 // read_stream for the circuit names (witness_stream.cpp:2163-2178, 2276-2311): block `fd.pos` of `size` elements, copied out of HBM.
 // "wiring_consistency_check_opt" blocks are X-half | Y-half of size/2 each.
 bool read_circuit_stream(stream_descriptor &fd, std::vector<F> &v, int size) {
-    if (fd.name == "witness") {
-        const F *w = witness_dev();
+    if (fd.name == "witness" || fd.name == "circuit") {
+        const bool wit = fd.name == "witness";
+        const F *w = wit ? witness_dev() : circuit_dev();
+        const size_t len = (wit ? 4 : 16) * circuit_size;
         size_t off = fd.pos * (size_t)size;
-        if (off + size > 4 * circuit_size) { printf("hobbit_b200: read past the end of stream 'witness'\n"); exit(-1); }
+        if (off + size > len) { printf("hobbit_b200: read past the end of stream '%s'\n", fd.name.c_str()); exit(-1); }
         CK(hb_memcpy(backend(), v.data(), w + off, (size_t)size * sizeof(F)));
-        fd.pos = (fd.pos + 1) % (4 * circuit_size / size);
+        fd.pos = (fd.pos + 1) % (len / size);
         return true;
     }
     if (fd.name == "wiring_consistency_check_opt" || fd.name == "lookup_basic") {           // two-half streams: X block | Y block per read

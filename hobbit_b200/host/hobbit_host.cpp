@@ -324,14 +324,14 @@ mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input,
 void reset_stream(stream_descriptor &fd) { fd.pos = 0; fd.idx = 0; fd.stage = 0; fd.offset = 0; fd.finished = false; }   // witness_stream.cpp:228-234
 void read_stream(stream_descriptor &fd, std::vector<F> &v, int size) {                                                   // :2106-2353, default branch
     if (read_circuit_stream(fd, v, size)) return;
-    static const char *circuit_names[] = {"input", "circuit", "wiring_consistency_check", "transcript_stream"};
+    static const char *circuit_names[] = {"input", "wiring_consistency_check", "transcript_stream"};
     for (const char *n : circuit_names)
         if (fd.name == n) { printf("hobbit_b200: stream '%s' is not built (use read_trace for the gate transcript)\n", n); exit(-1); }
     for (int i = 0; i < size; i++) v[i] = F((i % 1024) + 1);
 }
 
 const F *stream_chunk(stream_descriptor &fd, size_t i, size_t B, std::vector<F> &buff) {
-    if (fd.name == "witness" || fd.name == "lookup_witness_basic") return resident_stream(fd) + i * B;
+    if (fd.name == "witness" || fd.name == "lookup_witness_basic" || fd.name == "circuit") return resident_stream(fd) + i * B;
     buff.resize(B);
     read_stream(fd, buff, (int)B);
     return buff.data();

@@ -262,6 +262,9 @@ int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t
 int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out);
 int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S);
 int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy);
+/* "circuit" (16cs, has_lookups = false; witness_stream.cpp:2123-2162): selector 1 add / 0 mul per op record (cs) | (idx, access) pairs of
+ * (l, r, o) per op record (6cs) | (idx_o, access_o) pairs per delete record (2cs) | zeros (7cs) — what prove_arbitrary_circuit opens */
+int hb_trace_circuit(hb_ctx *ctx, size_t cs, hb_F *out);
 /* lookup streams (witness_stream.cpp:920-1053, 2198-2247); access = number of EARLIER lookups of the same table entry in the pass
  * (table = type-3, entry = value_l for the range table (type 3), value_l + 256 value_r otherwise):
  *   lookup_basic    2cs [X | Y]: per op record X = 1 + value_l + lr0 value_r + lr1 value_o + lr2 access + lr3 type on lookup records, 1 elsewhere;

@@ -398,6 +398,20 @@ int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *
     }
     return 0;
 }
+int hb_trace_circuit(hb_ctx *ctx, size_t cs, hb_F *out) {
+    const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); F *v = mF(out);
+    memset(v, 0, 16 * cs * sizeof(F));
+    size_t c = 0;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type > 0) v[c++] = mk(t[i].type == 1 ? 1 : 0);              /* read_circuit_trace */
+    c = cs;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type > 0) {                                                      /* read_circuit_memory_transcript */
+        v[c++] = f_int(t[i].idx_l); v[c++] = f_int(t[i].access_l); v[c++] = f_int(t[i].idx_r); v[c++] = f_int(t[i].access_r);
+        v[c++] = f_int(t[i].idx_o); v[c++] = f_int(t[i].access_o);
+    }
+    c = 7 * cs;
+    for (size_t i = 0; i < ctx->tr_n; i++) if (t[i].type == 0) { v[c++] = f_int(t[i].idx_o); v[c++] = f_int(t[i].access_o); }  /* read_circuit_memory_final */
+    return 0;
+}
 /* access_table semantics (witness_stream.cpp:920-1053): the count of EARLIER lookups of the same table entry in this pass */
 static std::vector<uint64_t> lookup_access_counts(const emu_tuple *t, size_t n) {
     std::vector<uint64_t> acc(n, 0);

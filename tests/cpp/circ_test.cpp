@@ -6,6 +6,8 @@
 // usage: circ_test <log2 BUFFER_SPACE> <layer sizes...>      e.g. circ_test 12 64 32 16   (MLP, `pigeon 9 b b 1 n l0 l1 ...`)
 //        circ_test <log2 BUFFER_SPACE> aes <n> <d>           e.g. circ_test 19 aes 8 1    (`pigeon 5 19 8 1`, lookups; main.cpp:887-917)
 //        circ_test <log2 BUFFER_SPACE> sql <n> <d>           e.g. circ_test 19 sql 17 1   (`pigeon 6 19 17 1`)
+//        circ_test <log2 BUFFER_SPACE> pruned <n> <d> <rate> e.g. circ_test 20 pruned 20 1 10 (`pigeon 8 20 20 1 10`: pruned MLP through
+//                                                            prove_arbitrary_circuit, main.cpp:812-858: also opens the "circuit" stream)
 #include "../../hobbit_b200/host/hobbit_host.hpp"
 namespace hobbit { typedef F Fe; }
 #include "config_pc.hpp"
@@ -32,6 +34,7 @@ extern int BUFFER_SPACE_tr;
 extern size_t BUFFER_SPACE;
 extern bool has_lookups;
 extern vector<F> lookup_rand;
+extern double prune_rate;
 void Seval_Oracle();
 void prove_gate_consistency_lookups(stream_descriptor tr, vector<F> r, double &vt, double &ps);
 void init_stream(int b, int n, int d);
@@ -57,6 +60,9 @@ int main(int argc, char **argv) {
     if (argc > 2 && (!strcmp(argv[2], "aes") || !strcmp(argv[2], "sql"))) {
         fun = !strcmp(argv[2], "aes") ? 5 : 6; lookups = true;
         n_arg = argc > 3 ? atoi(argv[3]) : 8; d_arg = argc > 4 ? atoi(argv[4]) : 1;
+    } else if (argc > 2 && !strcmp(argv[2], "pruned")) {
+        fun = 8; n_arg = argc > 3 ? atoi(argv[3]) : 20; d_arg = argc > 4 ? atoi(argv[4]) : 1;
+        prune_rate = (argc > 5 ? atoi(argv[5]) : 1) / 100.0;
     } else {
         fun = 9;
         for (int i = 2; i < argc; i++) layer_size.push_back(atoi(argv[i]));
@@ -104,6 +110,23 @@ int main(int argc, char **argv) {
             ok = ok && !memcmp(l.data(), hl.data(), B * 16) && !memcmp(r.data(), hr.data(), B * 16) && !memcmp(o.data(), ho.data(), B * 16) && s == hs;
         }
         CHECK(ok, "gate transcript via read_trace (L, R, O, selector)");
+        if (fun == 8) {
+            // The reference cannot be the checker for "circuit": its reader read_memory_circuit (witness_stream.cpp:1944-2019) is declared int
+            // and has no return statement — undefined behaviour that aborts at -O3 (the same path makes test_arb.sh crash).
+            // The mirror's stream is checked structurally instead: selectors == the transcript selectors, zero tail, pair section non-empty.
+            hobbit::stream_descriptor hfc; hfc.name = "circuit"; hfc.size = 16 * cs;
+            vector<hobbit::Fe> all; all.reserve(16 * cs);
+            for (size_t off = 0; off < 16 * cs; off += B) { hobbit::read_stream(hfc, hv, (int)B); all.insert(all.end(), hv.begin(), hv.end()); }
+            hobbit::stream_descriptor hft2; hft2.name = "transcript_stream"; hft2.size = cs;
+            ok = true; size_t nz_pairs = 0;
+            for (size_t off = 0; off < cs; off += B) {
+                hobbit::read_trace(hft2, hl, hr, ho, hs);
+                for (size_t i = 0; ok && i < B; i++) ok = all[off + i].real == (unsigned long long)hs[i] && all[off + i].img == 0;
+            }
+            for (size_t i = cs; i < 9 * cs; i++) nz_pairs += all[i].real != 0;
+            for (size_t i = 9 * cs; ok && i < 16 * cs; i++) ok = all[i].real == 0 && all[i].img == 0;
+            CHECK(ok && nz_pairs > 0, "stream \"circuit\" (16 cs): selector section == transcript selectors, memory-transcript pairs, zero tail");
+        }
         if (lookups) {
             stream_descriptor fl; fl.name = "lookup_basic"; fl.size = 2 * cs; reset_stream(fl);
             hobbit::stream_descriptor hfl; hfl.name = "lookup_basic"; hfl.size = 2 * cs;
@@ -143,7 +166,7 @@ int main(int argc, char **argv) {
         printf("      trace on the GPU in %.4f s (producer thread + upload: %.4f s)\n", t_eval, t_trace);
     }
     // ---- commit(witness) ---------------------------------------------------------------------------------------------------------------
-    vector<vector<_hash>> MT; vector<vector<hobbit::_hash>> hMT;
+    vector<vector<_hash>> MT, MT0; vector<vector<hobbit::_hash>> hMT, hMT0;
     {
         stream_descriptor fd; fd.name = "witness"; fd.size = 4 * cs; reset_stream(fd);
         init_commitment(false);
@@ -154,6 +177,7 @@ int main(int argc, char **argv) {
         vector<vector<_hash>> A = MT; vector<vector<hobbit::_hash>> Bm = hMT;
         A[0].back() = _hash(); memset(&Bm[0].back(), 0, 32);              // the reference's last leaf reads past its buffers
         CHECK(same_levels(A, Bm), "commit(witness): every Merkle level");
+        if (fun == 8) { MT0 = MT; hMT0 = hMT; }
     }
     vector<vector<_hash>> MTl; vector<vector<hobbit::_hash>> hMTl;
     if (lookups) {          // main.cpp:913: read_stream_PC does not know this name and commits its synthetic default stream; so does the mirror
@@ -217,6 +241,15 @@ int main(int argc, char **argv) {
         CHECK(ps == hps && r1 == r2, "open(witness): ps, RNG state");
         printf("      ps %f / %f KB\n", ps, hps);
     }
+    if (fun == 8) {         // prove_arbitrary_circuit (main.cpp:853): the circuit description is opened against a COPY of the witness tree.
+        // Mirror only (see above: the reference aborts while reading "circuit"); the opening's own identities (Error in fft, recursion checks) run.
+        vector<vector<hobbit::_hash>> hCH = hMT0;
+        hobbit::stream_descriptor hfd; hfd.name = "circuit"; hfd.size = 16 * cs;
+        double hps = 0;
+        srand(23); vector<hobbit::Fe> hx = hobbit::generate_randomness((int)log2(hfd.size)); t0 = now(); hobbit::open(hfd, hx, hCH, vt, hps); tr_gpu[3] += now() - t0;
+        CHECK(hps > 0 && hCH.empty(), "open(circuit) on the mirror: completes, tree freed");
+        printf("      ps %f KB\n", hps);
+    }
     if (lookups) {          // main.cpp:919: the second open of the process (the global query vector I keeps the first call's positions)
         stream_descriptor fd; fd.name = "lookup_witness_basic"; fd.size = 2 * cs; reset_stream(fd);
         hobbit::stream_descriptor hfd; hfd.name = "lookup_witness_basic"; hfd.size = 2 * cs;
@@ -228,7 +261,7 @@ int main(int argc, char **argv) {
     }
     printf("{\"workload\": \"%s circuit 2^%d gates, BUFFER_SPACE 2^%d\", \"trace_upload_s\": %.4f, \"ref_s\": {\"commit\": %.4f, \"mul_tree\": %.4f, \"gate\": %.4f, \"open\": %.4f}, "
            "\"gpu_s\": {\"commit\": %.4f, \"mul_tree\": %.4f, \"gate\": %.4f, \"open\": %.4f}, \"identical\": %s}\n",
-           fun == 9 ? "MLP" : fun == 5 ? "AES" : "SQL", (int)log2(cs), (int)log2(B), t_trace, tr_ref[0], tr_ref[1], tr_ref[2], tr_ref[3], tr_gpu[0], tr_gpu[1], tr_gpu[2], tr_gpu[3], failures ? "false" : "true");
+           fun == 9 ? "MLP" : fun == 8 ? "pruned MLP" : fun == 5 ? "AES" : "SQL", (int)log2(cs), (int)log2(B), t_trace, tr_ref[0], tr_ref[1], tr_ref[2], tr_ref[3], tr_gpu[0], tr_gpu[1], tr_gpu[2], tr_gpu[3], failures ? "false" : "true");
     printf(failures ? "CIRC: %d FAILURES\n" : "CIRC: all identical\n", failures);
     fflush(stdout);
     _exit(failures ? 1 : 0);                                          // the producer thread is still blocked on its mutex

@@ -28,7 +28,7 @@ def test_mlp_circuit_host_logic_vs_reference(args):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(GPU), reason="oracle/_ref/circ_test not prebuilt (needs /root/reference at build time)")
-@pytest.mark.parametrize("args", [(12, 64, 32, 16), (11, 128, 16, 8), (14, 256, 64, 64, 16), (19, "aes", 4, 1), (11, "sql", 9, 1)])
+@pytest.mark.parametrize("args", [(12, 64, 32, 16), (11, 128, 16, 8), (14, 256, 64, 64, 16), (19, "aes", 4, 1), (11, "sql", 9, 1), (14, "pruned", 20, 1, 1)])
 def test_mlp_circuit_gpu_vs_reference(args):
     _run(GPU, *args)
 
