@@ -99,7 +99,7 @@ extern bool materialize_tensor;
 void commit_standard(std::vector<F> &poly, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes,
                      std::vector<std::vector<std::vector<F>>> &_tensor, int K);
 // The data-parallel front half of open_standard (Our_PC.cpp:604-660): beta = eq(x1), aggregate, the rand()-drawn
-// queries I, the reply gather and the Merkle paths.  The recursion behind it (shockwave/WHIR) is the "next" row.
+// queries I, the reply gather and the Merkle paths; open_standard (below) continues with the shockwave / WHIR / linear-code recursion.
 struct open_front { std::vector<F> beta, aggr_vector; std::vector<std::vector<size_t>> I; std::vector<std::vector<F>> reply;
                     std::vector<std::vector<_hash>> commitment_paths; F r_v0; double ps = 0; };
 open_front open_standard_front(std::vector<F> &poly, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, int K);
@@ -181,7 +181,8 @@ proof batch_3product_sumcheck(std::vector<std::vector<F>> &arr1, std::vector<std
                               std::vector<F> a, double &vt, double &ps);
 mul_tree_proof prove_multiplication_tree_new(std::vector<std::vector<F>> &input, F previous_r, std::vector<F> prev_x, double &vt, double &ps);
 // witness_stream.h: name-dispatched producer.  Only the synthetic default stream (v[i] = F(i%1024+1)) exists without the
-// circuit evaluator; circuit streams ("wiring_consistency_check_opt", ...) are the next row.
+// circuit trace; the circuit streams ("witness", "wiring_consistency_check_opt", "circuit", the lookup streams) are served from the
+// HBM-resident trace (hobbit_circuit.cpp).
 void read_stream(stream_descriptor &fd, std::vector<F> &v, int size);
 void reset_stream(stream_descriptor &fd);
 // sumcheck.cpp:1746-1915.  The stream is materialised ONCE into HBM (instead of being re-generated per pass) and every layer is
