@@ -58,3 +58,58 @@ def test_commit_standard_2e26_properties():
         off += n
         n //= 2
     ctx.close()
+
+
+def test_elastic_commit_2e26_properties():
+    """BASELINE config 5 shape (test_Elastic_PC option 2: Orion columns, BUFFER_SPACE 2^20, tensor_row_size 64) at 2^26 coefficients:
+    streaming commit == sharding split (groups of 4 chunks), sampled leaves recomputed from inner digests with the oracle's BLAKE3, one
+    chunk-column of one group recomputed from scratch by the oracle, tree rule on sampled nodes."""
+    import torch
+    import hobbit_b200
+    from hobbit_b200.dist import GpuBackend, elastic_commit_sharded
+    N, B, trs = 1 << 26, 1 << 20, 64
+    K, cols = N // B, 2 * B // trs
+    orc = Checker("orc")
+    ctx = hobbit_b200.Context(0)
+    srand(1)
+    cw = orc.expander_init_store(trs)
+    assert ctx.expander_set(trs, orc.expander_graphs(trs)) == cw
+    rng = np.random.default_rng(5)
+    stream = rng.integers(0, 1 << 61, size=(N, 2), dtype=np.uint64) % np.uint64((1 << 61) - 1)
+    lv = ctx.elastic_commit([stream[i * B:(i + 1) * B] for i in range(K)], B, trs, 1)
+    dstream = torch.from_numpy(stream.view(np.int64)).cuda()
+    got = elastic_commit_sharded(GpuBackend(ctx, torch.device("cuda", 0)), dstream.data_ptr(), K // 4, B, trs, 1)
+    assert np.array_equal(got.cpu().numpy(), lv)
+    # inner digests of group 7, chained into the sampled leaves by the oracle
+    ng = K // 4
+    inner = torch.empty((ng, 4 * B, 32), dtype=torch.uint8, device="cuda")
+    ctx.elastic_encode_groups(dstream.data_ptr(), ng, B, trs, 1, inner.data_ptr())
+    pos = rng.integers(0, 4 * B - 1, size=8)
+    samp = inner[:, torch.from_numpy(pos).cuda()].cpu().numpy()
+    for q, p in enumerate(pos):
+        leaf = np.zeros(32, dtype=np.uint8)
+        for g in range(ng):
+            leaf = orc.blake3(np.concatenate([samp[g, q], leaf]))
+        assert np.array_equal(leaf, lv[p]), p
+    # group 7, column k: the four chunks' tensors at column k from the oracle -> inner digests of the positions (row, k), (row, k-1)
+    g, k = 7, int(rng.integers(1, cols - 1))
+    colcode = []
+    for c in range(4):
+        chunk = stream[(4 * g + c) * B:(4 * g + c + 1) * B].reshape(trs, cols // 2, 2)
+        rows = np.zeros((trs, cols, 2), dtype=np.uint64)
+        rows[:, :cols // 2] = chunk
+        ff = [orc.fft(rows[r], int(np.log2(cols))) for r in range(trs)]
+        colcode.append([orc.encode(np.stack([f[kk] for f in ff]), trs)[0] for kk in (k, k + 1)])       # columns k and k+1 (2*trs entries each)
+    gi = inner[g].cpu().numpy()
+    for row in rng.integers(0, 2 * trs, size=6):
+        p = int(row) * cols + k                                                # tuple hashed at p: (c0[p+1], c1[p+1], c2[p], c3[p])
+        cells = np.stack([colcode[0][1][row], colcode[1][1][row], colcode[2][0][row], colcode[3][0][row]])
+        assert np.array_equal(orc.blake3(cells.view(np.uint8).reshape(64)), gi[p]), (row, k)
+    off, n = 0, 4 * B
+    while n > 1:
+        for i in rng.integers(0, n // 2, size=3):
+            left = lv[off + 2 * i]
+            assert np.array_equal(orc.blake3(np.concatenate([left, left])), lv[off + n + i])
+        off += n
+        n //= 2
+    ctx.close()
