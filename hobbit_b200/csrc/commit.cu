@@ -332,16 +332,43 @@ extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nch
     }
     ctx->tensor_N = Nt; ctx->tensor_K = (int)total_chunks; ctx->tensor_trs = trs;
     const size_t N = nchunks * B;
-    Staged p(ctx), in(ctx);
-    HB_TRY(p.in(poly, N * sizeof(F)));
+    Staged in(ctx);
     HB_TRY(in.outbuf(inner_out, N * 32));
-    // groups bound the size of one launch (grid.y)
-    const size_t G = std::max<size_t>(1, std::min<size_t>(nchunks, ((size_t)1 << 30) / (B * 32)));
-    for (size_t c0 = 0; c0 < nchunks; c0 += G) {
-        size_t nc = std::min(G, nchunks - c0);
-        InnerLayout lay; lay.part_leaves = B / leaf_parts; lay.chunks_total = nchunks; lay.chunk0 = c0;
-        HB_TRY(tensorcode_dev(ctx, p.as<F>() + c0 * B, B, trs, linear_time, ctx->tensor + (first_chunk + c0) * 4 * B, nc, in.as<uint8_t>(), lay));
+    const bool on_dev = is_device_ptr(poly);
+    // groups bound the size of one launch (grid.y).  Host input: groups of 2 chunks, every group's H2D queued on the copy stream up
+    // front so that the copy of group g+1 runs under the encode of group g (as in hb_commit).
+    const size_t G = on_dev ? std::max<size_t>(1, std::min<size_t>(nchunks, ((size_t)1 << 30) / (B * 32))) : std::min<size_t>(nchunks, 2);
+    const size_t ngroups = (nchunks + G - 1) / G;
+    F *stage = nullptr;
+    std::vector<cudaEvent_t> ev(on_dev ? 0 : ngroups);
+    if (!on_dev) {
+        HB_CHECK(ctx, cudaMallocAsync(&stage, N * sizeof(F), ctx->stream));
+        cudaEvent_t start;
+        HB_CHECK(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+        HB_CHECK(ctx, cudaEventRecord(start, ctx->stream));                 // the staging buffer exists from here on
+        HB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, start, 0));
+        cudaEventDestroy(start);
+        for (size_t g = 0; g < ngroups; g++) {
+            size_t c0 = g * G, nc = std::min(G, nchunks - c0);
+            HB_CHECK(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+            HB_CHECK(ctx, cudaMemcpyAsync(stage + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
+            HB_CHECK(ctx, cudaEventRecord(ev[g], ctx->copy_stream));
+        }
     }
+    const F *src = on_dev ? (const F *)poly : stage;
+    int rc = 0;
+    for (size_t g = 0; g < ngroups && !rc; g++) {
+        size_t c0 = g * G, nc = std::min(G, nchunks - c0);
+        if (!on_dev) HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ev[g], 0));
+        InnerLayout lay; lay.part_leaves = B / leaf_parts; lay.chunks_total = nchunks; lay.chunk0 = c0;
+        rc = tensorcode_dev(ctx, src + c0 * B, B, trs, linear_time, ctx->tensor + (first_chunk + c0) * 4 * B, nc, in.as<uint8_t>(), lay);
+    }
+    if (!on_dev) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaFreeAsync(stage, ctx->stream);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    if (rc) return rc;
     HB_TRY(in.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

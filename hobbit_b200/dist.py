@@ -82,7 +82,9 @@ def commit_standard_sharded(backend, poly_local, K, B, trs, lin, group=None, gro
     The local chunks are encoded in `groups` pieces; the all_to_all of piece i runs (async, NCCL stream) while piece i+1 is being
     encoded, so the exchange hides behind the encode except for the last piece."""
     import time
+    import os
     G = dist.get_world_size(group) if dist.is_initialized() else 1
+    groups = int(os.environ.get("HB_SHARD_PIECES", groups))      # experiment switch: pieces of the local encode that the exchange is pipelined behind
     assert K % G == 0 and B % G == 0, "chunks and leaves must split evenly across ranks"
     kl, Bp = K // G, B // G
     if elastic_B is None:
