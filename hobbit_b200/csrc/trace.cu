@@ -9,19 +9,13 @@
 // a stream position is the rank of an op tuple (type 1..254) or of a delete tuple (type 0), so two exclusive scans over the type byte
 // give every element its destination and the streams are written by one scatter kernel each — HBM-bound, 80 B read per tuple.
 #include "common.cuh"
+#include "aes_circuit.cuh"        // TrTuple + the AES gate program in closed form
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace hb {
 
-struct TrTuple {                       // == reference tr_tuple: 3 F, 3 idx, 3 access counters, type; 80 bytes
-    F value_o, value_l, value_r;
-    int idx_o, idx_l, idx_r;
-    int access_o, access_l, access_r;
-    uint8_t type; uint8_t pad_[7];
-};
-static_assert(sizeof(TrTuple) == 80, "tr_tuple layout");
 
 __device__ __forceinline__ F f_int(int x) { return mkF(x >= 0 ? (u64)x : P61 - (u64)(-(long long)x), 0); }
 
@@ -242,6 +236,15 @@ __global__ void __launch_bounds__(256) mlp_inputs_kernel(F *__restrict__ val, in
     if (k < n) { val[k] = mkF((u64)((k + 1) % 256), 0); idx[k] = (int)(label0 + k); }
 }
 
+__global__ void __launch_bounds__(256) aes_block_kernel(TrTuple *__restrict__ tr, int n) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < (size_t)n * kAesRecs) tr[gid] = aes_record(n, (int)(gid / kAesRecs), (int)(gid % kAesRecs));
+}
+__global__ void __launch_bounds__(256) aes_tail_kernel(TrTuple *__restrict__ tr, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= 16 * n + 160) tr[i] = aes_tail_record(n, i);
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -293,6 +296,22 @@ extern "C" int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsi
     if (rec != recs) HB_FAIL(ctx, "hb_trace_generate_mlp: record count mismatch");
     t.n = rec; t.done = true;
     if (n_records) *n_records = rec;
+    return 0;
+}
+
+// AES on the GPU (fun == 5: `pigeon 5 b n d`, input_size = 2^n blocks): the resident trace of one pass of the CPU evaluator
+extern "C" int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records) {
+    if (input_size < 1) HB_FAIL(ctx, "hb_trace_generate_aes: need at least one block");
+    const size_t n = (size_t)input_size, recs = n * kAesRecs + 16 * n + 161;
+    if (n * (16 + kAesLabels) + 162 >= ((size_t)1 << 31) || n * kAesLookups >= ((size_t)1 << 31)) HB_FAIL(ctx, "hb_trace_generate_aes: labels do not fit the reference's int");
+    HB_TRY(hb_trace_begin(ctx, recs));
+    TraceState &t = ctx->trace;
+    TrTuple *tr = (TrTuple *)t.tuples;
+    HB_LAUNCH(ctx, aes_block_kernel, (unsigned)((n * kAesRecs + 255) / 256), 256, 0, tr, input_size);
+    HB_LAUNCH(ctx, aes_tail_kernel, (unsigned)((16 * n + 161 + 255) / 256), 256, 0, tr + n * kAesRecs, input_size);
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    t.n = recs; t.done = true;
+    if (n_records) *n_records = recs;
     return 0;
 }
 

@@ -51,6 +51,12 @@ void trace_generate_mlp(const std::vector<int> &layer_size) {
     CK(hb_trace_generate_mlp(backend(), layer_size.data(), (int)layer_size.size(), &n));
     have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
 }
+// 8f.4: the AES circuit (fun == 5, input_size = 2^n blocks) likewise; follow with trace_end()
+void trace_generate_aes(int input_size) {
+    size_t n = 0;
+    CK(hb_trace_generate_aes(backend(), input_size, &n));
+    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
+}
 // get_circuit_size (main.cpp:303-321): the number of delete records, rounded up to a power of two
 size_t trace_end() {
     size_t n = 0, ops = 0, dels = 0;

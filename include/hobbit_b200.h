@@ -259,6 +259,10 @@ int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_del
  * driver, :1462-1489: weights F((j+i+k)%256), inputs F((k+1)%256)): fills the resident trace with exactly the records, labels and access
  * counters one pass of the CPU evaluator emits.  layer_size: the network shape (`pigeon 9 ... n l0 l1 ...`). */
 int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t *n_records);
+/* 8f.4: the AES circuit (Seval.cpp:957-1084 lookup_box / encrypt / AES under the fun == 5 driver, :1353-1396: input_size blocks of 16 bytes
+ * F((i*122+j)%256), 10 round keys F((i+j+1)%256), toy tables (x+21)%256 / (x+3)%256 / (x+4)%256 / xor) evaluated on the GPU: 1824 records
+ * per block + the final deletes, exactly the records, labels and access counters of one pass of the CPU evaluator. */
+int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records);
 int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out);
 int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S);
 int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy);

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <array>
 
 typedef orc_F F;
 struct hb_ctx {
@@ -367,6 +368,62 @@ int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t
     }
     for (auto &Wi : W) for (auto &Wj : Wi) for (auto &g : Wj) E.del(g);
     for (auto &g : inp) E.del(g);
+    E.del(zero);
+    ctx->tr_done = true;
+    if (n_records) *n_records = ctx->tr_n;
+    return 0;
+}
+/* Seval.cpp:324-354 xor_gate, :957-989 lookup_box, :991-1084 encrypt / AES, :1353-1396 the fun == 5 driver, restated gate by gate */
+namespace {
+struct AesEval : MlpEval {
+    emu_gt table_gate(emu_gt &l, emu_gt &r, int table, uint64_t value) {       /* a lookup record: type = table + 3 */
+        emu_gt g; init(g, mk(value));
+        emu_tuple t; memset(&t, 0, sizeof t);
+        t.type = (uint8_t)(table + 3); t.idx_o = g.idx; t.value_o = g.value; t.idx_l = l.idx; t.value_l = l.value; t.idx_r = r.idx; t.value_r = r.value;
+        t.access_l = l.access; t.access_r = r.access; t.access_o = 0; l.access++; r.access++;
+        g.access = 1; emit(t);
+        return g;
+    }
+    emu_gt x(emu_gt &a, emu_gt &b) { return table_gate(a, b, 1, a.value.re ^ b.value.re); }
+    emu_gt box(emu_gt &a, emu_gt &zero, int table) {
+        const uint64_t shift = table == 2 ? 21 : (uint64_t)table;                     /* S-box (x+21)%256, mix boxes (x+idx)%256 */
+        return table_gate(a, zero, table, (a.value.re + shift) % 256);
+    }
+};
+}
+int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records) {
+    ctx->trace.clear(); ctx->tr_n = 0;
+    AesEval E; E.ctx = ctx;
+    std::vector<std::vector<emu_gt>> in(input_size, std::vector<emu_gt>(16)), key(10, std::vector<emu_gt>(16));
+    for (int i = 0; i < input_size; i++) for (int j = 0; j < 16; j++) E.init(in[i][j], mk((uint64_t)((i * 122 + j) % 256)));
+    for (int i = 0; i < 10; i++) for (int j = 0; j < 16; j++) E.init(key[i][j], mk((uint64_t)((i + j + 1) % 256)));
+    emu_gt zero; E.init(zero, mk(0));
+    for (int b = 0; b < input_size; b++) {
+        std::vector<emu_gt> out(16);
+        for (int j = 0; j < 16; j++) out[j] = E.x(in[b][j], key[0][j]);
+        for (int round = 1; round < 9; round++) {
+            std::vector<emu_gt> sb(16), mixed(16);
+            std::vector<std::array<emu_gt, 3>> t2(16);
+            for (int j = 0; j < 16; j++) sb[j] = E.box(out[j], zero, 2);
+            for (int j = 0; j < 16; j++) { t2[j][1] = E.box(sb[j], zero, 3); t2[j][2] = E.box(sb[j], zero, 4); t2[j][0] = sb[j]; }   /* a COPY of the S-box output */
+            static const int pick[4][4] = {{1, 2, 0, 0}, {0, 1, 2, 0}, {0, 0, 1, 2}, {2, 0, 0, 1}};        /* [output byte][group byte] */
+            for (int k = 0; k < 4; k++)
+                for (int m = 0; m < 4; m++) {
+                    emu_gt x1 = E.x(t2[4 * k][pick[m][0]], t2[4 * k + 1][pick[m][1]]);
+                    emu_gt x2 = E.x(t2[4 * k + 2][pick[m][2]], t2[4 * k + 3][pick[m][3]]);
+                    mixed[4 * k + m] = E.x(x1, x2);
+                    E.del(x1); E.del(x2);
+                }
+            for (int j = 0; j < 16; j++) for (int v = 0; v < 3; v++) E.del(t2[j][v]);
+            std::vector<emu_gt> next(16);
+            for (int j = 0; j < 16; j++) next[j] = E.x(mixed[j], key[round][j]);
+            for (int j = 0; j < 16; j++) E.del(mixed[j]);
+            for (int j = 0; j < 16; j++) { E.del(out[j]); out[j] = next[j]; }
+        }
+        for (int j = 0; j < 16; j++) E.del(out[j]);
+    }
+    for (auto &row : in) for (auto &g : row) E.del(g);
+    for (auto &row : key) for (auto &g : row) E.del(g);
     E.del(zero);
     ctx->tr_done = true;
     if (n_records) *n_records = ctx->tr_n;

@@ -140,13 +140,13 @@ int main(int argc, char **argv) {
             CHECK(ok, "stream \"lookup_witness_basic\" (2 cs), blocks of BUFFER_SPACE");
         }
     }
-    // ---- 8f.4: the same trace produced by the GPU evaluator instead of the producer thread (MLP only): every stream again ----------------
-    if (fun == 9) {
+    // ---- 8f.4: the same trace produced by the GPU evaluator instead of the producer thread (MLP, AES): every stream again ----------------
+    if (fun == 9 || fun == 5) {
         t0 = now();
-        hobbit::trace_generate_mlp(layer_size);
+        if (fun == 9) hobbit::trace_generate_mlp(layer_size); else hobbit::trace_generate_aes(1 << n_arg);
         size_t gcs = hobbit::trace_end();
         double t_eval = now() - t0;
-        CHECK(gcs == cs, "GPU MLP evaluator: circuit_size");
+        CHECK(gcs == cs, "GPU circuit evaluator: circuit_size");
         stream_descriptor fd; fd.name = "witness"; fd.size = 4 * cs; reset_stream(fd);
         hobbit::stream_descriptor hfd; hfd.name = "witness"; hfd.size = 4 * cs;
         vector<F> v(B); vector<hobbit::Fe> hv(B); bool ok = true;
@@ -162,7 +162,16 @@ int main(int argc, char **argv) {
             read_trace(ft, l, r, o, sv); hobbit::read_trace(hft, hl, hr, ho, hs);
             ok = ok && !memcmp(l.data(), hl.data(), B * 16) && !memcmp(r.data(), hr.data(), B * 16) && !memcmp(o.data(), ho.data(), B * 16) && sv == hs;
         }
-        CHECK(ok, "GPU MLP evaluator (8f.4): witness, wiring and transcript streams identical to the reference's (labels, access counters, values)");
+        if (lookups) {
+            stream_descriptor fl; fl.name = "lookup_basic"; fl.size = 2 * cs; reset_stream(fl);
+            hobbit::stream_descriptor hfl; hfl.name = "lookup_basic"; hfl.size = 2 * cs;
+            for (size_t off = 0; off < 2 * cs; off += 2 * B) { read_stream(fl, w, (int)(2 * B)); hobbit::read_stream(hfl, hw, (int)(2 * B)); ok = ok && !memcmp(w.data(), hw.data(), 2 * B * 16); }
+            stream_descriptor fq; fq.name = "lookup_witness_basic"; fq.size = 2 * cs; reset_stream(fq);
+            hobbit::stream_descriptor hfq; hfq.name = "lookup_witness_basic"; hfq.size = 2 * cs;
+            for (size_t off = 0; off < 2 * cs; off += B) { read_stream(fq, v, (int)B); hobbit::read_stream(hfq, hv, (int)B); ok = ok && !memcmp(v.data(), hv.data(), B * 16); }
+        }
+        CHECK(ok, fun == 9 ? "GPU MLP evaluator (8f.4): witness, wiring and transcript streams identical to the reference's (labels, access counters, values)"
+                           : "GPU AES evaluator (8f.4): witness, wiring, transcript and both lookup streams identical to the reference's");
         printf("      trace on the GPU in %.4f s (producer thread + upload: %.4f s)\n", t_eval, t_trace);
     }
     // ---- commit(witness) ---------------------------------------------------------------------------------------------------------------

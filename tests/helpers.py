@@ -562,3 +562,15 @@ def _raw_trace_generate_mlp(self, layer_size):
 
 
 RawABI.trace_generate_mlp = _raw_trace_generate_mlp
+
+
+def _raw_trace_generate_aes(self, input_size):
+    n = ctypes.c_size_t(0)
+    self.call("hb_trace_generate_aes", ctypes.c_int(input_size), ctypes.byref(n))
+    cnt = (ctypes.c_size_t * 3)()
+    self.call("hb_trace_finish", ctypes.byref(cnt, 0), ctypes.byref(cnt, 8), ctypes.byref(cnt, 16))
+    assert cnt[0] == n.value
+    return tuple(cnt)
+
+
+RawABI.trace_generate_aes = _raw_trace_generate_aes

@@ -47,3 +47,19 @@ def test_mlp_prove_reference_free_ps_kat():
     d = json.loads(line)
     print(line)
     assert d["ps_kb"] == 559.0
+
+
+@pytest.mark.gpu
+def test_aes_prove_reference_free_ps_kat():
+    """Same for the AES circuit with lookups (`pigeon 5 19 8 1`): GPU evaluator -> witness / wiring / lookup streams -> both commitments,
+    both product trees, prove_gate_consistency_lookups, both opens: Ps must be the reference's 1135.046875 KB."""
+    import json
+    binary = os.path.join(ROOT, "hobbit_b200", "mlp_prove")
+    if not os.path.exists(binary):
+        pytest.skip("hobbit_b200/mlp_prove not built")
+    p = subprocess.run([binary, "19", "aes", "8", "--reps", "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    print(line)
+    assert d["ps_kb"] == 1135.046875

@@ -182,3 +182,21 @@ def test_mlp_evaluator(abis, shape):
     a_w, b_w = rand_field(rng, 1), rand_field(rng, 1)
     for x, y in zip(g.trace_streams(cs, a_w, b_w, 0), e.trace_streams(cs, a_w, b_w, 0)):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("blocks", [1, 3, 64, 300])
+def test_aes_evaluator(abis, blocks):
+    """8f.4: the AES circuit evaluated on the GPU (closed-form records, one thread per record) == the gate-by-gate restatement of
+    encrypt / AES (Seval.cpp:957-1084): every derived stream including both lookup streams, hence every label, access counter and value."""
+    g, e = abis
+    cg, ce = g.trace_generate_aes(blocks), e.trace_generate_aes(blocks)
+    assert cg == ce == (1824 * blocks + 16 * blocks + 161, 912 * blocks, 912 * blocks + 16 * blocks + 161)
+    cs = 1
+    while cs < ce[2]:
+        cs *= 2
+    rng = np.random.default_rng(blocks)
+    a_w, b_w, lr = rand_field(rng, 1), rand_field(rng, 1), rand_field(rng, 4)
+    for x, y in zip(g.trace_streams(cs, a_w, b_w, 1), e.trace_streams(cs, a_w, b_w, 1)):
+        assert np.array_equal(x, y)
+    for x, y in zip(g.trace_lookup_streams(cs, lr), e.trace_lookup_streams(cs, lr)):
+        assert np.array_equal(x, y)
