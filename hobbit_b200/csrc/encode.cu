@@ -117,6 +117,7 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     dim3 grid((unsigned)(cols / CB), (unsigned)nchunks);
     // small codes: several CTAs per SM, 256 threads each; the big code (one 220 KB CTA per SM) gets 1024 threads
     unsigned threads = smem > 100 * 1024 ? 1024 : 256;
+    if (const char *e = getenv("HB_ENCODE_THREADS")) threads = (unsigned)atoi(e);          // experiment switch
     if (inner) {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
@@ -142,6 +143,10 @@ int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks,
     // Measured on B200 at n = 1024 (bench.py, ms per launch of 16 chunks): 8 columns per CTA (one 220 KB CTA per SM) 3.58; 4 columns (two
     // CTAs per SM, max carveout) 3.62; 2 columns (four CTAs) 4.43; fetching each edge once per 8-lane group and passing it round with
     // shuffles 5.01.  The kernel is bound by instruction issue (multiply-add chains + BLAKE3), not by occupancy or by the edge loads.
+    if (const char *e = getenv("HB_ENCODE_CB")) {                                            // experiment switch
+        if (atoi(e) == 4 && cols % 4 == 0) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+        if (atoi(e) == 2 && cols % 2 == 0) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
+    }
     if (cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 4 == 0 && per_col * 4 <= kMaxSmem) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 2 == 0 && per_col * 2 <= kMaxSmem) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);

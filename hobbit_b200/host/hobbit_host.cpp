@@ -221,12 +221,17 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     std::vector<F> buff(BUFFER_SPACE);
     CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
     const F *res = fd.name == "witness" ? resident_stream(fd) : nullptr;         // what read_stream_PC forwards (:2365-2370): slices of the HBM-resident stream
-    const bool same_chunks = fd.name == "PC_layer";                              // built from the synthetic default stream: every chunk is the same
-    for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++) {
-        if (res) { CK(hb_elastic_push(backend(), (const hb_F *)(res + i * BUFFER_SPACE))); continue; }
-        if (!(same_chunks && i > 0)) read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
-        CK(hb_elastic_push(backend(), (const hb_F *)buff.data()));
+    // Every other name ("PC_layer", and the names read_stream_PC does not know, e.g. "lookup_witness_basic") is built from the stateless
+    // synthetic default stream: every chunk is the same, so it is produced once, uploaded once and pushed from HBM.
+    void *chunk = nullptr;
+    if (!res) {
+        read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
+        CK(hb_malloc_stream(backend(), &chunk, BUFFER_SPACE * sizeof(F)));
+        CK(hb_memcpy(backend(), chunk, buff.data(), BUFFER_SPACE * sizeof(F)));
     }
+    for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++)
+        CK(hb_elastic_push(backend(), res ? (const hb_F *)(res + i * BUFFER_SPACE) : (const hb_F *)chunk));
+    if (chunk) CK(hb_free_stream(backend(), chunk));
     // every level goes straight from HBM into the caller's MT_hashes[l] (no intermediate flat copy of the 8B digests on the host)
     MT_hashes.clear();
     std::vector<uint8_t *> ptrs;
