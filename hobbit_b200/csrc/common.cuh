@@ -81,6 +81,7 @@ struct hb_ctx {
     // twiddle tables w[k] = omega_len^k, k < len/2, cached per log2(len)
     hb::F *tw[32] = {};
     bool tw_j_neg[32] = {};             // omega_len^(len/4) == -i (else +i)
+    uint8_t tw_w8[32] = {};             // omega_len^(len/8) = 2^30 (+-1 +- i): bit 0 = real part negative, bit 1 = imaginary part negative
     hb::ExpanderDev exp;
     // resident tensor of the last commit_standard
     hb::F *tensor = nullptr; size_t tensor_elems = 0; size_t tensor_N = 0; int tensor_K = 0; int tensor_trs = 0;

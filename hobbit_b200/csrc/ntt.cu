@@ -36,6 +36,14 @@ int get_twiddles(hb_ctx *ctx, int logn, const F **out) {
             if (j.re != 0 || (j.im != 1 && j.im != P61 - 1)) HB_FAIL(ctx, "get_twiddles: omega^(len/4) is not +-i");
             ctx->tw_j_neg[logn] = (j.im != 1);
         }
+        // omega^(len/8) is a primitive 8th root of unity: (1 + i)^2 = 2i and 2^61 = 1 mod p, so the four of them are 2^30 (+-1 +- i) and
+        // multiplying by one is two additions and a 30-bit rotation per limb (no wide multiply)
+        if (logn >= 3) {
+            F w8 = w[len / 8];
+            const u64 r30 = (u64)1 << 30;
+            if ((w8.re != r30 && w8.re != P61 - r30) || (w8.im != r30 && w8.im != P61 - r30)) HB_FAIL(ctx, "get_twiddles: omega^(len/8) is not 2^30 (+-1 +- i)");
+            ctx->tw_w8[logn] = (uint8_t)((w8.re != r30 ? 1 : 0) | (w8.im != r30 ? 2 : 0));
+        }
     }
     *out = ctx->tw[logn];
     return 0;
@@ -46,20 +54,47 @@ __device__ __forceinline__ F mul_j(F x, bool neg) {            // x * (+i) = (-i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// x * omega^(len/8) with omega^(len/8) = 2^30 (sr + si i), sr, si = +-1 (flags: bit 0 = sr negative, bit 1 = si negative):
+//   2^30 ((sr a - si b) + (si a + sr b) i); the factor 2^30 is a rotation by 30 inside the 61-bit limb
+__device__ __forceinline__ u64 rot30(u64 x) { return ((x << 30) & P61) | (x >> 31); }
+__device__ __forceinline__ u64 neg61(u64 x) { return x ? P61 - x : 0; }
+__device__ __forceinline__ F mul_w8(F x, unsigned flags) {
+    const u64 apb = add61(x.re, x.im), amb = sub61(x.re, x.im);
+    u64 re, im;
+    if (flags == 0) { re = amb; im = apb; }
+    else if (flags == 2) { re = apb; im = neg61(amb); }
+    else if (flags == 1) { re = neg61(apb); im = amb; }
+    else { re = neg61(amb); im = neg61(apb); }
+    return mkF(rot30(re), rot30(im));
+}
+// 8-point butterfly (three radix-2 stages) on inputs that already carry their stage twiddles: x[0], X1 .. X7 -> c_0 .. c_7 in place.
+// Inside, only powers of omega^(len/8) appear: J = omega^(len/4) = +-i (a limb swap) and W8 (above): no wide multiplies.
+__device__ __forceinline__ void dft8(F *x, bool j_neg, unsigned w8) {
+    const F a0 = fadd(x[0], x[1]), a1 = fsub(x[0], x[1]), a2 = fadd(x[2], x[3]), a3 = mul_j(fsub(x[2], x[3]), j_neg);
+    const F a4 = fadd(x[4], x[5]), a5 = fsub(x[4], x[5]), a6 = fadd(x[6], x[7]), a7 = mul_j(fsub(x[6], x[7]), j_neg);
+    const F b0 = fadd(a0, a2), b2 = fsub(a0, a2), b1 = fadd(a1, a3), b3 = fsub(a1, a3);
+    const F b4 = fadd(a4, a6), b6 = mul_j(fsub(a4, a6), j_neg), b5 = mul_w8(fadd(a5, a7), w8), b7 = mul_w8(mul_j(fsub(a5, a7), j_neg), w8);
+    x[0] = fadd(b0, b4); x[4] = fsub(b0, b4); x[1] = fadd(b1, b5); x[5] = fsub(b1, b5);
+    x[2] = fadd(b2, b6); x[6] = fsub(b2, b6); x[3] = fadd(b3, b7); x[7] = fsub(b3, b7);
+}
+
 // Tile kernel: stages 1..lb of a length-2^logn transform on positions [tile*2^lb, (tile+1)*2^lb) of one row.
 // Loads src[rev(p)] (zero if rev(p) >= in_len), writes dst[p].  src may alias dst only when lb == logn
 // (then the CTA reads its whole row before it writes anything).
 //  * rows are grouped in chunks: row r -> chunk r / rows_per_chunk; chunk strides are given separately so that all
 //    chunks of a commit go through ONE launch (no per-chunk grid tail).
-//  * zero-extended input (in_len == len/2, the RS encoding of a message row): every odd bit-reversed position is
-//    zero, so stage 1 is a plain duplication and is done while loading.
-//  * stages are taken two at a time (radix-4): with X1 = x1*w1, X2 = x2*w2, X3 = x3*(w1*w2) and J = omega^(len/4) = +-i
-//        out0 = (x0+X1) + (X2+X3),  out2 = (x0+X1) - (X2+X3),  out1 = (x0-X1) + J(X2-X3),  out3 = (x0-X1) - J(X2-X3)
-//    i.e. 3 multiplications per 4 outputs per 2 stages instead of 4, and half the shared-memory round trips.
-__global__ void __launch_bounds__(512)
+//  * stages are taken three at a time (radix-8): with e the twiddle exponent of the LAST of the three stages, the inputs are multiplied
+//    by w^(4e), w^(2e), w^(6e), w^e, w^(5e), w^(3e), w^(7e) (7 multiplications per 8 points per 3 stages instead of 12) and everything
+//    inside the 8-point butterfly is a power of omega^(len/8), which costs additions and rotations only.  A remainder of two stages is a
+//    radix-4 pass (3 multiplications per 4 points), of one stage a radix-2 pass.
+//  * zero-extended input (in_len == len/2, the RS encoding of a message row): every odd bit-reversed position is zero, so stage 1 is a
+//    plain duplication and stages 1..4 are done in registers while loading: the 16 positions of a group see the same 8 inputs; the
+//    even ones are their plain 8-point butterfly, the odd ones need the 16th roots: J, W8, W8 J and four real multiplications.
+template <int MINB>
+__global__ void __launch_bounds__(512, MINB)
 ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_stride, size_t in_len,
                 F *__restrict__ dst, size_t dst_stride, size_t dst_chunk_stride, unsigned rows_per_chunk,
-                int logn, int lb, const F *__restrict__ tw, bool j_neg) {
+                int logn, int lb, const F *__restrict__ tw, bool j_neg, unsigned w8) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *s = reinterpret_cast<F *>(smem_raw);
     const unsigned tiles_per_row = 1u << (logn - lb);
@@ -72,7 +107,23 @@ ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_s
     const unsigned len = 1u << logn;
 
     int st = 1;
-    if (in_len * 2 == len && lb >= 1) {
+    if (in_len * 2 == len && lb >= 4) {
+        const unsigned ngroups = tlen >> 4, e = len >> 4;
+        for (unsigned u = threadIdx.x; u < 2 * ngroups; u += blockDim.x) {     // k = u / ngroups: uniform per warp for tiles of >= 512 positions
+            const unsigned g = u % ngroups, k = u / ngroups;
+            F x[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = in[__brev(base + 16 * g + 2 * m) >> (32 - logn)];
+            if (k) {
+                x[1] = mul_j(x[1], j_neg); x[2] = mul_w8(x[2], w8); x[3] = mul_w8(mul_j(x[3], j_neg), w8);
+                x[4] = fmul(x[4], ldgF(&tw[e])); x[5] = fmul(x[5], ldgF(&tw[5 * e])); x[6] = fmul(x[6], ldgF(&tw[3 * e])); x[7] = fmul(x[7], ldgF(&tw[7 * e]));
+            }
+            dft8(x, j_neg, w8);
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[16 * g + 2 * m + k] = x[m];
+        }
+        st = 5;
+    } else if (in_len * 2 == len && lb >= 1) {
         for (unsigned i = threadIdx.x; i < (tlen >> 1); i += blockDim.x) {
             unsigned p = base + 2 * i;
             F v = in[__brev(p) >> (32 - logn)];
@@ -86,7 +137,25 @@ ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_s
         }
     }
     __syncthreads();
-    for (; st + 1 <= lb; st += 2) {                       // radix-4 pass: stages st and st+1
+    for (; st + 2 <= lb; st += 3) {                       // radix-8 pass: stages st, st+1, st+2
+        const unsigned h = 1u << (st - 1);
+        const unsigned tws3 = len >> (st + 2);            // twiddle stride of stage st+2
+        for (unsigned q = threadIdx.x; q < (tlen >> 3); q += blockDim.x) {
+            const unsigned k = q & (h - 1);
+            const unsigned p0 = ((q >> (st - 1)) << (st + 2)) + k;
+            const size_t e = (size_t)tws3 * k;
+            F x[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = s[p0 + m * h];
+            x[1] = fmul(x[1], ldgF(&tw[4 * e])); x[2] = fmul(x[2], ldgF(&tw[2 * e])); x[3] = fmul(x[3], ldgF(&tw[6 * e]));
+            x[4] = fmul(x[4], ldgF(&tw[e])); x[5] = fmul(x[5], ldgF(&tw[5 * e])); x[6] = fmul(x[6], ldgF(&tw[3 * e])); x[7] = fmul(x[7], ldgF(&tw[7 * e]));
+            dft8(x, j_neg, w8);
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[p0 + m * h] = x[m];
+        }
+        __syncthreads();
+    }
+    if (st + 1 <= lb) {                                   // radix-4 pass: stages st and st+1
         const unsigned h = 1u << (st - 1);
         const unsigned tws2 = len >> (st + 1);            // twiddle stride of stage st+1; stage st uses 2*tws2
         for (unsigned q = threadIdx.x; q < (tlen >> 2); q += blockDim.x) {
@@ -100,6 +169,7 @@ ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_s
             s[p0 + h] = fadd(a1, c); s[p0 + 3 * h] = fsub(a1, c);
         }
         __syncthreads();
+        st += 2;
     }
     if (st <= lb) {                                       // one radix-2 stage left
         const unsigned half = 1u << (st - 1), tws = len >> st;
@@ -163,16 +233,22 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
     const size_t smem = sizeof(F) << lb;
     static bool attr_set = false;
     if (!attr_set) {
-        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
         attr_set = true;
     }
-    unsigned threads = 1u << (lb > 2 ? lb - 2 : 0);          // one radix-4 butterfly per thread up to 512 threads
+    unsigned threads = 1u << (lb > 3 ? lb - 3 : 0);          // one radix-8 butterfly per thread up to 512 threads
     if (threads > 512) threads = 512;
     if (threads < 32) threads = 32;
     size_t grid = batch << (logn - lb);
     if (rows_per_chunk != batch && lb != logn) HB_FAIL(ctx, "ntt: chunked launch supports transforms up to one tile");
-    HB_LAUNCH(ctx, ntt_tile_kernel, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
-              (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn]);
+    static const int minb = getenv("HB_NTT_MINB") ? atoi(getenv("HB_NTT_MINB")) : 2;     // experiment switch: 3 CTAs/SM at 40 registers (spills) or 2 at 60
+    if (minb == 3)
+        HB_LAUNCH(ctx, ntt_tile_kernel<3>, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
+                  (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
+    else
+        HB_LAUNCH(ctx, ntt_tile_kernel<2>, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
+                  (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
     int s_lo = lb;
     while (s_lo < logn) {
         int cnt = logn - s_lo; if (cnt > 3) cnt = 3;
