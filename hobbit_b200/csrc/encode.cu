@@ -39,67 +39,143 @@ __device__ __forceinline__ u64 acc_reduce(const Acc &a) {
     return add61(u, v);
 }
 
+// Edge and row-pointer loads: read-only path, L1 evict-last.  One SM runs dozens of CTAs per launch and every CTA walks the same graph;
+// measured (bench.py, ms per launch of 16 chunks): evict-last on every edge 3.36, default policy 3.41, evict-first on the two big
+// stages (so that the small stages' lists stay resident) 3.48-3.66 — the big stages lose their same-line hits.
+__device__ __forceinline__ uint2 ld_edge(const uint2 *p) {
+    uint2 v;
+    asm("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_rowptr(const int *p) { int v; asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
 // grid: (cols / CB, nchunks).  inner != nullptr: also emit the inner leaf digests H1(T[4j][k] | .. | T[4j+3][k])
 // of this chunk (commit_standard hashes 4-row quads of every column, Our_PC.cpp:160-166); the Merkle–Damgård chaining
 // over chunks is done afterwards by md_chain_kernel so that all chunks can be encoded in one launch.
+constexpr int kHelpUnits = 2;
 template <int CB, bool INNER>
 __global__ void __launch_bounds__(1024)
 encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int n, int cwlen,
                    const EncStage *__restrict__ stages, int nstages,
                    const int *__restrict__ rowptr, const uint2 *__restrict__ edges,
-                   uint8_t *__restrict__ inner_base, Digest zero_quad, InnerLayout lay) {
+                   uint8_t *__restrict__ inner_base, Digest zero_quad, InnerLayout lay, unsigned long long *__restrict__ prof, int split_ok, int help_ok) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *cw = reinterpret_cast<F *>(smem_raw);                   // cw[row * CB + c]
+    long long tprev = prof ? clock64() : 0;                    // development aid (HB_ENCODE_PROF): cycles per phase, summed over CTAs by thread 0
+    auto mark = [&](int slot) { if (prof && threadIdx.x == 0) { long long t = clock64(); atomicAdd(&prof[slot], (unsigned long long)(t - tprev)); tprev = t; } };
     F *T = Tbase + (size_t)blockIdx.y * chunk_stride;
     const size_t col0 = (size_t)blockIdx.x * CB;
     const unsigned c = threadIdx.x % CB, t0 = threadIdx.x / CB, tstep = blockDim.x / CB;
+    // inner leaf digests: pair index idx = j * CB + c <-> quad j (rows 4j .. 4j+3) of column c
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned msg_pairs = (unsigned)(n / 4) * CB, msg_units = (msg_pairs + 31) / 32;    // quads made of message rows only, in units of one warp
+    __shared__ unsigned hash_next;                                                            // next message unit nobody has taken yet
+    auto hash_pair = [&](unsigned idx) {
+        const unsigned j = idx / CB, cc = idx % CB;
+        if (j >= (unsigned)n / 2) return;
+        uint32_t out[8];
+        if (4 * j >= (unsigned)cwlen) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) out[q] = zero_quad.w[q];           // H1(64 zero bytes), precomputed
+        } else {
+            uint32_t m[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                unsigned r = 4 * j + q;
+                F x = (r < (unsigned)cwlen) ? cw[r * CB + cc] : mkF(0, 0);
+                m[4 * q] = (uint32_t)x.re; m[4 * q + 1] = (uint32_t)(x.re >> 32);
+                m[4 * q + 2] = (uint32_t)x.im; m[4 * q + 3] = (uint32_t)(x.im >> 32);
+            }
+            blake3_compress64(m, out);
+        }
+        uint4 *lp = reinterpret_cast<uint4 *>(inner_base + lay.offset(blockIdx.y, (size_t)j * cols + col0 + cc) * 32);
+        lp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        lp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    };
+    if (INNER && threadIdx.x == 0) hash_next = 0;
 
-    for (unsigned r = t0; r < (unsigned)n; r += tstep) cw[r * CB + c] = T[(size_t)r * cols + col0 + c];
+    // message rows -> shared memory with asynchronous 16-byte copies: every thread has all of its loads in flight at once (a plain
+    // load/store loop serialises one DRAM round trip per row and was 10 % of the kernel)
+    for (unsigned r = t0; r < (unsigned)n; r += tstep) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&cw[r * CB + c]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(&T[(size_t)r * cols + col0 + c]) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    mark(0);
 
     for (int s = 0; s < nstages; s++) {
         const EncStage st = stages[s];
         const int *rp = rowptr + st.rowptr_base;
-        for (unsigned t = t0; t < (unsigned)st.R; t += tstep) {
-            int e0 = __ldg(&rp[t]), e1 = __ldg(&rp[t + 1]);
-            Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
+        // Small stages have fewer rows than the CTA has row slots (blockDim / CB): their rows are split over P = 2 or 4 adjacent slots
+        // (lanes 8 or 8 and 16 apart in the same warp when CB == 8), every slot sums every P-th edge and the partial sums are added
+        // with shuffles — exact in the field, so the result is the same canonical value.
+        const unsigned P = !split_ok ? 1u : (CB == 8 && (unsigned)st.R * 4 <= tstep) ? 4u : (CB == 8 && (unsigned)st.R * 2 <= tstep) ? 2u : 1u;
+        if (P == 1) {
+            for (unsigned t = t0; t < (unsigned)st.R; t += tstep) {
+                int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
+                Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
 #pragma unroll 4
-            for (int e = e0; e < e1; e++) {
-                uint2 ed = __ldg(&edges[e]);
-                F x = cw[ed.x * CB + c];
-                acc_mac(are, x.re, ed.y);
-                acc_mac(aim, x.im, ed.y);
+                for (int e = e0; e < e1; e++) {
+                    uint2 ed = ld_edge(&edges[e]);
+                    F x = cw[ed.x * CB + c];
+                    acc_mac(are, x.re, ed.y);
+                    acc_mac(aim, x.im, ed.y);
+                }
+                cw[(st.out_off + t) * CB + c] = mkF(acc_reduce(are), acc_reduce(aim));
             }
-            cw[(st.out_off + t) * CB + c] = mkF(acc_reduce(are), acc_reduce(aim));
+        } else {
+            const unsigned slots = (unsigned)st.R * P;                       // <= tstep: one pass
+            const unsigned slot = t0, t = slot / P, part = slot % P;
+            if ((t0 & ~3u) < slots) {                                         // warp-uniform: the four slots of a warp are 4a .. 4a+3
+                Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
+                if (slot < slots) {
+                    const int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
+#pragma unroll 2
+                    for (int e = e0 + (int)part; e < e1; e += (int)P) {
+                        uint2 ed = ld_edge(&edges[e]);
+                        F x = cw[ed.x * CB + c];
+                        acc_mac(are, x.re, ed.y);
+                        acc_mac(aim, x.im, ed.y);
+                    }
+                }
+                u64 re = acc_reduce(are), im = acc_reduce(aim);
+                re = add61(re, __shfl_xor_sync(0xffffffffu, re, 8)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 8));
+                if (P == 4) { re = add61(re, __shfl_xor_sync(0xffffffffu, re, 16)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 16)); }
+                if (slot < slots && part == 0) cw[(st.out_off + t) * CB + c] = mkF(re, im);
+            }
+        }
+        // Warps without a row slot in this stage (the small stages of the recursion keep only a few warps busy, and those are bound by
+        // load latency, not by issue slots) hash quads of MESSAGE rows meanwhile — the stages only write parity rows.  At most
+        // kHelpUnits units per warp and stage so that the stage barrier is not held up; what is left is done after the last stage.
+        if (INNER && help_ok) {
+            const unsigned nslots = (unsigned)st.R * P;
+            if (nslots <= tstep && (threadIdx.x & ~31u) / CB >= nslots) {
+                for (int it = 0; it < kHelpUnits; it++) {
+                    unsigned u = 0;
+                    if (lane == 0) u = atomicAdd(&hash_next, 1u);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= msg_units) break;
+                    if (32 * u + lane < msg_pairs) hash_pair(32 * u + lane);
+                }
+            }
         }
         __syncthreads();
+        mark(1 + s);
     }
 
     // rows [n, cwlen) are new; rows [cwlen, 2n) are the zero tail of the reference's 2n-sized buffer
     for (unsigned r = n + t0; r < 2u * n; r += tstep)
         T[(size_t)r * cols + col0 + c] = (r < (unsigned)cwlen) ? cw[r * CB + c] : mkF(0, 0);
+    if (prof) __syncthreads();
+    mark(14);
 
     if (INNER) {
-        for (unsigned j = t0; j < (unsigned)n / 2; j += tstep) {
-            uint32_t out[8];
-            if (4 * j >= (unsigned)cwlen) {
-#pragma unroll
-                for (int q = 0; q < 8; q++) out[q] = zero_quad.w[q];       // H1(64 zero bytes), precomputed
-            } else {
-                uint32_t m[16];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    unsigned r = 4 * j + q;
-                    F x = (r < (unsigned)cwlen) ? cw[r * CB + c] : mkF(0, 0);
-                    m[4 * q] = (uint32_t)x.re; m[4 * q + 1] = (uint32_t)(x.re >> 32);
-                    m[4 * q + 2] = (uint32_t)x.im; m[4 * q + 3] = (uint32_t)(x.im >> 32);
-                }
-                blake3_compress64(m, out);
-            }
-            uint4 *lp = reinterpret_cast<uint4 *>(inner_base + lay.offset(blockIdx.y, (size_t)j * cols + col0 + c) * 32);
-            lp[0] = make_uint4(out[0], out[1], out[2], out[3]);
-            lp[1] = make_uint4(out[4], out[5], out[6], out[7]);
-        }
+        const unsigned done = min((unsigned)hash_next, msg_units);                   // message units already hashed by idle warps
+        for (unsigned u = done + warp; u < msg_units; u += nwarps) if (32 * u + lane < msg_pairs) hash_pair(32 * u + lane);
+        for (unsigned idx = msg_pairs + threadIdx.x; idx < (unsigned)(n / 2) * CB; idx += blockDim.x) hash_pair(idx);
+        if (prof) __syncthreads();
+        mark(15);
     }
 }
 
@@ -117,15 +193,27 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     dim3 grid((unsigned)(cols / CB), (unsigned)nchunks);
     // small codes: several CTAs per SM, 256 threads each; the big code (one 220 KB CTA per SM) gets 1024 threads
     unsigned threads = smem > 100 * 1024 ? 1024 : 256;
+    static unsigned long long *prof = nullptr;
+    static const int help_ok = getenv("HB_ENCODE_HELP") ? atoi(getenv("HB_ENCODE_HELP")) : 1;      // experiment switch
+    static const int split_ok = getenv("HB_ENCODE_SPLIT") ? atoi(getenv("HB_ENCODE_SPLIT")) : 1;   // experiment switch
+    if (!prof && getenv("HB_ENCODE_PROF")) { cudaMalloc(&prof, 16 * 8); cudaMemset(prof, 0, 16 * 8); }
     if (const char *e = getenv("HB_ENCODE_THREADS")) threads = (unsigned)atoi(e);          // experiment switch
     if (inner) {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay);
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok);
     } else {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, false>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay);
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok);
+    }
+    if (prof) {                                                   // development aid: cumulative cycles per phase (thread 0 of every CTA)
+        unsigned long long h[16];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, prof, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "encode phases (load | stages.. | store | hash):");
+        for (int i = 0; i < 16; i++) if (h[i]) fprintf(stderr, " %d:%llu", i, h[i]);
+        fprintf(stderr, "\n");
     }
     return 0;
 }
