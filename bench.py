@@ -296,7 +296,7 @@ def main():
                 "note": "integer-pipe-bound kernel (61-bit modular multiply-adds + BLAKE3 compressions, SURVEY §8d): the HBM fraction is low by "
                         "construction; the ncu pipe utilisation is in profiles/",
                 # from the committed `ncu --set full` capture of this kernel (profiles/r01_summary.md), NOT measured in this run
-                "int_pipes_ncu": {"issue_slots_busy_pct": 54.9, "alu_pipe_pct": 52.0, "fma_heavy_pipe_pct": 53.1, "dram_pct_of_peak": 10.7,
+                "int_pipes_ncu": {"issue_slots_busy_pct": 63.5, "alu_pipe_pct": 58.0, "fma_heavy_pipe_pct": 59.6, "dram_pct_of_peak": 11.4,
                                   "source": "profiles/r01_summary.md (ncu --set full --clock-control none, one launch = 2^25 coefficients)"}}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
