@@ -187,7 +187,7 @@ ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_s
 // Register-resident radix-2^CNT pass over global memory: stages s_lo+1 .. s_lo+CNT of a length-2^logn transform.
 template <int CNT>
 __global__ void __launch_bounds__(256)
-ntt_global_kernel(F *__restrict__ data, size_t stride, int logn, int s_lo, const F *__restrict__ tw, size_t total_groups) {
+ntt_global_kernel(F *__restrict__ data, size_t stride, int logn, int s_lo, const F *__restrict__ tw, size_t total_groups, bool j_neg, unsigned w8) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total_groups) return;
     const unsigned groups_per_row = 1u << (logn - CNT);
@@ -199,6 +199,13 @@ ntt_global_kernel(F *__restrict__ data, size_t stride, int logn, int s_lo, const
     F v[1 << CNT];
 #pragma unroll
     for (int q = 0; q < (1 << CNT); q++) v[q] = a[base + ((unsigned)q << s_lo)];
+    if constexpr (CNT == 3) {
+        // the same radix-8 butterfly as in the tile kernel: stages s_lo+1 .. s_lo+3, h = 2^s_lo, k = low
+        const size_t e = (size_t)((1u << logn) >> (s_lo + 3)) * low;
+        v[1] = fmul(v[1], ldgF(&tw[4 * e])); v[2] = fmul(v[2], ldgF(&tw[2 * e])); v[3] = fmul(v[3], ldgF(&tw[6 * e]));
+        v[4] = fmul(v[4], ldgF(&tw[e])); v[5] = fmul(v[5], ldgF(&tw[5 * e])); v[6] = fmul(v[6], ldgF(&tw[3 * e])); v[7] = fmul(v[7], ldgF(&tw[7 * e]));
+        dft8(v, j_neg, w8);
+    } else {
 #pragma unroll
     for (int t = 0; t < CNT; t++) {
         const int st = s_lo + t + 1;
@@ -213,6 +220,7 @@ ntt_global_kernel(F *__restrict__ data, size_t stride, int logn, int s_lo, const
             v[q] = fadd(u, x);
             v[q | (1 << t)] = fsub(u, x);
         }
+    }
     }
 #pragma unroll
     for (int q = 0; q < (1 << CNT); q++) a[base + ((unsigned)q << s_lo)] = v[q];
@@ -254,9 +262,9 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
         int cnt = logn - s_lo; if (cnt > 3) cnt = 3;
         size_t groups = batch << (logn - cnt);
         unsigned g = (unsigned)((groups + 255) / 256);
-        if (cnt == 3) HB_LAUNCH(ctx, ntt_global_kernel<3>, g, 256, 0, dst, dst_stride, logn, s_lo, tw, groups);
-        else if (cnt == 2) HB_LAUNCH(ctx, ntt_global_kernel<2>, g, 256, 0, dst, dst_stride, logn, s_lo, tw, groups);
-        else HB_LAUNCH(ctx, ntt_global_kernel<1>, g, 256, 0, dst, dst_stride, logn, s_lo, tw, groups);
+        if (cnt == 3) HB_LAUNCH(ctx, ntt_global_kernel<3>, g, 256, 0, dst, dst_stride, logn, s_lo, tw, groups, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
+        else if (cnt == 2) HB_LAUNCH(ctx, ntt_global_kernel<2>, g, 256, 0, dst, dst_stride, logn, s_lo, tw, groups, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
+        else HB_LAUNCH(ctx, ntt_global_kernel<1>, g, 256, 0, dst, dst_stride, logn, s_lo, tw, groups, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
         s_lo += cnt;
     }
     return 0;
