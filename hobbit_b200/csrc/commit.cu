@@ -6,6 +6,7 @@
 // at tensor + i*4B — the same order the reference's `_tensor[i][row][col]` flattens to.  Leaves/levels are one flat
 // array of 32-byte digests, level after level, leaves first (== the reference's MT_hashes[lvl][i]).
 #include "common.cuh"
+#include <thread>
 #include <new>
 #include <algorithm>
 
@@ -90,6 +91,56 @@ int tensorcode_dev(hb_ctx *ctx, const F *msg, size_t n, int trs, int lin, F *T, 
     return 0;
 }
 
+// ---- pageable host memory <-> HBM (declared in common.cuh) -------------------------------------------------------------------
+static constexpr size_t kPinPiece = (size_t)8 << 20;
+static void par_memcpy(void *dst, const void *src, size_t n) {
+    static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    if (n < ((size_t)1 << 20) || hw == 1) { memcpy(dst, src, n); return; }
+    const size_t per = ((n + hw - 1) / hw + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (size_t off = per; off < n; off += per)
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, std::min(per, n - off)); });
+    memcpy(dst, src, std::min(per, n));
+    for (auto &t : th) t.join();
+}
+static int pin_ready(hb_ctx *ctx) {
+    for (int b = 0; b < 2; b++) {
+        if (!ctx->pin[b]) HB_CHECK(ctx, cudaHostAlloc(&ctx->pin[b], kPinPiece, cudaHostAllocDefault));
+        if (!ctx->pin_ev[b]) { HB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->pin_ev[b], cudaEventDisableTiming)); HB_CHECK(ctx, cudaEventRecord(ctx->pin_ev[b], ctx->stream)); }
+    }
+    return 0;
+}
+int copy_from_host(hb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream) {
+    HB_TRY(pin_ready(ctx));
+    size_t i = 0;
+    for (size_t off = 0; off < bytes; off += kPinPiece, i++) {
+        const int b = (int)(i & 1); const size_t sz = std::min(kPinPiece, bytes - off);
+        HB_CHECK(ctx, cudaEventSynchronize(ctx->pin_ev[b]));                    // the last DMA that used this half has finished
+        par_memcpy(ctx->pin[b], (const char *)src_host + off, sz);
+        HB_CHECK(ctx, cudaMemcpyAsync((char *)dst_dev + off, ctx->pin[b], sz, cudaMemcpyHostToDevice, stream));
+        HB_CHECK(ctx, cudaEventRecord(ctx->pin_ev[b], stream));
+    }
+    return 0;
+}
+int copy_to_host(hb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream) {
+    HB_TRY(pin_ready(ctx));
+    const size_t npieces = (bytes + kPinPiece - 1) / kPinPiece;
+    for (size_t i = 0; i <= npieces; i++) {
+        if (i < npieces) {
+            const int b = (int)(i & 1); const size_t off = i * kPinPiece, sz = std::min(kPinPiece, bytes - off);
+            HB_CHECK(ctx, cudaEventSynchronize(ctx->pin_ev[b]));
+            HB_CHECK(ctx, cudaMemcpyAsync(ctx->pin[b], (const char *)src_dev + off, sz, cudaMemcpyDeviceToHost, stream));
+            HB_CHECK(ctx, cudaEventRecord(ctx->pin_ev[b], stream));
+        }
+        if (i >= 1) {                                                            // piece i-1 has landed: hand it to the caller while piece i is in flight
+            const int b = (int)((i - 1) & 1); const size_t off = (i - 1) * kPinPiece, sz = std::min(kPinPiece, bytes - off);
+            HB_CHECK(ctx, cudaEventSynchronize(ctx->pin_ev[b]));
+            par_memcpy((char *)dst_host + off, ctx->pin[b], sz);
+        }
+    }
+    return 0;
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -147,6 +198,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto &e : ctx->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
+    for (int b = 0; b < 2; b++) { if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]); if (ctx->pin_ev[b]) cudaEventDestroy(ctx->pin_ev[b]); }
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
@@ -197,8 +249,11 @@ extern "C" int hb_free_stream(hb_ctx *ctx, void *p) { if (p) HB_CHECK(ctx, cudaF
 extern "C" int hb_malloc_pinned(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMallocHost(p, bytes)); return 0; }
 extern "C" int hb_free_pinned(hb_ctx *ctx, void *p) { HB_CHECK(ctx, cudaFreeHost(p)); return 0; }
 extern "C" int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    HB_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
-    if (!(is_device_ptr(dst) && is_device_ptr(src))) HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // device-to-device stays stream-ordered
+    const bool dd = is_device_ptr(dst), sd = is_device_ptr(src);
+    if (bytes >= kPageableDirect && dd && !sd && !is_pinned_host_ptr(src)) { HB_TRY(copy_from_host(ctx, dst, src, bytes, ctx->stream)); }
+    else if (bytes >= kPageableDirect && sd && !dd && !is_pinned_host_ptr(dst)) { HB_TRY(copy_to_host(ctx, dst, src, bytes, ctx->stream)); }
+    else HB_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    if (!(dd && sd)) HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));                                   // device-to-device stays stream-ordered
     return 0;
 }
 
@@ -290,16 +345,23 @@ extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K
         HB_CHECK(ctx, cudaEventRecord(start, ctx->stream));
         HB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, start, 0));    // do not overwrite ctx->poly under earlier work
         cudaEventDestroy(start);
-        for (int g = 0; g < ngroups; g++) {
-            size_t c0 = (size_t)g * G, nc = std::min<size_t>(G, K - c0);
-            HB_CHECK(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
-            HB_CHECK(ctx, cudaMemcpyAsync(ctx->poly + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
-            HB_CHECK(ctx, cudaEventRecord(ev[g], ctx->copy_stream));
-        }
+        for (int g = 0; g < ngroups; g++) HB_CHECK(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
     }
+    // pinned polynomial: every group's DMA is queued up front; pageable (a std::vector): the host stages group g+1 through the pinned
+    // double buffer while the GPU encodes group g (copy_from_host returns when the host memory has been read)
+    const bool pageable = !on_dev && !is_pinned_host_ptr(poly);
+    auto upload = [&](int g) -> int {
+        size_t c0 = (size_t)g * G, nc = std::min<size_t>(G, K - c0);
+        if (pageable) { HB_TRY(copy_from_host(ctx, ctx->poly + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), ctx->copy_stream)); }
+        else HB_CHECK(ctx, cudaMemcpyAsync(ctx->poly + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
+        HB_CHECK(ctx, cudaEventRecord(ev[g], ctx->copy_stream));
+        return 0;
+    };
+    if (!on_dev && !pageable) for (int g = 0; g < ngroups; g++) HB_TRY(upload(g));
     const F *src = on_dev ? (const F *)poly : ctx->poly;
     for (int g = 0; g < ngroups; g++) {
         size_t c0 = (size_t)g * G, nc = std::min<size_t>(G, K - c0);
+        if (pageable) HB_TRY(upload(g));
         if (!on_dev) HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ev[g], 0));
         HB_TRY(tensorcode_dev(ctx, src + c0 * B, B, trs, linear_time, ctx->tensor + c0 * 4 * B, nc, inner));
         HB_TRY(md_chain_dev(ctx, inner, nc, B, lv.as<uint8_t>()));
@@ -535,7 +597,8 @@ extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs,
     HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
     size_t off = 0, n = 4 * el.B;
     for (int l = 0; l < nlevels; l++, n /= 2) {
-        HB_CHECK(ctx, cudaMemcpyAsync(level_ptrs[l], el.leaves + off * 32, n * 32, cudaMemcpyDefault, ctx->stream));
+        if (n * 32 >= kPageableDirect && !is_device_ptr(level_ptrs[l]) && !is_pinned_host_ptr(level_ptrs[l])) { HB_TRY(copy_to_host(ctx, level_ptrs[l], el.leaves + off * 32, n * 32, ctx->stream)); }
+        else HB_CHECK(ctx, cudaMemcpyAsync(level_ptrs[l], el.leaves + off * 32, n * 32, cudaMemcpyDefault, ctx->stream));
         off += n;
     }
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -66,6 +66,7 @@ struct TraceState {
     void *tuples = nullptr; size_t capacity = 0, n = 0, n_ops = 0, n_del = 0;
     bool done = false, indexed = false;
     unsigned *pos = nullptr;            // is_op | is_del | op_pos | del_pos, n entries each
+    size_t pos_capacity = 0;            // entries allocated at pos (kept across traces: cudaFree / cudaMalloc of it cost more than the evaluator)
 };
 
 }  // namespace hb
@@ -76,6 +77,8 @@ struct hb_ctx {
     cudaStream_t copy_stream = nullptr; // H2D prefetch of the next chunk
     std::string err;
     uint64_t launches = 0;
+    void *pin[2] = {nullptr, nullptr};  // pinned staging for large PAGEABLE host buffers (hb::copy_from_host / copy_to_host)
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     bool sync_needed = false;           // set while a call has host-visible outputs (or pinned host inputs) in flight: see hb::end_call
     int sm_count = hb::kSMs;
     // twiddle tables w[k] = omega_len^k, k < len/2, cached per log2(len)
@@ -153,6 +156,13 @@ inline int end_call(hb_ctx *ctx) {
     return 0;
 }
 
+// Large PAGEABLE host buffers (the reference's std::vector storage) cross PCIe through the context's pinned double buffer: the host-side
+// memcpy of one piece (worker threads) overlaps the DMA of the other.  cudaMemcpy on pageable memory stages through the driver at
+// 3-6 GB/s (measured: 128 MiB of Merkle levels into a std::vector in 44 ms); this path is bound by the host memcpy instead.
+constexpr size_t kPageableDirect = (size_t)1 << 20;      // below this the plain cudaMemcpyAsync is used
+int copy_from_host(hb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);   // returns once src has been read
+int copy_to_host(hb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream);     // returns once dst is filled
+
 // RAII staging of a caller buffer: device pointers pass through, host pointers get a stream-ordered temporary.
 struct Staged {
     hb_ctx *ctx; void *dev = nullptr; void *host = nullptr; size_t bytes = 0; bool owned = false; bool out = false;
@@ -162,8 +172,10 @@ struct Staged {
         if (n == 0) { dev = nullptr; return 0; }
         if (is_device_ptr(p)) { dev = const_cast<void *>(p); return 0; }
         owned = true; host = const_cast<void *>(p);
-        if (is_pinned_host_ptr(p)) ctx->sync_needed = true;
+        const bool pinned = is_pinned_host_ptr(p);
+        if (pinned) ctx->sync_needed = true;
         HB_CHECK(ctx, cudaMallocAsync(&dev, n, ctx->stream));
+        if (!pinned && n >= kPageableDirect) return copy_from_host(ctx, dev, p, n, ctx->stream);
         HB_CHECK(ctx, cudaMemcpyAsync(dev, p, n, cudaMemcpyHostToDevice, ctx->stream));
         return 0;
     }
@@ -178,7 +190,10 @@ struct Staged {
     }
     // copy back (if host output) and synchronise
     int finish() {
-        if (owned && out && bytes) HB_CHECK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (owned && out && bytes) {
+            if (bytes >= kPageableDirect && !is_pinned_host_ptr(host)) return copy_to_host(ctx, host, dev, bytes, ctx->stream);
+            HB_CHECK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         return 0;
     }
     ~Staged() { if (owned && dev) cudaFreeAsync(dev, ctx->stream); }

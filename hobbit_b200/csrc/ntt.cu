@@ -296,8 +296,8 @@ int ntt_rows_padded_dev(hb_ctx *ctx, const F *src, size_t in_len, F *dst, size_t
 // shared memory as s[row][CB]; a quarter-warp reads one 16*CB-byte row segment -> conflict-free LDS.128 and
 // full-sector global accesses.  Rows >= nz_rows are zero on input and are not read.
 template <int CB>
-__global__ void __launch_bounds__(512)
-ntt_cols_kernel(F *__restrict__ mat, size_t cols, int logn, unsigned nz_rows, const F *__restrict__ tw) {
+__global__ void __launch_bounds__(512, 2)
+ntt_cols_kernel(F *__restrict__ mat, size_t cols, int logn, unsigned nz_rows, const F *__restrict__ tw, bool j_neg, unsigned w8) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *s = reinterpret_cast<F *>(smem_raw);
     const unsigned rows = 1u << logn;
@@ -308,7 +308,42 @@ ntt_cols_kernel(F *__restrict__ mat, size_t cols, int logn, unsigned nz_rows, co
         s[p * CB + c] = (q < nz_rows) ? mat[(size_t)q * cols + col0 + c] : mkF(0, 0);
     }
     __syncthreads();
-    for (int st = 1; st <= logn; st++) {
+    int st = 1;
+    for (; st + 2 <= logn; st += 3) {                     // radix-8 pass (see ntt_tile_kernel): stages st, st+1, st+2
+        const unsigned h = 1u << (st - 1), tws3 = rows >> (st + 2);
+        for (unsigned q = t0; q < (rows >> 3); q += tstep) {
+            const unsigned k = q & (h - 1), p0 = ((q >> (st - 1)) << (st + 2)) + k;
+            F x[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = s[(p0 + m * h) * CB + c];
+            if (k) {
+                const size_t e = (size_t)tws3 * k;
+                x[1] = fmul(x[1], ldgF(&tw[4 * e])); x[2] = fmul(x[2], ldgF(&tw[2 * e])); x[3] = fmul(x[3], ldgF(&tw[6 * e]));
+                x[4] = fmul(x[4], ldgF(&tw[e])); x[5] = fmul(x[5], ldgF(&tw[5 * e])); x[6] = fmul(x[6], ldgF(&tw[3 * e])); x[7] = fmul(x[7], ldgF(&tw[7 * e]));
+            }
+            dft8(x, j_neg, w8);
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[(p0 + m * h) * CB + c] = x[m];
+        }
+        __syncthreads();
+    }
+    if (st + 1 <= logn) {                                 // radix-4 pass: stages st, st+1
+        const unsigned h = 1u << (st - 1), tws2 = rows >> (st + 1);
+        for (unsigned q = t0; q < (rows >> 2); q += tstep) {
+            const unsigned k = q & (h - 1), p0 = ((q >> (st - 1)) << (st + 1)) + k;
+            F x0 = s[p0 * CB + c], x1 = s[(p0 + h) * CB + c], x2 = s[(p0 + 2 * h) * CB + c], x3 = s[(p0 + 3 * h) * CB + c];
+            if (k) {
+                const size_t e = (size_t)tws2 * k;
+                x1 = fmul(x1, ldgF(&tw[2 * e])); x2 = fmul(x2, ldgF(&tw[e])); x3 = fmul(x3, ldgF(&tw[3 * e]));
+            }
+            const F a0 = fadd(x0, x1), a1 = fsub(x0, x1), b = fadd(x2, x3), d = mul_j(fsub(x2, x3), j_neg);
+            s[p0 * CB + c] = fadd(a0, b); s[(p0 + 2 * h) * CB + c] = fsub(a0, b);
+            s[(p0 + h) * CB + c] = fadd(a1, d); s[(p0 + 3 * h) * CB + c] = fsub(a1, d);
+        }
+        __syncthreads();
+        st += 2;
+    }
+    if (st <= logn) {                                     // one radix-2 stage left
         const unsigned half = 1u << (st - 1), tws = rows >> st;
         for (unsigned b = t0; b < (rows >> 1); b += tstep) {
             unsigned k = b & (half - 1), j = (b >> (st - 1)) << st;
@@ -327,7 +362,7 @@ template <int CB>
 static int launch_cols(hb_ctx *ctx, F *mat, int logn, size_t cols, size_t nz_rows, const F *tw) {
     size_t smem = (sizeof(F) * CB) << logn;
     HB_CHECK(ctx, cudaFuncSetAttribute(ntt_cols_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HB_LAUNCH(ctx, ntt_cols_kernel<CB>, (unsigned)(cols / CB), 512, smem, mat, cols, logn, (unsigned)nz_rows, tw);
+    HB_LAUNCH(ctx, ntt_cols_kernel<CB>, (unsigned)(cols / CB), 512, smem, mat, cols, logn, (unsigned)nz_rows, tw, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
     return 0;
 }
 

@@ -319,7 +319,6 @@ extern "C" int hb_trace_begin(hb_ctx *ctx, size_t capacity) {
     TraceState &t = ctx->trace;
     if (t.tuples && t.capacity < capacity) { cudaFree(t.tuples); t.tuples = nullptr; }
     if (!t.tuples) { HB_CHECK(ctx, cudaMalloc(&t.tuples, std::max<size_t>(capacity, 1) * 80)); t.capacity = std::max<size_t>(capacity, 1); }
-    if (t.pos) { cudaFree(t.pos); t.pos = nullptr; }
     t.n = 0; t.n_ops = t.n_del = 0; t.done = false; t.indexed = false;
     return 0;
 }
@@ -352,7 +351,12 @@ static int trace_index(hb_ctx *ctx) {
     TraceState &t = ctx->trace;
     if (t.indexed) return 0;
     const size_t n = std::max<size_t>(t.n, 1);
-    HB_CHECK(ctx, cudaMalloc(&t.pos, 4 * n * sizeof(unsigned)));
+    if (t.pos_capacity < 4 * n) {
+        if (t.pos) cudaFree(t.pos);
+        t.pos = nullptr; t.pos_capacity = 0;
+        HB_CHECK(ctx, cudaMalloc(&t.pos, 4 * n * sizeof(unsigned)));
+        t.pos_capacity = 4 * n;
+    }
     unsigned *is_op = t.pos, *is_del = t.pos + n, *op_pos = t.pos + 2 * n, *del_pos = t.pos + 3 * n;
     if (t.n) {
         HB_LAUNCH(ctx, trace_flags_kernel, (unsigned)((t.n + 255) / 256), 256, 0, (const TrTuple *)t.tuples, t.n, is_op, is_del);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 namespace hobbit {
 
@@ -104,12 +105,12 @@ void _fft(F *arr, int logn, bool flag) {
 }
 
 // ---- Merkle ------------------------------------------------------------------------------------------------
-static void flat_to_levels(const std::vector<uint8_t> &flat, size_t nleaves, std::vector<std::vector<_hash>> &hashes) {
+static void flat_to_levels(const uint8_t *flat, size_t nleaves, std::vector<std::vector<_hash>> &hashes) {
     int lv = 0; size_t off = 0;
     for (size_t n = nleaves; n >= 1; n /= 2, lv++) {
         if ((int)hashes.size() <= lv) hashes.resize(lv + 1);
         hashes[lv].resize(n);
-        memcpy(hashes[lv].data(), flat.data() + off * 32, n * 32);
+        memcpy(hashes[lv].data(), flat + off * 32, n * 32);
         off += n;
         if (n == 1) break;
     }
@@ -118,13 +119,13 @@ namespace merkle_tree { namespace merkle_tree_prover {
 void MT_commit_Blake(F *leafs, std::vector<std::vector<_hash>> &hashes, int N) {
     std::vector<uint8_t> flat((2 * (size_t)(N / 4) - 1) * 32);
     CK(hb_mt_commit(backend(), (const hb_F *)leafs, (size_t)N, flat.data()));
-    flat_to_levels(flat, N / 4, hashes);
+    flat_to_levels(flat.data(), N / 4, hashes);
 }
 void create_tree_blake(int ele_num, std::vector<std::vector<_hash>> &hashes, const int, bool) {
     std::vector<uint8_t> flat((2 * (size_t)ele_num - 1) * 32);
     memcpy(flat.data(), hashes[0].data(), (size_t)ele_num * 32);
     CK(hb_merkle_tree(backend(), flat.data(), (size_t)ele_num));
-    flat_to_levels(flat, ele_num, hashes);
+    flat_to_levels(flat.data(), ele_num, hashes);
 }
 std::vector<_hash> open_tree_blake(std::vector<std::vector<_hash>> &MT_hashes, std::vector<size_t> c, int collumns) {   // merkle_tree.cpp:308-324
     int pos = (int)((c[1] / 4) * collumns + c[0]);
@@ -143,13 +144,23 @@ std::vector<_hash> open_tree_blake(std::vector<std::vector<_hash>> &MT_hashes, s
 void commit_standard(std::vector<F> &poly, _hash &, std::vector<std::vector<_hash>> &MT_hashes,
                      std::vector<std::vector<std::vector<F>>> &_tensor, int K) {
     int B = (int)(poly.size() / K);
-    std::vector<uint8_t> flat((2 * (size_t)B - 1) * 32);
+    // the levels stay in HBM until each one is copied straight into the caller's MT_hashes[l] (no flat host copy: at B = 2^21 that is
+    // 128 MiB which would be zero-filled, downloaded and copied once more)
+    void *dlev = nullptr;
+    CK(hb_malloc_stream(backend(), &dlev, (2 * (size_t)B - 1) * 32));
     std::vector<F> tflat;
     if (materialize_tensor) tflat.resize(4 * poly.size());
-    CK(hb_commit_standard(backend(), (const hb_F *)poly.data(), poly.size(), K, tensor_row_size, linear_time ? 1 : 0, flat.data(),
+    CK(hb_commit_standard(backend(), (const hb_F *)poly.data(), poly.size(), K, tensor_row_size, linear_time ? 1 : 0, (uint8_t *)dlev,
                           materialize_tensor ? (hb_F *)tflat.data() : nullptr));
     MT_hashes.clear();
-    flat_to_levels(flat, B, MT_hashes);
+    size_t loff = 0;
+    for (size_t n = (size_t)B;; n /= 2) {
+        MT_hashes.emplace_back(n);
+        CK(hb_memcpy(backend(), MT_hashes.back().data(), (const uint8_t *)dlev + loff * 32, n * 32));
+        loff += n;
+        if (n == 1) break;
+    }
+    CK(hb_free_stream(backend(), dlev));
     _tensor.resize(K);
     if (materialize_tensor) {
         size_t rows = 2 * (size_t)tensor_row_size, cols = 2 * (size_t)B / tensor_row_size;
@@ -216,7 +227,10 @@ void read_stream_PC(stream_descriptor &fd, F *v, int size) {                    
     if (fd.name == "circuit") { printf("hobbit_b200: stream 'circuit' (the circuit description) is not built\n"); exit(-1); }
     CK(hb_stream_pc_test(backend(), (hb_F *)v, (size_t)size));
 }
+static double wall_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + 1e-6 * ts.tv_nsec; }
 void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_hashes) {
+    const bool trace = getenv("HOBBIT_TRACE") != nullptr;                        // HOBBIT_TRACE=1: wall time of the phases on stderr
+    const double t_begin = trace ? wall_ms() : 0;
     if (fd.size / BUFFER_SPACE < 4) printf("Decrease buffer size %d\n", (int)(fd.size / BUFFER_SPACE));
     std::vector<F> buff(BUFFER_SPACE);
     CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
@@ -232,12 +246,14 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++)
         CK(hb_elastic_push(backend(), res ? (const hb_F *)(res + i * BUFFER_SPACE) : (const hb_F *)chunk));
     if (chunk) CK(hb_free_stream(backend(), chunk));
+    const double t_pushed = trace ? wall_ms() : 0;
     // every level goes straight from HBM into the caller's MT_hashes[l] (no intermediate flat copy of the 8B digests on the host)
     MT_hashes.clear();
     std::vector<uint8_t *> ptrs;
     for (size_t n = 4 * BUFFER_SPACE;; n /= 2) { MT_hashes.emplace_back(n); if (n == 1) break; }
     for (auto &lv : MT_hashes) ptrs.push_back((uint8_t *)lv.data());
     CK(hb_elastic_finish_levels(backend(), ptrs.data(), (int)ptrs.size()));
+    if (trace) fprintf(stderr, "[hobbit trace] commit(%s, %zu): stream + pushes %.3f ms, levels %.3f ms\n", fd.name.c_str(), (size_t)fd.size, t_pushed - t_begin, wall_ms() - t_pushed);
 }
 
 // ---- sumcheck.h ------------------------------------------------------------------------------------------------

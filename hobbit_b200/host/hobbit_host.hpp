@@ -41,7 +41,11 @@ struct F {                                     // virgo::fieldElement: {real, im
 };
 static_assert(sizeof(F) == sizeof(hb_F), "layout must match the C ABI");
 
-struct _hash { uint8_t arr[32]; };
+struct _hash {
+    uint8_t arr[32];
+    _hash() {}          // deliberately NOT zeroing: std::vector<_hash>(n) of a 128 MiB level must not be touched (page-faulted, zeroed) by one
+                        // thread before the download fills it; every level the mirror returns is written in full
+};
 
 struct quadratic_poly { F a, b, c; F eval(const F &x) const { return (a * x + b) * x + c; } };
 struct cubic_poly { F a, b, c, d; F eval(const F &x) const { return ((a * x + b) * x + c) * x + d; } };
