@@ -90,8 +90,8 @@ __device__ __forceinline__ void dft8(F *x, bool j_neg, unsigned w8) {
 //  * zero-extended input (in_len == len/2, the RS encoding of a message row): every odd bit-reversed position is zero, so stage 1 is a
 //    plain duplication and stages 1..4 are done in registers while loading: the 16 positions of a group see the same 8 inputs; the
 //    even ones are their plain 8-point butterfly, the odd ones need the 16th roots: J, W8, W8 J and four real multiplications.
-template <int MINB>
-__global__ void __launch_bounds__(512, MINB)
+// 64 registers: two CTAs per SM.  Forcing three (40 registers) spills the butterfly and is slower (13.68 vs 12.91 ms per 2^26 commit).
+__global__ void __launch_bounds__(512, 2)
 ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_stride, size_t in_len,
                 F *__restrict__ dst, size_t dst_stride, size_t dst_chunk_stride, unsigned rows_per_chunk,
                 int logn, int lb, const F *__restrict__ tw, bool j_neg, unsigned w8) {
@@ -241,8 +241,7 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
     const size_t smem = sizeof(F) << lb;
     static bool attr_set = false;
     if (!attr_set) {
-        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
-        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
         attr_set = true;
     }
     unsigned threads = 1u << (lb > 3 ? lb - 3 : 0);          // one radix-8 butterfly per thread up to 512 threads
@@ -250,13 +249,8 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
     if (threads < 32) threads = 32;
     size_t grid = batch << (logn - lb);
     if (rows_per_chunk != batch && lb != logn) HB_FAIL(ctx, "ntt: chunked launch supports transforms up to one tile");
-    static const int minb = getenv("HB_NTT_MINB") ? atoi(getenv("HB_NTT_MINB")) : 2;     // experiment switch: 3 CTAs/SM at 40 registers (spills) or 2 at 60
-    if (minb == 3)
-        HB_LAUNCH(ctx, ntt_tile_kernel<3>, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
-                  (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
-    else
-        HB_LAUNCH(ctx, ntt_tile_kernel<2>, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
-                  (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
+    HB_LAUNCH(ctx, ntt_tile_kernel, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
+              (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
     int s_lo = lb;
     while (s_lo < logn) {
         int cnt = logn - s_lo; if (cnt > 3) cnt = 3;
