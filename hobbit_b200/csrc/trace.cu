@@ -245,6 +245,98 @@ __global__ void __launch_bounds__(256) aes_tail_kernel(TrTuple *__restrict__ tr,
     if (i <= 16 * n + 160) tr[i] = aes_tail_record(n, i);
 }
 
+// ---- 8f.4: the pruned two-layer MLP (Seval.cpp:1170-1236 `inference`, fun == 8 driver :1424-1461) ------------------------------------------
+// Same per-neuron program as the dense MLP over a CSR pattern (the reference's indexes[l][i], host data drawn from libc rand()); what is
+// new is that the access counter of an input is the number of EARLIER reads of it in evaluation order — a stable rank of the position among
+// equal column indices (radix sort + run starts, as for the lookup counters) — and that a neuron without inputs is a copy of the gate `zero`.
+struct PrunedLayer {
+    int m;                               // neurons
+    const int *rowptr, *cols;            // CSR pattern (device)
+    const long long *recoff, *laboff;    // exclusive prefix sums over neurons of the records / labels they emit
+    const unsigned *rank;                // per CSR position: earlier reads of the same input
+    long long w_label0, g_label0;        // label of weight (0, 0) of this layer, of the layer's first gate
+    size_t rec0;                         // first record of this layer
+    int zero_label;
+};
+__global__ void __launch_bounds__(256)
+pruned_layer_kernel(TrTuple *__restrict__ tr, PrunedLayer L, const F *__restrict__ in_val, const int *__restrict__ in_idx, const int *__restrict__ in_acc0,
+                    F *__restrict__ out_val, int *__restrict__ out_idx, int *__restrict__ out_acc) {
+    __shared__ F sc[256];
+    __shared__ F carry;
+    const int i = blockIdx.x, r0 = L.rowptr[i], f = L.rowptr[i + 1] - r0;
+    if (f == 0) {                                                              // hidden_layer[i] = zero: a copy (label of zero, access 0)
+        if (threadIdx.x == 0) { out_val[i] = mkF(0, 0); out_idx[i] = L.zero_label; out_acc[i] = 0; }
+        return;
+    }
+    TrTuple *base = tr + L.rec0 + L.recoff[i];
+    const long long gl = L.g_label0 + L.laboff[i];
+    if (threadIdx.x == 0) carry = mkF(0, 0);
+    __syncthreads();
+    for (int k0 = 0; k0 < f; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        F w = mkF(0, 0), x = mkF(0, 0), p = mkF(0, 0);
+        int col = 0;
+        if (k < f) { w = mkF((u64)((k + i) % 256), 0); col = L.cols[r0 + k]; x = in_val[col]; p = fmul(w, x); }
+        sc[threadIdx.x] = p;
+        __syncthreads();
+        for (int d = 1; d < (int)blockDim.x; d <<= 1) {                    // inclusive scan of the products
+            F v = sc[threadIdx.x];
+            if ((int)threadIdx.x >= d) v = fadd(v, sc[threadIdx.x - d]);
+            __syncthreads();
+            sc[threadIdx.x] = v;
+            __syncthreads();
+        }
+        const F c = carry;
+        const F sum = fadd(c, sc[threadIdx.x]);
+        const F prev = (threadIdx.x == 0) ? c : fadd(c, sc[threadIdx.x - 1]);
+        if (k < f) {
+            TrTuple t;
+            t.type = 2; t.value_l = w; t.value_r = x; t.value_o = p;
+            t.idx_l = (int)(L.w_label0 + r0 + k); t.idx_r = in_idx[col]; t.access_l = 0; t.access_r = in_acc0[col] + (int)L.rank[r0 + k]; t.access_o = 0;
+            for (int q = 0; q < 7; q++) t.pad_[q] = 0;
+            if (k == 0) { t.idx_o = (int)gl; base[0] = t; }
+            else {
+                const int ml = (int)(gl + 1 + 2 * (long long)(k - 1)), hl = (k == 1) ? (int)gl : ml - 1;
+                TrTuple *r = base + 1 + 4 * (size_t)(k - 1);
+                t.idx_o = ml; r[0] = t;
+                TrTuple a = t;
+                a.type = 1; a.value_l = prev; a.value_r = p; a.value_o = sum; a.idx_l = hl; a.idx_r = ml; a.idx_o = ml + 1; a.access_l = 1; a.access_r = 1; a.access_o = 0;
+                r[1] = a;
+                TrTuple d1 = a; d1.type = 0; d1.idx_o = ml; d1.value_o = p; d1.access_o = 2; r[2] = d1;
+                TrTuple d2 = a; d2.type = 0; d2.idx_o = hl; d2.value_o = prev; d2.access_o = 2; r[3] = d2;
+            }
+            if (k == f - 1) { out_val[i] = sum; out_idx[i] = (f == 1) ? (int)gl : (int)(gl + 2 * (long long)f - 2); out_acc[i] = 1; }
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = sum;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) pruned_keys_kernel(const int *__restrict__ cols, size_t n, unsigned long long *__restrict__ keys, unsigned *__restrict__ idx, unsigned *__restrict__ count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (unsigned long long)cols[i]; idx[i] = (unsigned)i;
+    atomicAdd(&count[cols[i]], 1u);
+}
+// delete records of a layer's weights: one CTA per neuron
+__global__ void __launch_bounds__(256) pruned_delete_weights_kernel(TrTuple *__restrict__ tr, const int *__restrict__ rowptr, long long w_label0) {
+    const int i = blockIdx.x, r0 = rowptr[i], f = rowptr[i + 1] - r0;
+    for (int k = threadIdx.x; k < f; k += blockDim.x) {
+        TrTuple t; memset(&t, 0, sizeof t);
+        t.type = 0; t.idx_o = (int)(w_label0 + r0 + k); t.value_o = mkF((u64)((k + i) % 256), 0); t.access_o = 1;
+        tr[r0 + k] = t;
+    }
+}
+// delete records of inputs / hidden values / outputs: access = initial counter + number of reads
+__global__ void __launch_bounds__(256)
+pruned_delete_kernel(TrTuple *__restrict__ tr, size_t n, const F *__restrict__ val, const int *__restrict__ idx, const int *__restrict__ acc0, const unsigned *__restrict__ reads) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrTuple t; memset(&t, 0, sizeof t);
+    t.type = 0; t.idx_o = idx[i]; t.value_o = val[i]; t.access_o = (acc0 ? acc0[i] : 0) + (reads ? (int)reads[i] : 0);
+    tr[i] = t;
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -294,6 +386,102 @@ extern "C" int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsi
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(val, ctx->stream);
     if (rec != recs) HB_FAIL(ctx, "hb_trace_generate_mlp: record count mismatch");
+    t.n = rec; t.done = true;
+    if (n_records) *n_records = rec;
+    return 0;
+}
+
+// stable rank of every position among equal keys + reads per key (device arrays; rank and count are outputs)
+static int rank_positions(hb_ctx *ctx, const int *cols, size_t n, size_t nkeys, unsigned *rank, unsigned *count) {
+    HB_CHECK(ctx, cudaMemsetAsync(count, 0, nkeys * sizeof(unsigned), ctx->stream));
+    if (n == 0) return 0;
+    char *buf; HB_CHECK(ctx, cudaMallocAsync(&buf, n * (2 * 8 + 3 * 4), ctx->stream));
+    unsigned long long *keys = (unsigned long long *)buf, *keys_s = keys + n;
+    unsigned *idx = (unsigned *)(keys_s + n), *idx_s = idx + n, *start = idx_s + n;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    HB_LAUNCH(ctx, pruned_keys_kernel, g, 256, 0, cols, n, keys, idx, count);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_s, idx, idx_s, (int)n, 0, 32, ctx->stream);
+    cub::DeviceScan::InclusiveScan(nullptr, b2, start, start, MaxOp(), (int)n, ctx->stream);
+    void *tmp; HB_CHECK(ctx, cudaMallocAsync(&tmp, std::max(b1, b2), ctx->stream));
+    HB_CHECK(ctx, cub::DeviceRadixSort::SortPairs(tmp, b1, keys, keys_s, idx, idx_s, (int)n, 0, 32, ctx->stream));         // stable: evaluation order inside a run
+    HB_LAUNCH(ctx, run_start_kernel, g, 256, 0, keys_s, n, start);
+    HB_CHECK(ctx, cub::DeviceScan::InclusiveScan(tmp, b2, start, start, MaxOp(), (int)n, ctx->stream));
+    HB_LAUNCH(ctx, access_scatter_kernel, g, 256, 0, idx_s, start, n, rank);
+    ctx->launches += 2;
+    cudaFreeAsync(tmp, ctx->stream); cudaFreeAsync(buf, ctx->stream);
+    return 0;
+}
+
+// the pruned MLP on the GPU (fun == 8): rowptr / cols are HOST arrays (the reference driver's sparsity pattern)
+extern "C" int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hidden, int n_out, const int *rowptr0, const int *cols0, const int *rowptr1,
+                                            const int *cols1, size_t *n_records) {
+    if (n_inputs < 1 || n_hidden < 1 || n_out < 1) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: layer sizes must be positive");
+    const int m[2] = {n_hidden, n_out}, nin[2] = {n_inputs, n_hidden};
+    const int *rp[2] = {rowptr0, rowptr1}, *cl[2] = {cols0, cols1};
+    size_t W[2], R[2], Lb[2];
+    std::vector<long long> recoff[2], laboff[2];
+    for (int l = 0; l < 2; l++) {
+        if (rp[l][0] != 0) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: rowptr must start at 0");
+        recoff[l].assign(m[l] + 1, 0); laboff[l].assign(m[l] + 1, 0);
+        for (int i = 0; i < m[l]; i++) {
+            const long long f = (long long)rp[l][i + 1] - rp[l][i];
+            if (f < 0) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: rowptr must be non-decreasing");
+            recoff[l][i + 1] = recoff[l][i] + (f ? 1 + 4 * (f - 1) : 0);
+            laboff[l][i + 1] = laboff[l][i] + (f ? 2 * f - 1 : 0);
+        }
+        W[l] = (size_t)rp[l][m[l]]; R[l] = (size_t)recoff[l][m[l]]; Lb[l] = (size_t)laboff[l][m[l]];
+        for (size_t p = 0; p < W[l]; p++) if (cl[l][p] < 0 || cl[l][p] >= nin[l]) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: column index out of range");
+    }
+    const size_t recs = R[0] + R[1] + W[0] + W[1] + (size_t)n_inputs + n_hidden + n_out + 1;
+    const size_t labels = (size_t)n_inputs + W[0] + W[1] + 1 + Lb[0] + Lb[1];
+    if (labels >= ((size_t)1 << 31) || recs >= ((size_t)1 << 31)) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: labels do not fit the reference's int");
+    HB_TRY(hb_trace_begin(ctx, recs));
+    TraceState &t = ctx->trace;
+    TrTuple *tr = (TrTuple *)t.tuples;
+    // device copies of the pattern and the prefix sums
+    int *d_rp[2], *d_cl[2]; long long *d_ro[2], *d_lo[2]; unsigned *d_rank[2], *d_cnt[2];
+    for (int l = 0; l < 2; l++) {
+        HB_CHECK(ctx, cudaMallocAsync(&d_rp[l], (m[l] + 1) * sizeof(int), ctx->stream));
+        HB_CHECK(ctx, cudaMallocAsync(&d_cl[l], std::max<size_t>(W[l], 1) * sizeof(int), ctx->stream));
+        HB_CHECK(ctx, cudaMallocAsync(&d_ro[l], (m[l] + 1) * sizeof(long long), ctx->stream));
+        HB_CHECK(ctx, cudaMallocAsync(&d_lo[l], (m[l] + 1) * sizeof(long long), ctx->stream));
+        HB_CHECK(ctx, cudaMallocAsync(&d_rank[l], std::max<size_t>(W[l], 1) * sizeof(unsigned), ctx->stream));
+        HB_CHECK(ctx, cudaMallocAsync(&d_cnt[l], nin[l] * sizeof(unsigned), ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(d_rp[l], rp[l], (m[l] + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (W[l]) HB_TRY(copy_from_host(ctx, d_cl[l], cl[l], W[l] * sizeof(int), ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(d_ro[l], recoff[l].data(), (m[l] + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(d_lo[l], laboff[l].data(), (m[l] + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        HB_TRY(rank_positions(ctx, d_cl[l], W[l], (size_t)nin[l], d_rank[l], d_cnt[l]));
+    }
+    // values, labels and initial access counters of the inputs / hidden values / outputs
+    const size_t nv = (size_t)n_inputs + n_hidden + n_out;
+    F *val; int *idx, *acc;
+    HB_CHECK(ctx, cudaMallocAsync(&val, nv * sizeof(F), ctx->stream));
+    HB_CHECK(ctx, cudaMallocAsync(&idx, 2 * nv * sizeof(int), ctx->stream));
+    acc = idx + nv;
+    HB_CHECK(ctx, cudaMemsetAsync(acc, 0, nv * sizeof(int), ctx->stream));
+    F *v_in = val, *v_h = val + n_inputs, *v_o = v_h + n_hidden;
+    int *i_in = idx, *i_h = idx + n_inputs, *i_o = i_h + n_hidden, *a_in = acc, *a_h = acc + n_inputs, *a_o = a_h + n_hidden;
+    HB_LAUNCH(ctx, mlp_inputs_kernel, (unsigned)((n_inputs + 255) / 256), 256, 0, v_in, i_in, n_inputs, (long long)1);
+    const long long w_label[2] = {(long long)n_inputs + 1, (long long)n_inputs + 1 + (long long)W[0]};
+    const long long zero_label = w_label[1] + (long long)W[1];
+    PrunedLayer L0{m[0], d_rp[0], d_cl[0], d_ro[0], d_lo[0], d_rank[0], w_label[0], zero_label + 1, 0, (int)zero_label};
+    HB_LAUNCH(ctx, pruned_layer_kernel, (unsigned)m[0], 256, 0, tr, L0, v_in, i_in, a_in, v_h, i_h, a_h);
+    PrunedLayer L1{m[1], d_rp[1], d_cl[1], d_ro[1], d_lo[1], d_rank[1], w_label[1], zero_label + 1 + (long long)Lb[0], R[0], (int)zero_label};
+    HB_LAUNCH(ctx, pruned_layer_kernel, (unsigned)m[1], 256, 0, tr, L1, v_h, i_h, a_h, v_o, i_o, a_o);
+    size_t rec = R[0] + R[1];
+    for (int l = 0; l < 2; l++) { HB_LAUNCH(ctx, pruned_delete_weights_kernel, (unsigned)m[l], 256, 0, tr + rec, d_rp[l], w_label[l]); rec += W[l]; }
+    HB_LAUNCH(ctx, pruned_delete_kernel, (unsigned)((n_inputs + 255) / 256), 256, 0, tr + rec, (size_t)n_inputs, v_in, i_in, a_in, d_cnt[0]); rec += n_inputs;
+    HB_LAUNCH(ctx, pruned_delete_kernel, (unsigned)((n_hidden + 255) / 256), 256, 0, tr + rec, (size_t)n_hidden, v_h, i_h, a_h, d_cnt[1]); rec += n_hidden;
+    HB_LAUNCH(ctx, pruned_delete_kernel, (unsigned)((n_out + 255) / 256), 256, 0, tr + rec, (size_t)n_out, v_o, i_o, a_o, (const unsigned *)nullptr); rec += n_out;
+    TrTuple z; memset(&z, 0, sizeof z); z.type = 0; z.idx_o = (int)zero_label; z.access_o = 0;
+    HB_CHECK(ctx, cudaMemcpyAsync(tr + rec, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+    rec += 1;
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < 2; l++) { cudaFreeAsync(d_rp[l], ctx->stream); cudaFreeAsync(d_cl[l], ctx->stream); cudaFreeAsync(d_ro[l], ctx->stream); cudaFreeAsync(d_lo[l], ctx->stream); cudaFreeAsync(d_rank[l], ctx->stream); cudaFreeAsync(d_cnt[l], ctx->stream); }
+    cudaFreeAsync(val, ctx->stream); cudaFreeAsync(idx, ctx->stream);
+    if (rec != recs) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: record count mismatch");
     t.n = rec; t.done = true;
     if (n_records) *n_records = rec;
     return 0;

@@ -57,6 +57,19 @@ void trace_generate_aes(int input_size) {
     CK(hb_trace_generate_aes(backend(), input_size, &n));
     have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
 }
+// 8f.4: the pruned MLP (fun == 8) likewise; `indexes` is the reference driver's sparsity pattern (Seval.cpp:1427-1437, drawn from libc rand())
+void trace_generate_pruned_mlp(const std::vector<std::vector<std::vector<unsigned short>>> &indexes, int n_inputs) {
+    std::vector<int> rp[2], cols[2];
+    for (int l = 0; l < 2; l++) {
+        rp[l].push_back(0);
+        for (const auto &row : indexes[l]) { for (unsigned short c : row) cols[l].push_back((int)c); rp[l].push_back((int)cols[l].size()); }
+        if (cols[l].empty()) cols[l].push_back(0);
+    }
+    size_t n = 0;
+    CK(hb_trace_generate_pruned_mlp(backend(), n_inputs, (int)indexes[0].size(), (int)indexes[1].size(), rp[0].data(), cols[0].data(), rp[1].data(),
+                                    cols[1].data(), &n));
+    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
+}
 // get_circuit_size (main.cpp:303-321): the number of delete records, rounded up to a power of two
 size_t trace_end() {
     size_t n = 0, ops = 0, dels = 0;

@@ -263,6 +263,12 @@ int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t
  * F((i*122+j)%256), 10 round keys F((i+j+1)%256), toy tables (x+21)%256 / (x+3)%256 / (x+4)%256 / xor) evaluated on the GPU: 1824 records
  * per block + the final deletes, exactly the records, labels and access counters of one pass of the CPU evaluator. */
 int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records);
+/* 8f.4: the pruned two-layer MLP (Seval.cpp:1170-1236 `inference` under the fun == 8 driver, :1424-1461): n_inputs inputs F((i+1)%256);
+ * neuron i of layer l reads cols_l[rowptr_l[i] .. rowptr_l[i+1]) (the reference's indexes[l][i], drawn from libc rand() by its driver: HOST
+ * arrays) with weights F((j+i)%256); layer 1 reads hidden values; a neuron without inputs is a copy of the gate `zero`.  The access counter
+ * of an input is the number of earlier reads of it in evaluation order (a stable rank, computed on the GPU). */
+int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hidden, int n_out, const int *rowptr0, const int *cols0, const int *rowptr1,
+                                 const int *cols1, size_t *n_records);
 int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out);
 int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S);
 int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy);

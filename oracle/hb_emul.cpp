@@ -429,6 +429,40 @@ int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records) {
     if (n_records) *n_records = ctx->tr_n;
     return 0;
 }
+/* Seval.cpp:1170-1236 `inference` under the fun == 8 driver (:1424-1461), restated gate by gate: two sparse layers, neuron i of layer l reads
+ * the entries cols_l[rowptr_l[i] .. rowptr_l[i+1]) of the previous layer; a neuron without inputs is a COPY of the gate `zero` */
+int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hidden, int n_out, const int *rowptr0, const int *cols0, const int *rowptr1,
+                                 const int *cols1, size_t *n_records) {
+    ctx->trace.clear(); ctx->tr_n = 0;
+    MlpEval E; E.ctx = ctx;
+    std::vector<emu_gt> input(n_inputs), hidden(n_hidden), outl(n_out);
+    std::vector<std::vector<emu_gt>> W0(n_hidden), W1(n_out);
+    for (int i = 0; i < n_inputs; i++) E.init(input[i], mk((uint64_t)((i + 1) % 256)));
+    for (int i = 0; i < n_hidden; i++) { W0[i].resize(rowptr0[i + 1] - rowptr0[i]); for (size_t j = 0; j < W0[i].size(); j++) E.init(W0[i][j], mk((uint64_t)((j + i) % 256))); }
+    for (int i = 0; i < n_out; i++) { W1[i].resize(rowptr1[i + 1] - rowptr1[i]); for (size_t j = 0; j < W1[i].size(); j++) E.init(W1[i][j], mk((uint64_t)((j + i) % 256))); }
+    emu_gt zero; E.init(zero, mk(0));
+    auto layer = [&](std::vector<std::vector<emu_gt>> &W, const int *rowptr, const int *cols, std::vector<emu_gt> &in, std::vector<emu_gt> &out) {
+        for (size_t i = 0; i < W.size(); i++) {
+            for (size_t j = 0; j < W[i].size(); j++) {
+                emu_gt &x = in[cols[rowptr[i] + j]];
+                if (j == 0) out[i] = E.op(W[i][j], x, 2);
+                else { emu_gt t = E.op(W[i][j], x, 2); emu_gt sum = E.op(out[i], t, 1); E.del(t); E.del(out[i]); out[i] = sum; }
+            }
+            if (W[i].empty()) out[i] = zero;
+        }
+    };
+    layer(W0, rowptr0, cols0, input, hidden);
+    layer(W1, rowptr1, cols1, hidden, outl);
+    for (auto &Wi : W0) for (auto &g : Wi) E.del(g);
+    for (auto &Wi : W1) for (auto &g : Wi) E.del(g);
+    for (auto &g : input) E.del(g);
+    for (auto &g : hidden) E.del(g);
+    for (auto &g : outl) E.del(g);
+    E.del(zero);
+    ctx->tr_done = true;
+    if (n_records) *n_records = ctx->tr_n;
+    return 0;
+}
 int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_deletes) {
     const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); size_t o = 0, d = 0;
     for (size_t i = 0; i < ctx->tr_n; i++) { if (t[i].type == 0) d++; else o++; }

@@ -68,6 +68,16 @@ int main(int argc, char **argv) {
         for (int i = 2; i < argc; i++) layer_size.push_back(atoi(argv[i]));
         if (layer_size.empty()) layer_size = {64, 32, 16};
     }
+    // fun == 8: the producer thread draws the sparsity pattern from libc rand() (Seval.cpp:1427-1437); the same expressions, compiled with the
+    // same flags, are replayed here from the same RNG state so that the GPU evaluator can be handed the pattern the reference will use
+    vector<vector<vector<unsigned short>>> pruned_idx(2);
+    if (fun == 8) {
+        srand(1);
+        pruned_idx[0].resize(1024); pruned_idx[1].resize(128);
+        for (int i = 0; i < (int)(prune_rate * 1024 * 128 * 128); i++) pruned_idx[0][((unsigned int)rand()) % 1024].push_back(((unsigned int)rand()) % (128 * 128));
+        for (int i = 0; i < (int)(prune_rate * 1024 * 128); i++) pruned_idx[1][((unsigned int)rand()) % 128].push_back(((unsigned int)rand()) % (256));
+        srand(1);
+    }
     std::thread t(Seval_Oracle); t.detach();
     init_stream(b, n_arg, d_arg);
     const size_t cs = circuit_size, B = BUFFER_SPACE;
@@ -140,10 +150,10 @@ int main(int argc, char **argv) {
             CHECK(ok, "stream \"lookup_witness_basic\" (2 cs), blocks of BUFFER_SPACE");
         }
     }
-    // ---- 8f.4: the same trace produced by the GPU evaluator instead of the producer thread (MLP, AES): every stream again ----------------
-    if (fun == 9 || fun == 5) {
+    // ---- 8f.4: the same trace produced by the GPU evaluator instead of the producer thread (MLP, pruned MLP, AES): every stream again ----------------
+    if (fun == 9 || fun == 5 || fun == 8) {
         t0 = now();
-        if (fun == 9) hobbit::trace_generate_mlp(layer_size); else hobbit::trace_generate_aes(1 << n_arg);
+        if (fun == 9) hobbit::trace_generate_mlp(layer_size); else if (fun == 5) hobbit::trace_generate_aes(1 << n_arg); else hobbit::trace_generate_pruned_mlp(pruned_idx);
         size_t gcs = hobbit::trace_end();
         double t_eval = now() - t0;
         CHECK(gcs == cs, "GPU circuit evaluator: circuit_size");
@@ -171,6 +181,7 @@ int main(int argc, char **argv) {
             for (size_t off = 0; off < 2 * cs; off += B) { read_stream(fq, v, (int)B); hobbit::read_stream(hfq, hv, (int)B); ok = ok && !memcmp(v.data(), hv.data(), B * 16); }
         }
         CHECK(ok, fun == 9 ? "GPU MLP evaluator (8f.4): witness, wiring and transcript streams identical to the reference's (labels, access counters, values)"
+                : fun == 8 ? "GPU pruned-MLP evaluator (8f.4): witness, wiring and transcript streams identical to the reference's (sparsity pattern replayed from libc rand())"
                            : "GPU AES evaluator (8f.4): witness, wiring, transcript and both lookup streams identical to the reference's");
         printf("      trace on the GPU in %.4f s (producer thread + upload: %.4f s)\n", t_eval, t_trace);
     }

@@ -574,3 +574,23 @@ def _raw_trace_generate_aes(self, input_size):
 
 
 RawABI.trace_generate_aes = _raw_trace_generate_aes
+
+
+def _raw_trace_generate_pruned(self, n_inputs, rows0, rows1):
+    """rows_l: list (one entry per neuron) of lists of column indices"""
+    def csr(rows):
+        rp = np.zeros(len(rows) + 1, dtype=np.int32)
+        rp[1:] = np.cumsum([len(r) for r in rows])
+        cols = np.array([c for r in rows for c in r] or [0], dtype=np.int32)
+        return rp, cols
+    rp0, c0 = csr(rows0)
+    rp1, c1 = csr(rows1)
+    n = ctypes.c_size_t(0)
+    self.call("hb_trace_generate_pruned_mlp", ctypes.c_int(n_inputs), ctypes.c_int(len(rows0)), ctypes.c_int(len(rows1)), rp0, c0, rp1, c1, ctypes.byref(n))
+    cnt = (ctypes.c_size_t * 3)()
+    self.call("hb_trace_finish", ctypes.byref(cnt, 0), ctypes.byref(cnt, 8), ctypes.byref(cnt, 16))
+    assert cnt[0] == n.value
+    return tuple(cnt)
+
+
+RawABI.trace_generate_pruned = _raw_trace_generate_pruned

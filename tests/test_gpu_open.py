@@ -1,5 +1,7 @@
 """8f.1 building blocks (csrc/open.cu) against their plain CPU restatements (oracle/hb_emul.cpp), same calls through the C ABI.
 Bit-exact: field elements are canonical, digests are bytes."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -199,4 +201,51 @@ def test_aes_evaluator(abis, blocks):
     for x, y in zip(g.trace_streams(cs, a_w, b_w, 1), e.trace_streams(cs, a_w, b_w, 1)):
         assert np.array_equal(x, y)
     for x, y in zip(g.trace_lookup_streams(cs, lr), e.trace_lookup_streams(cs, lr)):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("nbytes", [1 << 20, (1 << 20) + 16, (8 << 20) - 32, 8 << 20, (8 << 20) + 4096, (24 << 20) + 48, 100_000_016])
+def test_pageable_copies_roundtrip(abis, nbytes):
+    """Pageable host buffers >= 1 MiB cross PCIe through the context's pinned double buffer (8 MiB pieces, threaded host memcpy):
+    upload + download must be the identity at and around the piece boundaries, also back to back (the halves are reused)."""
+    g, _ = abis
+    rng = np.random.default_rng(nbytes % 1000)
+    src = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    dev = ctypes.c_void_p()
+    g.call("hb_malloc_device", ctypes.byref(dev), nbytes)
+    try:
+        for _ in range(2):
+            back = np.zeros(nbytes, dtype=np.uint8)
+            g.call("hb_memcpy", dev, src.ctypes.data_as(ctypes.c_void_p), nbytes)
+            g.call("hb_memcpy", back.ctypes.data_as(ctypes.c_void_p), dev, nbytes)
+            assert np.array_equal(back, src)
+            src = src[::-1].copy()
+    finally:
+        g.call("hb_free_device", dev)
+
+
+@pytest.mark.parametrize("shape", [(64, 16, 4, 0.3), (1000, 40, 8, 0.05), (16384, 1024, 128, 0.002), (300, 7, 3, 2.5)])
+def test_pruned_mlp_evaluator(abis, shape):
+    """8f.4: the pruned MLP (`inference`, Seval.cpp:1170-1236) evaluated on the GPU == the gate-by-gate restatement: random sparsity patterns
+    with repeated columns (access counters = stable ranks), neurons without inputs (copies of `zero`) and hidden values never read."""
+    g, e = abis
+    n_in, n_h, n_o, density = shape
+    rng = np.random.default_rng(n_in)
+    rows0 = [[] for _ in range(n_h)]
+    for _ in range(int(density * n_in * n_h)):
+        rows0[int(rng.integers(n_h))].append(int(rng.integers(n_in)))
+    rows1 = [[] for _ in range(n_o)]
+    for _ in range(int(density * 40 * n_o) + 3):
+        rows1[int(rng.integers(n_o))].append(int(rng.integers(min(n_h, 256))))
+    rows0[0] = []                                   # a hidden neuron without inputs ...
+    rows1[0] = [0, 0, 1] + rows1[0]                 # ... that is read twice
+    if n_o > 1:
+        rows1[1] = []
+    cg, ce = g.trace_generate_pruned(n_in, rows0, rows1), e.trace_generate_pruned(n_in, rows0, rows1)
+    assert cg == ce
+    cs = 1
+    while cs < max(ce[1], ce[2]):
+        cs *= 2
+    a_w, b_w = rand_field(rng, 1), rand_field(rng, 1)
+    for x, y in zip(g.trace_streams(cs, a_w, b_w, 0), e.trace_streams(cs, a_w, b_w, 0)):
         assert np.array_equal(x, y)
