@@ -21,7 +21,7 @@ def _run(binary, *args, timeout=300):
 
 
 @pytest.mark.skipif(not os.path.exists(EMUL), reason="oracle/_ref/circ_test_emul not prebuilt (needs /root/reference at build time)")
-@pytest.mark.parametrize("args", [(12, 64, 32, 16), (11, 128, 16, 8), (19, "aes", 4, 1), (11, "sql", 9, 1)])
+@pytest.mark.parametrize("args", [(12, 64, 32, 16), (11, 128, 16, 8), (19, "aes", 4, 1), (11, "sql", 9, 1), (14, "pruned", 20, 1, 1)])
 def test_mlp_circuit_host_logic_vs_reference(args):
     _run(EMUL, *args)
 
