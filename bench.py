@@ -297,7 +297,20 @@ def main():
                         "construction; the ncu pipe utilisation is in profiles/",
                 # from the committed `ncu --set full` capture of this kernel (profiles/r01_summary.md), NOT measured in this run
                 "int_pipes_ncu": {"issue_slots_busy_pct": 63.5, "alu_pipe_pct": 58.0, "fma_heavy_pipe_pct": 59.6, "dram_pct_of_peak": 11.4,
+                                  "warp_instructions_per_coefficient": 2450087936 / float(1 << 25),
                                   "source": "profiles/r01_summary.md (ncu --set full --clock-control none, one launch = 2^25 coefficients)"}}
+    # the binding roof of this kernel is instruction issue (4 warp-instructions per clock and SM): the ncu instruction count of the kernel
+    # (static for a given graph) over THIS run's launch time and SM clock
+    try:
+        sm_hz = float(clocks.get("sm_mhz") or 0) * 1e6
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        if name == "encode_cols_kernel" and sm_hz > 0:
+            inst = roofline["int_pipes_ncu"]["warp_instructions_per_coefficient"] * coeffs_per_launch
+            roofline["issue"] = {"achieved_warp_inst_per_clk_per_sm": inst / (per_launch_ms * 1e-3 * sm_hz * sms), "peak": 4.0,
+                                 "frac": inst / (per_launch_ms * 1e-3 * sm_hz * sms) / 4.0,
+                                 "note": "instruction-issue roofline: ncu instruction count x live launch time; ALU-pipe roof (2 warp-inst/clk/SM) in profiles/"}
+    except Exception:
+        pass
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
