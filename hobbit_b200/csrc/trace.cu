@@ -10,6 +10,7 @@
 // give every element its destination and the streams are written by one scatter kernel each — HBM-bound, 80 B read per tuple.
 #include "common.cuh"
 #include "aes_circuit.cuh"        // TrTuple + the AES gate program in closed form
+#include "sql_circuit.cuh"        // the SQL range-query gate program in closed form
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -337,6 +338,11 @@ pruned_delete_kernel(TrTuple *__restrict__ tr, size_t n, const F *__restrict__ v
     tr[i] = t;
 }
 
+__global__ void __launch_bounds__(256) sql_kernel(TrTuple *__restrict__ tr, int n, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < total) tr[gid] = sql_record(n, gid);
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -484,6 +490,20 @@ extern "C" int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hid
     if (rec != recs) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: record count mismatch");
     t.n = rec; t.done = true;
     if (n_records) *n_records = rec;
+    return 0;
+}
+
+// the SQL range query on the GPU (fun == 6: `pigeon 6 b n d`, input_size = 2^n rows)
+extern "C" int hb_trace_generate_sql(hb_ctx *ctx, int input_size, size_t *n_records) {
+    if (input_size < 1) HB_FAIL(ctx, "hb_trace_generate_sql: need at least one row");
+    const size_t recs = sql_records(input_size);
+    if ((size_t)input_size * (kSqlRowLabels + 1) + 300 >= ((size_t)1 << 31)) HB_FAIL(ctx, "hb_trace_generate_sql: labels do not fit the reference's int");
+    HB_TRY(hb_trace_begin(ctx, recs));
+    TraceState &t = ctx->trace;
+    HB_LAUNCH(ctx, sql_kernel, (unsigned)((recs + 255) / 256), 256, 0, (TrTuple *)t.tuples, input_size, recs);
+    HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    t.n = recs; t.done = true;
+    if (n_records) *n_records = recs;
     return 0;
 }
 

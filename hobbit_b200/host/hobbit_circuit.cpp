@@ -70,6 +70,12 @@ void trace_generate_pruned_mlp(const std::vector<std::vector<std::vector<unsigne
                                     cols[1].data(), &n));
     have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
 }
+// 8f.4: the SQL range query (fun == 6, input_size = 2^n rows) likewise
+void trace_generate_sql(int input_size) {
+    size_t n = 0;
+    CK(hb_trace_generate_sql(backend(), input_size, &n));
+    have_witness = have_transcript = have_wiring = trace_loaded = have_lkp_basic = have_lkp_wit = have_circuit = false;
+}
 // get_circuit_size (main.cpp:303-321): the number of delete records, rounded up to a power of two
 size_t trace_end() {
     size_t n = 0, ops = 0, dels = 0;

@@ -173,6 +173,7 @@ bool trace_append(const tr_tuple *buf, size_t n);
 size_t trace_end();
 void trace_generate_mlp(const std::vector<int> &layer_size);   // 8f.4: MLP_inference (Seval.cpp:1238-1286) evaluated on the GPU; then trace_end()
 void trace_generate_aes(int input_size);                        // 8f.4: AES (Seval.cpp:991-1084, fun == 5 driver) evaluated on the GPU; then trace_end()
+void trace_generate_sql(int input_size);                        // 8f.4: range_query (Seval.cpp:1085-1166, fun == 6 driver) evaluated on the GPU
 void trace_generate_pruned_mlp(const std::vector<std::vector<std::vector<unsigned short>>> &indexes, int n_inputs = 128 * 128);   // 8f.4: `inference` (Seval.cpp:1170-1236, fun == 8 driver)
 const F *resident_stream(const stream_descriptor &fd);          // the whole logical stream in HBM, nullptr for non-circuit streams
 bool read_circuit_stream(stream_descriptor &fd, std::vector<F> &v, int size);

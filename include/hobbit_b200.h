@@ -269,6 +269,9 @@ int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records);
  * of an input is the number of earlier reads of it in evaluation order (a stable rank, computed on the GPU). */
 int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hidden, int n_out, const int *rowptr0, const int *cols0, const int *rowptr1,
                                  const int *cols1, size_t *n_records);
+/* 8f.4: the SQL range-query circuit (Seval.cpp:1085-1166 range_query with get_bytes :667-687, ltu_gate :223-293 and lookup_gate :190-221
+ * under the fun == 6 driver, :1398-1416: DB[i] = F((i+12)%16), L = 21, R = 321, two bytes per word) evaluated on the GPU. */
+int hb_trace_generate_sql(hb_ctx *ctx, int input_size, size_t *n_records);
 int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out);
 int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S);
 int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy);

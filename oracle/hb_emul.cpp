@@ -463,6 +463,74 @@ int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hidden, int n_
     if (n_records) *n_records = ctx->tr_n;
     return 0;
 }
+/* Seval.cpp:190-221 lookup_gate, :223-293 ltu_gate, :667-687 get_bytes, :1085-1166 range_query under the fun == 6 driver (:1398-1416),
+ * restated gate by gate; domain = 16 (two bytes per word) */
+int hb_trace_generate_sql(hb_ctx *ctx, int input_size, size_t *n_records) {
+    ctx->trace.clear(); ctx->tr_n = 0;
+    AesEval E; E.ctx = ctx;
+    const int NB = 2;
+    std::vector<emu_gt> DB(input_size), range_table(256), pows(NB);
+    for (int i = 0; i < input_size; i++) E.init(DB[i], mk((uint64_t)((i + 12) % 16)));
+    emu_gt R, L, zero, minus_one;
+    E.init(R, mk(321)); E.init(L, mk(21));
+    for (int i = 0; i < 256; i++) E.init(range_table[i], mk((uint64_t)i));
+    for (int i = 0; i < NB; i++) E.init(pows[i], mk((uint64_t)1 << (8 * i)));
+    E.init(zero, mk(0)); E.init(minus_one, mk(P - 1));
+    auto get_bytes = [&](emu_gt &word) {
+        std::vector<emu_gt> bytes(NB);
+        unsigned v = (unsigned)word.value.re;
+        for (int i = 0; i < NB; i++) { emu_gt &e = range_table[v % 256]; bytes[i] = E.table_gate(e, zero, 0, e.value.re); v >>= 8; }
+        emu_gt check = E.op(pows[0], bytes[0], 2);
+        for (int i = 1; i < NB; i++) { emu_gt tp = E.op(pows[i], bytes[i], 2); emu_gt tc = E.op(check, tp, 1); E.del(check); E.del(tp); check = tc; }
+        E.del(check);
+        return bytes;
+    };
+    auto ltu = [&](std::vector<emu_gt> &b1, std::vector<emu_gt> &b2) {
+        std::vector<emu_gt> lt(NB), eq(NB - 1);
+        for (int i = 0; i < NB; i++) lt[i] = E.table_gate(b1[i], b2[i], 1, b2[i].value.re < b1[i].value.re ? 1 : 0);
+        for (int i = 0; i < NB - 1; i++) eq[i] = E.table_gate(b1[i], b2[i], 2, b2[i].value.re == b1[i].value.re ? 1 : 0);
+        for (int i = NB - 3; i >= 0; i--) { emu_gt tp = E.op(eq[i], eq[i + 1], 2); E.del(eq[i]); eq[i] = tp; }
+        emu_gt out = E.op(eq[0], lt[0], 2);
+        for (int i = 1; i < NB - 2; i++) { emu_gt tp = E.op(eq[i], lt[i], 2); emu_gt to = E.op(out, tp, 1); E.del(out); E.del(tp); out = to; }
+        emu_gt to = E.op(out, lt[NB - 1], 1); E.del(out); out = to;
+        for (auto &g : lt) E.del(g);
+        for (auto &g : eq) E.del(g);
+        return out;
+    };
+    std::vector<emu_gt> Lb = get_bytes(L), Rb = get_bytes(L), mx(NB);            /* sic: both from L (Seval.cpp:1099) */
+    for (int i = 0; i < input_size; i++) {
+        std::vector<emu_gt> bytes = get_bytes(DB[i]);
+        emu_gt bit1 = ltu(bytes, Rb), bit2 = ltu(Lb, bytes);
+        emu_gt bit = E.op(bit1, bit2, 2);
+        E.del(bit1); E.del(bit2);
+        std::vector<emu_gt> tm(NB);
+        for (int j = 0; j < NB; j++) tm[j] = E.op(bytes[j], bit, 2);
+        E.del(bit);
+        for (int j = 0; j < NB; j++) E.del(bytes[j]);
+        if (i == 0) mx = tm;
+        else {
+            emu_gt mb = ltu(tm, mx);
+            emu_gt mbn = E.op(mb, minus_one, 1);
+            for (int j = 0; j < NB; j++) {
+                emu_gt p1 = E.op(mx[j], mb, 2), p2 = E.op(tm[j], mbn, 2);
+                E.del(mx[j]); E.del(tm[j]);
+                mx[j] = E.op(p1, p2, 1);
+                E.del(p1); E.del(p2);
+            }
+            E.del(mb); E.del(mbn);
+        }
+    }
+    for (auto &g : mx) E.del(g);
+    E.del(zero);
+    for (auto &g : pows) E.del(g);
+    for (auto &g : range_table) E.del(g);
+    for (int i = 0; i < NB; i++) { E.del(Lb[i]); E.del(Rb[i]); }
+    for (auto &g : DB) E.del(g);
+    E.del(R); E.del(L); E.del(minus_one);
+    ctx->tr_done = true;
+    if (n_records) *n_records = ctx->tr_n;
+    return 0;
+}
 int hb_trace_finish(hb_ctx *ctx, size_t *n_records, size_t *n_ops, size_t *n_deletes) {
     const emu_tuple *t = (const emu_tuple *)ctx->trace.data(); size_t o = 0, d = 0;
     for (size_t i = 0; i < ctx->tr_n; i++) { if (t[i].type == 0) d++; else o++; }

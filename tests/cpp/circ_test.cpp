@@ -151,9 +151,9 @@ int main(int argc, char **argv) {
         }
     }
     // ---- 8f.4: the same trace produced by the GPU evaluator instead of the producer thread (MLP, pruned MLP, AES): every stream again ----------------
-    if (fun == 9 || fun == 5 || fun == 8) {
+    if (fun == 9 || fun == 5 || fun == 8 || fun == 6) {
         t0 = now();
-        if (fun == 9) hobbit::trace_generate_mlp(layer_size); else if (fun == 5) hobbit::trace_generate_aes(1 << n_arg); else hobbit::trace_generate_pruned_mlp(pruned_idx);
+        if (fun == 9) hobbit::trace_generate_mlp(layer_size); else if (fun == 5) hobbit::trace_generate_aes(1 << n_arg); else if (fun == 6) hobbit::trace_generate_sql(1 << n_arg); else hobbit::trace_generate_pruned_mlp(pruned_idx);
         size_t gcs = hobbit::trace_end();
         double t_eval = now() - t0;
         CHECK(gcs == cs, "GPU circuit evaluator: circuit_size");
@@ -182,6 +182,7 @@ int main(int argc, char **argv) {
         }
         CHECK(ok, fun == 9 ? "GPU MLP evaluator (8f.4): witness, wiring and transcript streams identical to the reference's (labels, access counters, values)"
                 : fun == 8 ? "GPU pruned-MLP evaluator (8f.4): witness, wiring and transcript streams identical to the reference's (sparsity pattern replayed from libc rand())"
+                : fun == 6 ? "GPU SQL evaluator (8f.4): witness, wiring, transcript and both lookup streams identical to the reference's"
                            : "GPU AES evaluator (8f.4): witness, wiring, transcript and both lookup streams identical to the reference's");
         printf("      trace on the GPU in %.4f s (producer thread + upload: %.4f s)\n", t_eval, t_trace);
     }

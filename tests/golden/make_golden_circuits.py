@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CASES = {
     "mlp_64_32_16": {"fun": 9, "b": 12, "n": 12, "d": 1, "extra": [64, 32, 16]},
     "aes_16_blocks": {"fun": 5, "b": 19, "n": 4, "d": 1, "extra": []},
+    "sql_512_rows": {"fun": 6, "b": 11, "n": 9, "d": 1, "extra": []},
     # pattern_order: the order in which the reference's compiler (g++, gnu++14) evaluates the two rand() calls of
     # `indexes[l][rand() % rows].push_back(rand() % cols)` (Seval.cpp:1431-1436) — found by replaying both orders against these digests
     "pruned_mlp_rate_1pct": {"fun": 8, "b": 14, "n": 20, "d": 1, "extra": [], "prune_rate": 0.01, "pattern_order": "row_first"},
@@ -35,7 +36,7 @@ def child(name):
     L.ref_circuit_start.restype = ctypes.c_size_t
     extra = (ctypes.c_int * max(1, len(c["extra"])))(*c["extra"])
     cs = L.ref_circuit_start(c["fun"], c["b"], c["n"], c["d"], extra, len(c["extra"]))
-    lookups = c["fun"] == 5
+    lookups = c["fun"] in (5, 6)
     ctypes.c_bool.in_dll(L, "has_lookups").value = lookups              # what prove_circuit sets before it reads the streams (main.cpp:888)
     L.ref_buffer_space.restype = ctypes.c_size_t
     B = L.ref_buffer_space()

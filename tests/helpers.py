@@ -576,6 +576,18 @@ def _raw_trace_generate_aes(self, input_size):
 RawABI.trace_generate_aes = _raw_trace_generate_aes
 
 
+def _raw_trace_generate_sql(self, input_size):
+    n = ctypes.c_size_t(0)
+    self.call("hb_trace_generate_sql", ctypes.c_int(input_size), ctypes.byref(n))
+    cnt = (ctypes.c_size_t * 3)()
+    self.call("hb_trace_finish", ctypes.byref(cnt, 0), ctypes.byref(cnt, 8), ctypes.byref(cnt, 16))
+    assert cnt[0] == n.value
+    return tuple(cnt)
+
+
+RawABI.trace_generate_sql = _raw_trace_generate_sql
+
+
 def _raw_trace_generate_pruned(self, n_inputs, rows0, rows1):
     """rows_l: list (one entry per neuron) of lists of column indices"""
     def csr(rows):

@@ -25,6 +25,18 @@ def test_closed_form_records_equal_gate_by_gate(tmp_path):
     for blocks in (1, 2, 17):
         p = subprocess.run([exe, str(blocks)], capture_output=True, text=True, timeout=120)
         assert p.returncode == 0 and "every derived stream identical" in p.stdout, p.stdout[-1000:] + p.stderr[-1000:]
+    for rows in (1, 2, 5, 37, 300):                                  # the SQL range-query circuit (sql_circuit.cuh)
+        p = subprocess.run([exe, str(rows), "sql"], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0 and "every derived stream identical" in p.stdout, p.stdout[-1000:] + p.stderr[-1000:]
+
+
+@pytest.mark.skipif(not os.path.exists(PROVE), reason="oracle/prove_emul not built (__graft_entry__.build())")
+def test_reference_free_sql_proof_runs_on_emulation():
+    """the SQL flow at a small size (the full-run KAT `pigeon 6 19 17 1` -> 1329.890625 KB is checked on the GPU, tests/test_circuit_cpp.py)"""
+    p = subprocess.run([PROVE, "11", "sql", "9", "--reps", "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["ps_kb"] > 0
 
 
 @pytest.mark.skipif(not os.path.exists(PROVE), reason="oracle/prove_emul not built (__graft_entry__.build())")

@@ -63,3 +63,18 @@ def test_aes_prove_reference_free_ps_kat():
     d = json.loads(line)
     print(line)
     assert d["ps_kb"] == 1135.046875
+
+
+@pytest.mark.gpu
+def test_sql_prove_reference_free_ps_kat():
+    """Same for the SQL range query (`pigeon 6 19 17 1`, 2^17 rows, 2^22 gates): Ps must be the reference's 1329.890625 KB."""
+    import json
+    binary = os.path.join(ROOT, "hobbit_b200", "mlp_prove")
+    if not os.path.exists(binary):
+        pytest.skip("hobbit_b200/mlp_prove not built")
+    p = subprocess.run([binary, "19", "sql", "17", "--reps", "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    print(line)
+    assert d["ps_kb"] == 1329.890625

@@ -38,6 +38,8 @@ def check(abi, name):
         abi.trace_generate_mlp(g["extra"])
     elif g["fun"] == 5:
         abi.trace_generate_aes(1 << g["n"])
+    elif g["fun"] == 6:
+        abi.trace_generate_sql(1 << g["n"])
     else:
         rows0, rows1 = pruned_pattern(g["prune_rate"], g["pattern_order"])
         abi.trace_generate_pruned(128 * 128, rows0, rows1)

@@ -249,3 +249,21 @@ def test_pruned_mlp_evaluator(abis, shape):
     a_w, b_w = rand_field(rng, 1), rand_field(rng, 1)
     for x, y in zip(g.trace_streams(cs, a_w, b_w, 0), e.trace_streams(cs, a_w, b_w, 0)):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("rows", [1, 2, 21, 512, 5000])
+def test_sql_evaluator(abis, rows):
+    """8f.4: the SQL range-query circuit evaluated on the GPU (closed-form records) == the gate-by-gate restatement of range_query
+    (Seval.cpp:1085-1166): every derived stream including both lookup streams."""
+    g, e = abis
+    cg, ce = g.trace_generate_sql(rows), e.trace_generate_sql(rows)
+    assert cg == ce
+    cs = 1
+    while cs < max(ce[1], ce[2]):
+        cs *= 2
+    rng = np.random.default_rng(rows)
+    a_w, b_w, lr = rand_field(rng, 1), rand_field(rng, 1), rand_field(rng, 4)
+    for x, y in zip(g.trace_streams(cs, a_w, b_w, 1), e.trace_streams(cs, a_w, b_w, 1)):
+        assert np.array_equal(x, y)
+    for x, y in zip(g.trace_lookup_streams(cs, lr), e.trace_lookup_streams(cs, lr)):
+        assert np.array_equal(x, y)

@@ -1,7 +1,8 @@
 // Reference-free end-to-end MLP proof on the GPU (BASELINE config 3 without the CPU evaluator): the circuit is evaluated on the GPU
 // (hobbit::trace_generate_mlp), every stream is derived there, then the prove_circuit sequence (main.cpp:862-886):
 // commit(witness) -> prove_multiplication_tree_stream_shallow(wiring, 8) -> prove_gate_consistency -> open(witness).
-// `mlp_prove <b> aes <n>` is the same for the AES circuit with lookups (`pigeon 5 b n 1`, 2^n blocks; hobbit::trace_generate_aes and the
+// `mlp_prove <b> aes <n>` / `mlp_prove <b> sql <n>` are the same for the lookup circuits (`pigeon 5 b n 1`, 2^n AES blocks / `pigeon 6 b n 1`,
+// 2^n database rows; hobbit::trace_generate_aes / trace_generate_sql and the
 // fun == 5 sequence main.cpp:887-917: commit(witness), lookup_rand, commit(lookup_witness_basic), the wiring and lookup product trees,
 // prove_gate_consistency_lookups, both opens).
 // Links only libhobbit_host.so / libhobbit_b200.so.   usage: mlp_prove <log2 BUFFER_SPACE> <layer sizes...> [--reps R] | mlp_prove <b> aes <n> [--reps R]
@@ -18,10 +19,10 @@ static double now() { return std::chrono::duration<double>(std::chrono::steady_c
 int main(int argc, char **argv) {
     int b = argc > 1 ? atoi(argv[1]) : 18, reps = 2;
     std::vector<int> layers;
-    int aes_n = -1;
+    int aes_n = -1; bool sql = false;                        // aes_n: log2 of the blocks (AES) or rows (SQL) of a lookup circuit
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "--reps")) { reps = atoi(argv[++i]); continue; }
-        if (!strcmp(argv[i], "aes")) { aes_n = atoi(argv[++i]); continue; }
+        if (!strcmp(argv[i], "aes") || !strcmp(argv[i], "sql")) { sql = !strcmp(argv[i], "sql"); aes_n = atoi(argv[++i]); continue; }
         layers.push_back(atoi(argv[i]));
     }
     if (layers.empty()) layers = {1024, 256, 256, 16};
@@ -32,7 +33,7 @@ int main(int argc, char **argv) {
         fflush(stdout); dup2(fileno(nul), 1);               // the reference-style printf chatter of the provers
         srand(1);
         double t0 = now();
-        if (aes_n >= 0) trace_generate_aes(1 << aes_n); else trace_generate_mlp(layers);
+        if (aes_n >= 0 && sql) trace_generate_sql(1 << aes_n); else if (aes_n >= 0) trace_generate_aes(1 << aes_n); else trace_generate_mlp(layers);
         cs = trace_end();
         double t1 = now();
         BUFFER_SPACE = (size_t)1 << b;
@@ -67,7 +68,7 @@ int main(int argc, char **argv) {
         if (rd != wr) { printf("memory consistency check FAILED\n"); return 1; }
         if (rep) { const double t[6] = {t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0}; for (int i = 0; i < 6; i++) best[i] = std::min(best[i], t[i]); }
     }
-    if (aes_n >= 0) printf("{\"workload\": \"AES prove_circuit (lookups), 2^%d blocks", aes_n);
+    if (aes_n >= 0) printf("{\"workload\": \"%s prove_circuit (lookups), 2^%d %s", sql ? "SQL" : "AES", aes_n, sql ? "rows" : "blocks");
     else { printf("{\"workload\": \"MLP prove_circuit, layers"); for (int l : layers) printf(" %d", l); }
     printf(", circuit_size 2^%d, BUFFER_SPACE 2^%d\", \"evaluate_s\": %.5f, \"commit_s\": %.5f, \"mul_tree_s\": %.5f, \"gate_s\": %.5f, \"open_s\": %.5f, \"total_s\": %.5f, "
            "\"ps_kb\": %.6f, \"gates_per_s\": %.1f, \"gpu_launches\": %llu}\n",
