@@ -7,6 +7,7 @@
 // array of 32-byte digests, level after level, leaves first (== the reference's MT_hashes[lvl][i]).
 #include "common.cuh"
 #include <thread>
+#include <sys/mman.h>
 #include <new>
 #include <algorithm>
 
@@ -124,6 +125,12 @@ int copy_from_host(hb_ctx *ctx, void *dst_dev, const void *src_host, size_t byte
 }
 int copy_to_host(hb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream) {
     HB_TRY(pin_ready(ctx));
+    // a freshly allocated destination (the usual case: a std::vector level sized just before the call) is first touched here; with
+    // transparent huge pages the 2 MiB-aligned interior faults 512 x fewer times (advisory, ignored where THP is off)
+    if (bytes >= ((size_t)4 << 20)) {
+        const uintptr_t lo = ((uintptr_t)dst_host + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1), hi = ((uintptr_t)dst_host + bytes) & ~(((uintptr_t)2 << 20) - 1);
+        if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
+    }
     const size_t npieces = (bytes + kPinPiece - 1) / kPinPiece;
     for (size_t i = 0; i <= npieces; i++) {
         if (i < npieces) {
