@@ -607,6 +607,7 @@ extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs,
     HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
     size_t off = 0, n = 4 * el.B;
     for (int l = 0; l < nlevels; l++, n /= 2) {
+        if (!level_ptrs[l]) { off += n; continue; }
         if (n * 32 >= kPageableDirect && !is_device_ptr(level_ptrs[l]) && !is_pinned_host_ptr(level_ptrs[l])) { HB_TRY(copy_to_host(ctx, level_ptrs[l], el.leaves + off * 32, n * 32, ctx->stream)); }
         else HB_CHECK(ctx, cudaMemcpyAsync(level_ptrs[l], el.leaves + off * 32, n * 32, cudaMemcpyDefault, ctx->stream));
         off += n;

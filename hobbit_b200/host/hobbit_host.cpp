@@ -15,6 +15,7 @@ int tensor_row_size = 128;
 size_t BUFFER_SPACE = 0;
 bool linear_time = false;
 bool materialize_tensor = false;
+bool commit_levels_on_host = true;
 
 static hb_ctx *g_ctx = nullptr;
 [[noreturn]] static void die(const char *what) {
@@ -251,7 +252,7 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     MT_hashes.clear();
     std::vector<uint8_t *> ptrs;
     for (size_t n = 4 * BUFFER_SPACE;; n /= 2) { MT_hashes.emplace_back(n); if (n == 1) break; }
-    for (auto &lv : MT_hashes) ptrs.push_back((uint8_t *)lv.data());
+    for (auto &lv : MT_hashes) ptrs.push_back(commit_levels_on_host || lv.size() <= 1024 ? (uint8_t *)lv.data() : nullptr);
     CK(hb_elastic_finish_levels(backend(), ptrs.data(), (int)ptrs.size()));
     if (trace) fprintf(stderr, "[hobbit trace] commit(%s, %zu): stream + pushes %.3f ms, levels %.3f ms\n", fd.name.c_str(), (size_t)fd.size, t_pushed - t_begin, wall_ms() - t_pushed);
 }

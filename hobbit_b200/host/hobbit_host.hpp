@@ -100,6 +100,9 @@ std::vector<_hash> open_tree_blake(std::vector<std::vector<_hash>> &MT_hashes, s
 // in HBM for the open phase; copying 64 B per coefficient back to the host is what the reference's layout implies
 // but not what its open needs).
 extern bool materialize_tensor;
+// false: Elastic_PC commit() sizes every MT_hashes level as the reference does but only FILLS the levels of <= 1024 digests (root included);
+// the big levels stay in HBM.  The prover (open()) only uses the level sizes; a caller that hands the tree to a verifier keeps the default.
+extern bool commit_levels_on_host;
 void commit_standard(std::vector<F> &poly, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes,
                      std::vector<std::vector<std::vector<F>>> &_tensor, int K);
 // The data-parallel front half of open_standard (Our_PC.cpp:604-660): beta = eq(x1), aggregate, the rand()-drawn

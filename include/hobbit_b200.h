@@ -129,7 +129,8 @@ int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, const hb_F *bet
 int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time);
 int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk);
 int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out);
-/* the same, level l (4B >> l digests) written straight to level_ptrs[l] — the reference's MT_hashes[l] — nlevels = log2(4B)+1 */
+/* the same, level l (4B >> l digests) written straight to level_ptrs[l] — the reference's MT_hashes[l] — nlevels = log2(4B)+1;
+ * a NULL level_ptrs[l] skips that level (a prover that only needs the root and the level SIZES, see hobbit::commit_levels_on_host) */
 int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels);
 /* ---- O2, data-parallel front half of Elastic_PC open (Elastic_PC.cpp:316-333 aggregate, 487-533 compute_aggregation_reply) --------
  * begin: the `queries` cells (col[q], row[q]) drawn by the host (Elastic_PC.cpp:649-655), nchunks = N/B.  push chunk i with beta[i]:

@@ -157,7 +157,7 @@ int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevel
     std::vector<uint8_t> flat((8 * ctx->eB - 1) * 32);
     orc_elastic_commit_stream(ctx->estream.data(), ctx->estream.size(), ctx->eB, ctx->etrs, ctx->elin, flat.data());
     size_t off = 0, n = 4 * ctx->eB;
-    for (int l = 0; l < nlevels; l++, n /= 2) { memcpy(level_ptrs[l], flat.data() + off * 32, n * 32); off += n; }
+    for (int l = 0; l < nlevels; l++, n /= 2) { if (level_ptrs[l]) memcpy(level_ptrs[l], flat.data() + off * 32, n * 32); off += n; }
     ctx->estream.clear(); return 0;
 }
 int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int lin, const uint32_t *col, const uint32_t *row, size_t queries, size_t nchunks) {

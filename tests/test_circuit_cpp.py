@@ -78,3 +78,17 @@ def test_sql_prove_reference_free_ps_kat():
     d = json.loads(line)
     print(line)
     assert d["ps_kb"] == 1329.890625
+
+
+@pytest.mark.gpu
+def test_prove_with_resident_levels_same_ps():
+    """hobbit::commit_levels_on_host = false (big Merkle levels stay in HBM, only the levels of <= 1024 digests are filled): the prover only
+    uses the level sizes, so the proof-size counter of the reference-free AES run is unchanged."""
+    import json
+    binary = os.path.join(ROOT, "hobbit_b200", "mlp_prove")
+    if not os.path.exists(binary):
+        pytest.skip("hobbit_b200/mlp_prove not built")
+    p = subprocess.run([binary, "19", "aes", "8", "--reps", "1", "--resident-levels"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["ps_kb"] == 1135.046875

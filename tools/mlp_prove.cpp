@@ -22,6 +22,7 @@ int main(int argc, char **argv) {
     int aes_n = -1; bool sql = false;                        // aes_n: log2 of the blocks (AES) or rows (SQL) of a lookup circuit
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "--reps")) { reps = atoi(argv[++i]); continue; }
+        if (!strcmp(argv[i], "--resident-levels")) { commit_levels_on_host = false; continue; }      // prover-only run: big Merkle levels stay in HBM
         if (!strcmp(argv[i], "aes") || !strcmp(argv[i], "sql")) { sql = !strcmp(argv[i], "sql"); aes_n = atoi(argv[++i]); continue; }
         layers.push_back(atoi(argv[i]));
     }
