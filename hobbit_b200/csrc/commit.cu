@@ -179,11 +179,47 @@ extern "C" int hb_ctx_create(hb_ctx **out, int device) {
     return 0;
 }
 
+static int stager_init(hb_ctx *ctx, ChunkStager &st, size_t B) {
+    for (int q = 0; q < 2; q++) {
+        HB_CHECK(ctx, cudaMallocAsync(&st.buf[q], B * sizeof(F), ctx->stream));
+        HB_CHECK(ctx, cudaEventCreateWithFlags(&st.copied[q], cudaEventDisableTiming));
+        HB_CHECK(ctx, cudaEventCreateWithFlags(&st.consumed[q], cudaEventDisableTiming));
+        st.used[q] = false;
+    }
+    st.count = 0;
+    // the buffers are stream-ordered allocations of the compute stream: the copy stream may touch them only after this point
+    HB_CHECK(ctx, cudaEventRecord(st.consumed[0], ctx->stream));
+    HB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, st.consumed[0], 0));
+    return 0;
+}
+static void stager_free(hb_ctx *ctx, ChunkStager &st) {
+    for (int q = 0; q < 2; q++) {
+        if (st.buf[q]) { cudaStreamSynchronize(ctx->copy_stream); cudaFreeAsync(st.buf[q], ctx->stream); }
+        if (st.copied[q]) cudaEventDestroy(st.copied[q]);
+        if (st.consumed[q]) cudaEventDestroy(st.consumed[q]);
+    }
+    st = ChunkStager();
+}
+// host chunk -> device staging buffer; *src is valid for kernels launched on ctx->stream after this call; call stager_consumed after them
+static int stager_push(hb_ctx *ctx, ChunkStager &st, const void *chunk, size_t B, const F **src, int *slot) {
+    const int q = (int)(st.count++ & 1);
+    if (st.used[q]) HB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, st.consumed[q], 0));      // the encode of chunk i-2 read this buffer
+    HB_CHECK(ctx, cudaMemcpyAsync(st.buf[q], chunk, B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
+    HB_CHECK(ctx, cudaEventRecord(st.copied[q], ctx->copy_stream));
+    // pageable memory has been staged by the driver when cudaMemcpyAsync returns; a pinned buffer is read by the DMA engine later
+    if (is_pinned_host_ptr(chunk)) HB_CHECK(ctx, cudaEventSynchronize(st.copied[q]));
+    HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, st.copied[q], 0));
+    st.used[q] = true;
+    *src = st.buf[q]; *slot = q;
+    return 0;
+}
+static int stager_consumed(hb_ctx *ctx, ChunkStager &st, int slot) { HB_CHECK(ctx, cudaEventRecord(st.consumed[slot], ctx->stream)); return 0; }
+
 static void elastic_free(hb_ctx *ctx) {
     ElasticState &el = ctx->el;
     for (int i = 0; i < 3; i++) if (el.park[i]) cudaFreeAsync(el.park[i], ctx->stream);
     if (el.tensor) cudaFreeAsync(el.tensor, ctx->stream);
-    if (el.msg) cudaFreeAsync(el.msg, ctx->stream);
+    stager_free(ctx, el.stg);
     if (el.leaves) cudaFreeAsync(el.leaves, ctx->stream);
     el = ElasticState();
 }
@@ -335,7 +371,7 @@ extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K
             HB_CHECK(ctx, cudaMalloc(&ctx->poly, N * sizeof(F)));
             ctx->poly_elems = N;
         }
-        ctx->poly_host = poly;
+        ctx->poly_valid = false;                           // set again only once the whole polynomial has arrived (end of this call)
     }
     // Chunks are processed in groups of G through ONE launch per kernel (grid.y = chunk): no per-chunk grid tail.
     // The inner leaf digests of a group are staged in HBM (32 B per coefficient) and chained in chunk order afterwards.
@@ -382,6 +418,7 @@ extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K
     if (tensor_out) HB_CHECK(ctx, cudaMemcpyAsync(tensor_out, ctx->tensor, 4 * N * sizeof(F), cudaMemcpyDefault, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto &e : ev) cudaEventDestroy(e);
+    if (!on_dev) ctx->poly_valid = true;                  // the whole polynomial is resident: hb_aggregate(poly = NULL) may use it
     return 0;
 }
 
@@ -538,9 +575,9 @@ extern "C" int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, cons
     const size_t B = N / K;
     Staged p(ctx), b(ctx), o(ctx);
     const F *src;
-    if (poly == nullptr || (!is_device_ptr(poly) && ctx->poly && ctx->poly_elems == N && ctx->poly_host == (const void *)poly)) {
-        if (!ctx->poly || ctx->poly_elems != N) HB_FAIL(ctx, "hb_aggregate: no resident polynomial of this size (pass poly)");
-        src = ctx->poly;                                   // device copy kept by hb_commit_standard
+    if (poly == nullptr) {                                 // explicit request only: identity is never inferred from a host address
+        if (!ctx->poly || !ctx->poly_valid || ctx->poly_elems != N) HB_FAIL(ctx, "hb_aggregate: no resident polynomial of this size (pass poly)");
+        src = ctx->poly;                                   // device copy kept by the last successful hb_commit_standard from host memory
     } else {
         HB_TRY(p.in(poly, N * sizeof(F))); src = p.as<F>();
     }
@@ -562,7 +599,7 @@ extern "C" int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time)
     // stream-ordered pool allocations: a commit per call must not pay cudaMalloc/cudaFree (milliseconds each)
     for (int i = 0; i < 3; i++) HB_CHECK(ctx, cudaMallocAsync(&el.park[i], 4 * B * sizeof(F), ctx->stream));
     HB_CHECK(ctx, cudaMallocAsync(&el.tensor, 4 * B * sizeof(F), ctx->stream));
-    HB_CHECK(ctx, cudaMallocAsync(&el.msg, B * sizeof(F), ctx->stream));
+    HB_TRY(stager_init(ctx, el.stg, B));
     HB_CHECK(ctx, cudaMallocAsync(&el.leaves, (8 * B - 1) * 32, ctx->stream));
     HB_CHECK(ctx, cudaMemsetAsync(el.leaves, 0, 4 * B * 32, ctx->stream));   // Elastic_PC.cpp:195-199
     el.active = true;
@@ -574,15 +611,14 @@ extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) {
     if (!el.active) HB_FAIL(ctx, "hb_elastic_push: call hb_elastic_begin first");
     const size_t B = el.B;
     const F *src = (const F *)chunk;
-    if (!is_device_ptr(chunk)) {
-        HB_CHECK(ctx, cudaMemcpyAsync(el.msg, chunk, B * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
-        src = el.msg;
-    }
+    int stg_slot = -1;
+    if (!is_device_ptr(chunk)) HB_TRY(stager_push(ctx, el.stg, chunk, B, &src, &stg_slot));
     const unsigned slot = (unsigned)(el.chunk_idx % 4);
     F *T = slot == 3 ? el.tensor : el.park[slot];          // encode straight into the parking slot: no copy
     // The reference skips the encode of an all-zero chunk and zero-fills the tensor (Elastic_PC.cpp:206-222).  Both codes are
     // linear, so encoding the zero chunk yields exactly that all-zero tensor: no test, no host round trip, same bits.
     HB_TRY(tensorcode_dev(ctx, src, B, el.trs, el.lin, T, 1, nullptr));
+    if (stg_slot >= 0) HB_TRY(stager_consumed(ctx, el.stg, stg_slot));
     if (slot == 3) HB_TRY(md_leaves_stream4_dev(ctx, el.park[0], el.park[1], el.park[2], el.tensor, 4 * B, el.leaves));
     el.chunk_idx++;
     return 0;
@@ -632,11 +668,12 @@ extern "C" int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n) {
 extern "C" int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, const uint32_t *col, const uint32_t *row, size_t queries, size_t nchunks) {
     if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_open_begin: BUFFER_SPACE must be a power of two");
     ElasticOpen &eo = ctx->eo;
-    if (eo.active) { cudaFreeAsync(eo.buf, ctx->stream); eo = ElasticOpen(); }
+    if (eo.active) { cudaFreeAsync(eo.buf, ctx->stream); stager_free(ctx, eo.stg); eo = ElasticOpen(); }
     eo.B = B; eo.trs = trs; eo.lin = linear_time; eo.queries = queries; eo.nchunks = nchunks; eo.idx = 0;
-    size_t bytes = (B + 4 * B + B + queries * nchunks) * sizeof(F) + 2 * queries * sizeof(uint32_t);
+    size_t bytes = (B + 4 * B + queries * nchunks) * sizeof(F) + 2 * queries * sizeof(uint32_t);
     HB_CHECK(ctx, cudaMallocAsync(&eo.buf, bytes, ctx->stream));
-    eo.agg = (F *)eo.buf; eo.tensor = eo.agg + B; eo.msg = eo.tensor + 4 * B; eo.reply = eo.msg + B;
+    HB_TRY(stager_init(ctx, eo.stg, B));
+    eo.agg = (F *)eo.buf; eo.tensor = eo.agg + B; eo.reply = eo.tensor + 4 * B;
     eo.col = (uint32_t *)(eo.reply + queries * nchunks); eo.row = eo.col + queries;
     HB_CHECK(ctx, cudaMemsetAsync(eo.agg, 0, B * sizeof(F), ctx->stream));
     HB_CHECK(ctx, cudaMemsetAsync(eo.reply, 0, queries * nchunks * sizeof(F), ctx->stream));
@@ -650,11 +687,13 @@ extern "C" int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *
     if (!eo.active || eo.idx >= eo.nchunks) HB_FAIL(ctx, "hb_elastic_open_push: no open in progress / too many chunks");
     const size_t B = eo.B;
     const F *src = (const F *)chunk;
-    if (!is_device_ptr(chunk)) { HB_CHECK(ctx, cudaMemcpyAsync(eo.msg, chunk, B * sizeof(F), cudaMemcpyHostToDevice, ctx->stream)); src = eo.msg; }
+    int stg_slot = -1;
+    if (!is_device_ptr(chunk)) HB_TRY(stager_push(ctx, eo.stg, chunk, B, &src, &stg_slot));
     F beta = mkF(beta_i->real, beta_i->img);
     unsigned grid = (unsigned)std::min<size_t>((B + 255) / 256, (size_t)ctx->sm_count * 8);
     HB_LAUNCH(ctx, axpy_kernel, grid, 256, 0, eo.agg, src, beta, B);
     HB_TRY(tensorcode_dev(ctx, src, B, eo.trs, eo.lin, eo.tensor, 1, nullptr));
+    if (stg_slot >= 0) HB_TRY(stager_consumed(ctx, eo.stg, stg_slot));
     if (eo.queries) HB_LAUNCH(ctx, reply_gather_kernel, (unsigned)((eo.queries + 255) / 256), 256, 0, eo.tensor, 2 * B / eo.trs, eo.col, eo.row,
                               eo.queries, eo.nchunks, eo.idx, eo.reply);
     eo.idx++;
@@ -667,6 +706,7 @@ extern "C" int hb_elastic_open_finish(hb_ctx *ctx, hb_F *agg_out, hb_F *reply_ou
     if (eo.queries) HB_CHECK(ctx, cudaMemcpyAsync(reply_out, eo.reply, eo.queries * eo.nchunks * sizeof(F), cudaMemcpyDefault, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(eo.buf, ctx->stream);
+    stager_free(ctx, eo.stg);
     eo = ElasticOpen();
     return 0;
 }

@@ -44,13 +44,21 @@ struct ExpanderDev {
     int max_indeg = 0;
 };
 
+// Double-buffered staging of host chunks for the chunk-at-a-time calls (hb_elastic_push, hb_elastic_open_push): the H2D of chunk i runs on
+// the copy stream under the encode of chunk i-1, and the call returns only once the caller's buffer has been READ — a streaming
+// producer may refill a (pinned) chunk buffer as soon as the push returns.
+struct ChunkStager {
+    F *buf[2] = {nullptr, nullptr}; cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}; bool used[2] = {false, false};
+    size_t count = 0;
+};
+
 struct ElasticState {
     bool active = false;
     size_t B = 0; int trs = 0; int lin = 0;
     size_t chunk_idx = 0;
     F *park[3] = {nullptr, nullptr, nullptr};   // 3 parked encoded chunks (4B each), Elastic_PC.cpp:179-183
     F *tensor = nullptr;                        // current encoded chunk (4B)
-    F *msg = nullptr;                           // staging for a host chunk
+    ChunkStager stg;                            // staging for host chunks
     uint8_t *leaves = nullptr;                  // (2*4B-1)*32
     int *nz_flag = nullptr;
 };
@@ -58,7 +66,8 @@ struct ElasticState {
 struct ElasticOpen {
     bool active = false;
     size_t B = 0, queries = 0, nchunks = 0, idx = 0; int trs = 0, lin = 0;
-    void *buf = nullptr; F *agg = nullptr, *tensor = nullptr, *msg = nullptr, *reply = nullptr; uint32_t *col = nullptr, *row = nullptr;
+    void *buf = nullptr; F *agg = nullptr, *tensor = nullptr, *reply = nullptr; uint32_t *col = nullptr, *row = nullptr;
+    ChunkStager stg;
 };
 
 // one pass of the circuit evaluator's trace, resident in HBM (trace.cu)
@@ -89,7 +98,7 @@ struct hb_ctx {
     // resident tensor of the last commit_standard
     hb::F *tensor = nullptr; size_t tensor_elems = 0; size_t tensor_N = 0; int tensor_K = 0; int tensor_trs = 0;
     // device copy of the polynomial staged by the last commit_standard (open_standard's aggregate reads it again)
-    hb::F *poly = nullptr; size_t poly_elems = 0; const void *poly_host = nullptr;
+    hb::F *poly = nullptr; size_t poly_elems = 0; bool poly_valid = false;
     hb::ElasticState el;
     hb::ElasticOpen eo;
     hb::TraceState trace;

@@ -4,8 +4,7 @@
 // raw limb compare and any exact formula reproduces the reference bits.
 //
 // B200 notes: there is no 64-bit integer multiplier; mul.lo/mul.hi.u64 lower to IMAD.WIDE.U32 chains on the
-// FMA-heavy pipe, reductions (shift/and/add/select) go to the ALU pipe.  The code below keeps the number of
-// 64x64 products minimal (3 per F mul, Karatsuba) and reduces lazily (one fold per output limb).
+// FMA-heavy pipe, reductions (shift/and/add/select) go to the ALU pipe.  See the note above fmul.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -54,16 +53,46 @@ __host__ __device__ __forceinline__ F fneg(F a) { return mkF(a.re ? P61 - a.re :
 __host__ __device__ __forceinline__ bool feq(F a, F b) { return a.re == b.re && a.im == b.im; }
 __host__ __device__ __forceinline__ bool fzero(F a) { return (a.re | a.im) == 0; }
 
-// (a.re + i a.im)(b.re + i b.im): Karatsuba, 3 wide products (reference fieldElement.cpp:49-78)
-__device__ __forceinline__ F fmul(F a, F b) {
-    u64 ac = fold61(mul61_lazy(a.re, b.re));                       // <= p + 4
-    u64 bd = fold61(mul61_lazy(a.im, b.im));
-    u64 all = fold61(mul61_lazy(a.re + a.im, b.re + b.im));
-    // re = ac - bd ; im = all - ac - bd   (add multiples of p to stay non-negative)
-    u64 re = ac + (2 * P61 - bd);                                  // < 3p + 8
-    u64 im = all + (4 * P61 - ac - bd);                            // < 5p + 8
-    return mkF(canon61(fold61(re)), canon61(fold61(im)));
+// ---- F_{p^2} multiply for sm_100a ------------------------------------------------------------------------------------------------
+// B200 has no 64-bit multiplier: the only wide product is IMAD.WIDE.U32 (32x32 + 64-bit addend, FMA-heavy pipe, ~0.8-1 warp-inst/clk/SM),
+// everything else (shifts, masks, carries, selects) issues on the ALU pipe at 2 warp-inst/clk/SM.  The multiply is therefore written so
+// that nearly all additions ride on the free 64-bit addend of IMAD.WIDE: operands are split as x = x1*2^31 + x0 (x0 < 2^31, x1 <= 2^30),
+// and with 2^61 == 1 (mod p), i.e. 2^62 == 2,
+//     a*c + e*d  ==  (a0 c0 + e0 d0 + a1 (2 c1) + e1 (2 d1))  +  2^31 * (a1 c0 + a0 c1 + e1 d0 + e0 d1)          (mod p)
+// The middle sum M < 2^63 is one chain of four IMAD.WIDE; 2^31 M == (M mod 2^30) 2^31 + (M >> 30) is one more IMAD.WIDE whose addend
+// is the shifted-out part; the outer sum is a second chain of four that starts from it and stays below 2^64.  One fold (4 ALU ops)
+// gives a value <= p + 7.  Both limbs of a product are such dot products: re = a.re b.re + a.im (p - b.im), im = a.re b.im + a.im b.re:
+// 18 IMAD.WIDE + ~37 ALU instructions per canonical product, against 12 + ~80 for Karatsuba on 64x64 products (tools/ubench_fmul.cu).
+__device__ __forceinline__ u64 madwide(uint32_t a, uint32_t b, u64 c) { u64 d; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mulwide(uint32_t a, uint32_t b) { u64 d; asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b)); return d; }
+
+// a right-hand operand prepared once and reused (a sumcheck challenge, a twiddle): limbs of re, im and p - im, high limbs also doubled
+struct FN { uint32_t r0, r1, r1d, i0, i1, i1d, n0, n1, n1d; };
+__device__ __forceinline__ FN fprep(F b) {                       // b canonical
+    FN q; const u64 n = P61 - b.im;                              // == -b.im (mod p), in [1, p]
+    q.r0 = (uint32_t)b.re & 0x7fffffffu; q.r1 = (uint32_t)(b.re >> 31); q.r1d = q.r1 << 1;
+    q.i0 = (uint32_t)b.im & 0x7fffffffu; q.i1 = (uint32_t)(b.im >> 31); q.i1d = q.i1 << 1;
+    q.n0 = (uint32_t)n & 0x7fffffffu;    q.n1 = (uint32_t)(n >> 31);    q.n1d = q.n1 << 1;
+    return q;
 }
+// (a*c + e*d) mod p, result <= p + 7.  a, e given as (x0, x1) limbs of values <= p + 7; c, d as (y0, y1, 2 y1) of values <= p.
+__device__ __forceinline__ u64 dot61_lazy(uint32_t a0, uint32_t a1, uint32_t e0, uint32_t e1,
+                                          uint32_t c0, uint32_t c1, uint32_t c1d, uint32_t d0, uint32_t d1, uint32_t d1d) {
+    const u64 mid = madwide(e0, d1, madwide(e1, d0, madwide(a0, c1, mulwide(a1, c0))));                 // < 2^63
+    const u64 u = madwide((uint32_t)mid & 0x3fffffffu, 0x80000000u, mid >> 30);                         // == 2^31 mid, < 2^61 + 2^33
+    const u64 t = madwide(e1, d1d, madwide(a1, c1d, madwide(e0, d0, madwide(a0, c0, u))));              // < 2^64
+    return (t & P61) + (t >> 61);
+}
+// a (limbs <= p + 7, e.g. a previous lazy product) times a prepared operand; limbs of the result <= p + 7, NOT canonical
+__device__ __forceinline__ F fmul_n_lazy(F a, const FN &b) {
+    const uint32_t x0 = (uint32_t)a.re & 0x7fffffffu, x1 = (uint32_t)(a.re >> 31), y0 = (uint32_t)a.im & 0x7fffffffu, y1 = (uint32_t)(a.im >> 31);
+    return mkF(dot61_lazy(x0, x1, y0, y1, b.r0, b.r1, b.r1d, b.n0, b.n1, b.n1d),
+               dot61_lazy(x0, x1, y0, y1, b.i0, b.i1, b.i1d, b.r0, b.r1, b.r1d));
+}
+__device__ __forceinline__ F fcanon(F a) { return mkF(canon61(a.re), canon61(a.im)); }
+__device__ __forceinline__ F fmul_n(F a, const FN &b) { return fcanon(fmul_n_lazy(a, b)); }
+// canonical in, canonical out (reference fieldElement.cpp:49-78 computes the same value)
+__device__ __forceinline__ F fmul(F a, F b) { return fmul_n(a, fprep(b)); }
 // a * real scalar s (s canonical)
 __device__ __forceinline__ F fmul_real(F a, u64 s) { return mkF(mul61(a.re, s), mul61(a.im, s)); }
 

@@ -16,6 +16,8 @@ size_t BUFFER_SPACE = 0;
 bool linear_time = false;
 bool materialize_tensor = false;
 bool commit_levels_on_host = true;
+bool open_reuses_committed_poly = false;
+static size_t committed_poly_size = 0;
 
 static hb_ctx *g_ctx = nullptr;
 [[noreturn]] static void die(const char *what) {
@@ -153,6 +155,7 @@ void commit_standard(std::vector<F> &poly, _hash &, std::vector<std::vector<_has
     if (materialize_tensor) tflat.resize(4 * poly.size());
     CK(hb_commit_standard(backend(), (const hb_F *)poly.data(), poly.size(), K, tensor_row_size, linear_time ? 1 : 0, (uint8_t *)dlev,
                           materialize_tensor ? (hb_F *)tflat.data() : nullptr));
+    committed_poly_size = poly.size();
     MT_hashes.clear();
     size_t loff = 0;
     for (size_t n = (size_t)B;; n /= 2) {
@@ -181,7 +184,10 @@ open_front open_standard_front(std::vector<F> &poly, std::vector<F> x, std::vect
     precompute_beta(x1, o.beta);
     o.r_v0 = generate_randomness(1)[0];                                         // :625 (the powers r_v are unused downstream)
     o.aggr_vector.resize(BUFFER_SPACE);
-    CK(hb_aggregate(backend(), (const hb_F *)poly.data(), poly.size(), K, (const hb_F *)o.beta.data(), (hb_F *)o.aggr_vector.data()));
+    // the device copy the last commit_standard staged is used only when the caller says so (hobbit::open_reuses_committed_poly):
+    // identity is never inferred from the vector's address
+    const bool reuse = open_reuses_committed_poly && committed_poly_size == poly.size();
+    CK(hb_aggregate(backend(), reuse ? nullptr : (const hb_F *)poly.data(), poly.size(), K, (const hb_F *)o.beta.data(), (hb_F *)o.aggr_vector.data()));
     o.I.resize(queries);
     std::vector<uint32_t> col(queries), row(queries);
     for (int i = 0; i < queries; i++) {                                         // :633-638, two rand() per query in this order

@@ -103,6 +103,10 @@ extern bool materialize_tensor;
 // false: Elastic_PC commit() sizes every MT_hashes level as the reference does but only FILLS the levels of <= 1024 digests (root included);
 // the big levels stay in HBM.  The prover (open()) only uses the level sizes; a caller that hands the tree to a verifier keeps the default.
 extern bool commit_levels_on_host;
+// true: open_standard aggregates from the device copy of the polynomial that the LAST commit_standard staged instead of uploading
+// `poly` again — the caller asserts that `poly` still is that polynomial, unmodified.  Default false: the library never infers the
+// identity of a host buffer from its address.
+extern bool open_reuses_committed_poly;
 void commit_standard(std::vector<F> &poly, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes,
                      std::vector<std::vector<std::vector<F>>> &_tensor, int K);
 // The data-parallel front half of open_standard (Our_PC.cpp:604-660): beta = eq(x1), aggregate, the rand()-drawn
