@@ -17,7 +17,8 @@ class HobbitError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libhobbit_b200.so")
+    # HOBBIT_B200_LIB: development override (kernel variants built side by side); the product library is the in-tree one
+    return os.environ.get("HOBBIT_B200_LIB") or os.path.join(_HERE, "libhobbit_b200.so")
 
 
 def load_library():

@@ -25,7 +25,20 @@ __host__ __device__ __forceinline__ u64 fold61(u64 x) { return (x & P61) + (x >>
 __host__ __device__ __forceinline__ u64 canon61(u64 x) { return x >= P61 ? x - P61 : x; }
 
 __host__ __device__ __forceinline__ u64 add61(u64 a, u64 b) { return canon61(a + b); }
-__host__ __device__ __forceinline__ u64 sub61(u64 a, u64 b) { u64 d = a - b; return (a < b) ? d + P61 : d; }
+__host__ __device__ __forceinline__ u64 sub61(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    // a - b, plus p when it borrowed: the borrow becomes an all-ones mask, p & mask is added with one carry chain (6 instructions)
+    uint32_t lo, hi, m;
+    asm("{\n\t.reg .u32 al, ah, bl, bh;\n\tmov.b64 {al, ah}, %3;\n\tmov.b64 {bl, bh}, %4;\n\t"
+        "sub.cc.u32 %0, al, bl;\n\tsubc.cc.u32 %1, ah, bh;\n\tsubc.u32 %2, 0, 0;\n\t}"
+        : "=r"(lo), "=r"(hi), "=r"(m) : "l"(a), "l"(b));
+    uint32_t rl, rh;
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(rl), "=r"(rh) : "r"(lo), "r"(hi), "r"(m), "r"(m & 0x1fffffffu));
+    return ((u64)rh << 32) | rl;
+#else
+    u64 d = a - b; return (a < b) ? d + P61 : d;
+#endif
+}
 
 // 64x64 -> 128 product, folded with 2^61 == 1: returns a value congruent to a*b, < 2^63 + 2^61 for a,b < 2^62.
 __device__ __forceinline__ u64 mul61_lazy(u64 a, u64 b) {
@@ -69,10 +82,11 @@ __device__ __forceinline__ u64 mulwide(uint32_t a, uint32_t b) { u64 d; asm("mul
 // a right-hand operand prepared once and reused (a sumcheck challenge, a twiddle): limbs of re, im and p - im, high limbs also doubled
 struct FN { uint32_t r0, r1, r1d, i0, i1, i1d, n0, n1, n1d; };
 __device__ __forceinline__ FN fprep(F b) {                       // b canonical
-    FN q; const u64 n = P61 - b.im;                              // == -b.im (mod p), in [1, p]
+    FN q;
     q.r0 = (uint32_t)b.re & 0x7fffffffu; q.r1 = (uint32_t)(b.re >> 31); q.r1d = q.r1 << 1;
     q.i0 = (uint32_t)b.im & 0x7fffffffu; q.i1 = (uint32_t)(b.im >> 31); q.i1d = q.i1 << 1;
-    q.n0 = (uint32_t)n & 0x7fffffffu;    q.n1 = (uint32_t)(n >> 31);    q.n1d = q.n1 << 1;
+    // p - b.im == -b.im (mod p), in [1, p]: the limbs of p are all ones (2^30 - 1 and 2^31 - 1), so the subtraction never borrows
+    q.n0 = q.i0 ^ 0x7fffffffu; q.n1 = q.i1 ^ 0x3fffffffu; q.n1d = q.i1d ^ 0x7ffffffeu;
     return q;
 }
 // (a*c + e*d) mod p, result <= p + 7.  a, e given as (x0, x1) limbs of values <= p + 7; c, d as (y0, y1, 2 y1) of values <= p.
@@ -93,6 +107,10 @@ __device__ __forceinline__ F fcanon(F a) { return mkF(canon61(a.re), canon61(a.i
 __device__ __forceinline__ F fmul_n(F a, const FN &b) { return fcanon(fmul_n_lazy(a, b)); }
 // canonical in, canonical out (reference fieldElement.cpp:49-78 computes the same value)
 __device__ __forceinline__ F fmul(F a, F b) { return fmul_n(a, fprep(b)); }
+// lazy helpers for accumulation loops: limbs stay below 2^64, one fold per few additions
+__device__ __forceinline__ F lfold(F a) { return mkF(fold61(a.re), fold61(a.im)); }                       // any u64 limbs -> limbs <= p + 7
+__device__ __forceinline__ void lacc(F &acc, F v) { acc.re += v.re; acc.im += v.im; }                       // caller keeps the sum below 2^64
+__device__ __forceinline__ F fcanon2(F a) { return fcanon(lfold(a)); }                                      // limbs < 2^62 -> canonical
 // a * real scalar s (s canonical)
 __device__ __forceinline__ F fmul_real(F a, u64 s) { return mkF(mul61(a.re, s), mul61(a.im, s)); }
 

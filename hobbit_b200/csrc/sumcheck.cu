@@ -25,25 +25,35 @@ enum { POLY_ONLY = 0, FOLD_THEN_POLY = 1, POLY_AND_FOLD = 2, FOLD_ONLY = 3 };
 template <int NT> struct Tabs { const F *in[NT]; F *out[NT]; };
 
 __device__ __forceinline__ F fold1(F x, F y, F r) { return fadd(x, fmul(r, fsub(y, x))); }
+// the same against a prepared challenge: x + r (y - x), canonical; d = y - x is handed back for the round polynomial
+__device__ __forceinline__ F fold1n(F x, F d, const FN &rn) {
+    const F t = fmul_n_lazy(d, rn);                                  // limbs <= p + 7
+    return fcanon2(mkF(x.re + t.re, x.im + t.im));                   // < 2p + 7 < 2^62
+}
 
 // Round polynomial prod_t (x_t + X (y_t - x_t)) accumulated in EVALUATION form — fewer multiplications than its coefficients:
-//   NT = 2: acc = { P(inf) = d1 d2, P(1) = y1 y2, P(0) = x1 x2 }                                  (3 instead of 4)
-//   NT = 3: acc = { P(inf) = d1 d2 d3, P(1) = y1 y2 y3, P(-1) = (2x1-y1)(2x2-y2)(2x3-y3), P(0) }    (8 instead of 10)
+//   NT = 2: acc = { P(inf) = d1 d2, P(1) = y1 y2, P(0) = x1 x2 }                                  (3 multiplications instead of 4)
+//   NT = 3: acc = { P(inf) = d1 d2 d3, P(1) = y1 y2 y3, P(-1) = (2x1-y1)(2x2-y2)(2x3-y3), P(0) }    (7 instead of 10: the pair products
+//           A = x1 x2, B = y1 y2, C = d1 d2 give (2x1-y1)(2x2-y2) = 2A + 2C - B for free)
 // The sums over all pairs are linear in these, so the coefficients (a, b, c[, d]) the reference accumulates directly are recovered
 // exactly on the host from the reduced sums (coeffs_from_evals); all arithmetic is exact in F_p^2, so the bits are the same.
-template <int NT> __device__ __forceinline__ void poly_acc(F (&acc)[NT + 1], const F (&x)[NT], const F (&y)[NT]) {
+// Products are LAZY (limbs <= p + 7, fmul_n_lazy) and so are the accumulators (raw 64-bit sums, the caller folds them every few pairs):
+// the FMA-heavy pipe (IMAD.WIDE) is the binding unit of this kernel and canonicalising intermediates would only add ALU work.
+template <int NT> __device__ __forceinline__ void poly_acc(F (&acc)[NT + 1], const F (&x)[NT], const F (&y)[NT], const F (&d)[NT]) {
     if (NT == 2) {
-        F d1 = fsub(y[0], x[0]), d2 = fsub(y[1], x[1]);
-        acc[0] = fadd(acc[0], fmul(d1, d2));
-        acc[1] = fadd(acc[1], fmul(y[0], y[1]));
-        acc[2] = fadd(acc[2], fmul(x[0], x[1]));
+        lacc(acc[0], fmul_n_lazy(d[0], fprep(d[1])));
+        lacc(acc[1], fmul_n_lazy(y[0], fprep(y[1])));
+        lacc(acc[2], fmul_n_lazy(x[0], fprep(x[1])));
     } else if (NT == 3) {
-        F d1 = fsub(y[0], x[0]), d2 = fsub(y[1], x[1]), d3 = fsub(y[2], x[2]);
-        F m1 = fsub(x[0], d1), m2 = fsub(x[1], d2), m3 = fsub(x[2], d3);
-        acc[0] = fadd(acc[0], fmul(fmul(d1, d2), d3));
-        acc[1] = fadd(acc[1], fmul(fmul(y[0], y[1]), y[2]));
-        acc[2] = fadd(acc[2], fmul(fmul(m1, m2), m3));
-        acc[3] = fadd(acc[3], fmul(fmul(x[0], x[1]), x[2]));
+        const F A = fmul_n_lazy(x[0], fprep(x[1])), B = fmul_n_lazy(y[0], fprep(y[1])), C = fmul_n_lazy(d[0], fprep(d[1]));
+        // M = 2A + 2C - B: 2 (A + C) <= 4p + 28, + (2p - B) stays below 2^64; one fold -> limbs <= p + 7
+        const F M = lfold(mkF(2 * (A.re + C.re) + (2 * P61 - B.re), 2 * (A.im + C.im) + (2 * P61 - B.im)));
+        // m3 = 2 x3 - y3 (canonical: it is a right-hand operand)
+        const F m3 = fcanon2(mkF(2 * x[2].re + (P61 - y[2].re), 2 * x[2].im + (P61 - y[2].im)));
+        lacc(acc[0], fmul_n_lazy(C, fprep(d[2])));
+        lacc(acc[1], fmul_n_lazy(B, fprep(y[2])));
+        lacc(acc[2], fmul_n_lazy(M, fprep(m3)));
+        lacc(acc[3], fmul_n_lazy(A, fprep(x[2])));
     }
 }
 // host side: evaluation sums -> coefficients, highest degree first (1/2 = 2^60 mod p)
@@ -59,22 +69,32 @@ template <int NT> static inline void coeffs_from_evals(F *co) {
 
 // INTERLEAVED: tables 0 and 1 are the even/odd entries of one array t.in[0] (product-tree layer: in1[j]=prev[2j],
 // in2[j]=prev[2j+1], sumcheck.cpp:84-101), so the layer is consumed in place without materialising in1/in2.
+#ifndef HB_SC_MINB
+#define HB_SC_MINB 2
+#endif
+#ifndef HB_SC_THREADS
+#define HB_SC_THREADS 256
+#endif
+// (A variant that kept the next iterations' table entries in flight with cp.async into thread-private shared-memory slots was measured
+// and was 4 % slower: with both integer pipes ~60 % busy the kernel is not waiting on HBM, see profiles/r02_summary.md.)
 template <int NT, int MODE, bool INTERLEAVED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(HB_SC_THREADS, HB_SC_MINB)
 sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
     constexpr int NC = NT + 1;
     F acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[c] = mkF(0, 0);
+    const FN rn = fprep(r);
+    unsigned it = 0;
 
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
-        F x[NT], y[NT];
+        F x[NT], y[NT], d[NT];
         if (MODE == FOLD_THEN_POLY) {
 #pragma unroll
             for (int k = 0; k < NT; k++) {
                 const F *p = t.in[k] + 4 * j;
-                F a = p[0], b = p[1], c = p[2], d = p[3];
-                x[k] = fold1(a, b, r); y[k] = fold1(c, d, r);
+                const F a = p[0], b = p[1], c = p[2], e = p[3];
+                x[k] = fold1n(a, fsub(b, a), rn); y[k] = fold1n(c, fsub(e, c), rn);
                 t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y[k];
             }
         } else if (INTERLEAVED) {
@@ -86,13 +106,23 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__
 #pragma unroll
             for (int k = 0; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
         }
-        if (MODE != FOLD_ONLY) poly_acc<NT>(acc, x, y);
+#pragma unroll
+        for (int k = 0; k < NT; k++) d[k] = fsub(y[k], x[k]);
+        if (MODE != FOLD_ONLY) {
+            poly_acc<NT>(acc, x, y, d);
+            if ((++it & 3) == 0) {                                   // raw 64-bit sums: at most 4 lazy terms on top of a folded value
+#pragma unroll
+                for (int c = 0; c < NC; c++) acc[c] = lfold(acc[c]);
+            }
+        }
         if (MODE == POLY_AND_FOLD || MODE == FOLD_ONLY) {
 #pragma unroll
-            for (int k = 0; k < NT; k++) t.out[k][j] = fold1(x[k], y[k], r);
+            for (int k = 0; k < NT; k++) t.out[k][j] = fold1n(x[k], d[k], rn);
         }
     }
     if (MODE == FOLD_ONLY) return;
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = fcanon2(lfold(acc[c]));
 
     grid_reduce<NC>(acc, partial, ticket, result);
 }
@@ -492,7 +522,8 @@ static inline unsigned grid_for(hb_ctx *ctx, size_t L) {
 template <int NT, int MODE, bool IL>
 static int launch_round(hb_ctx *ctx, const Tabs<NT> &t, size_t L, F r, F *coeffs_host /* NT+1, may be null for FOLD_ONLY */) {
     HB_TRY(ensure_scratch(ctx));
-    HB_LAUNCH(ctx, (sc_round_kernel<NT, MODE, IL>), grid_for(ctx, L), 256, 0, t, L, r, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    const size_t want = (L + HB_SC_THREADS - 1) / HB_SC_THREADS, cap = std::min<size_t>((size_t)ctx->sm_count * (1024 / HB_SC_THREADS), kMaxRedBlocks);
+    HB_LAUNCH(ctx, (sc_round_kernel<NT, MODE, IL>), (unsigned)std::max<size_t>(1, std::min(want, cap)), HB_SC_THREADS, 0, t, L, r, ctx->red, ctx->ticket, ctx->mailbox_dev);
     if (MODE != FOLD_ONLY) { HB_TRY(read_result(ctx, NT + 1, coeffs_host)); coeffs_from_evals<NT>(coeffs_host); }
     return 0;
 }
