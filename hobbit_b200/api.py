@@ -389,6 +389,56 @@ class Context:
         self._ck(self.lib.hb_elastic_open_finish(self.h, _ptr(agg), _ptr(reply)))
         return agg, reply.reshape(len(col), len(chunks), 2)
 
+    # ---- multi-GPU (include/hobbit_b200.h "multi-GPU"): one process per GPU ----
+    def dist_local_info(self, data_bytes):
+        blob = np.zeros(256, dtype=np.uint8)
+        self._ck(self.lib.hb_dist_local_info(self.h, c_sz(int(data_bytes)), _ptr(blob)))
+        return blob
+
+    def dist_connect(self, rank, world, blobs):
+        blobs = np.ascontiguousarray(np.asarray(blobs, dtype=np.uint8).reshape(world, 256))
+        self._ck(self.lib.hb_dist_connect(self.h, int(rank), int(world), _ptr(blobs)))
+
+    def dist_init_torch(self, data_bytes, group=None):
+        """Bootstrap through an initialised torch.distributed process group (any backend): all-gathers the 256-byte window blobs."""
+        import torch
+        import torch.distributed as dist
+        blob = self.dist_local_info(data_bytes)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = torch.from_numpy(blob).to(dev)
+        allb = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine, group=group)
+        self.dist_connect(rank, world, np.stack([b.cpu().numpy() for b in allb]))
+        dist.barrier(group)
+
+    def dist_disconnect(self):
+        self._ck(self.lib.hb_dist_disconnect(self.h))
+
+    def dist_barrier(self):
+        self._ck(self.lib.hb_dist_barrier(self.h))
+
+    def dist_shard(self, on=True):
+        self._ck(self.lib.hb_dist_shard(self.h, 1 if on else 0))
+
+    def dist_allreduce(self, vec):
+        v = _F(vec).copy()
+        self._ck(self.lib.hb_dist_allreduce(self.h, _ptr(v), c_sz(len(v))))
+        return v
+
+    def dist_commit_standard(self, poly_local, K_total, B, trs, lin, levels_out=None):
+        """poly_local: this rank's K_total/world consecutive chunks (numpy F array, DevF or raw device pointer)."""
+        lv = np.zeros((2 * B - 1, 32), dtype=np.uint8) if levels_out is None else levels_out
+        src = poly_local if isinstance(poly_local, (int, DevF)) else _F(poly_local)
+        self._ck(self.lib.hb_dist_commit_standard(self.h, _ptr(src), c_sz(K_total), c_sz(B), int(trs), int(lin), _ptr(lv)))
+        return lv
+
+    def dist_elastic_commit(self, chunks_local, groups_total, B, trs, lin, levels_out=None):
+        lv = np.zeros((8 * B - 1, 32), dtype=np.uint8) if levels_out is None else levels_out
+        src = chunks_local if isinstance(chunks_local, (int, DevF)) else _F(chunks_local)
+        self._ck(self.lib.hb_dist_elastic_commit(self.h, _ptr(src), c_sz(groups_total), c_sz(B), int(trs), int(lin), _ptr(lv)))
+        return lv
+
     def sc3_round(self, ins, outs, L, rand):
         """ins/outs: 3 int device pointers each; returns the 4 cubic coefficients (4,2) of this slice."""
         r, co = _F(rand), np.zeros((4, 2), dtype=np.uint64)

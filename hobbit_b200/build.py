@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhobbit_b200.so")
-SOURCES = ["ntt.cu", "encode.cu", "merkle.cu", "commit.cu", "sumcheck.cu", "open.cu", "trace.cu"]
+SOURCES = ["ntt.cu", "encode.cu", "merkle.cu", "commit.cu", "sumcheck.cu", "open.cu", "trace.cu", "dist.cu"]
 HEADERS = ["common.cuh", "field.cuh", "blake3.cuh", "reduce.cuh", os.path.join("..", "..", "include", "hobbit_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

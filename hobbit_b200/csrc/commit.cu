@@ -238,6 +238,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
     elastic_free(ctx);
+    dist_release(ctx);
     for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto &e : ctx->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -423,14 +424,10 @@ extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K
 }
 
 // ---- C1, sharded form: the chunk-independent part and the chunk-ordered chain as two calls -----------------------
-extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out,
-                                       size_t leaf_parts, size_t first_chunk, size_t total_chunks) {
-    if (nchunks == 0) return 0;
-    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_commit_encode_chunks: chunk size must be a power of two");
-    if (trs < 2 || (2 * trs) % 4) HB_FAIL(ctx, "hb_commit_encode_chunks: tensor_row_size must be even");
-    if (leaf_parts == 0) leaf_parts = 1;
-    if (total_chunks == 0) { total_chunks = nchunks; first_chunk = 0; }
-    if (B % leaf_parts || first_chunk + nchunks > total_chunks) HB_FAIL(ctx, "hb_commit_encode_chunks: bad leaf_parts / chunk range");
+// shared by hb_commit_encode_chunks and the fused multi-GPU commit (dist.cu): `inner_dev` device memory (or, with lay0.peer set, the base of
+// this rank's own receive array); lay0.chunk0 = index of the first chunk of this call in the digest layout
+int hb::commit_encode_chunks_impl(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_dev,
+                                  InnerLayout lay0, size_t first_chunk, size_t total_chunks) {
     // the resident tensor covers ALL of this rank's chunks (total_chunks); this call fills [first_chunk, first_chunk + nchunks)
     const size_t Nt = total_chunks * B;
     if (ctx->tensor_elems != 4 * Nt) {
@@ -441,8 +438,6 @@ extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nch
     }
     ctx->tensor_N = Nt; ctx->tensor_K = (int)total_chunks; ctx->tensor_trs = trs;
     const size_t N = nchunks * B;
-    Staged in(ctx);
-    HB_TRY(in.outbuf(inner_out, N * 32));
     const bool on_dev = is_device_ptr(poly);
     // groups bound the size of one launch (grid.y).  Host input: groups of 2 chunks, every group's H2D queued on the copy stream up
     // front so that the copy of group g+1 runs under the encode of group g (as in hb_commit).
@@ -451,6 +446,7 @@ extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nch
     F *stage = nullptr;
     std::vector<cudaEvent_t> ev(on_dev ? 0 : ngroups);
     if (!on_dev) {
+        const bool pinned = is_pinned_host_ptr(poly);
         HB_CHECK(ctx, cudaMallocAsync(&stage, N * sizeof(F), ctx->stream));
         cudaEvent_t start;
         HB_CHECK(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
@@ -460,7 +456,8 @@ extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nch
         for (size_t g = 0; g < ngroups; g++) {
             size_t c0 = g * G, nc = std::min(G, nchunks - c0);
             HB_CHECK(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
-            HB_CHECK(ctx, cudaMemcpyAsync(stage + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (!pinned && nc * B * sizeof(F) >= kPageableDirect) { HB_TRY(copy_from_host(ctx, stage + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), ctx->copy_stream)); }
+            else HB_CHECK(ctx, cudaMemcpyAsync(stage + c0 * B, (const F *)poly + c0 * B, nc * B * sizeof(F), cudaMemcpyHostToDevice, ctx->copy_stream));
             HB_CHECK(ctx, cudaEventRecord(ev[g], ctx->copy_stream));
         }
     }
@@ -469,31 +466,36 @@ extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nch
     for (size_t g = 0; g < ngroups && !rc; g++) {
         size_t c0 = g * G, nc = std::min(G, nchunks - c0);
         if (!on_dev) HB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ev[g], 0));
-        InnerLayout lay; lay.part_leaves = B / leaf_parts; lay.chunks_total = nchunks; lay.chunk0 = c0;
-        rc = tensorcode_dev(ctx, src + c0 * B, B, trs, linear_time, ctx->tensor + (first_chunk + c0) * 4 * B, nc, in.as<uint8_t>(), lay);
+        InnerLayout lay = lay0; lay.chunk0 = lay0.chunk0 + c0;
+        rc = tensorcode_dev(ctx, src + c0 * B, B, trs, linear_time, ctx->tensor + (first_chunk + c0) * 4 * B, nc, inner_dev, lay);
     }
     if (!on_dev) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaFreeAsync(stage, ctx->stream);
         for (auto &e : ev) cudaEventDestroy(e);
     }
-    if (rc) return rc;
+    return rc;
+}
+
+extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out,
+                                       size_t leaf_parts, size_t first_chunk, size_t total_chunks) {
+    if (nchunks == 0) return 0;
+    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_commit_encode_chunks: chunk size must be a power of two");
+    if (leaf_parts == 0) leaf_parts = 1;
+    if (total_chunks == 0) { total_chunks = nchunks; first_chunk = 0; }
+    if (B % leaf_parts || first_chunk + nchunks > total_chunks) HB_FAIL(ctx, "hb_commit_encode_chunks: bad leaf_parts / chunk range");
+    Staged in(ctx);
+    HB_TRY(in.outbuf(inner_out, nchunks * B * 32));
+    InnerLayout lay; lay.part_leaves = B / leaf_parts; lay.chunks_total = nchunks; lay.chunk0 = 0;
+    HB_TRY(commit_encode_chunks_impl(ctx, poly, nchunks, B, trs, linear_time, in.as<uint8_t>(), lay, first_chunk, total_chunks));
     HB_TRY(in.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
 // Elastic_PC commit split for sharding: `ngroups` groups of 4 consecutive chunks -> inner digests of the 4B positions of each group
-extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t ngroups, size_t B, int trs, int linear_time, uint8_t *inner_out,
-                                        size_t leaf_parts, size_t first_group, size_t total_groups) {
-    if (ngroups == 0) return 0;
-    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_encode_groups: BUFFER_SPACE must be a power of two");
-    if (leaf_parts == 0) leaf_parts = 1;
-    if (total_groups == 0) { total_groups = ngroups; first_group = 0; }
+int hb::elastic_encode_groups_impl(hb_ctx *ctx, const hb_F *chunks, size_t ngroups, size_t B, int trs, int linear_time, uint8_t *inner_dev, InnerLayout lay0) {
     const size_t cells = 4 * B;
-    if (cells % leaf_parts || first_group + ngroups > total_groups) HB_FAIL(ctx, "hb_elastic_encode_groups: bad leaf_parts / group range");
-    Staged in(ctx);
-    HB_TRY(in.outbuf(inner_out, ngroups * cells * 32));
     // a launch covers up to 1 GiB of encoded tensors (64 B per coefficient)
     size_t G = std::max<size_t>(1, std::min<size_t>(ngroups, ((size_t)1 << 30) / (16 * B * sizeof(F))));
     if (const char *cap = getenv("HB_ELASTIC_GROUPS_PER_LAUNCH")) G = std::max<size_t>(1, std::min<size_t>(G, (size_t)atoll(cap)));   // tests: force several launches
@@ -529,8 +531,8 @@ extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t 
         }
         int rc = tensorcode_dev(ctx, src, B, trs, linear_time, T4, 4 * ng, nullptr);
         if (!on_dev) HB_CHECK(ctx, cudaEventRecord(freed[q], ctx->stream));              // stage[q] may be overwritten once this encode has read it
-        InnerLayout lay; lay.part_leaves = cells / leaf_parts; lay.chunks_total = ngroups; lay.chunk0 = g0;
-        if (!rc) rc = md_inner_stream4_dev(ctx, T4, cells, ng, in.as<uint8_t>(), lay);
+        InnerLayout lay = lay0; lay.chunk0 = lay0.chunk0 + g0;
+        if (!rc) rc = md_inner_stream4_dev(ctx, T4, cells, ng, inner_dev, lay);
         if (rc) { cudaFreeAsync(T4, ctx->stream); return rc; }
     }
     if (!on_dev) {
@@ -538,6 +540,21 @@ extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t 
         for (int q = 0; q < 2; q++) { cudaFreeAsync(stage[q], ctx->stream); cudaEventDestroy(copied[q]); cudaEventDestroy(freed[q]); }
     }
     cudaFreeAsync(T4, ctx->stream);
+    return 0;
+}
+
+extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t ngroups, size_t B, int trs, int linear_time, uint8_t *inner_out,
+                                        size_t leaf_parts, size_t first_group, size_t total_groups) {
+    if (ngroups == 0) return 0;
+    if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_encode_groups: BUFFER_SPACE must be a power of two");
+    if (leaf_parts == 0) leaf_parts = 1;
+    if (total_groups == 0) { total_groups = ngroups; first_group = 0; }
+    const size_t cells = 4 * B;
+    if (cells % leaf_parts || first_group + ngroups > total_groups) HB_FAIL(ctx, "hb_elastic_encode_groups: bad leaf_parts / group range");
+    Staged in(ctx);
+    HB_TRY(in.outbuf(inner_out, ngroups * cells * 32));
+    InnerLayout lay; lay.part_leaves = cells / leaf_parts; lay.chunks_total = ngroups; lay.chunk0 = 0;
+    HB_TRY(elastic_encode_groups_impl(ctx, chunks, ngroups, B, trs, linear_time, in.as<uint8_t>(), lay));
     HB_TRY(in.finish());
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -12,6 +12,7 @@
 
 namespace hb {
 
+static constexpr int kMaxRanks = 8;     // GPUs of one NVSwitch box
 static constexpr int kSMs = 148;        // B200: 2 dies x 74 SMs; grids for grid-stride kernels are multiples of this
 
 struct EncStage {                       // one sparse mat-vec of the expander encode: out[0..R) = G * in[0..L)
@@ -26,11 +27,39 @@ struct InnerLayout {
     size_t part_leaves = 0;      // leaves per part (0 = unset)
     size_t chunks_total = 0;     // chunks in the whole call
     size_t chunk0 = 0;           // index of this launch's first chunk inside the call
+    // Fused exchange (dist.cu): peer[h] != nullptr -> the digests of leaf part h are stored straight into rank h's receive array
+    // [global chunk][leaf inside the part] through its NVLink-mapped window; chunk0 then counts GLOBAL chunks.
+    uint8_t *peer[kMaxRanks] = {};
     __host__ __device__ size_t offset(size_t chunk_in_launch, size_t p) const {
         size_t part = p / part_leaves, off = p - part * part_leaves;
         return (part * chunks_total + chunk0 + chunk_in_launch) * part_leaves + off;
     }
+    __device__ __forceinline__ uint8_t *addr(uint8_t *base, size_t chunk_in_launch, size_t p) const {
+        size_t part = p / part_leaves, off = p - part * part_leaves;
+        if (peer[0]) return peer[part] + ((chunk0 + chunk_in_launch) * part_leaves + off) * 32;
+        return base + ((part * chunks_total + chunk0 + chunk_in_launch) * part_leaves + off) * 32;
+    }
     static InnerLayout plain(size_t leaves, size_t chunks) { InnerLayout l; l.part_leaves = leaves; l.chunks_total = chunks; l.chunk0 = 0; return l; }
+};
+
+// Multi-GPU state (dist.cu): one process per GPU; every rank owns a WINDOW of device memory that all ranks of the box map through CUDA IPC
+// (NVLink peer stores).  Control region (first kDistCtrlBytes): reduction mail slots, barrier flags, small-exchange slots; the rest is
+// the data region the sharded commitments exchange digests and tree levels through.
+static constexpr size_t kDistCtrlBytes = 64 << 10;
+static constexpr size_t kDistMailOff = 0;            // [2 parities][8 ranks][32 F]: per-round sums of the sharded sumchecks
+static constexpr size_t kDistBarOff = 16 << 10;      // [8] u64 epochs
+static constexpr size_t kDistXchgOff = 24 << 10;     // [2 parities][8 ranks][64 F]: small all-gathers (table heads)
+static constexpr size_t kDistErrOff = 60 << 10;      // u64: set when a peer wait timed out
+struct DistState {
+    int world = 1, rank = 0;
+    uint8_t *win = nullptr; size_t win_bytes = 0;    // my window (cudaMalloc, IPC-exported)
+    uint8_t *peer[kMaxRanks] = {};                   // every rank's window as mapped here (peer[rank] == win)
+    unsigned long long epoch = 0;                    // barrier epochs (identical call sequence on every rank)
+    unsigned long long rseq = 0;                     // sharded-reduction sequence
+    unsigned long long xseq = 0;                     // small-exchange sequence
+    bool shard = false;                              // provers slice their tables by rank and all-reduce the round sums (hb_dist_shard)
+    bool reduce_on = false;                          // set by a prover around its sliced phase: grid reductions span all ranks
+    size_t min_slice = 2;                            // a table is sliced only while its per-rank part keeps at least this many entries
 };
 
 struct ExpanderDev {
@@ -78,6 +107,22 @@ struct TraceState {
     size_t pos_capacity = 0;            // entries allocated at pos (kept across traces: cudaFree / cudaMalloc of it cost more than the evaluator)
 };
 
+// the chunk-independent half of the commitments (commit.cu), shared with the multi-GPU entry points (dist.cu)
+int commit_encode_chunks_impl(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_dev,
+                              InnerLayout lay0, size_t first_chunk, size_t total_chunks);
+int elastic_encode_groups_impl(hb_ctx *ctx, const hb_F *chunks, size_t ngroups, size_t B, int trs, int linear_time, uint8_t *inner_dev, InnerLayout lay0);
+
+// ---- multi-GPU helpers (dist.cu); all no-ops / identity on a single-GPU context -----------------------------------------------------
+struct Slice { size_t off, len; bool on; };
+// the part of an n-entry table this rank works on inside a prover: [rank * n/G, (rank+1) * n/G) when sharding is enabled and the part
+// keeps at least min_slice entries, otherwise the whole table (on = false: every rank then computes the same thing redundantly)
+Slice dist_slice(hb_ctx *ctx, size_t n);
+void dist_release(hb_ctx *ctx);                                     // unmap the peers, free the window
+int dist_barrier_dev(hb_ctx *ctx);                                   // cross-rank barrier, stream-ordered (a kernel on ctx->stream)
+// every rank contributes `cnt` leading entries of each of its nt tables; out_dev: nt small tables of cnt * world entries (rank order)
+int dist_gather_small(hb_ctx *ctx, const F *const *tabs, int nt, int cnt, F *out_dev);
+int dist_allreduce_vec(hb_ctx *ctx, F *vec_dev, size_t n);           // field sum over the ranks, in place, through the data region
+
 }  // namespace hb
 
 struct hb_ctx {
@@ -104,6 +149,7 @@ struct hb_ctx {
     hb::TraceState trace;
     // sumcheck reduction scratch: per-CTA partial coefficients + ticket counter (device), result mailbox (pinned host)
     hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr; unsigned long long seq = 0;
+    hb::DistState dist;
     // optional per-kernel timing (hb_profile_*): CUDA events around every launch, on this context's stream
     bool prof = false;
     struct ProfRec { const char *name; cudaEvent_t e0, e1; };

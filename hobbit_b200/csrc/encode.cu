@@ -88,7 +88,7 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
             }
             blake3_compress64(m, out);
         }
-        uint4 *lp = reinterpret_cast<uint4 *>(inner_base + lay.offset(blockIdx.y, (size_t)j * cols + col0 + cc) * 32);
+        uint4 *lp = reinterpret_cast<uint4 *>(lay.addr(inner_base, blockIdx.y, (size_t)j * cols + col0 + cc));
         lp[0] = make_uint4(out[0], out[1], out[2], out[3]);
         lp[1] = make_uint4(out[4], out[5], out[6], out[7]);
     };

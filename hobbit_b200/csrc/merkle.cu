@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) md_inner_standard_kernel(const F *__restr
 #pragma unroll
     for (int q = 0; q < 4; q++) cell_words(T[(4 * j + q) * cols + k], m + 4 * q);
     blake3_compress64(m, out);
-    store_digest(inner_base + lay.offset(blockIdx.y, i) * 32, out);
+    store_digest(lay.addr(inner_base, blockIdx.y, i), out);
 }
 // ... and only the outer compression is sequential in the chunk index (one thread walks one leaf position).
 __global__ void __launch_bounds__(256) md_chain_kernel(const uint8_t *__restrict__ inner, size_t nchunks, size_t nleaves, uint8_t *__restrict__ leaves) {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) md_inner_stream4_kernel(const F *__restri
     cell_words(c2[p], m + 8);
     cell_words(T[p], m + 12);
     blake3_compress64(m, out);
-    store_digest(inner + lay.offset(blockIdx.y, p) * 32, out);
+    store_digest(lay.addr(inner, blockIdx.y, p), out);
 }
 
 // MT_commit_Blake leaves: leaf i = H1(leafs[4i..4i+3])

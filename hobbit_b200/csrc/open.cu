@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) regroup_kernel(const F *__restrict__ in, 
 }
 // round polynomial over the pairs (j, j+L) of (poly, beta): sum_j (p[j] + X dp)(b[j] + X db) -> (a, b, c)
 __global__ void __launch_bounds__(256)
-whir_poly_kernel(const F *__restrict__ p, const F *__restrict__ b, size_t L, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+whir_poly_kernel(const F *__restrict__ p, const F *__restrict__ b, size_t L, RedArgs ra) {
     F acc[3] = {mkF(0, 0), mkF(0, 0), mkF(0, 0)};
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
         F x1 = p[j], x2 = b[j], d1 = fsub(p[j + L], x1), d2 = fsub(b[j + L], x2);
@@ -189,7 +189,7 @@ whir_poly_kernel(const F *__restrict__ p, const F *__restrict__ b, size_t L, F *
         acc[1] = fadd(acc[1], fadd(fmul(d1, x2), fmul(d2, x1)));
         acc[2] = fadd(acc[2], fmul(x1, x2));
     }
-    grid_reduce<3>(acc, partial, ticket, result);
+    grid_reduce<3>(acc, ra);
 }
 __global__ void __launch_bounds__(256) whir_fold_kernel(F *__restrict__ p, F *__restrict__ b, size_t L, F a) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
@@ -443,7 +443,7 @@ extern "C" int hb_whir_poly(hb_ctx *ctx, const hb_F *poly, const hb_F *beta, siz
     HB_TRY(ensure_scratch(ctx));
     Staged sp(ctx), sb(ctx);
     HB_TRY(sp.in(poly, 2 * L * sizeof(F))); HB_TRY(sb.in(beta, 2 * L * sizeof(F)));
-    HB_LAUNCH(ctx, whir_poly_kernel, red_grid_for(ctx, L), 256, 0, sp.as<F>(), sb.as<F>(), L, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    HB_LAUNCH(ctx, whir_poly_kernel, red_grid_for(ctx, L), 256, 0, sp.as<F>(), sb.as<F>(), L, red_args(ctx));
     F co[3]; HB_TRY(read_result(ctx, 3, co));
     for (int c = 0; c < 3; c++) { coeffs3[c].real = co[c].re; coeffs3[c].img = co[c].im; }
     return 0;

@@ -79,7 +79,7 @@ template <int NT> static inline void coeffs_from_evals(F *co) {
 // and was 4 % slower: with both integer pipes ~60 % busy the kernel is not waiting on HBM, see profiles/r02_summary.md.)
 template <int NT, int MODE, bool INTERLEAVED>
 __global__ void __launch_bounds__(HB_SC_THREADS, HB_SC_MINB)
-sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
     constexpr int NC = NT + 1;
     F acc[NC];
 #pragma unroll
@@ -124,7 +124,7 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[c] = fcanon2(lfold(acc[c]));
 
-    grid_reduce<NC>(acc, partial, ticket, result);
+    grid_reduce<NC>(acc, ra);
 }
 
 // ---- S4: streaming folding sumcheck over one product-tree layer (sumcheck.cpp:1093-1136, 1150-1392) -----------------------
@@ -132,20 +132,20 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, F *__restrict__ partial, unsigned *__
 // first block: fold tables := block, K = sum f1 f2 f3
 __global__ void __launch_bounds__(256)
 stream_init_kernel(const F *__restrict__ blk, const F *__restrict__ eq_low, F *__restrict__ f1, F *__restrict__ f2, F *__restrict__ f3, size_t B,
-                   F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+                   RedArgs ra) {
     F acc[1] = {mkF(0, 0)};
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < B; k += (size_t)gridDim.x * blockDim.x) {
         F b1 = blk[2 * k], b2 = blk[2 * k + 1], b3 = eq_low[k];
         f1[k] = b1; f2[k] = b2; f3[k] = b3;
         acc[0] = fadd(acc[0], fmul(fmul(b1, b2), b3));
     }
-    grid_reduce<1>(acc, partial, ticket, result);
+    grid_reduce<1>(acc, ra);
 }
 // error terms of folding one more block into (f1,f2,f3)  (batch_prod, :1103-1111):
 //   K1 = sum f3 (b1 f2 + b2 f1) + b3 f1 f2 ;  K2 = sum b3 (b1 f2 + b2 f1) + f3 b1 b2 ;  K3 = sum b1 b2 b3
 __global__ void __launch_bounds__(256)
 stream_err_kernel(const F *__restrict__ f1, const F *__restrict__ f2, const F *__restrict__ f3, const F *__restrict__ blk,
-                  const F *__restrict__ eq_low, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+                  const F *__restrict__ eq_low, size_t B, RedArgs ra) {
     F acc[3] = {mkF(0, 0), mkF(0, 0), mkF(0, 0)};
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < B; k += (size_t)gridDim.x * blockDim.x) {
         F b1 = blk[2 * k], b2 = blk[2 * k + 1], b3 = eq_low[k], x1 = f1[k], x2 = f2[k], x3 = f3[k];
@@ -154,7 +154,7 @@ stream_err_kernel(const F *__restrict__ f1, const F *__restrict__ f2, const F *_
         acc[1] = fadd(acc[1], fadd(fmul(b3, t1), fmul(x3, t2)));
         acc[2] = fadd(acc[2], fmul(t2, b3));
     }
-    grid_reduce<3>(acc, partial, ticket, result);
+    grid_reduce<3>(acc, ra);
 }
 // f += rho * block  (:1130-1135)
 __global__ void __launch_bounds__(256)
@@ -214,7 +214,7 @@ layer_claim_kernel(const F *__restrict__ A, const F *__restrict__ eq_low, size_t
 struct GateW { F a0, a1, a2, a3, c; };
 template <int MODE>
 __global__ void __launch_bounds__(256)
-gate_round_kernel(Tabs<5> t, size_t L, F r, GateW w, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+gate_round_kernel(Tabs<5> t, size_t L, F r, GateW w, RedArgs ra) {
     F acc[5];
 #pragma unroll
     for (int c = 0; c < 5; c++) acc[c] = mkF(0, 0);
@@ -246,7 +246,7 @@ gate_round_kernel(Tabs<5> t, size_t L, F r, GateW w, F *__restrict__ partial, un
         acc[3] = fadd(acc[3], fadd(fmul(b1, q0), fmul(b0, q1)));
         acc[4] = fadd(acc[4], fmul(b0, q0));
     }
-    grid_reduce<5>(acc, partial, ticket, result);
+    grid_reduce<5>(acc, ra);
 }
 
 // ---- S7 streaming pass (sumcheck.cpp:796-870): fold tables 0 add(S), 1 beta, 2 L, 3 R, 4 O; fold_mul = csum - fold_add ---------
@@ -254,7 +254,7 @@ gate_round_kernel(Tabs<5> t, size_t L, F r, GateW w, F *__restrict__ partial, un
 __global__ void __launch_bounds__(256)
 gs_init_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
                F *__restrict__ fA, F *__restrict__ fB, F *__restrict__ fL, F *__restrict__ fR, F *__restrict__ fO, size_t B,
-               F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+               RedArgs ra) {
     F acc[4] = {mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0)};
     const F one = mkF(1, 0);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
@@ -266,13 +266,13 @@ gs_init_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__rest
         acc[2] = fadd(acc[2], fmul(br, s));
         acc[3] = fadd(acc[3], fmul(fmul(br, l), fsub(one, s)));
     }
-    grid_reduce<4>(acc, partial, ticket, result);
+    grid_reduce<4>(acc, ra);
 }
 // the 12 error terms of folding one more chunk (compute2p/3p/4p_error_terms, :374-432): K1_O K2_O | K1_L K2_L K3_L | K1_R K2_R K3_R | K1_M..K4_M
 __global__ void __launch_bounds__(256)
 gs_err_kernel(const F *__restrict__ bL, const F *__restrict__ bR, const F *__restrict__ bO, const F *__restrict__ bS, const F *__restrict__ beta,
               const F *__restrict__ fA, const F *__restrict__ fB, const F *__restrict__ fL, const F *__restrict__ fR, const F *__restrict__ fO,
-              F csum, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+              F csum, size_t B, RedArgs ra) {
     F acc[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) acc[c] = mkF(0, 0);
@@ -297,7 +297,7 @@ gs_err_kernel(const F *__restrict__ bL, const F *__restrict__ bR, const F *__res
         acc[10] = fadd(acc[10], fadd(fmul(u1, u4), fmul(u2, u3)));
         acc[11] = fadd(acc[11], fmul(u3, u4));
     }
-    grid_reduce<12>(acc, partial, ticket, result);
+    grid_reduce<12>(acc, ra);
 }
 __global__ void __launch_bounds__(256)
 gs_fold_kernel(const F *__restrict__ bL, const F *__restrict__ bR, const F *__restrict__ bO, const F *__restrict__ bS, const F *__restrict__ beta,
@@ -360,7 +360,7 @@ struct S8Folds { F *t[9]; };
 // chunk 0: folds := chunk; Kf_O, Kf_L, Kf_R, Kf_M, Kf_lkp (:538-546)
 __global__ void __launch_bounds__(256)
 gl_init_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
-               S8Folds f, F lr0, F lr1, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+               S8Folds f, F lr0, F lr1, size_t B, RedArgs ra) {
     F acc[5] = {mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0)};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) {
         S8Row x = s8_row(L, R, O, S, i, lr0, lr1); F b = beta[i];
@@ -372,7 +372,7 @@ gl_init_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__rest
         acc[3] = fadd(acc[3], fmul(fmul(br, x.l), x.gM));
         acc[4] = fadd(acc[4], fmul(fmul(b, x.bK), x.gK));
     }
-    grid_reduce<5>(acc, partial, ticket, result);
+    grid_reduce<5>(acc, ra);
 }
 __device__ __forceinline__ void s8_err3(F b1, F gate, F f1, F f2, F fb, F be, F &k1, F &k2, F &k3) {
     F t1 = fadd(fmul(b1, f2), fmul(gate, f1)), t2 = fmul(b1, gate);
@@ -383,7 +383,7 @@ __device__ __forceinline__ void s8_err3(F b1, F gate, F f1, F f2, F fb, F be, F 
 // the 15 error terms of folding one more chunk: K1_O K2_O | K1..3_L | K1..3_R | K1..3_lkp | K1..4_M  (:560-588)
 __global__ void __launch_bounds__(256)
 gl_err_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
-              S8Folds f, F lr0, F lr1, size_t B, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+              S8Folds f, F lr0, F lr1, size_t B, RedArgs ra) {
     F acc[15];
 #pragma unroll
     for (int c = 0; c < 15; c++) acc[c] = mkF(0, 0);
@@ -402,7 +402,7 @@ gl_err_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restr
         acc[13] = fadd(acc[13], fadd(fmul(u1, u4), fmul(u2, u3)));
         acc[14] = fadd(acc[14], fmul(u3, u4));
     }
-    grid_reduce<15>(acc, partial, ticket, result);
+    grid_reduce<15>(acc, ra);
 }
 __global__ void __launch_bounds__(256)
 gl_fold_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
@@ -418,7 +418,7 @@ gl_fold_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__rest
 struct S8W { F a[5]; };
 template <int MODE>
 __global__ void __launch_bounds__(256)
-gatel_round_kernel(Tabs<9> t, size_t L, F r, S8W w, F *__restrict__ partial, unsigned *__restrict__ ticket, F *__restrict__ result) {
+gatel_round_kernel(Tabs<9> t, size_t L, F r, S8W w, RedArgs ra) {
     F acc[5];
 #pragma unroll
     for (int c = 0; c < 5; c++) acc[c] = mkF(0, 0);
@@ -452,7 +452,7 @@ gatel_round_kernel(Tabs<9> t, size_t L, F r, S8W w, F *__restrict__ partial, uns
         acc[3] = fadd(acc[3], fadd(fmul(d[8], q0), fmul(x[8], q1)));
         acc[4] = fadd(acc[4], fmul(x[8], q0));
     }
-    grid_reduce<5>(acc, partial, ticket, result);
+    grid_reduce<5>(acc, ra);
 }
 // pass B (:737-768): per chunk the dot products of eq(sumcheck_rand) with L, R, O, gate_L, gate_R, gate_mul, gate_lkp, lkp_O;
 // grid (parts, nch), out[(c*parts+part)*8 + k]
@@ -523,7 +523,7 @@ template <int NT, int MODE, bool IL>
 static int launch_round(hb_ctx *ctx, const Tabs<NT> &t, size_t L, F r, F *coeffs_host /* NT+1, may be null for FOLD_ONLY */) {
     HB_TRY(ensure_scratch(ctx));
     const size_t want = (L + HB_SC_THREADS - 1) / HB_SC_THREADS, cap = std::min<size_t>((size_t)ctx->sm_count * (1024 / HB_SC_THREADS), kMaxRedBlocks);
-    HB_LAUNCH(ctx, (sc_round_kernel<NT, MODE, IL>), (unsigned)std::max<size_t>(1, std::min(want, cap)), HB_SC_THREADS, 0, t, L, r, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    HB_LAUNCH(ctx, (sc_round_kernel<NT, MODE, IL>), (unsigned)std::max<size_t>(1, std::min(want, cap)), HB_SC_THREADS, 0, t, L, r, red_args(ctx));
     if (MODE != FOLD_ONLY) { HB_TRY(read_result(ctx, NT + 1, coeffs_host)); coeffs_from_evals<NT>(coeffs_host); }
     return 0;
 }
@@ -534,9 +534,9 @@ static inline hb_F toabi(F x) { hb_F o{x.re, x.im}; return o; }
 
 // download k scalars that sit at the head of k device tables
 static int fetch_heads(hb_ctx *ctx, F *const *tabs, int k, F *out) {
-    for (int i = 0; i < k; i++) HB_CHECK(ctx, cudaMemcpyAsync(ctx->mailbox + 8 + i, tabs[i], sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int i = 0; i < k; i++) HB_CHECK(ctx, cudaMemcpyAsync(ctx->mailbox + kMailHeads + i, tabs[i], sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < k; i++) out[i] = ctx->mailbox[8 + i];
+    for (int i = 0; i < k; i++) out[i] = ctx->mailbox[kMailHeads + i];
     return 0;
 }
 
@@ -920,7 +920,7 @@ static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F
     HB_CHECK(ctx, cudaMemcpyAsync(eq_high.data(), eqh_dev, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
     const unsigned grid = grid_for(ctx, B);
     F Kp;
-    HB_LAUNCH(ctx, stream_init_kernel, grid, 256, 0, A, eq_low, f1, f2, f3, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    HB_LAUNCH(ctx, stream_init_kernel, grid, 256, 0, A, eq_low, f1, f2, f3, B, red_args(ctx));
     if ((rc = read_result(ctx, 1, &Kp))) return fail(rc);                 // also completes the eq_high download
     const F a = rnd4[0];
     F Kf = h_fmul(a, Kp);
@@ -932,7 +932,7 @@ static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F
         const size_t g = (step % 2) ? nb / 2 + (step - 1) / 2 : step / 2;
         const F *blk = A + 2 * g * B;
         F K[3];
-        HB_LAUNCH(ctx, stream_err_kernel, grid, 256, 0, f1, f2, f3, blk, eq_low, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+        HB_LAUNCH(ctx, stream_err_kernel, grid, 256, 0, f1, f2, f3, blk, eq_low, B, red_args(ctx));
         if ((rc = read_result(ctx, 3, K))) return fail(rc);
         F K1 = h_fmul(a, K[0]), K2 = h_fmul(a, K[1]), K3 = K[2];
         F rand = R.back();
@@ -1021,7 +1021,7 @@ static int stream_batch_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B,
         if ((rc = beta_dev(ctx, r_dev, lgBj[j], eq_low[j]))) return fail(rc);
         if ((rc = beta_dev(ctx, r_dev + lgBj[j], lgnb, eqh_dev))) return fail(rc);
         HB_CHECK(ctx, cudaMemcpyAsync(eq_high[j].data(), eqh_dev, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
-        HB_LAUNCH(ctx, stream_init_kernel, grid_for(ctx, Bj[j]), 256, 0, A[j], eq_low[j], f1[j], f2[j], f3[j], Bj[j], ctx->red, ctx->ticket, ctx->mailbox_dev);
+        HB_LAUNCH(ctx, stream_init_kernel, grid_for(ctx, Bj[j]), 256, 0, A[j], eq_low[j], f1[j], f2[j], f3[j], Bj[j], red_args(ctx));
         if ((rc = read_result(ctx, 1, &Kp[j]))) return fail(rc);
         HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));                 // eq_high[j] is on the host; r_dev / eqh_dev are reused by the next batch
     }
@@ -1035,7 +1035,7 @@ static int stream_batch_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B,
         F K1 = mkF(0, 0), K2 = mkF(0, 0), K3[MAXB];
         for (int j = 0; j < batches; j++) {
             F K[3];
-            HB_LAUNCH(ctx, stream_err_kernel, grid_for(ctx, Bj[j]), 256, 0, f1[j], f2[j], f3[j], A[j] + 2 * g * Bj[j], eq_low[j], Bj[j], ctx->red, ctx->ticket, ctx->mailbox_dev);
+            HB_LAUNCH(ctx, stream_err_kernel, grid_for(ctx, Bj[j]), 256, 0, f1[j], f2[j], f3[j], A[j] + 2 * g * Bj[j], eq_low[j], Bj[j], red_args(ctx));
             if ((rc = read_result(ctx, 3, K))) return fail(rc);
             K1 = fadd(K1, h_fmul(a[j], K[0])); K2 = fadd(K2, h_fmul(a[j], K[1])); K3[j] = K[2];
         }
@@ -1243,9 +1243,9 @@ extern "C" int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb
         Tabs<5> t;
         for (int k = 0; k < 5; k++) { t.in[k] = cur[k]; t.out[k] = A[k]; }
         const GateW w = {mkF(1, 0), mkF(1, 0), mkF(1, 0), mkF(P61 - 1, 0), mkF(1, 0)};
-        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev); }
+        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx)); }
         else {
-            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev);
+            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx));
             for (int k = 0; k < 5; k++) { cur[k] = A[k]; std::swap(A[k], Bf[k]); }
         }
         rc = read_result(ctx, 5, co);
@@ -1287,7 +1287,7 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
     if ((rc = beta_dev(ctx, srr.as<F>(), lgB, beta))) return fail(rc);
     const unsigned grid = grid_for(ctx, B);
     F Kf[4];                                                    // Kf_O, Kf_L, Kf_R, Kf_M
-    HB_LAUNCH(ctx, gs_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, fA, fB, fL, fR, fO, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    HB_LAUNCH(ctx, gs_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, fA, fB, fL, fR, fO, B, red_args(ctx));
     if ((rc = read_result(ctx, 4, Kf))) return fail(rc);
     *ps += 4 * 16 / 1024.0;
     std::vector<F> Rv; Rv.push_back(mkF(1, 0));
@@ -1295,7 +1295,7 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
     for (size_t c = 1; c < nch; c++) {
         const F *bL = dL + c * B, *bR = dR + c * B, *bO = dO + c * B, *bS = dS + c * B;
         F K[12];
-        HB_LAUNCH(ctx, gs_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, fA, fB, fL, fR, fO, csum, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+        HB_LAUNCH(ctx, gs_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, fA, fB, fL, fR, fO, csum, B, red_args(ctx));
         if ((rc = read_result(ctx, 12, K))) return fail(rc);
         if (!fzero(fsub(fadd(fadd(K[11], K[4]), K[7]), K[1]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 1"); }
         for (int q = 0; q < 8; q++) rand = h_mimc(K[q], rand);                          // K*_M are not hashed (:844-851)
@@ -1324,9 +1324,9 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
         F co[5];
         Tabs<5> t;
         for (int q = 0; q < 5; q++) { t.in[q] = cur[q]; t.out[q] = A5[q]; }
-        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev); }
+        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx)); }
         else {
-            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev);
+            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx));
             for (int q = 0; q < 5; q++) { cur[q] = A5[q]; std::swap(A5[q], B5[q]); }
         }
         if ((rc = read_result(ctx, 5, co))) return fail(rc);
@@ -1419,7 +1419,7 @@ extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, co
     if ((rc = beta_dev(ctx, srr.as<F>(), lgB, beta))) return fail(rc);
     const unsigned grid = grid_for(ctx, B);
     F Kf[5];                                                    // Kf_O, Kf_L, Kf_R, Kf_M, Kf_lkp
-    HB_LAUNCH(ctx, gl_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, f, lr0, lr1, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+    HB_LAUNCH(ctx, gl_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, f, lr0, lr1, B, red_args(ctx));
     if ((rc = read_result(ctx, 5, Kf))) return fail(rc);
     if (!fzero(fsub(fsub(fadd(fadd(Kf[3], Kf[1]), Kf[2]), Kf[4]), Kf[0]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error (gate consistency with lookups, first chunk)"); }
     *ps += 5 * 16 / 1024.0;
@@ -1428,7 +1428,7 @@ extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, co
     for (size_t c = 1; c < nch; c++) {
         const F *bL = dL + c * B, *bR = dR + c * B, *bO = dO + c * B, *bS = dS + c * B;
         F K[15];
-        HB_LAUNCH(ctx, gl_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, f, lr0, lr1, B, ctx->red, ctx->ticket, ctx->mailbox_dev);
+        HB_LAUNCH(ctx, gl_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, f, lr0, lr1, B, red_args(ctx));
         if ((rc = read_result(ctx, 15, K))) return fail(rc);
         if (!fzero(fsub(fsub(fadd(fadd(K[14], K[4]), K[7]), K[10]), K[1]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 1"); }
         for (int q = 0; q < 8; q++) rand = h_mimc(K[q], rand);                          // only the O, L, R terms are hashed (:589-597)
@@ -1455,9 +1455,9 @@ extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, co
         F co[5];
         Tabs<9> t;
         for (int q = 0; q < 9; q++) { t.in[q] = cur[q]; t.out[q] = A9[q]; }
-        if (i == 0) { HB_LAUNCH(ctx, gatel_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev); }
+        if (i == 0) { HB_LAUNCH(ctx, gatel_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx)); }
         else {
-            HB_LAUNCH(ctx, gatel_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, ctx->red, ctx->ticket, ctx->mailbox_dev);
+            HB_LAUNCH(ctx, gatel_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx));
             for (int q = 0; q < 9; q++) { cur[q] = A9[q]; std::swap(A9[q], B9[q]); }
         }
         if ((rc = read_result(ctx, 5, co))) return fail(rc);

@@ -287,6 +287,36 @@ int hb_trace_circuit(hb_ctx *ctx, size_t cs, hb_F *out);
 int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand4, hb_F *xy);
 int hb_trace_lookup_witness(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand2, hb_F *out);
 
+/* ---- multi-GPU: one process per GPU, the GPUs of one NVSwitch box ------------------------------------------------------
+ * The reference is single-process; these entry points implement the partitioning §8e derives from it: commit_standard / Elastic_PC commit
+ * are chunk-parallel up to the Merkle–Damgård chain of each leaf (Our_PC.cpp:146-171, Elastic_PC.cpp:174-285), sumchecks are sharded by
+ * hypercube prefix (sumcheck.cpp:1974-2058 and the streaming provers).  Ranks exchange data with peer stores over NVLink through a
+ * WINDOW of device memory each rank exports with CUDA IPC; there is no host round trip and no separate collective on the data path.
+ * Bootstrap: every rank calls hb_dist_local_info (allocates its window: 64 KiB of control + data_bytes) and gets a 256-byte blob; the
+ * caller all-gathers the blobs (torch.distributed, MPI, the TCP store of the C++ host mirror ...) and passes all `world` blobs, in rank
+ * order, to hb_dist_connect.  world must be 1, 2, 4 or 8.  All ranks must then make the same sequence of hb_dist_* / prover calls. */
+int hb_dist_local_info(hb_ctx *ctx, size_t data_bytes, void *blob256);
+int hb_dist_connect(hb_ctx *ctx, int rank, int world, const void *blobs);
+int hb_dist_disconnect(hb_ctx *ctx);
+int hb_dist_rank(hb_ctx *ctx);
+int hb_dist_world(hb_ctx *ctx);
+int hb_dist_barrier(hb_ctx *ctx);                                   /* device-side barrier over the ranks, then stream sync */
+int hb_dist_allreduce(hb_ctx *ctx, hb_F *vec, size_t n);           /* field sum over the ranks, in place (needs n*16*world data bytes) */
+/* commit_standard of K_total chunks of B coefficients; this rank passes its K_total/world consecutive chunks (chunk range
+ * [rank*K_total/world, ...)), host or device memory.  The inner leaf digests are stored by the encode kernel straight into the window
+ * of the rank that owns the leaf range, every rank chains its B/world leaves over all chunks and builds its subtree, subtrees are
+ * scattered to every rank and the top log2(world) levels rebuilt: levels_out receives ALL (2B-1)*32 bytes on every rank (NULL: skip
+ * the copy; the tree stays in the window).  Needs data_bytes >= K_total*(B/world)*32 + (2B-1)*32 + 256.  world == 1: hb_commit_standard. */
+int hb_dist_commit_standard(hb_ctx *ctx, const hb_F *poly_local, size_t K_total, size_t B, int trs, int linear_time, uint8_t *levels_out);
+/* Elastic_PC commit of groups_total groups of 4 chunks of B coefficients, sharded the same way (4B leaves): levels_out (8B-1)*32 bytes */
+int hb_dist_elastic_commit(hb_ctx *ctx, const hb_F *chunks_local, size_t groups_total, size_t B, int trs, int linear_time, uint8_t *levels_out);
+/* on != 0: the provers (hb_sumcheck3, hb_batch_sumcheck3, hb_mul_tree, hb_stream_sumcheck_layer, hb_mul_tree_stream,
+ * hb_gate_consistency_stream, hb_gate_consistency_lookups_stream) shard their work over the ranks: every rank passes the SAME full
+ * tables (replicated in HBM) and works on its contiguous part of each table / of each BUFFER_SPACE chunk; the round sums are added
+ * across ranks inside the round kernel, so every rank derives the same Fiat–Shamir challenges and returns the same proof, bit-identical
+ * to the single-GPU proof. */
+int hb_dist_shard(hb_ctx *ctx, int on);
+
 #ifdef __cplusplus
 }
 #endif
