@@ -205,29 +205,21 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream())
 
     if world > 1:
-        from hobbit_b200.dist import GpuBackend, commit_standard_sharded
-        be = GpuBackend(ctx, torch.device("cuda", local))
+        ctx.dist_init_torch(K * world * (B // world) * 32 + 2 * B * 32 + 4096)
 
     def step_resident():
         if world > 1:
-            commit_standard_sharded(be, poly_dev.data_ptr(), K * world, B, trs, 1)
+            ctx.dist_commit_standard(poly_dev.data_ptr(), K * world, B, trs, 1, levels_out=levels_dev.data_ptr())
         else:
             ctx.commit_standard(poly_dev.data_ptr(), K, trs, 1, levels_out=levels_dev.data_ptr(), N=N)
 
     def step_e2e():
         if world > 1:
-            lv = commit_standard_sharded(be, poly_host, K * world, B, trs, 1)
-            levels_host_t.copy_(lv, non_blocking=False)
+            ctx.dist_commit_standard(poly_host, K * world, B, trs, 1, levels_out=levels_host if rank == 0 else levels_dev.data_ptr())
         else:
             ctx.commit_standard(poly_host, K, trs, 1, levels_out=levels_host)
 
     levels_host_t = torch.from_numpy(levels_host)
-    if world > 1 and os.environ.get("HB_DIST_TIMING"):
-        tm = []
-        for _ in range(3):
-            commit_standard_sharded(be, poly_dev.data_ptr(), K * world, B, trs, 1, timing=tm)
-        if rank == 0:
-            print("dist phases (encode+exchange, chain+subtree, gather+top) ms:", [[round(1e3 * x, 2) for x in t] for t in tm], file=sys.stderr)
 
     def barrier():
         torch.cuda.synchronize()

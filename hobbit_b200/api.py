@@ -421,6 +421,11 @@ class Context:
     def dist_shard(self, on=True):
         self._ck(self.lib.hb_dist_shard(self.h, 1 if on else 0))
 
+    def dist_stats(self):
+        out = np.zeros(3, dtype=np.uint64)
+        self.lib.hb_dist_stats(self.h, _ptr(out))
+        return {"reductions": int(out[0]), "gathers": int(out[1]), "barriers": int(out[2])}
+
     def dist_allreduce(self, vec):
         v = _F(vec).copy()
         self._ck(self.lib.hb_dist_allreduce(self.h, _ptr(v), c_sz(len(v))))

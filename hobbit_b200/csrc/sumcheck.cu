@@ -167,11 +167,12 @@ stream_fold_kernel(F *__restrict__ f1, F *__restrict__ f2, F *__restrict__ f3, c
 }
 // pass B (:1327-1340): PE0[g] = sum_j beta[j] A[2(gB+j)], PE1[g] = sum_j beta[j] A[2(gB+j)+1]; grid (parts, nb), out[(g*parts+part)*2 + {0,1}]
 __global__ void __launch_bounds__(256)
-partial_evals_kernel(const F *__restrict__ A, const F *__restrict__ beta, size_t B, F *__restrict__ out) {
+partial_evals_kernel(const F *__restrict__ A, const F *__restrict__ beta, size_t B, size_t j0, size_t jn, F *__restrict__ out) {
     __shared__ F sred[8][2];
     const F *blk = A + 2 * (size_t)blockIdx.y * B;
     F a0 = mkF(0, 0), a1 = mkF(0, 0);
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x) {
+    for (size_t jj = (size_t)blockIdx.x * blockDim.x + threadIdx.x; jj < jn; jj += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = j0 + jj;
         F bj = beta[j];
         a0 = fadd(a0, fmul(bj, blk[2 * j])); a1 = fadd(a1, fmul(bj, blk[2 * j + 1]));
     }
@@ -189,12 +190,14 @@ partial_evals_kernel(const F *__restrict__ A, const F *__restrict__ beta, size_t
 
 // generate_claims_opt (:1014-1055): per half-chunk g the sum over k of eq_low[k] A[2(gB+k)] A[2(gB+k)+1]; grid (parts, nb), out[g*parts+part]
 __global__ void __launch_bounds__(256)
-layer_claim_kernel(const F *__restrict__ A, const F *__restrict__ eq_low, size_t B, F *__restrict__ out) {
+layer_claim_kernel(const F *__restrict__ A, const F *__restrict__ eq_low, size_t B, size_t j0, size_t jn, F *__restrict__ out) {
     __shared__ F sred[8];
     const F *blk = A + 2 * (size_t)blockIdx.y * B;
     F a = mkF(0, 0);
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x)
+    for (size_t jj = (size_t)blockIdx.x * blockDim.x + threadIdx.x; jj < jn; jj += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = j0 + jj;
         a = fadd(a, fmul(fmul(eq_low[j], blk[2 * j]), blk[2 * j + 1]));
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) a = fadd(a, shfl_down_F(a, d));
     if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = a;
@@ -311,12 +314,13 @@ gs_fold_kernel(const F *__restrict__ bL, const F *__restrict__ bR, const F *__re
 // chunk-independent sums (sum beta1, sum beta1*beta) are appended by part 0.. of an extra pseudo-chunk (blockIdx.y == nch).
 __global__ void __launch_bounds__(256)
 gs_peval_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta,
-                const F *__restrict__ beta1, size_t B, unsigned nch, F *__restrict__ out) {
+                const F *__restrict__ beta1, size_t B, size_t j0, size_t jn, unsigned nch, F *__restrict__ out) {
     __shared__ F sred[8][4];
     const size_t base = (size_t)blockIdx.y * B;
     const bool extra = blockIdx.y == nch;
     F a[4] = {mkF(0, 0), mkF(0, 0), mkF(0, 0), mkF(0, 0)};
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x) {
+    for (size_t jj = (size_t)blockIdx.x * blockDim.x + threadIdx.x; jj < jn; jj += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = j0 + jj;
         F b1 = beta1[j];
         if (extra) { a[0] = fadd(a[0], b1); a[1] = fadd(a[1], fmul(b1, beta[j])); }
         else {
@@ -458,13 +462,14 @@ gatel_round_kernel(Tabs<9> t, size_t L, F r, S8W w, RedArgs ra) {
 // grid (parts, nch), out[(c*parts+part)*8 + k]
 __global__ void __launch_bounds__(256)
 gl_peval_kernel(const F *__restrict__ L, const F *__restrict__ R, const F *__restrict__ O, const F *__restrict__ S, const F *__restrict__ beta1,
-                F lr0, F lr1, size_t B, F *__restrict__ out) {
+                F lr0, F lr1, size_t B, size_t j0, size_t jn, F *__restrict__ out) {
     __shared__ F sred[8][8];
     const size_t base = (size_t)blockIdx.y * B;
     F a[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = mkF(0, 0);
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < B; j += (size_t)gridDim.x * blockDim.x) {
+    for (size_t jj = (size_t)blockIdx.x * blockDim.x + threadIdx.x; jj < jn; jj += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = j0 + jj;
         S8Row x = s8_row(L, R, O, S, base + j, lr0, lr1); const F b1 = beta1[j];
         const F v[8] = {x.l, x.r, x.o, x.gL, x.gR, x.gM, x.gK, x.bK};
 #pragma unroll
@@ -540,6 +545,24 @@ static int fetch_heads(hb_ctx *ctx, F *const *tabs, int k, F *out) {
     return 0;
 }
 
+// ---- multi-GPU slicing of a set of tables inside a prover (sumcheck sharded by hypercube prefix) ----------------------------
+// While `on`, cur[k] points at this rank's contiguous part of table k and the round sums are added across ranks inside the kernel
+// (ctx->dist.reduce_on).  Adjacent-pair folding keeps pairs rank-local until a round would have fewer than one pair per rank; then every
+// rank's remaining 1-2 entries per table are all-gathered (rank order == index order) into `small` and the last log2(world) rounds run
+// redundantly on every rank.  gsz = global entries per table before this round, L = global pairs of this round.
+struct DistRedGuard { hb_ctx *c; DistRedGuard(hb_ctx *ctx, bool on) : c(ctx) { c->dist.reduce_on = on; } ~DistRedGuard() { c->dist.reduce_on = false; } };
+static int slice_step(hb_ctx *ctx, bool &on, const F **cur, int nt, size_t gsz, size_t L, F *small, size_t *Lloc) {
+    const size_t G = (size_t)ctx->dist.world;
+    if (on && L < G) {
+        const int cnt = (int)(gsz / G);
+        HB_TRY(dist_gather_small(ctx, cur, nt, cnt, small));
+        for (int k = 0; k < nt; k++) cur[k] = small + (size_t)k * gsz;
+        on = false;
+    }
+    *Lloc = on ? L / G : L;
+    return 0;
+}
+
 // eq table on the device (out: 2^nr entries)
 int beta_dev(hb_ctx *ctx, const F *r_dev, int nr, F *out) {
     if (nr <= 12) {
@@ -586,26 +609,39 @@ static int sumcheck3_dev(hb_ctx *ctx, const F *v1, const F *v2, const F *v3, con
                          F *scratch, hb_F *proof, double *ps) {
     int rounds = ilog2(n);
     F rand = prev_r;
-    const F *cur[3] = {v1, v2, v3};
+    Slice sl = dist_slice(ctx, n);
+    bool on = sl.on;
+    const F *cur[3] = {v1 ? v1 + sl.off : nullptr, v2 ? v2 + sl.off : nullptr, v3 + sl.off};
+    if (il) il += 2 * sl.off;
     F *bufA[3], *bufB[3];
     for (int k = 0; k < 3; k++) { bufA[k] = scratch + (size_t)k * (n / 2 + n / 4); bufB[k] = bufA[k] + n / 2; }
+    F *small = nullptr;
+    if (on) HB_CHECK(ctx, cudaMallocAsync(&small, 3 * 2 * kMaxRanks * sizeof(F), ctx->stream));
+    auto done = [&](int rc) { if (small) cudaFreeAsync(small, ctx->stream); return rc; };
     hb_F *rs = proof + 4 * rounds;
     for (int i = 0; i < rounds; i++) {
-        size_t L = n >> (i + 1);
+        size_t L = n >> (i + 1), Ll;
         F co[4];
+        int rc = slice_step(ctx, on, cur, 3, 2 * L, L, small, &Ll);
+        if (rc) return done(rc);
         Tabs<3> t;
         for (int k = 0; k < 3; k++) { t.in[k] = cur[k]; t.out[k] = bufA[k]; }
-        if (i == 0 && il) { t.in[0] = il; t.in[1] = nullptr; HB_TRY((launch_round<3, POLY_AND_FOLD, true>(ctx, t, L, rand, co))); }
-        else HB_TRY((launch_round<3, POLY_AND_FOLD, false>(ctx, t, L, rand, co)));
+        {
+            DistRedGuard g(ctx, on);
+            if (i == 0 && il) { t.in[0] = il; t.in[1] = nullptr; rc = launch_round<3, POLY_AND_FOLD, true>(ctx, t, Ll, rand, co); }
+            else rc = launch_round<3, POLY_AND_FOLD, false>(ctx, t, Ll, rand, co);
+        }
+        if (rc) return done(rc);
         rs[i] = toabi(rand);
         for (int c = 0; c < 4; c++) { proof[4 * i + c] = toabi(co[c]); rand = h_mimc(rand, co[c]); }
         *ps += 5 * 16 / 1024.0;
         for (int k = 0; k < 3; k++) { cur[k] = bufA[k]; std::swap(bufA[k], bufB[k]); }
     }
     F vr[3];
-    if (rounds == 0 && il) HB_FAIL(ctx, "sumcheck3: interleaved input needs n >= 2");
+    if (rounds == 0 && il) { done(0); HB_FAIL(ctx, "sumcheck3: interleaved input needs n >= 2"); }
     F *heads[3] = {const_cast<F *>(cur[0]), const_cast<F *>(cur[1]), const_cast<F *>(cur[2])};
-    HB_TRY(fetch_heads(ctx, heads, 3, vr));
+    { int rc = fetch_heads(ctx, heads, 3, vr); if (rc) return done(rc); }
+    done(0);
     rand = h_mimc(rand, vr[0]); rand = h_mimc(rand, vr[1]);
     *ps += 3 * 16 / 1024.0;
     hb_F *o = proof + 5 * rounds;
@@ -711,14 +747,19 @@ static int batch_sumcheck3_dev(hb_ctx *ctx, const F *d1, const F *d2, const F *d
     std::vector<F> a(a_host, a_host + batches);
     // per batch: ping-pong scratch of size/2 + size/4 per table
     F *scratch; HB_CHECK(ctx, cudaMallocAsync(&scratch, (3 * tot + 8) * sizeof(F), ctx->stream));
-    struct Bt { const F *cur[3]; F *A[3], *B[3]; size_t size; bool exhausted; F x[3]; };
+    struct Bt { const F *cur[3]; F *A[3], *B[3]; size_t size; bool exhausted; F x[3]; bool on; F *small; };
     std::vector<Bt> bt(batches);
     size_t off = 0, soff = 0;
+    F *small_all = nullptr;
     for (int b = 0; b < batches; b++) {
         Bt &q = bt[b]; q.size = sizes[b]; q.exhausted = false;
-        const F *base[3] = {d1 + off, d2 + off, d3 + off};
+        const Slice sl = dist_slice(ctx, sizes[b]);                   // every batch is sliced on its own (its tables may hold only this rank's part)
+        q.on = sl.on; q.small = nullptr;
+        const F *base[3] = {d1 + off + sl.off, d2 + off + sl.off, d3 + off + sl.off};
         for (int k = 0; k < 3; k++) { q.cur[k] = base[k]; q.A[k] = scratch + soff; q.B[k] = q.A[k] + sizes[b] / 2; soff += sizes[b] / 2 + sizes[b] / 4 + 1; }
         off += sizes[b];
+        if (q.on && !small_all) HB_CHECK(ctx, cudaMallocAsync(&small_all, (size_t)batches * 3 * 2 * kMaxRanks * sizeof(F), ctx->stream));
+        if (q.on) q.small = small_all + (size_t)b * 3 * 2 * kMaxRanks;
     }
     const F unset = mkF(P61 - 1, 0);                  // F(-1), the reference's "not yet set" marker (sumcheck.cpp:289)
     std::vector<F> vr(3 * batches, unset);
@@ -737,12 +778,15 @@ static int batch_sumcheck3_dev(hb_ctx *ctx, const F *d1, const F *d2, const F *d
             int lg = ilog2(q.size) - 1 - i;
             F p[4];
             if (lg >= 0) {
-                size_t L = (size_t)1 << lg;
+                size_t L = (size_t)1 << lg, Ll;
+                rc = slice_step(ctx, q.on, q.cur, 3, i == 0 ? 2 * L : 4 * L, L, q.small, &Ll);
+                if (rc) break;
                 Tabs<3> t;
                 for (int k = 0; k < 3; k++) { t.in[k] = q.cur[k]; t.out[k] = q.A[k]; }
-                if (i == 0) rc = launch_round<3, POLY_ONLY, false>(ctx, t, L, rand, p);
+                DistRedGuard g(ctx, q.on);
+                if (i == 0) rc = launch_round<3, POLY_ONLY, false>(ctx, t, Ll, rand, p);
                 else {
-                    rc = launch_round<3, FOLD_THEN_POLY, false>(ctx, t, L, rand, p);
+                    rc = launch_round<3, FOLD_THEN_POLY, false>(ctx, t, Ll, rand, p);
                     for (int k = 0; k < 3; k++) { q.cur[k] = q.A[k]; std::swap(q.A[k], q.B[k]); }
                 }
             } else {
@@ -790,6 +834,7 @@ static int batch_sumcheck3_dev(hb_ctx *ctx, const F *d1, const F *d2, const F *d
         }
         vr[3 * b] = q.x[0]; vr[3 * b + 1] = q.x[1]; vr[3 * b + 2] = q.x[2];
     }
+    if (small_all) cudaFreeAsync(small_all, ctx->stream);
     cudaFreeAsync(scratch, ctx->stream);
     if (rc) return rc;
     *ps += (3 * batches - batches) * 16 / 1024.0;
@@ -918,9 +963,13 @@ static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F
     if ((rc = beta_dev(ctx, r_dev + lgB, lgnb, eqh_dev))) return fail(rc);
     std::vector<F> eq_high(nb);
     HB_CHECK(ctx, cudaMemcpyAsync(eq_high.data(), eqh_dev, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
-    const unsigned grid = grid_for(ctx, B);
+    // multi-GPU: every rank folds positions [so, so + sn) of each block; the error terms are summed across ranks inside the kernels
+    const Slice sl = dist_slice(ctx, B);
+    const size_t so = sl.off, sn = sl.len;
+    DistRedGuard dist_guard(ctx, sl.on);
+    const unsigned grid = grid_for(ctx, sn);
     F Kp;
-    HB_LAUNCH(ctx, stream_init_kernel, grid, 256, 0, A, eq_low, f1, f2, f3, B, red_args(ctx));
+    HB_LAUNCH(ctx, stream_init_kernel, grid, 256, 0, A + 2 * so, eq_low + so, f1 + so, f2 + so, f3 + so, sn, red_args(ctx));
     if ((rc = read_result(ctx, 1, &Kp))) return fail(rc);                 // also completes the eq_high download
     const F a = rnd4[0];
     F Kf = h_fmul(a, Kp);
@@ -930,9 +979,9 @@ static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F
     for (size_t step = 1; step < nb; step++) {
         // processing order of the reference: X0 | Y0, X1, Y1, ...   (natural block index g selects eq_high)
         const size_t g = (step % 2) ? nb / 2 + (step - 1) / 2 : step / 2;
-        const F *blk = A + 2 * g * B;
+        const F *blk = A + 2 * g * B + 2 * so;
         F K[3];
-        HB_LAUNCH(ctx, stream_err_kernel, grid, 256, 0, f1, f2, f3, blk, eq_low, B, red_args(ctx));
+        HB_LAUNCH(ctx, stream_err_kernel, grid, 256, 0, f1 + so, f2 + so, f3 + so, blk, eq_low + so, sn, red_args(ctx));
         if ((rc = read_result(ctx, 3, K))) return fail(rc);
         F K1 = h_fmul(a, K[0]), K2 = h_fmul(a, K[1]), K3 = K[2];
         F rand = R.back();
@@ -943,8 +992,9 @@ static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F
         Kf = fadd(Kf, fadd(h_fmul(x2, K2), h_fmul(x1, K1)));
         R.push_back(rand);
         *ps += 2 * 16 / 1024.0;
-        HB_LAUNCH(ctx, stream_fold_kernel, grid, 256, 0, f1, f2, f3, blk, eq_low, rand, B);
+        HB_LAUNCH(ctx, stream_fold_kernel, grid, 256, 0, f1 + so, f2 + so, f3 + so, blk, eq_low + so, rand, sn);
     }
+    ctx->dist.reduce_on = false;                                              // the provers below slice (and reduce) on their own
     if (!feq(Kp, old_claim)) printf("Error in sumcheck 0 %d\n", 0);           // the reference only warns (sumcheck.cpp:1246-1251)
     std::vector<hb_F> p1(5 * (size_t)lgB + 8);
     size_t szB = B;
@@ -958,9 +1008,10 @@ static int stream_layer_dev(hb_ctx *ctx, const F *A, size_t S, size_t B, const F
     for (int j = 0; j < lgB; j++) P1r[j] = fromabi(p1[4 * lgB + j]);
     HB_CHECK(ctx, cudaMemcpyAsync(r_dev, P1r.data(), lgB * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = beta_dev(ctx, r_dev, lgB, beta))) return fail(rc);
-    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((B + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
+    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((sn + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
     F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, nb * parts * 2 * sizeof(F), ctx->stream));
-    HB_LAUNCH(ctx, partial_evals_kernel, dim3(parts, (unsigned)nb), 256, 0, A, beta, B, pe_dev);
+    HB_LAUNCH(ctx, partial_evals_kernel, dim3(parts, (unsigned)nb), 256, 0, A, beta, B, so, sn, pe_dev);
+    if (sl.on) HB_TRY(dist_allreduce_vec(ctx, pe_dev, nb * parts * 2));
     std::vector<F> pe(nb * parts * 2);
     HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1015,13 +1066,19 @@ static int stream_batch_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B,
     int rc;
     std::vector<std::vector<F>> eq_high(batches, std::vector<F>(nb));
     F Kp[MAXB];
+    Slice sl[MAXB];                                                         // multi-GPU: positions [off, off + len) of every block of batch j
+    for (int j = 0; j < batches; j++) sl[j] = dist_slice(ctx, Bj[j]);
     for (int j = 0; j < batches; j++) {
         if ((int)r[j].size() < lgBj[j] + lgnb) return fail((ctx->err = "stream batch: point too short", 2));
         HB_CHECK(ctx, cudaMemcpyAsync(r_dev, r[j].data(), (lgBj[j] + lgnb) * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = beta_dev(ctx, r_dev, lgBj[j], eq_low[j]))) return fail(rc);
         if ((rc = beta_dev(ctx, r_dev + lgBj[j], lgnb, eqh_dev))) return fail(rc);
         HB_CHECK(ctx, cudaMemcpyAsync(eq_high[j].data(), eqh_dev, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
-        HB_LAUNCH(ctx, stream_init_kernel, grid_for(ctx, Bj[j]), 256, 0, A[j], eq_low[j], f1[j], f2[j], f3[j], Bj[j], red_args(ctx));
+        {
+            DistRedGuard g(ctx, sl[j].on);
+            const size_t so = sl[j].off;
+            HB_LAUNCH(ctx, stream_init_kernel, grid_for(ctx, sl[j].len), 256, 0, A[j] + 2 * so, eq_low[j] + so, f1[j] + so, f2[j] + so, f3[j] + so, sl[j].len, red_args(ctx));
+        }
         if ((rc = read_result(ctx, 1, &Kp[j]))) return fail(rc);
         HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));                 // eq_high[j] is on the host; r_dev / eqh_dev are reused by the next batch
     }
@@ -1035,7 +1092,11 @@ static int stream_batch_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B,
         F K1 = mkF(0, 0), K2 = mkF(0, 0), K3[MAXB];
         for (int j = 0; j < batches; j++) {
             F K[3];
-            HB_LAUNCH(ctx, stream_err_kernel, grid_for(ctx, Bj[j]), 256, 0, f1[j], f2[j], f3[j], A[j] + 2 * g * Bj[j], eq_low[j], Bj[j], red_args(ctx));
+            {
+                DistRedGuard gd(ctx, sl[j].on);
+                const size_t so = sl[j].off;
+                HB_LAUNCH(ctx, stream_err_kernel, grid_for(ctx, sl[j].len), 256, 0, f1[j] + so, f2[j] + so, f3[j] + so, A[j] + 2 * g * Bj[j] + 2 * so, eq_low[j] + so, sl[j].len, red_args(ctx));
+            }
             if ((rc = read_result(ctx, 3, K))) return fail(rc);
             K1 = fadd(K1, h_fmul(a[j], K[0])); K2 = fadd(K2, h_fmul(a[j], K[1])); K3[j] = K[2];
         }
@@ -1047,8 +1108,10 @@ static int stream_batch_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B,
         Kf = fadd(Kf, fadd(h_fmul(x2, K2), h_fmul(x1, K1)));
         R.push_back(rand);
         *ps += (1 + batches) * 16 / 1024.0;
-        for (int j = 0; j < batches; j++)
-            HB_LAUNCH(ctx, stream_fold_kernel, grid_for(ctx, Bj[j]), 256, 0, f1[j], f2[j], f3[j], A[j] + 2 * g * Bj[j], eq_low[j], rand, Bj[j]);
+        for (int j = 0; j < batches; j++) {
+            const size_t so = sl[j].off;
+            HB_LAUNCH(ctx, stream_fold_kernel, grid_for(ctx, sl[j].len), 256, 0, f1[j] + so, f2[j] + so, f3[j] + so, A[j] + 2 * g * Bj[j] + 2 * so, eq_low[j] + so, rand, sl[j].len);
+        }
     }
     for (int j = 0; j < batches; j++) if (!feq(Kp[j], old_claims[j])) printf("Error in sumcheck 0 %d\n", j);   // the reference only warns (:1246-1251)
     const int lgB = lgBj[0];
@@ -1065,9 +1128,10 @@ static int stream_batch_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B,
     std::vector<std::vector<F>> PE(2 * batches, std::vector<F>(nb, mkF(0, 0)));
     for (int j = 0; j < batches; j++) {
         if ((rc = beta_dev(ctx, r_dev, lgBj[j], beta[j]))) return fail(rc);
-        unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((Bj[j] + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
+        unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((sl[j].len + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
         F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, nb * parts * 2 * sizeof(F), ctx->stream));
-        HB_LAUNCH(ctx, partial_evals_kernel, dim3(parts, (unsigned)nb), 256, 0, A[j], beta[j], Bj[j], pe_dev);
+        HB_LAUNCH(ctx, partial_evals_kernel, dim3(parts, (unsigned)nb), 256, 0, A[j], beta[j], Bj[j], sl[j].off, sl[j].len, pe_dev);
+        if (sl[j].on) HB_TRY(dist_allreduce_vec(ctx, pe_dev, nb * parts * 2));
         std::vector<F> pe(nb * parts * 2);
         HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
         HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1114,9 +1178,11 @@ static int layer_claims_dev(hb_ctx *ctx, const F *const *A, size_t S0, size_t B,
         int rc;
         HB_CHECK(ctx, cudaMemcpyAsync(r_dev, r.data(), (lgBj + lgnb) * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = beta_dev(ctx, r_dev, lgBj, lo)) || (rc = beta_dev(ctx, r_dev + lgBj, lgnb, hi))) { cudaFreeAsync(buf, ctx->stream); return rc; }
-        unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((Bj + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
+        const Slice sl = dist_slice(ctx, Bj);
+        unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((sl.len + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nb + 1));
         F *out_dev; HB_CHECK(ctx, cudaMallocAsync(&out_dev, nb * parts * sizeof(F), ctx->stream));
-        HB_LAUNCH(ctx, layer_claim_kernel, dim3(parts, (unsigned)nb), 256, 0, A[j], lo, Bj, out_dev);
+        HB_LAUNCH(ctx, layer_claim_kernel, dim3(parts, (unsigned)nb), 256, 0, A[j], lo, Bj, sl.off, sl.len, out_dev);
+        if (sl.on) HB_TRY(dist_allreduce_vec(ctx, out_dev, nb * parts));
         std::vector<F> part(nb * parts), eh(nb);
         HB_CHECK(ctx, cudaMemcpyAsync(part.data(), out_dev, part.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
         HB_CHECK(ctx, cudaMemcpyAsync(eh.data(), hi, nb * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1285,17 +1351,21 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
     auto fail = [&](int rc) { cudaFreeAsync(buf, ctx->stream); return rc; };
     int rc;
     if ((rc = beta_dev(ctx, srr.as<F>(), lgB, beta))) return fail(rc);
-    const unsigned grid = grid_for(ctx, B);
+    // multi-GPU: every rank folds positions [so, so + dsn) of each chunk; sums are added across ranks inside the kernels
+    const Slice dsl = dist_slice(ctx, B);
+    const size_t dso = dsl.off, dsn = dsl.len;
+    DistRedGuard dist_guard(ctx, dsl.on);
+    const unsigned grid = grid_for(ctx, dsn);
     F Kf[4];                                                    // Kf_O, Kf_L, Kf_R, Kf_M
-    HB_LAUNCH(ctx, gs_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, fA, fB, fL, fR, fO, B, red_args(ctx));
+    HB_LAUNCH(ctx, gs_init_kernel, grid, 256, 0, dL + dso, dR + dso, dO + dso, dS + dso, beta + dso, fA + dso, fB + dso, fL + dso, fR + dso, fO + dso, dsn, red_args(ctx));
     if ((rc = read_result(ctx, 4, Kf))) return fail(rc);
     *ps += 4 * 16 / 1024.0;
     std::vector<F> Rv; Rv.push_back(mkF(1, 0));
     F rand = mkF(0, 0), csum = mkF(1, 0);
     for (size_t c = 1; c < nch; c++) {
-        const F *bL = dL + c * B, *bR = dR + c * B, *bO = dO + c * B, *bS = dS + c * B;
+        const F *bL = dL + c * B + dso, *bR = dR + c * B + dso, *bO = dO + c * B + dso, *bS = dS + c * B + dso;
         F K[12];
-        HB_LAUNCH(ctx, gs_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, fA, fB, fL, fR, fO, csum, B, red_args(ctx));
+        HB_LAUNCH(ctx, gs_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta + dso, fA + dso, fB + dso, fL + dso, fR + dso, fO + dso, csum, dsn, red_args(ctx));
         if ((rc = read_result(ctx, 12, K))) return fail(rc);
         if (!fzero(fsub(fadd(fadd(K[11], K[4]), K[7]), K[1]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 1"); }
         for (int q = 0; q < 8; q++) rand = h_mimc(K[q], rand);                          // K*_M are not hashed (:844-851)
@@ -1306,7 +1376,7 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
         Kf[2] = fadd(Kf[2], fadd(fadd(h_fmul(x1, K[5]), h_fmul(x2, K[6])), h_fmul(x3, K[7])));
         Kf[3] = fadd(Kf[3], fadd(fadd(fadd(h_fmul(x1, K[8]), h_fmul(x2, K[9])), h_fmul(x3, K[10])), h_fmul(x4, K[11])));
         *ps += 12 * 16 / 1024.0;
-        HB_LAUNCH(ctx, gs_fold_kernel, grid, 256, 0, bL, bR, bO, bS, beta, fA, fB, fL, fR, fO, rand, B);
+        HB_LAUNCH(ctx, gs_fold_kernel, grid, 256, 0, bL, bR, bO, bS, beta + dso, fA + dso, fB + dso, fL + dso, fR + dso, fO + dso, rand, dsn);
         csum = fadd(csum, rand);
     }
     size_t k = 0;
@@ -1314,19 +1384,24 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
     const F *a = (const F *)rnd10, *b = a + 4;
     F sum = fadd(fadd(h_fmul(a[0], Kf[1]), h_fmul(a[1], Kf[2])), fadd(h_fmul(a[2], Kf[3]), h_fmul(Kf[0], a[3])));
     // degree-4 sumcheck over the folds (:877-935)
-    const F *cur[5] = {fA, fB, fL, fR, fO};
+    const F *cur[5] = {fA + dso, fB + dso, fL + dso, fR + dso, fO + dso};
+    bool on = dsl.on;
+    F *small = nullptr;
+    if (on) HB_CHECK(ctx, cudaMallocAsync(&small, 5 * 2 * kMaxRanks * sizeof(F), ctx->stream));
     F *A5[5], *B5[5];
     for (int q = 0; q < 5; q++) { A5[q] = pp + (size_t)q * (B / 2 + B / 4 + 2); B5[q] = A5[q] + B / 2 + 1; }
     const GateW w = {a[0], a[1], a[2], a[3], csum};
     std::vector<F> srnd;
     for (int i = 0; i < lgB; i++) {
-        size_t Lp = B >> (i + 1);
+        size_t Lp = B >> (i + 1), Ll;
         F co[5];
+        if ((rc = slice_step(ctx, on, cur, 5, i == 0 ? 2 * Lp : 4 * Lp, Lp, small, &Ll))) return fail(rc);
+        ctx->dist.reduce_on = on;
         Tabs<5> t;
         for (int q = 0; q < 5; q++) { t.in[q] = cur[q]; t.out[q] = A5[q]; }
-        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx)); }
+        if (i == 0) { HB_LAUNCH(ctx, gate_round_kernel<POLY_ONLY>, grid_for(ctx, Ll), 256, 0, t, Ll, rand, w, red_args(ctx)); }
         else {
-            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx));
+            HB_LAUNCH(ctx, gate_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Ll), 256, 0, t, Ll, rand, w, red_args(ctx));
             for (int q = 0; q < 5; q++) { cur[q] = A5[q]; std::swap(A5[q], B5[q]); }
         }
         if ((rc = read_result(ctx, 5, co))) return fail(rc);
@@ -1338,6 +1413,7 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
         srnd.push_back(rand);
         *ps += 5 * 16 / 1024.0;
     }
+    ctx->dist.reduce_on = false;
     F fin[5];
     {
         Tabs<5> t;
@@ -1350,9 +1426,11 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
     // pass B: partial evaluations per chunk against eq(sumcheck_rand)
     HB_CHECK(ctx, cudaMemcpyAsync(r_dev, srnd.data(), lgB * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = beta_dev(ctx, r_dev, lgB, beta1))) return fail(rc);
-    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((B + 2047) / 2048, (size_t)(2 * ctx->sm_count) / (nch + 1) + 1));
+    if (small) cudaFreeAsync(small, ctx->stream);
+    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((dsn + 2047) / 2048, (size_t)(2 * ctx->sm_count) / (nch + 1) + 1));
     F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, (nch + 1) * parts * 4 * sizeof(F), ctx->stream));
-    HB_LAUNCH(ctx, gs_peval_kernel, dim3(parts, (unsigned)nch + 1), 256, 0, dL, dR, dO, dS, beta, beta1, B, (unsigned)nch, pe_dev);
+    HB_LAUNCH(ctx, gs_peval_kernel, dim3(parts, (unsigned)nch + 1), 256, 0, dL, dR, dO, dS, beta, beta1, B, dso, dsn, (unsigned)nch, pe_dev);
+    if (dsl.on) HB_TRY(dist_allreduce_vec(ctx, pe_dev, (nch + 1) * parts * 4));
     std::vector<F> pe((nch + 1) * parts * 4);
     HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1417,18 +1495,23 @@ extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, co
     auto fail = [&](int rc) { cudaFreeAsync(buf, ctx->stream); return rc; };
     int rc;
     if ((rc = beta_dev(ctx, srr.as<F>(), lgB, beta))) return fail(rc);
-    const unsigned grid = grid_for(ctx, B);
+    // multi-GPU: every rank folds positions [so, so + dsn) of each chunk; sums are added across ranks inside the kernels
+    const Slice dsl = dist_slice(ctx, B);
+    const size_t dso = dsl.off, dsn = dsl.len;
+    DistRedGuard dist_guard(ctx, dsl.on);
+    S8Folds fs; for (int q = 0; q < 9; q++) fs.t[q] = f.t[q] + dso;
+    const unsigned grid = grid_for(ctx, dsn);
     F Kf[5];                                                    // Kf_O, Kf_L, Kf_R, Kf_M, Kf_lkp
-    HB_LAUNCH(ctx, gl_init_kernel, grid, 256, 0, dL, dR, dO, dS, beta, f, lr0, lr1, B, red_args(ctx));
+    HB_LAUNCH(ctx, gl_init_kernel, grid, 256, 0, dL + dso, dR + dso, dO + dso, dS + dso, beta + dso, fs, lr0, lr1, dsn, red_args(ctx));
     if ((rc = read_result(ctx, 5, Kf))) return fail(rc);
     if (!fzero(fsub(fsub(fadd(fadd(Kf[3], Kf[1]), Kf[2]), Kf[4]), Kf[0]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error (gate consistency with lookups, first chunk)"); }
     *ps += 5 * 16 / 1024.0;
     std::vector<F> Rv; Rv.push_back(mkF(1, 0));
     F rand = mkF(0, 0);
     for (size_t c = 1; c < nch; c++) {
-        const F *bL = dL + c * B, *bR = dR + c * B, *bO = dO + c * B, *bS = dS + c * B;
+        const F *bL = dL + c * B + dso, *bR = dR + c * B + dso, *bO = dO + c * B + dso, *bS = dS + c * B + dso;
         F K[15];
-        HB_LAUNCH(ctx, gl_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta, f, lr0, lr1, B, red_args(ctx));
+        HB_LAUNCH(ctx, gl_err_kernel, grid, 256, 0, bL, bR, bO, bS, beta + dso, fs, lr0, lr1, dsn, red_args(ctx));
         if ((rc = read_result(ctx, 15, K))) return fail(rc);
         if (!fzero(fsub(fsub(fadd(fadd(K[14], K[4]), K[7]), K[10]), K[1]))) { cudaFreeAsync(buf, ctx->stream); HB_FAIL(ctx, "Error in gate consistency 1"); }
         for (int q = 0; q < 8; q++) rand = h_mimc(K[q], rand);                          // only the O, L, R terms are hashed (:589-597)
@@ -1440,24 +1523,29 @@ extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, co
         Kf[4] = fadd(Kf[4], fadd(fadd(h_fmul(x1, K[8]), h_fmul(x2, K[9])), h_fmul(x3, K[10])));
         Kf[3] = fadd(Kf[3], fadd(fadd(fadd(h_fmul(x1, K[11]), h_fmul(x2, K[12])), h_fmul(x3, K[13])), h_fmul(x4, K[14])));
         *ps += 15 * 16 / 1024.0;
-        HB_LAUNCH(ctx, gl_fold_kernel, grid, 256, 0, bL, bR, bO, bS, beta, f, lr0, lr1, rand, B);
+        HB_LAUNCH(ctx, gl_fold_kernel, grid, 256, 0, bL, bR, bO, bS, beta + dso, fs, lr0, lr1, rand, dsn);
     }
     size_t k = 0;
     for (auto &x : Rv) out[k++] = toabi(x);
     const F *a = (const F *)rnd13, *b = a + 5;
     F sum = fadd(fadd(fadd(h_fmul(a[0], Kf[1]), h_fmul(a[1], Kf[2])), fadd(h_fmul(a[2], Kf[3]), h_fmul(Kf[0], a[3]))), h_fmul(Kf[4], a[4]));
     const F *cur[9]; F *A9[9], *B9[9];
-    for (int q = 0; q < 9; q++) { cur[q] = f.t[q]; A9[q] = pp + (size_t)q * pps; B9[q] = A9[q] + B / 2 + 1; }
+    for (int q = 0; q < 9; q++) { cur[q] = f.t[q] + dso; A9[q] = pp + (size_t)q * pps; B9[q] = A9[q] + B / 2 + 1; }
+    bool on = dsl.on;
+    F *small = nullptr;
+    if (on) HB_CHECK(ctx, cudaMallocAsync(&small, 9 * 2 * kMaxRanks * sizeof(F), ctx->stream));
     S8W w; for (int q = 0; q < 5; q++) w.a[q] = a[q];
     std::vector<F> srnd;
     for (int i = 0; i < lgB; i++) {
-        size_t Lp = B >> (i + 1);
+        size_t Lp = B >> (i + 1), Ll;
         F co[5];
+        if ((rc = slice_step(ctx, on, cur, 9, i == 0 ? 2 * Lp : 4 * Lp, Lp, small, &Ll))) return fail(rc);
+        ctx->dist.reduce_on = on;
         Tabs<9> t;
         for (int q = 0; q < 9; q++) { t.in[q] = cur[q]; t.out[q] = A9[q]; }
-        if (i == 0) { HB_LAUNCH(ctx, gatel_round_kernel<POLY_ONLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx)); }
+        if (i == 0) { HB_LAUNCH(ctx, gatel_round_kernel<POLY_ONLY>, grid_for(ctx, Ll), 256, 0, t, Ll, rand, w, red_args(ctx)); }
         else {
-            HB_LAUNCH(ctx, gatel_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Lp), 256, 0, t, Lp, rand, w, red_args(ctx));
+            HB_LAUNCH(ctx, gatel_round_kernel<FOLD_THEN_POLY>, grid_for(ctx, Ll), 256, 0, t, Ll, rand, w, red_args(ctx));
             for (int q = 0; q < 9; q++) { cur[q] = A9[q]; std::swap(A9[q], B9[q]); }
         }
         if ((rc = read_result(ctx, 5, co))) return fail(rc);
@@ -1469,6 +1557,7 @@ extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, co
         srnd.push_back(rand);
         *ps += 5 * 16 / 1024.0;
     }
+    ctx->dist.reduce_on = false;
     F fin[9];
     {
         Tabs<9> t;
@@ -1481,9 +1570,11 @@ extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, co
     for (int q = 0; q < 9; q++) out[k++] = toabi(fo[q]);
     HB_CHECK(ctx, cudaMemcpyAsync(r_dev, srnd.data(), lgB * sizeof(F), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = beta_dev(ctx, r_dev, lgB, beta1))) return fail(rc);
-    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((B + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nch + 1));
+    if (small) cudaFreeAsync(small, ctx->stream);
+    unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>((dsn + 2047) / 2048, (size_t)(2 * ctx->sm_count) / nch + 1));
     F *pe_dev; HB_CHECK(ctx, cudaMallocAsync(&pe_dev, nch * parts * 8 * sizeof(F), ctx->stream));
-    HB_LAUNCH(ctx, gl_peval_kernel, dim3(parts, (unsigned)nch), 256, 0, dL, dR, dO, dS, beta1, lr0, lr1, B, pe_dev);
+    HB_LAUNCH(ctx, gl_peval_kernel, dim3(parts, (unsigned)nch), 256, 0, dL, dR, dO, dS, beta1, lr0, lr1, B, dso, dsn, pe_dev);
+    if (dsl.on) HB_TRY(dist_allreduce_vec(ctx, pe_dev, nch * parts * 8));
     std::vector<F> pe(nch * parts * 8);
     HB_CHECK(ctx, cudaMemcpyAsync(pe.data(), pe_dev, pe.size() * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

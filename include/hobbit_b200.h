@@ -316,6 +316,8 @@ int hb_dist_elastic_commit(hb_ctx *ctx, const hb_F *chunks_local, size_t groups_
  * across ranks inside the round kernel, so every rank derives the same Fiat–Shamir challenges and returns the same proof, bit-identical
  * to the single-GPU proof. */
 int hb_dist_shard(hb_ctx *ctx, int on);
+/* counters since hb_dist_connect: cross-rank reductions done inside round kernels, small all-gathers, device barriers */
+void hb_dist_stats(hb_ctx *ctx, uint64_t *out3);
 
 #ifdef __cplusplus
 }

@@ -87,3 +87,81 @@ def _run(worker, world, timeout=600):
 @pytest.mark.parametrize("world", [2, 4])
 def test_native_sharded_commits(world):
     _run(_commit_worker, world)
+
+
+def _prover_worker(rank, world, port, ret):
+    """Every sharded prover against its own single-GPU run on the same (replicated) tables: proofs must be bit-identical."""
+    from helpers import RawABI, consistent_trace, F
+    ctx, dist = _setup(rank, world, port, 0, 1 << 20)
+    raw = RawABI.__new__(RawABI); raw.lib = ctx.lib; raw.ctx = ctx.h
+    orc = Checker("orc")
+    rng = np.random.default_rng(77)
+    cases = []
+    for n in (1 << 12, 16, 2 * world, world):                                       # down to tables smaller than the slicing threshold
+        v = [rand_field(rng, n) for _ in range(3)]
+        cases.append(("sumcheck3 n=%d" % n, lambda v=v: ctx.sumcheck3(v[0], v[1], v[2], F([5, 7]))))
+    for sizes in ([1 << 10, 1 << 10], [1 << 11, 1 << 6, 4, 1], [8 * world]):
+        t = [rand_field(rng, sum(sizes)) for _ in range(3)]
+        a = rand_field(rng, len(sizes))
+        cases.append(("batch_sumcheck3 %s" % sizes, lambda t=t, a=a, sizes=sizes: ctx.batch_sumcheck3(t[0], t[1], t[2], sizes, a)))
+    for vectors, n in ((1, 1 << 10), (4, 1 << 9)):
+        x = rand_field(rng, vectors * n)
+        xr = rand_field(rng, max(1, int(np.log2(vectors))))
+        cases.append(("mul_tree %dx%d" % (vectors, n), lambda x=x, vectors=vectors, xr=xr: ctx.mul_tree(x, vectors, F([3, 0]), xr)))
+    for total, B, layer in ((1 << 14, 1 << 8, 0), (1 << 16, 1 << 10, 3)):
+        xy = rand_field(rng, total)
+        r = rand_field(rng, int(np.log2((total >> layer) // 2)))
+        rnd = rand_field(rng, 4)
+        cases.append(("stream_layer %d/%d/%d" % (total, B, layer), lambda xy=xy, B=B, layer=layer, r=r, rnd=rnd: ctx.stream_layer(xy, B, layer, r, F([5, 0]), rnd)))
+    for total, vectors, B, distance in ((1 << 15, 8, 1 << 10, 5), (1 << 16, 8, 1 << 8, 3)):      # shallow, and layers > distance (batched passes)
+        xy = rand_field(rng, total)
+        layers = int(np.log2(total // (2 * B)))
+        if layers % distance and layers > distance:
+            layers = distance + layers - layers % distance
+        nr = 4 * layers if layers <= distance else (layers - distance) + distance * (3 * (layers // distance) + 1)
+        rnd, pr, xr = rand_field(rng, nr), rand_field(rng, 1), rand_field(rng, int(np.log2(vectors)))
+        cases.append(("mul_tree_stream %d/%d/%d/%d" % (total, vectors, B, distance),
+                      lambda xy=xy, vectors=vectors, B=B, distance=distance, pr=pr, xr=xr, rnd=rnd: ctx.mul_tree_stream(xy, vectors, B, distance, 0, pr, xr, rnd)))
+    for cs, B in ((1 << 12, 1 << 9), (1 << 10, 1 << 10)):
+        L, R, O, S = consistent_trace(np.random.default_rng(cs), orc, cs)
+        r, rnd = rand_field(rng, int(np.log2(B))), rand_field(rng, 10)
+        cases.append(("gate_stream %d/%d" % (cs, B), lambda L=L, R=R, O=O, S=S, B=B, r=r, rnd=rnd: ctx.gate_consistency_stream(L, R, O, S, B, r, rnd)))
+    for cs, B in ((1 << 12, 1 << 8), (1 << 12, 1 << 12)):
+        r2 = np.random.default_rng(cs + B)
+        L, R = rand_field(r2, cs), rand_field(r2, cs)
+        S = np.zeros((cs, 2), dtype=np.uint64); S[:, 0] = r2.integers(0, 3, size=cs)
+        O = rand_field(r2, cs)
+        add, mul = S[:, 0] == 0, S[:, 0] == 1
+        O[add] = orc.binop(0, L, R)[add]
+        O[mul] = orc.binop(2, L, R)[mul]
+        r, lr, rnd = rand_field(r2, int(np.log2(B))), rand_field(r2, 2), rand_field(r2, 13)
+        cases.append(("gate_lookups %d/%d" % (cs, B), lambda L=L, R=R, O=O, S=S, B=B, r=r, lr=lr, rnd=rnd: raw.gate_consistency_lookups(L, R, O, S, B, r, lr, rnd)))
+
+    def same(a, b):
+        if isinstance(a, (tuple, list)):
+            return len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        if isinstance(a, np.ndarray):
+            return np.array_equal(a, b)
+        return a == b
+
+    ok = True
+    for name, fn in cases:
+        ctx.dist_shard(False)
+        want = fn()
+        ctx.dist_shard(True)
+        before = ctx.dist_stats()["reductions"]
+        got = fn()
+        sharded = ctx.dist_stats()["reductions"] > before
+        if not sharded and not any(s in name for s in ("n=%d" % world, "mul_tree 1x")) and "n=16" not in name:
+            print("rank %d: %s did not run sharded" % (rank, name), flush=True)
+            ok = False
+        if not same(want, got):
+            print("rank %d: MISMATCH in %s" % (rank, name), flush=True)
+            ok = False
+    ctx.dist_shard(False)
+    _finish(ctx, dist, ok, rank, ret)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_native_sharded_provers(world):
+    _run(_prover_worker, world)
