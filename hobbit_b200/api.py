@@ -31,6 +31,7 @@ def load_library():
         L = ctypes.CDLL(p)
         L.hb_last_error.restype = ctypes.c_char_p
         L.hb_launch_count.restype = ctypes.c_uint64
+        L.hb_transcript_digest.restype = ctypes.c_uint64
         L.hb_stream.restype = c_vp
         L.hb_tensor_device.restype = c_vp
         L.hb_expander_codeword_len.restype = ctypes.c_longlong
@@ -114,6 +115,9 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.hb_launch_count(self.h))
+
+    def transcript_digest(self, reset=False):
+        return int(self.lib.hb_transcript_digest(self.h, 1 if reset else 0))
 
     def profile(self, on=True):
         self._ck(self.lib.hb_profile_enable(self.h, 1 if on else 0))

@@ -250,6 +250,11 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
 extern "C" const char *hb_last_error(hb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int hb_sync(hb_ctx *ctx) { HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
 extern "C" uint64_t hb_launch_count(hb_ctx *ctx) { return ctx->launches; }
+extern "C" uint64_t hb_transcript_digest(hb_ctx *ctx, int reset) {
+    const uint64_t h = ctx->transcript;
+    if (reset) ctx->transcript = 0xcbf29ce484222325ULL;
+    return h;
+}
 extern "C" void *hb_stream(hb_ctx *ctx) { return (void *)ctx->stream; }
 // ---- per-kernel timing -------------------------------------------------------------------------------------
 extern "C" int hb_profile_enable(hb_ctx *ctx, int on) {

@@ -150,6 +150,8 @@ struct hb_ctx {
     // sumcheck reduction scratch: per-CTA partial coefficients + ticket counter (device), result mailbox (pinned host)
     hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr; unsigned long long seq = 0;
     hb::DistState dist;
+    // FNV-1a over every value a prover read back from the GPU (round sums, table heads): a digest of the whole Fiat–Shamir transcript
+    uint64_t transcript = 0xcbf29ce484222325ULL;
     // optional per-kernel timing (hb_profile_*): CUDA events around every launch, on this context's stream
     bool prof = false;
     struct ProfRec { const char *name; cudaEvent_t e0, e1; };
@@ -255,6 +257,11 @@ struct Staged {
     template <class T> T *as() { return reinterpret_cast<T *>(dev); }
 };
 
+inline void transcript_absorb(hb_ctx *ctx, const F *v, int n) {
+    uint64_t h = ctx->transcript;
+    for (int i = 0; i < n; i++) { h = (h ^ v[i].re) * 0x100000001b3ULL; h = (h ^ v[i].im) * 0x100000001b3ULL; }
+    ctx->transcript = h;
+}
 inline int ilog2(size_t x) { int l = 0; while (x >>= 1) l++; return l; }
 
 // internal entry points implemented across the .cu files (all take DEVICE pointers)

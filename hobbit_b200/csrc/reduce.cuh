@@ -164,6 +164,7 @@ inline int read_result(hb_ctx *ctx, int nc, F *out) {
     if (reinterpret_cast<volatile u64 *>(ctx->mailbox + kMailErr)[0]) HB_FAIL(ctx, "multi-GPU reduction: a peer rank did not answer within 10 s");
     const volatile u64 *m = reinterpret_cast<const volatile u64 *>(ctx->mailbox);
     for (int c = 0; c < nc; c++) { out[c].re = m[2 * c]; out[c].im = m[2 * c + 1]; }
+    transcript_absorb(ctx, out, nc);
     return 0;
 }
 inline unsigned red_grid_for(hb_ctx *ctx, size_t L) {

@@ -542,6 +542,7 @@ static int fetch_heads(hb_ctx *ctx, F *const *tabs, int k, F *out) {
     for (int i = 0; i < k; i++) HB_CHECK(ctx, cudaMemcpyAsync(ctx->mailbox + kMailHeads + i, tabs[i], sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < k; i++) out[i] = ctx->mailbox[kMailHeads + i];
+    transcript_absorb(ctx, out, k);
     return 0;
 }
 

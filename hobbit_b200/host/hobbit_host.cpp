@@ -7,6 +7,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/socket.h>
+#include <unistd.h>
 
 namespace hobbit {
 
@@ -31,6 +36,66 @@ void init_backend(int device) {
     if (hb_ctx_create(&g_ctx, device)) { printf("hobbit_b200: no CUDA device (there is no CPU fallback)\n"); exit(-1); }
 }
 hb_ctx *backend() { if (!g_ctx) init_backend(0); return g_ctx; }
+
+// ---- multi-GPU bootstrap: a one-shot TCP all-gather of the 256-byte window blobs (rank 0 serves) ----------------------------------
+static size_t g_dist_data_bytes = 0;
+static bool xfer(int fd, void *buf, size_t n, bool send_it) {
+    char *p = (char *)buf;
+    while (n) {
+        ssize_t k = send_it ? ::send(fd, p, n, MSG_NOSIGNAL) : ::recv(fd, p, n, 0);
+        if (k <= 0) return false;
+        p += k; n -= (size_t)k;
+    }
+    return true;
+}
+static void tcp_allgather(int rank, int world, const char *addr, int port, const void *mine, void *all, size_t bytes) {
+    if (rank == 0) {
+        int ls = socket(AF_INET, SOCK_STREAM, 0), one = 1;
+        setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+        sockaddr_in sa{}; sa.sin_family = AF_INET; sa.sin_port = htons((uint16_t)port); sa.sin_addr.s_addr = htonl(INADDR_ANY);
+        if (bind(ls, (sockaddr *)&sa, sizeof(sa)) || listen(ls, world)) { printf("hobbit_b200: rendezvous: cannot listen on port %d\n", port); exit(-1); }
+        memcpy(all, mine, bytes);
+        std::vector<int> fds;
+        for (int i = 1; i < world; i++) {
+            int fd = accept(ls, nullptr, nullptr); int r = -1;
+            if (fd < 0 || !xfer(fd, &r, sizeof(r), false) || r < 1 || r >= world || !xfer(fd, (char *)all + (size_t)r * bytes, bytes, false)) { printf("hobbit_b200: rendezvous: bad peer\n"); exit(-1); }
+            fds.push_back(fd);
+        }
+        for (int fd : fds) { if (!xfer(fd, all, bytes * world, true)) { printf("hobbit_b200: rendezvous: send failed\n"); exit(-1); } close(fd); }
+        close(ls);
+    } else {
+        sockaddr_in sa{}; sa.sin_family = AF_INET; sa.sin_port = htons((uint16_t)port); inet_pton(AF_INET, addr, &sa.sin_addr);
+        int fd = -1;
+        for (int tries = 0; tries < 600; tries++) {                      // rank 0 may still be starting: retry for a minute
+            fd = socket(AF_INET, SOCK_STREAM, 0);
+            if (connect(fd, (sockaddr *)&sa, sizeof(sa)) == 0) break;
+            close(fd); fd = -1; usleep(100000);
+        }
+        if (fd < 0 || !xfer(fd, &rank, sizeof(rank), true) || !xfer(fd, const_cast<void *>(mine), bytes, true) || !xfer(fd, all, bytes * world, false)) {
+            printf("hobbit_b200: rendezvous: cannot reach rank 0 at %s:%d\n", addr, port); exit(-1);
+        }
+        close(fd);
+    }
+}
+void dist_init_from_env(size_t data_bytes) {
+    const char *ws = getenv("WORLD_SIZE");
+    const int world = ws ? atoi(ws) : 1, rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
+    int dev = getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : rank;
+    if (getenv("HB_SHARE_GPU") && atoi(getenv("HB_SHARE_GPU"))) dev = 0;
+    init_backend(dev);
+    if (world <= 1) return;
+    const char *addr = getenv("MASTER_ADDR") ? getenv("MASTER_ADDR") : "127.0.0.1";
+    const int port = getenv("HB_RDV_PORT") ? atoi(getenv("HB_RDV_PORT")) : (getenv("MASTER_PORT") ? atoi(getenv("MASTER_PORT")) : 29500) + 29;
+    unsigned char mine[256]; std::vector<unsigned char> all((size_t)256 * world);
+    CK(hb_dist_local_info(g_ctx, data_bytes, mine));
+    tcp_allgather(rank, world, addr, port, mine, all.data(), 256);
+    CK(hb_dist_connect(g_ctx, rank, world, all.data()));
+    CK(hb_dist_barrier(g_ctx));
+    CK(hb_dist_shard(g_ctx, 1));
+    g_dist_data_bytes = data_bytes;
+}
+int dist_rank() { return g_ctx ? hb_dist_rank(g_ctx) : 0; }
+int dist_world() { return g_ctx ? hb_dist_world(g_ctx) : 1; }
 
 // ---- F (host scalars only: challenges, a handful of coefficients) -----------------------------------------
 static inline unsigned long long mulm(unsigned long long a, unsigned long long b) {
@@ -240,8 +305,30 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     const double t_begin = trace ? wall_ms() : 0;
     if (fd.size / BUFFER_SPACE < 4) printf("Decrease buffer size %d\n", (int)(fd.size / BUFFER_SPACE));
     std::vector<F> buff(BUFFER_SPACE);
-    CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
     const F *res = fd.name == "witness" ? resident_stream(fd) : nullptr;         // what read_stream_PC forwards (:2365-2370): slices of the HBM-resident stream
+    // Multi-GPU: a resident stream of whole groups of 4 chunks is committed sharded — this rank encodes its groups, the inner digests
+    // cross NVLink inside the encode kernel, every rank ends up with the whole tree (hb_dist_elastic_commit).  Same levels, bit for bit.
+    const int world = dist_world();
+    const size_t groups = fd.size / (4 * BUFFER_SPACE);
+    if (world > 1 && res && fd.size % (4 * BUFFER_SPACE) == 0 && groups % world == 0 && (4 * BUFFER_SPACE) % world == 0 &&
+        32 * (fd.size / world + 8 * BUFFER_SPACE) + 4096 <= g_dist_data_bytes) {
+        void *dlev = nullptr;
+        CK(hb_malloc_stream(backend(), &dlev, (8 * BUFFER_SPACE - 1) * 32));
+        CK(hb_dist_elastic_commit(backend(), (const hb_F *)(res + (size_t)dist_rank() * (groups / world) * 4 * BUFFER_SPACE), groups, BUFFER_SPACE,
+                                  tensor_row_size, linear_time ? 1 : 0, (uint8_t *)dlev));
+        MT_hashes.clear();
+        size_t off = 0;
+        for (size_t n = 4 * BUFFER_SPACE;; n /= 2) {
+            MT_hashes.emplace_back(n);
+            if (commit_levels_on_host || n <= 1024) CK(hb_memcpy(backend(), MT_hashes.back().data(), (const uint8_t *)dlev + off * 32, n * 32));
+            off += n;
+            if (n == 1) break;
+        }
+        CK(hb_free_stream(backend(), dlev));
+        if (trace) fprintf(stderr, "[hobbit trace] commit(%s, %zu) sharded over %d ranks: %.3f ms\n", fd.name.c_str(), (size_t)fd.size, world, wall_ms() - t_begin);
+        return;
+    }
+    CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
     // Every other name ("PC_layer", and the names read_stream_PC does not know, e.g. "lookup_witness_basic") is built from the stateless
     // synthetic default stream: every chunk is the same, so it is produced once, uploaded once and pushed from HBM.
     void *chunk = nullptr;

@@ -82,6 +82,15 @@ extern bool linear_time;
 // one-time setup: creates the GPU context (exits like the reference on failure: there is no CPU fallback)
 void init_backend(int device = 0);
 hb_ctx *backend();
+// Multi-GPU (one process per GPU of one box, include/hobbit_b200.h "multi-GPU").  Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR /
+// MASTER_PORT (what torchrun sets; HB_RDV_PORT overrides the rendezvous port, default MASTER_PORT + 29), creates the backend on device
+// LOCAL_RANK (HB_SHARE_GPU=1: all ranks on device 0 — single-GPU boxes, tests), exchanges the window blobs over a TCP store that rank 0
+// serves, and switches the provers to sharded mode.  Every rank must then run the same call sequence; all ranks obtain the same proof.
+// data_bytes: size of the window's data region (commit() shards a commitment only when its digests fit: 32 B per coefficient / world
+// + 256 B per leaf).  WORLD_SIZE unset or 1: plain init_backend.
+void dist_init_from_env(size_t data_bytes = (size_t)1 << 30);
+int dist_rank();
+int dist_world();
 
 std::vector<F> generate_randomness(int size);
 long long expander_init_store(long long n, int dep = 0);

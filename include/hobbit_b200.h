@@ -39,6 +39,9 @@ const char *hb_last_error(hb_ctx *ctx);
 int  hb_sync(hb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py reports the delta as gpu_launches) */
 uint64_t hb_launch_count(hb_ctx *ctx);
+/* FNV-1a digest of every value the provers of this context have read back from the GPU so far (round-polynomial sums, final table
+ * values): two runs with the same digest produced the same Fiat–Shamir transcript.  reset != 0 restarts it. */
+uint64_t hb_transcript_digest(hb_ctx *ctx, int reset);
 /* the CUDA stream (cudaStream_t) all work of this context is enqueued on — for event timing by the caller */
 void *hb_stream(hb_ctx *ctx);
 /* per-kernel timing: CUDA events around every launch on the context's stream.  enable(1) clears the records;

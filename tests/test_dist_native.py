@@ -152,7 +152,7 @@ def _prover_worker(rank, world, port, ret):
         before = ctx.dist_stats()["reductions"]
         got = fn()
         sharded = ctx.dist_stats()["reductions"] > before
-        if not sharded and not any(s in name for s in ("n=%d" % world, "mul_tree 1x")) and "n=16" not in name:
+        if not sharded and name != "sumcheck3 n=%d" % world:                          # a table of `world` entries cannot be sliced
             print("rank %d: %s did not run sharded" % (rank, name), flush=True)
             ok = False
         if not same(want, got):

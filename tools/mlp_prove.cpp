@@ -27,12 +27,17 @@ int main(int argc, char **argv) {
         layers.push_back(atoi(argv[i]));
     }
     if (layers.empty()) layers = {1024, 256, 256, 16};
-    init_backend(0);
+    // one process per GPU: RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT from the environment (tools/run_ranks.sh, torchrun);
+    // every rank evaluates the circuit (a millisecond on the GPU) and proves its share of every sumcheck and commitment
+    dist_init_from_env((size_t)3 << 29);
     int saved = dup(1); FILE *nul = fopen("/dev/null", "w");
     double best[6] = {1e9, 1e9, 1e9, 1e9, 1e9, 1e9}, ps = 0; size_t cs = 0;
+    unsigned long long transcript = 0, launches_last = 0;
     for (int rep = 0; rep <= reps; rep++) {                 // rep 0 = warm-up (tables, allocator)
         fflush(stdout); dup2(fileno(nul), 1);               // the reference-style printf chatter of the provers
         srand(1);
+        hb_transcript_digest(backend(), 1);
+        const unsigned long long l0 = hb_launch_count(backend());
         double t0 = now();
         if (aes_n >= 0 && sql) trace_generate_sql(1 << aes_n); else if (aes_n >= 0) trace_generate_aes(1 << aes_n); else trace_generate_mlp(layers);
         cs = trace_end();
@@ -64,16 +69,19 @@ int main(int argc, char **argv) {
         open(fdw, generate_randomness((int)std::log2((double)fdw.size)), MT, vt, ps);
         if (has_lookups) open(fdl, generate_randomness((int)std::log2((double)fdl.size)), MTl, vt, ps);
         double t5 = now();
+        transcript = hb_transcript_digest(backend(), 0); launches_last = hb_launch_count(backend()) - l0;
+        for (auto &lv : MT) if (lv.size() == 1) for (int q = 0; q < 32; q++) transcript = (transcript ^ ((const unsigned char *)&lv[0])[q]) * 0x100000001b3ULL;   // + the commitment root
         fflush(stdout); dup2(saved, 1);
         F rd = prods[0] * prods[1] * prods[2] * prods[7], wr = prods[4] * prods[5] * prods[6] * prods[3];
         if (rd != wr) { printf("memory consistency check FAILED\n"); return 1; }
         if (rep) { const double t[6] = {t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0}; for (int i = 0; i < 6; i++) best[i] = std::min(best[i], t[i]); }
     }
+    if (dist_rank() != 0) return 0;                          // every rank holds the same proof; rank 0 reports
     if (aes_n >= 0) printf("{\"workload\": \"%s prove_circuit (lookups), 2^%d %s", sql ? "SQL" : "AES", aes_n, sql ? "rows" : "blocks");
     else { printf("{\"workload\": \"MLP prove_circuit, layers"); for (int l : layers) printf(" %d", l); }
     printf(", circuit_size 2^%d, BUFFER_SPACE 2^%d\", \"evaluate_s\": %.5f, \"commit_s\": %.5f, \"mul_tree_s\": %.5f, \"gate_s\": %.5f, \"open_s\": %.5f, \"total_s\": %.5f, "
-           "\"ps_kb\": %.6f, \"gates_per_s\": %.1f, \"gpu_launches\": %llu}\n",
+           "\"ps_kb\": %.6f, \"gates_per_s\": %.1f, \"gpu_launches\": %llu, \"launches_per_proof\": %llu, \"n_gpus\": %d, \"transcript\": \"%016llx\", \"rng_next\": %ld}\n",
            (int)std::log2((double)cs), (int)std::log2((double)BUFFER_SPACE), best[0], best[1], best[2], best[3], best[4], best[5], ps, cs / best[5],
-           (unsigned long long)hb_launch_count(backend()));
+           (unsigned long long)hb_launch_count(backend()), (unsigned long long)launches_last, dist_world(), (unsigned long long)transcript, random());
     return 0;
 }
