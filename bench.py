@@ -14,9 +14,15 @@ A "step" is one whole commit of that polynomial.
     cpu_baseline : the unmodified reference (oracle/_ref, built from /root/reference) on a bounded sample
 
 `--impl reference` times the reference's own CPU implementation of the same call on the host cores.
-N > 1 (torchrun): ONE commitment of N*2^26 coefficients (32*N chunks of the same size) sharded over the ranks
-(hobbit_b200/dist.py: chunks by rank, inner leaf digests all_to_all by leaf range, subtree levels all_gather) -> weak
-scaling (fixed work per GPU); timing = max over ranks.
+N > 1 (torchrun): ONE commitment of N*2^26 coefficients (32*N chunks of the same size) sharded over the ranks behind the C ABI
+(hb_dist_commit_standard: chunks by rank, the encode kernel stores every inner leaf digest straight into the window of the rank that
+owns the leaf range over NVLink, subtree levels scattered to every rank) -> weak scaling (fixed work per GPU); timing = max over ranks.
+Outside the timed region the N > 1 run compares the sharded commitment with the single-GPU commitment of the same polynomial, level by
+level, and a sharded sumcheck proof with the single-GPU proof ("parity_check").
+
+"extras" (same JSON line, rank 0): the other BASELINE configurations, each run by the reference-free C++ tools through the host mirror
+(hobbit_b200/pc_prove, hobbit_b200/mlp_prove): config 1 test_PC(2^20, 4, 32) commit + open seconds, configs 3/4 MLP / AES / SQL prove
+seconds with ps_kb, and at N = 8 config 5 test_Elastic_PC(2^30, 2) commit + open with the stream in pinned host memory.
 """
 import argparse
 import ctypes
@@ -156,6 +162,56 @@ def run_reference(args, rank):
                           e2e={"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)))
 
 
+def host_mirror(local):
+    """libhobbit_host.so: the C++ mirror of the reference API; owns the libc-RNG-ordered generators (expander graphs) and ONE context."""
+    H = ctypes.CDLL(os.path.join(ROOT, "hobbit_b200", "libhobbit_host.so"))
+    H.hobbit_c_backend.restype = ctypes.c_void_p
+    H.hobbit_c_expander_init_store.restype = ctypes.c_longlong
+    return H, H.hobbit_c_backend(int(local))
+
+
+def run_tool(cmd, timeout=300):
+    """Runs one of the reference-free C++ tools and returns its JSON line (rank 0 prints it), or {"error": ...}."""
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if p.returncode or not lines:
+            return {"error": "rc=%d %s" % (p.returncode, (p.stdout + p.stderr)[-300:])}
+        return json.loads(lines[-1])
+    except Exception as e:                                   # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def extras(world, rank):
+    """The other BASELINE configurations through the host mirror (C++), outside every timed region of this script."""
+    pc, mlp = os.path.join(ROOT, "hobbit_b200", "pc_prove"), os.path.join(ROOT, "hobbit_b200", "mlp_prove")
+    env1 = dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK=os.environ.get("LOCAL_RANK", "0"))
+    out = {}
+    if world == 1:
+        def one(cmd):
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env1)
+            lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+            return json.loads(lines[-1]) if lines and not p.returncode else {"error": "rc=%d %s" % (p.returncode, (p.stdout + p.stderr)[-300:])}
+        out["config1_test_PC_2e20_K32"] = one([pc, "pc", "20", "32", "1"])
+        out["config3_MLP_pigeon_9_18_18_1_4_1024_256_256_16"] = one([mlp, "18", "1024", "256", "256", "16", "--reps", "3"])
+        out["config4_AES_pigeon_5_19_8_1"] = one([mlp, "19", "aes", "8", "--reps", "3"])
+        out["config4_SQL_pigeon_6_19_17_1"] = one([mlp, "19", "sql", "17", "--reps", "3"])
+        out["config5_test_Elastic_PC_2e28_pinned"] = one([pc, "elastic", "28", "20", "2", "--pinned", "--reps", "2"])
+    else:
+        # every rank of this job starts the same tool with its own RANK / LOCAL_RANK: the tools rendezvous among themselves (MASTER_PORT + 29)
+        logn = {2: 28, 4: 29, 8: 30}.get(world, 28)
+        r = run_tool([pc, "elastic", str(logn), "20", "2", "--pinned", "--reps", "2"])
+        if rank == 0:
+            out["config5_test_Elastic_PC_2e%d_pinned_%dgpus" % (logn, world)] = r
+        r = run_tool([mlp, "19", "sql", "17", "--reps", "2"])
+        if rank == 0:
+            out["config4_SQL_pigeon_6_19_17_1_%dgpus" % world] = r
+        r = run_tool([mlp, "19", "aes", "8", "--reps", "2"])
+        if rank == 0:
+            out["config4_AES_pigeon_5_19_8_1_%dgpus" % world] = r
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +220,7 @@ def main():
     ap.add_argument("--impl", default="hobbit_b200")
     ap.add_argument("--logn", type=int, default=LOGN, help="debug only: smaller polynomial (the reported workload is 2^26)")
     ap.add_argument("--cpu-chunks", type=int, default=4, help="chunks of the workload the CPU baseline is timed on")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations (C++ tools)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
 
@@ -173,7 +230,6 @@ def main():
 
     import torch
     import hobbit_b200
-    from helpers import Checker, srand
 
     if world > 1:
         import torch.distributed as dist
@@ -181,31 +237,35 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    ctx = hobbit_b200.Context(local)
+    # one context, owned by the host mirror: the expander graphs are drawn by the product's own generator (hobbit::expander_init_store,
+    # libc rand()/random() in the reference's call order) — nothing under oracle/ is loaded by this arm before the CPU baseline
+    H, handle = host_mirror(local)
+    ctx = hobbit_b200.Context.from_handle(handle)
     N = 1 << args.logn
     B = N // K
     trs = TRS if args.logn == LOGN else max(16, N // (K << 11))
+    ctypes.CDLL(None).srand(1)
+    cw = int(H.hobbit_c_expander_init_store(ctypes.c_longlong(trs)))
 
-    # expander graphs come from the HOST RNG in the reference's call order (expander_init_store); generated here with
-    # the oracle's graph generator purely as an input producer for the synthetic run
-    orc = Checker("orc")
-    srand(1)
-    orc.expander_init_store(trs)
-    cw = ctx.expander_set(trs, orc.expander_graphs(trs))
+    def gen_poly(r):
+        """generate_randomness-shaped synthetic input (utils.cpp:873-883: real-only values c + rand()), drawn on the device"""
+        g = torch.Generator(device="cuda"); g.manual_seed(1234 + r)
+        t = torch.zeros((N, 2), dtype=torch.int64, device="cuda")
+        t[:, 0] = torch.randint(0, 1 << 32, (N,), dtype=torch.int64, device="cuda", generator=g)
+        return t
 
     # N > 1: ONE commitment of N*world coefficients (K*world chunks of the same size) sharded over the ranks: rank g owns chunks
-    # [g*K, (g+1)*K) and the leaf range [g*B/world, (g+1)*B/world) (hobbit_b200/dist.py); N == 1: the plain C-ABI call.
+    # [g*K, (g+1)*K) and the leaf range [g*B/world, (g+1)*B/world); N == 1: the plain C-ABI call.
+    poly_dev = gen_poly(rank)
     poly_host = ctx.pinned((N, 2), np.uint64)
-    poly_host[:] = make_poly(N, 1234 + rank)
+    torch.from_numpy(poly_host.view(np.int64)).copy_(poly_dev)
     levels_host = ctx.pinned((2 * B - 1, 32), np.uint8)
-    poly_dev = torch.empty((N, 2), dtype=torch.int64, device="cuda")
     levels_dev = torch.empty(((2 * B - 1) * 32,), dtype=torch.uint8, device="cuda")
-    poly_dev.copy_(torch.from_numpy(poly_host.view(np.int64)))
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(ctx.stream())
 
     if world > 1:
-        ctx.dist_init_torch(K * world * (B // world) * 32 + 2 * B * 32 + 4096)
+        ctx.dist_init_torch(K * world * (B // world) * 32 + 2 * B * 32 + (1 << 20) + 3 * 16 * (1 << 22) * 0)
 
     def step_resident():
         if world > 1:
@@ -214,12 +274,12 @@ def main():
             ctx.commit_standard(poly_dev.data_ptr(), K, trs, 1, levels_out=levels_dev.data_ptr(), N=N)
 
     def step_e2e():
+        # host polynomial in (pinned), every Merkle level out to the host — on rank 0 (the caller that holds the commitment); the other
+        # ranks keep their copy of the tree in HBM
         if world > 1:
             ctx.dist_commit_standard(poly_host, K * world, B, trs, 1, levels_out=levels_host if rank == 0 else levels_dev.data_ptr())
         else:
             ctx.commit_standard(poly_host, K, trs, 1, levels_out=levels_host)
-
-    levels_host_t = torch.from_numpy(levels_host)
 
     def barrier():
         torch.cuda.synchronize()
@@ -234,8 +294,6 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             fn()
-        if world > 1:
-            torch.cuda.synchronize()          # the sharded step also runs torch/NCCL work on torch's streams
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -253,74 +311,125 @@ def main():
     while not sampler.rows and time.time() - t_wait < 5.0:     # nvidia-smi needs a moment to start streaming
         time.sleep(0.05)
     sampler.rows.clear()
-    ctx.profile(True)
-    ms, launches = timed(step_resident, args.steps)
-    prof = ctx.profile_report()
-    ctx.profile(False)
+    ms, launches = timed(step_resident, args.steps)            # headline: no per-launch events inside this region
     clocks = sampler.finish()
     for _ in range(max(1, args.warmup - 1)):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    # separate pass: CUDA events around every launch (on the library's stream) -> per-kernel launch times for the roofline
+    ctx.profile(True)
+    psteps = max(2, min(5, args.steps))
+    for _ in range(psteps):
+        step_resident()
+    prof = ctx.profile_report()
+    ctx.profile(False)
 
     value = world * args.steps * N / (ms * 1e-3)
     e2e_v = world * args.steps * N / (ms_e2e * 1e-3)
 
-    # roofline of the dominant kernel: expander encode fused with the Merkle–Damgård leaf update (one launch per chunk)
-    dom = max(prof.items(), key=lambda kv: kv[1]["total_ms"])
-    name, rec = dom
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------------------------
+    prof = {k: v for k, v in prof.items() if not k.startswith("dist_barrier")}
+    name, rec = max(prof.items(), key=lambda kv: kv[1]["total_ms"])
     per_launch_ms = rec["total_ms"] / rec["launches"]
-    # algorithmic bytes per coefficient for this kernel: read the RS-encoded rows (2 cells = 32 B),
-    # write the parity rows + zero tail (32 B), write the inner leaf digest (one 32 B digest per coefficient and chunk)
-    coeffs_per_launch = float(N) * args.steps / rec["launches"]
-    alg_bytes = {"encode_cols_kernel": 32 + 32 + 32.0, "ntt_tile_kernel": 16 + 32, "md_chain_kernel": 32.0}.get(name, 64.0) * coeffs_per_launch
+    coeffs_per_launch = float(N) * psteps / rec["launches"]
+    # algorithmic bytes per coefficient: encode = read the RS-encoded rows (32 B) + write the parity rows / zero tail (32 B)
+    # + write the inner leaf digest (32 B); NTT = 16 B in + 32 B out; chain = 32 B of inner digests
+    alg_bytes = {"encode_cols_kernel": 96.0, "ntt_tile_kernel": 48.0, "md_chain_kernel": 32.0}.get(name, 64.0) * coeffs_per_launch
     peak, how = peaks()
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")        # dram bytes per coefficient from the committed ncu --set full capture
-    if os.path.exists(tp):
-        tj = json.load(open(tp)).get(name)
-        if tj:
-            traffic = tj["dram_bytes_per_coefficient"] * coeffs_per_launch
-    kernel_share = {k: round(v["total_ms"] / sum(x["total_ms"] for x in prof.values()), 4) for k, v in prof.items()}
+    counts = {}
+    cp = os.path.join(ROOT, "profiles", "kernel_counts_r02.json")   # per-kernel ncu counters of this command (instructions, DRAM bytes), by kernel name
+    if os.path.exists(cp):
+        counts = json.load(open(cp)).get(name, {})
+    traffic = counts.get("dram_bytes_per_coefficient")
+    total_ms = sum(x["total_ms"] for x in prof.values())
     roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": how, "avg_launch_ms": per_launch_ms, "launches_timed": rec["launches"],
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_time_share": kernel_share,
-                "note": "integer-pipe-bound kernel (61-bit modular multiply-adds + BLAKE3 compressions, SURVEY §8d): the HBM fraction is low by "
-                        "construction; the ncu pipe utilisation is in profiles/",
-                # from the committed `ncu --set full` capture of this kernel (profiles/r01_summary.md), NOT measured in this run
-                "int_pipes_ncu": {"issue_slots_busy_pct": 63.5, "alu_pipe_pct": 58.0, "fma_heavy_pipe_pct": 59.6, "dram_pct_of_peak": 11.4,
-                                  "warp_instructions_per_coefficient": 2450087936 / float(1 << 25),
-                                  "source": "profiles/r01_summary.md (ncu --set full --clock-control none, one launch = 2^25 coefficients)"}}
-    # the binding roof of this kernel is instruction issue (4 warp-instructions per clock and SM): the ncu instruction count of the kernel
-    # (static for a given graph) over THIS run's launch time and SM clock
+                "traffic": traffic * coeffs_per_launch if traffic else None, "peak_source": how, "avg_launch_ms": per_launch_ms,
+                "launches_timed": rec["launches"], "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_time_share": {k: round(v["total_ms"] / total_ms, 4) for k, v in prof.items()},
+                "timing": "CUDA events around every launch on the library's stream, in a pass of %d steps separate from the headline region" % psteps}
+    # The BINDING roof of this kernel is not HBM: 61-bit modular multiply-adds and BLAKE3 are integer work and sm_100a has no 64-bit
+    # multiplier.  Measured here, on this GPU: the warp-instruction rates of the two integer pipes (hb_ubench_pipes) and, from the committed
+    # ncu counters of this kernel (by name), its instruction mix -> the time the pipes need at those measured rates.
     try:
-        sm_hz = float(clocks.get("sm_mhz") or 0) * 1e6
-        sms = torch.cuda.get_device_properties(0).multi_processor_count
-        if name == "encode_cols_kernel" and sm_hz > 0:
-            inst = roofline["int_pipes_ncu"]["warp_instructions_per_coefficient"] * coeffs_per_launch
-            roofline["issue"] = {"achieved_warp_inst_per_clk_per_sm": inst / (per_launch_ms * 1e-3 * sm_hz * sms), "peak": 4.0,
-                                 "frac": inst / (per_launch_ms * 1e-3 * sm_hz * sms) / 4.0,
-                                 "note": "instruction-issue roofline: ncu instruction count x live launch time; ALU-pipe roof (2 warp-inst/clk/SM) in profiles/"}
-    except Exception:
-        pass
+        pipes = ctx.ubench_pipes()
+        roofline["measured_pipe_rates"] = pipes
+        if counts.get("warp_inst_per_coefficient") and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            clk = per_launch_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sms                     # SM-cycles available during one launch
+            inst = counts["warp_inst_per_coefficient"] * coeffs_per_launch
+            roofline["binding"] = {"resource": "integer issue (IMAD.WIDE on the FMA-heavy pipe + ALU pipe)", "unit": "warp-inst/clk/SM",
+                                   "achieved": inst / clk, "peak": pipes["mix_1_wide_3_alu"], "frac": inst / clk / pipes["mix_1_wide_3_alu"],
+                                   "warp_instructions_per_launch": inst,
+                                   "source": "instruction count: profiles/kernel_counts_r02.json (ncu smsp__inst_executed.sum of this kernel); peak: "
+                                             "hb_ubench_pipes measured in this run (1 IMAD.WIDE : 3 ALU mix, the kernel's own ratio is in the file)"}
+    except Exception as e:                                   # noqa: BLE001
+        roofline["measured_pipe_rates"] = {"error": repr(e)}
+
+    # ---- N > 1: sharded vs single-GPU, outside the timed region --------------------------------------------------------------------
+    parity = None
+    if world > 1:
+        parity = {}
+        ctx.dist_commit_standard(poly_dev.data_ptr(), K * world, B, trs, 1, levels_out=levels_dev.data_ptr())
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            # rank 0 regenerates every rank's polynomial (same device generator, same seeds) and commits the whole thing on ONE GPU
+            whole = torch.cat([poly_dev] + [gen_poly(r) for r in range(1, world)], dim=0)
+            single = torch.empty(((2 * B - 1) * 32,), dtype=torch.uint8, device="cuda")
+            ctx.commit_standard(whole.data_ptr(), K * world, trs, 1, levels_out=single.data_ptr(), N=N * world)
+            ok[0] = int(torch.equal(single, levels_dev))
+            del whole, single
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity["commit"] = bool(ok.item())
+        parity["commit_what"] = "every Merkle level (2^%d - 1 digests) of the sharded 2^%d-coefficient commitment == hb_commit_standard of the same polynomial on one GPU" % (args.logn - 4, args.logn + int(np.log2(world)))
+        # one sharded sumcheck proof (3-product, 2^22-entry tables, identical on every rank) against the single-GPU proof
+        g = torch.Generator(device="cuda"); g.manual_seed(99)
+        tabs = [torch.randint(0, (1 << 61) - 1, (1 << 22, 2), dtype=torch.int64, device="cuda", generator=g) for _ in range(3)]
+        pr = np.array([[5, 7]], dtype=np.uint64)
+        dv = [hobbit_b200.DevF.from_torch(t) for t in tabs]
+        ctx.dist_shard(False)
+        want, _ = ctx.sumcheck3(dv[0], dv[1], dv[2], pr)
+        ctx.dist_shard(True)
+        r0 = ctx.dist_stats()["reductions"]
+        got, _ = ctx.sumcheck3(dv[0], dv[1], dv[2], pr)
+        ctx.dist_shard(False)
+        ok[0] = int(np.array_equal(want, got) and ctx.dist_stats()["reductions"] > r0)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity["sumcheck"] = bool(ok.item())
+        parity["sumcheck_what"] = "_generate_3product_sumcheck_proof over 2^22-entry tables sharded by hypercube prefix == the single-GPU proof, all 114 field elements"
+        del tabs
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u64 (F_p^2, p=2^61-1) + u32 BLAKE3", "data": "synthetic",
            "config": {"workload": "Our_PC commit_standard N=2^%d K=%d trs=%d linear_time (RS rows + Orion expander columns) + BLAKE3 Merkle (test_PC option 4 commit)" % (args.logn, K, trs),
                       "codeword_len": cw, "l2": "inputs larger than L2 (1 GiB polynomial, 4 GiB tensor per step)",
-                      "multi_gpu": ("ONE commitment of 2^%d x %d coefficients: chunks sharded by rank, inner leaf digests exchanged by leaf range (NCCL all_to_all), "
-                                    "subtree levels all_gathered" % (args.logn, world)) if world > 1 else "single GPU"},
+                      "multi_gpu": ("ONE commitment of 2^%d x %d coefficients behind the C ABI (hb_dist_commit_standard): chunks sharded by rank, inner leaf digests stored by the "
+                                    "encode kernel into the owner rank's window over NVLink, subtrees scattered to every rank" % (args.logn, world)) if world > 1 else "single GPU"},
            "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(poly_host.nbytes),
-                   "d2h_bytes_per_step": int(levels_host.nbytes)},
+                   "d2h_bytes_per_step": int(levels_host.nbytes),
+                   "note": "pinned host polynomial in on every rank, every Merkle level out on rank 0" if world > 1 else "pinned host polynomial in, every Merkle level out"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if parity is not None:
+        out["parity_check"] = parity
+    # free the big buffers before the C++ tools run on the same GPUs
+    del poly_dev, levels_dev
+    torch.cuda.empty_cache()
+    if world > 1:
+        ctx.dist_disconnect()
+    if not args.no_extras:
+        if world > 1:
+            dist.barrier()
+        ex = extras(world, rank)
+        if rank == 0:
+            out["extras"] = ex
     if rank == 0:
         if world == 1:
             out["cpu_baseline"] = cpu_baseline(args.cpu_chunks, B, trs)
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
 
 
 if __name__ == "__main__":

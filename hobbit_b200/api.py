@@ -119,6 +119,11 @@ class Context:
     def transcript_digest(self, reset=False):
         return int(self.lib.hb_transcript_digest(self.h, 1 if reset else 0))
 
+    def ubench_pipes(self):
+        out = (ctypes.c_double * 3)()
+        self._ck(self.lib.hb_ubench_pipes(self.h, out))
+        return {"imad_wide": out[0], "alu": out[1], "mix_1_wide_3_alu": out[2], "unit": "warp-inst/clk/SM"}
+
     def profile(self, on=True):
         self._ck(self.lib.hb_profile_enable(self.h, 1 if on else 0))
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhobbit_b200.so")
-SOURCES = ["ntt.cu", "encode.cu", "merkle.cu", "commit.cu", "sumcheck.cu", "open.cu", "trace.cu", "dist.cu"]
+SOURCES = ["ntt.cu", "encode.cu", "merkle.cu", "commit.cu", "sumcheck.cu", "open.cu", "trace.cu", "dist.cu", "ubench.cu"]
 HEADERS = ["common.cuh", "field.cuh", "blake3.cuh", "reduce.cuh", os.path.join("..", "..", "include", "hobbit_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -53,14 +53,15 @@ def build_library(force=False, verbose=False):
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode:
             raise RuntimeError("host library build failed:\n%s\n%s" % (p.stdout, p.stderr))
-    # reference-free example / bench binary (tools/mlp_prove.cpp)
-    tool_src = os.path.join(HERE, "..", "tools", "mlp_prove.cpp")
-    tool_bin = os.path.join(HERE, "mlp_prove")
-    if os.path.exists(tool_src) and (force or _newer(tool_src, tool_bin) or _newer(host_lib, tool_bin)):
-        cmd = ["g++", "-O2", "-std=c++17", "-o", tool_bin, tool_src, "-L" + HERE, "-lhobbit_host", "-lhobbit_b200", "-Wl,-rpath,$ORIGIN"]
-        p = subprocess.run(cmd, capture_output=True, text=True)
-        if p.returncode:
-            raise RuntimeError("mlp_prove build failed:\n%s\n%s" % (p.stdout, p.stderr))
+    # reference-free example / bench binaries (tools/mlp_prove.cpp: the circuit proofs; tools/pc_prove.cpp: test_PC / test_Elastic_PC)
+    for tool in ("mlp_prove", "pc_prove"):
+        tool_src = os.path.join(HERE, "..", "tools", tool + ".cpp")
+        tool_bin = os.path.join(HERE, tool)
+        if os.path.exists(tool_src) and (force or _newer(tool_src, tool_bin) or _newer(host_lib, tool_bin)):
+            cmd = ["g++", "-O2", "-std=c++17", "-o", tool_bin, tool_src, "-L" + HERE, "-lhobbit_host", "-lhobbit_b200", "-Wl,-rpath,$ORIGIN"]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode:
+                raise RuntimeError("%s build failed:\n%s\n%s" % (tool, p.stdout, p.stderr))
     return LIB, log
 
 

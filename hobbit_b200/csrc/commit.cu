@@ -217,8 +217,7 @@ static int stager_consumed(hb_ctx *ctx, ChunkStager &st, int slot) { HB_CHECK(ct
 
 static void elastic_free(hb_ctx *ctx) {
     ElasticState &el = ctx->el;
-    for (int i = 0; i < 3; i++) if (el.park[i]) cudaFreeAsync(el.park[i], ctx->stream);
-    if (el.tensor) cudaFreeAsync(el.tensor, ctx->stream);
+    if (el.park[0]) cudaFreeAsync(el.park[0], ctx->stream);
     stager_free(ctx, el.stg);
     if (el.leaves) cudaFreeAsync(el.leaves, ctx->stream);
     el = ElasticState();
@@ -619,8 +618,9 @@ extern "C" int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time)
     ElasticState &el = ctx->el;
     el.B = B; el.trs = trs; el.lin = linear_time; el.chunk_idx = 0;
     // stream-ordered pool allocations: a commit per call must not pay cudaMalloc/cudaFree (milliseconds each)
-    for (int i = 0; i < 3; i++) HB_CHECK(ctx, cudaMallocAsync(&el.park[i], 4 * B * sizeof(F), ctx->stream));
-    HB_CHECK(ctx, cudaMallocAsync(&el.tensor, 4 * B * sizeof(F), ctx->stream));
+    // one allocation: park[0..2] and the current tensor are contiguous (a group of 4 encoded chunks, as md_inner_stream4 wants it)
+    HB_CHECK(ctx, cudaMallocAsync(&el.park[0], 16 * B * sizeof(F), ctx->stream));
+    el.park[1] = el.park[0] + 4 * B; el.park[2] = el.park[1] + 4 * B; el.tensor = el.park[2] + 4 * B;
     HB_TRY(stager_init(ctx, el.stg, B));
     HB_CHECK(ctx, cudaMallocAsync(&el.leaves, (8 * B - 1) * 32, ctx->stream));
     HB_CHECK(ctx, cudaMemsetAsync(el.leaves, 0, 4 * B * 32, ctx->stream));   // Elastic_PC.cpp:195-199
@@ -641,14 +641,36 @@ extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) {
     // linear, so encoding the zero chunk yields exactly that all-zero tensor: no test, no host round trip, same bits.
     HB_TRY(tensorcode_dev(ctx, src, B, el.trs, el.lin, T, 1, nullptr));
     if (stg_slot >= 0) HB_TRY(stager_consumed(ctx, el.stg, stg_slot));
-    if (slot == 3) HB_TRY(md_leaves_stream4_dev(ctx, el.park[0], el.park[1], el.park[2], el.tensor, 4 * B, el.leaves));
+    if (slot == 3) {
+        if (el.dist_groups_total) {                        // sharded: inner digests of this group -> the owner ranks' windows (NVLink stores)
+            InnerLayout lay = el.dist_lay; lay.chunk0 += el.chunk_idx / 4;
+            HB_TRY(md_inner_stream4_dev(ctx, el.park[0], 4 * B, 1, ctx->dist.win + kDistCtrlBytes, lay));
+        } else HB_TRY(md_leaves_stream4_dev(ctx, el.park[0], el.park[1], el.park[2], el.tensor, 4 * B, el.leaves));
+    }
     el.chunk_idx++;
+    return 0;
+}
+
+// Streaming form of the sharded Elastic_PC commit: begin, then hb_elastic_push for this rank's 4 * groups_total / world chunks (its
+// consecutive groups, in order), then hb_elastic_finish / hb_elastic_finish_levels as usual — every rank receives the whole tree.
+extern "C" int hb_dist_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, size_t groups_total) {
+    HB_TRY(hb_elastic_begin(ctx, B, trs, linear_time));
+    if (ctx->dist.world <= 1) return 0;
+    ElasticState &el = ctx->el;
+    HB_TRY(sharded_begin(ctx, groups_total, 4 * B, &el.dist_lay));
+    el.dist_groups_total = groups_total;
     return 0;
 }
 
 extern "C" int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out) {
     ElasticState &el = ctx->el;
     if (!el.active) HB_FAIL(ctx, "hb_elastic_finish: no commit in progress");
+    if (el.dist_groups_total) {
+        if (el.chunk_idx * (size_t)ctx->dist.world != 4 * el.dist_groups_total) HB_FAIL(ctx, "hb_elastic_finish: this rank must push exactly its 4 * groups_total / world chunks");
+        int rc = sharded_finish(ctx, el.dist_groups_total, 4 * el.B, levels_out);
+        elastic_free(ctx);
+        return rc;
+    }
     HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
     HB_CHECK(ctx, cudaMemcpyAsync(levels_out, el.leaves, (8 * el.B - 1) * 32, cudaMemcpyDefault, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -662,12 +684,17 @@ extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs,
     ElasticState &el = ctx->el;
     if (!el.active) HB_FAIL(ctx, "hb_elastic_finish_levels: no commit in progress");
     if (nlevels != ilog2(4 * el.B) + 1) HB_FAIL(ctx, "hb_elastic_finish_levels: expected log2(4B)+1 levels");
-    HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
+    const uint8_t *tree = el.leaves;
+    if (el.dist_groups_total) {
+        if (el.chunk_idx * (size_t)ctx->dist.world != 4 * el.dist_groups_total) HB_FAIL(ctx, "hb_elastic_finish_levels: this rank must push exactly its 4 * groups_total / world chunks");
+        HB_TRY(sharded_finish(ctx, el.dist_groups_total, 4 * el.B, nullptr));
+        tree = sharded_tree(ctx, el.dist_groups_total, 4 * el.B);
+    } else HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
     size_t off = 0, n = 4 * el.B;
     for (int l = 0; l < nlevels; l++, n /= 2) {
         if (!level_ptrs[l]) { off += n; continue; }
-        if (n * 32 >= kPageableDirect && !is_device_ptr(level_ptrs[l]) && !is_pinned_host_ptr(level_ptrs[l])) { HB_TRY(copy_to_host(ctx, level_ptrs[l], el.leaves + off * 32, n * 32, ctx->stream)); }
-        else HB_CHECK(ctx, cudaMemcpyAsync(level_ptrs[l], el.leaves + off * 32, n * 32, cudaMemcpyDefault, ctx->stream));
+        if (n * 32 >= kPageableDirect && !is_device_ptr(level_ptrs[l]) && !is_pinned_host_ptr(level_ptrs[l])) { HB_TRY(copy_to_host(ctx, level_ptrs[l], tree + off * 32, n * 32, ctx->stream)); }
+        else HB_CHECK(ctx, cudaMemcpyAsync(level_ptrs[l], tree + off * 32, n * 32, cudaMemcpyDefault, ctx->stream));
         off += n;
     }
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -704,6 +731,26 @@ extern "C" int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int linear_
     eo.active = true;
     return 0;
 }
+// Multi-GPU: the next pushes are chunks [first, first + nchunks) of `total`; the reply array then has queries * total entries with
+// reply[q * total + first + i] filled by this pass and zeros elsewhere, so a field all-reduce over the ranks assembles it.
+extern "C" int hb_elastic_open_range(hb_ctx *ctx, size_t first, size_t total) {
+    ElasticOpen &eo = ctx->eo;
+    if (!eo.active || eo.idx || first + eo.nchunks > total) HB_FAIL(ctx, "hb_elastic_open_range: call right after hb_elastic_open_begin with a valid range");
+    if (eo.queries) {
+        void *old = eo.buf;
+        const size_t B = eo.B, bytes = (B + 4 * B + eo.queries * total) * sizeof(F) + 2 * eo.queries * sizeof(uint32_t);
+        uint32_t *oc = eo.col;                                               // the queries were uploaded into the old buffer: move them
+        void *nb; HB_CHECK(ctx, cudaMallocAsync(&nb, bytes, ctx->stream));
+        F *agg = (F *)nb, *tensor = agg + B, *reply = tensor + 4 * B; uint32_t *col = (uint32_t *)(reply + eo.queries * total);
+        HB_CHECK(ctx, cudaMemcpyAsync(col, oc, 2 * eo.queries * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        HB_CHECK(ctx, cudaMemsetAsync(agg, 0, B * sizeof(F), ctx->stream));
+        HB_CHECK(ctx, cudaMemsetAsync(reply, 0, eo.queries * total * sizeof(F), ctx->stream));
+        cudaFreeAsync(old, ctx->stream);
+        eo.buf = nb; eo.agg = agg; eo.tensor = tensor; eo.reply = reply; eo.col = col; eo.row = col + eo.queries;
+    }
+    eo.chunk_first = first; eo.chunk_total = total;
+    return 0;
+}
 extern "C" int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *beta_i) {
     ElasticOpen &eo = ctx->eo;
     if (!eo.active || eo.idx >= eo.nchunks) HB_FAIL(ctx, "hb_elastic_open_push: no open in progress / too many chunks");
@@ -717,7 +764,7 @@ extern "C" int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *
     HB_TRY(tensorcode_dev(ctx, src, B, eo.trs, eo.lin, eo.tensor, 1, nullptr));
     if (stg_slot >= 0) HB_TRY(stager_consumed(ctx, eo.stg, stg_slot));
     if (eo.queries) HB_LAUNCH(ctx, reply_gather_kernel, (unsigned)((eo.queries + 255) / 256), 256, 0, eo.tensor, 2 * B / eo.trs, eo.col, eo.row,
-                              eo.queries, eo.nchunks, eo.idx, eo.reply);
+                              eo.queries, eo.chunk_total ? eo.chunk_total : eo.nchunks, eo.chunk_first + eo.idx, eo.reply);
     eo.idx++;
     return 0;
 }
@@ -725,7 +772,7 @@ extern "C" int hb_elastic_open_finish(hb_ctx *ctx, hb_F *agg_out, hb_F *reply_ou
     ElasticOpen &eo = ctx->eo;
     if (!eo.active) HB_FAIL(ctx, "hb_elastic_open_finish: no open in progress");
     HB_CHECK(ctx, cudaMemcpyAsync(agg_out, eo.agg, eo.B * sizeof(F), cudaMemcpyDefault, ctx->stream));
-    if (eo.queries) HB_CHECK(ctx, cudaMemcpyAsync(reply_out, eo.reply, eo.queries * eo.nchunks * sizeof(F), cudaMemcpyDefault, ctx->stream));
+    if (eo.queries) HB_CHECK(ctx, cudaMemcpyAsync(reply_out, eo.reply, eo.queries * (eo.chunk_total ? eo.chunk_total : eo.nchunks) * sizeof(F), cudaMemcpyDefault, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(eo.buf, ctx->stream);
     stager_free(ctx, eo.stg);

@@ -90,12 +90,16 @@ struct ElasticState {
     ChunkStager stg;                            // staging for host chunks
     uint8_t *leaves = nullptr;                  // (2*4B-1)*32
     int *nz_flag = nullptr;
+    // multi-GPU streaming commit (hb_dist_elastic_begin): this rank pushes its groups_total/world consecutive groups; the four encoded
+    // chunks of a group are contiguous (park[0..2], tensor) and their inner digests go straight to the owner ranks
+    size_t dist_groups_total = 0; InnerLayout dist_lay;
 };
 
 struct ElasticOpen {
     bool active = false;
     size_t B = 0, queries = 0, nchunks = 0, idx = 0; int trs = 0, lin = 0;
     void *buf = nullptr; F *agg = nullptr, *tensor = nullptr, *reply = nullptr; uint32_t *col = nullptr, *row = nullptr;
+    size_t chunk_first = 0, chunk_total = 0;    // this pass covers chunks [chunk_first, chunk_first + nchunks) of chunk_total (multi-GPU: a rank's chunk range)
     ChunkStager stg;
 };
 
@@ -122,6 +126,10 @@ int dist_barrier_dev(hb_ctx *ctx);                                   // cross-ra
 // every rank contributes `cnt` leading entries of each of its nt tables; out_dev: nt small tables of cnt * world entries (rank order)
 int dist_gather_small(hb_ctx *ctx, const F *const *tabs, int nt, int cnt, F *out_dev);
 int dist_allreduce_vec(hb_ctx *ctx, F *vec_dev, size_t n);           // field sum over the ranks, in place, through the data region
+// the two halves of a sharded commitment (see dist.cu) and the global tree it leaves in the window
+int sharded_begin(hb_ctx *ctx, size_t units_total, size_t leaves, InnerLayout *lay_out);
+int sharded_finish(hb_ctx *ctx, size_t units_total, size_t leaves, uint8_t *levels_out);
+const uint8_t *sharded_tree(hb_ctx *ctx, size_t units_total, size_t leaves);
 
 }  // namespace hb
 

@@ -226,7 +226,8 @@ extern "C" int hb_dist_allreduce(hb_ctx *ctx, hb_F *vec, size_t n) {
 // ---- sharded commitments ------------------------------------------------------------------------------------------------------------
 // units: `units_total` chunks (commit_standard) or groups of 4 chunks (Elastic_PC) in the global order, rank g owns the contiguous range
 // [g * units/G, (g+1) * units/G) for the chunk-independent part and the leaf range [g * leaves/G, (g+1) * leaves/G) for the chain + subtree.
-static int sharded_commit(hb_ctx *ctx, const hb_F *local, size_t units_total, size_t leaves, size_t B, int trs, int lin, bool elastic, uint8_t *levels_out) {
+// first half: checks, barrier, and the layout that sends every inner digest to the rank owning its leaf
+int hb::sharded_begin(hb_ctx *ctx, size_t units_total, size_t leaves, InnerLayout *lay_out) {
     DistState &d = ctx->dist;
     const size_t G = d.world;
     if (units_total % G || leaves % G) HB_FAIL(ctx, "sharded commit: units and leaves must split evenly over the ranks");
@@ -236,12 +237,18 @@ static int sharded_commit(hb_ctx *ctx, const hb_F *local, size_t units_total, si
         ctx->err = "sharded commit: window too small, need " + std::to_string(recv_bytes + tree_bytes) + " data bytes (hb_dist_local_info)";
         return 2;
     }
-    const size_t recv_off = kDistCtrlBytes, tree_off = kDistCtrlBytes + recv_bytes;
     HB_TRY(dist_barrier_dev(ctx));                                        // every rank is done with the window contents of the previous call
     InnerLayout lay; lay.part_leaves = Lp; lay.chunks_total = units_total; lay.chunk0 = (size_t)d.rank * ul;
-    for (size_t h = 0; h < G; h++) lay.peer[h] = d.peer[h] + recv_off;
-    if (elastic) HB_TRY(elastic_encode_groups_impl(ctx, local, ul, B, trs, lin, d.win + recv_off, lay));
-    else HB_TRY(commit_encode_chunks_impl(ctx, local, ul, B, trs, lin, d.win + recv_off, lay, 0, ul));
+    for (size_t h = 0; h < G; h++) lay.peer[h] = d.peer[h] + kDistCtrlBytes;
+    *lay_out = lay;
+    return 0;
+}
+// second half: chain of my leaf range over all units, my subtree, scatter to every rank, top levels; levels_out may be NULL
+int hb::sharded_finish(hb_ctx *ctx, size_t units_total, size_t leaves, uint8_t *levels_out) {
+    DistState &d = ctx->dist;
+    const size_t G = d.world, Lp = leaves / G;
+    const size_t recv_bytes = (units_total * Lp * 32 + 255) & ~(size_t)255, tree_bytes = (2 * leaves - 1) * 32;
+    const size_t recv_off = kDistCtrlBytes, tree_off = kDistCtrlBytes + recv_bytes;
     HB_TRY(dist_barrier_dev(ctx));                                        // every rank's digests of MY leaf range have landed
     uint8_t *sub; HB_CHECK(ctx, cudaMallocAsync(&sub, (2 * Lp - 1) * 32, ctx->stream));
     HB_CHECK(ctx, cudaMemsetAsync(sub, 0, Lp * 32, ctx->stream));         // the chain starts from all-zero digests
@@ -264,6 +271,20 @@ static int sharded_commit(hb_ctx *ctx, const hb_F *local, size_t units_total, si
     }
     HB_TRY(check_peer_error(ctx));                                        // synchronises the stream
     return 0;
+}
+const uint8_t *hb::sharded_tree(hb_ctx *ctx, size_t units_total, size_t leaves) {
+    const size_t Lp = leaves / ctx->dist.world;
+    return ctx->dist.win + kDistCtrlBytes + ((units_total * Lp * 32 + 255) & ~(size_t)255);
+}
+
+static int sharded_commit(hb_ctx *ctx, const hb_F *local, size_t units_total, size_t leaves, size_t B, int trs, int lin, bool elastic, uint8_t *levels_out) {
+    DistState &d = ctx->dist;
+    InnerLayout lay;
+    HB_TRY(sharded_begin(ctx, units_total, leaves, &lay));
+    const size_t ul = units_total / d.world;
+    if (elastic) HB_TRY(elastic_encode_groups_impl(ctx, local, ul, B, trs, lin, d.win + kDistCtrlBytes, lay));
+    else HB_TRY(commit_encode_chunks_impl(ctx, local, ul, B, trs, lin, d.win + kDistCtrlBytes, lay, 0, ul));
+    return sharded_finish(ctx, units_total, leaves, levels_out);
 }
 
 extern "C" int hb_dist_commit_standard(hb_ctx *ctx, const hb_F *poly_local, size_t K_total, size_t B, int trs, int linear_time, uint8_t *levels_out) {

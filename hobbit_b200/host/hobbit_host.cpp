@@ -22,6 +22,7 @@ bool linear_time = false;
 bool materialize_tensor = false;
 bool commit_levels_on_host = true;
 bool open_reuses_committed_poly = false;
+bool stream_in_pinned_host = false;
 static size_t committed_poly_size = 0;
 
 static hb_ctx *g_ctx = nullptr;
@@ -38,7 +39,7 @@ void init_backend(int device) {
 hb_ctx *backend() { if (!g_ctx) init_backend(0); return g_ctx; }
 
 // ---- multi-GPU bootstrap: a one-shot TCP all-gather of the 256-byte window blobs (rank 0 serves) ----------------------------------
-static size_t g_dist_data_bytes = 0;
+size_t g_dist_data_bytes = 0;
 static bool xfer(int fd, void *buf, size_t n, bool send_it) {
     char *p = (char *)buf;
     while (n) {
@@ -328,18 +329,30 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
         if (trace) fprintf(stderr, "[hobbit trace] commit(%s, %zu) sharded over %d ranks: %.3f ms\n", fd.name.c_str(), (size_t)fd.size, world, wall_ms() - t_begin);
         return;
     }
-    CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
+    // a stream that is produced chunk by chunk (not resident) is sharded the same way through the streaming form: this rank pushes only
+    // the chunks of its groups
+    const bool shard_stream = world > 1 && !res && fd.size % (4 * BUFFER_SPACE) == 0 && groups % world == 0 && (4 * BUFFER_SPACE) % world == 0 &&
+                              32 * (fd.size / world + 8 * BUFFER_SPACE) + 4096 <= g_dist_data_bytes;
+    if (shard_stream) CK(hb_dist_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0, groups));
+    else CK(hb_elastic_begin(backend(), BUFFER_SPACE, tensor_row_size, linear_time ? 1 : 0));
     // Every other name ("PC_layer", and the names read_stream_PC does not know, e.g. "lookup_witness_basic") is built from the stateless
     // synthetic default stream: every chunk is the same, so it is produced once, uploaded once and pushed from HBM.
-    void *chunk = nullptr;
+    // hobbit::stream_in_pinned_host: the chunk lives in PINNED HOST memory and every push crosses PCIe (double-buffered against the encode
+    // of the previous chunk) — what a witness stream that does not fit HBM looks like (BASELINE config 5).
+    void *chunk = nullptr; bool chunk_pinned = false;
     if (!res) {
         read_stream_PC(fd, buff.data(), (int)BUFFER_SPACE);
-        CK(hb_malloc_stream(backend(), &chunk, BUFFER_SPACE * sizeof(F)));
-        CK(hb_memcpy(backend(), chunk, buff.data(), BUFFER_SPACE * sizeof(F)));
+        if (stream_in_pinned_host) { CK(hb_malloc_pinned(backend(), &chunk, BUFFER_SPACE * sizeof(F))); memcpy(chunk, buff.data(), BUFFER_SPACE * sizeof(F)); chunk_pinned = true; }
+        else {
+            CK(hb_malloc_stream(backend(), &chunk, BUFFER_SPACE * sizeof(F)));
+            CK(hb_memcpy(backend(), chunk, buff.data(), BUFFER_SPACE * sizeof(F)));
+        }
     }
-    for (size_t i = 0; i < fd.size / BUFFER_SPACE; i++)
+    const size_t nchunks = fd.size / BUFFER_SPACE, c0 = shard_stream ? (size_t)dist_rank() * (nchunks / world) : 0, c1 = shard_stream ? c0 + nchunks / world : nchunks;
+    for (size_t i = c0; i < c1; i++)
         CK(hb_elastic_push(backend(), res ? (const hb_F *)(res + i * BUFFER_SPACE) : (const hb_F *)chunk));
-    if (chunk) CK(hb_free_stream(backend(), chunk));
+    if (chunk_pinned) { CK(hb_sync(backend())); CK(hb_free_pinned(backend(), chunk)); }
+    else if (chunk) CK(hb_free_stream(backend(), chunk));
     const double t_pushed = trace ? wall_ms() : 0;
     // every level goes straight from HBM into the caller's MT_hashes[l] (no intermediate flat copy of the 8B digests on the host)
     MT_hashes.clear();

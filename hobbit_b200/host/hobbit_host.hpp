@@ -116,6 +116,11 @@ extern bool commit_levels_on_host;
 // `poly` again — the caller asserts that `poly` still is that polynomial, unmodified.  Default false: the library never infers the
 // identity of a host buffer from its address.
 extern bool open_reuses_committed_poly;
+// true: streams that are produced chunk by chunk (everything that is not a resident circuit stream) are pushed from PINNED HOST memory, one
+// PCIe transfer per chunk, double-buffered against the encode — the witness never has to fit HBM (BASELINE config 5).  Default false: the
+// synthetic chunk is uploaded once and pushed from HBM.
+extern bool stream_in_pinned_host;
+extern size_t g_dist_data_bytes;               // data bytes of this rank's multi-GPU window (0: single GPU)
 void commit_standard(std::vector<F> &poly, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes,
                      std::vector<std::vector<std::vector<F>>> &_tensor, int K);
 // The data-parallel front half of open_standard (Our_PC.cpp:604-660): beta = eq(x1), aggregate, the rand()-drawn

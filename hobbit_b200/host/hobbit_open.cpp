@@ -621,20 +621,46 @@ void open(stream_descriptor fd, std::vector<F> x, std::vector<std::vector<_hash>
         col[i] = (uint32_t)I[i][0]; row[i] = (uint32_t)I[i][1];
     }
     // aggregate (:316-333) and compute_aggregation_reply (:487-533) read the stream twice in the reference; here ONE pass feeds both
-    DV agg(B), reply((size_t)queries * K);
+    // Multi-GPU: the stream pass is sharded by chunk range — aggregate and replies are sums / independent cells over the chunks
+    // (Elastic_PC.cpp:316-333, 487-533), so every rank handles K / world chunks and one field all-reduce over NVLink assembles the
+    // aggregate (+ the count of non-zero chunks) and the replies on every rank; the recursion below then runs on every rank.
+    const int world = dist_world();
+    const bool shard = world > 1 && K % world == 0 && ((size_t)queries * K + B + 1) * sizeof(F) * world + 4096 <= g_dist_data_bytes;
+    const size_t c0 = shard ? (size_t)dist_rank() * (K / world) : 0, c1 = shard ? c0 + K / world : K;
+    DV agg(B + 1), reply((size_t)queries * K);
     size_t nonzero_chunks = 0;
     {
         Trace t("  stream pass (aggregate + replies)");
-        CK(hb_elastic_open_begin(backend(), B, (int)trs, linear_time ? 1 : 0, col.data(), row.data(), (size_t)queries, K));
+        CK(hb_elastic_open_begin(backend(), B, (int)trs, linear_time ? 1 : 0, col.data(), row.data(), (size_t)queries, c1 - c0));
+        if (shard) CK(hb_elastic_open_range(backend(), c0, K));
         std::vector<F> buff;
         reset_stream(fd);
-        for (size_t i = 0; i < K; i++) {
-            const F *chunk = stream_chunk(fd, i, B, buff);
+        // the stateless synthetic default stream (read_stream's fall-through branch) yields the same chunk every time: produce it once.
+        // stream_in_pinned_host: it sits in pinned host memory and every push crosses PCIe (double-buffered, see hb_elastic_open_push);
+        // otherwise it is uploaded once and pushed from HBM.
+        void *pinned = nullptr; DV synth;
+        const F *fixed = nullptr;
+        if (!resident_stream(fd)) {
+            const F *c = stream_chunk(fd, 0, B, buff);
+            if (stream_in_pinned_host) { CK(hb_malloc_pinned(backend(), &pinned, B * sizeof(F))); memcpy(pinned, c, B * sizeof(F)); fixed = (const F *)pinned; }
+            else { synth = DV(B); CK(hb_memcpy(backend(), synth.p, c, B * sizeof(F))); fixed = synth.p; }
+        }
+        for (size_t i = c0; i < c1; i++) {
+            const F *chunk = fixed ? fixed : stream_chunk(fd, i, B, buff);
             int nz = 0; CK(hb_any_nonzero(backend(), abi(chunk), B, &nz));
             nonzero_chunks += nz ? 1 : 0;
             CK(hb_elastic_open_push(backend(), abi(chunk), abi(&beta[i])));
         }
         CK(hb_elastic_open_finish(backend(), abi(agg.p), abi(reply.p)));
+        if (pinned) { CK(hb_sync(backend())); CK(hb_free_pinned(backend(), pinned)); }
+        if (shard) {
+            F cnt((long long)nonzero_chunks);
+            CK(hb_memcpy(backend(), agg.p + B, &cnt, sizeof(F)));
+            CK(hb_dist_allreduce(backend(), abi(agg.p), B + 1));
+            CK(hb_dist_allreduce(backend(), abi(reply.p), (size_t)queries * K));
+            CK(hb_memcpy(backend(), &cnt, agg.p + B, sizeof(F)));
+            nonzero_chunks = (size_t)cnt.real;
+        }
     }
     open_tail(agg.p, B, trs, nonzero_chunks, Commitment_MT[0].size(), (int)Commitment_MT.size(), vt, ps);
     for (auto &lv : Commitment_MT) { lv.clear(); std::vector<_hash>(lv).swap(lv); }                 // :693-698: the caller's tree is freed

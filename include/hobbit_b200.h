@@ -46,6 +46,10 @@ uint64_t hb_transcript_digest(hb_ctx *ctx, int reset);
 void *hb_stream(hb_ctx *ctx);
 /* per-kernel timing: CUDA events around every launch on the context's stream.  enable(1) clears the records;
  * report writes JSON {"kernel": {"launches": n, "total_ms": t}, ...} and returns the bytes needed. */
+/* measured integer-pipe roofs of this GPU, warp-instructions per clock per SM (cycles counted in-kernel): out3[0] IMAD.WIDE.U32 (the only
+ * wide multiplier of sm_100a), out3[1] 32-bit ALU work (SHF / LOP3 / IADD), out3[2] a 1:3 mix of the two — the binding roofs of the
+ * field and hash kernels, reported by bench.py next to the HBM roofline */
+int  hb_ubench_pipes(hb_ctx *ctx, double *out3);
 int  hb_profile_enable(hb_ctx *ctx, int on);
 size_t hb_profile_report(hb_ctx *ctx, char *buf, size_t cap);
 int  hb_malloc_device(hb_ctx *ctx, void **p, size_t bytes);
@@ -313,6 +317,14 @@ int hb_dist_allreduce(hb_ctx *ctx, hb_F *vec, size_t n);           /* field sum 
 int hb_dist_commit_standard(hb_ctx *ctx, const hb_F *poly_local, size_t K_total, size_t B, int trs, int linear_time, uint8_t *levels_out);
 /* Elastic_PC commit of groups_total groups of 4 chunks of B coefficients, sharded the same way (4B leaves): levels_out (8B-1)*32 bytes */
 int hb_dist_elastic_commit(hb_ctx *ctx, const hb_F *chunks_local, size_t groups_total, size_t B, int trs, int linear_time, uint8_t *levels_out);
+/* the streaming form: begin, hb_elastic_push for this rank's 4*groups_total/world chunks (its consecutive groups, in order), then
+ * hb_elastic_finish / hb_elastic_finish_levels: every rank receives the whole tree */
+int hb_dist_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, size_t groups_total);
+/* Elastic_PC open, stream pass of a chunk RANGE (call right after hb_elastic_open_begin(.., nchunks = the range length)): the pushes are
+ * chunks [first, first+nchunks) of `total`; reply_out of hb_elastic_open_finish then has queries*total entries, this range filled and
+ * zeros elsewhere, so hb_dist_allreduce over the ranks assembles aggregate and replies (Elastic_PC.cpp:316-333, 487-533 are sums /
+ * independent cells over the chunks) */
+int hb_elastic_open_range(hb_ctx *ctx, size_t first, size_t total);
 /* on != 0: the provers (hb_sumcheck3, hb_batch_sumcheck3, hb_mul_tree, hb_stream_sumcheck_layer, hb_mul_tree_stream,
  * hb_gate_consistency_stream, hb_gate_consistency_lookups_stream) shard their work over the ranks: every rank passes the SAME full
  * tables (replicated in HBM) and works on its contiguous part of each table / of each BUFFER_SPACE chunk; the round sums are added

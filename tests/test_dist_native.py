@@ -165,3 +165,38 @@ def _prover_worker(rank, world, port, ret):
 @pytest.mark.parametrize("world", [2, 4])
 def test_native_sharded_provers(world):
     _run(_prover_worker, world)
+
+
+def _fullsize_worker(rank, world, port, ret):
+    """BASELINE config 2 at full size, sharded over `world` ranks, against the SHA-256 level digests of the unmodified reference."""
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.json")))["commit_standard_2e26"]
+    N, K, trs = g["N"], g["K"], g["trs"]
+    B = N // K
+    import torch
+    import torch.distributed as dist
+    import hobbit_b200
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dev = rank if torch.cuda.device_count() >= world else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = hobbit_b200.Context(dev)
+    orc = Checker("orc")
+    srand(1)
+    poly = orc.generate_randomness(N)
+    orc.expander_init_store(trs)
+    ctx.expander_set(trs, orc.expander_graphs(trs))
+    ctx.dist_init_torch(K * (B // world) * 32 + 2 * B * 32 + 4096)
+    kl = K // world
+    lv = ctx.dist_commit_standard(np.ascontiguousarray(poly[rank * kl * B:(rank + 1) * kl * B]), K, B, trs, 1)
+    out, off, n = [], 0, B
+    while n >= 1:
+        out.append(hashlib.sha256(np.ascontiguousarray(lv[off:off + n]).tobytes()).hexdigest())
+        off += n
+        n //= 2
+    _finish(ctx, dist, out == g["levels_sha256"], rank, ret)
+
+
+def test_native_sharded_commit_2e26_equals_reference_digests():
+    _run(_fullsize_worker, 2, timeout=900)

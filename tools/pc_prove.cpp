@@ -1,0 +1,83 @@
+// Reference-free polynomial-commitment runs through the host mirror only (links libhobbit_host.so / libhobbit_b200.so):
+//   pc_prove pc <logN> <K> <lin> [--reps R]                    BASELINE config 1: test_PC(2^logN, 4 | 1, K) = commit_standard + open_standard
+//                                                               (Our_PC.cpp:763-779, 806-826)
+//   pc_prove elastic <logN> <logB> <option> [--pinned] [--reps R]  BASELINE config 5: test_Elastic_PC(2^logN, option) with BUFFER_SPACE = 2^logB
+//                                                               (Elastic_PC.cpp:736-784; option 2 = Orion columns, 1 = RS columns)
+// Under tools/run_ranks.sh / torchrun (RANK, WORLD_SIZE, ...) the Elastic run is sharded over the GPUs of the box: every rank pushes its
+// chunk range, the digests cross NVLink inside the kernels, every rank ends up with the same tree and the same opening.
+// --pinned: the stream chunks live in pinned host memory and every push crosses PCIe (double-buffered).  Prints one JSON line (rank 0).
+#include "../hobbit_b200/host/hobbit_host.hpp"
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unistd.h>
+using namespace hobbit;
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static unsigned long long fnv(unsigned long long h, const void *p, size_t n) { for (size_t i = 0; i < n; i++) h = (h ^ ((const unsigned char *)p)[i]) * 0x100000001b3ULL; return h; }
+
+int main(int argc, char **argv) {
+    if (argc < 5) { printf("usage: pc_prove pc <logN> <K> <lin> | pc_prove elastic <logN> <logB> <option> [--pinned] [--reps R]\n"); return 2; }
+    const bool elastic = !strcmp(argv[1], "elastic");
+    const int logN = atoi(argv[2]), a3 = atoi(argv[3]), a4 = atoi(argv[4]);
+    int reps = 3;
+    for (int i = 5; i < argc; i++) {
+        if (!strcmp(argv[i], "--reps")) reps = atoi(argv[++i]);
+        if (!strcmp(argv[i], "--pinned")) stream_in_pinned_host = true;
+        if (!strcmp(argv[i], "--resident-levels")) commit_levels_on_host = false;
+    }
+    const size_t N = (size_t)1 << logN;
+    const int world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
+    size_t win = 0;
+    if (elastic) { const size_t B = (size_t)1 << a3; win = std::max<size_t>(32 * (N / world + 8 * B), ((size_t)5900 * (N / B) + B + 1) * 16 * world) + (1 << 20); }
+    dist_init_from_env(win);
+    int saved = dup(1); FILE *nul = fopen("/dev/null", "w");
+    double best_c = 1e9, best_o = 1e9, ps = 0; unsigned long long digest = 0, launches = 0;
+    char root_hex[65] = {0};
+    for (int rep = 0; rep <= reps; rep++) {                  // rep 0 = warm-up (context, twiddle tables, allocator)
+        fflush(stdout); dup2(fileno(nul), 1);
+        srand(1);
+        hb_transcript_digest(backend(), 1);
+        const unsigned long long l0 = hb_launch_count(backend());
+        double vt = 0; ps = 0;
+        double tc, to;
+        std::vector<std::vector<_hash>> MT; _hash comm;
+        if (!elastic) {
+            const int K = a3; const bool lin = a4 != 0;
+            std::vector<F> poly = generate_randomness((int)N);
+            linear_time = lin; tensor_row_size = (int)(N / ((size_t)K << 11));
+            if (lin) expander_init_store(tensor_row_size);
+            std::vector<std::vector<std::vector<F>>> T;
+            open_reuses_committed_poly = true;               // test_PC opens the polynomial it has just committed
+            double t0 = now(); commit_standard(poly, comm, MT, T, K); double t1 = now();
+            std::vector<F> x = generate_randomness(logN);
+            double t2 = now(); open_standard(poly, x, MT, T, K, vt, ps); double t3 = now();
+            tc = t1 - t0; to = t3 - t2;
+            digest = fnv(0xcbf29ce484222325ULL, MT.back().data(), 32);
+            for (int q = 0; q < 32; q++) sprintf(root_hex + 2 * q, "%02x", ((const unsigned char *)MT.back().data())[q]);
+        } else {
+            BUFFER_SPACE = (size_t)1 << a3;
+            const int option = a4;
+            stream_descriptor cd; cd.name = "test"; cd.size = N;
+            if (option == 1) { linear_time = false; tensor_row_size = (int)(BUFFER_SPACE >> 11); }
+            else { linear_time = true; const size_t K = N / BUFFER_SPACE; tensor_row_size = (int)(N / (K << 14)); expander_init_store(tensor_row_size); }
+            double t0 = now(); commit(cd, comm, MT); double t1 = now();
+            for (auto &lv : MT) if (lv.size() == 1) { digest = fnv(0xcbf29ce484222325ULL, lv.data(), 32); for (int q = 0; q < 32; q++) sprintf(root_hex + 2 * q, "%02x", ((const unsigned char *)lv.data())[q]); }
+            std::vector<F> x = generate_randomness(logN);
+            double t2 = now(); open(cd, x, MT, vt, ps); double t3 = now();
+            tc = t1 - t0; to = t3 - t2;
+        }
+        const unsigned long long tr = hb_transcript_digest(backend(), 0);
+        digest = fnv(digest, &tr, 8);
+        launches = hb_launch_count(backend()) - l0;
+        fflush(stdout); dup2(saved, 1);
+        if (rep) { best_c = std::min(best_c, tc); best_o = std::min(best_o, to); }
+    }
+    if (dist_rank() != 0) return 0;
+    if (!elastic) printf("{\"workload\": \"test_PC(2^%d, %s, K=%d)\", ", logN, a4 ? "Orion columns" : "RS columns", a3);
+    else printf("{\"workload\": \"test_Elastic_PC(2^%d, %d) BUFFER_SPACE 2^%d%s\", ", logN, a4, a3, stream_in_pinned_host ? " stream in pinned host memory" : " stream chunk resident in HBM");
+    printf("\"commit_s\": %.6f, \"open_s\": %.6f, \"elems_per_s_commit\": %.1f, \"ps_kb\": %.6f, \"root\": \"%s\", \"transcript\": \"%016llx\", \"rng_next\": %ld, "
+           "\"launches\": %llu, \"n_gpus\": %d}\n", best_c, best_o, N / best_c, ps, root_hex, digest, random(), launches, dist_world());
+    return 0;
+}
