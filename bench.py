@@ -353,13 +353,16 @@ def main():
     # ncu counters of this kernel (by name), its instruction mix -> the time the pipes need at those measured rates.
     try:
         pipes = ctx.ubench_pipes()
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        if clocks.get("sm_mhz"):
+            per = clocks["sm_mhz"] * 1e6 * sms
+            pipes["per_clk_per_sm_at_sampled_clock"] = {k: pipes[k] / per for k in ("imad_wide", "alu", "mix_1_wide_3_alu")}
         roofline["measured_pipe_rates"] = pipes
-        if counts.get("warp_inst_per_coefficient") and clocks.get("sm_mhz"):
-            sms = torch.cuda.get_device_properties(local).multi_processor_count
-            clk = per_launch_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sms                     # SM-cycles available during one launch
+        if counts.get("warp_inst_per_coefficient"):
             inst = counts["warp_inst_per_coefficient"] * coeffs_per_launch
-            roofline["binding"] = {"resource": "integer issue (IMAD.WIDE on the FMA-heavy pipe + ALU pipe)", "unit": "warp-inst/clk/SM",
-                                   "achieved": inst / clk, "peak": pipes["mix_1_wide_3_alu"], "frac": inst / clk / pipes["mix_1_wide_3_alu"],
+            ach = inst / (per_launch_ms * 1e-3)                                           # warp-instructions per second of this kernel, live
+            roofline["binding"] = {"resource": "integer issue (IMAD.WIDE on the FMA-heavy pipe + ALU pipe)", "unit": "warp-inst/s (chip)",
+                                   "achieved": ach, "peak": pipes["mix_1_wide_3_alu"], "frac": ach / pipes["mix_1_wide_3_alu"],
                                    "warp_instructions_per_launch": inst,
                                    "source": "instruction count: profiles/kernel_counts_r02.json (ncu smsp__inst_executed.sum of this kernel); peak: "
                                              "hb_ubench_pipes measured in this run (1 IMAD.WIDE : 3 ALU mix, the kernel's own ratio is in the file)"}

@@ -122,7 +122,7 @@ class Context:
     def ubench_pipes(self):
         out = (ctypes.c_double * 3)()
         self._ck(self.lib.hb_ubench_pipes(self.h, out))
-        return {"imad_wide": out[0], "alu": out[1], "mix_1_wide_3_alu": out[2], "unit": "warp-inst/clk/SM"}
+        return {"imad_wide": out[0], "alu": out[1], "mix_1_wide_3_alu": out[2], "unit": "warp-inst/s (chip)"}
 
     def profile(self, on=True):
         self._ck(self.lib.hb_profile_enable(self.h, 1 if on else 0))

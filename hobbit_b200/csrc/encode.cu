@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "blake3.cuh"
 #include <algorithm>
+#include <cuda.h>
 
 namespace hb {
 
@@ -53,14 +54,28 @@ __device__ __forceinline__ int ld_rowptr(const int *p) { int v; asm("ld.global.n
 // of this chunk (commit_standard hashes 4-row quads of every column, Our_PC.cpp:160-166); the Merkle–Damgård chaining
 // over chunks is done afterwards by md_chain_kernel so that all chunks can be encoded in one launch.
 constexpr int kHelpUnits = 2;
+// TMA (cp.async.bulk.tensor): the CTA's tile — CB adjacent columns x all message rows, a dense [rows][CB] block of 16-byte elements — is
+// fetched by ONE thread as 2-D boxes of up to 256 rows that land in shared memory in exactly the cw[row][CB] layout the stages use
+// (no swizzle: a quarter-warp reads one contiguous 16*CB-byte row), completion on an mbarrier; the parity rows go back the same way.
+// The tensor map views all chunks of the launch as one (2*cols u64) x (2n*nchunks rows) matrix.
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int x, int y, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tm), "r"(x), "r"(y), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int x, int y, const void *smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tm), "r"(x), "r"(y), "r"((unsigned)__cvta_generic_to_shared(smem_src)) : "memory");
+}
 template <int CB, bool INNER>
 __global__ void __launch_bounds__(1024)
 encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int n, int cwlen,
                    const EncStage *__restrict__ stages, int nstages,
                    const int *__restrict__ rowptr, const uint2 *__restrict__ edges,
-                   uint8_t *__restrict__ inner_base, Digest zero_quad, InnerLayout lay, unsigned long long *__restrict__ prof, int split_ok, int help_ok) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+                   uint8_t *__restrict__ inner_base, Digest zero_quad, InnerLayout lay, unsigned long long *__restrict__ prof, int split_ok, int help_ok,
+                   const __grid_constant__ CUtensorMap tmap, int box_rows) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     F *cw = reinterpret_cast<F *>(smem_raw);                   // cw[row * CB + c]
+    __shared__ __align__(8) unsigned long long tma_bar;
     long long tprev = prof ? clock64() : 0;                    // development aid (HB_ENCODE_PROF): cycles per phase, summed over CTAs by thread 0
     auto mark = [&](int slot) { if (prof && threadIdx.x == 0) { long long t = clock64(); atomicAdd(&prof[slot], (unsigned long long)(t - tprev)); tprev = t; } };
     F *T = Tbase + (size_t)blockIdx.y * chunk_stride;
@@ -94,14 +109,29 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
     };
     if (INNER && threadIdx.x == 0) hash_next = 0;
 
-    // message rows -> shared memory with asynchronous 16-byte copies: every thread has all of its loads in flight at once (a plain
-    // load/store loop serialises one DRAM round trip per row and was 10 % of the kernel)
-    for (unsigned r = t0; r < (unsigned)n; r += tstep) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(&cw[r * CB + c]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(&T[(size_t)r * cols + col0 + c]) : "memory");
+    if (box_rows) {
+        // message rows -> shared memory by TMA: one thread, n / box_rows boxes in flight, one mbarrier
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&tma_bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&tma_bar)), "r"((unsigned)(n * CB * sizeof(F))) : "memory");
+            for (int r = 0; r < n; r += box_rows) tma_load_2d(&cw[r * CB], &tmap, (int)(2 * col0), (int)(blockIdx.y * 2 * n + r), &tma_bar);
+        }
+        __syncthreads();                                         // the barrier is initialised before anybody polls it
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(&tma_bar)) : "memory");
+    } else {
+        // shapes the tensor map cannot describe (rows not a multiple of the box, strided chunks): asynchronous 16-byte copies, every thread
+        // has all of its loads in flight at once
+        for (unsigned r = t0; r < (unsigned)n; r += tstep) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&cw[r * CB + c]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(&T[(size_t)r * cols + col0 + c]) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
     mark(0);
 
     for (int s = 0; s < nstages; s++) {
@@ -166,7 +196,20 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
     }
 
     // rows [n, cwlen) are new; rows [cwlen, 2n) are the zero tail of the reference's 2n-sized buffer
-    for (unsigned r = n + t0; r < 2u * n; r += tstep)
+    unsigned first_plain = n;
+    if (box_rows) {
+        // whole boxes of parity rows leave by TMA straight from shared memory (the last stage's barrier made them visible to this thread;
+        // the proxy fence makes them visible to the async proxy); the ragged rest and the zero tail are plain stores
+        const unsigned full = ((unsigned)(cwlen - n) / box_rows) * box_rows;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (unsigned r = n; r < n + full; r += box_rows) tma_store_2d(&tmap, (int)(2 * col0), (int)(blockIdx.y * 2 * n + r), &cw[r * CB]);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        first_plain = n + full;
+    }
+    for (unsigned r = first_plain + t0; r < 2u * n; r += tstep)
         T[(size_t)r * cols + col0 + c] = (r < (unsigned)cwlen) ? cw[r * CB + c] : mkF(0, 0);
     if (prof) __syncthreads();
     mark(14);
@@ -178,6 +221,22 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
         if (prof) __syncthreads();
         mark(15);
     }
+    // shared memory must stay alive until the bulk stores have read it
+    if (box_rows && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
 }
 
 // H1 of 64 zero bytes (blake3 KAT 4d006976...): the inner digest of every all-zero quad
@@ -199,14 +258,27 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     static const int split_ok = getenv("HB_ENCODE_SPLIT") ? atoi(getenv("HB_ENCODE_SPLIT")) : 1;   // experiment switch
     if (!prof && getenv("HB_ENCODE_PROF")) { cudaMalloc(&prof, 16 * 8); cudaMemset(prof, 0, 16 * 8); }
     if (const char *e = getenv("HB_ENCODE_THREADS")) threads = (unsigned)atoi(e);          // experiment switch
+    // TMA tile movement when the launch is one dense (2*cols u64) x (2n * nchunks) matrix and the message rows split into whole boxes
+    CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
+    int box_rows = 0;
+    static const int tma_ok = getenv("HB_ENCODE_TMA") ? atoi(getenv("HB_ENCODE_TMA")) : 1;   // experiment switch
+    if (tma_ok && encode_tiled_fn() && (nchunks == 1 || chunk_stride == (size_t)(2 * n) * cols) && (n % 256 == 0 || n <= 256) && ((uintptr_t)T % 16) == 0 &&
+        (size_t)(2 * n) * nchunks < ((size_t)1 << 31)) {
+        const int br = n <= 256 ? (int)n : 256;
+        cuuint64_t dims[2] = {(cuuint64_t)(2 * cols), (cuuint64_t)((size_t)(2 * n) * nchunks)};
+        cuuint64_t strides[1] = {(cuuint64_t)(cols * sizeof(F))};
+        cuuint32_t box[2] = {(cuuint32_t)(2 * CB), (cuuint32_t)br}, estr[2] = {1, 1};
+        if (encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)T, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) box_rows = br;
+    }
     if (inner) {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok);
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows);
     } else {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, false>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok);
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows);
     }
     if (prof) {                                                   // development aid: cumulative cycles per phase (thread 0 of every CTA)
         unsigned long long h[16];

@@ -2,6 +2,7 @@
 // warp-instructions per clock per SM for IMAD.WIDE.U32 (FMA-heavy pipe: the only wide multiplier of sm_100a), for 32-bit ALU work
 // (IADD3 / LOP3 / SHF) and for a 1:3 mix.  Cycles are counted with clock64 inside the kernel, so the result does not depend on the clock.
 #include "common.cuh"
+#include <algorithm>
 
 namespace hb {
 
@@ -37,26 +38,31 @@ template <int MODE> __global__ void __launch_bounds__(256) pipe_rate_kernel(unsi
 
 using namespace hb;
 
-// out[0] IMAD.WIDE.U32, out[1] ALU (SHF+LOP3 / IADD: 3 instructions per step), out[2] mix of 1 IMAD.WIDE + 3 ALU: warp-inst / clk / SM
+// out[0] IMAD.WIDE.U32, out[1] ALU (SHF, LOP3, IADD: 3 instructions per step), out[2] mix of 1 IMAD.WIDE + 3 ALU: warp-instructions per
+// SECOND, chip-wide, timed with CUDA events on the context's stream (the caller divides by the SM clock it samples and the SM count)
 extern "C" int hb_ubench_pipes(hb_ctx *ctx, double *out3) {
     cudaSetDevice(ctx->device);
-    const int per_sm = 4, blocks = ctx->sm_count * per_sm, iters = 1024;
+    const int per_sm = 4, blocks = ctx->sm_count * per_sm, iters = 4096;
     unsigned long long *cyc; uint32_t *sink;
     HB_CHECK(ctx, cudaMalloc(&cyc, blocks * sizeof(unsigned long long)));
     HB_CHECK(ctx, cudaMalloc(&sink, (size_t)blocks * 256 * sizeof(uint32_t)));
-    std::vector<unsigned long long> h(blocks);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const double ops[3] = {1, 3, 4};
     for (int mode = 0; mode < 3; mode++) {
-        for (int rep = 0; rep < 2; rep++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(e0, ctx->stream);
             if (mode == 0) { HB_LAUNCH(ctx, pipe_rate_kernel<0>, blocks, 256, 0, cyc, sink, 12345u, iters); }
             else if (mode == 1) { HB_LAUNCH(ctx, pipe_rate_kernel<1>, blocks, 256, 0, cyc, sink, 12345u, iters); }
             else { HB_LAUNCH(ctx, pipe_rate_kernel<2>, blocks, 256, 0, cyc, sink, 12345u, iters); }
+            cudaEventRecord(e1, ctx->stream);
+            HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep) best = std::min(best, ms);
         }
-        HB_CHECK(ctx, cudaMemcpyAsync(h.data(), cyc, blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        double mean = 0; for (auto c : h) mean += (double)c; mean /= blocks;
-        out3[mode] = per_sm * 8.0 * iters * 8.0 * ops[mode] / mean;          // CTAs/SM x warps x iterations x chains x instructions / cycles
+        out3[mode] = (double)blocks * 8.0 * iters * 8.0 * ops[mode] / (best * 1e-3);          // CTAs x warps x iterations x chains x instructions / s
     }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(cyc); cudaFree(sink);
     return 0;
 }

@@ -46,7 +46,7 @@ uint64_t hb_transcript_digest(hb_ctx *ctx, int reset);
 void *hb_stream(hb_ctx *ctx);
 /* per-kernel timing: CUDA events around every launch on the context's stream.  enable(1) clears the records;
  * report writes JSON {"kernel": {"launches": n, "total_ms": t}, ...} and returns the bytes needed. */
-/* measured integer-pipe roofs of this GPU, warp-instructions per clock per SM (cycles counted in-kernel): out3[0] IMAD.WIDE.U32 (the only
+/* measured integer-pipe roofs of this GPU, warp-instructions per SECOND chip-wide (CUDA-event timed): out3[0] IMAD.WIDE.U32 (the only
  * wide multiplier of sm_100a), out3[1] 32-bit ALU work (SHF / LOP3 / IADD), out3[2] a 1:3 mix of the two — the binding roofs of the
  * field and hash kernels, reported by bench.py next to the HBM roofline */
 int  hb_ubench_pipes(hb_ctx *ctx, double *out3);

@@ -165,10 +165,9 @@ def test_elastic_commit_2e26_equals_reference_digests():
     chunk = ctx.stream_pc_test(B)
     lv = ctx.elastic_commit([chunk] * (N // B), B, trs, 1)
     got = _level_sha256(lv, 4 * B)
+    ctx.close()
     assert lv[-1].tobytes().hex() == g["root"]
     assert got[1:] == g["levels_sha256"][1:]                       # every level above the leaves
-    # leaves: all but the very last digest (undefined behaviour in the reference, a right child that influences nothing)
-    ctx.close()
-    assert np.array_equal(lv[:4 * B - 1], lv[:4 * B - 1])          # shape sanity; the leaf level as a whole is compared below when it matches
-    if got[0] != g["levels_sha256"][0]:
-        pytest.skip("leaf level differs only in the reference's out-of-bounds last leaf (documented); upper levels and root identical")
+    # the leaves: all but the very last one (the reference computes it from reads past its buffers — undefined behaviour; it is a right
+    # child and, with the left||left parent rule, influences nothing)
+    assert hashlib.sha256(np.ascontiguousarray(lv[:4 * B - 1]).tobytes()).hexdigest() == g["leaves_sha256_without_last"]
