@@ -202,6 +202,7 @@ void read_trace(stream_descriptor &fd, std::vector<F> &buff_L, std::vector<F> &b
 // prove_gate_consistency (sumcheck.cpp:796-981) on the resident transcript.  libc draws in the reference's order: generate_randomness(4)
 // for the batching of the degree-4 sumcheck (:877-880), generate_randomness(6) for the Peval combination (:958).
 void prove_gate_consistency(stream_descriptor tr, std::vector<F> r, double &vt, double &ps) {
+    trace_rng("prove_gate_consistency");
     (void)vt;
     if (has_lookups) { printf("hobbit_b200: with has_lookups call prove_gate_consistency_lookups\n"); exit(-1); }
     transcript_dev();
@@ -216,6 +217,7 @@ void prove_gate_consistency(stream_descriptor tr, std::vector<F> r, double &vt, 
 
 // prove_gate_consistency_lookups (sumcheck.cpp:503-794).  libc draws: generate_randomness(5) (:637), generate_randomness(8) (:770).
 void prove_gate_consistency_lookups(stream_descriptor tr, std::vector<F> r, double &vt, double &ps) {
+    trace_rng("prove_gate_consistency_lookups");
     (void)vt;
     if (!has_lookups) { printf("hobbit_b200: prove_gate_consistency_lookups needs has_lookups\n"); exit(-1); }
     need_lookup_rand();

@@ -114,6 +114,20 @@ F F::operator*(const F &o) const {
     F r; r.real = ac >= bd ? ac - bd : ac + P - bd; r.img = ad + bc; if (r.img >= P) r.img -= P; return r;
 }
 
+// HOBBIT_TRACE_RNG=1: a fingerprint of glibc's random() state (read, not advanced) on stderr at the entry of every mirrored prover call —
+// how a divergence of the libc call order from the reference's is located
+void trace_rng(const char *where) {
+    static const bool on = getenv("HOBBIT_TRACE_RNG") != nullptr;
+    if (!on) return;
+    static char tmp[128];
+    static bool init = false;
+    if (!init) { char *cur = initstate(1, tmp, sizeof(tmp)); setstate(cur); init = true; }
+    char *cur = setstate(tmp); setstate(cur);                     // cur = the live state array (header word + 31 words for TYPE_3)
+    unsigned long long h = 0xcbf29ce484222325ULL;
+    for (int i = -4; i < 124; i++) h = (h ^ (unsigned char)cur[i]) * 0x100000001b3ULL;
+    fprintf(stderr, "[rng] %-48s %016llx\n", where, h);
+}
+
 // utils.cpp:873-883 — same libc calls in the same order
 std::vector<F> generate_randomness(int size) {
     std::vector<F> x; F c;
@@ -139,6 +153,17 @@ static long long init_rec(long long n, int dep, int &levels) {
     long long L = init_rec((long long)(kAlpha * n), dep + 1, levels);
     gen(gD[dep], L, (long long)(n * (kR - 1) - L), kDn);
     return n + L + (long long)(n * (kR - 1) - L);
+}
+// Link-level drop-in (hobbit_adapter.cpp): take over graphs the REFERENCE's expander_init_store has drawn (no second pass over the libc RNG)
+void expander_adopt(long long n, int levels, const std::vector<ext_graph> &C, const std::vector<ext_graph> &D) {
+    long long LC[100], RC[100], LD[100], RD[100]; const uint32_t *nC[100], *nD[100]; const uint64_t *wC[100], *wD[100];
+    for (int d = 0; d < levels; d++) {
+        gC[d].L = C[d].L; gC[d].R = C[d].R; gC[d].nbr = C[d].nbr; gC[d].w = C[d].w;
+        gD[d].L = D[d].L; gD[d].R = D[d].R; gD[d].nbr = D[d].nbr; gD[d].w = D[d].w;
+        LC[d] = gC[d].L; RC[d] = gC[d].R; nC[d] = gC[d].nbr.data(); wC[d] = gC[d].w.data();
+        LD[d] = gD[d].L; RD[d] = gD[d].R; nD[d] = gD[d].nbr.data(); wD[d] = gD[d].w.data();
+    }
+    CK(hb_expander_set(backend(), n, levels, kCn, kDn, LC, RC, nC, wC, LD, RD, nD, wD));
 }
 const host_graph &expander_graph(int which, int dep) {
     static host_graph g;
@@ -302,6 +327,7 @@ void read_stream_PC(stream_descriptor &fd, F *v, int size) {                    
 }
 static double wall_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + 1e-6 * ts.tv_nsec; }
 void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_hashes) {
+    trace_rng(("commit " + fd.name).c_str());
     const bool trace = getenv("HOBBIT_TRACE") != nullptr;                        // HOBBIT_TRACE=1: wall time of the phases on stderr
     const double t_begin = trace ? wall_ms() : 0;
     if (fd.size / BUFFER_SPACE < 4) printf("Decrease buffer size %d\n", (int)(fd.size / BUFFER_SPACE));
@@ -488,6 +514,7 @@ static void open_layers(std::vector<stream_descriptor> &fd_com, std::vector<std:
 
 std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, int vectors, int size, F previous_r, int distance,
                                                         std::vector<F> prev_x, bool naive, double &vt, double &ps) {
+    trace_rng(("prove_multiplication_tree_stream_shallow " + fd.name).c_str());
     if (!prev_x.empty()) { printf("hobbit_b200: prove_multiplication_tree_stream_shallow with prev_x is not wired yet\n"); exit(-1); }
     const size_t total = (size_t)size * vectors;
     // the stream in its logical two-half form [X | Y]: one read of the whole stream (a two-half producer emits X-block | Y-block)
@@ -504,6 +531,8 @@ std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, in
     if (!naive && total > 2 * BUFFER_SPACE) commit_layers(fd, fd_com, MT_hashes, layers / distance, distance - 1, distance);   // :1786-1789 (no libc draws)
     // libc draws in the reference's order: the product tree's points, then per streamed layer a, (b0, b1), pad — or, for a deep tree
     // (layers > distance): the tail of r_temp (:1875), then per batched pass a[batches], b[2*batches], pad
+    if (getenv("HOBBIT_TRACE_RNG")) fprintf(stderr, "[rng]   total %zu BUFFER_SPACE %zu layers %d distance %d deep %d naive %d trs %d lin %d\n", total, (size_t)BUFFER_SPACE, layers, distance, (int)deep, (int)naive, tensor_row_size, (int)linear_time);
+    trace_rng("  after commit_layers");
     std::vector<F> xr = generate_randomness((int)std::log2((double)vectors)), rnd;
     if (!deep) {
         for (int i = 0; i < layers; i++) {
@@ -524,6 +553,7 @@ std::vector<F> prove_multiplication_tree_stream_shallow(stream_descriptor fd, in
     int got_layers = 0;
     CK(hb_mul_tree_stream(backend(), (const hb_F *)xy_ptr, total, vectors, BUFFER_SPACE, distance, naive ? 1 : 0, (const hb_F *)&previous_r,
                           (const hb_F *)xr.data(), (const hb_F *)rnd.data(), (hb_F *)out.data(), &got_layers, &ps));
+    trace_rng("  before open_layers");
     if (!naive) open_layers(fd_com, MT_hashes, vt, ps);                          // :1909-1911
     return out;
 }

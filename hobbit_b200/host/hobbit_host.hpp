@@ -93,6 +93,7 @@ int dist_rank();
 int dist_world();
 
 std::vector<F> generate_randomness(int size);
+void trace_rng(const char *where);           // HOBBIT_TRACE_RNG=1: fingerprint of the libc random() state on stderr
 long long expander_init_store(long long n, int dep = 0);
 F mimc_hash(F input, F k);
 void precompute_beta(std::vector<F> r, std::vector<F> &B);
@@ -134,6 +135,10 @@ open_front open_standard_front(std::vector<F> &poly, std::vector<F> x, std::vect
 // vectors (a maintainer dropping this into the reference keeps the call sites: they only pass these objects around).
 struct host_graph { long long L = 0, R = 0; int deg = 0; const uint32_t *nbr = nullptr; const uint64_t *w = nullptr; };
 const host_graph &expander_graph(int which /*0 = _C, 1 = D*/, int dep);      // the graphs expander_init_store drew (expanders.h:18)
+// graphs drawn elsewhere (the reference's own expander_init_store, when this library is linked under the reference's callers):
+// nbr[i*deg + j] / w[i*deg + j] as in hb_expander_set; C: degree 9, D: degree 12
+struct ext_graph { long long L = 0, R = 0; std::vector<uint32_t> nbr; std::vector<uint64_t> w; };
+void expander_adopt(long long n, int levels, const std::vector<ext_graph> &C, const std::vector<ext_graph> &D);
 struct shockwave_data {                        // Virgo.h:27-51; matrix / encoded_matrix / MT live on the device
     int k = 0; size_t N = 0;
     F *matrix = nullptr, *encoded_matrix = nullptr;     // k x N/k and k x 2N/k, row-major

@@ -642,4 +642,21 @@ int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb
     return 0;
 }
 
+
+/* ---- single-process stand-ins for the multi-GPU / pinned-memory entry points the host mirror links against: the emulation is one rank ---- */
+int hb_malloc_pinned(hb_ctx *, void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : 1; }
+int hb_free_pinned(hb_ctx *, void *p) { free(p); return 0; }
+uint64_t hb_transcript_digest(hb_ctx *, int) { return 0; }
+int hb_dist_local_info(hb_ctx *, size_t, void *blob) { memset(blob, 0, 256); return 0; }
+int hb_dist_connect(hb_ctx *, int, int world, const void *) { return world == 1 ? 0 : 1; }
+int hb_dist_disconnect(hb_ctx *) { return 0; }
+int hb_dist_rank(hb_ctx *) { return 0; }
+int hb_dist_world(hb_ctx *) { return 1; }
+int hb_dist_barrier(hb_ctx *) { return 0; }
+int hb_dist_shard(hb_ctx *, int) { return 0; }
+int hb_dist_allreduce(hb_ctx *, hb_F *, size_t) { return 0; }
+int hb_dist_elastic_commit(hb_ctx *, const hb_F *, size_t, size_t, int, int, uint8_t *) { return 1; }   /* only reached with world > 1 */
+int hb_dist_elastic_begin(hb_ctx *ctx, size_t B, int trs, int lin, size_t) { return hb_elastic_begin(ctx, B, trs, lin); }
+int hb_elastic_open_range(hb_ctx *, size_t, size_t) { return 1; }                                       /* only reached with world > 1 */
+
 }  // extern "C"

@@ -34,7 +34,7 @@ int main(int argc, char **argv) {
     double best[6] = {1e9, 1e9, 1e9, 1e9, 1e9, 1e9}, ps = 0; size_t cs = 0;
     unsigned long long transcript = 0, launches_last = 0;
     for (int rep = 0; rep <= reps; rep++) {                 // rep 0 = warm-up (tables, allocator)
-        fflush(stdout); dup2(fileno(nul), 1);               // the reference-style printf chatter of the provers
+        fflush(stdout); if (!getenv("HOBBIT_KEEP_STDOUT")) dup2(fileno(nul), 1);   // the reference-style printf chatter of the provers
         srand(1);
         hb_transcript_digest(backend(), 1);
         const unsigned long long l0 = hb_launch_count(backend());
