@@ -196,13 +196,19 @@ def extras(world, rank):
         out["config3_MLP_pigeon_9_18_18_1_4_1024_256_256_16"] = one([mlp, "18", "1024", "256", "256", "16", "--reps", "3"])
         out["config4_AES_pigeon_5_19_8_1"] = one([mlp, "19", "aes", "8", "--reps", "3"])
         out["config4_SQL_pigeon_6_19_17_1"] = one([mlp, "19", "sql", "17", "--reps", "3"])
-        out["config5_test_Elastic_PC_2e28_pinned"] = one([pc, "elastic", "28", "20", "2", "--pinned", "--reps", "2"])
+        out["config5_test_Elastic_PC_2e28_pinned"] = one([pc, "elastic", "28", "20", "2", "--pinned", "--resident-levels", "--reps", "2"])
+        out["config5_test_Elastic_PC_2e28_hbm_chunk"] = one([pc, "elastic", "28", "20", "2", "--resident-levels", "--reps", "2"])
     else:
         # every rank of this job starts the same tool with its own RANK / LOCAL_RANK: the tools rendezvous among themselves (MASTER_PORT + 29)
         logn = {2: 28, 4: 29, 8: 30}.get(world, 28)
-        r = run_tool([pc, "elastic", str(logn), "20", "2", "--pinned", "--reps", "2"])
+        # prover-only form (--resident-levels): the big Merkle levels stay in HBM on every rank (open() only needs their sizes); the default
+        # form copies all 256 MiB of levels into every rank's MT_hashes, which at 8 ranks on one host is most of the commit time
+        r = run_tool([pc, "elastic", str(logn), "20", "2", "--pinned", "--resident-levels", "--reps", "2"])
         if rank == 0:
             out["config5_test_Elastic_PC_2e%d_pinned_%dgpus" % (logn, world)] = r
+        r = run_tool([pc, "elastic", str(logn), "20", "2", "--resident-levels", "--reps", "2"])
+        if rank == 0:
+            out["config5_test_Elastic_PC_2e%d_hbm_chunk_%dgpus" % (logn, world)] = r
         r = run_tool([mlp, "19", "sql", "17", "--reps", "2"])
         if rank == 0:
             out["config4_SQL_pigeon_6_19_17_1_%dgpus" % world] = r

@@ -261,13 +261,21 @@ class Context:
         self._ck(self.lib.hb_stream_pc_test(self.h, _ptr(out), c_sz(n)))
         return out
 
-    def elastic_commit(self, chunks, B, trs, lin):
-        """chunks: iterable of (B,2) arrays (the stream), pushed in order."""
+    def elastic_commit(self, chunks, B, trs, lin, reuse_pinned=False):
+        """chunks: iterable of (B,2) arrays (the stream), pushed in order.  reuse_pinned: every chunk is first copied into ONE pinned host
+        buffer that is overwritten right after the push returns — what a streaming producer does (hb_elastic_push returns only once the
+        buffer has been read)."""
         self._ck(self.lib.hb_elastic_begin(self.h, c_sz(B), int(trs), int(lin)))
+        pin = self.pinned((B, 2), np.uint64) if reuse_pinned else None
         for c in chunks:
             c = _F(c)
             assert len(c) == B
-            self._ck(self.lib.hb_elastic_push(self.h, _ptr(c)))
+            if pin is not None:
+                pin[:] = c
+                self._ck(self.lib.hb_elastic_push(self.h, _ptr(pin)))
+                pin[:] = 0xdeadbeef                                  # the producer refills its buffer at once
+            else:
+                self._ck(self.lib.hb_elastic_push(self.h, _ptr(c)))
         levels = np.zeros((8 * B - 1, 32), dtype=np.uint8)
         self._ck(self.lib.hb_elastic_finish(self.h, _ptr(levels)))
         return levels

@@ -247,7 +247,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
 }
 
 extern "C" const char *hb_last_error(hb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-extern "C" int hb_sync(hb_ctx *ctx) { HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
+extern "C" int hb_sync(hb_ctx *ctx) { HB_DEV(ctx);  HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
 extern "C" uint64_t hb_launch_count(hb_ctx *ctx) { return ctx->launches; }
 extern "C" uint64_t hb_transcript_digest(hb_ctx *ctx, int reset) {
     const uint64_t h = ctx->transcript;
@@ -256,7 +256,7 @@ extern "C" uint64_t hb_transcript_digest(hb_ctx *ctx, int reset) {
 }
 extern "C" void *hb_stream(hb_ctx *ctx) { return (void *)ctx->stream; }
 // ---- per-kernel timing -------------------------------------------------------------------------------------
-extern "C" int hb_profile_enable(hb_ctx *ctx, int on) {
+extern "C" int hb_profile_enable(hb_ctx *ctx, int on) { HB_DEV(ctx);
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->prof_recs) { ctx->prof_pool.push_back(r.e0); ctx->prof_pool.push_back(r.e1); }
     ctx->prof_recs.clear();
@@ -289,14 +289,14 @@ extern "C" size_t hb_profile_report(hb_ctx *ctx, char *buf, size_t cap) {
     return js.size() + 1;
 }
 
-extern "C" int hb_malloc_device(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMalloc(p, bytes)); return 0; }
-extern "C" int hb_free_device(hb_ctx *ctx, void *p) { HB_CHECK(ctx, cudaFree(p)); return 0; }
+extern "C" int hb_malloc_device(hb_ctx *ctx, void **p, size_t bytes) { HB_DEV(ctx);  HB_CHECK(ctx, cudaMalloc(p, bytes)); return 0; }
+extern "C" int hb_free_device(hb_ctx *ctx, void *p) { HB_DEV(ctx);  HB_CHECK(ctx, cudaFree(p)); return 0; }
 // stream-ordered scratch from the context's pool (release threshold = never): no device synchronisation, microseconds per call
-extern "C" int hb_malloc_stream(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream)); return 0; }
-extern "C" int hb_free_stream(hb_ctx *ctx, void *p) { if (p) HB_CHECK(ctx, cudaFreeAsync(p, ctx->stream)); return 0; }
-extern "C" int hb_malloc_pinned(hb_ctx *ctx, void **p, size_t bytes) { HB_CHECK(ctx, cudaMallocHost(p, bytes)); return 0; }
-extern "C" int hb_free_pinned(hb_ctx *ctx, void *p) { HB_CHECK(ctx, cudaFreeHost(p)); return 0; }
-extern "C" int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+extern "C" int hb_malloc_stream(hb_ctx *ctx, void **p, size_t bytes) { HB_DEV(ctx);  HB_CHECK(ctx, cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream)); return 0; }
+extern "C" int hb_free_stream(hb_ctx *ctx, void *p) { HB_DEV(ctx);  if (p) HB_CHECK(ctx, cudaFreeAsync(p, ctx->stream)); return 0; }
+extern "C" int hb_malloc_pinned(hb_ctx *ctx, void **p, size_t bytes) { HB_DEV(ctx);  HB_CHECK(ctx, cudaMallocHost(p, bytes)); return 0; }
+extern "C" int hb_free_pinned(hb_ctx *ctx, void *p) { HB_DEV(ctx);  HB_CHECK(ctx, cudaFreeHost(p)); return 0; }
+extern "C" int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes) { HB_DEV(ctx);
     const bool dd = is_device_ptr(dst), sd = is_device_ptr(src);
     if (bytes >= kPageableDirect && dd && !sd && !is_pinned_host_ptr(src)) { HB_TRY(copy_from_host(ctx, dst, src, bytes, ctx->stream)); }
     else if (bytes >= kPageableDirect && sd && !dd && !is_pinned_host_ptr(dst)) { HB_TRY(copy_to_host(ctx, dst, src, bytes, ctx->stream)); }
@@ -306,7 +306,7 @@ extern "C" int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes) 
 }
 
 // ---- F1/F2 ---------------------------------------------------------------------------------------------
-extern "C" int hb_field_binop(hb_ctx *ctx, int op, const hb_F *a, const hb_F *b, hb_F *c, size_t n) {
+extern "C" int hb_field_binop(hb_ctx *ctx, int op, const hb_F *a, const hb_F *b, hb_F *c, size_t n) { HB_DEV(ctx);
     if (op < 0 || op > 4) HB_FAIL(ctx, "hb_field_binop: unknown op");
     if (n == 0) return 0;
     Staged sa(ctx), sb(ctx), sc(ctx);
@@ -326,18 +326,31 @@ extern "C" void hb_root_of_unity(int logn, hb_F *out) {          // utils.cpp:45
     out->real = rou.re; out->img = rou.im;
 }
 
+// MiMC sits on the critical path between sumcheck rounds (3-5 hashes per round, each 161 dependent cubings), so the host version is
+// written for latency: (a + bi)^3 = a (a^2 - 3 b^2) + i b (3 a^2 - b^2) is FOUR 64x64 products per cubing (two squarings, two
+// products) instead of the eight of two generic F multiplications, and limbs stay lazily reduced (< 2^62) until the very end.
+// (One GPU thread needs 31 us per hash, tools/ubench_fmul.cu; this takes about 1.5 us.)
+static inline u64 mimc_red(unsigned __int128 x) {              // x < 2^124 + 2^72 -> congruent value < 2^61 + 8
+    u64 s = (u64)(x >> 61) + ((u64)x & P61);                    // < 2^63 + 2^11 + 2^61: fits
+    return (s & P61) + (s >> 61);
+}
 extern "C" void hb_mimc_hash(const hb_F *input, const hb_F *k, hb_F *out) {   // mimc.cpp:95-107, constants c_i = F(i) (:11-19)
-    F in = mkF(input->real, input->img), key = mkF(k->real, k->img), t, h = mkF(0, 0);
+    typedef unsigned __int128 u128;
+    const u64 kr = k->real, ki = k->img;
+    u64 a = input->real + kr, b = input->img + ki;              // t_0 = in + k            (limbs < 2^62 throughout)
+    u64 hr = 0, hi = 0;
     for (int i = 0; i < 161; i++) {
-        t = (i == 0) ? fadd(in, key) : fadd(fadd(h, key), mkF((u64)(i - 1), 0));
-        h = h_fmul(h_fmul(t, t), t);
+        if (i) { a = hr + kr + (u64)(i - 1); b = hi + ki; }     // t_i = h + k + c_{i-1}
+        const u64 s = mimc_red((u128)a * a), u = mimc_red((u128)b * b);          // a^2, b^2 < 2^61 + 4
+        const u64 m = fold61(s + 4 * P61 - 3 * u);               // a^2 - 3 b^2   (3u < 4p)
+        const u64 n = fold61(3 * s + 2 * P61 - u);               // 3 a^2 - b^2
+        hr = mimc_red((u128)a * m); hi = mimc_red((u128)b * n);
     }
-    h = fadd(h, key);
-    out->real = h.re; out->img = h.im;
+    out->real = canon61(fold61(hr + kr)); out->img = canon61(fold61(hi + ki));
 }
 
 // ---- T1 ------------------------------------------------------------------------------------------------
-extern "C" int hb_tensorcode(hb_ctx *ctx, const hb_F *msg, size_t n, int trs, int linear_time, hb_F *tensor) {
+extern "C" int hb_tensorcode(hb_ctx *ctx, const hb_F *msg, size_t n, int trs, int linear_time, hb_F *tensor) { HB_DEV(ctx);
     Staged m(ctx), t(ctx);
     HB_TRY(m.in(msg, n * sizeof(F)));
     HB_TRY(t.outbuf(tensor, 4 * n * sizeof(F)));
@@ -349,7 +362,7 @@ extern "C" int hb_tensorcode(hb_ctx *ctx, const hb_F *msg, size_t n, int trs, in
 
 // ---- C1 ------------------------------------------------------------------------------------------------
 extern "C" int hb_commit_standard(hb_ctx *ctx, const hb_F *poly, size_t N, int K, int trs, int linear_time,
-                                  uint8_t *levels_out, hb_F *tensor_out) {
+                                  uint8_t *levels_out, hb_F *tensor_out) { HB_DEV(ctx);
     if (K <= 0 || N % K) HB_FAIL(ctx, "hb_commit_standard: N must be a multiple of K");
     const size_t B = N / K;
     if (B & (B - 1)) HB_FAIL(ctx, "hb_commit_standard: N/K must be a power of two");
@@ -482,7 +495,7 @@ int hb::commit_encode_chunks_impl(hb_ctx *ctx, const hb_F *poly, size_t nchunks,
 }
 
 extern "C" int hb_commit_encode_chunks(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_out,
-                                       size_t leaf_parts, size_t first_chunk, size_t total_chunks) {
+                                       size_t leaf_parts, size_t first_chunk, size_t total_chunks) { HB_DEV(ctx);
     if (nchunks == 0) return 0;
     if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_commit_encode_chunks: chunk size must be a power of two");
     if (leaf_parts == 0) leaf_parts = 1;
@@ -548,7 +561,7 @@ int hb::elastic_encode_groups_impl(hb_ctx *ctx, const hb_F *chunks, size_t ngrou
 }
 
 extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t ngroups, size_t B, int trs, int linear_time, uint8_t *inner_out,
-                                        size_t leaf_parts, size_t first_group, size_t total_groups) {
+                                        size_t leaf_parts, size_t first_group, size_t total_groups) { HB_DEV(ctx);
     if (ngroups == 0) return 0;
     if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_encode_groups: BUFFER_SPACE must be a power of two");
     if (leaf_parts == 0) leaf_parts = 1;
@@ -564,7 +577,7 @@ extern "C" int hb_elastic_encode_groups(hb_ctx *ctx, const hb_F *chunks, size_t 
     return 0;
 }
 
-extern "C" int hb_md_chain(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves) {
+extern "C" int hb_md_chain(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, size_t nleaves, uint8_t *leaves) { HB_DEV(ctx);
     Staged in(ctx), lv(ctx);
     HB_TRY(in.in(inner, nchunks * nleaves * 32));
     HB_TRY(lv.outbuf(leaves, nleaves * 32, true));
@@ -576,7 +589,7 @@ extern "C" int hb_md_chain(hb_ctx *ctx, const uint8_t *inner, size_t nchunks, si
 
 extern "C" const hb_F *hb_tensor_device(hb_ctx *ctx) { return (const hb_F *)ctx->tensor; }
 
-extern "C" int hb_tensor_gather(hb_ctx *ctx, const uint32_t *col, const uint32_t *row, size_t queries, hb_F *reply) {
+extern "C" int hb_tensor_gather(hb_ctx *ctx, const uint32_t *col, const uint32_t *row, size_t queries, hb_F *reply) { HB_DEV(ctx);
     if (!ctx->tensor) HB_FAIL(ctx, "hb_tensor_gather: no committed tensor in this context");
     if (queries == 0) return 0;
     const size_t B = ctx->tensor_N / ctx->tensor_K, cols = 2 * B / ctx->tensor_trs;
@@ -591,7 +604,7 @@ extern "C" int hb_tensor_gather(hb_ctx *ctx, const uint32_t *col, const uint32_t
     return 0;
 }
 
-extern "C" int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, const hb_F *beta, hb_F *agg) {
+extern "C" int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, const hb_F *beta, hb_F *agg) { HB_DEV(ctx);
     if (K <= 0 || N % K) HB_FAIL(ctx, "hb_aggregate: N must be a multiple of K");
     const size_t B = N / K;
     Staged p(ctx), b(ctx), o(ctx);
@@ -612,7 +625,7 @@ extern "C" int hb_aggregate(hb_ctx *ctx, const hb_F *poly, size_t N, int K, cons
 }
 
 // ---- C2 ------------------------------------------------------------------------------------------------
-extern "C" int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time) {
+extern "C" int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time) { HB_DEV(ctx);
     if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_begin: BUFFER_SPACE must be a power of two");
     elastic_free(ctx);
     ElasticState &el = ctx->el;
@@ -628,7 +641,7 @@ extern "C" int hb_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time)
     return 0;
 }
 
-extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) {
+extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) { HB_DEV(ctx);
     ElasticState &el = ctx->el;
     if (!el.active) HB_FAIL(ctx, "hb_elastic_push: call hb_elastic_begin first");
     const size_t B = el.B;
@@ -653,7 +666,7 @@ extern "C" int hb_elastic_push(hb_ctx *ctx, const hb_F *chunk) {
 
 // Streaming form of the sharded Elastic_PC commit: begin, then hb_elastic_push for this rank's 4 * groups_total / world chunks (its
 // consecutive groups, in order), then hb_elastic_finish / hb_elastic_finish_levels as usual — every rank receives the whole tree.
-extern "C" int hb_dist_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, size_t groups_total) {
+extern "C" int hb_dist_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, size_t groups_total) { HB_DEV(ctx);
     HB_TRY(hb_elastic_begin(ctx, B, trs, linear_time));
     if (ctx->dist.world <= 1) return 0;
     ElasticState &el = ctx->el;
@@ -662,7 +675,7 @@ extern "C" int hb_dist_elastic_begin(hb_ctx *ctx, size_t B, int trs, int linear_
     return 0;
 }
 
-extern "C" int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out) {
+extern "C" int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out) { HB_DEV(ctx);
     ElasticState &el = ctx->el;
     if (!el.active) HB_FAIL(ctx, "hb_elastic_finish: no commit in progress");
     if (el.dist_groups_total) {
@@ -680,7 +693,7 @@ extern "C" int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out) {
 
 // The same, written level by level straight into the caller's per-level arrays (== MT_hashes[l].data(): no intermediate flat copy of the
 // 8B digests on the host).  level_ptrs[l] receives 4B >> l digests, l = 0 .. log2(4B).
-extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels) {
+extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels) { HB_DEV(ctx);
     ElasticState &el = ctx->el;
     if (!el.active) HB_FAIL(ctx, "hb_elastic_finish_levels: no commit in progress");
     if (nlevels != ilog2(4 * el.B) + 1) HB_FAIL(ctx, "hb_elastic_finish_levels: expected log2(4B)+1 levels");
@@ -704,7 +717,7 @@ extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs,
 
 // W1: synthetic default stream of read_stream_PC (witness_stream.cpp:2405-2411).  The recurrence is inherently
 // sequential (x <- x^2 + i), it is the INPUT GENERATOR of test_Elastic_PC, so it is evaluated once on the host.
-extern "C" int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n) {
+extern "C" int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n) { HB_DEV(ctx);
     std::vector<F> v(n);
     F x = mkF(322322, 0);
     for (size_t i = 0; i < n; i++) { v[i] = x; x = fadd(h_fmul(x, x), mkF((u64)i, 0)); }
@@ -714,7 +727,7 @@ extern "C" int hb_stream_pc_test(hb_ctx *ctx, hb_F *out, size_t n) {
 }
 
 // ---- O2 (front half): Elastic_PC open = aggregate + compute_aggregation_reply (Elastic_PC.cpp:316-333, 487-533), chunk at a time ----
-extern "C" int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, const uint32_t *col, const uint32_t *row, size_t queries, size_t nchunks) {
+extern "C" int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int linear_time, const uint32_t *col, const uint32_t *row, size_t queries, size_t nchunks) { HB_DEV(ctx);
     if (B == 0 || (B & (B - 1))) HB_FAIL(ctx, "hb_elastic_open_begin: BUFFER_SPACE must be a power of two");
     ElasticOpen &eo = ctx->eo;
     if (eo.active) { cudaFreeAsync(eo.buf, ctx->stream); stager_free(ctx, eo.stg); eo = ElasticOpen(); }
@@ -733,7 +746,7 @@ extern "C" int hb_elastic_open_begin(hb_ctx *ctx, size_t B, int trs, int linear_
 }
 // Multi-GPU: the next pushes are chunks [first, first + nchunks) of `total`; the reply array then has queries * total entries with
 // reply[q * total + first + i] filled by this pass and zeros elsewhere, so a field all-reduce over the ranks assembles it.
-extern "C" int hb_elastic_open_range(hb_ctx *ctx, size_t first, size_t total) {
+extern "C" int hb_elastic_open_range(hb_ctx *ctx, size_t first, size_t total) { HB_DEV(ctx);
     ElasticOpen &eo = ctx->eo;
     if (!eo.active || eo.idx || first + eo.nchunks > total) HB_FAIL(ctx, "hb_elastic_open_range: call right after hb_elastic_open_begin with a valid range");
     if (eo.queries) {
@@ -751,7 +764,7 @@ extern "C" int hb_elastic_open_range(hb_ctx *ctx, size_t first, size_t total) {
     eo.chunk_first = first; eo.chunk_total = total;
     return 0;
 }
-extern "C" int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *beta_i) {
+extern "C" int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *beta_i) { HB_DEV(ctx);
     ElasticOpen &eo = ctx->eo;
     if (!eo.active || eo.idx >= eo.nchunks) HB_FAIL(ctx, "hb_elastic_open_push: no open in progress / too many chunks");
     const size_t B = eo.B;
@@ -768,7 +781,7 @@ extern "C" int hb_elastic_open_push(hb_ctx *ctx, const hb_F *chunk, const hb_F *
     eo.idx++;
     return 0;
 }
-extern "C" int hb_elastic_open_finish(hb_ctx *ctx, hb_F *agg_out, hb_F *reply_out) {
+extern "C" int hb_elastic_open_finish(hb_ctx *ctx, hb_F *agg_out, hb_F *reply_out) { HB_DEV(ctx);
     ElasticOpen &eo = ctx->eo;
     if (!eo.active) HB_FAIL(ctx, "hb_elastic_open_finish: no open in progress");
     HB_CHECK(ctx, cudaMemcpyAsync(agg_out, eo.agg, eo.B * sizeof(F), cudaMemcpyDefault, ctx->stream));

@@ -184,6 +184,9 @@ inline cudaEvent_t prof_event(hb_ctx *ctx) {
             return 1;                                                                         \
         }                                                                                     \
     } while (0)
+// every C-ABI entry binds the calling thread to the context's device first (a context may be used from any host thread, and other
+// libraries in the process may have changed the current device)
+#define HB_DEV(ctx) do { cudaSetDevice((ctx)->device); } while (0)
 #define HB_TRY(expr) do { int r__ = (expr); if (r__) return r__; } while (0)
 #define HB_FAIL(ctx, msg) do { (ctx)->err = (msg); return 2; } while (0)
 // every kernel launch goes through this so the launch counter is honest

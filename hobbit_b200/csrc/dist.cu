@@ -200,20 +200,20 @@ extern "C" int hb_dist_connect(hb_ctx *ctx, int rank, int world, const void *blo
     return 0;
 }
 
-extern "C" int hb_dist_rank(hb_ctx *ctx) { return ctx->dist.rank; }
-extern "C" int hb_dist_world(hb_ctx *ctx) { return ctx->dist.world; }
-extern "C" int hb_dist_shard(hb_ctx *ctx, int on) { ctx->dist.shard = on != 0 && ctx->dist.world > 1; return 0; }
+extern "C" int hb_dist_rank(hb_ctx *ctx) { HB_DEV(ctx);  return ctx->dist.rank; }
+extern "C" int hb_dist_world(hb_ctx *ctx) { HB_DEV(ctx);  return ctx->dist.world; }
+extern "C" int hb_dist_shard(hb_ctx *ctx, int on) { HB_DEV(ctx);  ctx->dist.shard = on != 0 && ctx->dist.world > 1; return 0; }
 extern "C" int hb_dist_disconnect(hb_ctx *ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); dist_release(ctx); return 0; }
 
 extern "C" void hb_dist_stats(hb_ctx *ctx, uint64_t *out3) { out3[0] = ctx->dist.rseq; out3[1] = ctx->dist.xseq; out3[2] = ctx->dist.epoch; }
 
-extern "C" int hb_dist_barrier(hb_ctx *ctx) {
+extern "C" int hb_dist_barrier(hb_ctx *ctx) { HB_DEV(ctx);
     HB_TRY(dist_barrier_dev(ctx));
     if (ctx->dist.world > 1) HB_TRY(check_peer_error(ctx));
     return 0;
 }
 
-extern "C" int hb_dist_allreduce(hb_ctx *ctx, hb_F *vec, size_t n) {
+extern "C" int hb_dist_allreduce(hb_ctx *ctx, hb_F *vec, size_t n) { HB_DEV(ctx);
     Staged v(ctx);
     HB_TRY(v.outbuf(vec, n * sizeof(F), true));
     HB_TRY(dist_allreduce_vec(ctx, v.as<F>(), n));

@@ -320,7 +320,7 @@ int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks,
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, int deg_D,
                                const long long *L_C, const long long *R_C, const uint32_t *const *nbr_C, const uint64_t *const *w_C,
-                               const long long *L_D, const long long *R_D, const uint32_t *const *nbr_D, const uint64_t *const *w_D) {
+                               const long long *L_D, const long long *R_D, const uint32_t *const *nbr_D, const uint64_t *const *w_D) { HB_DEV(ctx);
     using namespace hb;
     ExpanderDev &ex = ctx->exp;
     if (ex.d_stages) { cudaFree(ex.d_stages); cudaFree(ex.d_rowptr); cudaFree(ex.d_edges); }
@@ -377,7 +377,7 @@ extern "C" int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, 
 
 extern "C" long long hb_expander_codeword_len(hb_ctx *ctx) { return ctx->exp.cwlen; }
 
-extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_F *src, hb_F *dst, long long n, size_t ncols) {
+extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_F *src, hb_F *dst, long long n, size_t ncols) { HB_DEV(ctx);
     using namespace hb;
     if (ncols == 0) return 0;
     Staged d(ctx);

@@ -195,7 +195,7 @@ int merkle_tree_dev(hb_ctx *ctx, uint8_t *levels, size_t nleaves) {
 }  // namespace hb
 
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int hb_blake3_64(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count) {
+extern "C" int hb_blake3_64(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t count) { HB_DEV(ctx);
     using namespace hb;
     Staged s(ctx), d(ctx);
     HB_TRY(s.in(src, count * 64)); HB_TRY(d.outbuf(dst, count * 32));
@@ -205,7 +205,7 @@ extern "C" int hb_blake3_64(hb_ctx *ctx, const uint8_t *src, uint8_t *dst, size_
     return 0;
 }
 
-extern "C" int hb_merkle_tree(hb_ctx *ctx, uint8_t *levels, size_t nleaves) {
+extern "C" int hb_merkle_tree(hb_ctx *ctx, uint8_t *levels, size_t nleaves) { HB_DEV(ctx);
     using namespace hb;
     if (nleaves == 0 || (nleaves & (nleaves - 1))) HB_FAIL(ctx, "hb_merkle_tree: nleaves must be a power of two");
     Staged d(ctx);
@@ -216,7 +216,7 @@ extern "C" int hb_merkle_tree(hb_ctx *ctx, uint8_t *levels, size_t nleaves) {
     return 0;
 }
 
-extern "C" int hb_mt_commit(hb_ctx *ctx, const hb_F *leafs, size_t N, uint8_t *levels) {
+extern "C" int hb_mt_commit(hb_ctx *ctx, const hb_F *leafs, size_t N, uint8_t *levels) { HB_DEV(ctx);
     using namespace hb;
     size_t nl = N / 4;
     if (nl == 0 || (nl & (nl - 1))) HB_FAIL(ctx, "hb_mt_commit: N/4 must be a power of two");

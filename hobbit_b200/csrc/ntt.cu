@@ -239,7 +239,8 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
     const int lb = logn < kLogTile ? logn : kLogTile;
     if (src == dst && lb != logn) HB_FAIL(ctx, "ntt: in-place transform longer than one tile needs a distinct source");
     const size_t smem = sizeof(F) << lb;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};                        // the attribute is per device
+    bool &attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
         HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
         attr_set = true;
@@ -375,7 +376,7 @@ int ntt_cols_dev(hb_ctx *ctx, F *mat, int logn, size_t cols, size_t nz_rows) {
 }  // namespace hb
 
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int hb_ntt_batch(hb_ctx *ctx, hb_F *data, int logn, size_t batch, size_t stride) {
+extern "C" int hb_ntt_batch(hb_ctx *ctx, hb_F *data, int logn, size_t batch, size_t stride) { HB_DEV(ctx);
     using namespace hb;
     if (logn < 0 || logn > 30) HB_FAIL(ctx, "hb_ntt_batch: logn out of range");
     size_t len = (size_t)1 << logn;

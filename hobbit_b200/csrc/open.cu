@@ -242,14 +242,14 @@ whir_zeta_beta_kernel(F *__restrict__ beta, size_t n, int repeats, int hlo, int 
 
 using namespace hb;
 
-extern "C" int hb_vec_zero(hb_ctx *ctx, hb_F *v, size_t n) {
+extern "C" int hb_vec_zero(hb_ctx *ctx, hb_F *v, size_t n) { HB_DEV(ctx);
     if (n == 0) return 0;
     if (is_device_ptr(v)) HB_CHECK(ctx, cudaMemsetAsync(v, 0, n * sizeof(F), ctx->stream));
     else { HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); memset(v, 0, n * sizeof(F)); }
     return 0;
 }
 
-extern "C" int hb_rs_encode_rows(hb_ctx *ctx, const hb_F *src, size_t in_len, size_t rows, hb_F *dst, int logn) {
+extern "C" int hb_rs_encode_rows(hb_ctx *ctx, const hb_F *src, size_t in_len, size_t rows, hb_F *dst, int logn) { HB_DEV(ctx);
     const size_t len = (size_t)1 << logn;
     if (logn < 0 || logn > 28 || in_len > len) HB_FAIL(ctx, "hb_rs_encode_rows: need in_len <= 2^logn <= 2^28");
     if (rows == 0) return 0;
@@ -262,7 +262,7 @@ extern "C" int hb_rs_encode_rows(hb_ctx *ctx, const hb_F *src, size_t in_len, si
     return 0;
 }
 
-extern "C" int hb_matvec_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *w, hb_F *out) {
+extern "C" int hb_matvec_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *w, hb_F *out) { HB_DEV(ctx);
     if (rows == 0 || cols == 0) return 0;
     if (stride < cols) HB_FAIL(ctx, "hb_matvec_cols: stride < cols");
     Staged m(ctx), sw(ctx), o(ctx);
@@ -286,7 +286,7 @@ extern "C" int hb_matvec_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     return 0;
 }
 
-extern "C" int hb_matvec_rows(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *s, hb_F *out) {
+extern "C" int hb_matvec_rows(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const hb_F *s, hb_F *out) { HB_DEV(ctx);
     if (rows == 0) return 0;
     if (stride < cols) HB_FAIL(ctx, "hb_matvec_rows: stride < cols");
     Staged m(ctx), ss(ctx), o(ctx);
@@ -299,7 +299,7 @@ extern "C" int hb_matvec_rows(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     return 0;
 }
 
-extern "C" int hb_axpy(hb_ctx *ctx, hb_F *y, const hb_F *x, const hb_F *a, size_t n) {
+extern "C" int hb_axpy(hb_ctx *ctx, hb_F *y, const hb_F *x, const hb_F *a, size_t n) { HB_DEV(ctx);
     if (n == 0) return 0;
     Staged sy(ctx), sx(ctx);
     HB_TRY(sy.outbuf(y, n * sizeof(F), true));
@@ -311,7 +311,7 @@ extern "C" int hb_axpy(hb_ctx *ctx, hb_F *y, const hb_F *x, const hb_F *a, size_
     return 0;
 }
 
-extern "C" int hb_scatter(hb_ctx *ctx, hb_F *out, size_t n, const uint64_t *idx, const hb_F *val, size_t m) {
+extern "C" int hb_scatter(hb_ctx *ctx, hb_F *out, size_t n, const uint64_t *idx, const hb_F *val, size_t m) { HB_DEV(ctx);
     if (n == 0) return 0;
     Staged so(ctx), si(ctx), sv(ctx);
     HB_TRY(so.outbuf(out, n * sizeof(F)));
@@ -326,7 +326,7 @@ extern "C" int hb_scatter(hb_ctx *ctx, hb_F *out, size_t n, const uint64_t *idx,
     return 0;
 }
 
-extern "C" int hb_gather_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out) {
+extern "C" int hb_gather_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out) { HB_DEV(ctx);
     if (m == 0 || rows == 0) return 0;
     Staged sm(ctx), sc(ctx), so(ctx);
     HB_TRY(sm.in(M, ((rows - 1) * stride + cols) * sizeof(F)));
@@ -338,7 +338,7 @@ extern "C" int hb_gather_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     return 0;
 }
 
-extern "C" int hb_select_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out) {
+extern "C" int hb_select_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t cols, size_t stride, const uint64_t *col, size_t m, hb_F *out) { HB_DEV(ctx);
     if (m == 0 || rows == 0) return 0;
     Staged sm(ctx), sc(ctx), so(ctx);
     HB_TRY(sm.in(M, ((rows - 1) * stride + cols) * sizeof(F)));
@@ -350,7 +350,7 @@ extern "C" int hb_select_cols(hb_ctx *ctx, const hb_F *M, size_t rows, size_t co
     return 0;
 }
 
-extern "C" int hb_transpose(hb_ctx *ctx, const hb_F *in, size_t rows, size_t cols, hb_F *out) {
+extern "C" int hb_transpose(hb_ctx *ctx, const hb_F *in, size_t rows, size_t cols, hb_F *out) { HB_DEV(ctx);
     if (rows == 0 || cols == 0) return 0;
     Staged si(ctx), so(ctx);
     HB_TRY(si.in(in, rows * cols * sizeof(F)));
@@ -361,7 +361,7 @@ extern "C" int hb_transpose(hb_ctx *ctx, const hb_F *in, size_t rows, size_t col
     return 0;
 }
 
-extern "C" int hb_any_nonzero(hb_ctx *ctx, const hb_F *v, size_t n, int *out) {
+extern "C" int hb_any_nonzero(hb_ctx *ctx, const hb_F *v, size_t n, int *out) { HB_DEV(ctx);
     *out = 0;
     if (n == 0) return 0;
     if (!is_device_ptr(v)) {                       // host chunk: a linear scan on the host beats a round trip
@@ -379,7 +379,7 @@ extern "C" int hb_any_nonzero(hb_ctx *ctx, const hb_F *v, size_t n, int *out) {
     return 0;
 }
 
-extern "C" int hb_phi_g_init(hb_ctx *ctx, const hb_F *r, int n, hb_F *out) {
+extern "C" int hb_phi_g_init(hb_ctx *ctx, const hb_F *r, int n, hb_F *out) { HB_DEV(ctx);
     if (n < 1 || n > 28) HB_FAIL(ctx, "hb_phi_g_init: n out of range");
     const size_t N = (size_t)1 << n;
     Staged sr(ctx), so(ctx);
@@ -397,7 +397,7 @@ extern "C" int hb_phi_g_init(hb_ctx *ctx, const hb_F *r, int n, hb_F *out) {
     return 0;
 }
 
-extern "C" int hb_shockwave_leaves(hb_ctx *ctx, const hb_F *enc, int k, size_t cols, uint8_t *leaves) {
+extern "C" int hb_shockwave_leaves(hb_ctx *ctx, const hb_F *enc, int k, size_t cols, uint8_t *leaves) { HB_DEV(ctx);
     if (k < 4 || (k & (k - 1))) HB_FAIL(ctx, "hb_shockwave_leaves: k must be a power of two >= 4");
     if (cols == 0) return 0;
     Staged se(ctx), sl(ctx);
@@ -409,7 +409,7 @@ extern "C" int hb_shockwave_leaves(hb_ctx *ctx, const hb_F *enc, int k, size_t c
     return 0;
 }
 
-extern "C" int hb_change_form(hb_ctx *ctx, hb_F *poly, int logn) {
+extern "C" int hb_change_form(hb_ctx *ctx, hb_F *poly, int logn) { HB_DEV(ctx);
     if (logn < 1 || logn > 30) HB_FAIL(ctx, "hb_change_form: logn out of range");
     const size_t n = (size_t)1 << logn;
     Staged sp(ctx);
@@ -427,7 +427,7 @@ extern "C" int hb_change_form(hb_ctx *ctx, hb_F *poly, int logn) {
     return 0;
 }
 
-extern "C" int hb_regroup(hb_ctx *ctx, const hb_F *in, size_t n, int k, hb_F *out) {
+extern "C" int hb_regroup(hb_ctx *ctx, const hb_F *in, size_t n, int k, hb_F *out) { HB_DEV(ctx);
     if (n == 0 || (n & (n - 1)) || ((size_t)1 << k) > n) HB_FAIL(ctx, "hb_regroup: n must be a power of two >= 2^k");
     Staged si(ctx), so(ctx);
     HB_TRY(si.in(in, n * sizeof(F)));
@@ -438,7 +438,7 @@ extern "C" int hb_regroup(hb_ctx *ctx, const hb_F *in, size_t n, int k, hb_F *ou
     return 0;
 }
 
-extern "C" int hb_whir_poly(hb_ctx *ctx, const hb_F *poly, const hb_F *beta, size_t L, hb_F *coeffs3) {
+extern "C" int hb_whir_poly(hb_ctx *ctx, const hb_F *poly, const hb_F *beta, size_t L, hb_F *coeffs3) { HB_DEV(ctx);
     if (L == 0) HB_FAIL(ctx, "hb_whir_poly: L must be positive");
     HB_TRY(ensure_scratch(ctx));
     Staged sp(ctx), sb(ctx);
@@ -449,7 +449,7 @@ extern "C" int hb_whir_poly(hb_ctx *ctx, const hb_F *poly, const hb_F *beta, siz
     return 0;
 }
 
-extern "C" int hb_whir_fold(hb_ctx *ctx, hb_F *poly, hb_F *beta, size_t L, const hb_F *a) {
+extern "C" int hb_whir_fold(hb_ctx *ctx, hb_F *poly, hb_F *beta, size_t L, const hb_F *a) { HB_DEV(ctx);
     if (L == 0) return 0;
     Staged sp(ctx), sb(ctx);
     HB_TRY(sp.outbuf(poly, 2 * L * sizeof(F), true)); HB_TRY(sb.outbuf(beta, 2 * L * sizeof(F), true));
@@ -459,7 +459,7 @@ extern "C" int hb_whir_fold(hb_ctx *ctx, hb_F *poly, hb_F *beta, size_t L, const
     return 0;
 }
 
-extern "C" int hb_whir_zeta(hb_ctx *ctx, const hb_F *poly, hb_F *beta, int v, const hb_F *zetas, int repeats, const hb_F *pows, hb_F *y) {
+extern "C" int hb_whir_zeta(hb_ctx *ctx, const hb_F *poly, hb_F *beta, int v, const hb_F *zetas, int repeats, const hb_F *pows, hb_F *y) { HB_DEV(ctx);
     if (v < 1 || v > 20 || repeats < 1) HB_FAIL(ctx, "hb_whir_zeta: need 1 <= v <= 20 and repeats >= 1");
     const size_t n = (size_t)1 << v;
     const int hlo = v / 2;

@@ -655,7 +655,7 @@ static int sumcheck3_dev(hb_ctx *ctx, const F *v1, const F *v2, const F *v3, con
 using namespace hb;
 
 // =========================================================================================================
-extern "C" int hb_precompute_beta(hb_ctx *ctx, const hb_F *r, int nr, hb_F *out) {
+extern "C" int hb_precompute_beta(hb_ctx *ctx, const hb_F *r, int nr, hb_F *out) { HB_DEV(ctx);
     if (nr < 0 || nr > 24) HB_FAIL(ctx, "hb_precompute_beta: nr out of range");
     Staged sr(ctx), so(ctx);
     HB_TRY(sr.in(r, (size_t)std::max(nr, 1) * sizeof(F)));
@@ -666,7 +666,7 @@ extern "C" int hb_precompute_beta(hb_ctx *ctx, const hb_F *r, int nr, hb_F *out)
     return 0;
 }
 
-extern "C" int hb_evaluate_vector(hb_ctx *ctx, const hb_F *v, size_t n, const hb_F *r, hb_F *out) {
+extern "C" int hb_evaluate_vector(hb_ctx *ctx, const hb_F *v, size_t n, const hb_F *r, hb_F *out) { HB_DEV(ctx);
     if (n == 0 || (n & (n - 1))) HB_FAIL(ctx, "hb_evaluate_vector: n must be a power of two");
     HB_TRY(ensure_scratch(ctx));
     Staged sv(ctx);
@@ -680,7 +680,7 @@ extern "C" int hb_evaluate_vector(hb_ctx *ctx, const hb_F *v, size_t n, const hb
     return 0;
 }
 
-extern "C" int hb_sumcheck2(hb_ctx *ctx, const hb_F *v1, const hb_F *v2, size_t n, const hb_F *prev_r, hb_F *proof, double *ps) {
+extern "C" int hb_sumcheck2(hb_ctx *ctx, const hb_F *v1, const hb_F *v2, size_t n, const hb_F *prev_r, hb_F *proof, double *ps) { HB_DEV(ctx);
     if (n == 0 || (n & (n - 1))) HB_FAIL(ctx, "hb_sumcheck2: n must be a power of two");
     HB_TRY(ensure_scratch(ctx));
     int rounds = ilog2(n);
@@ -724,7 +724,7 @@ extern "C" int hb_sumcheck2(hb_ctx *ctx, const hb_F *v1, const hb_F *v2, size_t 
 }
 
 extern "C" int hb_sumcheck3(hb_ctx *ctx, const hb_F *v1, const hb_F *v2, const hb_F *v3, size_t n, const hb_F *prev_r,
-                            hb_F *proof, double *ps) {
+                            hb_F *proof, double *ps) { HB_DEV(ctx);
     if (n == 0 || (n & (n - 1))) HB_FAIL(ctx, "hb_sumcheck3: n must be a power of two");
     HB_TRY(ensure_scratch(ctx));
     Staged a(ctx), b(ctx), c(ctx);
@@ -844,7 +844,7 @@ static int batch_sumcheck3_dev(hb_ctx *ctx, const F *d1, const F *d2, const F *d
 }
 
 extern "C" int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, const hb_F *t3, const size_t *sizes, int batches,
-                                  const hb_F *a_in, hb_F *proof, double *ps) {
+                                  const hb_F *a_in, hb_F *proof, double *ps) { HB_DEV(ctx);
     size_t tot = 0;
     for (int b = 0; b < batches; b++) tot += sizes[b];
     Staged s1(ctx), s2(ctx), s3(ctx);
@@ -855,7 +855,7 @@ extern "C" int hb_batch_sumcheck3(hb_ctx *ctx, const hb_F *t1, const hb_F *t2, c
 }
 
 extern "C" int hb_mul_tree(hb_ctx *ctx, const hb_F *input, int vectors, size_t n, const hb_F *prev_r, const hb_F *x_rand,
-                           hb_F *out, size_t *written, int *nfr, double *ps) {
+                           hb_F *out, size_t *written, int *nfr, double *ps) { HB_DEV(ctx);
     if (n < 2 || (n & (n - 1)) || vectors < 1 || (vectors & (vectors - 1)))
         HB_FAIL(ctx, "hb_mul_tree: vectors and n must be powers of two (pad with F(1)/zero vectors as the reference does)");
     HB_TRY(ensure_scratch(ctx));
@@ -1211,7 +1211,7 @@ static int build_layers(hb_ctx *ctx, const F *xy, size_t total, int layers, std:
 }
 
 extern "C" int hb_stream_sumcheck_layer(hb_ctx *ctx, const hb_F *xy, size_t total, size_t B, int layer_id, const hb_F *r, int nr,
-                                        const hb_F *old_claim, const hb_F *rnd4, hb_F *new_claim, hb_F *new_r, int *n_new_r, double *ps) {
+                                        const hb_F *old_claim, const hb_F *rnd4, hb_F *new_claim, hb_F *new_r, int *n_new_r, double *ps) { HB_DEV(ctx);
     if (total == 0 || (total & (total - 1))) HB_FAIL(ctx, "hb_stream_sumcheck_layer: stream size must be a power of two");
     Staged sx(ctx);
     HB_TRY(sx.in(xy, total * sizeof(F)));
@@ -1232,7 +1232,7 @@ extern "C" int hb_stream_sumcheck_layer(hb_ctx *ctx, const hb_F *xy, size_t tota
 // S6: prove_multiplication_tree_stream_shallow (sumcheck.cpp:1746-1915) with the stream resident in HBM.
 // x_rand: log2(vectors) points for the product tree; rnd: 4 values (a, b0, b1, pad) per streamed layer, top layer first.
 extern "C" int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int vectors, size_t B, int distance, int naive,
-                                  const hb_F *prev_r, const hb_F *x_rand, const hb_F *rnd, hb_F *out, int *layers_out, double *ps) {
+                                  const hb_F *prev_r, const hb_F *x_rand, const hb_F *rnd, hb_F *out, int *layers_out, double *ps) { HB_DEV(ctx);
     if (total == 0 || (total & (total - 1)) || vectors < 2 || (vectors & (vectors - 1))) HB_FAIL(ctx, "hb_mul_tree_stream: sizes must be powers of two, vectors >= 2");
     Staged sx(ctx);
     HB_TRY(sx.in(xy, total * sizeof(F)));
@@ -1290,7 +1290,7 @@ extern "C" int hb_mul_tree_stream(hb_ctx *ctx, const hb_F *xy, size_t total, int
 
 // prove_gate_consistency_standard (sumcheck.cpp:434-501).  out: (a,b,c,d,e,rand) per round, then the final add, L, R, O, mul, beta.
 extern "C" int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *add_gate, size_t n,
-                                            const hb_F *r, hb_F *out) {
+                                            const hb_F *r, hb_F *out) { HB_DEV(ctx);
     if (n < 2 || (n & (n - 1))) HB_FAIL(ctx, "hb_gate_consistency_standard: n must be a power of two >= 2");
     HB_TRY(ensure_scratch(ctx));
     const int rounds = ilog2(n);
@@ -1339,7 +1339,7 @@ extern "C" int hb_gate_consistency_standard(hb_ctx *ctx, const hb_F *L, const hb
 // rnd10 = a[4] (generate_randomness(4)) | b[6] (generate_randomness(6)), drawn by the host in that order.
 // out: R[nch] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add,mul,beta | Peval[6][nch] | P2 flat proof (4*log2 nch + 3).
 extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B,
-                                          const hb_F *r, const hb_F *rnd10, hb_F *out, double *ps) {
+                                          const hb_F *r, const hb_F *rnd10, hb_F *out, double *ps) { HB_DEV(ctx);
     if (B < 2 || (B & (B - 1)) || cs < B || (cs & (cs - 1))) HB_FAIL(ctx, "hb_gate_consistency_stream: sizes must be powers of two, cs >= B >= 2");
     HB_TRY(ensure_scratch(ctx));
     const size_t nch = cs / B; const int lgB = ilog2(B), lgn = ilog2(nch);
@@ -1465,7 +1465,7 @@ extern "C" int hb_gate_consistency_stream(hb_ctx *ctx, const hb_F *L, const hb_F
 // hobbit_b200/dist.py): accumulates the cubic coefficients of sum_j prod_t (in_t[2j] + X (in_t[2j+1] - in_t[2j])) over L pairs and
 // writes out_t[j] = in_t[2j] + rand * (in_t[2j+1] - in_t[2j])  (the S2 schedule: fold with the incoming challenge, sumcheck.cpp:1987-2014).
 extern "C" int hb_sc3_round(hb_ctx *ctx, const hb_F *in1, const hb_F *in2, const hb_F *in3, hb_F *out1, hb_F *out2, hb_F *out3, size_t L,
-                            const hb_F *rand, hb_F *coeffs4) {
+                            const hb_F *rand, hb_F *coeffs4) { HB_DEV(ctx);
     HB_TRY(ensure_scratch(ctx));
     if (!is_device_ptr(in1) || !is_device_ptr(out1)) HB_FAIL(ctx, "hb_sc3_round: tables must be device memory");
     Tabs<3> t;
@@ -1480,7 +1480,7 @@ extern "C" int hb_sc3_round(hb_ctx *ctx, const hb_F *in1, const hb_F *in2, const
 // S8: prove_gate_consistency_lookups (sumcheck.cpp:503-794) on a transcript resident in HBM.  rnd13 = a[5] | b[8], lookup_rand2 = lookup_rand[0..1].
 // out: R[nch] | (a,b,c,d,e,rand) x log2 B | final L,R,O,add_L,add_R,mul,lkp,lkp_O,beta | Peval[8][nch] | P2 flat proof (4*log2 nch + 3).
 extern "C" int hb_gate_consistency_lookups_stream(hb_ctx *ctx, const hb_F *L, const hb_F *R, const hb_F *O, const hb_F *S, size_t cs, size_t B,
-                                                  const hb_F *r, const hb_F *lookup_rand2, const hb_F *rnd13, hb_F *out, double *ps) {
+                                                  const hb_F *r, const hb_F *lookup_rand2, const hb_F *rnd13, hb_F *out, double *ps) { HB_DEV(ctx);
     if (B < 2 || (B & (B - 1)) || cs < B || (cs & (cs - 1))) HB_FAIL(ctx, "hb_gate_consistency_lookups_stream: sizes must be powers of two, cs >= B >= 2");
     HB_TRY(ensure_scratch(ctx));
     const size_t nch = cs / B; const int lgB = ilog2(B), lgn = ilog2(nch);

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) sql_kernel(TrTuple *__restrict__ tr, int 
 using namespace hb;
 
 // MLP_inference on the GPU: fills the context's resident trace as if the producer had been drained (hb_trace_begin/push), one pass.
-extern "C" int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t *n_records) {
+extern "C" int hb_trace_generate_mlp(hb_ctx *ctx, const int *layer_size, int nsizes, size_t *n_records) { HB_DEV(ctx);
     if (nsizes < 2) HB_FAIL(ctx, "hb_trace_generate_mlp: need at least an input and an output layer");
     size_t recs = 0, wt = 0; int maxw = 0;
     for (int i = 0; i + 1 < nsizes; i++) {
@@ -421,7 +421,7 @@ static int rank_positions(hb_ctx *ctx, const int *cols, size_t n, size_t nkeys, 
 
 // the pruned MLP on the GPU (fun == 8): rowptr / cols are HOST arrays (the reference driver's sparsity pattern)
 extern "C" int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hidden, int n_out, const int *rowptr0, const int *cols0, const int *rowptr1,
-                                            const int *cols1, size_t *n_records) {
+                                            const int *cols1, size_t *n_records) { HB_DEV(ctx);
     if (n_inputs < 1 || n_hidden < 1 || n_out < 1) HB_FAIL(ctx, "hb_trace_generate_pruned_mlp: layer sizes must be positive");
     const int m[2] = {n_hidden, n_out}, nin[2] = {n_inputs, n_hidden};
     const int *rp[2] = {rowptr0, rowptr1}, *cl[2] = {cols0, cols1};
@@ -494,7 +494,7 @@ extern "C" int hb_trace_generate_pruned_mlp(hb_ctx *ctx, int n_inputs, int n_hid
 }
 
 // the SQL range query on the GPU (fun == 6: `pigeon 6 b n d`, input_size = 2^n rows)
-extern "C" int hb_trace_generate_sql(hb_ctx *ctx, int input_size, size_t *n_records) {
+extern "C" int hb_trace_generate_sql(hb_ctx *ctx, int input_size, size_t *n_records) { HB_DEV(ctx);
     if (input_size < 1) HB_FAIL(ctx, "hb_trace_generate_sql: need at least one row");
     const size_t recs = sql_records(input_size);
     if ((size_t)input_size * (kSqlRowLabels + 1) + 300 >= ((size_t)1 << 31)) HB_FAIL(ctx, "hb_trace_generate_sql: labels do not fit the reference's int");
@@ -508,7 +508,7 @@ extern "C" int hb_trace_generate_sql(hb_ctx *ctx, int input_size, size_t *n_reco
 }
 
 // AES on the GPU (fun == 5: `pigeon 5 b n d`, input_size = 2^n blocks): the resident trace of one pass of the CPU evaluator
-extern "C" int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records) {
+extern "C" int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_records) { HB_DEV(ctx);
     if (input_size < 1) HB_FAIL(ctx, "hb_trace_generate_aes: need at least one block");
     const size_t n = (size_t)input_size, recs = n * kAesRecs + 16 * n + 161;
     if (n * (16 + kAesLabels) + 162 >= ((size_t)1 << 31) || n * kAesLookups >= ((size_t)1 << 31)) HB_FAIL(ctx, "hb_trace_generate_aes: labels do not fit the reference's int");
@@ -523,7 +523,7 @@ extern "C" int hb_trace_generate_aes(hb_ctx *ctx, int input_size, size_t *n_reco
     return 0;
 }
 
-extern "C" int hb_trace_begin(hb_ctx *ctx, size_t capacity) {
+extern "C" int hb_trace_begin(hb_ctx *ctx, size_t capacity) { HB_DEV(ctx);
     TraceState &t = ctx->trace;
     if (t.tuples && t.capacity < capacity) { cudaFree(t.tuples); t.tuples = nullptr; }
     if (!t.tuples) { HB_CHECK(ctx, cudaMalloc(&t.tuples, std::max<size_t>(capacity, 1) * 80)); t.capacity = std::max<size_t>(capacity, 1); }
@@ -531,7 +531,7 @@ extern "C" int hb_trace_begin(hb_ctx *ctx, size_t capacity) {
     return 0;
 }
 
-extern "C" int hb_trace_push(hb_ctx *ctx, const void *tuples, size_t n, int *done) {
+extern "C" int hb_trace_push(hb_ctx *ctx, const void *tuples, size_t n, int *done) { HB_DEV(ctx);
     TraceState &t = ctx->trace;
     if (!t.tuples) HB_FAIL(ctx, "hb_trace_push: call hb_trace_begin first");
     if (done) *done = t.done ? 1 : 0;
@@ -587,7 +587,7 @@ static int trace_index(hb_ctx *ctx) {
     return 0;
 }
 
-extern "C" int hb_trace_finish(hb_ctx *ctx, size_t *n_tuples, size_t *n_ops, size_t *n_deletes) {
+extern "C" int hb_trace_finish(hb_ctx *ctx, size_t *n_tuples, size_t *n_ops, size_t *n_deletes) { HB_DEV(ctx);
     if (!ctx->trace.tuples) HB_FAIL(ctx, "hb_trace_finish: no trace");
     HB_TRY(trace_index(ctx));
     if (n_tuples) *n_tuples = ctx->trace.n;
@@ -603,7 +603,7 @@ static int trace_check(hb_ctx *ctx, size_t cs, const char *who) {
     return 0;
 }
 
-extern "C" int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out) {
+extern "C" int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out) { HB_DEV(ctx);
     HB_TRY(trace_check(ctx, cs, "hb_trace_witness"));
     TraceState &t = ctx->trace;
     Staged so(ctx);
@@ -615,7 +615,7 @@ extern "C" int hb_trace_witness(hb_ctx *ctx, size_t cs, hb_F *out) {
     return 0;
 }
 
-extern "C" int hb_trace_circuit(hb_ctx *ctx, size_t cs, hb_F *out) {
+extern "C" int hb_trace_circuit(hb_ctx *ctx, size_t cs, hb_F *out) { HB_DEV(ctx);
     HB_TRY(trace_check(ctx, cs, "hb_trace_circuit"));
     TraceState &t = ctx->trace;
     Staged so(ctx);
@@ -627,7 +627,7 @@ extern "C" int hb_trace_circuit(hb_ctx *ctx, size_t cs, hb_F *out) {
     return 0;
 }
 
-extern "C" int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S) {
+extern "C" int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F *L, hb_F *R, hb_F *O, hb_F *S) { HB_DEV(ctx);
     HB_TRY(trace_check(ctx, cs, "hb_trace_transcript"));
     TraceState &t = ctx->trace;
     Staged sl(ctx), sr(ctx), so(ctx), ss(ctx);
@@ -640,7 +640,7 @@ extern "C" int hb_trace_transcript(hb_ctx *ctx, size_t cs, int has_lookups, hb_F
     return 0;
 }
 
-extern "C" int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy) {
+extern "C" int hb_trace_wiring(hb_ctx *ctx, size_t cs, const hb_F *a_w, const hb_F *b_w, hb_F *xy) { HB_DEV(ctx);
     HB_TRY(trace_check(ctx, cs, "hb_trace_wiring"));
     TraceState &t = ctx->trace;
     Staged so(ctx);
@@ -681,7 +681,7 @@ static int lookup_index(hb_ctx *ctx, unsigned **access, unsigned **lkp_pos, void
     return 0;
 }
 
-extern "C" int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand4, hb_F *xy) {
+extern "C" int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand4, hb_F *xy) { HB_DEV(ctx);
     HB_TRY(trace_check(ctx, cs, "hb_trace_lookup_basic"));
     TraceState &t = ctx->trace;
     Staged so(ctx);
@@ -699,7 +699,7 @@ extern "C" int hb_trace_lookup_basic(hb_ctx *ctx, size_t cs, const hb_F *lookup_
     return 0;
 }
 
-extern "C" int hb_trace_lookup_witness(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand2, hb_F *out) {
+extern "C" int hb_trace_lookup_witness(hb_ctx *ctx, size_t cs, const hb_F *lookup_rand2, hb_F *out) { HB_DEV(ctx);
     HB_TRY(trace_check(ctx, cs, "hb_trace_lookup_witness"));
     TraceState &t = ctx->trace;
     Staged so(ctx);

@@ -176,6 +176,42 @@ def test_elastic_zero_chunk_and_ragged_tail(ctx):
     assert np.array_equal(ctx.elastic_commit([c] * 4, B, trs, 0), orc.elastic_commit(4 * B, B, trs, 0))
 
 
+def test_elastic_push_from_a_reused_pinned_buffer(ctx):
+    """A streaming producer refills its (pinned) chunk buffer as soon as hb_elastic_push returns: the push must have READ the buffer by
+    then (the copy runs on the copy stream and is waited for; round 1 returned while the DMA was still pending)."""
+    B, trs = 1 << 12, 16
+    rng = np.random.default_rng(31)
+    stream = rand_field(rng, 12 * B, full=True)
+    chunks = [stream[i * B:(i + 1) * B] for i in range(12)]
+    orc = Checker("orc")
+    srand(1); orc.expander_init_store(trs)
+    ctx.expander_set(trs, orc.expander_graphs(trs))
+    for lin in (0, 1):
+        want = ctx.elastic_commit(chunks, B, trs, lin)
+        got = ctx.elastic_commit(chunks, B, trs, lin, reuse_pinned=True)
+        assert np.array_equal(want, got)
+
+
+def test_aggregate_never_trusts_a_host_address(ctx):
+    """hb_aggregate must aggregate the data it is GIVEN: a host buffer at the same address with new contents after a commit (round 1 used
+    the stale device copy whenever address and size matched)."""
+    N, K, trs = 1 << 14, 4, 16
+    orc = Checker("orc")
+    srand(1); orc.expander_init_store(trs)
+    ctx.expander_set(trs, orc.expander_graphs(trs))
+    rng = np.random.default_rng(32)
+    poly = rand_field(rng, N, full=True)
+    ctx.commit_standard(poly, K, trs, 1)
+    beta = rand_field(rng, K, full=True)
+    a0 = ctx.aggregate(poly, K, beta)
+    poly[:] = rand_field(rng, N, full=True)                          # same address, same size, new contents
+    a1 = ctx.aggregate(poly, K, beta)
+    want = np.zeros((N // K, 2), dtype=np.uint64)
+    for i in range(K):
+        want = orc.binop(0, want, orc.binop(2, np.repeat(beta[i:i + 1], N // K, axis=0), poly[i * (N // K):(i + 1) * (N // K)]))
+    assert np.array_equal(a1, want) and not np.array_equal(a0, a1)
+
+
 def test_beta_eval(ctx, chk):
     rng = np.random.default_rng(9)
     for nr in (0, 1, 5, 12, 13, 16):
