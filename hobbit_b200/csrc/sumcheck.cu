@@ -75,6 +75,13 @@ template <int NT> static inline void coeffs_from_evals(F *co) {
 #ifndef HB_SC_THREADS
 #define HB_SC_THREADS 256
 #endif
+// the tables are streamed exactly once per round: HB_SC_STREAM=1 marks the loads evict-first (ld.global.cs)
+#if defined(HB_SC_STREAM) && HB_SC_STREAM
+__device__ __forceinline__ F ld_stream(const F *p) { ulonglong2 v; asm volatile("ld.global.cs.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p)); return mkF(v.x, v.y); }
+#define HB_SC_LD(p) ld_stream(p)
+#else
+#define HB_SC_LD(p) (*(p))
+#endif
 // (A variant that kept the next iterations' table entries in flight with cp.async into thread-private shared-memory slots was measured
 // and was 4 % slower: with both integer pipes ~60 % busy the kernel is not waiting on HBM, see profiles/r02_summary.md.)
 template <int NT, int MODE, bool INTERLEAVED>
@@ -104,7 +111,7 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
             for (int k = 2; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
         } else {
 #pragma unroll
-            for (int k = 0; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
+            for (int k = 0; k < NT; k++) { x[k] = HB_SC_LD(&t.in[k][2 * j]); y[k] = HB_SC_LD(&t.in[k][2 * j + 1]); }
         }
 #pragma unroll
         for (int k = 0; k < NT; k++) d[k] = fsub(y[k], x[k]);
@@ -527,7 +534,10 @@ static inline unsigned grid_for(hb_ctx *ctx, size_t L) {
 template <int NT, int MODE, bool IL>
 static int launch_round(hb_ctx *ctx, const Tabs<NT> &t, size_t L, F r, F *coeffs_host /* NT+1, may be null for FOLD_ONLY */) {
     HB_TRY(ensure_scratch(ctx));
-    const size_t want = (L + HB_SC_THREADS - 1) / HB_SC_THREADS, cap = std::min<size_t>((size_t)ctx->sm_count * (1024 / HB_SC_THREADS), kMaxRedBlocks);
+#ifndef HB_SC_WAVES
+#define HB_SC_WAVES (1024 / HB_SC_THREADS)
+#endif
+    const size_t want = (L + HB_SC_THREADS - 1) / HB_SC_THREADS, cap = std::min<size_t>((size_t)ctx->sm_count * HB_SC_WAVES, kMaxRedBlocks);
     HB_LAUNCH(ctx, (sc_round_kernel<NT, MODE, IL>), (unsigned)std::max<size_t>(1, std::min(want, cap)), HB_SC_THREADS, 0, t, L, r, red_args(ctx));
     if (MODE != FOLD_ONLY) { HB_TRY(read_result(ctx, NT + 1, coeffs_host)); coeffs_from_evals<NT>(coeffs_host); }
     return 0;

@@ -146,6 +146,7 @@ static void gen(Graph &g, long long L, long long R, int d) {
     g.L = L; g.R = R; g.nbr.resize(L * d); g.w.resize(L * d);
     for (long long i = 0; i < L; i++) for (int j = 0; j < d; j++) { g.nbr[i * d + j] = (uint32_t)(rand() % R); g.w[i * d + j] = (uint64_t)random(); }
 }
+static long long g_store_n = -1; static int g_store_levels = 0;       // the code expander_init_store / expander_adopt installed last
 static long long init_rec(long long n, int dep, int &levels) {
     if (n <= kThreshold) return n;
     levels = dep + 1 > levels ? dep + 1 : levels;
@@ -164,6 +165,7 @@ void expander_adopt(long long n, int levels, const std::vector<ext_graph> &C, co
         LD[d] = gD[d].L; RD[d] = gD[d].R; nD[d] = gD[d].nbr.data(); wD[d] = gD[d].w.data();
     }
     CK(hb_expander_set(backend(), n, levels, kCn, kDn, LC, RC, nC, wC, LD, RD, nD, wD));
+    g_store_n = n; g_store_levels = levels;
 }
 const host_graph &expander_graph(int which, int dep) {
     static host_graph g;
@@ -174,6 +176,7 @@ const host_graph &expander_graph(int which, int dep) {
 long long expander_init_store(long long n, int dep) {
     int levels = 0;
     long long cw = init_rec(n, dep, levels);
+    g_store_n = n; g_store_levels = levels;
     long long LC[100], RC[100], LD[100], RD[100]; const uint32_t *nC[100], *nD[100]; const uint64_t *wC[100], *wD[100];
     for (int d = 0; d < levels; d++) {
         LC[d] = gC[d].L; RC[d] = gC[d].R; nC[d] = gC[d].nbr.data(); wC[d] = gC[d].w.data();
@@ -181,6 +184,56 @@ long long expander_init_store(long long n, int dep) {
     }
     CK(hb_expander_set(backend(), n, levels, kCn, kDn, LC, RC, nC, wC, LD, RD, nD, wD));
     return cw;
+}
+
+// E3: encode() (linear_code_encode.h:122-191) — the variant whose graph is re-drawn on every call from fixed libc seeds (srand(666 + dep)
+// for the C stage: target, then weight; srand(2 (666 + dep)) for the D stage: weight, then target).  The graph therefore only depends on
+// n: it is drawn once per n (same rand() sequence), installed on the GPU for the call, and the code expander_init_store had installed is
+// put back afterwards.  The libc state the caller sees afterwards is the one the reference leaves: that of the depth-0 D stage.
+int encode(const F *src, F *dst, long long n, int) {
+    struct Code { long long n = -1; int levels = 0; std::vector<Graph> C, D; long long cw = 0; };
+    static Code code;
+    if (code.n != n) {
+        code = Code(); code.n = n;
+        long long nn = n; int levels = 0;
+        while (nn > kThreshold) { nn = (long long)(kAlpha * nn); levels++; }
+        code.levels = levels; code.C.resize(levels); code.D.resize(levels);
+        std::vector<long long> Ls(levels + 1), ns(levels + 1);
+        ns[0] = n;
+        for (int d = 0; d < levels; d++) ns[d + 1] = (long long)(kAlpha * ns[d]);
+        Ls[levels] = ns[levels];                                                // n <= threshold: the message itself
+        for (int d = levels - 1; d >= 0; d--) {
+            const long long L = Ls[d + 1], RD = (long long)(ns[d] * (kR - 1) - L);
+            Graph &c = code.C[d], &g = code.D[d];
+            c.L = ns[d]; c.R = ns[d + 1]; c.nbr.resize(c.L * kCn); c.w.resize(c.L * kCn);
+            srand(666 + d);
+            for (long long i = 0; i < c.L; i++) for (int j = 0; j < kCn; j++) { c.nbr[i * kCn + j] = (uint32_t)(rand() % (int)c.R); c.w[i * kCn + j] = (uint64_t)rand(); }
+            g.L = L; g.R = RD; g.nbr.resize(L * kDn); g.w.resize(L * kDn);
+            srand(2 * (666 + d));
+            for (long long i = 0; i < L; i++) for (int j = 0; j < kDn; j++) { g.w[i * kDn + j] = (uint64_t)rand(); g.nbr[i * kDn + j] = (uint32_t)(rand() % RD); }
+            Ls[d] = ns[d] + L + RD;
+        }
+        code.cw = Ls[0];
+    }
+    if (code.levels == 0) { for (long long i = 0; i < n; i++) dst[i] = src[i]; return (int)n; }
+    auto install = [&](long long nn, int levels, const Graph *C, const Graph *D) {
+        long long LC[100], RC[100], LD[100], RD[100]; const uint32_t *nC[100], *nD[100]; const uint64_t *wC[100], *wD[100];
+        for (int d = 0; d < levels; d++) {
+            LC[d] = C[d].L; RC[d] = C[d].R; nC[d] = C[d].nbr.data(); wC[d] = C[d].w.data();
+            LD[d] = D[d].L; RD[d] = D[d].R; nD[d] = D[d].nbr.data(); wD[d] = D[d].w.data();
+        }
+        CK(hb_expander_set(backend(), nn, levels, kCn, kDn, LC, RC, nC, wC, LD, RD, nD, wD));
+    };
+    const long long store_n = g_store_n; const int store_levels = g_store_levels;
+    install(n, code.levels, code.C.data(), code.D.data());
+    std::vector<F> out(2 * n);
+    CK(hb_encode_batch(backend(), (const hb_F *)src, (hb_F *)out.data(), n, 1));
+    memcpy(dst, out.data(), (size_t)code.cw * sizeof(F));
+    if (store_n > 0) install(store_n, store_levels, gC, gD);                      // the code of expander_init_store is the resident one
+    // leave libc where the reference's call leaves it: srand(2 * 666) followed by the depth-0 D stage's 2 * L * dn draws
+    srand(2 * 666);
+    for (long long i = 0; i < code.D[0].L * kDn * 2; i++) rand();
+    return (int)code.cw;
 }
 
 F mimc_hash(F input, F k) { F o; hb_mimc_hash((const hb_F *)&input, (const hb_F *)&k, (hb_F *)&o); return o; }

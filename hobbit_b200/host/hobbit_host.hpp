@@ -95,6 +95,8 @@ int dist_world();
 std::vector<F> generate_randomness(int size);
 void trace_rng(const char *where);           // HOBBIT_TRACE_RNG=1: fingerprint of the libc random() state on stderr
 long long expander_init_store(long long n, int dep = 0);
+// E3: encode() (linear_code_encode.h:122-191): the expander code whose graph is re-drawn from fixed seeds on every call; returns n + L + R
+int encode(const F *src, F *dst, long long n, int dep = 0);
 F mimc_hash(F input, F k);
 void precompute_beta(std::vector<F> r, std::vector<F> &B);
 F evaluate_vector(std::vector<F> v, std::vector<F> r);

@@ -676,6 +676,7 @@ extern "C" {
 void *hobbit_c_backend(int device) { hobbit::init_backend(device); return hobbit::backend(); }
 void hobbit_c_set_globals(size_t buffer_space, int trs, int lin) { hobbit::BUFFER_SPACE = buffer_space; hobbit::tensor_row_size = trs; hobbit::linear_time = lin != 0; }
 long long hobbit_c_expander_init_store(long long n) { return hobbit::expander_init_store(n); }
+int hobbit_c_encode_reseed(const hb_F *src, hb_F *dst, long long n) { return hobbit::encode(reinterpret_cast<const hobbit::F *>(src), reinterpret_cast<hobbit::F *>(dst), n); }
 void hobbit_c_generate_randomness(int n, hb_F *out) { std::vector<hobbit::F> v = hobbit::generate_randomness(n); memcpy(out, v.data(), (size_t)n * sizeof(hb_F)); }
 // the queries of Elastic_PC open (:649-655), drawn with rand() into the global I; col/row receive I[i][0], I[i][1]
 void hobbit_c_elastic_draw_queries(int queries, uint32_t *col, uint32_t *row) {

@@ -196,6 +196,37 @@ static long long encode_rec(const F *src, F *dst, long long n, int dep) {
 }
 int orc_encode_monolithic(const F *src, F *dst, long long n) { return (int)encode_rec(src, dst, n, 0); }
 
+/* E3: encode() (linear_code_encode.h:122-191) — the variant that re-draws its graph on every call from FIXED libc seeds: the C stage of
+ * depth dep after srand(666 + dep) (per edge: target = rand() % R, then weight = rand()), the D stage after srand(2 * (666 + dep)) (per
+ * edge: weight = rand(), THEN target = rand() % R).  Sizes as in expander_init (R_C = alpha n; D: L x (n (r - 1) - L)).  The libc state
+ * a caller sees afterwards is the one the depth-0 D stage leaves behind. */
+static long long encode_reseed_rec(const F *src, F *dst, long long n, int dep) {
+    if (n <= kDistThreshold) { for (long long i = 0; i < n; i++) dst[i] = src[i]; return n; }
+    for (long long i = 0; i < n; i++) dst[i] = src[i];
+    long long R = (long long)(kAlpha * n);
+    F *y = (F *)calloc((size_t)R, sizeof(F));
+    srand(666 + dep);
+    for (long long i = 0; i < n; i++)
+        for (int d = 0; d < kCn; d++) {
+            int t = rand() % (int)R;
+            F wv = { (uint64_t)rand(), 0 };
+            y[t] = f_add(y[t], f_mul(wv, src[i]));
+        }
+    long long L = encode_reseed_rec(y, dst + n, R, dep + 1);
+    free(y);
+    long long RD = (long long)(n * (kR - 1) - L);
+    for (long long i = 0; i < RD; i++) dst[n + L + i] = f_int(0);
+    srand(2 * (666 + dep));
+    for (long long i = 0; i < L; i++)
+        for (int d = 0; d < kDn; d++) {
+            F wv = { (uint64_t)rand(), 0 };
+            long long t = rand() % RD;
+            dst[n + L + t] = f_add(dst[n + L + t], f_mul(dst[n + i], wv));
+        }
+    return n + L + RD;
+}
+int orc_encode_reseed(const F *src, F *dst, long long n) { return (int)encode_reseed_rec(src, dst, n, 0); }
+
 /* ------------------------------------------------------------------ H1 ---
  * Blake3_hash.cpp:5-10 = BLAKE3 of exactly 64 bytes -> one compression with
  * cv = IV, counter 0, block_len 64, flags CHUNK_START|CHUNK_END|ROOT

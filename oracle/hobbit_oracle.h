@@ -39,6 +39,7 @@ long long orc_expander_dims(int which, int dep, long long *R, int *deg);
 void orc_expander_dump(int which, int dep, uint32_t *nbr, uint64_t *w);
 void orc_expander_install(int which, int dep, long long L, long long R, int deg, const uint32_t *nbr, const uint64_t *w);
 int  orc_encode_monolithic(const orc_F *src, orc_F *dst, long long n);
+int  orc_encode_reseed(const orc_F *src, orc_F *dst, long long n);       /* E3: encode(), graph re-drawn from fixed seeds per call */
 /* H1..H4 */
 void orc_blake3_hash(const uint8_t *src64, uint8_t *dst32);
 void orc_md_leaf(const orc_F *xyzw, const uint8_t *prev, uint8_t *out);

@@ -119,6 +119,10 @@ void ref_expander_dump(int which, int dep, uint32_t *nbr, uint64_t *w) {
 int ref_encode_monolithic(const uint64_t *src, uint64_t *dst, long long n) {
     return encode_monolithic((const F *)src, (F *)dst, n);
 }
+// E3: encode() (linear_code_encode.h:122-191); needs the graph DIMENSIONS of expander_init / expander_init_store(n) in _C[] / D[]
+int ref_encode_reseed(const uint64_t *src, uint64_t *dst, long long n) {
+    return encode((const F *)src, (F *)dst, n);
+}
 
 // ---- H1..H4 ---------------------------------------------------------------
 void ref_blake3_hash(const uint8_t *src, uint8_t *dst) { blake3_hash((uint8_t *)src, dst); }

@@ -125,6 +125,13 @@ class Checker:
         cw = self.fn("encode_monolithic", ctypes.c_int)(_p(s), _p(d), ctypes.c_longlong(n))
         return d, cw
 
+    def encode_reseed(self, src, n):
+        """E3: encode() — graph re-drawn from fixed seeds per call; returns the n + L + R codeword entries."""
+        s = F(src)
+        d = fzeros(2 * n)
+        cw = self.fn("encode_reseed", ctypes.c_int)(_p(s), _p(d), ctypes.c_longlong(n))
+        return d[:cw].copy(), cw
+
     # ---- hashes ----
     def blake3(self, src64):
         s = np.ascontiguousarray(src64, dtype=np.uint8)

@@ -118,3 +118,18 @@ def test_oracle_reproduces_golden():
 @pytest.mark.gpu
 def test_gpu_reproduces_golden():
     run_all(GpuImpl(), False)
+
+
+def test_encode_reseed_golden():
+    """E3, encode() (linear_code_encode.h:122-191): the C restatement against vectors from the unmodified reference, codeword and the libc
+    state the call leaves behind."""
+    import ctypes
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encode_reseed.npz"))
+    orc = Checker("orc")
+    libc = ctypes.CDLL(None); libc.rand.restype = ctypes.c_int
+    for n in (16, 64, 1024):
+        srand(5)
+        y, cw = orc.encode_reseed(g["in_%d" % n], n)
+        assert cw == len(g["out_%d" % n]) and np.array_equal(y, g["out_%d" % n])
+        assert libc.rand() == int(g["rand_after_%d" % n][0])

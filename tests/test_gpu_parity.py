@@ -382,3 +382,29 @@ def test_elastic_open_front(ctx, chk, lin, trs, synthetic):
     got = ctx.elastic_open_front([stream[i * B:(i + 1) * B] for i in range(N // B)], beta, B, trs, lin, col, row)
     want = chk.elastic_open_front(stream, B, trs, lin, beta, col, row)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("n", [16, 64, 1024])
+def test_encode_reseed_mirror(n):
+    """E3: hobbit::encode (the graph re-drawn from fixed seeds per call) on the GPU == the reference's golden codeword, the libc state it
+    leaves == the reference's, and the code installed by expander_init_store is still the resident one afterwards."""
+    import ctypes
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    H = ctypes.CDLL(os.path.join(root, "hobbit_b200", "libhobbit_host.so"))
+    H.hobbit_c_backend.restype = ctypes.c_void_p
+    H.hobbit_c_expander_init_store.restype = ctypes.c_longlong
+    import hobbit_b200
+    hctx = hobbit_b200.Context.from_handle(H.hobbit_c_backend(0))
+    g = np.load(os.path.join(root, "tests", "golden", "encode_reseed.npz"))
+    libc = ctypes.CDLL(None); libc.rand.restype = ctypes.c_int
+    srand(1)
+    H.hobbit_c_expander_init_store(ctypes.c_longlong(64))                 # a resident "store" code of another size
+    msg = rand_field(np.random.default_rng(3), 64 * 4)
+    before = hctx.encode(msg, 64, 4)
+    x = np.ascontiguousarray(g["in_%d" % n]); y = np.zeros((2 * n, 2), dtype=np.uint64)
+    srand(5)
+    cw = H.hobbit_c_encode_reseed(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(n))
+    assert cw == len(g["out_%d" % n]) and np.array_equal(y[:cw], g["out_%d" % n])
+    assert libc.rand() == int(g["rand_after_%d" % n][0])
+    assert np.array_equal(hctx.encode(msg, 64, 4), before)                # the store code was put back
