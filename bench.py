@@ -355,23 +355,28 @@ def main():
                 "kernel_time_share": {k: round(v["total_ms"] / total_ms, 4) for k, v in prof.items()},
                 "timing": "CUDA events around every launch on the library's stream, in a pass of %d steps separate from the headline region" % psteps}
     # The BINDING roof of this kernel is not HBM: 61-bit modular multiply-adds and BLAKE3 are integer work and sm_100a has no 64-bit
-    # multiplier.  Measured here, on this GPU: the warp-instruction rates of the two integer pipes (hb_ubench_pipes) and, from the committed
-    # ncu counters of this kernel (by name), its instruction mix -> the time the pipes need at those measured rates.
+    # multiplier.  Reported next to the HBM numbers: (1) the issue-slot roof — the kernel's warp-instruction count (ncu counters of THIS
+    # kernel, by name, from the committed launch list) over the live launch time, against the 4 warp-instructions per clock and SM the
+    # four schedulers can issue; (2) the same for the ALU pipe and the FMA-heavy pipe; (3) what the two integer pipes deliver on THIS GPU
+    # in isolation, measured now (hb_ubench_pipes): IMAD.WIDE.U32 alone, SHF/LOP3 alone, a 1:3 mix.
     try:
         pipes = ctx.ubench_pipes()
         sms = torch.cuda.get_device_properties(local).multi_processor_count
-        if clocks.get("sm_mhz"):
-            per = clocks["sm_mhz"] * 1e6 * sms
+        per = (clocks.get("sm_mhz") or 0) * 1e6 * sms                                     # SM-cycles per second at the sampled clock
+        if per:
             pipes["per_clk_per_sm_at_sampled_clock"] = {k: pipes[k] / per for k in ("imad_wide", "alu", "mix_1_wide_3_alu")}
         roofline["measured_pipe_rates"] = pipes
-        if counts.get("warp_inst_per_coefficient"):
-            inst = counts["warp_inst_per_coefficient"] * coeffs_per_launch
-            ach = inst / (per_launch_ms * 1e-3)                                           # warp-instructions per second of this kernel, live
-            roofline["binding"] = {"resource": "integer issue (IMAD.WIDE on the FMA-heavy pipe + ALU pipe)", "unit": "warp-inst/s (chip)",
-                                   "achieved": ach, "peak": pipes["mix_1_wide_3_alu"], "frac": ach / pipes["mix_1_wide_3_alu"],
-                                   "warp_instructions_per_launch": inst,
-                                   "source": "instruction count: profiles/kernel_counts_r02.json (ncu smsp__inst_executed.sum of this kernel); peak: "
-                                             "hb_ubench_pipes measured in this run (1 IMAD.WIDE : 3 ALU mix, the kernel's own ratio is in the file)"}
+        if counts.get("warp_inst_per_coefficient") and per:
+            cyc = per_launch_ms * 1e-3 * per                                              # SM-cycles of one launch
+            rate = lambda key: counts[key] * coeffs_per_launch / cyc if counts.get(key) else None
+            issue = rate("warp_inst_per_coefficient")
+            roofline["binding"] = {"resource": "instruction issue (integer pipes: IMAD / IMAD.WIDE on FMA-heavy, LOP3 / SHF / IADD3 on ALU)",
+                                   "unit": "warp-inst/clk/SM", "achieved": issue, "peak": 4.0, "frac": issue / 4.0,
+                                   "alu_pipe": {"achieved": rate("alu_inst_per_coefficient"), "measured_peak": pipes["per_clk_per_sm_at_sampled_clock"]["alu"]},
+                                   "fmaheavy_pipe": {"achieved": rate("fmaheavy_inst_per_coefficient"),
+                                                     "note": "IMAD.WIDE alone sustains %.2f on this GPU; plain IMAD issues at twice that" % pipes["per_clk_per_sm_at_sampled_clock"]["imad_wide"]},
+                                   "source": "instruction counts: profiles/kernel_counts_r02.json (ncu smsp__inst_executed.sum / sm__inst_executed_pipe_*.sum of this "
+                                             "kernel's full-size launches, by name); time and clock: this run"}
     except Exception as e:                                   # noqa: BLE001
         roofline["measured_pipe_rates"] = {"error": repr(e)}
 

@@ -39,21 +39,48 @@ __device__ __forceinline__ F fold1n(F x, F d, const FN &rn) {
 // exactly on the host from the reduced sums (coeffs_from_evals); all arithmetic is exact in F_p^2, so the bits are the same.
 // Products are LAZY (limbs <= p + 7, fmul_n_lazy) and so are the accumulators (raw 64-bit sums, the caller folds them every few pairs):
 // the FMA-heavy pipe (IMAD.WIDE) is the binding unit of this kernel and canonicalising intermediates would only add ALU work.
-template <int NT> __device__ __forceinline__ void poly_acc(F (&acc)[NT + 1], const F (&x)[NT], const F (&y)[NT], const F (&d)[NT]) {
+// accumulators either in registers or — to free 12-16 registers for a third resident CTA — in a thread-private shared-memory column
+template <int NC> struct RegAcc {
+    F a[NC];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int c = 0; c < NC; c++) a[c] = mkF(0, 0);
+    }
+    __device__ __forceinline__ void add(int c, F v) { lacc(a[c], v); }
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int c = 0; c < NC; c++) a[c] = lfold(a[c]);
+    }
+    __device__ __forceinline__ F get(int c) { return a[c]; }
+};
+template <int NC> struct SmemAcc {
+    F *col;                                             // col[c * blockDim.x]: consecutive threads -> consecutive 16-byte slots, conflict-free
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int c = 0; c < NC; c++) col[c * blockDim.x] = mkF(0, 0);
+    }
+    __device__ __forceinline__ void add(int c, F v) { F t = col[c * blockDim.x]; lacc(t, v); col[c * blockDim.x] = t; }
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int c = 0; c < NC; c++) col[c * blockDim.x] = lfold(col[c * blockDim.x]);
+    }
+    __device__ __forceinline__ F get(int c) { return col[c * blockDim.x]; }
+};
+template <int NT, class Acc> __device__ __forceinline__ void poly_acc(Acc &acc, const F (&x)[NT], const F (&y)[NT], const F (&d)[NT]) {
     if (NT == 2) {
-        lacc(acc[0], fmul_n_lazy(d[0], fprep(d[1])));
-        lacc(acc[1], fmul_n_lazy(y[0], fprep(y[1])));
-        lacc(acc[2], fmul_n_lazy(x[0], fprep(x[1])));
+        acc.add(0, fmul_n_lazy(d[0], fprep(d[1])));
+        acc.add(1, fmul_n_lazy(y[0], fprep(y[1])));
+        acc.add(2, fmul_n_lazy(x[0], fprep(x[1])));
     } else if (NT == 3) {
         const F A = fmul_n_lazy(x[0], fprep(x[1])), B = fmul_n_lazy(y[0], fprep(y[1])), C = fmul_n_lazy(d[0], fprep(d[1]));
         // M = 2A + 2C - B: 2 (A + C) <= 4p + 28, + (2p - B) stays below 2^64; one fold -> limbs <= p + 7
         const F M = lfold(mkF(2 * (A.re + C.re) + (2 * P61 - B.re), 2 * (A.im + C.im) + (2 * P61 - B.im)));
         // m3 = 2 x3 - y3 (canonical: it is a right-hand operand)
         const F m3 = fcanon2(mkF(2 * x[2].re + (P61 - y[2].re), 2 * x[2].im + (P61 - y[2].im)));
-        lacc(acc[0], fmul_n_lazy(C, fprep(d[2])));
-        lacc(acc[1], fmul_n_lazy(B, fprep(y[2])));
-        lacc(acc[2], fmul_n_lazy(M, fprep(m3)));
-        lacc(acc[3], fmul_n_lazy(A, fprep(x[2])));
+        acc.add(0, fmul_n_lazy(C, fprep(d[2])));
+        acc.add(1, fmul_n_lazy(B, fprep(y[2])));
+        acc.add(2, fmul_n_lazy(M, fprep(m3)));
+        acc.add(3, fmul_n_lazy(A, fprep(x[2])));
     }
 }
 // host side: evaluation sums -> coefficients, highest degree first (1/2 = 2^60 mod p)
@@ -88,14 +115,37 @@ template <int NT, int MODE, bool INTERLEAVED>
 __global__ void __launch_bounds__(HB_SC_THREADS, HB_SC_MINB)
 sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
     constexpr int NC = NT + 1;
-    F acc[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) acc[c] = mkF(0, 0);
+#ifndef HB_SC_SACC
+#define HB_SC_SACC 0
+#endif
+#if HB_SC_SACC
+    __shared__ F sacc[NC * HB_SC_THREADS];
+    SmemAcc<NC> acc; acc.col = sacc + threadIdx.x;
+#else
+    RegAcc<NC> acc;
+#endif
+    acc.init();
     const FN rn = fprep(r);
     unsigned it = 0;
 
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (size_t)gridDim.x * blockDim.x) {
+#ifndef HB_SC_PF
+#define HB_SC_PF 2
+#endif
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += stride) {
         F x[NT], y[NT], d[NT];
+        // The tables are streamed at ~3 TB/s: the loads of a pair would wait a loaded-DRAM round trip (ncu: long_scoreboard is the top stall
+        // with only 16 warps per SM).  The sectors of the pair this thread handles HB_SC_PF iterations later are pulled into L2 now — one
+        // prefetch instruction per 32-byte sector, no registers held.
+        if (HB_SC_PF > 0 && j + HB_SC_PF * stride < L) {
+            const size_t jp = j + HB_SC_PF * stride;
+#pragma unroll
+            for (int k = 0; k < NT; k++) {
+                if (MODE == FOLD_THEN_POLY) { asm volatile("prefetch.global.L2 [%0];" ::"l"(t.in[k] + 4 * jp)); asm volatile("prefetch.global.L2 [%0];" ::"l"(t.in[k] + 4 * jp + 2)); }
+                else if (INTERLEAVED && k == 0) { asm volatile("prefetch.global.L2 [%0];" ::"l"(t.in[0] + 4 * jp)); asm volatile("prefetch.global.L2 [%0];" ::"l"(t.in[0] + 4 * jp + 2)); }
+                else if (!(INTERLEAVED && k == 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(t.in[k] + 2 * jp));
+            }
+        }
         if (MODE == FOLD_THEN_POLY) {
 #pragma unroll
             for (int k = 0; k < NT; k++) {
@@ -117,10 +167,7 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
         for (int k = 0; k < NT; k++) d[k] = fsub(y[k], x[k]);
         if (MODE != FOLD_ONLY) {
             poly_acc<NT>(acc, x, y, d);
-            if ((++it & 3) == 0) {                                   // raw 64-bit sums: at most 4 lazy terms on top of a folded value
-#pragma unroll
-                for (int c = 0; c < NC; c++) acc[c] = lfold(acc[c]);
-            }
+            if ((++it & 3) == 0) acc.fold();                         // raw 64-bit sums: at most 4 lazy terms on top of a folded value
         }
         if (MODE == POLY_AND_FOLD || MODE == FOLD_ONLY) {
 #pragma unroll
@@ -128,10 +175,11 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
         }
     }
     if (MODE == FOLD_ONLY) return;
+    F accv[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) acc[c] = fcanon2(lfold(acc[c]));
+    for (int c = 0; c < NC; c++) accv[c] = fcanon2(lfold(acc.get(c)));
 
-    grid_reduce<NC>(acc, ra);
+    grid_reduce<NC>(accv, ra);
 }
 
 // ---- S4: streaming folding sumcheck over one product-tree layer (sumcheck.cpp:1093-1136, 1150-1392) -----------------------

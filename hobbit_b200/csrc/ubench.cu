@@ -17,11 +17,16 @@ template <int MODE> __global__ void __launch_bounds__(256) pipe_rate_kernel(unsi
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (MODE == 0 || MODE == 2) w[i] = madwide((uint32_t)w[i], b, w[i]);
-            // each ALU step is three separate SASS instructions (SHF, LOP3, IADD3): volatile asm keeps ptxas from fusing them
-            if (MODE == 1 || MODE == 2) {
+            // an ALU step is separate SASS instructions that can only issue on the ALU pipe (SHF, LOP3; ptxas may turn integer adds into
+            // IMAD.IADD on the FMA pipe): volatile asm keeps them apart
+            if (MODE == 1) {
                 asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
                 asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+            }
+            if (MODE == 2) {
+                asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
+                asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+                asm volatile("shf.r.wrap.b32 %0, %0, %0, 3;" : "+r"(a[i]));
             }
         }
     }
@@ -38,7 +43,7 @@ template <int MODE> __global__ void __launch_bounds__(256) pipe_rate_kernel(unsi
 
 using namespace hb;
 
-// out[0] IMAD.WIDE.U32, out[1] ALU (SHF, LOP3, IADD: 3 instructions per step), out[2] mix of 1 IMAD.WIDE + 3 ALU: warp-instructions per
+// out[0] IMAD.WIDE.U32, out[1] ALU pipe only (SHF, LOP3: 2 instructions per step), out[2] mix of 1 IMAD.WIDE + 3 ALU: warp-instructions per
 // SECOND, chip-wide, timed with CUDA events on the context's stream (the caller divides by the SM clock it samples and the SM count)
 extern "C" int hb_ubench_pipes(hb_ctx *ctx, double *out3) {
     cudaSetDevice(ctx->device);
@@ -47,7 +52,7 @@ extern "C" int hb_ubench_pipes(hb_ctx *ctx, double *out3) {
     HB_CHECK(ctx, cudaMalloc(&cyc, blocks * sizeof(unsigned long long)));
     HB_CHECK(ctx, cudaMalloc(&sink, (size_t)blocks * 256 * sizeof(uint32_t)));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const double ops[3] = {1, 3, 4};
+    const double ops[3] = {1, 2, 4};
     for (int mode = 0; mode < 3; mode++) {
         float best = 1e30f;
         for (int rep = 0; rep < 3; rep++) {

@@ -25,22 +25,27 @@ for r in rows:
 out = {}
 for k, m in acc.items():
     d = {"launches": len(next(iter(m.values())))}
-    for metric, vals in m.items():
-        v = [x[1] for x in vals]
-        d[metric + " (avg per launch, " + vals[0][2] + ")"] = sum(v) / len(v)
+    # the full-size launches of this kernel (instruction count within 2x of the largest): the commit kernels process `coeffs` coefficients each
+    big_ids = None
     if "smsp__inst_executed.sum" in m:
-        # full-size launches only (the largest instruction counts): the commit kernels process `coeffs` coefficients per launch
-        v = sorted(x[1] for x in m["smsp__inst_executed.sum"])
-        big = [x for x in v if x >= 0.5 * v[-1]]
-        d["warp_inst_per_launch"] = sum(big) / len(big)
+        top = max(x[1] for x in m["smsp__inst_executed.sum"])
+        big_ids = {x[0] for x in m["smsp__inst_executed.sum"] if x[1] >= 0.5 * top}
+        d["full_size_launches"] = len(big_ids)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "inst": 1.0}
+    for metric, vals in m.items():
+        v = [x[1] * scale.get(x[2], 1.0) for x in vals if big_ids is None or x[0] in big_ids]
+        if v:
+            d[metric + " (avg per full-size launch)"] = sum(v) / len(v)
+    g = lambda name: d.get(name + " (avg per full-size launch)")
+    if g("smsp__inst_executed.sum"):
+        d["warp_inst_per_launch"] = g("smsp__inst_executed.sum")
         d["warp_inst_per_coefficient"] = d["warp_inst_per_launch"] / coeffs
-    if "dram__bytes_read.sum" in m and "dram__bytes_write.sum" in m:
-        rd = sorted(x[1] for x in m["dram__bytes_read.sum"]); wr = sorted(x[1] for x in m["dram__bytes_write.sum"])
-        unit = m["dram__bytes_read.sum"][0][2]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
-        bigr = [x for x in rd if x >= 0.5 * rd[-1]]; bigw = [x for x in wr if x >= 0.5 * wr[-1]]
-        d["dram_bytes_per_coefficient"] = (sum(bigr) / len(bigr) + sum(bigw) / len(bigw)) * scale / coeffs
+        for pipe in ("alu", "fmaheavy", "fma"):
+            if g("sm__inst_executed_pipe_%s.sum" % pipe):
+                d["%s_inst_per_coefficient" % pipe] = g("sm__inst_executed_pipe_%s.sum" % pipe) / coeffs
+    if g("dram__bytes_read.sum") is not None and g("dram__bytes_write.sum") is not None:
+        d["dram_bytes_per_coefficient"] = (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")) / coeffs
     out[k] = d
 json.dump({"source": src, "coefficients_per_launch": coeffs, **out}, open(dst, "w"), indent=1)
 for k, d in out.items():
-    print(k, d.get("launches"), d.get("warp_inst_per_coefficient"), d.get("dram_bytes_per_coefficient"))
+    print(k, d.get("launches"), d.get("full_size_launches"), d.get("warp_inst_per_coefficient"), d.get("alu_inst_per_coefficient"), d.get("fmaheavy_inst_per_coefficient"), d.get("dram_bytes_per_coefficient"))
