@@ -13,7 +13,6 @@
 namespace hb {
 
 static constexpr int kMaxRanks = 8;     // GPUs of one NVSwitch box
-static constexpr int kSMs = 148;        // B200: 2 dies x 74 SMs; grids for grid-stride kernels are multiples of this
 
 struct EncStage {                       // one sparse mat-vec of the expander encode: out[0..R) = G * in[0..L)
     int in_off, out_off, L, R;          // offsets/sizes in codeword coordinates
@@ -142,7 +141,7 @@ struct hb_ctx {
     void *pin[2] = {nullptr, nullptr};  // pinned staging for large PAGEABLE host buffers (hb::copy_from_host / copy_to_host)
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     bool sync_needed = false;           // set while a call has host-visible outputs (or pinned host inputs) in flight: see hb::end_call
-    int sm_count = hb::kSMs;
+    int sm_count = 148;                 // overwritten from cudaDeviceProp in hb_ctx_create; grids of grid-stride kernels are multiples of it
     // twiddle tables w[k] = omega_len^k, k < len/2, cached per log2(len)
     hb::F *tw[32] = {};
     bool tw_j_neg[32] = {};             // omega_len^(len/4) == -i (else +i)

@@ -6,7 +6,7 @@
 
 namespace hb {
 
-static constexpr int kMaxRedBlocks = 148 * 4;
+static constexpr int kMaxRedBlocks = 1024;            // capacity of the per-CTA partial array (grids are sm_count x waves, capped here)
 
 __device__ __forceinline__ F shfl_down_F(F v, int d) {
     F r; r.re = __shfl_down_sync(0xffffffffu, v.re, d); r.im = __shfl_down_sync(0xffffffffu, v.im, d); return r;
