@@ -49,7 +49,7 @@ def build_library(force=False, verbose=False):
     host_srcs = [os.path.join(HERE, "host", f) for f in ("hobbit_host.cpp", "hobbit_open.cpp", "hobbit_circuit.cpp")]
     host_lib = os.path.join(HERE, "libhobbit_host.so")
     if force or any(_newer(f, host_lib) for f in host_srcs) or _newer(os.path.join(HERE, "host", "hobbit_host.hpp"), host_lib) or _newer(LIB, host_lib):
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", host_lib] + host_srcs + ["-L" + HERE, "-lhobbit_b200", "-Wl,-rpath,$ORIGIN"]
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", host_lib] + host_srcs + ["-L" + HERE, "-lhobbit_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode:
             raise RuntimeError("host library build failed:\n%s\n%s" % (p.stdout, p.stderr))

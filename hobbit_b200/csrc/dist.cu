@@ -37,7 +37,7 @@ __global__ void dist_barrier_kernel(PeerPtrs pp, int rank, int world, u64 epoch)
         const volatile u64 *mine = reinterpret_cast<const u64 *>(pp.p[rank] + kDistBarOff) + h;
         const long long t0 = clock64();
         while (*mine < epoch) {
-            if (clock64() - t0 > 20000000000LL) { *reinterpret_cast<volatile u64 *>(pp.p[rank] + kDistErrOff) = 1; break; }
+            if (clock64() - t0 > 60000000000LL) { *reinterpret_cast<volatile u64 *>(pp.p[rank] + kDistErrOff) = 1; break; }
         }
         __threadfence_system();
     }
@@ -114,7 +114,7 @@ static int check_peer_error(hb_ctx *ctx) {
     u64 e = 0;
     HB_CHECK(ctx, cudaMemcpyAsync(&e, ctx->dist.win + kDistErrOff, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (e) HB_FAIL(ctx, "multi-GPU: a peer rank did not reach a barrier / exchange within 10 s");
+    if (e) HB_FAIL(ctx, "multi-GPU: a peer rank did not reach a barrier / exchange within 30 s");
     return 0;
 }
 

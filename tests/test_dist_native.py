@@ -78,10 +78,15 @@ def _run(worker, world, timeout=600):
     procs = [c.Process(target=worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout)
-        assert p.exitcode == 0
-    assert ret.get(timeout=10) == 1
+    try:
+        for p in procs:
+            p.join(timeout)
+            assert p.exitcode == 0, "rank process failed or timed out (exitcode %r)" % (p.exitcode,)
+        assert ret.get(timeout=10) == 1
+    finally:
+        for p in procs:                                                    # never leave a rank behind (it would spin in a device barrier)
+            if p.is_alive():
+                p.kill()
 
 
 @pytest.mark.parametrize("world", [2, 4])
