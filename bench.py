@@ -170,7 +170,7 @@ def host_mirror(local):
     return H, H.hobbit_c_backend(int(local))
 
 
-def run_tool(cmd, timeout=300):
+def run_tool(cmd, timeout=150):
     """Runs one of the reference-free C++ tools and returns its JSON line (rank 0 prints it), or {"error": ...}."""
     try:
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)

@@ -51,6 +51,14 @@ def _commit_worker(rank, world, port, ret):
             got = ctx.dist_commit_standard(np.ascontiguousarray(poly[rank * kl * B:(rank + 1) * kl * B]), K, B, trs, lin)
             want, _ = ctx.commit_standard(poly, K, trs, lin)
             ok = ok and np.array_equal(got, want)
+    # shapes that do not split over the ranks are refused loudly (no silent fallback to one GPU)
+    import hobbit_b200
+    try:
+        ctx.dist_commit_standard(np.ascontiguousarray(poly[:3 * B]), 3 * world + 1, B, trs, 1)
+        ok = False
+    except hobbit_b200.HobbitError as e:
+        ok = ok and "split evenly" in str(e)
+    ctx.dist_barrier()
     # Elastic_PC: groups of 4 chunks
     ngroups, Be = 4, 1 << 12
     stream = rand_field(np.random.default_rng(16), ngroups * 4 * Be, full=True)
