@@ -37,7 +37,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "pc_commit_field_elems_per_s"
 UNIT = "field-elems/s"
