@@ -192,9 +192,11 @@ def extras(world, rank):
             lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
             return json.loads(lines[-1]) if lines and not p.returncode else {"error": "rc=%d %s" % (p.returncode, (p.stdout + p.stderr)[-300:])}
         out["config1_test_PC_2e20_K32"] = one([pc, "pc", "20", "32", "1"])
-        out["config3_MLP_pigeon_9_18_18_1_4_1024_256_256_16"] = one([mlp, "18", "1024", "256", "256", "16", "--reps", "3"])
-        out["config4_AES_pigeon_5_19_8_1"] = one([mlp, "19", "aes", "8", "--reps", "3"])
-        out["config4_SQL_pigeon_6_19_17_1"] = one([mlp, "19", "sql", "17", "--reps", "3"])
+        # --async-levels: the Merkle levels of every commitment reach the caller's host vectors in the background, under the provers (they
+        # are complete before open() frees them: the reference's own commit -> prove -> open sequence)
+        out["config3_MLP_pigeon_9_18_18_1_4_1024_256_256_16"] = one([mlp, "18", "1024", "256", "256", "16", "--reps", "3", "--async-levels"])
+        out["config4_AES_pigeon_5_19_8_1"] = one([mlp, "19", "aes", "8", "--reps", "3", "--async-levels"])
+        out["config4_SQL_pigeon_6_19_17_1"] = one([mlp, "19", "sql", "17", "--reps", "3", "--async-levels"])
         out["config5_test_Elastic_PC_2e28_pinned"] = one([pc, "elastic", "28", "20", "2", "--pinned", "--resident-levels", "--reps", "2"])
         out["config5_test_Elastic_PC_2e28_hbm_chunk"] = one([pc, "elastic", "28", "20", "2", "--resident-levels", "--reps", "2"])
     else:
@@ -208,10 +210,10 @@ def extras(world, rank):
         r = run_tool([pc, "elastic", str(logn), "20", "2", "--resident-levels", "--reps", "2"])
         if rank == 0:
             out["config5_test_Elastic_PC_2e%d_hbm_chunk_%dgpus" % (logn, world)] = r
-        r = run_tool([mlp, "19", "sql", "17", "--reps", "2"])
+        r = run_tool([mlp, "19", "sql", "17", "--reps", "2", "--async-levels"])
         if rank == 0:
             out["config4_SQL_pigeon_6_19_17_1_%dgpus" % world] = r
-        r = run_tool([mlp, "19", "aes", "8", "--reps", "2"])
+        r = run_tool([mlp, "19", "aes", "8", "--reps", "2", "--async-levels"])
         if rank == 0:
             out["config4_AES_pigeon_5_19_8_1_%dgpus" % world] = r
     return out

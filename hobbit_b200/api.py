@@ -261,6 +261,18 @@ class Context:
         self._ck(self.lib.hb_stream_pc_test(self.h, _ptr(out), c_sz(n)))
         return out
 
+    def elastic_commit_async_levels(self, chunks, B, trs, lin):
+        """Same commitment, the levels delivered level by level in the BACKGROUND (hb_elastic_finish_levels_async + hb_levels_wait)."""
+        self._ck(self.lib.hb_elastic_begin(self.h, c_sz(B), int(trs), int(lin)))
+        for c in chunks:
+            self._ck(self.lib.hb_elastic_push(self.h, _ptr(_F(c))))
+        nlev = int(np.log2(4 * B)) + 1
+        lv = [np.empty((4 * B >> l, 32), dtype=np.uint8) for l in range(nlev)]
+        ptrs = (c_vp * nlev)(*[x.ctypes.data_as(c_vp) for x in lv])
+        self._ck(self.lib.hb_elastic_finish_levels_async(self.h, ptrs, nlev))
+        self._ck(self.lib.hb_levels_wait(self.h))
+        return np.concatenate(lv)
+
     def elastic_commit(self, chunks, B, trs, lin, reuse_pinned=False):
         """chunks: iterable of (B,2) arrays (the stream), pushed in order.  reuse_pinned: every chunk is first copied into ONE pinned host
         buffer that is overwritten right after the push returns — what a streaming producer does (hb_elastic_push returns only once the

@@ -148,6 +148,103 @@ int copy_to_host(hb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes,
     return 0;
 }
 
+// ---- background level copier ---------------------------------------------------------------------------------------------------------
+static constexpr size_t kLvlPiece = (size_t)8 << 20;
+static void levels_worker(hb_ctx *ctx) {
+    LevelsCopier *L = ctx->lvl;
+    cudaSetDevice(ctx->device);
+    for (;;) {
+        LevelsJob job;
+        {
+            std::unique_lock<std::mutex> lk(L->mu);
+            L->cv.wait(lk, [&] { return L->stop || !L->q.empty(); });
+            if (L->q.empty()) return;                                   // stop requested and nothing left
+            job = std::move(L->q.front()); L->q.pop_front(); L->busy = true;
+        }
+        cudaError_t e = cudaStreamWaitEvent(L->stream, job.ready, 0);
+        // every level, piece by piece: D2H into one half of the pinned double buffer while the previous piece is copied out (first touch of
+        // the caller's fresh pages happens here, off the proving thread)
+        struct Piece { uint8_t *dst; const uint8_t *src; size_t n; };
+        std::vector<Piece> pieces;
+        for (size_t l = 0; l < job.dst.size(); l++)
+            if (job.bytes[l] >= ((size_t)4 << 20)) {
+                const uintptr_t lo = ((uintptr_t)job.dst[l] + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1), hi = ((uintptr_t)job.dst[l] + job.bytes[l]) & ~(((uintptr_t)2 << 20) - 1);
+                if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
+            }
+        for (size_t l = 0; l < job.dst.size(); l++)
+            for (size_t o = 0; o < job.bytes[l]; o += kLvlPiece) pieces.push_back({job.dst[l] + o, job.dev + job.off[l] + o, std::min(kLvlPiece, job.bytes[l] - o)});
+        for (size_t i = 0; i <= pieces.size() && e == cudaSuccess; i++) {
+            if (i < pieces.size()) {
+                const int b = (int)(i & 1);
+                e = cudaMemcpyAsync(L->pin[b], pieces[i].src, pieces[i].n, cudaMemcpyDeviceToHost, L->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(L->ev[b], L->stream);
+            }
+            if (i >= 1 && e == cudaSuccess) {
+                const int b = (int)((i - 1) & 1);
+                e = cudaEventSynchronize(L->ev[b]);
+                if (e == cudaSuccess) par_memcpy(pieces[i - 1].dst, L->pin[b], pieces[i - 1].n);      // fresh pages: faulted in by several threads
+            }
+        }
+        if (job.owned) cudaFreeAsync(job.dev, L->stream);
+        cudaStreamSynchronize(L->stream);
+        cudaEventDestroy(job.ready);
+        {
+            std::lock_guard<std::mutex> lk(L->mu);
+            if (e != cudaSuccess && L->err.empty()) L->err = cudaGetErrorString(e);
+            L->busy = false;
+        }
+        L->cv_idle.notify_all();
+    }
+}
+static int levels_copier_start(hb_ctx *ctx) {
+    if (!ctx->lvl) ctx->lvl = new LevelsCopier();
+    LevelsCopier *L = ctx->lvl;
+    if (L->started) return 0;
+    HB_CHECK(ctx, cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        HB_CHECK(ctx, cudaHostAlloc(&L->pin[b], kLvlPiece, cudaHostAllocDefault));
+        HB_CHECK(ctx, cudaEventCreateWithFlags(&L->ev[b], cudaEventDisableTiming));
+    }
+    L->th = std::thread(levels_worker, ctx);
+    L->started = true;
+    return 0;
+}
+int levels_copy_wait(hb_ctx *ctx) {
+    LevelsCopier *L = ctx->lvl;
+    if (!L || !L->started) return 0;
+    std::unique_lock<std::mutex> lk(L->mu);
+    L->cv_idle.wait(lk, [&] { return L->q.empty() && !L->busy; });
+    if (!L->err.empty()) { ctx->err = "background level copy: " + L->err; L->err.clear(); return 1; }
+    return 0;
+}
+static void levels_copier_stop(hb_ctx *ctx) {
+    LevelsCopier *L = ctx->lvl;
+    if (!L) return;
+    if (L->started) {
+        { std::lock_guard<std::mutex> lk(L->mu); L->stop = true; }
+        L->cv.notify_all();
+        L->th.join();
+        for (int b = 0; b < 2; b++) { cudaFreeHost(L->pin[b]); cudaEventDestroy(L->ev[b]); }
+        cudaStreamDestroy(L->stream);
+    }
+    delete L; ctx->lvl = nullptr;
+}
+// queue: levels l = 0.. (n >> l digests each, flat in `dev` leaves first) -> level_ptrs[l] (NULL: skipped); the tree must be complete in stream order
+static int levels_copy_enqueue(hb_ctx *ctx, uint8_t *dev, bool owned, uint8_t *const *level_ptrs, int nlevels, size_t nleaves) {
+    HB_TRY(levels_copier_start(ctx));
+    LevelsJob job; job.dev = dev; job.owned = owned;
+    size_t off = 0, n = nleaves;
+    for (int l = 0; l < nlevels; l++, n /= 2) {
+        if (level_ptrs[l]) { job.dst.push_back(level_ptrs[l]); job.off.push_back(off * 32); job.bytes.push_back(n * 32); }
+        off += n;
+    }
+    HB_CHECK(ctx, cudaEventCreateWithFlags(&job.ready, cudaEventDisableTiming));
+    HB_CHECK(ctx, cudaEventRecord(job.ready, ctx->stream));
+    { std::lock_guard<std::mutex> lk(ctx->lvl->mu); ctx->lvl->q.push_back(std::move(job)); }
+    ctx->lvl->cv.notify_all();
+    return 0;
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -236,6 +333,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     if (ctx->red) cudaFree(ctx->red);
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    levels_copier_stop(ctx);
     elastic_free(ctx);
     dist_release(ctx);
     for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -329,7 +427,7 @@ extern "C" void hb_root_of_unity(int logn, hb_F *out) {          // utils.cpp:45
 // MiMC sits on the critical path between sumcheck rounds (3-5 hashes per round, each 161 dependent cubings), so the host version is
 // written for latency: (a + bi)^3 = a (a^2 - 3 b^2) + i b (3 a^2 - b^2) is FOUR 64x64 products per cubing (two squarings, two
 // products) instead of the eight of two generic F multiplications, and limbs stay lazily reduced (< 2^62) until the very end.
-// (One GPU thread needs 31 us per hash, tools/ubench_fmul.cu; this takes about 1.5 us.)
+// (One GPU thread needs 31 us per hash, tools/ubench_fmul.cu; this takes 2.3 us.)
 static inline u64 mimc_red(unsigned __int128 x) {              // x < 2^124 + 2^72 -> congruent value < 2^61 + 8
     u64 s = (u64)(x >> 61) + ((u64)x & P61);                    // < 2^63 + 2^11 + 2^61: fits
     return (s & P61) + (s >> 61);
@@ -714,6 +812,30 @@ extern "C" int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs,
     elastic_free(ctx);
     return 0;
 }
+
+// The same, but the copies into level_ptrs happen in the BACKGROUND (a worker thread with its own stream and pinned double buffer) while the
+// context goes on proving: the call returns as soon as the tree kernels are queued.  The caller must not read or free the destination
+// arrays before hb_levels_wait() returned (the host mirror's open() waits before it frees the tree; hobbit::commit_levels_async).
+extern "C" int hb_elastic_finish_levels_async(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels) { HB_DEV(ctx);
+    ElasticState &el = ctx->el;
+    if (!el.active) HB_FAIL(ctx, "hb_elastic_finish_levels_async: no commit in progress");
+    if (nlevels != ilog2(4 * el.B) + 1) HB_FAIL(ctx, "hb_elastic_finish_levels_async: expected log2(4B)+1 levels");
+    if (el.dist_groups_total) {
+        // the global tree lives in the multi-GPU window, which the next sharded call overwrites: copy out of a private snapshot
+        if (el.chunk_idx * (size_t)ctx->dist.world != 4 * el.dist_groups_total) HB_FAIL(ctx, "hb_elastic_finish_levels_async: this rank must push exactly its 4 * groups_total / world chunks");
+        HB_TRY(sharded_finish(ctx, el.dist_groups_total, 4 * el.B, nullptr));
+        uint8_t *snap; HB_CHECK(ctx, cudaMallocAsync(&snap, (8 * el.B - 1) * 32, ctx->stream));
+        HB_CHECK(ctx, cudaMemcpyAsync(snap, sharded_tree(ctx, el.dist_groups_total, 4 * el.B), (8 * el.B - 1) * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        HB_TRY(levels_copy_enqueue(ctx, snap, true, level_ptrs, nlevels, 4 * el.B));
+    } else {
+        HB_TRY(merkle_tree_dev(ctx, el.leaves, 4 * el.B));
+        HB_TRY(levels_copy_enqueue(ctx, el.leaves, true, level_ptrs, nlevels, 4 * el.B));
+        el.leaves = nullptr;                                   // ownership moved to the job
+    }
+    elastic_free(ctx);
+    return 0;
+}
+extern "C" int hb_levels_wait(hb_ctx *ctx) { HB_DEV(ctx); return levels_copy_wait(ctx); }
 
 // W1: synthetic default stream of read_stream_PC (witness_stream.cpp:2405-2411).  The recurrence is inherently
 // sequential (x <- x^2 + i), it is the INPUT GENERATOR of test_Elastic_PC, so it is evaluated once on the host.

@@ -6,6 +6,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
 #include <cuda_runtime.h>
 #include "../../include/hobbit_b200.h"
 #include "field.cuh"
@@ -110,6 +114,7 @@ struct TraceState {
     size_t pos_capacity = 0;            // entries allocated at pos (kept across traces: cudaFree / cudaMalloc of it cost more than the evaluator)
 };
 
+int levels_copy_wait(hb_ctx *ctx);                                   // all queued background level copies are done (commit.cu)
 // the chunk-independent half of the commitments (commit.cu), shared with the multi-GPU entry points (dist.cu)
 int commit_encode_chunks_impl(hb_ctx *ctx, const hb_F *poly, size_t nchunks, size_t B, int trs, int linear_time, uint8_t *inner_dev,
                               InnerLayout lay0, size_t first_chunk, size_t total_chunks);
@@ -129,6 +134,20 @@ int dist_allreduce_vec(hb_ctx *ctx, F *vec_dev, size_t n);           // field su
 int sharded_begin(hb_ctx *ctx, size_t units_total, size_t leaves, InnerLayout *lay_out);
 int sharded_finish(hb_ctx *ctx, size_t units_total, size_t leaves, uint8_t *levels_out);
 const uint8_t *sharded_tree(hb_ctx *ctx, size_t units_total, size_t leaves);
+
+// Background copy of Merkle levels to caller (pageable) memory: a worker thread with its own stream and pinned double buffer drains a queue
+// of jobs while the context's stream goes on proving (hb_elastic_finish_levels_async / hb_levels_wait).
+struct LevelsJob {
+    uint8_t *dev = nullptr; bool owned = false;          // flat levels on the device (owned: freed when the job is done)
+    cudaEvent_t ready = nullptr;                         // recorded on the context's stream once the tree is complete
+    std::vector<uint8_t *> dst; std::vector<size_t> off, bytes;
+};
+struct LevelsCopier {
+    std::thread th; std::mutex mu; std::condition_variable cv, cv_idle;
+    std::deque<LevelsJob> q; bool busy = false, stop = false, started = false;
+    cudaStream_t stream = nullptr; void *pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::string err;
+};
 
 }  // namespace hb
 
@@ -156,6 +175,7 @@ struct hb_ctx {
     hb::TraceState trace;
     // sumcheck reduction scratch: per-CTA partial coefficients + ticket counter (device), result mailbox (pinned host)
     hb::F *red = nullptr; unsigned *ticket = nullptr; hb::F *mailbox = nullptr; hb::F *mailbox_dev = nullptr; unsigned long long seq = 0;
+    hb::LevelsCopier *lvl = nullptr;    // created on first use
     hb::DistState dist;
     // FNV-1a over every value a prover read back from the GPU (round sums, table heads): a digest of the whole Fiat–Shamir transcript
     uint64_t transcript = 0xcbf29ce484222325ULL;

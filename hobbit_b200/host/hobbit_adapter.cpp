@@ -57,6 +57,9 @@ std::vector<hobbit::Fe> &fv(std::vector<F> &v) { return reinterpret_cast<std::ve
 std::vector<std::vector<hobbit::_hash>> &hv(std::vector<std::vector<_hash>> &v) { return reinterpret_cast<std::vector<std::vector<hobbit::_hash>> &>(v); }
 
 void sync_globals() {
+    // the reference's callers only hand MT_hashes from commit() to open() (prove_circuit main.cpp:862-951, test_Elastic_PC): the levels may
+    // arrive in the background
+    hobbit::commit_levels_async = true;
     hobbit::linear_time = linear_time; hobbit::tensor_row_size = tensor_row_size; hobbit::BUFFER_SPACE = BUFFER_SPACE;
     hobbit::has_lookups = has_lookups; hobbit::circuit_size = circuit_size;
     hobbit::a_w = hobbit::Fe(a_w.real, a_w.img); hobbit::b_w = hobbit::Fe(b_w.real, b_w.img);

@@ -25,6 +25,8 @@ bool materialize_tensor = false;
 bool commit_levels_on_host = true;
 bool open_reuses_committed_poly = false;
 bool stream_in_pinned_host = false;
+bool commit_levels_async = false;
+static bool g_levels_pending = false;
 static size_t committed_poly_size = 0;
 
 static hb_ctx *g_ctx = nullptr;
@@ -39,6 +41,7 @@ void init_backend(int device) {
     if (hb_ctx_create(&g_ctx, device)) { printf("hobbit_b200: no CUDA device (there is no CPU fallback)\n"); exit(-1); }
 }
 hb_ctx *backend() { if (!g_ctx) init_backend(0); return g_ctx; }
+void wait_levels() { if (g_levels_pending) { CK(hb_levels_wait(backend())); g_levels_pending = false; } }
 
 // ---- multi-GPU bootstrap: a one-shot TCP all-gather of the 256-byte window blobs (rank 0 serves) ----------------------------------
 size_t g_dist_data_bytes = 0;
@@ -451,7 +454,8 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
     std::vector<uint8_t *> ptrs;
     for (size_t n = 4 * BUFFER_SPACE;; n /= 2) { MT_hashes.emplace_back(n); if (n == 1) break; }
     for (auto &lv : MT_hashes) ptrs.push_back(commit_levels_on_host || lv.size() <= 1024 ? (uint8_t *)lv.data() : nullptr);
-    CK(hb_elastic_finish_levels(backend(), ptrs.data(), (int)ptrs.size()));
+    if (commit_levels_async) { CK(hb_elastic_finish_levels_async(backend(), ptrs.data(), (int)ptrs.size())); g_levels_pending = true; }
+    else CK(hb_elastic_finish_levels(backend(), ptrs.data(), (int)ptrs.size()));
     if (trace) fprintf(stderr, "[hobbit trace] commit(%s, %zu): stream + pushes %.3f ms, levels %.3f ms\n", fd.name.c_str(), (size_t)fd.size, t_pushed - t_begin, wall_ms() - t_pushed);
 }
 

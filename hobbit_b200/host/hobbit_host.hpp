@@ -123,6 +123,11 @@ extern bool open_reuses_committed_poly;
 // PCIe transfer per chunk, double-buffered against the encode — the witness never has to fit HBM (BASELINE config 5).  Default false: the
 // synthetic chunk is uploaded once and pushed from HBM.
 extern bool stream_in_pinned_host;
+// true: Elastic_PC commit() returns as soon as the tree kernels are queued; the Merkle levels are copied into MT_hashes in the BACKGROUND
+// (worker thread, own stream) while the caller goes on proving.  MT_hashes must not be read before wait_levels() returned; open() waits on
+// its own before it frees the tree, so the reference's commit -> prove -> open sequences (prove_circuit, test_Elastic_PC) need nothing else.
+extern bool commit_levels_async;
+void wait_levels();
 extern size_t g_dist_data_bytes;               // data bytes of this rank's multi-GPU window (0: single GPU)
 void commit_standard(std::vector<F> &poly, _hash &comm, std::vector<std::vector<_hash>> &MT_hashes,
                      std::vector<std::vector<std::vector<F>>> &_tensor, int K);

@@ -606,6 +606,7 @@ static void open_tail(const F *agg, size_t B, size_t trs, size_t nonzero_chunks,
 
 void open(stream_descriptor fd, std::vector<F> x, std::vector<std::vector<_hash>> &Commitment_MT, double &vt, double &ps) {
     trace_rng(("open " + fd.name).c_str());
+    wait_levels();                                               // a background copy into Commitment_MT (commit_levels_async) must be over before it is freed
     Trace tall("open (Elastic_PC) total");
     const size_t B = BUFFER_SPACE, trs = (size_t)tensor_row_size, cols = 2 * B / trs, K = fd.size / B;
     const int queries = linear_time ? 5900 : 700;                               // :626-629

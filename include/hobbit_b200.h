@@ -139,6 +139,11 @@ int hb_elastic_finish(hb_ctx *ctx, uint8_t *levels_out);
 /* the same, level l (4B >> l digests) written straight to level_ptrs[l] — the reference's MT_hashes[l] — nlevels = log2(4B)+1;
  * a NULL level_ptrs[l] skips that level (a prover that only needs the root and the level SIZES, see hobbit::commit_levels_on_host) */
 int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels);
+/* hb_elastic_finish_levels with the host copies in the BACKGROUND (worker thread, own stream, pinned double buffer): returns once the tree
+ * kernels are queued, so the copy of 64-256 MiB of levels into fresh pageable pages overlaps whatever the context proves next.  The
+ * destination arrays must not be read or freed before hb_levels_wait returned. */
+int hb_elastic_finish_levels_async(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels);
+int hb_levels_wait(hb_ctx *ctx);
 /* ---- O2, data-parallel front half of Elastic_PC open (Elastic_PC.cpp:316-333 aggregate, 487-533 compute_aggregation_reply) --------
  * begin: the `queries` cells (col[q], row[q]) drawn by the host (Elastic_PC.cpp:649-655), nchunks = N/B.  push chunk i with beta[i]:
  *   agg[j] += beta[i] * chunk[j]  and  reply[q*nchunks + i] = tensorcode(chunk)[row[q]][col[q]].  finish: agg (B), reply (queries*nchunks).

@@ -192,6 +192,20 @@ def test_elastic_push_from_a_reused_pinned_buffer(ctx):
         assert np.array_equal(want, got)
 
 
+def test_elastic_levels_in_the_background(ctx):
+    """hb_elastic_finish_levels_async + hb_levels_wait deliver exactly the levels of hb_elastic_finish (two commits queued back to back)."""
+    B, trs = 1 << 14, 16
+    rng = np.random.default_rng(33)
+    orc = Checker("orc")
+    srand(1); orc.expander_init_store(trs)
+    ctx.expander_set(trs, orc.expander_graphs(trs))
+    for lin in (0, 1):
+        chunks = [rand_field(rng, B, full=True) for _ in range(8)]
+        want = ctx.elastic_commit(chunks, B, trs, lin)
+        got = ctx.elastic_commit_async_levels(chunks, B, trs, lin)
+        assert np.array_equal(want, got)
+
+
 def test_aggregate_never_trusts_a_host_address(ctx):
     """hb_aggregate must aggregate the data it is GIVEN: a host buffer at the same address with new contents after a commit (round 1 used
     the stale device copy whenever address and size matched)."""

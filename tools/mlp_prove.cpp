@@ -23,6 +23,7 @@ int main(int argc, char **argv) {
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "--reps")) { reps = atoi(argv[++i]); continue; }
         if (!strcmp(argv[i], "--resident-levels")) { commit_levels_on_host = false; continue; }      // prover-only run: big Merkle levels stay in HBM
+        if (!strcmp(argv[i], "--async-levels")) { commit_levels_async = true; continue; }            // levels reach the host in the background, under the provers
         if (!strcmp(argv[i], "aes") || !strcmp(argv[i], "sql")) { sql = !strcmp(argv[i], "sql"); aes_n = atoi(argv[++i]); continue; }
         layers.push_back(atoi(argv[i]));
     }
@@ -69,6 +70,7 @@ int main(int argc, char **argv) {
         open(fdw, generate_randomness((int)std::log2((double)fdw.size)), MT, vt, ps);
         if (has_lookups) open(fdl, generate_randomness((int)std::log2((double)fdl.size)), MTl, vt, ps);
         double t5 = now();
+        wait_levels();
         transcript = hb_transcript_digest(backend(), 0); launches_last = hb_launch_count(backend()) - l0;
         for (auto &lv : MT) if (lv.size() == 1) for (int q = 0; q < 32; q++) transcript = (transcript ^ ((const unsigned char *)&lv[0])[q]) * 0x100000001b3ULL;   // + the commitment root
         fflush(stdout); dup2(saved, 1);
@@ -79,9 +81,9 @@ int main(int argc, char **argv) {
     if (dist_rank() != 0) return 0;                          // every rank holds the same proof; rank 0 reports
     if (aes_n >= 0) printf("{\"workload\": \"%s prove_circuit (lookups), 2^%d %s", sql ? "SQL" : "AES", aes_n, sql ? "rows" : "blocks");
     else { printf("{\"workload\": \"MLP prove_circuit, layers"); for (int l : layers) printf(" %d", l); }
-    printf(", circuit_size 2^%d, BUFFER_SPACE 2^%d\", \"evaluate_s\": %.5f, \"commit_s\": %.5f, \"mul_tree_s\": %.5f, \"gate_s\": %.5f, \"open_s\": %.5f, \"total_s\": %.5f, "
+    printf(", circuit_size 2^%d, BUFFER_SPACE 2^%d%s\", \"evaluate_s\": %.5f, \"commit_s\": %.5f, \"mul_tree_s\": %.5f, \"gate_s\": %.5f, \"open_s\": %.5f, \"total_s\": %.5f, "
            "\"ps_kb\": %.6f, \"gates_per_s\": %.1f, \"gpu_launches\": %llu, \"launches_per_proof\": %llu, \"n_gpus\": %d, \"transcript\": \"%016llx\", \"rng_next\": %ld}\n",
-           (int)std::log2((double)cs), (int)std::log2((double)BUFFER_SPACE), best[0], best[1], best[2], best[3], best[4], best[5], ps, cs / best[5],
+           (int)std::log2((double)cs), (int)std::log2((double)BUFFER_SPACE), !commit_levels_on_host ? ", Merkle levels resident in HBM" : commit_levels_async ? ", Merkle levels to the host in the background" : "", best[0], best[1], best[2], best[3], best[4], best[5], ps, cs / best[5],
            (unsigned long long)hb_launch_count(backend()), (unsigned long long)launches_last, dist_world(), (unsigned long long)transcript, random());
     return 0;
 }

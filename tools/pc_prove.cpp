@@ -26,6 +26,7 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "--reps")) reps = atoi(argv[++i]);
         if (!strcmp(argv[i], "--pinned")) stream_in_pinned_host = true;
         if (!strcmp(argv[i], "--resident-levels")) commit_levels_on_host = false;
+        if (!strcmp(argv[i], "--async-levels")) commit_levels_async = true;
     }
     const size_t N = (size_t)1 << logN;
     const int world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
