@@ -835,6 +835,12 @@ extern "C" int hb_elastic_finish_levels_async(hb_ctx *ctx, uint8_t *const *level
     elastic_free(ctx);
     return 0;
 }
+// any flat tree in device memory (leaves first, nleaves >> l digests per level) -> level_ptrs in the background; take_ownership != 0: `dev_levels`
+// (a stream-ordered allocation, hb_malloc_stream) is freed when the copy is done
+extern "C" int hb_levels_copy_async(hb_ctx *ctx, uint8_t *dev_levels, int take_ownership, uint8_t *const *level_ptrs, int nlevels, size_t nleaves) { HB_DEV(ctx);
+    if (!is_device_ptr(dev_levels)) HB_FAIL(ctx, "hb_levels_copy_async: the tree must be in device memory");
+    return levels_copy_enqueue(ctx, dev_levels, take_ownership != 0, level_ptrs, nlevels, nleaves);
+}
 extern "C" int hb_levels_wait(hb_ctx *ctx) { HB_DEV(ctx); return levels_copy_wait(ctx); }
 
 // W1: synthetic default stream of read_stream_PC (witness_stream.cpp:2405-2411).  The recurrence is inherently

@@ -413,14 +413,22 @@ void commit(stream_descriptor fd, _hash &, std::vector<std::vector<_hash>> &MT_h
         CK(hb_dist_elastic_commit(backend(), (const hb_F *)(res + (size_t)dist_rank() * (groups / world) * 4 * BUFFER_SPACE), groups, BUFFER_SPACE,
                                   tensor_row_size, linear_time ? 1 : 0, (uint8_t *)dlev));
         MT_hashes.clear();
-        size_t off = 0;
-        for (size_t n = 4 * BUFFER_SPACE;; n /= 2) {
-            MT_hashes.emplace_back(n);
-            if (commit_levels_on_host || n <= 1024) CK(hb_memcpy(backend(), MT_hashes.back().data(), (const uint8_t *)dlev + off * 32, n * 32));
-            off += n;
-            if (n == 1) break;
+        if (commit_levels_async) {                                 // the levels reach the caller's vectors in the background (wait_levels / open)
+            std::vector<uint8_t *> lp;
+            for (size_t n = 4 * BUFFER_SPACE;; n /= 2) { MT_hashes.emplace_back(n); if (n == 1) break; }
+            for (auto &lv : MT_hashes) lp.push_back(commit_levels_on_host || lv.size() <= 1024 ? (uint8_t *)lv.data() : nullptr);
+            CK(hb_levels_copy_async(backend(), (uint8_t *)dlev, 1, lp.data(), (int)lp.size(), 4 * BUFFER_SPACE));
+            g_levels_pending = true;
+        } else {
+            size_t off = 0;
+            for (size_t n = 4 * BUFFER_SPACE;; n /= 2) {
+                MT_hashes.emplace_back(n);
+                if (commit_levels_on_host || n <= 1024) CK(hb_memcpy(backend(), MT_hashes.back().data(), (const uint8_t *)dlev + off * 32, n * 32));
+                off += n;
+                if (n == 1) break;
+            }
+            CK(hb_free_stream(backend(), dlev));
         }
-        CK(hb_free_stream(backend(), dlev));
         if (trace) fprintf(stderr, "[hobbit trace] commit(%s, %zu) sharded over %d ranks: %.3f ms\n", fd.name.c_str(), (size_t)fd.size, world, wall_ms() - t_begin);
         return;
     }

@@ -143,6 +143,7 @@ int hb_elastic_finish_levels(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevel
  * kernels are queued, so the copy of 64-256 MiB of levels into fresh pageable pages overlaps whatever the context proves next.  The
  * destination arrays must not be read or freed before hb_levels_wait returned. */
 int hb_elastic_finish_levels_async(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels);
+int hb_levels_copy_async(hb_ctx *ctx, uint8_t *dev_levels, int take_ownership, uint8_t *const *level_ptrs, int nlevels, size_t nleaves);
 int hb_levels_wait(hb_ctx *ctx);
 /* ---- O2, data-parallel front half of Elastic_PC open (Elastic_PC.cpp:316-333 aggregate, 487-533 compute_aggregation_reply) --------
  * begin: the `queries` cells (col[q], row[q]) drawn by the host (Elastic_PC.cpp:649-655), nchunks = N/B.  push chunk i with beta[i]:

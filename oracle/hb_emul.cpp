@@ -659,6 +659,7 @@ int hb_dist_elastic_commit(hb_ctx *, const hb_F *, size_t, size_t, int, int, uin
 int hb_dist_elastic_begin(hb_ctx *ctx, size_t B, int trs, int lin, size_t) { return hb_elastic_begin(ctx, B, trs, lin); }
 int hb_elastic_open_range(hb_ctx *, size_t, size_t) { return 1; }
 int hb_elastic_finish_levels_async(hb_ctx *ctx, uint8_t *const *level_ptrs, int nlevels) { return hb_elastic_finish_levels(ctx, level_ptrs, nlevels); }
-int hb_levels_wait(hb_ctx *) { return 0; }                                       /* only reached with world > 1 */
+int hb_levels_wait(hb_ctx *) { return 0; }
+int hb_levels_copy_async(hb_ctx *, uint8_t *, int, uint8_t *const *, int, size_t) { return 1; }                                /* only reached with world > 1 */                                       /* only reached with world > 1 */
 
 }  // extern "C"
