@@ -74,6 +74,7 @@ struct ExpanderDev {
     uint2 *d_edges = nullptr;           // {absolute source index in the codeword, 32-bit weight}
     size_t n_edges = 0;
     int max_indeg = 0;
+    bool w31 = true;                    // every weight < 2^31 (the reference draws them with random()): enables the four-edges-at-a-time accumulation
 };
 
 // Double-buffered staging of host chunks for the chunk-at-a-time calls (hb_elastic_push, hb_elastic_open_push): the H2D of chunk i runs on

@@ -33,6 +33,22 @@ __device__ __forceinline__ void acc_mac(Acc &a, u64 x, uint32_t w) {
     asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
         : "+r"(a.v0), "+r"(a.v1), "+r"(a.v2) : "r"((uint32_t)p1), "r"((uint32_t)(p1 >> 32)));
 }
+// Four edges at once (HB_ENC_MAC4): with weights < 2^31 and canonical entries (< 2^61) a low-half product is < 2^63 and a high-half product
+// < 2^60, so two low products and all four high products are summed on the 64-bit addend of IMAD.WIDE before anything touches the 96-bit
+// accumulators: 9 additions per limb and four edges instead of 24.
+__device__ __forceinline__ void add96(uint32_t &a0, uint32_t &a1, uint32_t &a2, u64 v) {
+    asm("{\n\t.reg .u32 vl, vh;\n\tmov.b64 {vl, vh}, %3;\n\tadd.cc.u32 %0, %0, vl;\n\taddc.cc.u32 %1, %1, vh;\n\taddc.u32 %2, %2, 0;\n\t}"
+        : "+r"(a0), "+r"(a1), "+r"(a2) : "l"(v));
+}
+__device__ __forceinline__ void acc_mac4(Acc &a, u64 x0, u64 x1, u64 x2, u64 x3, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    const u64 ua = madwide((uint32_t)x1, w1, mulwide((uint32_t)x0, w0));
+    const u64 ub = madwide((uint32_t)x3, w3, mulwide((uint32_t)x2, w2));
+    const u64 v = madwide((uint32_t)(x3 >> 32), w3, madwide((uint32_t)(x2 >> 32), w2, madwide((uint32_t)(x1 >> 32), w1, mulwide((uint32_t)(x0 >> 32), w0))));
+    add96(a.u0, a.u1, a.u2, ua); add96(a.u0, a.u1, a.u2, ub); add96(a.v0, a.v1, a.v2, v);
+}
+#ifndef HB_ENC_MAC4
+#define HB_ENC_MAC4 1
+#endif
 __device__ __forceinline__ u64 acc_reduce(const Acc &a) {
     u64 u = red128(((u64)a.u1 << 32) | a.u0, a.u2);
     u64 v = red128(((u64)a.v1 << 32) | a.v0, a.v2);
@@ -72,7 +88,7 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
                    const EncStage *__restrict__ stages, int nstages,
                    const int *__restrict__ rowptr, const uint2 *__restrict__ edges,
                    uint8_t *__restrict__ inner_base, Digest zero_quad, InnerLayout lay, unsigned long long *__restrict__ prof, int split_ok, int help_ok,
-                   const __grid_constant__ CUtensorMap tmap, int box_rows) {
+                   const __grid_constant__ CUtensorMap tmap, int box_rows, int mac4_ok) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     F *cw = reinterpret_cast<F *>(smem_raw);                   // cw[row * CB + c]
     __shared__ __align__(8) unsigned long long tma_bar;
@@ -145,8 +161,18 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
             for (unsigned t = t0; t < (unsigned)st.R; t += tstep) {
                 int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
                 Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
+                int e = e0;
+                if (HB_ENC_MAC4 && mac4_ok) {
+#pragma unroll 1
+                    for (; e + 4 <= e1; e += 4) {
+                        const uint2 d0 = ld_edge(&edges[e]), d1 = ld_edge(&edges[e + 1]), d2 = ld_edge(&edges[e + 2]), d3 = ld_edge(&edges[e + 3]);
+                        const F x0 = cw[d0.x * CB + c], x1 = cw[d1.x * CB + c], x2 = cw[d2.x * CB + c], x3 = cw[d3.x * CB + c];
+                        acc_mac4(are, x0.re, x1.re, x2.re, x3.re, d0.y, d1.y, d2.y, d3.y);
+                        acc_mac4(aim, x0.im, x1.im, x2.im, x3.im, d0.y, d1.y, d2.y, d3.y);
+                    }
+                }
 #pragma unroll 4
-                for (int e = e0; e < e1; e++) {
+                for (; e < e1; e++) {
                     uint2 ed = ld_edge(&edges[e]);
                     F x = cw[ed.x * CB + c];
                     acc_mac(are, x.re, ed.y);
@@ -161,8 +187,18 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
                 Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
                 if (slot < slots) {
                     const int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
+                    int e = e0 + (int)part;
+                    if (HB_ENC_MAC4 && mac4_ok) {
+#pragma unroll 1
+                        for (; e + 3 * (int)P < e1; e += 4 * (int)P) {
+                            const uint2 d0 = ld_edge(&edges[e]), d1 = ld_edge(&edges[e + P]), d2 = ld_edge(&edges[e + 2 * P]), d3 = ld_edge(&edges[e + 3 * P]);
+                            const F x0 = cw[d0.x * CB + c], x1 = cw[d1.x * CB + c], x2 = cw[d2.x * CB + c], x3 = cw[d3.x * CB + c];
+                            acc_mac4(are, x0.re, x1.re, x2.re, x3.re, d0.y, d1.y, d2.y, d3.y);
+                            acc_mac4(aim, x0.im, x1.im, x2.im, x3.im, d0.y, d1.y, d2.y, d3.y);
+                        }
+                    }
 #pragma unroll 2
-                    for (int e = e0 + (int)part; e < e1; e += (int)P) {
+                    for (; e < e1; e += (int)P) {
                         uint2 ed = ld_edge(&edges[e]);
                         F x = cw[ed.x * CB + c];
                         acc_mac(are, x.re, ed.y);
@@ -261,6 +297,8 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     // TMA tile movement when the launch is one dense (2*cols u64) x (2n * nchunks) matrix and the message rows split into whole boxes
     CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
     int box_rows = 0;
+    static const int mac4_env = getenv("HB_ENCODE_MAC4") ? atoi(getenv("HB_ENCODE_MAC4")) : 1;   // experiment switch
+    const int mac4_ok = mac4_env && ex.w31;
     static const int tma_ok = getenv("HB_ENCODE_TMA") ? atoi(getenv("HB_ENCODE_TMA")) : 1;   // experiment switch
     if (tma_ok && encode_tiled_fn() && (nchunks == 1 || chunk_stride == (size_t)(2 * n) * cols) && (n % 256 == 0 || n <= 256) && ((uintptr_t)T % 16) == 0 &&
         (size_t)(2 * n) * nchunks < ((size_t)1 << 31)) {
@@ -274,11 +312,11 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     if (inner) {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows);
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows, mac4_ok);
     } else {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, false>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
-                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows);
+                  ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows, mac4_ok);
     }
     if (prof) {                                                   // development aid: cumulative cycles per phase (thread 0 of every CTA)
         unsigned long long h[16];
@@ -347,7 +385,7 @@ extern "C" int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, 
     auto add_stage = [&](long long in_off, long long L, long long out_off, long long R, int deg, const uint32_t *nbr, const uint64_t *w) -> int {
         EncStage st; st.in_off = (int)in_off; st.out_off = (int)out_off; st.L = (int)L; st.R = (int)R; st.rowptr_base = (int)rowptr.size();
         std::vector<int> cnt(R + 1, 0);
-        for (long long i = 0; i < L * deg; i++) { if (nbr[i] >= (uint32_t)R) return 1; if (w[i] >> 32) return 1; cnt[nbr[i] + 1]++; }
+        for (long long i = 0; i < L * deg; i++) { if (nbr[i] >= (uint32_t)R) return 1; if (w[i] >> 32) return 1; if (w[i] >> 31) ex.w31 = false; cnt[nbr[i] + 1]++; }
         for (long long t = 0; t < R; t++) { ex.max_indeg = std::max(ex.max_indeg, cnt[t + 1]); cnt[t + 1] += cnt[t]; }
         size_t ebase = edges.size();
         edges.resize(ebase + (size_t)L * deg);

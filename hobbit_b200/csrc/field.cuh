@@ -90,11 +90,17 @@ __device__ __forceinline__ FN fprep(F b) {                       // b canonical
     return q;
 }
 // (a*c + e*d) mod p, result <= p + 7.  a, e given as (x0, x1) limbs of values <= p + 7; c, d as (y0, y1, 2 y1) of values <= p.
-__device__ __forceinline__ u64 dot61_lazy(uint32_t a0, uint32_t a1, uint32_t e0, uint32_t e1,
-                                          uint32_t c0, uint32_t c1, uint32_t c1d, uint32_t d0, uint32_t d1, uint32_t d1d) {
+// the unreduced sum: < 2^63 + 2^62 + 2^61 (two products < (2^31-1)^2, two <= 2^30 (2^31-2), u < 2^61 + 2^33), so one more canonical
+// value can be added to it without leaving 64 bits
+__device__ __forceinline__ u64 dot61_raw(uint32_t a0, uint32_t a1, uint32_t e0, uint32_t e1,
+                                         uint32_t c0, uint32_t c1, uint32_t c1d, uint32_t d0, uint32_t d1, uint32_t d1d) {
     const u64 mid = madwide(e0, d1, madwide(e1, d0, madwide(a0, c1, mulwide(a1, c0))));                 // < 2^63
     const u64 u = madwide((uint32_t)mid & 0x3fffffffu, 0x80000000u, mid >> 30);                         // == 2^31 mid, < 2^61 + 2^33
-    const u64 t = madwide(e1, d1d, madwide(a1, c1d, madwide(e0, d0, madwide(a0, c0, u))));              // < 2^64
+    return madwide(e1, d1d, madwide(a1, c1d, madwide(e0, d0, madwide(a0, c0, u))));                     // < 2^64 - 2^61
+}
+__device__ __forceinline__ u64 dot61_lazy(uint32_t a0, uint32_t a1, uint32_t e0, uint32_t e1,
+                                          uint32_t c0, uint32_t c1, uint32_t c1d, uint32_t d0, uint32_t d1, uint32_t d1d) {
+    const u64 t = dot61_raw(a0, a1, e0, e1, c0, c1, c1d, d0, d1, d1d);
     return (t & P61) + (t >> 61);
 }
 // a (limbs <= p + 7, e.g. a previous lazy product) times a prepared operand; limbs of the result <= p + 7, NOT canonical
@@ -102,6 +108,12 @@ __device__ __forceinline__ F fmul_n_lazy(F a, const FN &b) {
     const uint32_t x0 = (uint32_t)a.re & 0x7fffffffu, x1 = (uint32_t)(a.re >> 31), y0 = (uint32_t)a.im & 0x7fffffffu, y1 = (uint32_t)(a.im >> 31);
     return mkF(dot61_lazy(x0, x1, y0, y1, b.r0, b.r1, b.r1d, b.n0, b.n1, b.n1d),
                dot61_lazy(x0, x1, y0, y1, b.i0, b.i1, b.i1d, b.r0, b.r1, b.r1d));
+}
+// the same product with both limbs left as raw 64-bit sums (< 2^64 - 2^61): for callers that add something before the one fold
+__device__ __forceinline__ F fmul_n_raw(F a, const FN &b) {
+    const uint32_t x0 = (uint32_t)a.re & 0x7fffffffu, x1 = (uint32_t)(a.re >> 31), y0 = (uint32_t)a.im & 0x7fffffffu, y1 = (uint32_t)(a.im >> 31);
+    return mkF(dot61_raw(x0, x1, y0, y1, b.r0, b.r1, b.r1d, b.n0, b.n1, b.n1d),
+               dot61_raw(x0, x1, y0, y1, b.i0, b.i1, b.i1d, b.r0, b.r1, b.r1d));
 }
 __device__ __forceinline__ F fcanon(F a) { return mkF(canon61(a.re), canon61(a.im)); }
 __device__ __forceinline__ F fmul_n(F a, const FN &b) { return fcanon(fmul_n_lazy(a, b)); }

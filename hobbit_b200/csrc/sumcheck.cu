@@ -26,9 +26,17 @@ template <int NT> struct Tabs { const F *in[NT]; F *out[NT]; };
 
 __device__ __forceinline__ F fold1(F x, F y, F r) { return fadd(x, fmul(r, fsub(y, x))); }
 // the same against a prepared challenge: x + r (y - x), canonical; d = y - x is handed back for the round polynomial
+#ifndef HB_SC_FUSEFOLD
+#define HB_SC_FUSEFOLD 1
+#endif
 __device__ __forceinline__ F fold1n(F x, F d, const FN &rn) {
+#if HB_SC_FUSEFOLD
+    const F t = fmul_n_raw(d, rn);                                   // raw sums < 2^64 - 2^61: x (canonical) is added BEFORE the one fold
+    return fcanon(lfold(mkF(x.re + t.re, x.im + t.im)));
+#else
     const F t = fmul_n_lazy(d, rn);                                  // limbs <= p + 7
     return fcanon2(mkF(x.re + t.re, x.im + t.im));                   // < 2p + 7 < 2^62
+#endif
 }
 
 // Round polynomial prod_t (x_t + X (y_t - x_t)) accumulated in EVALUATION form — fewer multiplications than its coefficients:
@@ -53,6 +61,25 @@ template <int NC> struct RegAcc {
     }
     __device__ __forceinline__ F get(int c) { return a[c]; }
 };
+// raw product sums (< 2^64 each) added into 96-bit accumulators: 3 instructions per limb and product instead of a fold (4) and an add (2),
+// and no periodic re-fold; 2^64 == 8 (mod p) brings the top word back at the end.  add_raw takes UNFOLDED limbs (fmul_n_raw).
+template <int NC> struct WideAcc {
+    uint32_t w[NC][2][3];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+            for (int l = 0; l < 2; l++) w[c][l][0] = w[c][l][1] = w[c][l][2] = 0;
+    }
+    __device__ __forceinline__ void add1(uint32_t (&a)[3], u64 v) {
+        asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+            : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]) : "r"((uint32_t)v), "r"((uint32_t)(v >> 32)));
+    }
+    __device__ __forceinline__ void add_raw(int c, F v) { add1(w[c][0], v.re); add1(w[c][1], v.im); }
+    __device__ __forceinline__ void fold() {}
+    __device__ __forceinline__ u64 get1(const uint32_t (&a)[3]) { return fold61(((u64)a[1] << 32) | a[0]) + 8ull * a[2]; }   // < 2^62
+    __device__ __forceinline__ F get(int c) { return mkF(get1(w[c][0]), get1(w[c][1])); }
+};
 template <int NC> struct SmemAcc {
     F *col;                                             // col[c * blockDim.x]: consecutive threads -> consecutive 16-byte slots, conflict-free
     __device__ __forceinline__ void init() {
@@ -66,21 +93,37 @@ template <int NC> struct SmemAcc {
     }
     __device__ __forceinline__ F get(int c) { return col[c * blockDim.x]; }
 };
+#ifndef HB_SC_ACC3
+#define HB_SC_ACC3 1
+#endif
 template <int NT, class Acc> __device__ __forceinline__ void poly_acc(Acc &acc, const F (&x)[NT], const F (&y)[NT], const F (&d)[NT]) {
     if (NT == 2) {
+#if HB_SC_ACC3
+        acc.add_raw(0, fmul_n_raw(d[0], fprep(d[1])));
+        acc.add_raw(1, fmul_n_raw(y[0], fprep(y[1])));
+        acc.add_raw(2, fmul_n_raw(x[0], fprep(x[1])));
+#else
         acc.add(0, fmul_n_lazy(d[0], fprep(d[1])));
         acc.add(1, fmul_n_lazy(y[0], fprep(y[1])));
         acc.add(2, fmul_n_lazy(x[0], fprep(x[1])));
+#endif
     } else if (NT == 3) {
         const F A = fmul_n_lazy(x[0], fprep(x[1])), B = fmul_n_lazy(y[0], fprep(y[1])), C = fmul_n_lazy(d[0], fprep(d[1]));
         // M = 2A + 2C - B: 2 (A + C) <= 4p + 28, + (2p - B) stays below 2^64; one fold -> limbs <= p + 7
         const F M = lfold(mkF(2 * (A.re + C.re) + (2 * P61 - B.re), 2 * (A.im + C.im) + (2 * P61 - B.im)));
         // m3 = 2 x3 - y3 (canonical: it is a right-hand operand)
         const F m3 = fcanon2(mkF(2 * x[2].re + (P61 - y[2].re), 2 * x[2].im + (P61 - y[2].im)));
+#if HB_SC_ACC3
+        acc.add_raw(0, fmul_n_raw(C, fprep(d[2])));
+        acc.add_raw(1, fmul_n_raw(B, fprep(y[2])));
+        acc.add_raw(2, fmul_n_raw(M, fprep(m3)));
+        acc.add_raw(3, fmul_n_raw(A, fprep(x[2])));
+#else
         acc.add(0, fmul_n_lazy(C, fprep(d[2])));
         acc.add(1, fmul_n_lazy(B, fprep(y[2])));
         acc.add(2, fmul_n_lazy(M, fprep(m3)));
         acc.add(3, fmul_n_lazy(A, fprep(x[2])));
+#endif
     }
 }
 // host side: evaluation sums -> coefficients, highest degree first (1/2 = 2^60 mod p)
@@ -121,6 +164,8 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
 #if HB_SC_SACC
     __shared__ F sacc[NC * HB_SC_THREADS];
     SmemAcc<NC> acc; acc.col = sacc + threadIdx.x;
+#elif HB_SC_ACC3
+    WideAcc<NC> acc;
 #else
     RegAcc<NC> acc;
 #endif
@@ -132,11 +177,28 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
 #define HB_SC_PF 2
 #endif
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += stride) {
-        F x[NT], y[NT], d[NT];
-        // The tables are streamed at ~3 TB/s: the loads of a pair would wait a loaded-DRAM round trip (ncu: long_scoreboard is the top stall
-        // with only 16 warps per SM).  The sectors of the pair this thread handles HB_SC_PF iterations later are pulled into L2 now — one
-        // prefetch instruction per 32-byte sector, no registers held.
+#ifndef HB_SC_RPF
+#define HB_SC_RPF 2
+#endif
+    // HB_SC_RPF: the table entries of this thread's NEXT pair are loaded into registers before the current pair is multiplied out (software
+    // pipelining one iteration deep), so that the DRAM round trip overlaps ~800 instructions of arithmetic instead of stalling the warp at the
+    // top of every iteration (ncu, round 2: long_scoreboard was the largest stall with 4 warps per scheduler).
+    constexpr int RPF = (MODE != FOLD_THEN_POLY && NT <= 3) ? HB_SC_RPF : 0;       // wider table sets (the fold-only passes of S7/S8) would spill
+    auto load_pair = [&](size_t jj, F (&xx)[NT], F (&yy)[NT]) {
+        if (INTERLEAVED) {
+            const F *p = t.in[0] + 4 * jj;
+            xx[0] = p[0]; xx[1] = p[1]; yy[0] = p[2]; yy[1] = p[3];
+#pragma unroll
+            for (int k = 2; k < NT; k++) { xx[k] = t.in[k][2 * jj]; yy[k] = t.in[k][2 * jj + 1]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NT; k++) { xx[k] = HB_SC_LD(&t.in[k][2 * jj]); yy[k] = HB_SC_LD(&t.in[k][2 * jj + 1]); }
+        }
+    };
+    // The tables are streamed at ~3 TB/s: the loads of a pair would wait a loaded-DRAM round trip (ncu: long_scoreboard is the top stall
+    // with only 16 warps per SM).  The sectors of the pair this thread handles HB_SC_PF iterations later are pulled into L2 now — one
+    // prefetch instruction per 32-byte sector, no registers held.
+    auto prefetch_l2 = [&](size_t j) {
         if (HB_SC_PF > 0 && j + HB_SC_PF * stride < L) {
             const size_t jp = j + HB_SC_PF * stride;
 #pragma unroll
@@ -146,23 +208,10 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
                 else if (!(INTERLEAVED && k == 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(t.in[k] + 2 * jp));
             }
         }
-        if (MODE == FOLD_THEN_POLY) {
-#pragma unroll
-            for (int k = 0; k < NT; k++) {
-                const F *p = t.in[k] + 4 * j;
-                const F a = p[0], b = p[1], c = p[2], e = p[3];
-                x[k] = fold1n(a, fsub(b, a), rn); y[k] = fold1n(c, fsub(e, c), rn);
-                t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y[k];
-            }
-        } else if (INTERLEAVED) {
-            const F *p = t.in[0] + 4 * j;
-            x[0] = p[0]; x[1] = p[1]; y[0] = p[2]; y[1] = p[3];
-#pragma unroll
-            for (int k = 2; k < NT; k++) { x[k] = t.in[k][2 * j]; y[k] = t.in[k][2 * j + 1]; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NT; k++) { x[k] = HB_SC_LD(&t.in[k][2 * j]); y[k] = HB_SC_LD(&t.in[k][2 * j + 1]); }
-        }
+    };
+    // one pair whose entries are in registers: round polynomial terms and/or the folded entry
+    auto process = [&](size_t j, const F (&x)[NT], const F (&y)[NT]) {
+        F d[NT];
 #pragma unroll
         for (int k = 0; k < NT; k++) d[k] = fsub(y[k], x[k]);
         if (MODE != FOLD_ONLY) {
@@ -173,11 +222,54 @@ sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
 #pragma unroll
             for (int k = 0; k < NT; k++) t.out[k][j] = fold1n(x[k], d[k], rn);
         }
+    };
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (RPF == 2) {
+        // two register sets in ping-pong (the loop is unrolled twice so that no set is ever copied)
+        F ax[NT], ay[NT], bx[NT], by[NT];
+        if (j < L) load_pair(j, ax, ay);
+        while (j < L) {
+            prefetch_l2(j);
+            if (j + stride < L) load_pair(j + stride, bx, by);
+            process(j, ax, ay);
+            j += stride;
+            if (j >= L) break;
+            prefetch_l2(j);
+            if (j + stride < L) load_pair(j + stride, ax, ay);
+            process(j, bx, by);
+            j += stride;
+        }
+    } else if (RPF == 1) {
+        F nx[NT], ny[NT];
+        if (j < L) load_pair(j, nx, ny);
+        for (; j < L; j += stride) {
+            F x[NT], y[NT];
+            prefetch_l2(j);
+#pragma unroll
+            for (int k = 0; k < NT; k++) { x[k] = nx[k]; y[k] = ny[k]; }
+            if (j + stride < L) load_pair(j + stride, nx, ny);
+            process(j, x, y);
+        }
+    } else {
+        for (; j < L; j += stride) {
+            F x[NT], y[NT];
+            prefetch_l2(j);
+            if (MODE == FOLD_THEN_POLY) {
+#pragma unroll
+                for (int k = 0; k < NT; k++) {
+                    const F *p = t.in[k] + 4 * j;
+                    const F a = p[0], b = p[1], c = p[2], e = p[3];
+                    x[k] = fold1n(a, fsub(b, a), rn); y[k] = fold1n(c, fsub(e, c), rn);
+                    t.out[k][2 * j] = x[k]; t.out[k][2 * j + 1] = y[k];
+                }
+            } else load_pair(j, x, y);
+            process(j, x, y);
+        }
     }
     if (MODE == FOLD_ONLY) return;
     F accv[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) accv[c] = fcanon2(lfold(acc.get(c)));
+    for (int c = 0; c < NC; c++) accv[c] = fcanon2(lfold(acc.get(c)));          // get(): limbs < 2^64 (RegAcc) or < 2^62 (WideAcc)
 
     grid_reduce<NC>(accv, ra);
 }
