@@ -124,6 +124,18 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
         lp[1] = make_uint4(out[4], out[5], out[6], out[7]);
     };
     if (INNER && threadIdx.x == 0) hash_next = 0;
+    // edges e, e + step, .. below e1 in groups of four.  (Measured and not kept, profiles/r02_summary.md: fetching the NEXT group's edge
+    // records early — into a second register set, or into L1 with prefetch.global.L1 — to hide their L2 round trip: ptxas sinks the loads
+    // to the end of the group under the 64-register cap, 3.58 vs 3.32 ms; the L1 prefetch changes nothing.  Two CTAs per SM hide it instead.)
+    auto mac4_run = [&](Acc &are, Acc &aim, int &e, int e1, int step) {
+#pragma unroll 1
+        for (; e + 3 * step < e1; e += 4 * step) {
+            const uint2 a0 = ld_edge(&edges[e]), a1 = ld_edge(&edges[e + step]), a2 = ld_edge(&edges[e + 2 * step]), a3 = ld_edge(&edges[e + 3 * step]);
+            const F x0 = cw[a0.x * CB + c], x1 = cw[a1.x * CB + c], x2 = cw[a2.x * CB + c], x3 = cw[a3.x * CB + c];
+            acc_mac4(are, x0.re, x1.re, x2.re, x3.re, a0.y, a1.y, a2.y, a3.y);
+            acc_mac4(aim, x0.im, x1.im, x2.im, x3.im, a0.y, a1.y, a2.y, a3.y);
+        }
+    };
 
     if (box_rows) {
         // message rows -> shared memory by TMA: one thread, n / box_rows boxes in flight, one mbarrier
@@ -156,21 +168,16 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
         // Small stages have fewer rows than the CTA has row slots (blockDim / CB): their rows are split over P = 2 or 4 adjacent slots
         // (lanes 8 or 8 and 16 apart in the same warp when CB == 8), every slot sums every P-th edge and the partial sums are added
         // with shuffles — exact in the field, so the result is the same canonical value.
-        const unsigned P = !split_ok ? 1u : (CB == 8 && (unsigned)st.R * 4 <= tstep) ? 4u : (CB == 8 && (unsigned)st.R * 2 <= tstep) ? 2u : 1u;
+        // (CB == 4: the slots of a row are lanes 4, 8 and 16 apart and a row may be split eight ways.)
+        constexpr unsigned SPW = 32 / CB;                                     // row slots per warp
+        const unsigned P = (!split_ok || (CB != 8 && CB != 4)) ? 1u : (CB == 4 && (unsigned)st.R * 8 <= tstep) ? 8u : ((unsigned)st.R * 4 <= tstep) ? 4u
+                         : ((unsigned)st.R * 2 <= tstep) ? 2u : 1u;
         if (P == 1) {
             for (unsigned t = t0; t < (unsigned)st.R; t += tstep) {
                 int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
                 Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
                 int e = e0;
-                if (HB_ENC_MAC4 && mac4_ok) {
-#pragma unroll 1
-                    for (; e + 4 <= e1; e += 4) {
-                        const uint2 d0 = ld_edge(&edges[e]), d1 = ld_edge(&edges[e + 1]), d2 = ld_edge(&edges[e + 2]), d3 = ld_edge(&edges[e + 3]);
-                        const F x0 = cw[d0.x * CB + c], x1 = cw[d1.x * CB + c], x2 = cw[d2.x * CB + c], x3 = cw[d3.x * CB + c];
-                        acc_mac4(are, x0.re, x1.re, x2.re, x3.re, d0.y, d1.y, d2.y, d3.y);
-                        acc_mac4(aim, x0.im, x1.im, x2.im, x3.im, d0.y, d1.y, d2.y, d3.y);
-                    }
-                }
+                if (HB_ENC_MAC4 && mac4_ok) mac4_run(are, aim, e, e1, 1);
 #pragma unroll 4
                 for (; e < e1; e++) {
                     uint2 ed = ld_edge(&edges[e]);
@@ -183,20 +190,12 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
         } else {
             const unsigned slots = (unsigned)st.R * P;                       // <= tstep: one pass
             const unsigned slot = t0, t = slot / P, part = slot % P;
-            if ((t0 & ~3u) < slots) {                                         // warp-uniform: the four slots of a warp are 4a .. 4a+3
+            if ((t0 & ~(SPW - 1)) < slots) {                                  // warp-uniform: the slots of a warp are SPW*a .. SPW*a + SPW - 1
                 Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
                 if (slot < slots) {
                     const int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
                     int e = e0 + (int)part;
-                    if (HB_ENC_MAC4 && mac4_ok) {
-#pragma unroll 1
-                        for (; e + 3 * (int)P < e1; e += 4 * (int)P) {
-                            const uint2 d0 = ld_edge(&edges[e]), d1 = ld_edge(&edges[e + P]), d2 = ld_edge(&edges[e + 2 * P]), d3 = ld_edge(&edges[e + 3 * P]);
-                            const F x0 = cw[d0.x * CB + c], x1 = cw[d1.x * CB + c], x2 = cw[d2.x * CB + c], x3 = cw[d3.x * CB + c];
-                            acc_mac4(are, x0.re, x1.re, x2.re, x3.re, d0.y, d1.y, d2.y, d3.y);
-                            acc_mac4(aim, x0.im, x1.im, x2.im, x3.im, d0.y, d1.y, d2.y, d3.y);
-                        }
-                    }
+                    if (HB_ENC_MAC4 && mac4_ok) mac4_run(are, aim, e, e1, (int)P);
 #pragma unroll 2
                     for (; e < e1; e += (int)P) {
                         uint2 ed = ld_edge(&edges[e]);
@@ -206,8 +205,9 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
                     }
                 }
                 u64 re = acc_reduce(are), im = acc_reduce(aim);
-                re = add61(re, __shfl_xor_sync(0xffffffffu, re, 8)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 8));
-                if (P == 4) { re = add61(re, __shfl_xor_sync(0xffffffffu, re, 16)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 16)); }
+                re = add61(re, __shfl_xor_sync(0xffffffffu, re, CB)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, CB));
+                if (P >= 4) { re = add61(re, __shfl_xor_sync(0xffffffffu, re, 2 * CB)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 2 * CB)); }
+                if (P >= 8) { re = add61(re, __shfl_xor_sync(0xffffffffu, re, 4 * CB)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 4 * CB)); }
                 if (slot < slots && part == 0) cw[(st.out_off + t) * CB + c] = mkF(re, im);
             }
         }
@@ -287,8 +287,10 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     const ExpanderDev &ex = ctx->exp;
     size_t smem = (size_t)ex.cwlen * CB * sizeof(F);
     dim3 grid((unsigned)(cols / CB), (unsigned)nchunks);
-    // small codes: several CTAs per SM, 256 threads each; the big code (one 220 KB CTA per SM) gets 1024 threads
-    unsigned threads = smem > 100 * 1024 ? 1024 : 256;
+    // small codes: several CTAs per SM, 256 threads each; the big code gets 1024 threads when one CTA fills the SM (8 columns, 220 KB) and
+    // 512 when two CTAs share it (4 columns, 2 x 110 KB: one CTA's tile load, small stages and barriers overlap the other's big stages)
+    const bool two_per_sm = smem > 100 * 1024 && 2 * (smem + 1024) <= 228 * 1024;
+    unsigned threads = two_per_sm ? 512 : smem > 100 * 1024 ? 1024 : 256;
     static unsigned long long *prof = nullptr;
     static const int help_ok = getenv("HB_ENCODE_HELP") ? atoi(getenv("HB_ENCODE_HELP")) : 1;      // experiment switch
     static const int split_ok = getenv("HB_ENCODE_SPLIT") ? atoi(getenv("HB_ENCODE_SPLIT")) : 1;   // experiment switch
@@ -311,10 +313,12 @@ static int launch_encode(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nch
     }
     if (inner) {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (two_per_sm) HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, true>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
                   ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows, mac4_ok);
     } else {
         HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (two_per_sm) HB_CHECK(ctx, cudaFuncSetAttribute(encode_cols_kernel<CB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         HB_LAUNCH(ctx, (encode_cols_kernel<CB, false>), grid, threads, smem, T, chunk_stride, cols, (int)n, ex.cwlen, ex.d_stages, (int)ex.stages.size(),
                   ex.d_rowptr, ex.d_edges, inner, zero_quad_digest(), lay, prof, split_ok, help_ok, tmap, box_rows, mac4_ok);
     }
@@ -339,13 +343,17 @@ int encode_cols_dev(hb_ctx *ctx, F *T, long long n, size_t cols, size_t nchunks,
     // widest column block that fits; prefer <= ~100 KB tiles when the code is small so several CTAs share an SM
     if (cols % 32 == 0 && per_col * 32 <= 100 * 1024) return launch_encode<32>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 16 == 0 && per_col * 16 <= 100 * 1024) return launch_encode<16>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
-    // Measured on B200 at n = 1024 (bench.py, ms per launch of 16 chunks): 8 columns per CTA (one 220 KB CTA per SM) 3.58; 4 columns (two
-    // CTAs per SM, max carveout) 3.62; 2 columns (four CTAs) 4.43; fetching each edge once per 8-lane group and passing it round with
-    // shuffles 5.01.  The kernel is bound by instruction issue (multiply-add chains + BLAKE3), not by occupancy or by the edge loads.
+    // Measured on B200 at n = 1024 (bench.py, ms per launch of 16 chunks).  Round 1: 8 columns per CTA (one 220 KB CTA per SM) 3.58; 4 columns
+    // (two CTAs per SM) 3.62; 2 columns (four CTAs) 4.43; fetching each edge once per 8-lane group and passing it round with shuffles 5.01.
+    // Round 2, after the four-edge accumulation cut the instruction count by 16 %: 8 columns x 1024 threads 3.32, 4 columns x 512 threads
+    // x two CTAs per SM 3.17 — with fewer instructions the stage barriers, the tile load and the edge-load latency of one CTA are worth
+    // overlapping with the other CTA's arithmetic.  So: two CTAs of 4 columns when both tiles fit, else one CTA of 8.
     if (const char *e = getenv("HB_ENCODE_CB")) {                                            // experiment switch
+        if (atoi(e) == 8 && cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
         if (atoi(e) == 4 && cols % 4 == 0) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
         if (atoi(e) == 2 && cols % 2 == 0) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     }
+    if (cols % 4 == 0 && per_col * 4 > 100 * 1024 && 2 * (per_col * 4 + 1024) <= 228 * 1024) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 8 == 0 && per_col * 8 <= kMaxSmem) return launch_encode<8>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 4 == 0 && per_col * 4 <= kMaxSmem) return launch_encode<4>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
     if (cols % 2 == 0 && per_col * 2 <= kMaxSmem) return launch_encode<2>(ctx, T, n, cols, nchunks, chunk_stride, inner, lay);
