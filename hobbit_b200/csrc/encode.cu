@@ -69,7 +69,10 @@ __device__ __forceinline__ int ld_rowptr(const int *p) { int v; asm("ld.global.n
 // grid: (cols / CB, nchunks).  inner != nullptr: also emit the inner leaf digests H1(T[4j][k] | .. | T[4j+3][k])
 // of this chunk (commit_standard hashes 4-row quads of every column, Our_PC.cpp:160-166); the Merkle–Damgård chaining
 // over chunks is done afterwards by md_chain_kernel so that all chunks can be encoded in one launch.
-constexpr int kHelpUnits = 2;
+#ifndef HB_ENC_HELP_UNITS
+#define HB_ENC_HELP_UNITS 2
+#endif
+constexpr int kHelpUnits = HB_ENC_HELP_UNITS;
 // TMA (cp.async.bulk.tensor): the CTA's tile — CB adjacent columns x all message rows, a dense [rows][CB] block of 16-byte elements — is
 // fetched by ONE thread as 2-D boxes of up to 256 rows that land in shared memory in exactly the cw[row][CB] layout the stages use
 // (no swizzle: a quarter-warp reads one contiguous 16*CB-byte row), completion on an mbarrier; the parity rows go back the same way.
@@ -127,8 +130,12 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
     // edges e, e + step, .. below e1 in groups of four.  (Measured and not kept, profiles/r02_summary.md: fetching the NEXT group's edge
     // records early — into a second register set, or into L1 with prefetch.global.L1 — to hide their L2 round trip: ptxas sinks the loads
     // to the end of the group under the 64-register cap, 3.58 vs 3.32 ms; the L1 prefetch changes nothing.  Two CTAs per SM hide it instead.)
+#ifndef HB_ENC_MAC4_UNROLL
+#define HB_ENC_MAC4_UNROLL 1
+#endif
+    constexpr int kMac4Unroll = HB_ENC_MAC4_UNROLL;
     auto mac4_run = [&](Acc &are, Acc &aim, int &e, int e1, int step) {
-#pragma unroll 1
+#pragma unroll kMac4Unroll
         for (; e + 3 * step < e1; e += 4 * step) {
             const uint2 a0 = ld_edge(&edges[e]), a1 = ld_edge(&edges[e + step]), a2 = ld_edge(&edges[e + 2 * step]), a3 = ld_edge(&edges[e + 3 * step]);
             const F x0 = cw[a0.x * CB + c], x1 = cw[a1.x * CB + c], x2 = cw[a2.x * CB + c], x3 = cw[a3.x * CB + c];

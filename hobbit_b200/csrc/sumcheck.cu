@@ -111,8 +111,8 @@ template <int NT, class Acc> __device__ __forceinline__ void poly_acc(Acc &acc, 
         const F A = fmul_n_lazy(x[0], fprep(x[1])), B = fmul_n_lazy(y[0], fprep(y[1])), C = fmul_n_lazy(d[0], fprep(d[1]));
         // M = 2A + 2C - B: 2 (A + C) <= 4p + 28, + (2p - B) stays below 2^64; one fold -> limbs <= p + 7
         const F M = lfold(mkF(2 * (A.re + C.re) + (2 * P61 - B.re), 2 * (A.im + C.im) + (2 * P61 - B.im)));
-        // m3 = 2 x3 - y3 (canonical: it is a right-hand operand)
-        const F m3 = fcanon2(mkF(2 * x[2].re + (P61 - y[2].re), 2 * x[2].im + (P61 - y[2].im)));
+        // m3 = 2 x3 - y3 = x3 - d3 (canonical: it is a right-hand operand; one borrow-chain subtraction)
+        const F m3 = fsub(x[2], d[2]);
 #if HB_SC_ACC3
         acc.add_raw(0, fmul_n_raw(C, fprep(d[2])));
         acc.add_raw(1, fmul_n_raw(B, fprep(y[2])));

@@ -82,7 +82,10 @@ int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, int deg_D,
 /* codeword length of the installed code (n + L + R), 0 if none */
 long long hb_expander_codeword_len(hb_ctx *ctx);
 /* encode_monolithic for `ncols` messages at once.  src: n x ncols row-major (message c = column c);
- * dst: 2n x ncols row-major; rows >= codeword length are zero (the reference's caller buffer is 2n, zero tail). */
+ * dst: 2n x ncols row-major; rows >= codeword length are zero (the reference's caller buffer is 2n, zero tail).
+ * Message entries must be canonical field elements (both limbs < p, as every fieldElement the reference produces is): with weights
+ * < 2^31 (the reference draws them with random()) the kernel sums four edge products on the 64-bit addend of IMAD.WIDE before it touches
+ * the wide accumulators, which has no headroom for limbs >= 2^61.  Graphs with a weight >= 2^31 take the one-edge-at-a-time path. */
 int hb_encode_batch(hb_ctx *ctx, const hb_F *src, hb_F *dst, long long n, size_t ncols);
 
 /* ---- H1..H4: BLAKE3 leaves and the Merkle tree (Blake3_hash.cpp:5-10; merkle_tree.cpp:62-87,193-287) ------ */
