@@ -20,7 +20,7 @@ static constexpr int kMaxRanks = 8;     // GPUs of one NVSwitch box
 
 struct EncStage {                       // one sparse mat-vec of the expander encode: out[0..R) = G * in[0..L)
     int in_off, out_off, L, R;          // offsets/sizes in codeword coordinates
-    int rowptr_base;                    // index into rowptr[] (R+1 entries)
+    int rowptr_base;                    // index into rows[] (R+1 entries)
 };
 
 // Where the inner leaf digest of (chunk c of this launch, leaf position p) goes.  Plain: [chunk][leaf].  Sharded exchange layout
@@ -70,7 +70,7 @@ struct ExpanderDev {
     int cwlen = 0;
     std::vector<EncStage> stages;       // execution order: C0..C_last, D_last..D0
     EncStage *d_stages = nullptr;
-    int *d_rowptr = nullptr;            // CSR by target
+    uint2 *d_rowptr = nullptr;          // CSR by target, rows in processing order: {first edge, target row within the stage}; R+1 entries per stage
     uint2 *d_edges = nullptr;           // {absolute source index in the codeword, 32-bit weight}
     size_t n_edges = 0;
     int max_indeg = 0;

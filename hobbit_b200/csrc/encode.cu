@@ -64,7 +64,7 @@ __device__ __forceinline__ uint2 ld_edge(const uint2 *p) {
     asm("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
-__device__ __forceinline__ int ld_rowptr(const int *p) { int v; asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int ld_rowptr(const uint2 *p) { int v; asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }   // .x only
 
 // grid: (cols / CB, nchunks).  inner != nullptr: also emit the inner leaf digests H1(T[4j][k] | .. | T[4j+3][k])
 // of this chunk (commit_standard hashes 4-row quads of every column, Our_PC.cpp:160-166); the Merkle–Damgård chaining
@@ -89,7 +89,7 @@ template <int CB, bool INNER>
 __global__ void __launch_bounds__(1024)
 encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int n, int cwlen,
                    const EncStage *__restrict__ stages, int nstages,
-                   const int *__restrict__ rowptr, const uint2 *__restrict__ edges,
+                   const uint2 *__restrict__ rowptr, const uint2 *__restrict__ edges,
                    uint8_t *__restrict__ inner_base, Digest zero_quad, InnerLayout lay, unsigned long long *__restrict__ prof, int split_ok, int help_ok,
                    const __grid_constant__ CUtensorMap tmap, int box_rows, int mac4_ok) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -171,7 +171,7 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
 
     for (int s = 0; s < nstages; s++) {
         const EncStage st = stages[s];
-        const int *rp = rowptr + st.rowptr_base;
+        const uint2 *rp = rowptr + st.rowptr_base;        // rows in processing order (sorted by in-degree on the host): {first edge, target row}
         // Small stages have fewer rows than the CTA has row slots (blockDim / CB): their rows are split over P = 2 or 4 adjacent slots
         // (lanes 8 or 8 and 16 apart in the same warp when CB == 8), every slot sums every P-th edge and the partial sums are added
         // with shuffles — exact in the field, so the result is the same canonical value.
@@ -181,7 +181,8 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
                          : ((unsigned)st.R * 2 <= tstep) ? 2u : 1u;
         if (P == 1) {
             for (unsigned t = t0; t < (unsigned)st.R; t += tstep) {
-                int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
+                const uint2 row = ld_edge(&rp[t]);
+                const int e0 = (int)row.x, e1 = ld_rowptr(&rp[t + 1]);
                 Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
                 int e = e0;
                 if (HB_ENC_MAC4 && mac4_ok) mac4_run(are, aim, e, e1, 1);
@@ -192,15 +193,18 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
                     acc_mac(are, x.re, ed.y);
                     acc_mac(aim, x.im, ed.y);
                 }
-                cw[(st.out_off + t) * CB + c] = mkF(acc_reduce(are), acc_reduce(aim));
+                cw[(st.out_off + row.y) * CB + c] = mkF(acc_reduce(are), acc_reduce(aim));
             }
         } else {
             const unsigned slots = (unsigned)st.R * P;                       // <= tstep: one pass
             const unsigned slot = t0, t = slot / P, part = slot % P;
             if ((t0 & ~(SPW - 1)) < slots) {                                  // warp-uniform: the slots of a warp are SPW*a .. SPW*a + SPW - 1
                 Acc are = {0, 0, 0, 0, 0, 0}, aim = {0, 0, 0, 0, 0, 0};
+                unsigned target = 0;
                 if (slot < slots) {
-                    const int e0 = ld_rowptr(&rp[t]), e1 = ld_rowptr(&rp[t + 1]);
+                    const uint2 row = ld_edge(&rp[t]);
+                    const int e0 = (int)row.x, e1 = ld_rowptr(&rp[t + 1]);
+                    target = row.y;
                     int e = e0 + (int)part;
                     if (HB_ENC_MAC4 && mac4_ok) mac4_run(are, aim, e, e1, (int)P);
 #pragma unroll 2
@@ -215,7 +219,7 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
                 re = add61(re, __shfl_xor_sync(0xffffffffu, re, CB)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, CB));
                 if (P >= 4) { re = add61(re, __shfl_xor_sync(0xffffffffu, re, 2 * CB)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 2 * CB)); }
                 if (P >= 8) { re = add61(re, __shfl_xor_sync(0xffffffffu, re, 4 * CB)); im = add61(im, __shfl_xor_sync(0xffffffffu, im, 4 * CB)); }
-                if (slot < slots && part == 0) cw[(st.out_off + t) * CB + c] = mkF(re, im);
+                if (slot < slots && part == 0) cw[(st.out_off + target) * CB + c] = mkF(re, im);
             }
         }
         // Warps without a row slot in this stage (the small stages of the recursion keep only a few warps busy, and those are bound by
@@ -396,21 +400,46 @@ extern "C" int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, 
     ex.cwlen = (int)lenc[0];
     if (levels == 0) return 0;
 
-    std::vector<int> rowptr; std::vector<uint2> edges;
+    // CSR by target.  The rows of a stage are stored in PROCESSING order, not in target order: a warp walks the edge lists of its 32 / CB
+    // rows in lockstep, so it runs as long as its longest row (in-degrees of these random graphs spread +-40 %: natural order costs 25 %
+    // more lockstep steps than the edges need).  Rows are therefore sorted by in-degree, longest first, and laid out in snake order over
+    // the passes of kRowSlots rows so that every row slot gets a similar total; each row record carries its target.  Within a row the
+    // edges are ordered by the parity of their source row (even rows first for even positions, odd first for odd ones): with 4-column
+    // tiles two adjacent rows share one shared-memory wavefront and collide when their sources have the same parity.  The sums are exact
+    // in the field, so neither order changes a bit of the result.
+    static const int sort_rows = getenv("HB_ENCODE_ROWSORT") ? atoi(getenv("HB_ENCODE_ROWSORT")) : 1;     // experiment switches
+    static const int sort_edges = getenv("HB_ENCODE_EDGEPAR") ? atoi(getenv("HB_ENCODE_EDGEPAR")) : 1;
+    constexpr long long kRowSlots = 128;                  // row slots of the big-code launches (1024 threads x 8 columns, 512 x 4)
+    std::vector<uint2> rowptr; std::vector<uint2> edges;
     auto add_stage = [&](long long in_off, long long L, long long out_off, long long R, int deg, const uint32_t *nbr, const uint64_t *w) -> int {
         EncStage st; st.in_off = (int)in_off; st.out_off = (int)out_off; st.L = (int)L; st.R = (int)R; st.rowptr_base = (int)rowptr.size();
         std::vector<int> cnt(R + 1, 0);
         for (long long i = 0; i < L * deg; i++) { if (nbr[i] >= (uint32_t)R) return 1; if (w[i] >> 32) return 1; if (w[i] >> 31) ex.w31 = false; cnt[nbr[i] + 1]++; }
-        for (long long t = 0; t < R; t++) { ex.max_indeg = std::max(ex.max_indeg, cnt[t + 1]); cnt[t + 1] += cnt[t]; }
+        // processing position of every target
+        std::vector<int> by_deg(R), pos_of(R);
+        for (long long t = 0; t < R; t++) { by_deg[t] = (int)t; ex.max_indeg = std::max(ex.max_indeg, cnt[t + 1]); }
+        if (sort_rows) std::stable_sort(by_deg.begin(), by_deg.end(), [&](int a, int b) { return cnt[a + 1] > cnt[b + 1]; });
+        for (long long r = 0; r < R; r++) {
+            long long pass = r / kRowSlots, within = r % kRowSlots, in_pass = std::min(kRowSlots, R - pass * kRowSlots);
+            if (sort_rows && (pass & 1)) within = in_pass - 1 - within;
+            pos_of[by_deg[r]] = (int)(pass * kRowSlots + within);
+        }
+        std::vector<int> target_at(R), start(R + 1, 0);
+        for (long long t = 0; t < R; t++) target_at[pos_of[t]] = (int)t;
+        for (long long v = 0; v < R; v++) start[v + 1] = start[v] + cnt[target_at[v] + 1];
         size_t ebase = edges.size();
         edges.resize(ebase + (size_t)L * deg);
-        std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+        std::vector<int> fill(start.begin(), start.end() - 1);
         for (long long i = 0; i < L; i++)
             for (int j = 0; j < deg; j++) {
-                uint32_t t = nbr[i * deg + j];
-                edges[ebase + fill[t]++] = make_uint2((unsigned)(in_off + i), (unsigned)w[i * deg + j]);
+                const int v = pos_of[nbr[i * deg + j]];
+                edges[ebase + fill[v]++] = make_uint2((unsigned)(in_off + i), (unsigned)w[i * deg + j]);
             }
-        for (long long t = 0; t <= R; t++) rowptr.push_back((int)ebase + cnt[t]);
+        if (sort_edges)
+            for (long long v = 0; v < R; v++)
+                std::stable_partition(edges.begin() + ebase + start[v], edges.begin() + ebase + start[v + 1],
+                                      [&](const uint2 &e) { return ((e.x ^ (unsigned)v) & 1u) == 0; });
+        for (long long v = 0; v <= R; v++) rowptr.push_back(make_uint2((unsigned)(ebase + start[v]), v < R ? (unsigned)target_at[v] : 0u));
         ex.stages.push_back(st);
         return 0;
     };
@@ -420,10 +449,10 @@ extern "C" int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, 
         if (add_stage(off[d + 1], lenc[d + 1], off[d + 1] + lenc[d + 1], R_D[d], deg_D, nbr_D[d], w_D[d])) HB_FAIL(ctx, "hb_expander_set: bad D graph (target >= R or weight >= 2^32)");
     ex.n_edges = edges.size();
     HB_CHECK(ctx, cudaMalloc(&ex.d_stages, ex.stages.size() * sizeof(EncStage)));
-    HB_CHECK(ctx, cudaMalloc(&ex.d_rowptr, rowptr.size() * sizeof(int)));
+    HB_CHECK(ctx, cudaMalloc(&ex.d_rowptr, rowptr.size() * sizeof(uint2)));
     HB_CHECK(ctx, cudaMalloc(&ex.d_edges, edges.size() * sizeof(uint2)));
     HB_CHECK(ctx, cudaMemcpy(ex.d_stages, ex.stages.data(), ex.stages.size() * sizeof(EncStage), cudaMemcpyHostToDevice));
-    HB_CHECK(ctx, cudaMemcpy(ex.d_rowptr, rowptr.data(), rowptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    HB_CHECK(ctx, cudaMemcpy(ex.d_rowptr, rowptr.data(), rowptr.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     HB_CHECK(ctx, cudaMemcpy(ex.d_edges, edges.data(), edges.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     return 0;
 }

@@ -83,6 +83,52 @@ def test_encode(ctx, chk, n):
         assert np.array_equal(got[:, c], want), (n, c)
 
 
+def _encode_bigint(graphs, x, dep=0):
+    """encode_monolithic restated on Python integers (linear_code_encode.h:62-119): enc_d(x) = x | enc_{d+1}(C_d x) | D_d enc_{d+1}(C_d x)."""
+    if (0, dep) not in graphs:
+        return list(x)
+
+    def spmv(g, v):
+        L, R, deg, nbr, w = g
+        assert len(v) == L
+        out = [[0, 0] for _ in range(R)]
+        for i in range(L):
+            for j in range(deg):
+                t, wt = int(nbr[i * deg + j]), int(w[i * deg + j])
+                out[t][0] = (out[t][0] + wt * v[i][0]) % P61
+                out[t][1] = (out[t][1] + wt * v[i][1]) % P61
+        return out
+    z = _encode_bigint(graphs, spmv(graphs[(0, dep)], x), dep + 1)
+    return list(x) + z + spmv(graphs[(1, dep)], z)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_encode_weight_paths(ctx, chk, wide):
+    """Both accumulation paths of the encode kernel against a big-integer restatement: weights < 2^31 (four edges summed on the IMAD.WIDE
+    addend) and a graph with weights >= 2^31 (one edge at a time), limbs at the edges of the field included."""
+    n, ncols = 256, 8
+    srand(7)
+    chk.expander_init_store(n)
+    graphs = chk.expander_graphs(n)
+    rng = np.random.default_rng(11)
+    if wide:
+        graphs = {k: (L, R, deg, nbr, (w | (rng.integers(0, 2, len(w), dtype=np.uint64) << np.uint64(31)))) for k, (L, R, deg, nbr, w) in graphs.items()}
+        assert any((g[4] >> np.uint64(31)).any() for g in graphs.values())
+    else:
+        graphs = {k: (L, R, deg, nbr, np.where(rng.integers(0, 4, len(w)) == 0, np.uint64((1 << 31) - 1), w)) for k, (L, R, deg, nbr, w) in graphs.items()}
+    cw = ctx.expander_set(n, graphs)
+    x = rand_field(rng, n * ncols).reshape(n, ncols, 2)
+    x[:3, 0] = [[P61 - 1, P61 - 1], [0, P61 - 1], [P61 - 1, 0]]
+    x[:, 1] = P61 - 1                                            # every limb maximal: the tightest case for the 64-bit partial sums
+    got = ctx.encode(np.ascontiguousarray(x.reshape(-1, 2)), n, ncols).reshape(2 * n, ncols, 2)
+    for c in (0, 1, 5):
+        want = _encode_bigint(graphs, [[int(v[0]), int(v[1])] for v in x[:, c]])
+        assert len(want) == cw
+        assert np.array_equal(got[:cw, c], np.array(want, dtype=np.uint64)), (wide, c)
+        assert not got[cw:, c].any()
+    install_expander(ctx, chk, n)                                # leave a reference graph installed
+
+
 def test_hashes(ctx, chk):
     rng = np.random.default_rng(3)
     s = rng.integers(0, 256, (1000, 64), dtype=np.uint8)
