@@ -341,7 +341,7 @@ def main():
     coeffs_per_launch = float(N) * psteps / rec["launches"]
     # algorithmic bytes per coefficient: encode = read the RS-encoded rows (32 B) + write the parity rows / zero tail (32 B)
     # + write the inner leaf digest (32 B); NTT = 16 B in + 32 B out; chain = 32 B of inner digests
-    alg_bytes = {"encode_cols_kernel": 96.0, "ntt_tile_kernel": 48.0, "md_chain_kernel": 32.0}.get(name, 64.0) * coeffs_per_launch
+    alg_bytes = {"encode_cols_kernel": 96.0, "ntt_tile_kernel": 48.0, "ntt_tile_lazy_kernel": 48.0, "md_chain_kernel": 32.0}.get(name, 64.0) * coeffs_per_launch
     peak, how = peaks()
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
     counts = {}

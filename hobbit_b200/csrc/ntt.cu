@@ -184,6 +184,149 @@ ntt_tile_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_s
     for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) out[base + i] = s[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Lazy-reduction variant of the tile kernel (HB_NTT_LAZY, the default).  The tile kernel is bound by the ALU pipe, and more than half of its
+// ALU work was canonicalisation: every fadd / fsub / fmul ended in a compare-subtract-select.  Here values inside a pass are only kept
+// CONGRUENT mod p and below 2^64; the bounds (p = 2^61 - 1, so 8p = 2^64 - 8):
+//   * shared memory holds "folded" limbs, <= p + 7 (fold61 of any 64-bit value); global input is canonical; the final store canonicalises;
+//   * products are fmul_n_lazy (left limbs <= p + 7, canonical twiddle) -> <= p + 7;  x * 2^30 of any 64-bit x is (x >> 31) + ((x & (2^31-1)) << 30)
+//     <= 2^61 + 2^33;  so every input of an 8-point butterfly is <= B0 := p + 2^34;
+//   * a + b is a plain 64-bit addition; a - b is a + (K p - b) with K p >= the bound of b; multiplying by +-i swaps the limbs and turns one
+//     of the two subtractions around (no negation);
+//   * layer 1 of the butterfly: sums <= 2 B0, differences (K = 2) <= B0 + 2p, both <= U1 := 3p + 2^35;
+//     layer 2: sums <= 2 U1, differences (K = 4) <= U1 + 4p < 8p; the two values that go through W8 are folded first (W8 adds both limbs);
+//     before layer 3 everything is folded (<= p + 7, W8 outputs <= 2^61 + 2^33): sums <= 2 B0, differences (K = 2) <= 3p + 2^35; one more
+//     fold per output.  16 folds (8 instructions each) + 24 additions (4 each) per 8 points instead of 24 canonical additions (12 - 16 each)
+//     and 7 canonical products.
+// The arithmetic is exact, so the canonical result is bit-identical to the canonical path (and to the reference's _fft).
+__device__ __forceinline__ F ladd(F a, F b) { return mkF(a.re + b.re, a.im + b.im); }
+template <int K> __device__ __forceinline__ u64 lsub1(u64 a, u64 b) { return a + ((u64)K * P61 - b); }             // requires b <= K p
+template <int K> __device__ __forceinline__ F lsub(F a, F b) { return mkF(lsub1<K>(a.re, b.re), lsub1<K>(a.im, b.im)); }
+// (a - b) * (+i) = (b.im - a.im, a.re - b.re);  (a - b) * (-i) = (a.im - b.im, b.re - a.re)
+template <int K, bool JNEG> __device__ __forceinline__ F lsub_j(F a, F b) {
+    return JNEG ? mkF(lsub1<K>(a.im, b.im), lsub1<K>(b.re, a.re)) : mkF(lsub1<K>(b.im, a.im), lsub1<K>(a.re, b.re));
+}
+// x * (+-i) for a CANONICAL x: p - limb is in [1, p] (congruent to the negated limb, 0 -> p)
+template <bool JNEG> __device__ __forceinline__ F lmul_j(F x) { return JNEG ? mkF(x.im, P61 - x.re) : mkF(P61 - x.im, x.re); }
+__device__ __forceinline__ u64 lrot30(u64 x) { return (x >> 31) + ((x & 0x7fffffffull) << 30); }                 // == 2^30 x (mod p), <= 2^61 + 2^33
+// x * omega^(len/8) = 2^30 (sr + si i) x for FOLDED x (limbs <= p + 7); W8F bit 0: sr negative, bit 1: si negative
+template <unsigned W8F> __device__ __forceinline__ F lmul_w8(F x) {
+    const u64 apb = x.re + x.im, amb = lsub1<2>(x.re, x.im), bma = lsub1<2>(x.im, x.re), napb = 4 * P61 - apb;     // apb <= 2p + 14 <= 4p
+    u64 re, im;
+    if (W8F == 0) { re = amb; im = apb; }
+    else if (W8F == 2) { re = apb; im = bma; }
+    else if (W8F == 1) { re = napb; im = amb; }
+    else { re = bma; im = napb; }
+    return mkF(lrot30(re), lrot30(im));
+}
+// 8-point butterfly, inputs <= B0 per limb, outputs folded (<= p + 7)
+template <unsigned W8F> __device__ __forceinline__ void dft8_lazy(F *x) {
+    constexpr bool JN = ((W8F & 1) != ((W8F >> 1) & 1));          // omega^(len/4) = (omega^(len/8))^2 = sr si i
+    const F a0 = ladd(x[0], x[1]), a1 = lsub<2>(x[0], x[1]), a2 = ladd(x[2], x[3]), a3 = lsub_j<2, JN>(x[2], x[3]);
+    const F a4 = ladd(x[4], x[5]), a5 = lsub<2>(x[4], x[5]), a6 = ladd(x[6], x[7]), a7 = lsub_j<2, JN>(x[6], x[7]);
+    const F b0 = lfold(ladd(a0, a2)), b2 = lfold(lsub<4>(a0, a2)), b1 = lfold(ladd(a1, a3)), b3 = lfold(lsub<4>(a1, a3));
+    const F b4 = lfold(ladd(a4, a6)), b6 = lfold(lsub_j<4, JN>(a4, a6));
+    const F b5 = lmul_w8<W8F>(lfold(ladd(a5, a7))), b7 = lmul_w8<W8F>(lfold(lsub_j<4, JN>(a5, a7)));
+    x[0] = lfold(ladd(b0, b4)); x[4] = lfold(lsub<2>(b0, b4)); x[1] = lfold(ladd(b1, b5)); x[5] = lfold(lsub<2>(b1, b5));
+    x[2] = lfold(ladd(b2, b6)); x[6] = lfold(lsub<2>(b2, b6)); x[3] = lfold(ladd(b3, b7)); x[7] = lfold(lsub<2>(b3, b7));
+}
+__device__ __forceinline__ F lmul_tw(F x, const F *tw) { return fmul_n_lazy(x, fprep(ldgF(tw))); }                 // x folded, twiddle canonical
+
+template <unsigned W8F>
+__global__ void __launch_bounds__(512, 2)
+ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_stride, size_t in_len,
+                     F *__restrict__ dst, size_t dst_stride, size_t dst_chunk_stride, unsigned rows_per_chunk,
+                     int logn, int lb, const F *__restrict__ tw) {
+    constexpr bool JN = ((W8F & 1) != ((W8F >> 1) & 1));
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F *s = reinterpret_cast<F *>(smem_raw);
+    const unsigned tiles_per_row = 1u << (logn - lb);
+    const size_t row = blockIdx.x / tiles_per_row;
+    const unsigned tile = blockIdx.x % tiles_per_row;
+    const unsigned tlen = 1u << lb, base = tile << lb;
+    const size_t chunk = row / rows_per_chunk, rr = row % rows_per_chunk;
+    const F *in = src + chunk * src_chunk_stride + rr * src_stride;
+    F *out = dst + chunk * dst_chunk_stride + rr * dst_stride;
+    const unsigned len = 1u << logn;
+
+    int st = 1;
+    if (in_len * 2 == len && lb >= 4) {
+        const unsigned ngroups = tlen >> 4, e = len >> 4;
+        for (unsigned u = threadIdx.x; u < 2 * ngroups; u += blockDim.x) {     // k = u / ngroups: uniform per warp for tiles of >= 512 positions
+            const unsigned g = u % ngroups, k = u / ngroups;
+            F x[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = in[__brev(base + 16 * g + 2 * m) >> (32 - logn)];      // canonical
+            if (k) {
+                x[1] = lmul_j<JN>(x[1]); x[2] = lmul_w8<W8F>(x[2]); x[3] = lmul_w8<W8F>(lmul_j<JN>(x[3]));       // canonical inputs: limbs stay <= p
+                x[4] = lmul_tw(x[4], &tw[e]); x[5] = lmul_tw(x[5], &tw[5 * e]); x[6] = lmul_tw(x[6], &tw[3 * e]); x[7] = lmul_tw(x[7], &tw[7 * e]);
+            }
+            dft8_lazy<W8F>(x);
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[16 * g + 2 * m + k] = x[m];
+        }
+        st = 5;
+    } else if (in_len * 2 == len && lb >= 1) {
+        for (unsigned i = threadIdx.x; i < (tlen >> 1); i += blockDim.x) {
+            unsigned p = base + 2 * i;
+            F v = in[__brev(p) >> (32 - logn)];
+            s[2 * i] = v; s[2 * i + 1] = v;
+        }
+        st = 2;
+    } else {
+        for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) {
+            unsigned q = __brev(base + i) >> (32 - logn);
+            s[i] = (q < in_len) ? in[q] : mkF(0, 0);
+        }
+    }
+    __syncthreads();
+    for (; st + 2 <= lb; st += 3) {                       // radix-8 pass: stages st, st+1, st+2
+        const unsigned h = 1u << (st - 1);
+        const unsigned tws3 = len >> (st + 2);            // twiddle stride of stage st+2
+        for (unsigned q = threadIdx.x; q < (tlen >> 3); q += blockDim.x) {
+            const unsigned k = q & (h - 1);
+            const unsigned p0 = ((q >> (st - 1)) << (st + 2)) + k;
+            const size_t e = (size_t)tws3 * k;
+            F x[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = s[p0 + m * h];
+            x[1] = lmul_tw(x[1], &tw[4 * e]); x[2] = lmul_tw(x[2], &tw[2 * e]); x[3] = lmul_tw(x[3], &tw[6 * e]);
+            x[4] = lmul_tw(x[4], &tw[e]); x[5] = lmul_tw(x[5], &tw[5 * e]); x[6] = lmul_tw(x[6], &tw[3 * e]); x[7] = lmul_tw(x[7], &tw[7 * e]);
+            dft8_lazy<W8F>(x);
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[p0 + m * h] = x[m];
+        }
+        __syncthreads();
+    }
+    if (st + 1 <= lb) {                                   // radix-4 pass: stages st and st+1
+        const unsigned h = 1u << (st - 1);
+        const unsigned tws2 = len >> (st + 1);            // twiddle stride of stage st+1; stage st uses 2*tws2
+        for (unsigned q = threadIdx.x; q < (tlen >> 2); q += blockDim.x) {
+            unsigned k = q & (h - 1);
+            unsigned p0 = ((q >> (st - 1)) << (st + 1)) + k;
+            const F x0 = s[p0], x1 = s[p0 + h], x2 = s[p0 + 2 * h], x3 = s[p0 + 3 * h];
+            size_t e = (size_t)tws2 * k;
+            const F X1 = lmul_tw(x1, &tw[2 * e]), X2 = lmul_tw(x2, &tw[e]), X3 = lmul_tw(x3, &tw[3 * e]);       // <= p + 7
+            const F a0 = ladd(x0, X1), a1 = lsub<2>(x0, X1), b = ladd(X2, X3), c = lsub_j<2, JN>(X2, X3);       // <= 3p + 14
+            s[p0] = lfold(ladd(a0, b)); s[p0 + 2 * h] = lfold(lsub<4>(a0, b));
+            s[p0 + h] = lfold(ladd(a1, c)); s[p0 + 3 * h] = lfold(lsub<4>(a1, c));
+        }
+        __syncthreads();
+        st += 2;
+    }
+    if (st <= lb) {                                       // one radix-2 stage left
+        const unsigned half = 1u << (st - 1), tws = len >> st;
+        for (unsigned b = threadIdx.x; b < (tlen >> 1); b += blockDim.x) {
+            unsigned k = b & (half - 1);
+            unsigned p0 = ((b >> (st - 1)) << st) + k, p1 = p0 + half;
+            const F u = s[p0], v = lmul_tw(s[p1], &tw[(size_t)tws * k]);
+            s[p0] = lfold(ladd(u, v)); s[p1] = lfold(lsub<2>(u, v));
+        }
+        __syncthreads();
+    }
+    for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) out[base + i] = fcanon(s[i]);       // folded (<= p + 7) -> canonical
+}
+
 // Register-resident radix-2^CNT pass over global memory: stages s_lo+1 .. s_lo+CNT of a length-2^logn transform.
 template <int CNT>
 __global__ void __launch_bounds__(256)
@@ -250,6 +393,27 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
     if (threads < 32) threads = 32;
     size_t grid = batch << (logn - lb);
     if (rows_per_chunk != batch && lb != logn) HB_FAIL(ctx, "ntt: chunked launch supports transforms up to one tile");
+#ifndef HB_NTT_LAZY
+#define HB_NTT_LAZY 1
+#endif
+    static const int lazy_ok = getenv("HB_NTT_LAZY") ? atoi(getenv("HB_NTT_LAZY")) : HB_NTT_LAZY;      // experiment switch
+    // the lazy kernel is specialised on the 8th root (and derives +-i from it: (omega^(len/8))^2 = omega^(len/4)); lengths below 8 have no 8th root
+    const unsigned w8f = logn >= 3 ? (unsigned)ctx->tw_w8[logn] : (ctx->tw_j_neg[logn] ? 1u : 0u);
+    const bool jn_derived = ((w8f & 1) != ((w8f >> 1) & 1));
+    if (lazy_ok && (logn < 2 || jn_derived == ctx->tw_j_neg[logn])) {
+        static bool lazy_attr_dev[64] = {};
+        if (!lazy_attr_dev[ctx->device & 63]) {
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+            lazy_attr_dev[ctx->device & 63] = true;
+        }
+#define HB_NTT_LAZY_LAUNCH(W) HB_LAUNCH(ctx, ntt_tile_lazy_kernel<W>, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, \
+                                       dst_chunk_stride, (unsigned)rows_per_chunk, logn, lb, tw)
+        if (w8f == 0) { HB_NTT_LAZY_LAUNCH(0); } else if (w8f == 1) { HB_NTT_LAZY_LAUNCH(1); } else if (w8f == 2) { HB_NTT_LAZY_LAUNCH(2); } else { HB_NTT_LAZY_LAUNCH(3); }
+#undef HB_NTT_LAZY_LAUNCH
+    } else
     HB_LAUNCH(ctx, ntt_tile_kernel, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, dst_chunk_stride,
               (unsigned)rows_per_chunk, logn, lb, tw, ctx->tw_j_neg[logn], (unsigned)ctx->tw_w8[logn]);
     int s_lo = lb;
