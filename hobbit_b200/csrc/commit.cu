@@ -325,6 +325,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &t : ctx->tw) if (t) cudaFree(t);
+    for (auto &t : ctx->tw_pass) if (t) cudaFree(t);
     if (ctx->exp.d_stages) { cudaFree(ctx->exp.d_stages); cudaFree(ctx->exp.d_rowptr); cudaFree(ctx->exp.d_edges); }
     if (ctx->tensor) cudaFree(ctx->tensor);
     if (ctx->poly) cudaFree(ctx->poly);

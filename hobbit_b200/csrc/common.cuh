@@ -164,6 +164,7 @@ struct hb_ctx {
     int sm_count = 148;                 // overwritten from cudaDeviceProp in hb_ctx_create; grids of grid-stride kernels are multiples of it
     // twiddle tables w[k] = omega_len^k, k < len/2, cached per log2(len)
     hb::F *tw[32] = {};
+    hb::F *tw_pass[32] = {};            // per-pass twiddle tables of the tile kernel (ntt.cu: pass_tables), lane-contiguous
     bool tw_j_neg[32] = {};             // omega_len^(len/4) == -i (else +i)
     uint8_t tw_w8[32] = {};             // omega_len^(len/8) = 2^30 (+-1 +- i): bit 0 = real part negative, bit 1 = imaginary part negative
     hb::ExpanderDev exp;

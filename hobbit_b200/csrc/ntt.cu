@@ -234,11 +234,48 @@ __device__ __forceinline__ F lmul_tw(F x, const F *tw) { return fmul_n_lazy(x, f
 // (Measured and not kept: reading the twiddles as PREPARED operands — limbs already split, doubled and negated, 32 bytes each — saves fprep's nine
 // instructions per product but doubles the twiddle loads: step 11.29 vs 10.52 ms.)
 
+// Per-pass twiddle tables.  A pass at stage st (h = 2^(st-1) butterflies apart) multiplies input j of butterfly k by omega^(mult_j * stride * k):
+// read from the full-period table that is a different stride per input and 32 scattered sectors per warp request (ncu, round 2: the L1
+// data pipe of the tile kernel was as busy as the ALU pipe, 61 %, two thirds of it these loads and the bit-reversed input gather).  The
+// tables below hold, for every stage st <= 12 of one transform length, the factors of a radix-8 pass (7 per butterfly), of a radix-4 pass (3)
+// and of a radix-2 pass (1) as [input j][k], so that the lanes of a warp (consecutive k) read consecutive 16-byte entries.
+//   layout: [radix-8: 7 (2^12 - 1)] [radix-4: 3 (2^12 - 1)] [radix-2: 2^12 - 1], the block of stage st at offset R (2^(st-1) - 1)
+static constexpr size_t kPassR8 = 0, kPassR4 = 7 * (((size_t)1 << kLogTile) - 1), kPassR2 = kPassR4 + 3 * (((size_t)1 << kLogTile) - 1),
+                        kPassTotal = kPassR2 + (((size_t)1 << kLogTile) - 1);
+__global__ void __launch_bounds__(256) pass_table_kernel(const F *__restrict__ tw, F *__restrict__ out, int logn, int lb) {
+    const unsigned len = 1u << logn;
+    for (int st = 1; st <= lb; st++) {
+        const unsigned h = 1u << (st - 1);
+        for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < h; k += gridDim.x * blockDim.x) {
+            if (st + 2 <= lb) {
+                const size_t e = (size_t)(len >> (st + 2)) * k;
+                const unsigned mult[7] = {4, 2, 6, 1, 5, 3, 7};
+                for (int j = 0; j < 7; j++) out[kPassR8 + 7 * (size_t)(h - 1) + (size_t)j * h + k] = tw[mult[j] * e];
+            }
+            if (st + 1 <= lb) {
+                const size_t e = (size_t)(len >> (st + 1)) * k;
+                const unsigned mult[3] = {2, 1, 3};
+                for (int j = 0; j < 3; j++) out[kPassR4 + 3 * (size_t)(h - 1) + (size_t)j * h + k] = tw[mult[j] * e];
+            }
+            out[kPassR2 + (size_t)(h - 1) + k] = tw[(size_t)(len >> st) * k];
+        }
+    }
+}
+static int get_pass_tables(hb_ctx *ctx, int logn, int lb, const F *tw, const F **out) {
+    if (!ctx->tw_pass[logn]) {
+        HB_CHECK(ctx, cudaMalloc(&ctx->tw_pass[logn], kPassTotal * sizeof(F)));
+        HB_CHECK(ctx, cudaMemsetAsync(ctx->tw_pass[logn], 0, kPassTotal * sizeof(F), ctx->stream));
+        HB_LAUNCH(ctx, pass_table_kernel, 8, 256, 0, tw, ctx->tw_pass[logn], logn, lb);
+    }
+    *out = ctx->tw_pass[logn];
+    return 0;
+}
+
 template <unsigned W8F>
 __global__ void __launch_bounds__(512, 2)
 ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_chunk_stride, size_t in_len,
                      F *__restrict__ dst, size_t dst_stride, size_t dst_chunk_stride, unsigned rows_per_chunk,
-                     int logn, int lb, const F *__restrict__ tw) {
+                     int logn, int lb, const F *__restrict__ tw, const F *__restrict__ tp) {
     constexpr bool JN = ((W8F & 1) != ((W8F >> 1) & 1));
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *s = reinterpret_cast<F *>(smem_raw);
@@ -254,8 +291,11 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
     int st = 1;
     if (in_len * 2 == len && lb >= 4) {
         const unsigned ngroups = tlen >> 4, e = len >> 4;
+        const int lg = lb - 4;                                                  // log2(ngroups)
         for (unsigned u = threadIdx.x; u < 2 * ngroups; u += blockDim.x) {     // k = u / ngroups: uniform per warp for tiles of >= 512 positions
-            const unsigned g = u % ngroups, k = u / ngroups;
+            // thread -> group in bit-reversed order: the input index of (group g, input m) is brev(m) * 2^.. + brev(g) (+ the tile's bits), so
+            // consecutive threads gather consecutive input elements (4 wavefronts per warp request instead of 32)
+            const unsigned gu = u % ngroups, k = u / ngroups, g = lg ? (__brev(gu) >> (32 - lg)) : 0u;
             F x[8];
 #pragma unroll
             for (int m = 0; m < 8; m++) x[m] = in[__brev(base + 16 * g + 2 * m) >> (32 - logn)];      // canonical
@@ -284,16 +324,15 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
     __syncthreads();
     for (; st + 2 <= lb; st += 3) {                       // radix-8 pass: stages st, st+1, st+2
         const unsigned h = 1u << (st - 1);
-        const unsigned tws3 = len >> (st + 2);            // twiddle stride of stage st+2
         for (unsigned q = threadIdx.x; q < (tlen >> 3); q += blockDim.x) {
             const unsigned k = q & (h - 1);
             const unsigned p0 = ((q >> (st - 1)) << (st + 2)) + k;
-            const size_t e = (size_t)tws3 * k;
+            const F *t8 = tp + kPassR8 + 7 * (size_t)(h - 1) + k;            // [input j][k]: omega^({4,2,6,1,5,3,7}[j] * tws3 * k)
             F x[8];
 #pragma unroll
             for (int m = 0; m < 8; m++) x[m] = s[p0 + m * h];
-            x[1] = lmul_tw(x[1], &tw[4 * e]); x[2] = lmul_tw(x[2], &tw[2 * e]); x[3] = lmul_tw(x[3], &tw[6 * e]);
-            x[4] = lmul_tw(x[4], &tw[e]); x[5] = lmul_tw(x[5], &tw[5 * e]); x[6] = lmul_tw(x[6], &tw[3 * e]); x[7] = lmul_tw(x[7], &tw[7 * e]);
+#pragma unroll
+            for (int j = 0; j < 7; j++) x[j + 1] = lmul_tw(x[j + 1], &t8[(size_t)j * h]);
             dft8_lazy<W8F>(x);
 #pragma unroll
             for (int m = 0; m < 8; m++) s[p0 + m * h] = x[m];
@@ -302,13 +341,12 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
     }
     if (st + 1 <= lb) {                                   // radix-4 pass: stages st and st+1
         const unsigned h = 1u << (st - 1);
-        const unsigned tws2 = len >> (st + 1);            // twiddle stride of stage st+1; stage st uses 2*tws2
         for (unsigned q = threadIdx.x; q < (tlen >> 2); q += blockDim.x) {
             unsigned k = q & (h - 1);
             unsigned p0 = ((q >> (st - 1)) << (st + 1)) + k;
             const F x0 = s[p0], x1 = s[p0 + h], x2 = s[p0 + 2 * h], x3 = s[p0 + 3 * h];
-            size_t e = (size_t)tws2 * k;
-            const F X1 = lmul_tw(x1, &tw[2 * e]), X2 = lmul_tw(x2, &tw[e]), X3 = lmul_tw(x3, &tw[3 * e]);       // <= p + 7
+            const F *t4 = tp + kPassR4 + 3 * (size_t)(h - 1) + k;            // [j][k]: omega^({2,1,3}[j] * tws2 * k)
+            const F X1 = lmul_tw(x1, &t4[0]), X2 = lmul_tw(x2, &t4[h]), X3 = lmul_tw(x3, &t4[2 * (size_t)h]);      // <= p + 7
             const F a0 = ladd(x0, X1), a1 = lsub<2>(x0, X1), b = ladd(X2, X3), c = lsub_j<2, JN>(X2, X3);       // <= 3p + 14
             s[p0] = lfold(ladd(a0, b)); s[p0 + 2 * h] = lfold(lsub<4>(a0, b));
             s[p0 + h] = lfold(ladd(a1, c)); s[p0 + 3 * h] = lfold(lsub<4>(a1, c));
@@ -317,11 +355,11 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
         st += 2;
     }
     if (st <= lb) {                                       // one radix-2 stage left
-        const unsigned half = 1u << (st - 1), tws = len >> st;
+        const unsigned half = 1u << (st - 1);
         for (unsigned b = threadIdx.x; b < (tlen >> 1); b += blockDim.x) {
             unsigned k = b & (half - 1);
             unsigned p0 = ((b >> (st - 1)) << st) + k, p1 = p0 + half;
-            const F u = s[p0], v = lmul_tw(s[p1], &tw[(size_t)tws * k]);
+            const F u = s[p0], v = lmul_tw(s[p1], &tp[kPassR2 + (size_t)(half - 1) + k]);
             s[p0] = lfold(ladd(u, v)); s[p1] = lfold(lsub<2>(u, v));
         }
         __syncthreads();
@@ -411,8 +449,9 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
             HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
             lazy_attr_dev[ctx->device & 63] = true;
         }
+        const F *tp; HB_TRY(get_pass_tables(ctx, logn, lb, tw, &tp));
 #define HB_NTT_LAZY_LAUNCH(W) HB_LAUNCH(ctx, ntt_tile_lazy_kernel<W>, (unsigned)grid, threads, smem, src, src_stride, src_chunk_stride, in_len, dst, dst_stride, \
-                                       dst_chunk_stride, (unsigned)rows_per_chunk, logn, lb, tw)
+                                       dst_chunk_stride, (unsigned)rows_per_chunk, logn, lb, tw, tp)
         if (w8f == 0) { HB_NTT_LAZY_LAUNCH(0); } else if (w8f == 1) { HB_NTT_LAZY_LAUNCH(1); } else if (w8f == 2) { HB_NTT_LAZY_LAUNCH(2); } else { HB_NTT_LAZY_LAUNCH(3); }
 #undef HB_NTT_LAZY_LAUNCH
     } else
