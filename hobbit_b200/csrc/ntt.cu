@@ -279,6 +279,12 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
     constexpr bool JN = ((W8F & 1) != ((W8F >> 1) & 1));
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F *s = reinterpret_cast<F *>(smem_raw);
+    // Shared-memory index padding: with the bit-reversed thread order of the first pass the 8 lanes of a store phase differ in the TOP three
+    // bits of their position, all in one bank group; one extra 16-byte slot per 2^(lb-3) positions (7 slots in all) moves them to 8 different
+    // groups, and every later pass still reads aligned runs of 8 consecutive slots.  (Round 1 measured the padding alone at +1 %: the kernel was
+    // ALU-bound then.)
+    const int psh = lb >= 7 ? lb - 3 : 31;
+    auto P = [psh](unsigned i) { return i + (i >> psh); };
     const unsigned tiles_per_row = 1u << (logn - lb);
     const size_t row = blockIdx.x / tiles_per_row;
     const unsigned tile = blockIdx.x % tiles_per_row;
@@ -305,20 +311,20 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
             }
             dft8_lazy<W8F>(x);
 #pragma unroll
-            for (int m = 0; m < 8; m++) s[16 * g + 2 * m + k] = x[m];
+            for (int m = 0; m < 8; m++) s[P(16 * g + 2 * m + k)] = x[m];
         }
         st = 5;
     } else if (in_len * 2 == len && lb >= 1) {
         for (unsigned i = threadIdx.x; i < (tlen >> 1); i += blockDim.x) {
             unsigned p = base + 2 * i;
             F v = in[__brev(p) >> (32 - logn)];
-            s[2 * i] = v; s[2 * i + 1] = v;
+            s[P(2 * i)] = v; s[P(2 * i + 1)] = v;
         }
         st = 2;
     } else {
         for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) {
             unsigned q = __brev(base + i) >> (32 - logn);
-            s[i] = (q < in_len) ? in[q] : mkF(0, 0);
+            s[P(i)] = (q < in_len) ? in[q] : mkF(0, 0);
         }
     }
     __syncthreads();
@@ -330,12 +336,12 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
             const F *t8 = tp + kPassR8 + 7 * (size_t)(h - 1) + k;            // [input j][k]: omega^({4,2,6,1,5,3,7}[j] * tws3 * k)
             F x[8];
 #pragma unroll
-            for (int m = 0; m < 8; m++) x[m] = s[p0 + m * h];
+            for (int m = 0; m < 8; m++) x[m] = s[P(p0 + m * h)];
 #pragma unroll
             for (int j = 0; j < 7; j++) x[j + 1] = lmul_tw(x[j + 1], &t8[(size_t)j * h]);
             dft8_lazy<W8F>(x);
 #pragma unroll
-            for (int m = 0; m < 8; m++) s[p0 + m * h] = x[m];
+            for (int m = 0; m < 8; m++) s[P(p0 + m * h)] = x[m];
         }
         __syncthreads();
     }
@@ -344,12 +350,12 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
         for (unsigned q = threadIdx.x; q < (tlen >> 2); q += blockDim.x) {
             unsigned k = q & (h - 1);
             unsigned p0 = ((q >> (st - 1)) << (st + 1)) + k;
-            const F x0 = s[p0], x1 = s[p0 + h], x2 = s[p0 + 2 * h], x3 = s[p0 + 3 * h];
+            const F x0 = s[P(p0)], x1 = s[P(p0 + h)], x2 = s[P(p0 + 2 * h)], x3 = s[P(p0 + 3 * h)];
             const F *t4 = tp + kPassR4 + 3 * (size_t)(h - 1) + k;            // [j][k]: omega^({2,1,3}[j] * tws2 * k)
             const F X1 = lmul_tw(x1, &t4[0]), X2 = lmul_tw(x2, &t4[h]), X3 = lmul_tw(x3, &t4[2 * (size_t)h]);      // <= p + 7
             const F a0 = ladd(x0, X1), a1 = lsub<2>(x0, X1), b = ladd(X2, X3), c = lsub_j<2, JN>(X2, X3);       // <= 3p + 14
-            s[p0] = lfold(ladd(a0, b)); s[p0 + 2 * h] = lfold(lsub<4>(a0, b));
-            s[p0 + h] = lfold(ladd(a1, c)); s[p0 + 3 * h] = lfold(lsub<4>(a1, c));
+            s[P(p0)] = lfold(ladd(a0, b)); s[P(p0 + 2 * h)] = lfold(lsub<4>(a0, b));
+            s[P(p0 + h)] = lfold(ladd(a1, c)); s[P(p0 + 3 * h)] = lfold(lsub<4>(a1, c));
         }
         __syncthreads();
         st += 2;
@@ -359,12 +365,12 @@ ntt_tile_lazy_kernel(const F *__restrict__ src, size_t src_stride, size_t src_ch
         for (unsigned b = threadIdx.x; b < (tlen >> 1); b += blockDim.x) {
             unsigned k = b & (half - 1);
             unsigned p0 = ((b >> (st - 1)) << st) + k, p1 = p0 + half;
-            const F u = s[p0], v = lmul_tw(s[p1], &tp[kPassR2 + (size_t)(half - 1) + k]);
-            s[p0] = lfold(ladd(u, v)); s[p1] = lfold(lsub<2>(u, v));
+            const F u = s[P(p0)], v = lmul_tw(s[P(p1)], &tp[kPassR2 + (size_t)(half - 1) + k]);
+            s[P(p0)] = lfold(ladd(u, v)); s[P(p1)] = lfold(lsub<2>(u, v));
         }
         __syncthreads();
     }
-    for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) out[base + i] = fcanon(s[i]);       // folded (<= p + 7) -> canonical
+    for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) out[base + i] = fcanon(s[P(i)]);       // folded (<= p + 7) -> canonical
 }
 
 // Register-resident radix-2^CNT pass over global memory: stages s_lo+1 .. s_lo+CNT of a length-2^logn transform.
@@ -421,11 +427,11 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
     const F *tw; HB_TRY(get_twiddles(ctx, logn, &tw));
     const int lb = logn < kLogTile ? logn : kLogTile;
     if (src == dst && lb != logn) HB_FAIL(ctx, "ntt: in-place transform longer than one tile needs a distinct source");
-    const size_t smem = sizeof(F) << lb;
+    const size_t smem = (sizeof(F) << lb) + 8 * sizeof(F);         // + the 7 padding slots of the lazy tile kernel
     static bool attr_set_dev[64] = {};                        // the attribute is per device
     bool &attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
-        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+        HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(F) << kLogTile) + 8 * sizeof(F))));
         attr_set = true;
     }
     unsigned threads = 1u << (lb > 3 ? lb - 3 : 0);          // one radix-8 butterfly per thread up to 512 threads
@@ -443,10 +449,10 @@ static int ntt_rows_impl(hb_ctx *ctx, const F *src, size_t src_stride, size_t in
     if (lazy_ok && (logn < 2 || jn_derived == ctx->tw_j_neg[logn])) {
         static bool lazy_attr_dev[64] = {};
         if (!lazy_attr_dev[ctx->device & 63]) {
-            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
-            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
-            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
-            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << kLogTile)));
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(F) << kLogTile) + 8 * sizeof(F))));
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(F) << kLogTile) + 8 * sizeof(F))));
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(F) << kLogTile) + 8 * sizeof(F))));
+            HB_CHECK(ctx, cudaFuncSetAttribute(ntt_tile_lazy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(F) << kLogTile) + 8 * sizeof(F))));
             lazy_attr_dev[ctx->device & 63] = true;
         }
         const F *tp; HB_TRY(get_pass_tables(ctx, logn, lb, tw, &tp));
