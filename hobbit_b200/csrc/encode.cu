@@ -64,6 +64,11 @@ __device__ __forceinline__ uint2 ld_edge(const uint2 *p) {
     asm("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ld_edge2(const uint2 *p) {            // two consecutive edge records, p 16-byte aligned
+    uint4 v;
+    asm("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ int ld_rowptr(const uint2 *p) { int v; asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }   // .x only
 
 // grid: (cols / CB, nchunks).  inner != nullptr: also emit the inner leaf digests H1(T[4j][k] | .. | T[4j+3][k])
@@ -135,6 +140,17 @@ encode_cols_kernel(F *__restrict__ Tbase, size_t chunk_stride, size_t cols, int 
 #endif
     constexpr int kMac4Unroll = HB_ENC_MAC4_UNROLL;
     auto mac4_run = [&](Acc &are, Acc &aim, int &e, int e1, int step) {
+        if (step == 1) {
+            // whole rows: lists start at even indices (hb_expander_set), two records per 16-byte load
+#pragma unroll kMac4Unroll
+            for (; e + 3 < e1; e += 4) {
+                const uint4 q0 = ld_edge2(&edges[e]), q1 = ld_edge2(&edges[e + 2]);
+                const F x0 = cw[q0.x * CB + c], x1 = cw[q0.z * CB + c], x2 = cw[q1.x * CB + c], x3 = cw[q1.z * CB + c];
+                acc_mac4(are, x0.re, x1.re, x2.re, x3.re, q0.y, q0.w, q1.y, q1.w);
+                acc_mac4(aim, x0.im, x1.im, x2.im, x3.im, q0.y, q0.w, q1.y, q1.w);
+            }
+            return;
+        }
 #pragma unroll kMac4Unroll
         for (; e + 3 * step < e1; e += 4 * step) {
             const uint2 a0 = ld_edge(&edges[e]), a1 = ld_edge(&edges[e + step]), a2 = ld_edge(&edges[e + 2 * step]), a3 = ld_edge(&edges[e + 3 * step]);
@@ -427,9 +443,11 @@ extern "C" int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, 
         }
         std::vector<int> target_at(R), start(R + 1, 0);
         for (long long t = 0; t < R; t++) target_at[pos_of[t]] = (int)t;
-        for (long long v = 0; v < R; v++) start[v + 1] = start[v] + cnt[target_at[v] + 1];
-        size_t ebase = edges.size();
-        edges.resize(ebase + (size_t)L * deg);
+        // every edge list holds an even number of records (one zero-weight record appended where needed) and starts at an even index, so
+        // that the kernel fetches two records per 16-byte load: half the L1 wavefronts of the edge loads
+        for (long long v = 0; v < R; v++) start[v + 1] = start[v] + ((cnt[target_at[v] + 1] + 1) & ~1);
+        size_t ebase = edges.size();                                   // even: every stage appends an even number of records
+        edges.resize(ebase + (size_t)start[R], make_uint2((unsigned)in_off, 0u));
         std::vector<int> fill(start.begin(), start.end() - 1);
         for (long long i = 0; i < L; i++)
             for (int j = 0; j < deg; j++) {
