@@ -232,7 +232,8 @@ template <unsigned W8F> __device__ __forceinline__ void dft8_lazy(F *x) {
 }
 __device__ __forceinline__ F lmul_tw(F x, const F *tw) { return fmul_n_lazy(x, fprep(ldgF(tw))); }                 // x folded, twiddle canonical
 // (Measured and not kept: reading the twiddles as PREPARED operands — limbs already split, doubled and negated, 32 bytes each — saves fprep's nine
-// instructions per product but doubles the twiddle loads: step 11.29 vs 10.52 ms.)
+// instructions per product but doubles the twiddle loads: step 11.29 vs 10.52 ms from the strided full-period table, 9.72 vs 9.72 ms as two
+// lane-contiguous planes next to the per-pass tables.)
 
 // Per-pass twiddle tables.  A pass at stage st (h = 2^(st-1) butterflies apart) multiplies input j of butterfly k by omega^(mult_j * stride * k):
 // read from the full-period table that is a different stride per input and 32 scattered sectors per warp request (ncu, round 2: the L1
