@@ -49,11 +49,14 @@ __device__ __forceinline__ void acc_mac4(Acc &a, u64 x0, u64 x1, u64 x2, u64 x3,
 #ifndef HB_ENC_MAC4
 #define HB_ENC_MAC4 1
 #endif
+// value = U + V 2^32 is put together as ONE 128-bit number (three additions with carry) and reduced once: its upper half is below
+// 2^29 x (number of terms), inside red128's 2^58 for any in-degree below 2^29 (hb_expander_set checks it).  Two reductions, a rotation and a
+// modular addition before: ~100 instructions per row and both limbs, a third of the work of a 12-edge row of the D stages; now ~40.
 __device__ __forceinline__ u64 acc_reduce(const Acc &a) {
-    u64 u = red128(((u64)a.u1 << 32) | a.u0, a.u2);
-    u64 v = red128(((u64)a.v1 << 32) | a.v0, a.v2);
-    v = ((v << 32) & P61) | (v >> 29);                   // v * 2^32 mod p: rotate left by 32 inside 61 bits
-    return add61(u, v);
+    uint32_t s1, s2, s3;
+    asm("add.cc.u32 %0, %3, %4;\n\taddc.cc.u32 %1, %5, %6;\n\taddc.u32 %2, %7, 0;"
+        : "=r"(s1), "=r"(s2), "=r"(s3) : "r"(a.u1), "r"(a.v0), "r"(a.u2), "r"(a.v1), "r"(a.v2));
+    return red128(((u64)s1 << 32) | a.u0, ((u64)s3 << 32) | s2);
 }
 
 // Edge and row-pointer loads: read-only path, L1 evict-last.  One SM runs dozens of CTAs per launch and every CTA walks the same graph;
@@ -466,6 +469,7 @@ extern "C" int hb_expander_set(hb_ctx *ctx, long long n, int levels, int deg_C, 
         if (add_stage(off[d], nd[d], off[d + 1], R_C[d], deg_C, nbr_C[d], w_C[d])) HB_FAIL(ctx, "hb_expander_set: bad C graph (target >= R or weight >= 2^32)");
     for (int d = levels - 1; d >= 0; d--)
         if (add_stage(off[d + 1], lenc[d + 1], off[d + 1] + lenc[d + 1], R_D[d], deg_D, nbr_D[d], w_D[d])) HB_FAIL(ctx, "hb_expander_set: bad D graph (target >= R or weight >= 2^32)");
+    if (ex.max_indeg >= (1 << 29)) HB_FAIL(ctx, "hb_expander_set: in-degree above 2^29 (headroom of the 128-bit row accumulators)");
     ex.n_edges = edges.size();
     HB_CHECK(ctx, cudaMalloc(&ex.d_stages, ex.stages.size() * sizeof(EncStage)));
     HB_CHECK(ctx, cudaMalloc(&ex.d_rowptr, rowptr.size() * sizeof(uint2)));
