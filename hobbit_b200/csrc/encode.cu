@@ -6,10 +6,11 @@
 // each stage reads an already-final segment of the codeword and writes a disjoint later segment.
 //
 // B200 mapping: all columns share one graph, so a CTA takes CB adjacent columns and keeps their whole codewords
-// in shared memory as cw[row][CB] (n=1024: 1761 rows x 8 columns x 16 B = 220 KB, one CTA per SM).  A thread owns
-// (target row, column); each stage is a GATHER over the target's in-edges (CSR by target, built on the host from
-// the reference's scatter lists) so there are no atomics, and the 61x32-bit products are accumulated in 128 bits
-// and reduced once per target.  A quarter-warp reads one contiguous 16*CB-byte row -> conflict-free LDS.128.
+// in shared memory as cw[row][CB] (n=1024: 1761 rows x 4 columns x 16 B = 110 KB, two CTAs of 512 threads per SM; 8 columns /
+// 220 KB / one CTA where two do not fit).  A thread owns (row, column); each stage is a GATHER over the row's in-edges (CSR by
+// target, built on the host from the reference's scatter lists, rows in order of in-degree) so there are no atomics, and the
+// 61x32-bit products are accumulated in 128 bits and reduced once per row.  The lanes of a row read one contiguous 16*CB-byte
+// segment (LDS.128); with 4 columns two rows share a wavefront and the host orders the edges so that their sources differ in parity.
 // The weights are 31-bit reals (expanders.h:37 `F weight = random()`), so F x weight is two 61x32 products.
 // The inner half of the commit_standard leaf hashing (Our_PC.cpp:160-166; H1 of each 4-row quad of a column) is fused
 // here: the CTA already holds every row of its columns, so the quads are hashed straight out of shared memory and the
@@ -24,7 +25,8 @@ namespace hb {
 
 // Sum of 61-bit x 32-bit products without carry chains through compares: the two 64-bit partial products
 // p0 = x.lo32 * w and p1 = x.hi32 * w (IMAD.WIDE, FMA pipe) are accumulated in two independent 96-bit accumulators
-// with add.cc/addc (3 IADD3 each, ALU pipe); value = U + V * 2^32.  Headroom: 2^32 terms.
+// with add.cc/addc (3 IADD3 each, ALU pipe); value = U + V * 2^32.  Headroom: 2^29 terms (acc_reduce).  This is the one-edge form
+// (tail of a row, graphs with weights >= 2^31); acc_mac4 below is the hot one.
 struct Acc { uint32_t u0, u1, u2, v0, v1, v2; };
 __device__ __forceinline__ void acc_mac(Acc &a, u64 x, uint32_t w) {
     u64 p0 = (u64)(uint32_t)x * w, p1 = (u64)(uint32_t)(x >> 32) * w;
