@@ -5,7 +5,7 @@
 // Field arithmetic is exact and canonical, so the stage order/grouping below is free to differ.
 //
 // B200 mapping: one CTA owns up to 4096 consecutive (bit-reversed) positions of one row in shared memory
-// (64 KB -> 3 CTAs/SM) and runs the first 12 stages there; longer transforms finish with register-resident
+// (64 KB, 64 registers -> 2 CTAs/SM) and runs the first 12 stages there (ntt_tile_lazy_kernel: lazy reduction, per-pass twiddle tables); longer transforms finish with register-resident
 // radix-2^k passes over global memory (coalesced: consecutive threads own consecutive low index bits).
 // The zero-extension of the message rows (the RS encoding evaluates a degree < len/2 polynomial on len points)
 // is fused into the load, so the tensor's upper half is never memset nor read.

@@ -45,9 +45,11 @@ __device__ __forceinline__ F fold1n(F x, F d, const FN &rn) {
 //           A = x1 x2, B = y1 y2, C = d1 d2 give (2x1-y1)(2x2-y2) = 2A + 2C - B for free)
 // The sums over all pairs are linear in these, so the coefficients (a, b, c[, d]) the reference accumulates directly are recovered
 // exactly on the host from the reduced sums (coeffs_from_evals); all arithmetic is exact in F_p^2, so the bits are the same.
-// Products are LAZY (limbs <= p + 7, fmul_n_lazy) and so are the accumulators (raw 64-bit sums, the caller folds them every few pairs):
-// the FMA-heavy pipe (IMAD.WIDE) is the binding unit of this kernel and canonicalising intermediates would only add ALU work.
-// accumulators either in registers or — to free 12-16 registers for a third resident CTA — in a thread-private shared-memory column
+// Products are LAZY (limbs <= p + 7, fmul_n_lazy) and so are the accumulators: the two integer pipes are the binding units of this
+// kernel and canonicalising intermediates would only add ALU work.  Accumulator flavours: WideAcc (the default: the UNFOLDED 64-bit dot
+// products of the last multiplication are added into 96-bit sums, no fold per product), RegAcc (64-bit sums of folded products, re-folded
+// every 4th pair; HB_SC_ACC3=0) and SmemAcc (the same in a thread-private shared-memory column, an experiment that freed registers for a
+// third resident CTA and was slower; HB_SC_SACC=1).
 template <int NC> struct RegAcc {
     F a[NC];
     __device__ __forceinline__ void init() {
@@ -153,7 +155,8 @@ __device__ __forceinline__ F ld_stream(const F *p) { ulonglong2 v; asm volatile(
 #define HB_SC_LD(p) (*(p))
 #endif
 // (A variant that kept the next iterations' table entries in flight with cp.async into thread-private shared-memory slots was measured
-// and was 4 % slower: with both integer pipes ~60 % busy the kernel is not waiting on HBM, see profiles/r02_summary.md.)
+// and was 4 % slower; what did pay is the register ping-pong below — the next pair's entries loaded into a second register set —
+// which took long_scoreboard from 1.62 to 0.09 stall cycles per issue, see profiles/r02_summary.md section 0.)
 template <int NT, int MODE, bool INTERLEAVED>
 __global__ void __launch_bounds__(HB_SC_THREADS, HB_SC_MINB)
 sc_round_kernel(Tabs<NT> t, size_t L, F r, RedArgs ra) {
