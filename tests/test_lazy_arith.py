@@ -124,6 +124,41 @@ def test_dft8_lazy_at_the_bounds(f):
             assert g.val() == e
 
 
+@pytest.mark.parametrize("jn", [False, True])
+def test_radix4_and_radix2_passes_at_the_bounds(jn):
+    """The radix-4 / radix-2 passes of ntt_tile_lazy_kernel: x0 folded (<= p + 7), X1..X3 lazy products (<= p + 7)."""
+    rng = random.Random(7 + jn)
+    j = (0, P - 1) if jn else (0, 1)
+    edge = [0, 1, P - 1, P, P + 7]
+    for _ in range(2000):
+        x0, X1, X2, X3 = (Z(rng.choice(edge + [rng.randrange(P + 8)]), rng.choice(edge + [rng.randrange(P + 8)])) for _ in range(4))
+        a0, a1, b, c = ladd(x0, X1), lsubz(x0, X1, 2), ladd(X2, X3), lsub_j(X2, X3, 2, jn)
+        got = [lfold(ladd(a0, b)), lfold(ladd(a1, c)), lfold(lsubz(a0, b, 4)), lfold(lsubz(a1, c, 4))]
+        e0, e1, eb, ec = cadd(x0.val(), X1.val()), csub(x0.val(), X1.val()), cadd(X2.val(), X3.val()), cmul(csub(X2.val(), X3.val()), j)
+        want = [cadd(e0, eb), cadd(e1, ec), csub(e0, eb), csub(e1, ec)]
+        for g, e in zip(got, want):
+            assert g.re <= P + 7 and g.im <= P + 7 and g.val() == e
+        u, v = x0, X1                                                                    # radix-2: s[p0] = u + v, s[p1] = u - v
+        assert lfold(ladd(u, v)).val() == cadd(u.val(), v.val()) and lfold(lsubz(u, v, 2)).val() == csub(u.val(), v.val())
+
+
+def test_first_pass_operands_stay_folded():
+    """Stages 1-4 in registers (zero-extended rows): canonical inputs through lmul_j (p - limb) and lmul_w8 must be valid butterfly inputs."""
+    rng = random.Random(9)
+    for f in range(4):
+        jn = (f & 1) != ((f >> 1) & 1)
+        sr, si = (-1 if f & 1 else 1), (-1 if f & 2 else 1)
+        w8 = ((sr << 30) % P, (si << 30) % P)
+        j = cmul(w8, w8)
+        for _ in range(500):
+            x = Z(rng.choice([0, 1, P - 1, rng.randrange(P)]), rng.choice([0, 1, P - 1, rng.randrange(P)]))
+            mj = Z(x.im, P - x.re) if jn else Z(P - x.im, x.re)                           # lmul_j of a canonical value: limbs in [0, p]
+            assert mj.re <= P and mj.im <= P and mj.val() == cmul(x.val(), j)
+            for y in (x, mj):
+                r = lmul_w8(y, f)
+                assert r.re <= B0 and r.im <= B0 and r.val() == cmul(y.val(), w8)
+
+
 def test_lrot30_any_64_bit_value():
     rng = random.Random(1)
     for x in [0, 1, P, P + 1, M64, M64 - 1, 1 << 63, (1 << 31) - 1, 1 << 31] + [rng.getrandbits(64) for _ in range(2000)]:
