@@ -213,3 +213,28 @@ def test_acc_mac4_partial_sums_fit_64_bits():
         for x, wt in zip(xs, ws):
             v = w((x >> 32) * wt + v)
         assert (ua + ub + (v << 32)) % P == sum(x * wt for x, wt in zip(xs, ws)) % P
+
+
+def test_row_accumulators_reduced_once():
+    """encode.cu acc_reduce: U + V 2^32 (two 96-bit accumulators) assembled as one 128-bit number and reduced once by red128, whose upper half
+    must stay below 2^58 — true for any in-degree below 2^29 (hb_expander_set rejects larger ones)."""
+    M32 = (1 << 32) - 1
+
+    def red128(lo, hi):
+        assert hi < (1 << 58)
+        t = w(w((hi << 3) & M64 | (lo >> 61)) + (lo & P))
+        assert t == (hi << 3) + (lo >> 61) + (lo & P)
+        f = (t & P) + (t >> 61)
+        return f - P if f >= P else f
+
+    rng = random.Random(5)
+    for _ in range(20000):
+        terms = rng.choice([1, 4, 64, 4096, 1 << 20, (1 << 29) - 1])
+        U = rng.choice([terms * M64 >> 0, rng.randrange(terms << 64)]) % (1 << 96)      # <= terms low-half sums of < 2^64 each
+        V = rng.choice([terms * ((1 << 61) - 1), rng.randrange(terms << 61)]) % (1 << 96)  # <= terms high-half sums of < 2^61 each
+        u, v = [U & M32, (U >> 32) & M32, U >> 64], [V & M32, (V >> 32) & M32, V >> 64]
+        t = u[1] + v[0]; s1, c = t & M32, t >> 32
+        t = u[2] + v[1] + c; s2, c = t & M32, t >> 32
+        s3 = v[2] + c
+        assert s3 <= M32
+        assert red128((s1 << 32) | u[0], (s3 << 32) | s2) == (U + (V << 32)) % P
